@@ -1,0 +1,642 @@
+// oracle/ref_harness.cpp - extern "C" driver around the REFERENCE's own CPU classes.
+//
+// TEST INFRASTRUCTURE ONLY.  Compiled by oracle/build_ref.sh together with the reference
+// sources (where they lie under /root/reference) into oracle/_ref/libthunder_ref.so.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load that library.  Nothing here is product code and nothing here re-implements the
+// reference's arithmetic: every numeric result comes out of a reference function
+// (Projector::project, translate, CTF, logDataVSPrior_*, Reconstructor::insertP/insertDir/
+// prepareTF, Particle::*, rotate3D).  The two "loop" entry points at the bottom reproduce
+// only the *driver loops* of Optimiser::expectation (reference src/Optimiser.cpp:1162-1660)
+// and Optimiser::reconstructRef (src/Optimiser.cpp:7036-7241), because the Optimiser object
+// itself cannot run without >=3 MPI ranks, a .thu database and MRC stacks.
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <map>
+#include <omp.h>
+#include <pthread.h>
+
+#define private public
+#define protected public
+#include "Projector.h"
+#include "Reconstructor.h"
+#include "Particle.h"
+#include "Optimiser.h"
+#undef private
+#undef protected
+
+#include "CTF.h"
+#include "FFT.h"
+#include "ImageFunctions.h"
+#include "Euler.h"
+#include "Random.h"
+
+INITIALIZE_EASYLOGGINGPP
+
+// Free functions defined in the reference's src/Optimiser.cpp and forward-declared only there
+// (src/Optimiser.cpp:13-22); re-declared so the harness links against the reference objects.
+RFLOAT logDataVSPrior_m_huabin(const Complex* dat, const Complex* pri, const RFLOAT* ctf,
+                               const RFLOAT* sigRcp, const int m);
+RFLOAT logDataVSPrior_m_huabin_SIMD256(Complex* dat, const Complex* pri, const RFLOAT* ctf,
+                                       const RFLOAT* sigRcp, const int m);
+RFLOAT* logDataVSPrior_m_n_huabin(const Complex* dat, const Complex* pri, const RFLOAT* ctf,
+                                  const RFLOAT* sigRcp, const int n, const int m, RFLOAT* result);
+RFLOAT* logDataVSPrior_m_n_huabin_SIMD256(Complex* dat, const Complex* pri, const RFLOAT* ctf,
+                                          const RFLOAT* sigRcp, const int n, const int m, RFLOAT* result);
+
+// ------------------------------------------------------------------------------------------
+// Deterministic replacement for the reference's src/Functions/Random.cpp (urandom-seeded,
+// :51-100).  Same engine type (gsl_rng_mt19937), one engine per thread, seed = base + tid.
+// ------------------------------------------------------------------------------------------
+static unsigned long g_seed_base = 20240229UL;
+static unsigned long g_seed_epoch = 1;
+struct TlsRng { gsl_rng* eng; unsigned long epoch; };
+static __thread TlsRng t_rng = {NULL, 0};
+
+gsl_rng* get_random_engine()
+{
+    if (!t_rng.eng) t_rng.eng = gsl_rng_alloc(gsl_rng_mt19937);
+    if (t_rng.epoch != g_seed_epoch)
+    {
+        gsl_rng_set(t_rng.eng, g_seed_base + (unsigned long)omp_get_thread_num());
+        t_rng.epoch = g_seed_epoch;
+    }
+    return t_rng.eng;
+}
+
+static void quiet_loggers()
+{
+    el::Configurations conf;
+    conf.setToDefault();
+    conf.set(el::Level::All, el::ConfigurationType::ToFile, "false");
+    conf.set(el::Level::All, el::ConfigurationType::ToStandardOutput, "false");
+    conf.set(el::Level::All, el::ConfigurationType::Enabled, "false");
+    conf.set(el::Level::Fatal, el::ConfigurationType::Enabled, "true");
+    conf.set(el::Level::Fatal, el::ConfigurationType::ToStandardOutput, "true");
+    el::Loggers::setDefaultConfigurations(conf, true);
+    const char* names[] = {"LOGGER_SYS", "LOGGER_INIT", "LOGGER_ROUND", "LOGGER_COMPARE", "LOGGER_RECO",
+                           "LOGGER_MPI", "LOGGER_FFT", "LOGGER_GPU", "LOGGER_MEM", "LOGGER"};
+    for (size_t i = 0; i < sizeof(names) / sizeof(*names); ++i) el::Loggers::getLogger(names[i]);
+    el::Loggers::reconfigureAllLoggers(conf);
+}
+
+static inline dmat33 mat_from_colmajor(const double* m)
+{
+    dmat33 r;
+    for (int c = 0; c < 3; c++)
+        for (int rr = 0; rr < 3; rr++) r(rr, c) = m[c * 3 + rr];
+    return r;
+}
+
+struct RefProjector
+{
+    Projector proj;
+};
+
+struct RefReco
+{
+    Reconstructor reco;
+    std::vector<int> iCol, iRow, iPxl, iSig;
+};
+
+extern "C" {
+
+int ref_init(int nThreadFFTW)
+{
+    static bool done = false;
+    if (!done)
+    {
+        quiet_loggers();
+        TSFFTW_init_threads();
+        done = true;
+    }
+    (void)nThreadFFTW;
+    return 0;
+}
+
+void ref_set_seed(unsigned long seed)
+{
+    g_seed_base = seed;
+    g_seed_epoch++;
+}
+
+int ref_sizeof_rfloat() { return (int)sizeof(RFLOAT); }
+
+// ---------------------------------------------------------------- pixel list
+// Optimiser::allocPreCalIdx (reference src/Optimiser.cpp:7991-8041), run on a minimal
+// Optimiser object (one empty N x N Fourier image, rank 1 of 3 so that IF_MASTER is false).
+int ref_alloc_precal_idx(int N, int pf, float rU, float rL, int* iCol, int* iRow, int* iPxl, int* iSig,
+                         int* iColPad, int* iRowPad)
+{
+    Optimiser* opt = new Optimiser();
+    opt->setMPIEnv(3, 1, MPI_COMM_SELF, MPI_COMM_SELF);
+    opt->_para.pf = pf;
+    opt->_para.size = N;
+    opt->_imgOri.push_back(Image(N, N, FT_SPACE));
+    opt->allocPreCalIdx(rU, rL);
+    int n = opt->_nPxl;
+    if (iCol) memcpy(iCol, opt->_iCol, n * sizeof(int));
+    if (iRow) memcpy(iRow, opt->_iRow, n * sizeof(int));
+    if (iPxl) memcpy(iPxl, opt->_iPxl, n * sizeof(int));
+    if (iSig) memcpy(iSig, opt->_iSig, n * sizeof(int));
+    if (iColPad) memcpy(iColPad, opt->_iColPad, n * sizeof(int));
+    if (iRowPad) memcpy(iRowPad, opt->_iRowPad, n * sizeof(int));
+    opt->freePreCalIdx();
+    // The Optimiser destructor touches members that were never initialised in this minimal
+    // object; leak the (small) shell instead of running it.
+    opt->_imgOri.clear();
+    return n;
+}
+
+// ---------------------------------------------------------------- geometry / small helpers
+void ref_rotate3D(const double* quat, double* mat9_colmajor)
+{
+    dmat33 m;
+    rotate3D(m, dvec4(quat[0], quat[1], quat[2], quat[3]));
+    memcpy(mat9_colmajor, m.data(), 9 * sizeof(double));
+}
+
+void ref_translate(float* dst, float tx, float ty, int N, const int* iCol, const int* iRow, int nPxl)
+{
+    translate((Complex*)dst, tx, ty, N, N, iCol, iRow, nPxl, 1);
+}
+
+void ref_translate_src(float* dst, const float* src, float tx, float ty, int N, const int* iCol,
+                       const int* iRow, int nPxl)
+{
+    translate((Complex*)dst, (const Complex*)src, tx, ty, N, N, iCol, iRow, nPxl, 1);
+}
+
+void ref_ctf(float* dst, float pixelSize, float voltage, float defocusU, float defocusV, float theta, float Cs,
+             float amplitudeContrast, float phaseShift, int N, const int* iCol, const int* iRow, int nPxl)
+{
+    CTF(dst, pixelSize, voltage, defocusU, defocusV, theta, Cs, amplitudeContrast, phaseShift, N, N, iCol, iRow,
+        nPxl, 1);
+}
+
+// variant 0: scalar (src/Optimiser.cpp:9187-9213); 1: AVX256 (:9410-9471, default build)
+float ref_logDataVSPrior(const float* dat, const float* pri, const float* ctf, const float* sigRcp, int m,
+                         int variant)
+{
+    if (variant == 0)
+        return logDataVSPrior_m_huabin((const Complex*)dat, (const Complex*)pri, ctf, sigRcp, m);
+    return logDataVSPrior_m_huabin_SIMD256((Complex*)dat, (const Complex*)pri, ctf, sigRcp, m);
+}
+
+// pixel-major, n images against one template (src/Optimiser.cpp:9931-9973 / :9222-9306)
+void ref_logDataVSPrior_m_n(const float* dat, const float* pri, const float* ctf, const float* sigRcp, int n,
+                            int m, float* result, int variant)
+{
+    if (variant == 0)
+        logDataVSPrior_m_n_huabin((const Complex*)dat, (const Complex*)pri, ctf, sigRcp, n, m, result);
+    else
+        logDataVSPrior_m_n_huabin_SIMD256((Complex*)dat, (const Complex*)pri, ctf, sigRcp, n, m, result);
+}
+
+// ---------------------------------------------------------------- Projector
+void* ref_projector_create(int pf)
+{
+    RefProjector* p = new RefProjector();
+    p->proj.setMode(MODE_3D);
+    p->proj.setInterp(LINEAR_INTERP);
+    p->proj.setPf(pf);
+    return p;
+}
+
+void ref_projector_destroy(void* h) { delete (RefProjector*)h; }
+
+// real-space N^3 volume -> FFT -> Projector::setProjectee (pad, grid correction, FFT;
+// reference src/Projector.cpp:123-148)
+void ref_projector_set_from_real(void* h, const float* volRL, int N, int nThread)
+{
+    RefProjector* p = (RefProjector*)h;
+    Volume v(N, N, N, RL_SPACE);
+    for (size_t i = 0; i < v.sizeRL(); i++) v(i) = volRL[i];
+    FFT fft;
+    fft.fw(v, nThread);
+    v.clearRL();
+    p->proj.setProjectee(v.copyVolume(), nThread);
+}
+
+// load an already padded half-complex Fourier volume (pfN/2+1) x pfN x pfN verbatim
+void ref_projector_set_padded_ft(void* h, const float* volFT, int pfN)
+{
+    RefProjector* p = (RefProjector*)h;
+    p->proj._projectee3D.alloc(pfN, pfN, pfN, FT_SPACE);
+    memcpy(&p->proj._projectee3D[0], volFT, p->proj._projectee3D.sizeFT() * sizeof(Complex));
+    p->proj._maxRadius = pfN / p->proj._pf / 2 - 1;
+}
+
+int ref_projector_padded_dim(void* h) { return (int)((RefProjector*)h)->proj._projectee3D.nSlcFT(); }
+
+void ref_projector_get_padded_ft(void* h, float* out)
+{
+    RefProjector* p = (RefProjector*)h;
+    memcpy(out, &p->proj._projectee3D[0], p->proj._projectee3D.sizeFT() * sizeof(Complex));
+}
+
+void ref_projector_set_max_radius(void* h, int r) { ((RefProjector*)h)->proj.setMaxRadius(r); }
+
+// Projector::project(Complex*, const dmat33&, iCol, iRow, nPxl, nThread), src/Projector.cpp:356-374
+void ref_projector_project(void* h, float* dst, const double* mat9_colmajor, const int* iCol, const int* iRow,
+                           int nPxl)
+{
+    RefProjector* p = (RefProjector*)h;
+    p->proj.project((Complex*)dst, mat_from_colmajor(mat9_colmajor), iCol, iRow, nPxl, 1);
+}
+
+// ---------------------------------------------------------------- Reconstructor
+void* ref_reco_create(int size, int N, int pf, int nThread)
+{
+    RefReco* r = new RefReco();
+    r->reco.setMPIEnv(3, 1, MPI_COMM_SELF, MPI_COMM_SELF);
+    r->reco.init(MODE_3D, size, N, pf, NULL, 1.9, 15);
+    r->reco.allocSpace(nThread);
+    return r;
+}
+
+void ref_reco_destroy(void* h)
+{
+    RefReco* r = (RefReco*)h;
+    r->reco.freeSpace();
+    delete r;
+}
+
+void ref_reco_reset(void* h, int nThread) { ((RefReco*)h)->reco.reset(nThread); }
+
+void ref_reco_set_precal(void* h, int nPxl, const int* iColPad, const int* iRowPad, const int* iPxl,
+                         const int* iSig)
+{
+    RefReco* r = (RefReco*)h;
+    r->iCol.assign(iColPad, iColPad + nPxl);
+    r->iRow.assign(iRowPad, iRowPad + nPxl);
+    r->iPxl.assign(iPxl, iPxl + nPxl);
+    r->iSig.assign(iSig, iSig + nPxl);
+    r->reco.setPreCal(nPxl, r->iCol.data(), r->iRow.data(), r->iPxl.data(), r->iSig.data());
+}
+
+// Reconstructor::insertP(const Complex*, const RFLOAT*, const dmat33&, RFLOAT, NULL)
+// src/Reconstructor.cpp:782-863
+void ref_reco_insertP(void* h, const float* src, const float* ctf, const double* mat9_colmajor, float w)
+{
+    ((RefReco*)h)->reco.insertP((const Complex*)src, ctf, mat_from_colmajor(mat9_colmajor), w, NULL);
+}
+
+void ref_reco_insertDir(void* h, double ox, double oy, double oz) { ((RefReco*)h)->reco.insertDir(ox, oy, oz); }
+
+int ref_reco_pad_size(void* h) { return (int)((RefReco*)h)->reco._F3D.nSlcFT(); }
+
+// F as complex64 half-volume, T as the real part of the reference's complex T volume
+void ref_reco_get(void* h, float* F, float* T, double* O3, int* counter)
+{
+    RefReco* r = (RefReco*)h;
+    size_t n = r->reco._F3D.sizeFT();
+    if (F) memcpy(F, &r->reco._F3D[0], n * sizeof(Complex));
+    if (T)
+        for (size_t i = 0; i < n; i++) T[i] = REAL(r->reco._T3D[i]);
+    if (O3)
+    {
+        O3[0] = r->reco._ox;
+        O3[1] = r->reco._oy;
+        O3[2] = r->reco._oz;
+    }
+    if (counter) *counter = r->reco._counter;
+}
+
+// Reconstructor::prepareTF (src/Reconstructor.cpp:1056-1091): allreduce (identity at one rank),
+// normalise by 1/Re T[0], symmetrise (C1: identity)
+void ref_reco_prepareTF(void* h, int nThread) { ((RefReco*)h)->reco.prepareTF(nThread); }
+
+// ---------------------------------------------------------------- Particle (reference class, as is)
+void* ref_particle_create(int nC, int nR, int nT, int nD, double transS, double transQ)
+{
+    return new Particle(MODE_3D, nC, nR, nT, nD, transS, transQ, NULL);
+}
+void ref_particle_destroy(void* h) { delete (Particle*)h; }
+
+void ref_particle_load(void* h, int nR, int nT, int nD, const double* q, double k1, double k2, double k3,
+                       const double* t, double s0, double s1, double d, double s, double score)
+{
+    ((Particle*)h)->load(nR, nT, nD, dvec4(q[0], q[1], q[2], q[3]), k1, k2, k3, dvec2(t[0], t[1]), s0, s1, d, s,
+                         score);
+}
+
+void ref_particle_get_counts(void* h, int* n4)
+{
+    Particle* p = (Particle*)h;
+    n4[0] = p->nC(); n4[1] = p->nR(); n4[2] = p->nT(); n4[3] = p->nD();
+}
+
+// state <-> flat arrays: r[nR][4], t[nT][2], d[nD], wC,wR,wT,wD, uC,uR,uT,uD ; c[nC] as int
+void ref_particle_get(void* h, int* c, double* r, double* t, double* d, double* wC, double* wR, double* wT,
+                      double* wD, double* uC, double* uR, double* uT, double* uD)
+{
+    Particle* p = (Particle*)h;
+    for (int i = 0; i < p->_nC; i++) { if (c) c[i] = (int)p->_c(i); if (wC) wC[i] = p->_wC(i); if (uC) uC[i] = p->_uC(i); }
+    for (int i = 0; i < p->_nR; i++)
+    {
+        if (r) for (int j = 0; j < 4; j++) r[i * 4 + j] = p->_r(i, j);
+        if (wR) wR[i] = p->_wR(i);
+        if (uR) uR[i] = p->_uR(i);
+    }
+    for (int i = 0; i < p->_nT; i++)
+    {
+        if (t) { t[i * 2] = p->_t(i, 0); t[i * 2 + 1] = p->_t(i, 1); }
+        if (wT) wT[i] = p->_wT(i);
+        if (uT) uT[i] = p->_uT(i);
+    }
+    for (int i = 0; i < p->_nD; i++) { if (d) d[i] = p->_d(i); if (wD) wD[i] = p->_wD(i); if (uD) uD[i] = p->_uD(i); }
+}
+
+void ref_particle_set(void* h, const int* c, const double* r, const double* t, const double* d, const double* wC,
+                      const double* wR, const double* wT, const double* wD)
+{
+    Particle* p = (Particle*)h;
+    for (int i = 0; i < p->_nC; i++) { if (c) p->_c(i) = c[i]; if (wC) p->_wC(i) = wC[i]; }
+    for (int i = 0; i < p->_nR; i++)
+    {
+        if (r) for (int j = 0; j < 4; j++) p->_r(i, j) = r[i * 4 + j];
+        if (wR) p->_wR(i) = wR[i];
+    }
+    for (int i = 0; i < p->_nT; i++)
+    {
+        if (t) { p->_t(i, 0) = t[i * 2]; p->_t(i, 1) = t[i * 2 + 1]; }
+        if (wT) p->_wT(i) = wT[i];
+    }
+    for (int i = 0; i < p->_nD; i++) { if (d) p->_d(i) = d[i]; if (wD) p->_wD(i) = wD[i]; }
+}
+
+// scalars: k1,k2,k3,s0,s1,rho,s,score, topR[4], topT[2], topD, peakFactor C,R,T,D  (19 doubles)
+void ref_particle_get_scalars(void* h, double* out)
+{
+    Particle* p = (Particle*)h;
+    out[0] = p->_k1; out[1] = p->_k2; out[2] = p->_k3; out[3] = p->_s0; out[4] = p->_s1; out[5] = p->_rho;
+    out[6] = p->_s; out[7] = p->_score;
+    for (int j = 0; j < 4; j++) out[8 + j] = p->_topR(j);
+    out[12] = p->_topT(0); out[13] = p->_topT(1); out[14] = p->_topD;
+    out[15] = p->_peakFactorC; out[16] = p->_peakFactorR; out[17] = p->_peakFactorT; out[18] = p->_peakFactorD;
+}
+void ref_particle_set_scalars(void* h, const double* in)
+{
+    Particle* p = (Particle*)h;
+    p->_k1 = in[0]; p->_k2 = in[1]; p->_k3 = in[2]; p->_s0 = in[3]; p->_s1 = in[4]; p->_rho = in[5];
+    p->_s = in[6]; p->_score = in[7];
+    for (int j = 0; j < 4; j++) p->_topR(j) = in[8 + j];
+    p->_topT(0) = in[12]; p->_topT(1) = in[13]; p->_topD = in[14];
+    p->_peakFactorC = in[15]; p->_peakFactorR = in[16]; p->_peakFactorT = in[17]; p->_peakFactorD = in[18];
+}
+
+void ref_particle_set_u(void* h, int which /*0 C,1 R,2 T,3 D*/, const double* u, int n)
+{
+    Particle* p = (Particle*)h;
+    for (int i = 0; i < n; i++)
+    {
+        if (which == 0) p->setUC(u[i], i);
+        else if (which == 1) p->setUR(u[i], i);
+        else if (which == 2) p->setUT(u[i], i);
+        else p->setUD(u[i], i);
+    }
+}
+
+void ref_particle_perturb(void* h, double pf, int pt) { ((Particle*)h)->perturb(pf, (ParticleType)pt); }
+void ref_particle_resample(void* h, int n, int pt) { ((Particle*)h)->resample(n, (ParticleType)pt); }
+void ref_particle_calVari(void* h, int pt) { ((Particle*)h)->calVari((ParticleType)pt); }
+void ref_particle_calRank1st(void* h, int pt) { ((Particle*)h)->calRank1st((ParticleType)pt); }
+void ref_particle_keepHalfHeightPeak(void* h, int pt) { ((Particle*)h)->keepHalfHeightPeak((ParticleType)pt); }
+void ref_particle_setPeakFactor(void* h, int pt) { ((Particle*)h)->setPeakFactor((ParticleType)pt); }
+void ref_particle_resetPeakFactor(void* h) { ((Particle*)h)->resetPeakFactor(); }
+void ref_particle_normW(void* h) { ((Particle*)h)->normW(); }
+void ref_particle_shuffle(void* h, int pt) { ((Particle*)h)->shuffle((ParticleType)pt); }
+void ref_particle_balanceWeight(void* h, int pt) { ((Particle*)h)->balanceWeight((ParticleType)pt); }
+void ref_particle_calScore(void* h) { ((Particle*)h)->calScore(); }
+double ref_particle_compressR(void* h) { return ((Particle*)h)->compressR(); }
+double ref_particle_compressT(void* h) { return ((Particle*)h)->compressT(); }
+double ref_particle_variR(void* h) { return ((Particle*)h)->variR(); }
+double ref_particle_variT(void* h) { return ((Particle*)h)->variT(); }
+double ref_particle_variD(void* h) { return ((Particle*)h)->variD(); }
+void ref_particle_rand(void* h, int* cls, double* quat, double* tran, double* d)
+{
+    size_t c; dvec4 q; dvec2 t; double dd;
+    ((Particle*)h)->rand(c, q, t, dd);
+    *cls = (int)c; for (int j = 0; j < 4; j++) quat[j] = q(j);
+    tran[0] = t(0); tran[1] = t(1); *d = dd;
+}
+void ref_particle_rank1st(void* h, int* cls, double* quat, double* tran, double* d)
+{
+    size_t c; dvec4 q; dvec2 t; double dd;
+    ((Particle*)h)->rank1st(c, q, t, dd);
+    *cls = (int)c; for (int j = 0; j < 4; j++) quat[j] = q(j);
+    tran[0] = t(0); tran[1] = t(1); *d = dd;
+}
+
+// ------------------------------------------------------------------------------------------
+// Driver loop 1: the particle-filter phase loop of Optimiser::expectation
+// (reference src/Optimiser.cpp:1162-1660) for SEARCH_TYPE_LOCAL, MODE_3D, k = 1, no CTF search,
+// default Config.h switches (OPTIMISER_PEAK_FACTOR_R/T on, OPTIMISER_COMPRESS_CRITERIA on).
+//
+//   pars        nImg Particle handles (state is advanced in place)
+//   datP,ctfP,sigRcpP   image-major packed arrays [nImg][nPxl]
+//   minPhase/maxPhase   MIN_N_PHASE_PER_ITER_LOCAL / MAX_N_PHASE_PER_ITER; fixedPhases > 0 runs
+//                       exactly that many phases (benchmark mode, stop rule disabled)
+//   nPhaseOut   phases actually run per image
+//   dvpOut      optional [nImg][mLR*mLT] log-likelihoods of the LAST phase run (for parity)
+// ------------------------------------------------------------------------------------------
+void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP, const float* ctfP,
+                           const float* sigRcpP, const int* iCol, const int* iRow, int nPxl, int N, int mLR,
+                           int mLT, double perturbFactorL, double perturbFactorS, int minPhase, int maxPhase,
+                           int noDecreaseLimit, double decreaseFactor, int fixedPhases, int simd,
+                           int nThread, int* nPhaseOut, float* dvpOut)
+{
+    RefProjector* P = (RefProjector*)projH;
+    if (nThread <= 0) nThread = omp_get_max_threads();
+
+    Complex* poolPriRotP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    Complex* poolPriAllP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    Complex* poolTraP = (Complex*)TSFFTW_malloc((size_t)mLT * nPxl * nThread * sizeof(Complex));
+
+    #pragma omp parallel for schedule(dynamic) num_threads(nThread)
+    for (int l = 0; l < nImg; l++)
+    {
+        Particle& par = *(Particle*)pars[l];
+        Complex* priRotP = poolPriRotP + (size_t)nPxl * omp_get_thread_num();
+        Complex* priAllP = poolPriAllP + (size_t)nPxl * omp_get_thread_num();
+        Complex* traP = poolTraP + (size_t)mLT * nPxl * omp_get_thread_num();
+        Complex* dat = (Complex*)datP + (size_t)l * nPxl;
+        const RFLOAT* ctf = ctfP + (size_t)l * nPxl;
+        const RFLOAT* sigRcp = sigRcpP + (size_t)l * nPxl;
+
+        int nPhaseWithNoVariDecrease = 0;
+        double variR = DBL_MAX, variT = DBL_MAX, variD = DBL_MAX;
+        int phasesRun = 0;
+        int phaseMax = fixedPhases > 0 ? fixedPhases : maxPhase;
+
+        for (int phase = 0; phase < phaseMax; phase++)
+        {
+            if (phase == 0)
+            {
+                par.perturb(perturbFactorL, PAR_R);
+                par.perturb(perturbFactorL, PAR_T);
+            }
+            else
+            {
+                par.perturb(perturbFactorS, PAR_R);
+                par.perturb(perturbFactorS, PAR_T);
+            }
+
+            RFLOAT baseLine = GSL_NAN;
+            vec wC = vec::Zero(1);
+            vec wR = vec::Zero(mLR);
+            vec wT = vec::Zero(mLT);
+            vec wD = vec::Zero(1);
+
+            dmat33 rot3D;
+            dvec2 t;
+
+            FOR_EACH_C(par)
+            {
+                FOR_EACH_T(par)
+                {
+                    par.t(t, iT);
+                    translate(traP + (size_t)iT * nPxl, t(0), t(1), N, N, iCol, iRow, nPxl, 1);
+                }
+
+                FOR_EACH_R(par)
+                {
+                    par.rot(rot3D, iR);
+                    P->proj.project(priRotP, rot3D, iCol, iRow, nPxl, 1);
+
+                    FOR_EACH_T(par)
+                    {
+                        for (int i = 0; i < nPxl; i++) priAllP[i] = traP[(size_t)nPxl * iT + i] * priRotP[i];
+
+                        FOR_EACH_D(par)
+                        {
+                            RFLOAT w = simd ? logDataVSPrior_m_huabin_SIMD256(dat, priAllP, ctf, sigRcp, nPxl)
+                                            : logDataVSPrior_m_huabin(dat, priAllP, ctf, sigRcp, nPxl);
+
+                            if (dvpOut && (fixedPhases <= 0 || phase == phaseMax - 1))
+                                dvpOut[(size_t)l * mLR * mLT + (size_t)iR * mLT + iT] = w;
+
+                            baseLine = TSGSL_isnan(baseLine) ? w : baseLine;
+                            if (w > baseLine)
+                            {
+                                RFLOAT nf = exp(baseLine - w);
+                                wC *= nf; wR *= nf; wT *= nf; wD *= nf;
+                                baseLine = w;
+                            }
+                            RFLOAT s = exp(w - baseLine);
+                            wC(iC) += s * (par.wR(iR) * par.wT(iT) * par.wD(iD));
+                            wR(iR) += s * (par.wC(iC) * par.wT(iT) * par.wD(iD));
+                            wT(iT) += s * (par.wC(iC) * par.wR(iR) * par.wD(iD));
+                            wD(iD) += s * (par.wC(iC) * par.wR(iR) * par.wT(iT));
+                        }
+                    }
+                }
+            }
+
+            par.setUC(wC(0), 0);
+            for (int iR = 0; iR < mLR; iR++) par.setUR(wR(iR), iR);
+            par.keepHalfHeightPeak(PAR_R);
+            for (int iT = 0; iT < mLT; iT++) par.setUT(wT(iT), iT);
+            par.keepHalfHeightPeak(PAR_T);
+
+            par.calRank1st(PAR_R);
+            par.calRank1st(PAR_T);
+            par.calVari(PAR_R);
+            par.calVari(PAR_T);
+            par.resample(mLR, PAR_R);
+            par.resample(mLT, PAR_T);
+
+            phasesRun = phase + 1;
+
+            if (fixedPhases <= 0 && phase >= minPhase)
+            {
+                double variRCur = par.variR();
+                double variTCur = par.variT();
+                double variDCur = par.variD();
+
+                if ((variRCur < variR * decreaseFactor) || (variTCur < variT * decreaseFactor) ||
+                    (variDCur < variD * decreaseFactor))
+                    nPhaseWithNoVariDecrease = 0;
+                else
+                    nPhaseWithNoVariDecrease += 1;
+
+                if (variRCur < variR) variR = variRCur;
+                if (variTCur < variT) variT = variTCur;
+                if (variDCur < variD) variD = variDCur;
+
+                if (nPhaseWithNoVariDecrease == noDecreaseLimit) break;
+            }
+        }
+        if (nPhaseOut) nPhaseOut[l] = phasesRun;
+    }
+
+    TSFFTW_free(poolPriRotP);
+    TSFFTW_free(poolPriAllP);
+    TSFFTW_free(poolTraP);
+}
+
+// ------------------------------------------------------------------------------------------
+// Driver loop 2: the insert loop of Optimiser::reconstructRef (reference
+// src/Optimiser.cpp:7036-7241), MODE_3D, k = 1, no CTF search, OPTIMISER_RECENTRE_IMAGE_EACH_ITERATION.
+// Draws come either from Particle::rand (pars != NULL) or from explicit arrays
+// nr[nImg][mReco][4], nt[nImg][mReco][2] (the layout the reference GPU seam uses, :6993-7013).
+// ------------------------------------------------------------------------------------------
+void ref_insert_loop(void* recoH, void** pars, int nImg, const float* datP, const float* ctfP,
+                     const float* wImg, const double* offS, const double* nr, const double* nt,
+                     const int* iCol, const int* iRow, int nPxl, int N, int mReco, int nThread)
+{
+    RefReco* R = (RefReco*)recoH;
+    if (nThread <= 0) nThread = omp_get_max_threads();
+    Complex* poolTransImgP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+
+    #pragma omp parallel for num_threads(nThread)
+    for (int l = 0; l < nImg; l++)
+    {
+        RFLOAT w = wImg ? wImg[l] : (RFLOAT)1;
+        if (!wImg) w /= mReco;   // reference: w = 1 (or compressR) then w /= mReco; wImg is already divided
+
+        Complex* transImgP = poolTransImgP + (size_t)nPxl * omp_get_thread_num();
+        const Complex* orignImgP = (const Complex*)datP + (size_t)nPxl * l;
+        dvec2 offset(offS ? offS[2 * l] : 0, offS ? offS[2 * l + 1] : 0);
+
+        for (int m = 0; m < mReco; m++)
+        {
+            size_t cls;
+            dvec4 quat;
+            dvec2 tran;
+            double d;
+
+            if (pars)
+                ((Particle*)pars[l])->rand(cls, quat, tran, d);
+            else
+            {
+                const double* q = nr + ((size_t)l * mReco + m) * 4;
+                const double* t = nt + ((size_t)l * mReco + m) * 2;
+                quat = dvec4(q[0], q[1], q[2], q[3]);
+                tran = dvec2(t[0], t[1]);
+            }
+
+            dmat33 rot3D;
+            rotate3D(rot3D, quat);
+
+            translate(transImgP, orignImgP, -(tran - offset)(0), -(tran - offset)(1), N, N, iCol, iRow, nPxl, 1);
+
+            R->reco.insertP(transImgP, ctfP + (size_t)nPxl * l, rot3D, w, NULL);
+
+            dvec3 dir = -rot3D * dvec3((tran - offset)[0], (tran - offset)[1], 0);
+            R->reco.insertDir(dir);
+        }
+    }
+    TSFFTW_free(poolTransImgP);
+}
+
+}  // extern "C"
