@@ -1,0 +1,35 @@
+# Build libthunder_b200.so (sm_100a only) and the C oracle.  `python -c "import __graft_entry__ as g; g.build()"`
+# runs the same commands.
+NVCC      ?= nvcc
+CXX       := g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp -Xptxas -v
+CSRC      := thunder_b200/csrc
+OUT       := thunder_b200/lib/libthunder_b200.so
+OBJS      := build/thb_api.o build/thb_pf.o build/thb_comm.o
+HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h include/*.h)
+
+all: $(OUT) oracle
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Iinclude -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+build/thb_comm.o: $(CSRC)/thb_comm.cpp $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Iinclude -x cu -c $< -o $@ 2> build/thb_comm.ptxas.log || (cat build/thb_comm.ptxas.log; false)
+
+$(OUT): $(OBJS)
+	@mkdir -p thunder_b200/lib
+	$(NVCC) $(ARCH) -shared -Xcompiler -fPIC -o $@ $(OBJS) -Xlinker --no-as-needed -lgomp -ldl
+
+oracle: oracle/_port/libthb_oracle.so
+
+oracle/_port/libthb_oracle.so: oracle/thb_oracle.c
+	@mkdir -p oracle/_port
+	gcc -O2 -fPIC -shared -std=gnu99 -o $@ $< -lm
+
+clean:
+	rm -rf build $(OUT) oracle/_port
+
+.PHONY: all oracle clean

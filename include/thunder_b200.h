@@ -1,0 +1,187 @@
+/*
+ * thunder_b200.h - C ABI of the B200-native Optimiser hot path for THUNDER.
+ *
+ * One shared library (libthunder_b200.so), one opaque context per GPU / per process.
+ * Plain pointers and sizes only: no THUNDER, Eigen, MPI or torch types.  Every entry point
+ * returns 0 on success and a negative THB_E_* code on failure (thb_last_error() gives the
+ * message); nothing in here ever calls exit()/abort(), unlike the seam it replaces
+ * (reference gpu/config/Device.cuh.in:27-61).
+ *
+ * The entry points are what a binding of the reference's GPU seam for this path needs.
+ * Reference interface each one replaces (paths relative to the THUNDER tree):
+ *
+ *   thb_pixel_list            Optimiser::allocPreCalIdx              src/Optimiser.cpp:7991-8041
+ *                             (+ ExpectPreidx                        gpu/interface/Interface.h:18)
+ *   thb_set_expect_pixels     ExpectPreidx / ExpectPrefre            gpu/interface/Interface.h:18-29
+ *   thb_set_insert_pixels     Reconstructor::setPreCal               src/Reconstructor.cpp (setPreCal), InsertFT args iCol/iRow
+ *   thb_set_volume            ExpectLocalV3D / ManagedArrayTexture   gpu/interface/Interface.h:31-164
+ *                             (Projector::projectee3D(), src/Projector.cpp:123-148)
+ *   thb_upload_stack          ExpectLocalP / the datP,ctfP,sigRcpP   src/Optimiser.cpp:8043-8171 (allocPreCal)
+ *                             arguments of ExpectGlobal3D, InsertFT
+ *   thb_project               Projector::project(Complex*,...)       src/Projector.cpp:356-374
+ *   thb_expect_local          ExpectLocalRTD + ExpectLocalPreI3D +   gpu/interface/Interface.h:31-164
+ *                             ExpectLocalM (one call, many images)   (CPU loop: src/Optimiser.cpp:1162-1402)
+ *   thb_expect_scan           ExpectRotran + ExpectProject +         gpu/interface/Interface.h:199-221
+ *                             ExpectGlobal3D                         (CPU loop: src/Optimiser.cpp:633-914)
+ *   thb_reco_alloc/reset      Reconstructor::allocSpace / reset      src/Reconstructor.cpp:92-143
+ *   thb_insert                InsertFT                               gpu/interface/Interface.h:267-318
+ *                             (CPU loop: src/Optimiser.cpp:7036-7241; insertP src/Reconstructor.cpp:782-863;
+ *                              insertDir :407-422)
+ *   thb_comm_* / thb_allreduce Reconstructor::allReduceF/T/O         src/Reconstructor.cpp:2350-2520
+ *                             (NCCL twin: gpu/src/cuthunder.cu:5294-5324, 5903-5985)
+ *   thb_reco_download         the F3D/T3D/O3D/counter out-arguments  gpu/interface/Interface.cpp:581-619
+ *                             of InsertFT, + prepareTF normalisation src/Reconstructor.cpp:1056-1091, 2458-2483
+ *   thb_pf_* / thb_expectation Particle::perturb/resample/calVari/.. src/Particle.cpp:1004-1478, 1964-2002, 2309-2495
+ *                             + the phase loop of                    src/Optimiser.cpp:1162-1660
+ *   thb_reconstruct_insert    the insert loop of reconstructRef      src/Optimiser.cpp:7036-7241
+ *
+ * Data conventions (identical to the reference seam):
+ *   complex = float[2] (re, im); packed image arrays are image-major [img][nPxl];
+ *   Fourier volumes are FFTW r2c half-complex, x fastest, (vdim/2+1) x vdim x vdim,
+ *   origin at index 0, negative y/z stored at +vdim; quaternions double[4] (w,x,y,z);
+ *   translations double[2] in pixels; all host pointers are caller-owned.
+ */
+#ifndef THUNDER_B200_H
+#define THUNDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct thb_ctx thb_ctx;
+
+enum {
+    THB_OK = 0,
+    THB_E_ARG = -1,      /* invalid argument / call order */
+    THB_E_CUDA = -2,     /* CUDA runtime error (message in thb_last_error) */
+    THB_E_NOGPU = -3,    /* no usable sm_100 device: the product path refuses to run */
+    THB_E_NCCL = -4,     /* NCCL missing or failed */
+    THB_E_STATE = -5     /* object not initialised (volume / stack / pixels missing) */
+};
+
+/* stack kinds for thb_upload_stack */
+enum { THB_STACK_EXPECT = 0 /* masked images, E pixel set */, THB_STACK_INSERT = 1 /* unmasked, M pixel set */ };
+
+#define THB_UNIQUE_ID_BYTES 128
+
+/* ---------------------------------------------------------------- library / context */
+int thb_version(void);
+int thb_device_count(void);                       /* CUDA devices visible; 0 if none */
+int thb_create(thb_ctx** out, int device);        /* fails with THB_E_NOGPU without an sm_100 GPU */
+void thb_destroy(thb_ctx* ctx);
+const char* thb_last_error(const thb_ctx* ctx);   /* ctx may be NULL: last error of thb_create */
+int thb_synchronize(thb_ctx* ctx);
+/* counters for bench.py: kernels launched by this library since the last reset */
+int64_t thb_launch_count(thb_ctx* ctx, int reset);
+/* CUDA-event time (ms) accumulated per kernel family since the last reset:
+ * which = 0 expect, 1 insert, 2 particle filter, 3 pack/unpack, 4 allreduce ; launches returned in *n */
+double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset);
+int thb_enable_timing(thb_ctx* ctx, int on);
+
+/* ---------------------------------------------------------------- a1: pixel list (host integer math) */
+/* Returns nPxl (>= 0) or a negative error.  Any output pointer may be NULL.  Arrays must hold
+ * (N/2+1)*N ints.  Order and rounding follow the reference loop exactly. */
+int thb_pixel_list(int N, int pf, float rU, float rL, int* iCol, int* iRow, int* iPxl, int* iSig,
+                   int* iColPad, int* iRowPad);
+
+/* ---------------------------------------------------------------- geometry of the problem */
+/* E pixel set: unpadded iCol/iRow (the library multiplies by pf, as Projector::project does). */
+int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol, const int* iRow);
+/* M pixel set: padded iColPad/iRowPad (already multiplied by pf, as Reconstructor::insertP expects)
+ * and N (image size, for the translation phase ramp). */
+int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iColPad, const int* iRowPad);
+
+/* Projector volume for slot (class x half-set), half-complex (vdim/2+1) x vdim x vdim complex64. */
+int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim);
+int thb_get_volume(thb_ctx* ctx, int slot, float* volFT);      /* round trip of the device layout */
+
+/* Resident packed stack, image-major [nImg][nPxl].  sigRcp may be NULL for THB_STACK_INSERT.
+ * slotOfImg[nImg] (may be NULL = all 0) says which volume slot / accumulator each image uses. */
+int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf,
+                     const float* sigRcp, const int* slotOfImg);
+
+/* ---------------------------------------------------------------- a4/a5: slice extraction */
+/* dst[nRot][nPxl] complex64 (host) = Projector::project for each rotation (quat[nRot][4]) */
+int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst);
+
+/* ---------------------------------------------------------------- a3-a8: fused E kernel, local-search shape */
+/* For each of nAct images (imgIdx into the THB_STACK_EXPECT stack): nR rotations x nT translations.
+ *   quat[nAct][nR][4], tran[nAct][nT][2], wR[nAct][nR], wT[nAct][nT]   (prior weights, double)
+ * outputs (host, any may be NULL):
+ *   uR[nAct][nR], uT[nAct][nT], uC[nAct]   marginal weights relative to the per-image maximum
+ *   base[nAct]                             the maximum log-likelihood (the "baseline")
+ *   logL[nAct][nR][nT]                     raw log-likelihoods                                        */
+int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, const double* quat,
+                     const double* tran, const double* wR, const double* wT, float* uR, float* uT,
+                     float* uC, float* base, float* logL);
+
+/* ---------------------------------------------------------------- a7: global scan shape */
+/* One shared set of nR rotations x nT translations against every image of the E stack that uses
+ * `slot`.  pR[nR], pT[nT] prior weights.  Outputs (host): wC[nImg], wR[nImg][nR], wT[nImg][nT],
+ * base[nImg]; logL[nImg][nR][nT] optional. Images of other slots get zeros. */
+int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, const double* tran,
+                    const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base,
+                    float* logL);
+
+/* ---------------------------------------------------------------- a11-a14: fused M kernel */
+int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad);   /* accumulators F,T: (vdimPad/2+1) x vdimPad^2 */
+int thb_reco_reset(thb_ctx* ctx, int slot);
+/* Insert nImg images of the THB_STACK_INSERT stack (imgIdx may be NULL = 0..nImg-1):
+ *   w[nImg] (already divided by mReco), offS[nImg][2] (may be NULL = 0),
+ *   nr[nImg][mReco][4] quaternions, nt[nImg][mReco][2] translations.
+ * Each image goes to the accumulator of its slot. */
+int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
+               const double* nr, const double* nt);
+/* F[(vdimPad/2+1)*vdimPad^2][2], T[...] real part, O[3], counter.  normalise != 0 applies
+ * sf = 1/T[0] to T and F (RECONSTRUCTOR_NORMALISE_T_F). Any pointer may be NULL. */
+int thb_reco_download(thb_ctx* ctx, int slot, float* F, float* T, double* O, int* counter, int normalise);
+
+/* ---------------------------------------------------------------- a15: half-map allreduce */
+int thb_comm_unique_id(char id[THB_UNIQUE_ID_BYTES]);
+int thb_comm_init(thb_ctx* ctx, int nRanks, int rank, const char id[THB_UNIQUE_ID_BYTES]);
+/* One sum-allreduce of every allocated accumulator (F|T interleaved, all slots) + O, counter. */
+int thb_allreduce(thb_ctx* ctx);
+
+/* ---------------------------------------------------------------- a9: device-resident particle filter */
+typedef struct thb_pf_params {
+    int mLR, mLT;               /* support sizes (rotation, translation) */
+    double transS, transQ;      /* translation prior sigma and the re-centre quantile */
+    double perturbFactorL, perturbFactorS;
+    int minPhase, maxPhase;     /* MIN_N_PHASE_PER_ITER_LOCAL, MAX_N_PHASE_PER_ITER */
+    int fixedPhases;            /* > 0: run exactly this many phases (benchmark mode) */
+    double decreaseFactor;      /* PARTICLE_FILTER_DECREASE_FACTOR */
+    int noDecreaseLimit;        /* N_PHASE_WITH_NO_VARI_DECREASE */
+    uint64_t seed;
+} thb_pf_params;
+
+/* Initialise nPar particles from (quat[nPar][4], k1,k2,k3[nPar], tran[nPar][2], s0,s1[nPar]) -
+ * Particle::load semantics (src/Particle.cpp:401-556): ACG cloud about quat, Gaussian cloud about tran. */
+int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* quat, const double* k123,
+                const double* tran, const double* s01);
+/* Read back particle state.  Any pointer may be NULL.
+ *   r[nPar][mLR][4], t[nPar][mLT][2], wR[nPar][mLR], wT[nPar][mLT],
+ *   scal[nPar][16] = k1,k2,k3,s0,s1,rho,topR[4],topT[2],score,nPhase,variR,variT */
+int thb_pf_get(thb_ctx* ctx, double* r, double* t, double* wR, double* wT, double* scal);
+int thb_pf_set(thb_ctx* ctx, const double* r, const double* t, const double* wR, const double* wT,
+               const double* scal);
+/* E-step of one iteration over all loaded particles (particle p <-> image p of the E stack):
+ * phase loop of Optimiser::expectation with the particle filter on the device. */
+int thb_expectation(thb_ctx* ctx, int* nPhaseOut /* [nPar] or NULL */);
+/* M-step insert loop of reconstructRef: mReco uniform draws per particle from its support
+ * (Particle::rand), w = 1/mReco (or compressR/mReco when parGra != 0). */
+int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* offS);
+
+/* single particle-filter operators on the device state, for parity tests against Particle::* */
+int thb_pf_op(thb_ctx* ctx, int op, double arg, const float* uR, const float* uT);
+enum {
+    THB_PF_PERTURB_R = 1, THB_PF_PERTURB_T = 2, THB_PF_SET_U_KEEP_PEAK = 3, THB_PF_RANK1ST = 4,
+    THB_PF_CALVARI = 5, THB_PF_RESAMPLE = 6, THB_PF_BALANCE_R = 7, THB_PF_BALANCE_T = 8
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THUNDER_B200_H */

@@ -38,6 +38,7 @@
 #include "ImageFunctions.h"
 #include "Euler.h"
 #include "Random.h"
+#include "DirectionalStat.h"
 
 INITIALIZE_EASYLOGGINGPP
 
@@ -437,6 +438,38 @@ void ref_particle_rank1st(void* h, int* cls, double* quat, double* tran, double*
     tran[0] = t(0); tran[1] = t(1); *d = dd;
 }
 
+// ---------------------------------------------------------------- DirectionalStat (free functions)
+// inferACG(dmat44&, const dmat4&) (src/Geometry/DirectionalStat.cpp:93-145) + the derived
+// k1,k2,k3 (:184-222) and mean (:224-250); pdfACG (:19-24)
+void ref_inferACG(const double* r, int n, double* A16_rowmajor, double* k123, double* mean4)
+{
+    dmat4 src(n, 4);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 4; j++) src(i, j) = r[i * 4 + j];
+    if (A16_rowmajor)
+    {
+        dmat44 A;
+        inferACG(A, src);
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) A16_rowmajor[i * 4 + j] = A(i, j);
+    }
+    if (k123) inferACG(k123[0], k123[1], k123[2], src);
+    if (mean4)
+    {
+        dvec4 m;
+        inferACG(m, src);
+        for (int j = 0; j < 4; j++) mean4[j] = m(j);
+    }
+}
+
+double ref_pdfACG(const double* x4, const double* A16_rowmajor)
+{
+    dmat44 A;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) A(i, j) = A16_rowmajor[i * 4 + j];
+    return pdfACG(dvec4(x4[0], x4[1], x4[2], x4[3]), A);
+}
+
 // ------------------------------------------------------------------------------------------
 // Driver loop 1: the particle-filter phase loop of Optimiser::expectation
 // (reference src/Optimiser.cpp:1162-1660) for SEARCH_TYPE_LOCAL, MODE_3D, k = 1, no CTF search,
@@ -546,7 +579,7 @@ void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP
             for (int iR = 0; iR < mLR; iR++) par.setUR(wR(iR), iR);
             par.keepHalfHeightPeak(PAR_R);
             for (int iT = 0; iT < mLT; iT++) par.setUT(wT(iT), iT);
-            par.keepHalfHeightPeak(PAR_T);
+            // OPTIMISER_PEAK_FACTOR_T is off in the reference's Config.h:218 -> no keepHalfHeightPeak(PAR_T)
 
             par.calRank1st(PAR_R);
             par.calRank1st(PAR_T);

@@ -1,0 +1,292 @@
+"""ctypes wrapper of oracle/_ref/libthunder_ref.so - the REFERENCE's own CPU classes.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs, never by thunder_b200/.  The library is built by
+oracle/build_ref.sh from the sources under /root/reference; every number it returns is
+computed by reference code (see oracle/ref_harness.cpp).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "_ref" / "libthunder_ref.so"
+
+_p, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
+_lib = None
+
+
+def available() -> bool:
+    return LIB.exists()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            raise RuntimeError(f"{LIB} missing: run oracle/build_ref.sh where /root/reference exists")
+        L = C.CDLL(os.fspath(LIB))
+        L.ref_init.argtypes = [_i]
+        L.ref_set_seed.argtypes = [C.c_ulong]
+        L.ref_alloc_precal_idx.restype = _i
+        L.ref_alloc_precal_idx.argtypes = [_i, _i, _f, _f] + [_p] * 6
+        L.ref_rotate3D.argtypes = [_p, _p]
+        L.ref_translate.argtypes = [_p, _f, _f, _i, _p, _p, _i]
+        L.ref_translate_src.argtypes = [_p, _p, _f, _f, _i, _p, _p, _i]
+        L.ref_ctf.argtypes = [_p] + [_f] * 8 + [_i, _p, _p, _i]
+        L.ref_logDataVSPrior.restype = _f
+        L.ref_logDataVSPrior.argtypes = [_p, _p, _p, _p, _i, _i]
+        L.ref_logDataVSPrior_m_n.argtypes = [_p, _p, _p, _p, _i, _i, _p, _i]
+        L.ref_projector_create.restype = _p
+        L.ref_projector_create.argtypes = [_i]
+        L.ref_projector_destroy.argtypes = [_p]
+        L.ref_projector_set_from_real.argtypes = [_p, _p, _i, _i]
+        L.ref_projector_set_padded_ft.argtypes = [_p, _p, _i]
+        L.ref_projector_padded_dim.restype = _i
+        L.ref_projector_padded_dim.argtypes = [_p]
+        L.ref_projector_get_padded_ft.argtypes = [_p, _p]
+        L.ref_projector_set_max_radius.argtypes = [_p, _i]
+        L.ref_projector_project.argtypes = [_p, _p, _p, _p, _p, _i]
+        L.ref_reco_create.restype = _p
+        L.ref_reco_create.argtypes = [_i, _i, _i, _i]
+        L.ref_reco_destroy.argtypes = [_p]
+        L.ref_reco_reset.argtypes = [_p, _i]
+        L.ref_reco_set_precal.argtypes = [_p, _i, _p, _p, _p, _p]
+        L.ref_reco_insertP.argtypes = [_p, _p, _p, _p, _f]
+        L.ref_reco_insertDir.argtypes = [_p, _d, _d, _d]
+        L.ref_reco_pad_size.restype = _i
+        L.ref_reco_pad_size.argtypes = [_p]
+        L.ref_reco_get.argtypes = [_p, _p, _p, _p, _p]
+        L.ref_reco_prepareTF.argtypes = [_p, _i]
+        L.ref_particle_create.restype = _p
+        L.ref_particle_create.argtypes = [_i, _i, _i, _i, _d, _d]
+        L.ref_particle_destroy.argtypes = [_p]
+        L.ref_particle_load.argtypes = [_p, _i, _i, _i, _p, _d, _d, _d, _p, _d, _d, _d, _d, _d]
+        L.ref_particle_get_counts.argtypes = [_p, _p]
+        L.ref_particle_get.argtypes = [_p] * 13
+        L.ref_particle_set.argtypes = [_p] * 9
+        L.ref_particle_get_scalars.argtypes = [_p, _p]
+        L.ref_particle_set_scalars.argtypes = [_p, _p]
+        L.ref_particle_set_u.argtypes = [_p, _i, _p, _i]
+        for name in ("perturb",):
+            getattr(L, "ref_particle_" + name).argtypes = [_p, _d, _i]
+        L.ref_particle_resample.argtypes = [_p, _i, _i]
+        for name in ("calVari", "calRank1st", "keepHalfHeightPeak", "setPeakFactor", "shuffle", "balanceWeight"):
+            getattr(L, "ref_particle_" + name).argtypes = [_p, _i]
+        for name in ("resetPeakFactor", "normW", "calScore"):
+            getattr(L, "ref_particle_" + name).argtypes = [_p]
+        for name in ("compressR", "compressT", "variR", "variT", "variD"):
+            getattr(L, "ref_particle_" + name).restype = _d
+            getattr(L, "ref_particle_" + name).argtypes = [_p]
+        L.ref_particle_rand.argtypes = [_p] * 5
+        L.ref_particle_rank1st.argtypes = [_p] * 5
+        L.ref_expectation_local.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _i, _d, _i,
+                                            _i, _i, _p, _p]
+        L.ref_insert_loop.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i]
+        if hasattr(L, "ref_inferACG"):
+            L.ref_inferACG.argtypes = [_p, _i, _p, _p, _p]
+            L.ref_pdfACG.restype = _d
+            L.ref_pdfACG.argtypes = [_p, _p]
+        L.ref_init(1)
+        _lib = L
+    return _lib
+
+
+# ---------------------------------------------------------------------------------------------
+def pixel_list(N, pf, rU, rL):
+    cap = (N // 2 + 1) * N
+    names = ("iCol", "iRow", "iPxl", "iSig", "iColPad", "iRowPad")
+    b = {k: np.empty(cap, np.int32) for k in names}
+    n = lib().ref_alloc_precal_idx(N, pf, rU, rL, *[_ptr(b[k]) for k in names])
+    return {k: v[:n].copy() for k, v in b.items()}
+
+
+def rotate3D(quat):
+    q = np.ascontiguousarray(quat, np.float64)
+    m = np.empty(9, np.float64)
+    lib().ref_rotate3D(_ptr(q), _ptr(m))
+    return m  # column-major
+
+
+def translate(tx, ty, N, iCol, iRow, src=None):
+    n = len(iCol)
+    out = np.empty(n, np.complex64)
+    if src is None:
+        lib().ref_translate(_ptr(out), tx, ty, N, _ptr(iCol), _ptr(iRow), n)
+    else:
+        src = np.ascontiguousarray(src, np.complex64)
+        lib().ref_translate_src(_ptr(out), _ptr(src), tx, ty, N, _ptr(iCol), _ptr(iRow), n)
+    return out
+
+
+def ctf(pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, iCol, iRow):
+    n = len(iCol)
+    out = np.empty(n, np.float32)
+    lib().ref_ctf(_ptr(out), pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, _ptr(iCol), _ptr(iRow), n)
+    return out
+
+
+def logDataVSPrior(dat, pri, ctf_, sigRcp, variant=1):
+    dat = np.ascontiguousarray(dat, np.complex64); pri = np.ascontiguousarray(pri, np.complex64)
+    ctf_ = np.ascontiguousarray(ctf_, np.float32); sigRcp = np.ascontiguousarray(sigRcp, np.float32)
+    return float(lib().ref_logDataVSPrior(_ptr(dat), _ptr(pri), _ptr(ctf_), _ptr(sigRcp), len(ctf_), variant))
+
+
+def logDataVSPrior_m_n(datPM, pri, ctfPM, sigPM, n, m, variant=1):
+    """pixel-major arrays [m][n]; returns result[n] (the reference accumulates into a caller-zeroed array)"""
+    out = np.zeros(n, np.float32)
+    lib().ref_logDataVSPrior_m_n(_ptr(datPM), _ptr(pri), _ptr(ctfPM), _ptr(sigPM), n, m, _ptr(out), variant)
+    return out
+
+
+class Projector:
+    def __init__(self, pf=2):
+        self.h = lib().ref_projector_create(pf)
+        self.pf = pf
+
+    def close(self):
+        if self.h:
+            lib().ref_projector_destroy(self.h)
+            self.h = None
+
+    def set_from_real(self, vol, nThread=1):
+        vol = np.ascontiguousarray(vol, np.float32)
+        lib().ref_projector_set_from_real(self.h, _ptr(vol), vol.shape[0], nThread)
+
+    def set_padded_ft(self, volFT):
+        v = np.ascontiguousarray(volFT, np.complex64)
+        lib().ref_projector_set_padded_ft(self.h, _ptr(v), v.shape[0])
+
+    def padded_ft(self):
+        n = lib().ref_projector_padded_dim(self.h)
+        out = np.empty((n, n, n // 2 + 1), np.complex64)
+        lib().ref_projector_get_padded_ft(self.h, _ptr(out))
+        return out
+
+    def project(self, mat9, iCol, iRow):
+        out = np.empty(len(iCol), np.complex64)
+        m = np.ascontiguousarray(mat9, np.float64)
+        lib().ref_projector_project(self.h, _ptr(out), _ptr(m), _ptr(iCol), _ptr(iRow), len(iCol))
+        return out
+
+
+class Reconstructor:
+    def __init__(self, size, N, pf=2, nThread=1):
+        self.h = lib().ref_reco_create(size, N, pf, nThread)
+        self.nThread = nThread
+
+    def close(self):
+        if self.h:
+            lib().ref_reco_destroy(self.h)
+            self.h = None
+
+    def set_precal(self, iColPad, iRowPad, iPxl, iSig):
+        lib().ref_reco_set_precal(self.h, len(iColPad), _ptr(iColPad), _ptr(iRowPad), _ptr(iPxl), _ptr(iSig))
+
+    def insertP(self, src, ctf_, mat9, w):
+        src = np.ascontiguousarray(src, np.complex64); ctf_ = np.ascontiguousarray(ctf_, np.float32)
+        m = np.ascontiguousarray(mat9, np.float64)
+        lib().ref_reco_insertP(self.h, _ptr(src), _ptr(ctf_), _ptr(m), w)
+
+    def insertDir(self, o):
+        lib().ref_reco_insertDir(self.h, float(o[0]), float(o[1]), float(o[2]))
+
+    def pad_size(self):
+        return lib().ref_reco_pad_size(self.h)
+
+    def get(self):
+        m = self.pad_size()
+        F = np.empty((m, m, m // 2 + 1), np.complex64); T = np.empty((m, m, m // 2 + 1), np.float32)
+        O = np.empty(3); cnt = np.zeros(1, np.int32)
+        lib().ref_reco_get(self.h, _ptr(F), _ptr(T), _ptr(O), _ptr(cnt))
+        return dict(F=F, T=T, O=O, counter=int(cnt[0]))
+
+    def prepareTF(self):
+        lib().ref_reco_prepareTF(self.h, self.nThread)
+
+    def insert_loop(self, dat, ctf_, w, offS, nr, nt, iCol, iRow, N, nThread=1, pars=None):
+        dat = np.ascontiguousarray(dat, np.complex64); ctf_ = np.ascontiguousarray(ctf_, np.float32)
+        nImg, P = dat.shape
+        w = None if w is None else np.ascontiguousarray(w, np.float32)
+        offS = None if offS is None else np.ascontiguousarray(offS, np.float64)
+        if pars is None:
+            nr = np.ascontiguousarray(nr, np.float64); nt = np.ascontiguousarray(nt, np.float64)
+            mReco = nr.shape[1]
+            parr = None
+        else:
+            mReco = int(nr)
+            parr = (_p * nImg)(*[p.h for p in pars])
+            nr = nt = None
+        lib().ref_insert_loop(self.h, parr, nImg, _ptr(dat), _ptr(ctf_), _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt),
+                              _ptr(iCol), _ptr(iRow), P, N, mReco, nThread)
+
+
+class Particle:
+    PAR_C, PAR_R, PAR_T, PAR_D = 0, 1, 2, 3
+
+    def __init__(self, nR, nT, transS=2.0, transQ=0.01):
+        self.h = lib().ref_particle_create(1, nR, nT, 1, transS, transQ)
+
+    def close(self):
+        if self.h:
+            lib().ref_particle_destroy(self.h)
+            self.h = None
+
+    def load(self, nR, nT, q, k1, k2, k3, t, s0, s1, d=1.0, s=0.0, score=1.0):
+        q = np.ascontiguousarray(q, np.float64); t = np.ascontiguousarray(t, np.float64)
+        lib().ref_particle_load(self.h, nR, nT, 1, _ptr(q), k1, k2, k3, _ptr(t), s0, s1, d, s, score)
+
+    def counts(self):
+        n = np.zeros(4, np.int32)
+        lib().ref_particle_get_counts(self.h, _ptr(n))
+        return n
+
+    def get(self):
+        nC, nR, nT, nD = self.counts()
+        r = np.empty((nR, 4)); t = np.empty((nT, 2)); wR = np.empty(nR); wT = np.empty(nT); uR = np.empty(nR); uT = np.empty(nT)
+        lib().ref_particle_get(self.h, None, _ptr(r), _ptr(t), None, None, _ptr(wR), _ptr(wT), None, None, _ptr(uR), _ptr(uT), None)
+        return dict(r=r, t=t, wR=wR, wT=wT, uR=uR, uT=uT)
+
+    def set(self, r=None, t=None, wR=None, wT=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        r, t, wR, wT = f(r), f(t), f(wR), f(wT)
+        lib().ref_particle_set(self.h, None, _ptr(r), _ptr(t), None, None, _ptr(wR), _ptr(wT), None)
+
+    def scalars(self):
+        out = np.empty(19)
+        lib().ref_particle_get_scalars(self.h, _ptr(out))
+        return out
+
+    def set_scalars(self, s):
+        s = np.ascontiguousarray(s, np.float64)
+        lib().ref_particle_set_scalars(self.h, _ptr(s))
+
+    def set_u(self, which, u):
+        u = np.ascontiguousarray(u, np.float64)
+        lib().ref_particle_set_u(self.h, which, _ptr(u), len(u))
+
+    def __getattr__(self, name):
+        fn = getattr(lib(), "ref_particle_" + name)
+        return lambda *a: fn(self.h, *a)
+
+
+def expectation_local(pars, proj, datP, ctfP, sigRcpP, iCol, iRow, N, mLR, mLT, pfL=2.0, pfS=0.5, minPhase=3, maxPhase=100,
+                      noDecreaseLimit=1, decreaseFactor=0.95, fixedPhases=0, simd=1, nThread=1, want_dvp=False):
+    datP = np.ascontiguousarray(datP, np.complex64)
+    nImg, P = datP.shape
+    ctfP = np.ascontiguousarray(ctfP, np.float32); sigRcpP = np.ascontiguousarray(sigRcpP, np.float32)
+    parr = (_p * nImg)(*[p.h for p in pars])
+    nPhase = np.zeros(nImg, np.int32)
+    dvp = np.zeros((nImg, mLR, mLT), np.float32) if want_dvp else None
+    lib().ref_expectation_local(parr, nImg, proj.h, _ptr(datP), _ptr(ctfP), _ptr(sigRcpP), _ptr(iCol), _ptr(iRow), P, N, mLR,
+                                mLT, pfL, pfS, minPhase, maxPhase, noDecreaseLimit, decreaseFactor, fixedPhases, simd,
+                                nThread, _ptr(nPhase), _ptr(dvp))
+    return nPhase, dvp

@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA hot path, called through the C ABI, against the oracle.
+
+Oracle = the reference-built library (oracle/_ref) when present, else the pinned plain-C port, plus the
+committed golden fixture.  Tolerances (fp32 arithmetic, double coordinates):
+  * projected slice values: |d| <= 2e-6 * max|slice|  (FMA contraction vs separate mul/add)
+  * log-likelihoods: |d| <= 2e-6 * |logL| + 1e-4  (the reference's own scalar-vs-SIMD tolerance is 1e-5 rel)
+  * marginal weights uR/uT/uC: rel 2e-3 after exp() of a difference of large numbers, and
+    <= 20 * eps * |logL| in log space
+  * F / T volumes: relative L2 <= 1e-6 (only summation order differs), per-shell FSC >= 0.99999
+"""
+import numpy as np
+import pytest
+
+from thunder_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import portapi, refapi
+    return portapi, (refapi if refapi.available() else None)
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------- golden, N = 16
+def test_project_golden(ctx, golden):
+    N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.set_expect_pixels(N, pf, golden["pixE_iCol"], golden["pixE_iRow"])
+    ctx.set_volume(0, golden["volFT"])
+    assert np.array_equal(ctx.get_volume(0), golden["volFT"])
+    got = ctx.project(0, golden["quat"])
+    ref = golden["slices"]
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    # identity rotation: integer coordinates, zero fractional weights -> exact voxel values
+    assert np.array_equal(got[0], ref[0])
+
+
+def test_expect_local_golden(ctx, golden):
+    N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.set_expect_pixels(N, pf, golden["pixE_iCol"], golden["pixE_iRow"])
+    ctx.set_volume(0, golden["volFT"])
+    ctx.upload_stack(capi.STACK_EXPECT, golden["dat"][None], golden["ctf"][None], golden["sigRcp"][None])
+    nR, nT = golden["logL"].shape
+    wR = np.full((1, nR), 1.0 / nR); wT = np.full((1, nT), 1.0 / nT)
+    out = ctx.expect_local(golden["quat"][None], golden["tran"][None], wR, wT)
+    ref = golden["logL"]
+    assert np.abs(out["logL"][0] - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-4
+    assert abs(out["base"][0] - ref.max()) <= 2e-6 * abs(ref.max())
+
+
+def test_insert_golden(ctx, golden):
+    N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.set_insert_pixels(N, pf, golden["pixM_iColPad"], golden["pixM_iRowPad"])
+    ctx.upload_stack(capi.STACK_INSERT, golden["datM"], golden["ctfM"])
+    ctx.reco_alloc(0, N * pf)
+    ctx.insert(golden["w"], golden["nr"], golden["nt"], offS=golden["offS"])
+    out = ctx.reco_download(0)
+    assert out["counter"] == int(golden["counter"])
+    assert np.allclose(out["O"], golden["O"], rtol=1e-12, atol=1e-12)
+    assert _rel_l2(out["F"], golden["F"]) <= 1e-6
+    assert _rel_l2(out["T"], golden["T"]) <= 1e-6
+    outn = ctx.reco_download(0, normalise=True)       # prepareTF normalisation, sf = 1 / T[0]
+    assert _rel_l2(outn["F"], golden["Fn"]) <= 1e-6
+    assert _rel_l2(outn["T"], golden["Tn"]) <= 1e-6
+    assert abs(outn["T"].ravel()[0] - 1.0) < 1e-6
+    # reset really clears
+    ctx.reco_reset(0)
+    z = ctx.reco_download(0)
+    assert not z["F"].any() and not z["T"].any() and z["counter"] == 0 and not z["O"].any()
+
+
+# ------------------------------------------------------------------------------------------- random, larger
+@pytest.fixture(scope="module")
+def problem():
+    """N = 64 synthetic problem with two half-set volumes, built with the oracle's projector."""
+    port, ref = _oracle()
+    N, pf = 64, 2
+    rng = np.random.default_rng(77)
+    vols = [synth.padded_ft(synth.phantom(N, 12, seed=s), pf) for s in (1, 2)]
+    pixE = port.pixel_list(N, pf, 30.0, 1.0)
+    pixM = port.pixel_list(N, pf, 31.0, 0.0)
+    nImg = 6
+    slot = np.array([0, 1, 0, 1, 1, 0], np.int32)
+
+    def project_fn(quats):
+        return np.stack([port.project(vols[slot[l]], pf, port.rotate3D(q), pixE["iCol"], pixE["iRow"])
+                         for l, q in enumerate(quats)])
+    par = synth.make_particles(nImg, N, pixE, project_fn, seed=5, snr_scale=4.0)
+    # local-search clouds: nR rotations about the truth (+ a few wild ones), nT translations
+    nR, nT = 37, 9
+    quat = np.stack([synth.acg_cloud(par["quat"][l], 2e-4, nR, rng) for l in range(nImg)])
+    quat[:, -3:] = synth.random_quats(nImg * 3, rng).reshape(nImg, 3, 4)
+    quat[:, 0] = par["quat"]
+    tran = par["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
+    tran[:, 0] = par["tran"]
+    wR = rng.uniform(0.5, 1.5, (nImg, nR)); wR /= wR.sum(1, keepdims=True)
+    wT = rng.uniform(0.5, 1.5, (nImg, nT)); wT /= wT.sum(1, keepdims=True)
+    return dict(N=N, pf=pf, vols=vols, pixE=pixE, pixM=pixM, par=par, slot=slot, quat=quat, tran=tran, wR=wR, wT=wT,
+                nImg=nImg, nR=nR, nT=nT, rng=rng)
+
+
+def _setup_E(ctx, pb):
+    ctx.set_expect_pixels(pb["N"], pb["pf"], pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+    for s, v in enumerate(pb["vols"]):
+        ctx.set_volume(s, v)
+    ctx.upload_stack(capi.STACK_EXPECT, pb["par"]["dat"], pb["par"]["ctf"], pb["par"]["sigRcp"], pb["slot"])
+
+
+def test_project_random(ctx, problem):
+    pb = problem
+    port, ref = _oracle()
+    _setup_E(ctx, pb)
+    q = synth.random_quats(16, np.random.default_rng(1))
+    got = ctx.project(1, q)
+    for i in range(len(q)):
+        want = port.project(pb["vols"][1], pb["pf"], port.rotate3D(q[i]), pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+        assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_expect_local_random(ctx, problem):
+    pb = problem
+    port, ref = _oracle()
+    _setup_E(ctx, pb)
+    out = ctx.expect_local(pb["quat"], pb["tran"], pb["wR"], pb["wT"])
+    for l in range(pb["nImg"]):
+        o = port.expect_local(pb["vols"][pb["slot"][l]], pb["pf"], pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"],
+                              pb["par"]["dat"][l], pb["par"]["ctf"][l], pb["par"]["sigRcp"][l], pb["quat"][l], pb["tran"][l],
+                              pb["wR"][l], pb["wT"][l])
+        L = o["logL"]
+        assert np.abs(out["logL"][l] - L).max() <= 2e-6 * np.abs(L).max() + 1e-4
+        assert abs(out["base"][l] - o["base"]) <= 2e-6 * abs(o["base"]) + 1e-4
+        # marginals: compare against float64 weights of the ORACLE's logL shifted to our baseline
+        tol_log = 20 * np.finfo(np.float32).eps * np.abs(L).max()
+        for key, want in (("uR", o["uR"]), ("uT", o["uT"])):
+            got = out[key][l]
+            big = want > 1e-6 * want.max()
+            assert np.all(np.abs(np.log(got[big]) - np.log(want[big])) <= tol_log + 2e-3), key
+        assert abs(np.log(out["uC"][l]) - np.log(o["uC"])) <= tol_log + 2e-3
+
+
+def test_expect_local_subset_and_order(ctx, problem):
+    """imgIdx selects / permutes images; results follow the selection"""
+    pb = problem
+    _setup_E(ctx, pb)
+    full = ctx.expect_local(pb["quat"], pb["tran"], pb["wR"], pb["wT"])
+    idx = np.array([4, 1, 3], np.int32)
+    sub = ctx.expect_local(pb["quat"][idx], pb["tran"][idx], pb["wR"][idx], pb["wT"][idx], imgIdx=idx)
+    assert np.array_equal(sub["logL"], full["logL"][idx])
+    assert np.array_equal(sub["uR"], full["uR"][idx])
+
+
+def test_expect_local_ragged_shapes(ctx, problem):
+    """nT not a multiple of the register chunk (9), nR above one CTA (128), nT = 1, nR = 1"""
+    pb = problem
+    port, ref = _oracle()
+    _setup_E(ctx, pb)
+    rng = np.random.default_rng(9)
+    for nR, nT in ((1, 1), (3, 10), (130, 2), (5, 19)):
+        quat = synth.random_quats(nR, rng)[None]
+        tran = rng.normal(scale=1.5, size=(1, nT, 2))
+        wR = np.full((1, nR), 1.0 / nR); wT = np.full((1, nT), 1.0 / nT)
+        out = ctx.expect_local(quat, tran, wR, wT, imgIdx=np.array([2], np.int32))
+        o = port.expect_local(pb["vols"][pb["slot"][2]], pb["pf"], pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"],
+                              pb["par"]["dat"][2], pb["par"]["ctf"][2], pb["par"]["sigRcp"][2], quat[0], tran[0], wR[0], wT[0])
+        assert np.abs(out["logL"][0] - o["logL"]).max() <= 2e-6 * np.abs(o["logL"]).max() + 1e-4, (nR, nT)
+
+
+def test_expect_scan_matches_local(ctx, problem):
+    """global-scan shape: one shared rotation/translation set against every image of a slot"""
+    pb = problem
+    port, ref = _oracle()
+    _setup_E(ctx, pb)
+    rng = np.random.default_rng(10)
+    nR, nT = 40, 12
+    quat = synth.random_quats(nR, rng); tran = rng.normal(scale=2.0, size=(nT, 2))
+    pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
+    out = ctx.expect_scan(1, quat, tran, pR, pT, want_logL=True)
+    imgs = np.nonzero(pb["slot"] == 1)[0]
+    # pixel-major n-image likelihood of the oracle (logDataVSPrior_m_n) for a few templates
+    datPM = np.ascontiguousarray(pb["par"]["dat"][imgs].T); ctfPM = np.ascontiguousarray(pb["par"]["ctf"][imgs].T)
+    sigPM = np.ascontiguousarray(pb["par"]["sigRcp"][imgs].T)
+    for r in (0, 7, 39):
+        pri = port.project(pb["vols"][1], pb["pf"], port.rotate3D(quat[r]), pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+        for t in (0, 11):
+            tra = port.translate(np.float32(tran[t, 0]), np.float32(tran[t, 1]), pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+            want = port.logDataVSPrior_m_n(datPM, (tra * pri).astype(np.complex64), ctfPM, sigPM, len(imgs), datPM.shape[0])
+            got = out["logL"][imgs, r, t]
+            assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max() + 1e-4
+    others = np.nonzero(pb["slot"] != 1)[0]
+    assert not out["wR"][others].any() and not out["wC"][others].any()
+    for l in imgs:
+        w = np.exp(out["logL"][l].astype(np.float64) - out["base"][l])
+        assert np.allclose(out["wR"][l], (w * pT).sum(1), rtol=1e-4, atol=1e-30)
+        assert np.allclose(out["wT"][l], (w * pR[:, None]).sum(0), rtol=1e-4, atol=1e-30)
+
+
+def test_insert_random_two_halves(ctx, problem):
+    pb = problem
+    port, ref = _oracle()
+    N, pf = pb["N"], pb["pf"]
+    rng = np.random.default_rng(21)
+    PM = len(pb["pixM"]["iCol"])
+    nImg, mReco = pb["nImg"], 11
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    nr = np.stack([synth.acg_cloud(pb["par"]["quat"][l], 3e-4, mReco, rng) for l in range(nImg)])
+    nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    w = (rng.uniform(0.5, 1.0, nImg) / mReco).astype(np.float32)
+    offS = rng.normal(scale=0.5, size=(nImg, 2))
+    ctx.set_insert_pixels(N, pf, pb["pixM"]["iColPad"], pb["pixM"]["iRowPad"])
+    ctx.upload_stack(capi.STACK_INSERT, datM, ctfM, slotOfImg=pb["slot"])
+    for s in (0, 1):
+        ctx.reco_alloc(s, N * pf)
+    ctx.insert(w, nr, nt, offS=offS)
+    for s in (0, 1):
+        sel = np.nonzero(pb["slot"] == s)[0]
+        want = port.insert_loop(N * pf, pf, N, datM[sel], ctfM[sel], w[sel], offS[sel], nr[sel], nt[sel],
+                                pb["pixM"]["iCol"], pb["pixM"]["iRow"])
+        got = ctx.reco_download(s)
+        assert got["counter"] == want["counter"] == len(sel) * mReco
+        assert np.allclose(got["O"], want["O"], rtol=1e-11, atol=1e-11)
+        assert _rel_l2(got["F"], want["F"]) <= 1e-6
+        assert _rel_l2(got["T"], want["T"]) <= 1e-6
+        f = synth.fsc(got["F"], want["F"], N * pf // 2 - 2)
+        assert f[1:].min() >= 0.99999
+    # linearity: inserting the same list again doubles the accumulators (size-independent property)
+    before = ctx.reco_download(0)
+    ctx.insert(w, nr, nt, offS=offS)
+    after = ctx.reco_download(0)
+    assert _rel_l2(after["F"], 2 * before["F"]) <= 1e-6
+    assert after["counter"] == 2 * before["counter"]
+
+
+def test_reference_library_agrees(ctx, problem):
+    """where the reference-built oracle travelled to this box: Projector / Reconstructor classes directly"""
+    port, ref = _oracle()
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    pb = problem
+    _setup_E(ctx, pb)
+    P = ref.Projector(pb["pf"])
+    P.set_padded_ft(pb["vols"][0])
+    q = synth.random_quats(4, np.random.default_rng(2))
+    got = ctx.project(0, q)
+    for i in range(4):
+        want = P.project(ref.rotate3D(q[i]), pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+        assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+    P.close()
+
+
+def test_error_paths(ctx):
+    c2 = capi.Context(0)
+    with pytest.raises(capi.ThbError):
+        c2.upload_stack(capi.STACK_EXPECT, np.zeros((1, 4), np.complex64), np.zeros((1, 4), np.float32), np.zeros((1, 4), np.float32))
+    with pytest.raises(capi.ThbError):
+        c2.reco_reset(3)
+    with pytest.raises(capi.ThbError):
+        c2.set_volume(99, np.zeros((4, 4, 3), np.complex64))
+    c2.close()

@@ -1,0 +1,315 @@
+"""ctypes binding of libthunder_b200.so (the C ABI in include/thunder_b200.h).
+
+This is the host-side mirror used by tests/, bench.py and __graft_entry__: numpy arrays in,
+numpy arrays out, every call going through the C ABI.  There is no CPU implementation behind
+it: if the library or a B200 is missing, `load()` / `Context()` raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libthunder_b200.so"
+
+UNIQUE_ID_BYTES = 128
+STACK_EXPECT, STACK_INSERT = 0, 1
+KF_EXPECT, KF_INSERT, KF_PF, KF_PACK, KF_COMM = range(5)
+PF_PERTURB_R, PF_PERTURB_T, PF_SET_U_KEEP_PEAK, PF_RANK1ST, PF_CALVARI, PF_RESAMPLE, PF_BALANCE_R, PF_BALANCE_T = range(1, 9)
+
+
+class ThbError(RuntimeError):
+    pass
+
+
+class PFParams(C.Structure):
+    _fields_ = [
+        ("mLR", C.c_int), ("mLT", C.c_int),
+        ("transS", C.c_double), ("transQ", C.c_double),
+        ("perturbFactorL", C.c_double), ("perturbFactorS", C.c_double),
+        ("minPhase", C.c_int), ("maxPhase", C.c_int),
+        ("fixedPhases", C.c_int),
+        ("decreaseFactor", C.c_double),
+        ("noDecreaseLimit", C.c_int),
+        ("seed", C.c_uint64),
+    ]
+
+
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+
+
+def _sig(lib):
+    f = lib.thb_version; f.restype = _i; f.argtypes = []
+    f = lib.thb_device_count; f.restype = _i; f.argtypes = []
+    f = lib.thb_create; f.restype = _i; f.argtypes = [C.POINTER(_p), _i]
+    f = lib.thb_destroy; f.restype = None; f.argtypes = [_p]
+    f = lib.thb_last_error; f.restype = C.c_char_p; f.argtypes = [_p]
+    f = lib.thb_synchronize; f.restype = _i; f.argtypes = [_p]
+    f = lib.thb_launch_count; f.restype = C.c_int64; f.argtypes = [_p, _i]
+    f = lib.thb_kernel_ms; f.restype = C.c_double; f.argtypes = [_p, _i, C.POINTER(C.c_int64), _i]
+    f = lib.thb_enable_timing; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_pixel_list; f.restype = _i; f.argtypes = [_i, _i, C.c_float, C.c_float] + [_p] * 6
+    f = lib.thb_set_expect_pixels; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p]
+    f = lib.thb_set_insert_pixels; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p]
+    f = lib.thb_set_volume; f.restype = _i; f.argtypes = [_p, _i, _p, _i]
+    f = lib.thb_get_volume; f.restype = _i; f.argtypes = [_p, _i, _p]
+    f = lib.thb_upload_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
+    f = lib.thb_expect_local; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i] + [_p] * 9
+    f = lib.thb_expect_scan; f.restype = _i; f.argtypes = [_p, _i, _i, _i] + [_p] * 9
+    f = lib.thb_reco_alloc; f.restype = _i; f.argtypes = [_p, _i, _i]
+    f = lib.thb_reco_reset; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_insert; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p]
+    f = lib.thb_reco_download; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p, _p, _i]
+    f = lib.thb_comm_unique_id; f.restype = _i; f.argtypes = [_p]
+    f = lib.thb_comm_init; f.restype = _i; f.argtypes = [_p, _i, _i, _p]
+    f = lib.thb_allreduce; f.restype = _i; f.argtypes = [_p]
+    f = lib.thb_pf_load; f.restype = _i; f.argtypes = [_p, _i, C.POINTER(PFParams), _p, _p, _p, _p]
+    f = lib.thb_pf_get; f.restype = _i; f.argtypes = [_p] * 6
+    f = lib.thb_pf_set; f.restype = _i; f.argtypes = [_p] * 6
+    f = lib.thb_expectation; f.restype = _i; f.argtypes = [_p, _p]
+    f = lib.thb_reconstruct_insert; f.restype = _i; f.argtypes = [_p, _i, _i, _p]
+    f = lib.thb_pf_op; f.restype = _i; f.argtypes = [_p, _i, C.c_double, _p, _p]
+
+
+def load() -> C.CDLL:
+    """Load the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ThbError(f"{LIB_PATH} is missing - run `make` or __graft_entry__.build() first")
+        _lib = C.CDLL(os.fspath(LIB_PATH))
+        _sig(_lib)
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+def _arr(a, dtype, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def pixel_list(N: int, pf: int, rU: float, rL: float):
+    """Optimiser::allocPreCalIdx.  Returns dict of int32 arrays iCol,iRow,iPxl,iSig,iColPad,iRowPad."""
+    lib = load()
+    cap = (N // 2 + 1) * N
+    bufs = {k: np.empty(cap, np.int32) for k in ("iCol", "iRow", "iPxl", "iSig", "iColPad", "iRowPad")}
+    n = lib.thb_pixel_list(N, pf, rU, rL, *[_ptr(bufs[k]) for k in ("iCol", "iRow", "iPxl", "iSig", "iColPad", "iRowPad")])
+    if n < 0:
+        raise ThbError(f"thb_pixel_list failed ({n})")
+    return {k: v[:n].copy() for k, v in bufs.items()}
+
+
+def comm_unique_id() -> bytes:
+    lib = load()
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    rc = lib.thb_comm_unique_id(buf)
+    if rc:
+        raise ThbError(f"thb_comm_unique_id failed ({rc}): NCCL not available")
+    return buf.raw
+
+
+class Context:
+    """One context per GPU (thb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _p()
+        rc = self.lib.thb_create(C.byref(h), device)
+        if rc:
+            raise ThbError(f"thb_create({device}) failed ({rc}): {self.lib.thb_last_error(None).decode()}")
+        self.h = h
+        self.nPxlE = self.nPxlM = 0
+        self.nImgE = self.nImgM = 0
+        self.vdim = {}
+        self.accdim = {}
+        self.pf_params = None
+        self.nPar = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.thb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise ThbError(f"libthunder_b200 error {rc}: {self.lib.thb_last_error(self.h).decode()}")
+
+    # ---- accounting
+    def synchronize(self):
+        self._chk(self.lib.thb_synchronize(self.h))
+
+    def launch_count(self, reset=False):
+        return int(self.lib.thb_launch_count(self.h, int(reset)))
+
+    def enable_timing(self, on=True):
+        self._chk(self.lib.thb_enable_timing(self.h, int(on)))
+
+    def kernel_ms(self, which, reset=False):
+        n = C.c_int64(0)
+        ms = self.lib.thb_kernel_ms(self.h, which, C.byref(n), int(reset))
+        return float(ms), int(n.value)
+
+    # ---- geometry / resident data
+    def set_expect_pixels(self, N, pf, iCol, iRow):
+        iCol = _arr(iCol, np.int32); iRow = _arr(iRow, np.int32)
+        self._chk(self.lib.thb_set_expect_pixels(self.h, N, pf, len(iCol), _ptr(iCol), _ptr(iRow)))
+        self.nPxlE = len(iCol)
+
+    def set_insert_pixels(self, N, pf, iColPad, iRowPad):
+        a = _arr(iColPad, np.int32); b = _arr(iRowPad, np.int32)
+        self._chk(self.lib.thb_set_insert_pixels(self.h, N, pf, len(a), _ptr(a), _ptr(b)))
+        self.nPxlM = len(a)
+
+    def set_volume(self, slot, volFT):
+        """volFT: complex64 [vdim][vdim][vdim/2+1] (z, y, x) half-complex."""
+        v = np.ascontiguousarray(volFT, dtype=np.complex64)
+        vdim = v.shape[0]
+        assert v.shape == (vdim, vdim, vdim // 2 + 1), v.shape
+        self._chk(self.lib.thb_set_volume(self.h, slot, _ptr(v), vdim))
+        self.vdim[slot] = vdim
+
+    def get_volume(self, slot):
+        vdim = self.vdim[slot]
+        out = np.empty((vdim, vdim, vdim // 2 + 1), np.complex64)
+        self._chk(self.lib.thb_get_volume(self.h, slot, _ptr(out)))
+        return out
+
+    def upload_stack(self, kind, dat, ctf, sigRcp=None, slotOfImg=None):
+        dat = np.ascontiguousarray(dat, dtype=np.complex64)
+        nImg, P = dat.shape
+        ctf = _arr(ctf, np.float32, (nImg, P))
+        sigRcp = _arr(sigRcp, np.float32, (nImg, P))
+        slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
+        self._chk(self.lib.thb_upload_stack(self.h, kind, nImg, _ptr(dat), _ptr(ctf), _ptr(sigRcp), _ptr(slotOfImg)))
+        if kind == STACK_EXPECT:
+            self.nImgE = nImg
+        else:
+            self.nImgM = nImg
+
+    # ---- E
+    def project(self, slot, quat):
+        quat = _arr(quat, np.float64)
+        nRot = quat.shape[0]
+        out = np.empty((nRot, self.nPxlE), np.complex64)
+        self._chk(self.lib.thb_project(self.h, slot, nRot, _ptr(quat), _ptr(out)))
+        return out
+
+    def expect_local(self, quat, tran, wR, wT, imgIdx=None, want_logL=True):
+        quat = _arr(quat, np.float64)
+        nAct, nR, _ = quat.shape
+        tran = _arr(tran, np.float64)
+        nT = tran.shape[1]
+        wR = _arr(wR, np.float64, (nAct, nR)); wT = _arr(wT, np.float64, (nAct, nT))
+        imgIdx = _arr(imgIdx, np.int32, (nAct,))
+        uR = np.empty((nAct, nR), np.float32); uT = np.empty((nAct, nT), np.float32)
+        uC = np.empty(nAct, np.float32); base = np.empty(nAct, np.float32)
+        logL = np.empty((nAct, nR, nT), np.float32) if want_logL else None
+        self._chk(self.lib.thb_expect_local(self.h, nAct, _ptr(imgIdx), nR, nT, _ptr(quat), _ptr(tran), _ptr(wR), _ptr(wT),
+                                            _ptr(uR), _ptr(uT), _ptr(uC), _ptr(base), _ptr(logL)))
+        return dict(uR=uR, uT=uT, uC=uC, base=base, logL=logL)
+
+    def expect_scan(self, slot, quat, tran, pR, pT, want_logL=False):
+        quat = _arr(quat, np.float64); tran = _arr(tran, np.float64)
+        nR, nT = quat.shape[0], tran.shape[0]
+        pR = _arr(pR, np.float64, (nR,)); pT = _arr(pT, np.float64, (nT,))
+        n = self.nImgE
+        wC = np.empty(n, np.float32); wR = np.empty((n, nR), np.float32); wT = np.empty((n, nT), np.float32)
+        base = np.empty(n, np.float32)
+        logL = np.empty((n, nR, nT), np.float32) if want_logL else None
+        self._chk(self.lib.thb_expect_scan(self.h, slot, nR, nT, _ptr(quat), _ptr(tran), _ptr(pR), _ptr(pT),
+                                           _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base), _ptr(logL)))
+        return dict(wC=wC, wR=wR, wT=wT, base=base, logL=logL)
+
+    # ---- M
+    def reco_alloc(self, slot, vdimPad):
+        self._chk(self.lib.thb_reco_alloc(self.h, slot, vdimPad))
+        self.accdim[slot] = vdimPad
+
+    def reco_reset(self, slot):
+        self._chk(self.lib.thb_reco_reset(self.h, slot))
+
+    def insert(self, w, nr, nt, offS=None, imgIdx=None):
+        nr = _arr(nr, np.float64)
+        nImg, mReco, _ = nr.shape
+        nt = _arr(nt, np.float64, (nImg, mReco, 2))
+        w = _arr(w, np.float32, (nImg,))
+        offS = _arr(offS, np.float64, (nImg, 2))
+        imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        self._chk(self.lib.thb_insert(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt)))
+
+    def reco_download(self, slot, normalise=False, want_F=True, want_T=True):
+        m = self.accdim[slot]
+        shape = (m, m, m // 2 + 1)
+        F = np.empty(shape, np.complex64) if want_F else None
+        T = np.empty(shape, np.float32) if want_T else None
+        O = np.empty(3, np.float64)
+        cnt = np.zeros(1, np.int32)
+        self._chk(self.lib.thb_reco_download(self.h, slot, _ptr(F), _ptr(T), _ptr(O), _ptr(cnt), int(normalise)))
+        return dict(F=F, T=T, O=O, counter=int(cnt[0]))
+
+    # ---- collective
+    def comm_init(self, nRanks, rank, uid: bytes | None):
+        buf = C.create_string_buffer(uid, UNIQUE_ID_BYTES) if uid is not None else None
+        self._chk(self.lib.thb_comm_init(self.h, nRanks, rank, buf))
+
+    def allreduce(self):
+        self._chk(self.lib.thb_allreduce(self.h))
+
+    # ---- particle filter
+    def pf_load(self, params: PFParams, quat, k123, tran, s01):
+        quat = _arr(quat, np.float64)
+        nPar = quat.shape[0]
+        k123 = _arr(k123, np.float64, (nPar, 3)); tran = _arr(tran, np.float64, (nPar, 2)); s01 = _arr(s01, np.float64, (nPar, 2))
+        self._chk(self.lib.thb_pf_load(self.h, nPar, C.byref(params), _ptr(quat), _ptr(k123), _ptr(tran), _ptr(s01)))
+        self.pf_params = params
+        self.nPar = nPar
+
+    def pf_get(self):
+        n, R, T = self.nPar, self.pf_params.mLR, self.pf_params.mLT
+        r = np.empty((n, R, 4)); t = np.empty((n, T, 2)); wR = np.empty((n, R)); wT = np.empty((n, T)); scal = np.empty((n, 16))
+        self._chk(self.lib.thb_pf_get(self.h, _ptr(r), _ptr(t), _ptr(wR), _ptr(wT), _ptr(scal)))
+        return dict(r=r, t=t, wR=wR, wT=wT, scal=scal)
+
+    def pf_get_scal(self):
+        scal = np.empty((self.nPar, 16))
+        self._chk(self.lib.thb_pf_get(self.h, None, None, None, None, _ptr(scal)))
+        return scal
+
+    def pf_set(self, r=None, t=None, wR=None, wT=None, scal=None):
+        n, R, T = self.nPar, self.pf_params.mLR, self.pf_params.mLT
+        r = _arr(r, np.float64, (n, R, 4)); t = _arr(t, np.float64, (n, T, 2))
+        wR = _arr(wR, np.float64, (n, R)); wT = _arr(wT, np.float64, (n, T)); scal = _arr(scal, np.float64, (n, 16))
+        self._chk(self.lib.thb_pf_set(self.h, _ptr(r), _ptr(t), _ptr(wR), _ptr(wT), _ptr(scal)))
+
+    def expectation(self, want_phases=False):
+        ph = np.zeros(self.nPar, np.int32) if want_phases else None
+        self._chk(self.lib.thb_expectation(self.h, _ptr(ph)))
+        return ph
+
+    def reconstruct_insert(self, mReco, parGra=False, offS=None):
+        offS = _arr(offS, np.float64, (self.nPar, 2))
+        self._chk(self.lib.thb_reconstruct_insert(self.h, mReco, int(parGra), _ptr(offS)))
+
+    def pf_op(self, op, arg=0.0, uR=None, uT=None):
+        uR = _arr(uR, np.float32); uT = _arr(uT, np.float32)
+        self._chk(self.lib.thb_pf_op(self.h, op, float(arg), _ptr(uR), _ptr(uT)))

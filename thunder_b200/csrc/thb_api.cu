@@ -1,0 +1,675 @@
+// thb_api.cu - C ABI entry points: context, geometry, resident data, E / M launches.
+// See include/thunder_b200.h for the reference interface each entry point replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include "thb_context.h"
+#include "thb_kernels.cuh"
+
+static thread_local std::string g_create_error;
+
+namespace thb {
+
+int set_error(thb_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+int cuda_fail(thb_ctx* ctx, cudaError_t e, const char* what)
+{
+    return set_error(ctx, THB_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+void* scratch(thb_ctx* ctx, int which, size_t bytes)
+{
+    if (ctx->scratchCap[which] >= bytes && ctx->scratch[which]) return ctx->scratch[which];
+    if (ctx->scratch[which]) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->scratch[which]);
+        ctx->scratch[which] = nullptr;
+        ctx->scratchCap[which] = 0;
+    }
+    size_t cap = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&ctx->scratch[which], cap);
+    if (e != cudaSuccess) {
+        cuda_fail(ctx, e, "cudaMalloc(scratch)");
+        return nullptr;
+    }
+    ctx->scratchCap[which] = cap;
+    return ctx->scratch[which];
+}
+
+void span_begin(thb_ctx* ctx, int family)
+{
+    if (!ctx->timing) return;
+    TimedSpan s;
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+    s.family = family;
+    cudaEventRecord(s.a, ctx->stream);
+    ctx->spans.push_back(s);
+}
+
+void span_end(thb_ctx* ctx)
+{
+    if (!ctx->timing || ctx->spans.empty()) return;
+    cudaEventRecord(ctx->spans.back().b, ctx->stream);
+}
+
+void resolve_spans(thb_ctx* ctx)
+{
+    if (ctx->spans.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            ctx->famMs[s.family] += ms;
+            ctx->famN[s.family] += 1;
+        }
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    ctx->spans.clear();
+}
+
+VolTable vol_table(const thb_ctx* ctx)
+{
+    VolTable t;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) t.p[i] = ctx->vols[i].d;
+    return t;
+}
+
+AccTable acc_table(const thb_ctx* ctx)
+{
+    AccTable t;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) t.p[i] = ctx->accs[i].d;
+    t.O = ctx->dO;
+    t.counter = ctx->dCounter;
+    return t;
+}
+
+int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a)
+{
+    if (a.nAct <= 0) return THB_OK;
+    const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
+    if (smem > 200 * 1024)
+        return set_error(ctx, THB_E_ARG, "expect_local: nR*nT = %d too large for the local-search kernel", a.nR * a.nT);
+    static bool attr_set = false;
+    if (!attr_set) {
+        THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    span_begin(ctx, KF_EXPECT);
+    expect_local_kernel<<<a.nAct, E_THREADS, smem, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
+int launch_insert(thb_ctx* ctx, const InsertArgs& a)
+{
+    if (a.nImg <= 0) return THB_OK;
+    // enough CTAs to fill the chip even for a handful of images
+    int split = 1;
+    const int tiles = (a.P + M_THREADS - 1) / M_THREADS;
+    while (a.nImg * split < 4 * ctx->smCount && split < tiles) split *= 2;
+    split = std::min(split, std::max(tiles, 1));
+    dim3 grid(a.nImg, split);
+    span_begin(ctx, KF_INSERT);
+    insert_kernel<<<grid, M_THREADS, 0, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
+}  // namespace thb
+
+using namespace thb;
+
+extern "C" {
+
+int thb_version(void) { return 100; }
+
+int thb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int thb_create(thb_ctx** out, int device)
+{
+    if (!out) return set_error(nullptr, THB_E_ARG, "thb_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(nullptr, THB_E_NOGPU,
+                         "thb_create: no CUDA device visible (%s); libthunder_b200 has no CPU path",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= n) return set_error(nullptr, THB_E_ARG, "thb_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return set_error(nullptr, THB_E_NOGPU, "thb_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                         device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    thb_ctx* ctx = new thb_ctx();
+    ctx->device = device;
+    ctx->smCount = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    if ((e = cudaMalloc(&ctx->dO, sizeof(double) * 3 * THB_MAX_SLOTS)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->dCounter, sizeof(int) * THB_MAX_SLOTS)) != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(nullptr, e, "cudaMalloc");
+    }
+    cudaMemset(ctx->dO, 0, sizeof(double) * 3 * THB_MAX_SLOTS);
+    cudaMemset(ctx->dCounter, 0, sizeof(int) * THB_MAX_SLOTS);
+    *out = ctx;
+    return THB_OK;
+}
+
+static void free_stack(Stack& s)
+{
+    cudaFree(s.dat); cudaFree(s.ctf); cudaFree(s.sig); cudaFree(s.slot);
+    s = Stack();
+}
+
+void thb_destroy(thb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    resolve_spans(ctx);
+    comm_destroy(ctx);
+    pf_free(ctx);
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) {
+        cudaFree(ctx->vols[i].d);
+        cudaFree(ctx->accs[i].d);
+    }
+    free_stack(ctx->stackE);
+    free_stack(ctx->stackM);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM);
+    cudaFree(ctx->dO); cudaFree(ctx->dCounter);
+    for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* thb_last_error(const thb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int thb_synchronize(thb_ctx* ctx)
+{
+    if (!ctx) return THB_E_ARG;
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int64_t thb_launch_count(thb_ctx* ctx, int reset)
+{
+    if (!ctx) return 0;
+    int64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+int thb_enable_timing(thb_ctx* ctx, int on)
+{
+    if (!ctx) return THB_E_ARG;
+    resolve_spans(ctx);
+    ctx->timing = on != 0;
+    return THB_OK;
+}
+
+double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset)
+{
+    if (!ctx || which < 0 || which >= KF_COUNT) return 0.0;
+    resolve_spans(ctx);
+    double v = ctx->famMs[which];
+    if (n) *n = ctx->famN[which];
+    if (reset) {
+        ctx->famMs[which] = 0;
+        ctx->famN[which] = 0;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1: Optimiser::allocPreCalIdx (reference src/Optimiser.cpp:7991-8041), host integer math.
+//   IMAGE_FOR_PIXEL_R_FT(rU + 1): j in [-(rU+1), rU+1), i in [0, rU+1]  (include/Image/Image.h:68-70)
+//   QUAD(i,j) = i*i + j*j ; NORM = hypot ; AROUND = rint                 (include/Functions/Functions.h)
+// ------------------------------------------------------------------------------------------------
+int thb_pixel_list(int N, int pf, float rU, float rL, int* iCol, int* iRow, int* iPxl, int* iSig, int* iColPad,
+                   int* iRowPad)
+{
+    if (N <= 0 || (N & 1) || pf <= 0) return THB_E_ARG;
+    const float rU2 = rU * rU, rL2 = rL * rL;
+    const float R = rU + 1;                // the macro argument (a float expression) is the loop bound
+    const int nColFT = N / 2 + 1;
+    int n = 0;
+    for (long j = (long)(-R); (float)j < R; ++j)
+        for (long i = 0; (float)i <= R; ++i) {
+            if (i == 0 && j < 0) continue;
+            const float u = (float)((double)(i * i) + (double)(j * j));
+            if (u < rU2 && u >= rL2) {
+                const int v = (int)rint(hypot((double)i, (double)j));
+                if ((float)v < rU && (float)v >= rL) {
+                    if (n >= nColFT * N) return THB_E_ARG;
+                    if (iPxl) iPxl[n] = (int)((j >= 0 ? j : j + N) * nColFT + i);
+                    if (iCol) iCol[n] = (int)(i);
+                    if (iRow) iRow[n] = (int)(j);
+                    if (iSig) iSig[n] = v;
+                    if (iColPad) iColPad[n] = (int)(i * pf);
+                    if (iRowPad) iRowPad[n] = (int)(j * pf);
+                    ++n;
+                }
+            }
+        }
+    return n;
+}
+
+static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst)
+{
+    if (nPxl <= 0 || !a || !b) return set_error(ctx, THB_E_ARG, "pixel list is empty or NULL");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int* tmp = (int*)scratch(ctx, 0, sizeof(int) * 2 * (size_t)nPxl);
+    if (!tmp) return THB_E_CUDA;
+    THB_CUDA(ctx, cudaMemcpyAsync(tmp, a, sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(tmp + nPxl, b, sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    THB_CUDA(ctx, cudaMalloc(dst, sizeof(int4) * (size_t)nPxl));
+    make_pix_kernel<<<(nPxl + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + nPxl, nPxl, pf, padded, *dst);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol, const int* iRow)
+{
+    if (!ctx) return THB_E_ARG;
+    if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_expect_pixels: bad N/pf");
+    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE);
+    if (rc) return rc;
+    ctx->N = N; ctx->pf = pf; ctx->nPxlE = nPxl;
+    return THB_OK;
+}
+
+int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iColPad, const int* iRowPad)
+{
+    if (!ctx) return THB_E_ARG;
+    if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_insert_pixels: bad N/pf");
+    int rc = upload_pixels(ctx, pf, nPxl, iColPad, iRowPad, 1, &ctx->pixM);
+    if (rc) return rc;
+    ctx->NM = N; ctx->pfM = pf; ctx->nPxlM = nPxl;
+    return THB_OK;
+}
+
+static size_t vol_elems(int vdim) { return (size_t)(vdim / 2 + 1) * vdim * vdim; }
+
+int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !volFT || vdim <= 0 || (vdim & 1))
+        return set_error(ctx, THB_E_ARG, "set_volume: bad slot/vdim");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Volume3& v = ctx->vols[slot];
+    if (v.vdim != vdim) {
+        cudaFree(v.d);
+        v.d = nullptr;
+        v.vdim = 0;
+        THB_CUDA(ctx, cudaMalloc(&v.d, vol_elems(vdim) * sizeof(float2)));
+        v.vdim = vdim;
+    }
+    THB_CUDA(ctx, cudaMemcpyAsync(v.d, volFT, vol_elems(vdim) * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_get_volume(thb_ctx* ctx, int slot, float* volFT)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !volFT || !ctx->vols[slot].d)
+        return set_error(ctx, THB_E_STATE, "get_volume: slot %d has no volume", slot);
+    const Volume3& v = ctx->vols[slot];
+    THB_CUDA(ctx, cudaMemcpyAsync(volFT, v.d, vol_elems(v.vdim) * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                     const int* slotOfImg)
+{
+    if (!ctx) return THB_E_ARG;
+    if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "upload_stack: bad kind");
+    const int P = kind == THB_STACK_EXPECT ? ctx->nPxlE : ctx->nPxlM;
+    if (P <= 0) return set_error(ctx, THB_E_STATE, "upload_stack: pixel list for this stack kind not set");
+    if (nImg <= 0 || !dat || !ctf) return set_error(ctx, THB_E_ARG, "upload_stack: empty stack / NULL arrays");
+    if (kind == THB_STACK_EXPECT && !sigRcp) return set_error(ctx, THB_E_ARG, "upload_stack: sigRcp required for the E stack");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Stack& s = kind == THB_STACK_EXPECT ? ctx->stackE : ctx->stackM;
+    const size_t n = (size_t)nImg * P;
+    if (s.nImg != nImg) {
+        free_stack(s);
+        THB_CUDA(ctx, cudaMalloc(&s.dat, n * sizeof(float2)));
+        THB_CUDA(ctx, cudaMalloc(&s.ctf, n * sizeof(float)));
+        if (kind == THB_STACK_EXPECT) THB_CUDA(ctx, cudaMalloc(&s.sig, n * sizeof(float)));
+        THB_CUDA(ctx, cudaMalloc(&s.slot, (size_t)nImg * sizeof(int)));
+        s.nImg = nImg;
+    }
+    THB_CUDA(ctx, cudaMemcpyAsync(s.dat, dat, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(s.ctf, ctf, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (kind == THB_STACK_EXPECT)
+        THB_CUDA(ctx, cudaMemcpyAsync(s.sig, sigRcp, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (slotOfImg) {
+        for (int i = 0; i < nImg; ++i)
+            if (slotOfImg[i] < 0 || slotOfImg[i] >= THB_MAX_SLOTS)
+                return set_error(ctx, THB_E_ARG, "upload_stack: slotOfImg[%d] = %d out of range", i, slotOfImg[i]);
+        THB_CUDA(ctx, cudaMemcpyAsync(s.slot, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        THB_CUDA(ctx, cudaMemsetAsync(s.slot, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    }
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->vols[slot].d) return set_error(ctx, THB_E_STATE, "project: no volume in slot %d", slot);
+    if (!ctx->pixE) return set_error(ctx, THB_E_STATE, "project: E pixel list not set");
+    if (nRot <= 0 || !quat || !dst) return set_error(ctx, THB_E_ARG, "project: bad arguments");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int P = ctx->nPxlE;
+    double* dq = (double*)scratch(ctx, 0, sizeof(double) * 4 * (size_t)nRot);
+    float2* dd = (float2*)scratch(ctx, 1, sizeof(float2) * (size_t)nRot * P);
+    if (!dq || !dd) return THB_E_CUDA;
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * 4 * (size_t)nRot, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((P + 255) / 256, nRot);
+    span_begin(ctx, KF_EXPECT);
+    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->pixE, P, dq, dd);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaMemcpyAsync(dst, dd, sizeof(float2) * (size_t)nRot * P, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+static int check_expect_state(thb_ctx* ctx, const char* who)
+{
+    if (!ctx->pixE) return set_error(ctx, THB_E_STATE, "%s: E pixel list not set", who);
+    if (!ctx->stackE.dat) return set_error(ctx, THB_E_STATE, "%s: E stack not uploaded", who);
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->vols[i].d) {
+            if (vdim && ctx->vols[i].vdim != vdim) return set_error(ctx, THB_E_STATE, "%s: volumes of different size", who);
+            vdim = ctx->vols[i].vdim;
+        }
+    if (!vdim) return set_error(ctx, THB_E_STATE, "%s: no projector volume uploaded", who);
+    if (vdim < ctx->pf * ctx->N) return set_error(ctx, THB_E_STATE, "%s: volume dimension %d < pf*N = %d", who, vdim, ctx->pf * ctx->N);
+    return vdim;
+}
+
+int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, const double* quat, const double* tran,
+                     const double* wR, const double* wT, float* uR, float* uT, float* uC, float* base, float* logL)
+{
+    if (!ctx) return THB_E_ARG;
+    const int vdim = check_expect_state(ctx, "expect_local");
+    if (vdim < 0) return vdim;
+    if (nAct <= 0 || nR <= 0 || nT <= 0 || !quat || !tran || !wR || !wT) return set_error(ctx, THB_E_ARG, "expect_local: bad arguments");
+    if (imgIdx)
+        for (int i = 0; i < nAct; ++i)
+            if (imgIdx[i] < 0 || imgIdx[i] >= ctx->stackE.nImg)
+                return set_error(ctx, THB_E_ARG, "expect_local: imgIdx[%d] = %d outside the stack", i, imgIdx[i]);
+    if (!imgIdx && nAct > ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "expect_local: nAct exceeds the stack");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const size_t nq = (size_t)nAct * nR * 4, nt = (size_t)nAct * nT * 2, nwr = (size_t)nAct * nR, nwt = (size_t)nAct * nT;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + nt + nwr + nwt) + sizeof(int) * (size_t)nAct);
+    const size_t nout = nwr + nwt + 2 * (size_t)nAct + (logL ? nwr * nT : 0);
+    float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
+    if (!din || !dout) return THB_E_CUDA;
+    double* dq = din; double* dt = dq + nq; double* dwr = dt + nt; double* dwt = dwr + nwr;
+    int* didx = (int*)(dwt + nwt);
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwr, wR, sizeof(double) * nwr, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwt, wT, sizeof(double) * nwt, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(didx, imgIdx, sizeof(int) * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
+
+    ExpectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vols = vol_table(ctx);
+    a.vdim = vdim;
+    a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
+    a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
+    a.nAct = nAct; a.imgIdx = imgIdx ? didx : nullptr; a.imgBase = 0; a.active = nullptr;
+    a.nR = nR; a.nT = nT;
+    a.quat = View3{dq, (long long)nR * 4, 4, 1};
+    a.tran = View3{dt, (long long)nT * 2, 2, 1};
+    a.wR = View3{dwr, (long long)nR, 1, 0};
+    a.wT = View3{dwt, (long long)nT, 1, 0};
+    a.uR = dout; a.uT = a.uR + nwr; a.uC = a.uT + nwt; a.base = a.uC + nAct;
+    a.logL = logL ? a.base + nAct : nullptr;
+    int rc = launch_expect_local(ctx, a);
+    if (rc) return rc;
+    if (uR) THB_CUDA(ctx, cudaMemcpyAsync(uR, a.uR, sizeof(float) * nwr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uT) THB_CUDA(ctx, cudaMemcpyAsync(uT, a.uT, sizeof(float) * nwt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uC) THB_CUDA(ctx, cudaMemcpyAsync(uC, a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+    if (base) THB_CUDA(ctx, cudaMemcpyAsync(base, a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logL) THB_CUDA(ctx, cudaMemcpyAsync(logL, a.logL, sizeof(float) * nwr * nT, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+// Global-scan shape (src/Optimiser.cpp:633-914): one shared rotation/translation set against every
+// image.  Round 1: the same fused kernel with particle-stride 0 views; rotations beyond one CTA's
+// shared-memory budget are processed in chunks and merged on the host with the reference's
+// running-baseline rule.
+int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, const double* tran, const double* pR,
+                    const double* pT, float* wC, float* wR, float* wT, float* base, float* logL)
+{
+    if (!ctx) return THB_E_ARG;
+    const int vdim = check_expect_state(ctx, "expect_scan");
+    if (vdim < 0) return vdim;
+    if (nR <= 0 || nT <= 0 || !quat || !tran || !pR || !pT) return set_error(ctx, THB_E_ARG, "expect_scan: bad arguments");
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->vols[slot].d) return set_error(ctx, THB_E_STATE, "expect_scan: no volume in slot %d", slot);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nImg = ctx->stackE.nImg;
+    std::vector<int> hslot(nImg);
+    THB_CUDA(ctx, cudaMemcpy(hslot.data(), ctx->stackE.slot, sizeof(int) * nImg, cudaMemcpyDeviceToHost));
+    std::vector<int> idx;
+    for (int i = 0; i < nImg; ++i) if (hslot[i] == slot) idx.push_back(i);
+    const int nAct = (int)idx.size();
+    if (wC) memset(wC, 0, sizeof(float) * nImg);
+    if (wR) memset(wR, 0, sizeof(float) * (size_t)nImg * nR);
+    if (wT) memset(wT, 0, sizeof(float) * (size_t)nImg * nT);
+    if (base) memset(base, 0, sizeof(float) * nImg);
+    if (logL) memset(logL, 0, sizeof(float) * (size_t)nImg * nR * nT);
+    if (nAct == 0) return THB_OK;
+
+    const int rChunk = std::max(1, std::min(nR, (int)((160 * 1024) / (sizeof(float) * nT))));
+    std::vector<float> cuR((size_t)nAct * rChunk), cuT((size_t)nAct * nT), cuC(nAct), cbase(nAct), clog;
+    std::vector<float> aR((size_t)nAct * nR, 0.f), aT((size_t)nAct * nT, 0.f), aC(nAct, 0.f), abase(nAct, -INFINITY);
+    if (logL) clog.resize((size_t)nAct * rChunk * nT);
+
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * ((size_t)rChunk * 4 + nT * 2 + rChunk + nT) + sizeof(int) * (size_t)nAct);
+    if (!din) return THB_E_CUDA;
+    for (int r0 = 0; r0 < nR; r0 += rChunk) {
+        const int nr = std::min(rChunk, nR - r0);
+        double* dq = din; double* dt = dq + (size_t)rChunk * 4; double* dwr = dt + nT * 2; double* dwt = dwr + rChunk;
+        int* didx = (int*)(dwt + nT);
+        const size_t nout = (size_t)nAct * nr + (size_t)nAct * nT + 2 * (size_t)nAct + (logL ? (size_t)nAct * nr * nT : 0);
+        float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
+        if (!dout) return THB_E_CUDA;
+        THB_CUDA(ctx, cudaMemcpyAsync(dq, quat + (size_t)r0 * 4, sizeof(double) * 4 * nr, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * 2 * nT, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dwr, pR + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dwt, pT, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(didx, idx.data(), sizeof(int) * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
+        ExpectArgs a;
+        memset(&a, 0, sizeof(a));
+        a.vols = vol_table(ctx); a.vdim = vdim;
+        a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
+        a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
+        a.nAct = nAct; a.imgIdx = didx; a.nR = nr; a.nT = nT;
+        a.quat = View3{dq, 0, 4, 1};
+        a.tran = View3{dt, 0, 2, 1};
+        a.wR = View3{dwr, 0, 1, 0};
+        a.wT = View3{dwt, 0, 1, 0};
+        a.uR = dout; a.uT = a.uR + (size_t)nAct * nr; a.uC = a.uT + (size_t)nAct * nT; a.base = a.uC + nAct;
+        a.logL = logL ? a.base + nAct : nullptr;
+        int rc = launch_expect_local(ctx, a);
+        if (rc) return rc;
+        THB_CUDA(ctx, cudaMemcpyAsync(cuR.data(), a.uR, sizeof(float) * (size_t)nAct * nr, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(cuT.data(), a.uT, sizeof(float) * (size_t)nAct * nT, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(cuC.data(), a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(cbase.data(), a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+        if (logL) THB_CUDA(ctx, cudaMemcpyAsync(clog.data(), a.logL, sizeof(float) * (size_t)nAct * nr * nT, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // merge this rotation chunk: rescale to the larger baseline (Optimiser.cpp:846-870)
+        for (int l = 0; l < nAct; ++l) {
+            float nb = std::max(abase[l], cbase[l]);
+            float so = abase[l] == -INFINITY ? 0.f : expf(abase[l] - nb), sn = expf(cbase[l] - nb);
+            for (int r = 0; r < r0; ++r) aR[(size_t)l * nR + r] *= so;
+            for (int r = 0; r < nr; ++r) aR[(size_t)l * nR + r0 + r] = cuR[(size_t)l * nr + r] * sn;
+            for (int t = 0; t < nT; ++t) aT[(size_t)l * nT + t] = aT[(size_t)l * nT + t] * so + cuT[(size_t)l * nT + t] * sn;
+            aC[l] = aC[l] * so + cuC[l] * sn;
+            abase[l] = nb;
+            if (logL)
+                for (int r = 0; r < nr; ++r)
+                    memcpy(logL + ((size_t)idx[l] * nR + r0 + r) * nT, clog.data() + ((size_t)l * nr + r) * nT, sizeof(float) * nT);
+        }
+    }
+    for (int l = 0; l < nAct; ++l) {
+        const int i = idx[l];
+        if (wC) wC[i] = aC[l];
+        if (base) base[i] = abase[l];
+        if (wR) memcpy(wR + (size_t)i * nR, aR.data() + (size_t)l * nR, sizeof(float) * nR);
+        if (wT) memcpy(wT + (size_t)i * nT, aT.data() + (size_t)l * nT, sizeof(float) * nT);
+    }
+    return THB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || vdimPad <= 0 || (vdimPad & 1)) return set_error(ctx, THB_E_ARG, "reco_alloc: bad slot/vdim");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Accum& a = ctx->accs[slot];
+    if (a.vdim != vdimPad) {
+        cudaFree(a.d);
+        a = Accum();
+        const size_t n = vol_elems(vdimPad);
+        THB_CUDA(ctx, cudaMalloc(&a.d, n * sizeof(float4)));
+        a.vdim = vdimPad;
+        a.nVox = n;
+    }
+    return thb_reco_reset(ctx, slot);
+}
+
+int thb_reco_reset(thb_ctx* ctx, int slot)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reco_reset: slot %d not allocated", slot);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaMemsetAsync(ctx->accs[slot].d, 0, ctx->accs[slot].nVox * sizeof(float4), ctx->stream));
+    THB_CUDA(ctx, cudaMemsetAsync(ctx->dO + 3 * slot, 0, 3 * sizeof(double), ctx->stream));
+    THB_CUDA(ctx, cudaMemsetAsync(ctx->dCounter + slot, 0, sizeof(int), ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const double* nr,
+               const double* nt)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->pixM) return set_error(ctx, THB_E_STATE, "insert: M pixel list not set");
+    if (!ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "insert: M stack not uploaded");
+    if (nImg <= 0 || mReco <= 0 || !w || !nr || !nt) return set_error(ctx, THB_E_ARG, "insert: bad arguments");
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->accs[i].d) {
+            if (vdim && ctx->accs[i].vdim != vdim) return set_error(ctx, THB_E_STATE, "insert: accumulators of different size");
+            vdim = ctx->accs[i].vdim;
+        }
+    if (!vdim) return set_error(ctx, THB_E_STATE, "insert: no accumulator allocated (thb_reco_alloc)");
+    if (imgIdx)
+        for (int i = 0; i < nImg; ++i)
+            if (imgIdx[i] < 0 || imgIdx[i] >= ctx->stackM.nImg) return set_error(ctx, THB_E_ARG, "insert: imgIdx[%d] outside the stack", i);
+    if (!imgIdx && nImg > ctx->stackM.nImg) return set_error(ctx, THB_E_ARG, "insert: nImg exceeds the stack");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const size_t nq = (size_t)nImg * mReco * 4, ntt = (size_t)nImg * mReco * 2;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * (size_t)nImg);
+    if (!din) return THB_E_CUDA;
+    double* dq = din; double* dt = dq + nq; double* doff = dt + ntt;
+    float* dw = (float*)(doff + 2 * (size_t)nImg);
+    int* didx = (int*)(dw + nImg);
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, nr, sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dt, nt, sizeof(double) * ntt, cudaMemcpyHostToDevice, ctx->stream));
+    if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dw, w, sizeof(float) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(didx, imgIdx, sizeof(int) * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+
+    InsertArgs a;
+    memset(&a, 0, sizeof(a));
+    a.acc = acc_table(ctx);
+    a.vdim = vdim;
+    a.dat = ctx->stackM.dat; a.ctf = ctx->stackM.ctf; a.slotOfImg = ctx->stackM.slot;
+    a.pix = ctx->pixM; a.P = ctx->nPxlM; a.N = ctx->NM;
+    a.nImg = nImg; a.imgIdx = imgIdx ? didx : nullptr; a.imgBase = 0;
+    a.mReco = mReco; a.w = dw; a.wAll = 0.f; a.offS = offS ? doff : nullptr;
+    a.nr = View3{dq, (long long)mReco * 4, 4, 1};
+    a.nt = View3{dt, (long long)mReco * 2, 2, 1};
+    int rc = launch_insert(ctx, a);
+    if (rc) return rc;
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_reco_download(thb_ctx* ctx, int slot, float* F, float* T, double* O, int* counter, int normalise)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reco_download: slot %d not allocated", slot);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Accum& a = ctx->accs[slot];
+    if (F || T) {
+        float2* dF = nullptr; float* dT = nullptr;
+        if (F) { dF = (float2*)scratch(ctx, 2, a.nVox * sizeof(float2)); if (!dF) return THB_E_CUDA; }
+        if (T) { dT = (float*)scratch(ctx, 3, a.nVox * sizeof(float)); if (!dT) return THB_E_CUDA; }
+        span_begin(ctx, KF_PACK);
+        unpack_acc_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(a.d, a.nVox, dF, dT, normalise);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+        if (F) THB_CUDA(ctx, cudaMemcpyAsync(F, dF, a.nVox * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        if (T) THB_CUDA(ctx, cudaMemcpyAsync(T, dT, a.nVox * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (O) THB_CUDA(ctx, cudaMemcpyAsync(O, ctx->dO + 3 * slot, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counter) THB_CUDA(ctx, cudaMemcpyAsync(counter, ctx->dCounter + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+}  // extern "C"

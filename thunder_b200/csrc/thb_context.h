@@ -1,0 +1,126 @@
+// thb_context.h - the opaque context behind the C ABI (host side, C++).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/thunder_b200.h"
+#include "thb_types.cuh"
+
+namespace thb {
+
+enum KernelFamily { KF_EXPECT = 0, KF_INSERT = 1, KF_PF = 2, KF_PACK = 3, KF_COMM = 4, KF_COUNT = 5 };
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int family;
+};
+
+struct Stack {
+    int nImg = 0;
+    float2* dat = nullptr;
+    float* ctf = nullptr;
+    float* sig = nullptr;
+    int* slot = nullptr;
+};
+
+struct Volume3 {
+    float2* d = nullptr;
+    int vdim = 0;
+};
+
+struct Accum {
+    float4* d = nullptr;
+    int vdim = 0;
+    size_t nVox = 0;
+};
+
+// device-resident particle-filter state, SoA with the particle index fastest:
+//   r[(c*mLR + i)*nPar + p], t[(c*mLT + i)*nPar + p], wR[i*nPar + p], wT[i*nPar + p]
+struct PFState {
+    int nPar = 0;
+    thb_pf_params prm{};
+    double* r = nullptr;
+    double* t = nullptr;
+    double* wR = nullptr;
+    double* wT = nullptr;
+    double* scal = nullptr;      // [16][nPar]
+    float* uR = nullptr;         // [nPar][mLR]
+    float* uT = nullptr;         // [nPar][mLT]
+    float* uC = nullptr;
+    float* base = nullptr;
+    unsigned char* active = nullptr;
+    int* nPhase = nullptr;
+    double* vari = nullptr;      // [3][nPar] best variR, variT, and no-decrease counter
+    int* drawR = nullptr;        // [nPar][mReco]
+    int* drawT = nullptr;
+    int drawCap = 0;
+    uint64_t epoch = 0;          // advances the counter-based RNG stream between calls
+};
+
+}  // namespace thb
+
+struct thb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int smCount = 148;
+
+    // pixel sets
+    int N = 0, pf = 0, nPxlE = 0, nPxlM = 0, NM = 0, pfM = 0;
+    int4* pixE = nullptr;
+    int4* pixM = nullptr;
+
+    thb::Volume3 vols[thb::THB_MAX_SLOTS];
+    thb::Accum accs[thb::THB_MAX_SLOTS];
+    double* dO = nullptr;        // [THB_MAX_SLOTS][3]
+    int* dCounter = nullptr;     // [THB_MAX_SLOTS]
+
+    thb::Stack stackE, stackM;
+    thb::PFState pf_;
+
+    // NCCL
+    void* ncclComm = nullptr;
+    int nRanks = 1, rank = 0;
+
+    // accounting
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<thb::TimedSpan> spans;
+    double famMs[thb::KF_COUNT] = {0, 0, 0, 0, 0};
+    int64_t famN[thb::KF_COUNT] = {0, 0, 0, 0, 0};
+
+    // scratch device buffers (grown on demand)
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratchCap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace thb {
+
+int set_error(thb_ctx* ctx, int code, const char* fmt, ...);
+int cuda_fail(thb_ctx* ctx, cudaError_t e, const char* what);
+void* scratch(thb_ctx* ctx, int which, size_t bytes);   // nullptr on failure (error set)
+void span_begin(thb_ctx* ctx, int family);
+void span_end(thb_ctx* ctx);
+void resolve_spans(thb_ctx* ctx);
+
+#define THB_CUDA(ctx, call)                                         \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return thb::cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// launches (thb_launch.cu)
+int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a);
+int launch_insert(thb_ctx* ctx, const InsertArgs& a);
+VolTable vol_table(const thb_ctx* ctx);
+AccTable acc_table(const thb_ctx* ctx);
+
+// NCCL (thb_comm.cpp)
+int comm_allreduce(thb_ctx* ctx);
+void comm_destroy(thb_ctx* ctx);
+
+// particle filter (thb_pf.cu)
+void pf_free(thb_ctx* ctx);
+
+}  // namespace thb

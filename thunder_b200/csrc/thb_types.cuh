@@ -1,0 +1,80 @@
+// thb_types.cuh - argument structs shared by the kernels and the host-side launch code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace thb {
+
+constexpr int THB_MAX_SLOTS = 16;
+constexpr int E_THREADS = 128;   // one rotation sample per thread
+constexpr int E_TILE = 128;      // pixels staged in shared memory per step
+constexpr int E_TC = 9;          // translations carried in registers per pass (mLT default = 9)
+constexpr int M_THREADS = 256;
+constexpr int M_MAXRECO = 128;
+
+struct VolTable { const float2* p[THB_MAX_SLOTS]; };
+struct AccTable { float4* p[THB_MAX_SLOTS]; double* O; int* counter; };
+
+// strided view of a [particle][sample][component] array (API arrays and the SoA particle state
+// use different strides)
+struct View3 {
+    const double* p;
+    long long sP, sS, sC;
+#ifdef __CUDACC__
+    __device__ __forceinline__ double at(long long ip, long long is, long long ic) const
+    {
+        return p[ip * sP + is * sS + ic * sC];
+    }
+#endif
+};
+
+struct __align__(16) PixelE {
+    double a, b;        // pf*iCol, pf*iRow
+    float ctf, sig;
+    float2 d[E_TC];     // dat * conj(tra_t)
+};
+static_assert(sizeof(PixelE) == 96, "PixelE must be 96 bytes");
+
+struct ExpectArgs {
+    VolTable vols;
+    int vdim;
+    const float2* dat;
+    const float* ctf;
+    const float* sig;
+    const int* slotOfImg;
+    const int4* pix;
+    int P, N;
+    int nAct;
+    const int* imgIdx;      // may be null: image = particle index + imgBase
+    int imgBase;
+    const unsigned char* active;   // may be null; skip particle when active[p] == 0
+    int nR, nT;
+    View3 quat, tran, wR, wT;
+    float* uR;      // [nAct][nR]
+    float* uT;      // [nAct][nT]
+    float* uC;      // [nAct]
+    float* base;    // [nAct]
+    float* logL;    // [nAct][nR][nT] or null
+};
+
+struct InsertArgs {
+    AccTable acc;
+    int vdim;                 // padded accumulator dimension
+    const float2* dat;
+    const float* ctf;
+    const int* slotOfImg;
+    const int4* pix;
+    int P, N;
+    int nImg;
+    const int* imgIdx;        // may be null
+    int imgBase;
+    int mReco;
+    const float* w;           // [nImg] or null (then wAll)
+    float wAll;
+    const double* offS;       // [nImg][2] indexed by image, or null
+    View3 nr, nt;             // [nImg][mReco][4], [nImg][mReco][2]
+    const int* drawR;         // optional [nImg][mReco] indices into nr/nt sample axis (particle filter draws)
+    const int* drawT;
+};
+
+}  // namespace thb
