@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py - particles/s per Optimiser iteration (box 256^2) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA hot path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's own CPU path (oracle/_ref)
+
+Workload (BASELINE.json configs[1]): 100k synthetic particles, box 256, pf 2, r = 127 (25 134 Fourier
+pixels per image), 2000 orientation samples per particle per iteration = 125 rotations x 16 particle-
+filter phases, x 9 translations; M-step with mReco = 100 draws per particle; two half-set volumes.
+The whole packed stack (masked E stack + unmasked M stack, ~70 GB at N = 1) is resident in HBM.
+A "step" is one Optimiser iteration (E-step all phases + M-step insert + half-map allreduce) over one
+batch of `--batch` particles per GPU taken from the resident stack; consecutive steps walk the stack,
+so every step reads images that are not in L2 (a batch is ~7 GB).  value = particles processed by all
+ranks / device time (max over ranks).  e2e = the same step driven from HOST buffers: the batch's packed
+images are copied from pinned host memory (thb_upload_stack_at), the particle parameters go up and the
+particle results + (once per timed region) the half-map volumes come back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "particles/sec per Optimiser iteration (box 256^2)"
+UNIT = "particles/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=100000, help="particles in the whole job (resident stack)")
+    ap.add_argument("--batch", type=int, default=5000, help="particles per GPU per step")
+    ap.add_argument("--box", type=int, default=256)
+    ap.add_argument("--phases", type=int, default=16)
+    ap.add_argument("--mlr", type=int, default=125)
+    ap.add_argument("--mlt", type=int, default=9)
+    ap.add_argument("--mreco", type=int, default=100)
+    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic particles generated on the host")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles of the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    N, pf = args.box, 2
+    r = N // 2 - 1
+    rL = float(np.floor(N * 1.32 / 200.0))        # ignoreRes 200 A at 1.32 A/pixel (src/Optimiser.cpp:243)
+    return dict(N=N, pf=pf, r=r, rL=rL, k0=7.6e-5, transS=2.0)
+
+
+def config_dict(args, wl, nPxlE, nPxlM, n_gpus):
+    return {
+        "workload": f"100k synthetic particles, box {wl['N']}, {args.mlr * args.phases} orientation samples "
+                    f"({args.mlr} rot x {args.phases} phases) x {args.mlt} translations, mReco {args.mreco}, "
+                    f"{n_gpus}xB200" + (" with NCCL half-map allreduce" if n_gpus > 1 else ""),
+        "particles_resident_per_gpu": args.particles // n_gpus, "batch_per_gpu_per_step": args.batch,
+        "box": wl["N"], "pf": wl["pf"], "r": wl["r"], "nPxl_E": nPxlE, "nPxl_M": nPxlM,
+        "mLR": args.mlr, "mLT": args.mlt, "phases": args.phases, "mReco": args.mreco, "half_sets": 2,
+        "l2": "inputs larger than L2 (each step reads a fresh ~%.1f GB image batch)" % (args.batch * (nPxlE * 16 + nPxlM * 12) / 1e9),
+        "parallelism": f"particles sharded over {n_gpus} GPU(s); one allreduce of F|T per step",
+    }
+
+
+# ------------------------------------------------------------------------------------------------- helpers
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            j = json.loads(p.read_text())
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+                if k in j:
+                    return float(j[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(nPxlE, mLR):
+    """per-particle-phase DRAM traffic of the dominant kernel from the committed ncu capture, if any"""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, wl, steps, warmup, rank, world, sample_only=False):
+    """the reference's own CPU path (oracle/_ref = THUNDER's Projector / Particle / logDataVSPrior / Reconstructor
+    classes compiled from its sources; driver loops of expectation() and reconstructRef() in oracle/ref_harness.cpp)"""
+    from oracle import refapi as ref
+    from thunder_b200 import synth
+    if not ref.available():
+        return None
+    cores = os.cpu_count() or 1
+    N, pf = wl["N"], wl["pf"]
+    pixE = ref.pixel_list(N, pf, float(wl["r"]), wl["rL"])
+    pixM = ref.pixel_list(N, pf, float(wl["r"]), 0.0)
+    nS = args.cpu_sample or cores
+    rng = np.random.default_rng(5)
+    vol = synth.padded_ft(synth.phantom(N, 30), pf)
+    P = ref.Projector(pf)
+    P.set_padded_ft(vol)
+    quat = synth.random_quats(nS, rng)
+    clean = np.stack([P.project(ref.rotate3D(q), pixE["iCol"], pixE["iRow"]) for q in quat])
+    par = synth.make_particles(nS, N, pixE, lambda q: clean, seed=3)
+    par["quat"] = quat
+    PM = len(pixM["iCol"])
+    datM = (rng.normal(size=(nS, PM)) + 1j * rng.normal(size=(nS, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nS, PM)).astype(np.float32)
+    reco = ref.Reconstructor(N, N, pf, cores)
+    reco.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+
+    def one_step():
+        pars = []
+        for l in range(nS):
+            p = ref.Particle(args.mlr, args.mlt, wl["transS"], 0.01)
+            p.load(args.mlr, args.mlt, quat[l], wl["k0"], wl["k0"], wl["k0"], par["tran"][l], 1.0, 1.0)
+            pars.append(p)
+        t0 = time.perf_counter()
+        ref.expectation_local(pars, P, par["dat"], par["ctf"], par["sigRcp"], pixE["iCol"], pixE["iRow"], N, args.mlr, args.mlt,
+                              fixedPhases=args.phases, nThread=cores)
+        reco.insert_loop(datM, ctfM, None, None, args.mreco, None, pixM["iCol"], pixM["iRow"], N, nThread=cores, pars=pars)
+        dt = time.perf_counter() - t0
+        for p in pars:
+            p.close()
+        return dt
+
+    if sample_only:
+        dt = one_step()
+        return {"value": nS / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{nS} particles of the same workload (box {N}, {args.mlr}x{args.phases} rotations x {args.mlt} "
+                          f"translations, mReco {args.mreco}), one pass, {dt:.1f} s, OpenMP over images on {cores} threads"}
+    for _ in range(warmup):
+        one_step()
+    ts = [one_step() for _ in range(steps)]
+    total = sum(ts)
+    value = nS * steps / total
+    return {"value": value, "ms_per_step": 1e3 * total / steps, "cores": cores, "nS": nS, "nPxlE": len(pixE["iCol"]), "nPxlM": PM}
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res = run_reference(args, wl, args.steps, args.warmup, rank, world)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libthunder_ref.so not built"}))
+            return 0
+        cb = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+              "sample": f"{res['nS']} particles per step of the same workload, OpenMP over images on {res['cores']} host threads"}
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, wl, res["nPxlE"], res["nPxlM"], args.gpus), "cpu_baseline": cb,
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from thunder_b200 import capi, synth
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = capi.Context(local)
+    if world > 1:
+        ids = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+
+    N, pf = wl["N"], wl["pf"]
+    pixE = capi.pixel_list(N, pf, float(wl["r"]), wl["rL"])
+    pixM = capi.pixel_list(N, pf, float(wl["r"]), 0.0)
+    PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+    vol = synth.padded_ft(synth.phantom(N, 30), pf)
+    vol_b = (vol * np.float32(0.98)).astype(np.complex64)     # second half-set reference (distinct buffer)
+    ctx.set_volume(0, vol)
+    ctx.set_volume(1, vol_b)
+    del vol_b
+    for s in (0, 1):
+        ctx.reco_alloc(s, N * pf)
+
+    # ---- synthetic pool (host), tiled into the resident stack
+    B = args.batch
+    nRes = max(args.particles // world, B)
+    pool = min(args.pool, B)
+    rng = np.random.default_rng(1000 + rank)
+    slot_pool = (np.arange(pool) % 2).astype(np.int32)
+    par = synth.make_particles(pool, N, pixE, lambda q: ctx.project(0, q), seed=100 + rank)
+    # unmasked images on the M pixel set: same statistics (fresh noise), CTF of the same particles
+    ctfM = np.stack([synth.ctf_values(pixM["iCol"].astype(float), pixM["iRow"].astype(float), N, 1.32, 3e5, *par["ctfpar"][l], 2.7e7, 0.1)
+                     for l in range(pool)]).astype(np.float32)
+    datM = (rng.normal(size=(pool, PM)) + 1j * rng.normal(size=(pool, PM))).astype(np.complex64) * np.float32(np.sqrt(0.5))
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    reps = (B + pool - 1) // pool
+    tile = lambda a: np.concatenate([a] * reps, axis=0)[:B]
+    keep = []
+    hb = {}
+    for name, a in (("datE", par["dat"]), ("ctfE", par["ctf"]), ("sigE", par["sigRcp"]), ("datM", datM), ("ctfM", ctfM)):
+        t, v = pinned(tile(a))
+        keep.append(t)
+        hb[name] = v
+    slot_b = tile(slot_pool)
+    quat_true = tile(par["quat"]); tran_true = tile(par["tran"])
+    ctx.stack_reserve(capi.STACK_EXPECT, nRes)
+    ctx.stack_reserve(capi.STACK_INSERT, nRes)
+    for base in range(0, nRes, B):
+        c = min(B, nRes - base)
+        ctx.upload_stack_at(capi.STACK_EXPECT, base, hb["datE"][:c], hb["ctfE"][:c], hb["sigE"][:c], slot_b[:c])
+        ctx.upload_stack_at(capi.STACK_INSERT, base, hb["datM"][:c], hb["ctfM"][:c], None, slot_b[:c])
+
+    prm = capi.PFParams(mLR=args.mlr, mLT=args.mlt, transS=wl["transS"], transQ=0.01, perturbFactorL=2.0, perturbFactorS=0.5,
+                        minPhase=3, maxPhase=100, fixedPhases=args.phases, decreaseFactor=0.95, noDecreaseLimit=1,
+                        seed=20260000 + rank)
+    q_start = np.stack([synth.acg_cloud(quat_true[l], wl["k0"], 1, rng)[0] for l in range(B)])
+    t_start = tran_true + rng.normal(scale=0.5, size=(B, 2))
+    k123 = np.full((B, 3), wl["k0"]); s01 = np.full((B, 2), 1.0)
+    nBatches = max(nRes // B, 1)
+
+    def step(i, e2e=False):
+        base = (i % nBatches) * B
+        if e2e:
+            ctx.upload_stack_at(capi.STACK_EXPECT, base, hb["datE"], hb["ctfE"], hb["sigE"], slot_b)
+            ctx.upload_stack_at(capi.STACK_INSERT, base, hb["datM"], hb["ctfM"], None, slot_b)
+        ctx.pf_set_image_base(base, rank * nRes + base)
+        ctx.pf_load(prm, q_start, k123, t_start, s01)
+        ctx.expectation()
+        ctx.reconstruct_insert(args.mreco)
+        ctx.allreduce()
+        if e2e:
+            return ctx.pf_get_scal()
+        return None
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, first, e2e):
+        barrier()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        for i in range(nsteps):
+            step(first + i, e2e)
+        if e2e:
+            for s in (0, 1):
+                ctx.reco_download(s)
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1])
+        return ms, wall
+
+    for i in range(args.warmup):
+        step(i)
+    ctx.enable_timing(True)
+    for k in range(5):
+        ctx.kernel_ms(k, reset=True)
+    ctx.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall = timed(args.steps, args.warmup, e2e=False)
+    clocks = sampler.summary()
+    launches = ctx.launch_count(reset=True)
+    fam = {name: ctx.kernel_ms(k, reset=True) for k, name in enumerate(("expect", "insert", "pf", "pack", "comm"))}
+    ctx.enable_timing(False)
+    value = world * B * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        k2 = max(1, min(args.steps, 2))
+        step(0, e2e=True)                                        # warm the e2e path (staging buffers)
+        ms2, wall2 = timed(k2, 1, e2e=True)
+        h2d = B * (PE * 16 + PM * 12) + B * 11 * 8
+        d2h = B * 20 * 8 + (2 * (N * pf // 2 + 1) * (N * pf) ** 2 * 12) // k2
+        e2e = {"value": world * B * k2 / (wall2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": k2, "note": "host wall clock around pinned-host upload + iteration + result download"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        e_ms, e_n = fam["expect"]
+        alg_bytes = B * (PE * 16 + args.mlr * PE * 64.0)           # B_E per particle-phase x particles per launch
+        achieved = alg_bytes / (e_ms / max(e_n, 1) / 1e3) / 1e9 if e_n else None
+        tr = ncu_traffic(PE, args.mlr)
+        roof = {"bound": "hbm", "kernel": "expect_local_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                "traffic": (tr["dram_bytes_per_particle_phase"] * B if tr else None),
+                "algorithmic_bytes_per_launch": alg_bytes, "launches": e_n, "avg_launch_ms": e_ms / max(e_n, 1),
+                "share_of_step": {k: v[0] / ms for k, v in fam.items()}}
+        m_ms, m_n = fam["insert"]
+        if m_n:
+            roof["insert_kernel"] = {"achieved": B * (PM * 12 + args.mreco * PM * 8 * 12 * 2.0) / (m_ms / m_n / 1e3) / 1e9,
+                                     "avg_launch_ms": m_ms / m_n}
+        cb = None
+        if not args.no_cpu_baseline:
+            try:
+                cb = run_reference(args, wl, 1, 0, 0, 1, sample_only=True)
+            except Exception as e:  # the checker must never take the product bench down
+                cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+            if cb is None:
+                cb = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref not built"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_dict(args, wl, PE, PM, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "wall_ms_per_step": wall / args.steps}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -80,6 +80,9 @@ int64_t thb_launch_count(thb_ctx* ctx, int reset);
  * which = 0 expect, 1 insert, 2 particle filter, 3 pack/unpack, 4 allreduce ; launches returned in *n */
 double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset);
 int thb_enable_timing(thb_ctx* ctx, int on);
+/* CUDA-event stopwatch on the library's launch stream: stop == 0 records the start, stop != 0 records the
+ * end, waits for it and returns the elapsed device time in *ms */
+int thb_timer(thb_ctx* ctx, int stop, float* ms);
 
 /* ---------------------------------------------------------------- a1: pixel list (host integer math) */
 /* Returns nPxl (>= 0) or a negative error.  Any output pointer may be NULL.  Arrays must hold
@@ -102,6 +105,11 @@ int thb_get_volume(thb_ctx* ctx, int slot, float* volFT);      /* round trip of 
  * slotOfImg[nImg] (may be NULL = all 0) says which volume slot / accumulator each image uses. */
 int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf,
                      const float* sigRcp, const int* slotOfImg);
+/* The same in pieces: reserve HBM for `capacity` images, then fill images [base, base+nImg) - lets a
+ * caller stream a stack that is larger than its host buffers (100k x 256^2 = 70 GB) batch by batch. */
+int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity);
+int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf,
+                        const float* sigRcp, const int* slotOfImg);
 
 /* ---------------------------------------------------------------- a4/a5: slice extraction */
 /* dst[nRot][nPxl] complex64 (host) = Projector::project for each rotation (quat[nRot][4]) */
@@ -163,11 +171,17 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
                 const double* tran, const double* s01);
 /* Read back particle state.  Any pointer may be NULL.
  *   r[nPar][mLR][4], t[nPar][mLT][2], wR[nPar][mLR], wT[nPar][mLT],
- *   scal[nPar][16] = k1,k2,k3,s0,s1,rho,topR[4],topT[2],score,nPhase,variR,variT */
+ *   scal[nPar][20] = k1,k2,k3,s0,s1,rho,topR[4],topT[2],score,nPhase,variR,variT,peakFactorR,
+ *                    noDecreaseCount,variD,spare */
 int thb_pf_get(thb_ctx* ctx, double* r, double* t, double* wR, double* wT, double* scal);
 int thb_pf_set(thb_ctx* ctx, const double* r, const double* t, const double* wR, const double* wT,
                const double* scal);
-/* E-step of one iteration over all loaded particles (particle p <-> image p of the E stack):
+/* particle p <-> image imgBase + p of the resident stacks; streamBase offsets the per-particle random
+ * stream (use the global index of the first particle so that ranks / batches draw different numbers) */
+int thb_pf_set_image_base(thb_ctx* ctx, int imgBase, uint64_t streamBase);
+/* the support indices drawn by the last thb_reconstruct_insert: drawR/drawT [nPar][mReco] */
+int thb_pf_get_draws(thb_ctx* ctx, int mReco, int* drawR, int* drawT);
+/* E-step of one iteration over all loaded particles (particle p <-> image imgBase + p of the E stack):
  * phase loop of Optimiser::expectation with the particle filter on the device. */
 int thb_expectation(thb_ctx* ctx, int* nPhaseOut /* [nPar] or NULL */);
 /* M-step insert loop of reconstructRef: mReco uniform draws per particle from its support

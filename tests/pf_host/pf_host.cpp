@@ -1,0 +1,62 @@
+// Test-only host build of the particle-filter operators in thunder_b200/csrc/thb_pf.cuh (the same
+// source the CUDA kernels compile, one particle per thread there, one particle per call here), so
+// that the CPU suite can compare them with the reference's Particle / DirectionalStat classes.
+// Compiled by tests/test_pf_host.py with g++; never part of libthunder_b200.so.
+#include <cstring>
+#include <vector>
+#include "thb_pf.cuh"
+
+using namespace thb;
+
+extern "C" {
+
+// arrays are component-major for one particle: r[c*mLR+i], t[c*mLT+i]; scal[20]; uR/uT double in/out
+int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* wR, double* wT, double* uR, double* uT,
+            const float* uRf, const float* uTf, double* scal, double transS, double transQ, unsigned long long seed,
+            unsigned long long epoch)
+{
+    std::vector<double> r2(4 * mLR), t2(2 * mLT), w2(mLR > mLT ? mLR : mLT);
+    pf::View v;
+    v.r = r; v.t = t; v.wR = wR; v.wT = wT; v.uR = uR; v.uT = uT; v.scal = scal;
+    v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data();
+    v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT;
+    pf::Rng g;
+    g.init(seed, 0, epoch);
+    switch (op) {
+        case 1: pf::perturb_R(v, arg, g); break;
+        case 2: pf::perturb_T(v, arg, transS, transQ, g); break;
+        case 3: pf::set_u_keep_peak(v, uRf, uTf); break;
+        case 4: pf::rank1st(v); break;
+        case 5: pf::cal_vari(v, g); break;
+        case 6: pf::resample_R(v, g); pf::resample_T(v, g); pf::norm_w(v); break;
+        case 7: pf::balance_R(v); break;
+        case 8: pf::balance_T(v); break;
+        case 100: {   // load: arg unused; scal[0..2] = k, scal[3..4] = s, scal[6..9] = q, scal[10..11] = t on input
+            double q[4] = {scal[6], scal[7], scal[8], scal[9]}, tt[2] = {scal[10], scal[11]};
+            pf::load(v, q, scal[0], scal[1], scal[2], tt, scal[3], scal[4], g);
+            break;
+        }
+        case 101: return pf::stop_rule(v, (int)arg, 3, 0.95, 1) ? 1 : 0;
+        default: return -1;
+    }
+    return 0;
+}
+
+void pfh_infer_acg(int mLR, double* r, double* A16, double* mean4)
+{
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.r = r; v.n = 1; v.p = 0; v.mLR = mLR;
+    pf::infer_acg(v, A16);
+    if (mean4) pf::sym4_top_eigvec(A16, mean4);
+}
+
+void pfh_rng(unsigned long long seed, unsigned long long stream, unsigned long long epoch, int n, double* uni, double* nor)
+{
+    pf::Rng g;
+    g.init(seed, stream, epoch);
+    for (int i = 0; i < n; i++) uni[i] = g.uniform();
+    for (int i = 0; i < n; i++) nor[i] = g.normal();
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""Particle-filter operators (thunder_b200/csrc/thb_pf.cuh, the source the CUDA kernels compile)
+built for the host and compared with the reference's Particle / DirectionalStat classes.
+Deterministic operators: exact (1e-9) parity.  Stochastic ones (different RNG by design): structural
+and statistical properties.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from thunder_b200 import synth
+
+ROOT = Path(__file__).resolve().parent.parent
+SRC = ROOT / "tests" / "pf_host" / "pf_host.cpp"
+LIB = ROOT / "tests" / "pf_host" / "libpf_host.so"
+_p, _i, _d = C.c_void_p, C.c_int, C.c_double
+
+
+@pytest.fixture(scope="module")
+def pfh():
+    hdr = ROOT / "thunder_b200" / "csrc" / "thb_pf.cuh"
+    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "thunder_b200" / "csrc"),
+                               "-o", os.fspath(LIB), os.fspath(SRC)])
+    L = C.CDLL(os.fspath(LIB))
+    L.pfh_run.restype = _i
+    L.pfh_run.argtypes = [_i, _d, _i, _i] + [_p] * 9 + [_d, _d, C.c_ulonglong, C.c_ulonglong]
+    L.pfh_infer_acg.argtypes = [_i, _p, _p, _p]
+    L.pfh_rng.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _p, _p]
+    return L
+
+
+class HostParticle:
+    """one particle in the component-major layout of the device state"""
+
+    def __init__(self, L, mLR, mLT, transS=2.0, transQ=0.01, seed=1):
+        self.L, self.mLR, self.mLT = L, mLR, mLT
+        self.r = np.zeros((4, mLR)); self.t = np.zeros((2, mLT)); self.wR = np.full(mLR, 1.0 / mLR); self.wT = np.full(mLT, 1.0 / mLT)
+        self.uR = np.zeros(mLR); self.uT = np.zeros(mLT); self.scal = np.zeros(20)
+        self.scal[16] = 1e-3
+        self.transS, self.transQ, self.seed, self.epoch = transS, transQ, seed, 0
+
+    def run(self, op, arg=0.0, uRf=None, uTf=None):
+        self.epoch += 1
+        uRf = None if uRf is None else np.ascontiguousarray(uRf, np.float32)
+        uTf = None if uTf is None else np.ascontiguousarray(uTf, np.float32)
+        pt = lambda a: None if a is None else a.ctypes.data_as(_p)
+        return self.L.pfh_run(op, arg, self.mLR, self.mLT, pt(self.r), pt(self.t), pt(self.wR), pt(self.wT), pt(self.uR),
+                              pt(self.uT), pt(uRf), pt(uTf), pt(self.scal), self.transS, self.transQ, self.seed, self.epoch)
+
+
+def _cloud(rng, n, k=(3e-4, 1e-4, 6e-4)):
+    q0 = synth.random_quats(1, rng)[0]
+    v = rng.normal(size=(n, 4)) * np.sqrt(np.array([1.0, *k]))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return synth.quat_mul(v, np.broadcast_to(q0, (n, 4))), q0
+
+
+def test_rng_uniform_normal(pfh):
+    n = 200000
+    u = np.empty(n); g = np.empty(n)
+    pfh.pfh_rng(7, 3, 9, n, u.ctypes.data_as(_p), g.ctypes.data_as(_p))
+    assert 0 < u.min() and u.max() < 1
+    assert abs(u.mean() - 0.5) < 4e-3 and abs(u.var() - 1 / 12) < 2e-3
+    assert abs(g.mean()) < 1e-2 and abs(g.var() - 1) < 2e-2 and abs((g ** 4).mean() - 3) < 0.1
+    u2 = np.empty(n); g2 = np.empty(n)
+    pfh.pfh_rng(7, 4, 9, n, u2.ctypes.data_as(_p), g2.ctypes.data_as(_p))     # another stream: decorrelated
+    assert abs(np.corrcoef(u, u2)[0, 1]) < 1e-2
+
+
+def test_infer_acg_matches_reference(pfh, ref):
+    rng = np.random.default_rng(0)
+    for n in (125, 37, 9):
+        r, q0 = _cloud(rng, n)
+        A_ref = np.empty(16); k_ref = np.empty(3); m_ref = np.empty(4)
+        rr = np.ascontiguousarray(r)
+        ref.lib().ref_inferACG(rr.ctypes.data_as(_p), n, A_ref.ctypes.data_as(_p), k_ref.ctypes.data_as(_p), m_ref.ctypes.data_as(_p))
+        rc = np.ascontiguousarray(r.T)
+        A = np.empty(16); m = np.empty(4)
+        pfh.pfh_infer_acg(n, rc.ctypes.data_as(_p), A.ctypes.data_as(_p), m.ctypes.data_as(_p))
+        assert np.abs(A - A_ref).max() <= 1e-8 * np.abs(A_ref).max()   # A is near-singular for a tight cloud
+        assert np.allclose(np.array([A[5], A[10], A[15]]) / A[0], k_ref, rtol=1e-6)
+        assert min(np.abs(m - m_ref).max(), np.abs(m + m_ref).max()) < 1e-9        # eigenvector up to sign
+        assert abs(abs(np.dot(m, q0)) - 1) < 1e-2
+
+
+def _ref_particle(ref, r, t, wR=None, wT=None, k=(1e-4, 1e-4, 1e-4), s=(1.0, 1.0)):
+    p = ref.Particle(len(r), len(t))
+    p.load(len(r), len(t), r[0], k[0], k[1], k[2], t[0], s[0], s[1])
+    p.set(r=r, t=t, wR=wR, wT=wT)
+    return p
+
+
+def test_balance_calvari_keep_peak_match_reference(pfh, ref):
+    rng = np.random.default_rng(1)
+    mLR, mLT = 125, 9
+    r, q0 = _cloud(rng, mLR)
+    t = rng.normal(scale=1.3, size=(mLT, 2)) + [0.5, -1.0]
+    P = _ref_particle(ref, r, t)
+    H = HostParticle(pfh, mLR, mLT)
+    H.r[:] = r.T; H.t[:] = t.T
+    # balanceWeight
+    P.balanceWeight(P.PAR_R); P.balanceWeight(P.PAR_T)
+    H.run(7); H.run(8)
+    g = P.get()
+    assert np.allclose(H.wR, g["wR"], rtol=1e-9)
+    assert np.allclose(H.wT, g["wT"], rtol=1e-9)
+    # calVari (R rotates the cloud by conj(mean) and back: compare the cloud too)
+    P.calVari(P.PAR_R); P.calVari(P.PAR_T)
+    H.run(5)
+    sc = P.scalars()
+    assert np.allclose(H.scal[0:3], sc[0:3], rtol=1e-9)          # k1 k2 k3
+    assert np.allclose(H.scal[3:5], sc[3:5], rtol=1e-12)         # s0 s1
+    assert np.allclose(H.r.T, P.get()["r"], atol=1e-12)
+    assert abs(P.variR() - (H.scal[0] * H.scal[1] * H.scal[2]) ** (1 / 6)) < 1e-12
+    assert abs(P.variT() - H.scal[3] * H.scal[4]) < 1e-6          # the reference evaluates this in float (mat22)
+    # setU + keepHalfHeightPeak(R) + calRank1st
+    uR = rng.uniform(0, 1, mLR).astype(np.float32) ** 6
+    uT = rng.uniform(0, 1, mLT).astype(np.float32)
+    sc[16] = 0.3                                                   # peakFactorR
+    P.set_scalars(sc); H.scal[16] = 0.3
+    P.set_u(1, uR.astype(np.float64)); P.set_u(2, uT.astype(np.float64))
+    P.keepHalfHeightPeak(P.PAR_R)
+    P.calRank1st(P.PAR_R); P.calRank1st(P.PAR_T)
+    H.run(3, uRf=uR, uTf=uT); H.run(4)
+    g = P.get()
+    assert np.array_equal(H.uR, g["uR"]) and np.array_equal(H.uT, g["uT"])
+    sc = P.scalars()
+    assert np.allclose(H.scal[6:10], sc[8:12], atol=0) and np.allclose(H.scal[10:12], sc[12:14], atol=0)
+    P.close()
+
+
+def test_resample_is_systematic(pfh):
+    """each support point i is copied floor(n w_i) or ceil(n w_i) times (systematic resampling with one u0);
+    the new prior is 1/u (PARTICLE_PRIOR_ONE), normalised; top = argmax u"""
+    rng = np.random.default_rng(2)
+    mLR, mLT = 125, 9
+    for trial in range(20):
+        H = HostParticle(pfh, mLR, mLT, seed=trial)
+        r, _ = _cloud(rng, mLR); t = rng.normal(size=(mLT, 2))
+        H.r[:] = r.T; H.t[:] = t.T
+        H.wR[:] = rng.uniform(0.5, 1.5, mLR); H.wR /= H.wR.sum()
+        H.wT[:] = rng.uniform(0.5, 1.5, mLT); H.wT /= H.wT.sum()
+        H.uR[:] = rng.uniform(0, 1, mLR) ** 8; H.uT[:] = rng.uniform(0, 1, mLT) ** 2
+        H.uR[rng.integers(0, mLR, 30)] = 0.0
+        wpost = H.wR * H.uR; wpost /= wpost.sum()
+        key = {tuple(np.round(q, 12)): (w, u) for q, w, u in zip(r, wpost, H.uR)}
+        top = r[np.argmax(H.uR)]
+        tpost = H.wT * H.uT; tpost /= tpost.sum()
+        tkey = {tuple(np.round(x, 12)): w for x, w in zip(t, tpost)}
+        H.run(6)
+        out = H.r.T
+        counts = {}
+        for q in out:
+            counts[tuple(np.round(q, 12))] = counts.get(tuple(np.round(q, 12)), 0) + 1
+        for k_, c in counts.items():
+            assert k_ in key
+            e = mLR * key[k_][0]
+            assert np.floor(e) - 1e-9 <= c <= np.ceil(e) + 1e-9
+        for k_, (w, u) in key.items():
+            if mLR * w >= 1.0:
+                assert k_ in counts
+        assert np.allclose(H.scal[6:10], top)
+        prior = np.array([1.0 / key[tuple(np.round(q, 12))][1] for q in out]); prior /= prior.sum()
+        assert np.allclose(H.wR, prior, rtol=1e-12)
+        tc = {}
+        for x in H.t.T:
+            tc[tuple(np.round(x, 12))] = tc.get(tuple(np.round(x, 12)), 0) + 1
+        for k_, c in tc.items():
+            e = mLT * tkey[k_]
+            assert np.floor(e) - 1e-9 <= c <= np.ceil(e) + 1e-9
+        assert abs(H.wT.sum() - 1) < 1e-12
+
+
+def test_perturb_statistics_match_reference(pfh, ref):
+    """perturb(pf, R/T): same distribution as the reference (different random numbers): compare the spread of the
+    perturbed cloud about its mean over many repetitions"""
+    rng = np.random.default_rng(3)
+    mLR, mLT = 125, 9
+    k = (4e-4, 4e-4, 4e-4)
+    r, q0 = _cloud(rng, mLR, k)
+    t = rng.normal(scale=1.0, size=(mLT, 2))
+    ref.lib().ref_set_seed(5)
+
+    def spread(rr):
+        d = synth.quat_mul(rr, np.broadcast_to(q0 * [1, -1, -1, -1], rr.shape))
+        d *= np.sign(d[:, :1])
+        return (d[:, 1:] ** 2).sum(1).mean()
+
+    s_ref, s_our, st_ref, st_our = [], [], [], []
+    for rep in range(400):
+        P = _ref_particle(ref, r, t, k=k)
+        sc = P.scalars(); sc[0:3] = k; sc[3:5] = (0.8, 1.2); sc[8:12] = q0
+        P.set_scalars(sc); P.set(r=r, t=t)
+        P.perturb(2.0, P.PAR_R); P.perturb(2.0, P.PAR_T)
+        g = P.get()
+        s_ref.append(spread(g["r"])); st_ref.append(((g["t"] - t) ** 2).mean(0))
+        P.close()
+        H = HostParticle(pfh, mLR, mLT, seed=100 + rep)
+        H.r[:] = r.T; H.t[:] = t.T; H.scal[0:3] = k; H.scal[3:5] = (0.8, 1.2)
+        H.run(1, 2.0); H.run(2, 2.0)
+        s_our.append(spread(H.r.T)); st_our.append(((H.t.T - t) ** 2).mean(0))
+        assert abs(np.linalg.norm(H.r, axis=0) - 1).max() < 1e-12
+        assert abs(H.wR.sum() - 1) < 1e-12 and abs(H.wT.sum() - 1) < 1e-12
+    assert abs(np.mean(s_our) / np.mean(s_ref) - 1) < 0.05
+    assert np.allclose(np.mean(st_our, 0), np.mean(st_ref, 0), rtol=0.12)
+    assert np.allclose(np.mean(st_our, 0), [(0.8 * 2) ** 2, (1.2 * 2) ** 2], rtol=0.1)
+
+
+def test_load_and_stop_rule(pfh, ref):
+    rng = np.random.default_rng(4)
+    mLR, mLT = 125, 9
+    q0 = synth.random_quats(1, rng)[0]
+    H = HostParticle(pfh, mLR, mLT, seed=11)
+    H.scal[0:3] = (2e-4, 3e-4, 4e-4); H.scal[3:5] = (1.5, 0.7); H.scal[6:10] = q0; H.scal[10:12] = (1.0, -2.0)
+    H.run(100)
+    assert abs(np.linalg.norm(H.r, axis=0) - 1).max() < 1e-12
+    d = np.abs(H.r.T @ q0)
+    assert np.median(d) > 0.999 and np.quantile(d, 0.1) > 0.97   # cloud about +-q0 (the ACG has heavy tails)
+    assert (H.r.T @ q0 > 0).sum() not in (0, mLR)            # both hemisphere signs occur, as in Particle::load
+    assert np.allclose(H.t.mean(1), (1.0, -2.0), atol=1.5)
+    # calVari ran: k of the order of the input concentration
+    assert np.all(H.scal[0:3] > 2e-5) and np.all(H.scal[0:3] < 4e-3)
+    # stop rule: first check (phase == minPhase) always resets the counter; a non-decreasing variance then stops
+    assert H.run(101, 2.0) == 0
+    assert H.run(101, 3.0) == 0
+    assert H.run(101, 4.0) == 1

@@ -54,12 +54,17 @@ def _sig(lib):
     f = lib.thb_launch_count; f.restype = C.c_int64; f.argtypes = [_p, _i]
     f = lib.thb_kernel_ms; f.restype = C.c_double; f.argtypes = [_p, _i, C.POINTER(C.c_int64), _i]
     f = lib.thb_enable_timing; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_timer; f.restype = _i; f.argtypes = [_p, _i, C.POINTER(C.c_float)]
     f = lib.thb_pixel_list; f.restype = _i; f.argtypes = [_i, _i, C.c_float, C.c_float] + [_p] * 6
     f = lib.thb_set_expect_pixels; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p]
     f = lib.thb_set_insert_pixels; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p]
     f = lib.thb_set_volume; f.restype = _i; f.argtypes = [_p, _i, _p, _i]
     f = lib.thb_get_volume; f.restype = _i; f.argtypes = [_p, _i, _p]
     f = lib.thb_upload_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_stack_reserve; f.restype = _i; f.argtypes = [_p, _i, _i]
+    f = lib.thb_upload_stack_at; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
+    f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
     f = lib.thb_expect_local; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i] + [_p] * 9
     f = lib.thb_expect_scan; f.restype = _i; f.argtypes = [_p, _i, _i, _i] + [_p] * 9
@@ -169,6 +174,14 @@ class Context:
         ms = self.lib.thb_kernel_ms(self.h, which, C.byref(n), int(reset))
         return float(ms), int(n.value)
 
+    def timer_start(self):
+        self._chk(self.lib.thb_timer(self.h, 0, None))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._chk(self.lib.thb_timer(self.h, 1, C.byref(ms)))
+        return float(ms.value)
+
     # ---- geometry / resident data
     def set_expect_pixels(self, N, pf, iCol, iRow):
         iCol = _arr(iCol, np.int32); iRow = _arr(iRow, np.int32)
@@ -205,6 +218,20 @@ class Context:
             self.nImgE = nImg
         else:
             self.nImgM = nImg
+
+    def stack_reserve(self, kind, capacity):
+        self._chk(self.lib.thb_stack_reserve(self.h, kind, capacity))
+        if kind == STACK_EXPECT:
+            self.nImgE = capacity
+        else:
+            self.nImgM = capacity
+
+    def upload_stack_at(self, kind, base, dat, ctf, sigRcp=None, slotOfImg=None):
+        """arrays must already be C-contiguous complex64 / float32 (no copies: they may be pinned buffers)"""
+        nImg, P = dat.shape
+        assert dat.dtype == np.complex64 and dat.flags.c_contiguous and ctf.dtype == np.float32 and ctf.flags.c_contiguous
+        slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
+        self._chk(self.lib.thb_upload_stack_at(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sigRcp), _ptr(slotOfImg)))
 
     # ---- E
     def project(self, slot, quat):
@@ -286,20 +313,28 @@ class Context:
 
     def pf_get(self):
         n, R, T = self.nPar, self.pf_params.mLR, self.pf_params.mLT
-        r = np.empty((n, R, 4)); t = np.empty((n, T, 2)); wR = np.empty((n, R)); wT = np.empty((n, T)); scal = np.empty((n, 16))
+        r = np.empty((n, R, 4)); t = np.empty((n, T, 2)); wR = np.empty((n, R)); wT = np.empty((n, T)); scal = np.empty((n, 20))
         self._chk(self.lib.thb_pf_get(self.h, _ptr(r), _ptr(t), _ptr(wR), _ptr(wT), _ptr(scal)))
         return dict(r=r, t=t, wR=wR, wT=wT, scal=scal)
 
     def pf_get_scal(self):
-        scal = np.empty((self.nPar, 16))
+        scal = np.empty((self.nPar, 20))
         self._chk(self.lib.thb_pf_get(self.h, None, None, None, None, _ptr(scal)))
         return scal
 
     def pf_set(self, r=None, t=None, wR=None, wT=None, scal=None):
         n, R, T = self.nPar, self.pf_params.mLR, self.pf_params.mLT
         r = _arr(r, np.float64, (n, R, 4)); t = _arr(t, np.float64, (n, T, 2))
-        wR = _arr(wR, np.float64, (n, R)); wT = _arr(wT, np.float64, (n, T)); scal = _arr(scal, np.float64, (n, 16))
+        wR = _arr(wR, np.float64, (n, R)); wT = _arr(wT, np.float64, (n, T)); scal = _arr(scal, np.float64, (n, 20))
         self._chk(self.lib.thb_pf_set(self.h, _ptr(r), _ptr(t), _ptr(wR), _ptr(wT), _ptr(scal)))
+
+    def pf_set_image_base(self, imgBase, streamBase=0):
+        self._chk(self.lib.thb_pf_set_image_base(self.h, int(imgBase), int(streamBase)))
+
+    def pf_get_draws(self, mReco):
+        dR = np.empty((self.nPar, mReco), np.int32); dT = np.empty((self.nPar, mReco), np.int32)
+        self._chk(self.lib.thb_pf_get_draws(self.h, mReco, _ptr(dR), _ptr(dT)))
+        return dR, dT
 
     def expectation(self, want_phases=False):
         ph = np.zeros(self.nPar, np.int32) if want_phases else None

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cmath>
 #include <algorithm>
+#include <vector>
 #include "thb_context.h"
 #include "thb_kernels.cuh"
 
@@ -207,7 +208,7 @@ void thb_destroy(thb_ctx* ctx)
     }
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
-    cudaFree(ctx->pixE); cudaFree(ctx->pixM);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
     for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
@@ -220,6 +221,26 @@ int thb_synchronize(thb_ctx* ctx)
 {
     if (!ctx) return THB_E_ARG;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+// CUDA-event stopwatch on the library's launch stream (bench.py times its steps with it)
+int thb_timer(thb_ctx* ctx, int stop, float* ms)
+{
+    if (!ctx) return THB_E_ARG;
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!stop) {
+        if (!ctx->tA) { THB_CUDA(ctx, cudaEventCreate(&ctx->tA)); THB_CUDA(ctx, cudaEventCreate(&ctx->tB)); }
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        THB_CUDA(ctx, cudaEventRecord(ctx->tA, ctx->stream));
+        return THB_OK;
+    }
+    if (!ctx->tA) return set_error(ctx, THB_E_STATE, "timer: stop without start");
+    THB_CUDA(ctx, cudaEventRecord(ctx->tB, ctx->stream));
+    THB_CUDA(ctx, cudaEventSynchronize(ctx->tB));
+    float v = 0.f;
+    THB_CUDA(ctx, cudaEventElapsedTime(&v, ctx->tA, ctx->tB));
+    if (ms) *ms = v;
     return THB_OK;
 }
 
@@ -286,29 +307,59 @@ int thb_pixel_list(int N, int pf, float rU, float rL, int* iCol, int* iRow, int*
     return n;
 }
 
-static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst)
+// Blocked pixel order.  The reference walks the half-plane row by row; consecutive rows of one
+// orientation cloud then revisit the same volume neighbourhood only after a whole row of work, far
+// beyond L1/L2 reach.  The device keeps every per-pixel array in an order that walks 8x8-pixel
+// blocks boustrophedon (rows of blocks alternate direction), so the trilinear cells of consecutive
+// pixels stay inside a compact 3D neighbourhood.  Sums over pixels are order-independent up to fp32
+// rounding; per-pixel results handed back to the caller (thb_project) are un-permuted.
+static void blocked_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm)
+{
+    const int B = 8;
+    std::vector<long long> key(n);
+    for (int i = 0; i < n; ++i) {
+        const int x = a[i] / unit, y = b[i] / unit + (1 << 20);
+        const int by = y / B, bx = x / B;
+        const int sx = (by & 1) ? (1 << 16) - bx : bx;
+        const int iy = y % B, ix = (iy & 1) ? B - 1 - x % B : x % B;
+        key[i] = (((long long)by << 40) | ((long long)sx << 20) | (long long)(iy << 4 | ix));
+    }
+    perm.resize(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int l, int r) { return key[l] < key[r]; });
+}
+
+static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst, int** dperm)
 {
     if (nPxl <= 0 || !a || !b) return set_error(ctx, THB_E_ARG, "pixel list is empty or NULL");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> perm;
+    blocked_order(nPxl, a, b, padded ? pf : 1, perm);
     int* tmp = (int*)scratch(ctx, 0, sizeof(int) * 2 * (size_t)nPxl);
     if (!tmp) return THB_E_CUDA;
     THB_CUDA(ctx, cudaMemcpyAsync(tmp, a, sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(tmp + nPxl, b, sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
     if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (*dperm) { cudaFree(*dperm); *dperm = nullptr; }
     THB_CUDA(ctx, cudaMalloc(dst, sizeof(int4) * (size_t)nPxl));
-    make_pix_kernel<<<(nPxl + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + nPxl, nPxl, pf, padded, *dst);
+    THB_CUDA(ctx, cudaMalloc(dperm, sizeof(int) * (size_t)nPxl));
+    THB_CUDA(ctx, cudaMemcpyAsync(*dperm, perm.data(), sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
+    make_pix_kernel<<<(nPxl + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + nPxl, *dperm, nPxl, pf, padded, *dst);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
 
+static void free_stack(Stack& s);
+
 int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol, const int* iRow)
 {
     if (!ctx) return THB_E_ARG;
     if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_expect_pixels: bad N/pf");
-    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE);
+    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE);
     if (rc) return rc;
+    if (ctx->nPxlE != nPxl) free_stack(ctx->stackE);   // a resident stack belongs to one pixel list
     ctx->N = N; ctx->pf = pf; ctx->nPxlE = nPxl;
     return THB_OK;
 }
@@ -317,8 +368,9 @@ int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
 {
     if (!ctx) return THB_E_ARG;
     if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_insert_pixels: bad N/pf");
-    int rc = upload_pixels(ctx, pf, nPxl, iColPad, iRowPad, 1, &ctx->pixM);
+    int rc = upload_pixels(ctx, pf, nPxl, iColPad, iRowPad, 1, &ctx->pixM, &ctx->permM);
     if (rc) return rc;
+    if (ctx->nPxlM != nPxl) free_stack(ctx->stackM);
     ctx->NM = N; ctx->pfM = pf; ctx->nPxlM = nPxl;
     return THB_OK;
 }
@@ -355,40 +407,81 @@ int thb_get_volume(thb_ctx* ctx, int slot, float* volFT)
     return THB_OK;
 }
 
-int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf, const float* sigRcp,
-                     const int* slotOfImg)
+int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity)
+{
+    if (!ctx) return THB_E_ARG;
+    if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "stack_reserve: bad kind");
+    const int P = kind == THB_STACK_EXPECT ? ctx->nPxlE : ctx->nPxlM;
+    if (P <= 0) return set_error(ctx, THB_E_STATE, "stack_reserve: pixel list for this stack kind not set");
+    if (capacity <= 0) return set_error(ctx, THB_E_ARG, "stack_reserve: capacity <= 0");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    Stack& s = kind == THB_STACK_EXPECT ? ctx->stackE : ctx->stackM;
+    if (s.nImg == capacity && s.dat) return THB_OK;
+    free_stack(s);
+    const size_t n = (size_t)capacity * P;
+    THB_CUDA(ctx, cudaMalloc(&s.dat, n * sizeof(float2)));
+    THB_CUDA(ctx, cudaMalloc(&s.ctf, n * sizeof(float)));
+    if (kind == THB_STACK_EXPECT) THB_CUDA(ctx, cudaMalloc(&s.sig, n * sizeof(float)));
+    THB_CUDA(ctx, cudaMalloc(&s.slot, (size_t)capacity * sizeof(int)));
+    THB_CUDA(ctx, cudaMemsetAsync(s.slot, 0, (size_t)capacity * sizeof(int), ctx->stream));
+    s.nImg = capacity;
+    return THB_OK;
+}
+
+int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                        const int* slotOfImg)
 {
     if (!ctx) return THB_E_ARG;
     if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "upload_stack: bad kind");
     const int P = kind == THB_STACK_EXPECT ? ctx->nPxlE : ctx->nPxlM;
+    const int* perm = kind == THB_STACK_EXPECT ? ctx->permE : ctx->permM;
     if (P <= 0) return set_error(ctx, THB_E_STATE, "upload_stack: pixel list for this stack kind not set");
     if (nImg <= 0 || !dat || !ctf) return set_error(ctx, THB_E_ARG, "upload_stack: empty stack / NULL arrays");
     if (kind == THB_STACK_EXPECT && !sigRcp) return set_error(ctx, THB_E_ARG, "upload_stack: sigRcp required for the E stack");
-    THB_CUDA(ctx, cudaSetDevice(ctx->device));
     Stack& s = kind == THB_STACK_EXPECT ? ctx->stackE : ctx->stackM;
-    const size_t n = (size_t)nImg * P;
-    if (s.nImg != nImg) {
-        free_stack(s);
-        THB_CUDA(ctx, cudaMalloc(&s.dat, n * sizeof(float2)));
-        THB_CUDA(ctx, cudaMalloc(&s.ctf, n * sizeof(float)));
-        if (kind == THB_STACK_EXPECT) THB_CUDA(ctx, cudaMalloc(&s.sig, n * sizeof(float)));
-        THB_CUDA(ctx, cudaMalloc(&s.slot, (size_t)nImg * sizeof(int)));
-        s.nImg = nImg;
-    }
-    THB_CUDA(ctx, cudaMemcpyAsync(s.dat, dat, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    THB_CUDA(ctx, cudaMemcpyAsync(s.ctf, ctf, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (kind == THB_STACK_EXPECT)
-        THB_CUDA(ctx, cudaMemcpyAsync(s.sig, sigRcp, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (slotOfImg) {
+    if (!s.dat) return set_error(ctx, THB_E_STATE, "upload_stack: stack not reserved");
+    if (base < 0 || base + nImg > s.nImg) return set_error(ctx, THB_E_ARG, "upload_stack: images [%d,%d) exceed the capacity %d", base, base + nImg, s.nImg);
+    if (slotOfImg)
         for (int i = 0; i < nImg; ++i)
             if (slotOfImg[i] < 0 || slotOfImg[i] >= THB_MAX_SLOTS)
                 return set_error(ctx, THB_E_ARG, "upload_stack: slotOfImg[%d] = %d out of range", i, slotOfImg[i]);
-        THB_CUDA(ctx, cudaMemcpyAsync(s.slot, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        THB_CUDA(ctx, cudaMemsetAsync(s.slot, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // stage chunks of images in HBM, then permute each chunk into the resident blocked layout
+    const size_t perImg = (size_t)P * 16;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, ((size_t)256 << 20) / perImg));
+    float2* sdat = (float2*)scratch(ctx, 4, (size_t)chunk * P * sizeof(float2));
+    float* sctf = (float*)scratch(ctx, 5, (size_t)chunk * P * sizeof(float));
+    float* ssig = kind == THB_STACK_EXPECT ? (float*)scratch(ctx, 6, (size_t)chunk * P * sizeof(float)) : nullptr;
+    if (!sdat || !sctf || (kind == THB_STACK_EXPECT && !ssig)) return THB_E_CUDA;
+    for (int i0 = 0; i0 < nImg; i0 += chunk) {
+        const int c = std::min(chunk, nImg - i0);
+        const size_t off = (size_t)i0 * P, n = (size_t)c * P;
+        THB_CUDA(ctx, cudaMemcpyAsync(sdat, dat + 2 * off, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(sctf, ctf + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        if (ssig) THB_CUDA(ctx, cudaMemcpyAsync(ssig, sigRcp + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        const size_t doff = (size_t)(base + i0) * P;
+        dim3 grid(std::min((P + 255) / 256, 64), c);
+        span_begin(ctx, KF_PACK);
+        permute_stack_kernel<<<grid, 256, 0, ctx->stream>>>(sdat, sctf, ssig, perm, P, c, s.dat + doff, s.ctf + doff,
+                                                            ssig ? s.sig + doff : nullptr);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
     }
+    if (slotOfImg)
+        THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
+}
+
+int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                     const int* slotOfImg)
+{
+    int rc = thb_stack_reserve(ctx, kind, nImg);
+    if (rc) return rc;
+    return thb_upload_stack_at(ctx, kind, 0, nImg, dat, ctf, sigRcp, slotOfImg);
 }
 
 int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst)
@@ -405,7 +498,7 @@ int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst
     THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * 4 * (size_t)nRot, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((P + 255) / 256, nRot);
     span_begin(ctx, KF_EXPECT);
-    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->pixE, P, dq, dd);
+    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->pixE, ctx->permE, P, dq, dd);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());

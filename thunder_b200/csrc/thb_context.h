@@ -17,7 +17,7 @@ struct TimedSpan {
 };
 
 struct Stack {
-    int nImg = 0;
+    int nImg = 0;                // capacity (images)
     float2* dat = nullptr;
     float* ctf = nullptr;
     float* sig = nullptr;
@@ -44,7 +44,10 @@ struct PFState {
     double* t = nullptr;
     double* wR = nullptr;
     double* wT = nullptr;
-    double* scal = nullptr;      // [16][nPar]
+    double* scal = nullptr;      // [20][nPar]
+    double* dbl = nullptr;       // double scratch: uR, uT (as double), resampling buffers
+    int imgBase = 0;             // particle p <-> image imgBase + p of the resident stacks
+    uint64_t streamBase = 0;     // offset of the per-particle RNG stream (rank / batch offset)
     float* uR = nullptr;         // [nPar][mLR]
     float* uT = nullptr;         // [nPar][mLT]
     float* uC = nullptr;
@@ -68,8 +71,10 @@ struct thb_ctx {
 
     // pixel sets
     int N = 0, pf = 0, nPxlE = 0, nPxlM = 0, NM = 0, pfM = 0;
-    int4* pixE = nullptr;
+    int4* pixE = nullptr;        // device pixel lists, in the blocked order
     int4* pixM = nullptr;
+    int* permE = nullptr;        // blocked position -> caller's pixel index
+    int* permM = nullptr;
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];
     thb::Accum accs[thb::THB_MAX_SLOTS];
@@ -84,6 +89,7 @@ struct thb_ctx {
     int nRanks = 1, rank = 0;
 
     // accounting
+    cudaEvent_t tA = nullptr, tB = nullptr;
     int64_t launches = 0;
     bool timing = false;
     std::vector<thb::TimedSpan> spans;

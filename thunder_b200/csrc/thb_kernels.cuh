@@ -48,8 +48,9 @@ __device__ __forceinline__ float2 gather_ft(const float2* __restrict__ vol, int 
 // ------------------------------------------------------------------------------------------------
 // Projector::project for many rotations (src/Projector.cpp:356-374); lanes = pixels
 // ------------------------------------------------------------------------------------------------
-__global__ void project_kernel(const float2* __restrict__ vol, int n, const int4* __restrict__ pix, int P,
-                               const double* __restrict__ quat, float2* __restrict__ dst)
+__global__ void project_kernel(const float2* __restrict__ vol, int n, const int4* __restrict__ pix,
+                               const int* __restrict__ perm, int P, const double* __restrict__ quat,
+                               float2* __restrict__ dst)
 {
     const int r = blockIdx.y;
     double q[4] = {quat[4 * r], quat[4 * r + 1], quat[4 * r + 2], quat[4 * r + 3]};
@@ -59,7 +60,7 @@ __global__ void project_kernel(const float2* __restrict__ vol, int n, const int4
         const int4 px = pix[i];
         float x, y, z;
         slice_coord(rot, (double)px.x, (double)px.y, x, y, z);
-        dst[(size_t)r * P + i] = gather_ft(vol, n, nColFT, x, y, z);
+        dst[(size_t)r * P + perm[i]] = gather_ft(vol, n, nColFT, x, y, z);   // caller's pixel order
     }
 }
 
@@ -345,15 +346,32 @@ __global__ void unpack_acc_kernel(const float4* __restrict__ acc, size_t nVox, f
     }
 }
 
-__global__ void make_pix_kernel(const int* __restrict__ a, const int* __restrict__ b, int P, int pf, int padded,
-                                int4* __restrict__ out)
+// pixel list in the device (blocked) order: out[i] describes the caller's pixel perm[i]
+__global__ void make_pix_kernel(const int* __restrict__ a, const int* __restrict__ b, const int* __restrict__ perm, int P,
+                                int pf, int padded, int4* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    const int s = perm[i];
     if (padded)
-        out[i] = make_int4(a[i], b[i], a[i] / pf, b[i] / pf);
+        out[i] = make_int4(a[s], b[s], a[s] / pf, b[s] / pf);
     else
-        out[i] = make_int4(a[i] * pf, b[i] * pf, a[i], b[i]);
+        out[i] = make_int4(a[s] * pf, b[s] * pf, a[s], b[s]);
+}
+
+// resident stack = caller's image-major packed arrays with the pixels of each image permuted into
+// the blocked order: dst[l][i] = src[l][perm[i]]
+__global__ void permute_stack_kernel(const float2* __restrict__ sdat, const float* __restrict__ sctf,
+                                     const float* __restrict__ ssig, const int* __restrict__ perm, int P, int nImg,
+                                     float2* __restrict__ ddat, float* __restrict__ dctf, float* __restrict__ dsig)
+{
+    const int l = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const size_t s = (size_t)l * P + perm[i], d = (size_t)l * P + i;
+        ddat[d] = sdat[s];
+        dctf[d] = sctf[s];
+        if (ssig) dsig[d] = ssig[s];
+    }
 }
 
 }  // namespace thb

@@ -1,11 +1,470 @@
-// placeholder - replaced by the device particle filter
+// thb_pf.cu - device-resident particle filter and the iteration-level drivers built on it:
+// thb_expectation (phase loop of Optimiser::expectation, src/Optimiser.cpp:1162-1660) and
+// thb_reconstruct_insert (insert loop of Optimiser::reconstructRef, src/Optimiser.cpp:7036-7241).
+// One CUDA thread per particle runs the serial operators of thb_pf.cuh on the SoA state; the fused
+// E kernel reads rotations / translations / priors straight from that state and writes the marginal
+// weights back, so a whole E-step needs no host round trip per phase (the reference's GPU path
+// crosses PCIe per image per phase, src/Optimiser.cpp:2813-3300).
+#include <cstring>
+#include <vector>
 #include "thb_context.h"
-namespace thb { void pf_free(thb_ctx*) {} }
-extern "C" {
-int thb_pf_load(thb_ctx* c, int, const thb_pf_params*, const double*, const double*, const double*, const double*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
-int thb_pf_get(thb_ctx* c, double*, double*, double*, double*, double*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
-int thb_pf_set(thb_ctx* c, const double*, const double*, const double*, const double*, const double*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
-int thb_expectation(thb_ctx* c, int*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
-int thb_reconstruct_insert(thb_ctx* c, int, int, const double*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
-int thb_pf_op(thb_ctx* c, int, double, const float*, const float*) { return thb::set_error(c, THB_E_STATE, "pf: not built"); }
+#include "thb_pf.cuh"
+
+namespace thb {
+
+struct PFDev {
+    double *r, *t, *wR, *wT, *uR, *uT, *scal, *r2, *t2, *w2;
+    const float *uRf, *uTf;
+    unsigned char* active;
+    int* nPhase;
+    int* activeCount;
+    int nPar, mLR, mLT;
+    uint64_t seed, streamBase;
+};
+
+__device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
+{
+    pf::View v;
+    v.r = d.r; v.t = d.t; v.wR = d.wR; v.wT = d.wT; v.uR = d.uR; v.uT = d.uT; v.scal = d.scal;
+    v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2;
+    v.n = d.nPar; v.p = p; v.mLR = d.mLR; v.mLT = d.mLT;
+    return v;
 }
+
+__global__ void pf_load_kernel(PFDev d, uint64_t epoch, const double* quat, const double* k123, const double* tran,
+                               const double* s01)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nPar) return;
+    pf::View v = make_view(d, p);
+    pf::Rng g;
+    g.init(d.seed, d.streamBase + p, epoch);
+    pf::load(v, quat + 4 * p, k123[3 * p], k123[3 * p + 1], k123[3 * p + 2], tran + 2 * p, s01[2 * p], s01[2 * p + 1], g);
+    d.active[p] = 1;
+    d.nPhase[p] = 0;
+}
+
+// begin an E-step: per-iteration stop-rule state
+__global__ void pf_begin_kernel(PFDev d)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nPar) return;
+    pf::View v = make_view(d, p);
+    v.S(pf::S_VARIR) = 1.79769313486231570e308;
+    v.S(pf::S_VARIT) = 1.79769313486231570e308;
+    v.S(pf::S_VARID) = 1.79769313486231570e308;
+    v.S(pf::S_NODEC) = 0.0;
+    v.S(pf::S_NPHASE) = 0.0;
+    d.active[p] = 1;
+    d.nPhase[p] = 0;
+}
+
+struct StepArgs {
+    int doPost, doPre;
+    int phase;              // phase whose likelihoods were just computed (doPost)
+    double prePf;           // perturbation factor of the next perturb (doPre)
+    double transS, transQ;
+    int minPhase, maxPhase, fixedPhases, noDecreaseLimit;
+    double decreaseFactor;
+    uint64_t epoch;
+};
+
+__global__ void pf_step_kernel(PFDev d, StepArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nPar) return;
+    if (!d.active[p]) return;
+    pf::View v = make_view(d, p);
+    pf::Rng g;
+    g.init(d.seed, d.streamBase + p, a.epoch);
+    bool cont = true;
+    if (a.doPost) {
+        pf::set_u_keep_peak(v, d.uRf + (size_t)p * d.mLR, d.uTf + (size_t)p * d.mLT);
+        pf::rank1st(v);
+        pf::cal_vari(v, g);
+        pf::resample_R(v, g);
+        pf::resample_T(v, g);
+        pf::norm_w(v);
+        d.nPhase[p] = a.phase + 1;
+        v.S(pf::S_NPHASE) = (double)(a.phase + 1);
+        bool done;
+        if (a.fixedPhases > 0)
+            done = a.phase + 1 >= a.fixedPhases;
+        else
+            done = pf::stop_rule(v, a.phase, a.minPhase, a.decreaseFactor, a.noDecreaseLimit) || a.phase + 1 >= a.maxPhase;
+        if (done) {
+            d.active[p] = 0;
+            v.S(pf::S_SCORE) = pf::compress_R(v);   // calScore() at the start of reconstructRef
+            cont = false;
+        }
+    }
+    if (cont && a.doPre) {
+        pf::perturb_R(v, a.prePf, g);
+        pf::perturb_T(v, a.prePf, a.transS, a.transQ, g);
+        atomicAdd(d.activeCount, 1);
+    }
+}
+
+// Particle::rand(cls, quat, tran, d) x mReco: independent uniform draws of support indices
+__global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, int* drawR, int* drawT, float* w)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nPar) return;
+    pf::View v = make_view(d, p);
+    pf::Rng g;
+    g.init(d.seed, d.streamBase + p, epoch);
+    for (int m = 0; m < mReco; ++m) {
+        (void)g.uniform_int(1);                                   // class
+        drawR[(size_t)p * mReco + m] = (int)g.uniform_int((uint32_t)d.mLR);
+        drawT[(size_t)p * mReco + m] = (int)g.uniform_int((uint32_t)d.mLT);
+        (void)g.uniform_int(1);                                   // defocus
+    }
+    const double ww = parGra ? pf::compress_R(v) : 1.0;
+    w[p] = (float)ww / (float)mReco;                              // RFLOAT w; w /= mReco
+}
+
+__global__ void pf_op_kernel(PFDev d, int op, double arg, double transS, double transQ, uint64_t epoch)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nPar) return;
+    pf::View v = make_view(d, p);
+    pf::Rng g;
+    g.init(d.seed, d.streamBase + p, epoch);
+    switch (op) {
+        case THB_PF_PERTURB_R: pf::perturb_R(v, arg, g); break;
+        case THB_PF_PERTURB_T: pf::perturb_T(v, arg, transS, transQ, g); break;
+        case THB_PF_SET_U_KEEP_PEAK: pf::set_u_keep_peak(v, d.uRf + (size_t)p * d.mLR, d.uTf + (size_t)p * d.mLT); break;
+        case THB_PF_RANK1ST: pf::rank1st(v); break;
+        case THB_PF_CALVARI: pf::cal_vari(v, g); break;
+        case THB_PF_RESAMPLE: pf::resample_R(v, g); pf::resample_T(v, g); pf::norm_w(v); break;
+        case THB_PF_BALANCE_R: pf::balance_R(v); break;
+        case THB_PF_BALANCE_T: pf::balance_T(v); break;
+        default: break;
+    }
+}
+
+void pf_free(thb_ctx* ctx)
+{
+    PFState& s = ctx->pf_;
+    cudaFree(s.r); cudaFree(s.t); cudaFree(s.wR); cudaFree(s.wT); cudaFree(s.scal);
+    cudaFree(s.uR); cudaFree(s.uT); cudaFree(s.uC); cudaFree(s.base); cudaFree(s.active); cudaFree(s.nPhase);
+    cudaFree(s.vari); cudaFree(s.drawR); cudaFree(s.drawT);
+    cudaFree(s.dbl);
+    s = PFState();
+}
+
+static PFDev dev_view(thb_ctx* ctx)
+{
+    PFState& s = ctx->pf_;
+    PFDev d;
+    const size_t n = s.nPar;
+    d.r = s.r; d.t = s.t; d.wR = s.wR; d.wT = s.wT; d.scal = s.scal;
+    // dbl: [uR mLR][uT mLT][r2 4 mLR][t2 2 mLT][w2 max(mLR,mLT)] x nPar doubles
+    double* q = s.dbl;
+    d.uR = q; q += n * s.prm.mLR;
+    d.uT = q; q += n * s.prm.mLT;
+    d.r2 = q; q += n * 4 * s.prm.mLR;
+    d.t2 = q; q += n * 2 * s.prm.mLT;
+    d.w2 = q;
+    d.uRf = s.uR; d.uTf = s.uT;
+    d.active = s.active; d.nPhase = s.nPhase; d.activeCount = (int*)s.vari;
+    d.nPar = s.nPar; d.mLR = s.prm.mLR; d.mLT = s.prm.mLT;
+    d.seed = s.prm.seed; d.streamBase = s.streamBase;
+    return d;
+}
+
+static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
+{
+    PFState& s = ctx->pf_;
+    if (s.nPar == nPar && s.prm.mLR == p.mLR && s.prm.mLT == p.mLT && s.r) {
+        s.prm = p;
+        return THB_OK;
+    }
+    pf_free(ctx);
+    const size_t n = nPar;
+    const int mw = p.mLR > p.mLT ? p.mLR : p.mLT;
+    THB_CUDA(ctx, cudaMalloc(&s.r, sizeof(double) * n * 4 * p.mLR));
+    THB_CUDA(ctx, cudaMalloc(&s.t, sizeof(double) * n * 2 * p.mLT));
+    THB_CUDA(ctx, cudaMalloc(&s.wR, sizeof(double) * n * p.mLR));
+    THB_CUDA(ctx, cudaMalloc(&s.wT, sizeof(double) * n * p.mLT));
+    THB_CUDA(ctx, cudaMalloc(&s.scal, sizeof(double) * n * pf::S_COUNT));
+    THB_CUDA(ctx, cudaMalloc(&s.dbl, sizeof(double) * n * (size_t)(5 * p.mLR + 3 * p.mLT + mw)));
+    THB_CUDA(ctx, cudaMalloc(&s.uR, sizeof(float) * n * p.mLR));
+    THB_CUDA(ctx, cudaMalloc(&s.uT, sizeof(float) * n * p.mLT));
+    THB_CUDA(ctx, cudaMalloc(&s.uC, sizeof(float) * n));
+    THB_CUDA(ctx, cudaMalloc(&s.base, sizeof(float) * n));
+    THB_CUDA(ctx, cudaMalloc(&s.active, n));
+    THB_CUDA(ctx, cudaMalloc(&s.nPhase, sizeof(int) * n));
+    THB_CUDA(ctx, cudaMalloc(&s.vari, sizeof(double) * 4));
+    THB_CUDA(ctx, cudaMemset(s.scal, 0, sizeof(double) * n * pf::S_COUNT));
+    s.nPar = nPar;
+    s.prm = p;
+    return THB_OK;
+}
+
+// [nPar][S][C] (API, host) <-> [(c*S + i)*nPar + p] (device SoA)
+static void to_soa(const double* aos, double* soa, size_t nPar, int S, int Cn)
+{
+#pragma omp parallel for
+    for (long long p = 0; p < (long long)nPar; ++p)
+        for (int i = 0; i < S; ++i)
+            for (int c = 0; c < Cn; ++c) soa[((size_t)c * S + i) * nPar + p] = aos[((size_t)p * S + i) * Cn + c];
+}
+static void to_aos(const double* soa, double* aos, size_t nPar, int S, int Cn)
+{
+#pragma omp parallel for
+    for (long long p = 0; p < (long long)nPar; ++p)
+        for (int i = 0; i < S; ++i)
+            for (int c = 0; c < Cn; ++c) aos[((size_t)p * S + i) * Cn + c] = soa[((size_t)c * S + i) * nPar + p];
+}
+
+}  // namespace thb
+
+using namespace thb;
+
+static inline int nblk(int n) { return (n + 63) / 64; }
+
+extern "C" {
+
+int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* quat, const double* k123, const double* tran,
+                const double* s01)
+{
+    if (!ctx) return THB_E_ARG;
+    if (nPar <= 0 || !p || !quat || !k123 || !tran || !s01 || p->mLR < 2 || p->mLT < 2)
+        return set_error(ctx, THB_E_ARG, "pf_load: bad arguments");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = pf_alloc(ctx, nPar, *p);
+    if (rc) return rc;
+    PFState& s = ctx->pf_;
+    const size_t n = nPar;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * n * 11);
+    if (!din) return THB_E_CUDA;
+    THB_CUDA(ctx, cudaMemcpyAsync(din, quat, sizeof(double) * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(din + 4 * n, k123, sizeof(double) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(din + 7 * n, tran, sizeof(double) * n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(din + 9 * n, s01, sizeof(double) * n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    s.epoch += 1;
+    span_begin(ctx, KF_PF);
+    pf_load_kernel<<<nblk(nPar), 64, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, din, din + 4 * n, din + 7 * n, din + 9 * n);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_pf_set_image_base(thb_ctx* ctx, int imgBase, uint64_t streamBase)
+{
+    if (!ctx) return THB_E_ARG;
+    ctx->pf_.imgBase = imgBase;
+    ctx->pf_.streamBase = streamBase;
+    return THB_OK;
+}
+
+int thb_pf_get(thb_ctx* ctx, double* r, double* t, double* wR, double* wT, double* scal)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r) return set_error(ctx, THB_E_STATE, "pf_get: no particles loaded");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = s.nPar;
+    std::vector<double> tmp;
+    auto fetch = [&](const double* dsrc, double* dst, int S, int Cn) -> int {
+        if (!dst) return THB_OK;
+        tmp.resize(n * S * Cn);
+        THB_CUDA(ctx, cudaMemcpy(tmp.data(), dsrc, sizeof(double) * n * S * Cn, cudaMemcpyDeviceToHost));
+        to_aos(tmp.data(), dst, n, S, Cn);
+        return THB_OK;
+    };
+    int rc;
+    if ((rc = fetch(s.r, r, s.prm.mLR, 4))) return rc;
+    if ((rc = fetch(s.t, t, s.prm.mLT, 2))) return rc;
+    if ((rc = fetch(s.wR, wR, s.prm.mLR, 1))) return rc;
+    if ((rc = fetch(s.wT, wT, s.prm.mLT, 1))) return rc;
+    if ((rc = fetch(s.scal, scal, pf::S_COUNT, 1))) return rc;
+    return THB_OK;
+}
+
+int thb_pf_set(thb_ctx* ctx, const double* r, const double* t, const double* wR, const double* wT, const double* scal)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r) return set_error(ctx, THB_E_STATE, "pf_set: no particles loaded");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = s.nPar;
+    std::vector<double> tmp;
+    auto put = [&](const double* src, double* ddst, int S, int Cn) -> int {
+        if (!src) return THB_OK;
+        tmp.resize(n * S * Cn);
+        to_soa(src, tmp.data(), n, S, Cn);
+        THB_CUDA(ctx, cudaMemcpy(ddst, tmp.data(), sizeof(double) * n * S * Cn, cudaMemcpyHostToDevice));
+        return THB_OK;
+    };
+    int rc;
+    if ((rc = put(r, s.r, s.prm.mLR, 4))) return rc;
+    if ((rc = put(t, s.t, s.prm.mLT, 2))) return rc;
+    if ((rc = put(wR, s.wR, s.prm.mLR, 1))) return rc;
+    if ((rc = put(wT, s.wT, s.prm.mLT, 1))) return rc;
+    if ((rc = put(scal, s.scal, pf::S_COUNT, 1))) return rc;
+    return THB_OK;
+}
+
+static int expect_args_from_pf(thb_ctx* ctx, ExpectArgs& a)
+{
+    PFState& s = ctx->pf_;
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->vols[i].d) vdim = ctx->vols[i].vdim;
+    if (!vdim || !ctx->pixE || !ctx->stackE.dat) return set_error(ctx, THB_E_STATE, "expectation: volume / pixels / E stack missing");
+    if (s.imgBase < 0 || s.imgBase + s.nPar > ctx->stackE.nImg)
+        return set_error(ctx, THB_E_STATE, "expectation: particles [%d,%d) exceed the E stack (%d images)", s.imgBase,
+                         s.imgBase + s.nPar, ctx->stackE.nImg);
+    memset(&a, 0, sizeof(a));
+    a.vols = vol_table(ctx); a.vdim = vdim;
+    a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
+    a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
+    a.nAct = s.nPar; a.imgIdx = nullptr; a.imgBase = s.imgBase; a.active = s.active;
+    a.nR = s.prm.mLR; a.nT = s.prm.mLT;
+    const long long n = s.nPar;
+    a.quat = View3{s.r, 1, n, n * s.prm.mLR};
+    a.tran = View3{s.t, 1, n, n * s.prm.mLT};
+    a.wR = View3{s.wR, 1, n, 0};
+    a.wT = View3{s.wT, 1, n, 0};
+    a.uR = s.uR; a.uT = s.uT; a.uC = s.uC; a.base = s.base; a.logL = nullptr;
+    return THB_OK;
+}
+
+int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r) return set_error(ctx, THB_E_STATE, "expectation: no particles loaded (thb_pf_load)");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ExpectArgs ea;
+    int rc = expect_args_from_pf(ctx, ea);
+    if (rc) return rc;
+    const thb_pf_params& p = s.prm;
+    PFDev d = dev_view(ctx);
+    const int nb = nblk(s.nPar);
+    s.epoch += 1;
+    StepArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.transS = p.transS; sa.transQ = p.transQ;
+    sa.minPhase = p.minPhase; sa.maxPhase = p.maxPhase; sa.fixedPhases = p.fixedPhases;
+    sa.noDecreaseLimit = p.noDecreaseLimit; sa.decreaseFactor = p.decreaseFactor;
+
+    span_begin(ctx, KF_PF);
+    pf_begin_kernel<<<nb, 64, 0, ctx->stream>>>(d);
+    sa.doPost = 0; sa.doPre = 1; sa.phase = -1; sa.prePf = p.perturbFactorL; sa.epoch = (s.epoch << 20);
+    THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
+    pf_step_kernel<<<nb, 64, 0, ctx->stream>>>(d, sa);
+    span_end(ctx);
+    ctx->launches += 2;
+    const int phaseMax = p.fixedPhases > 0 ? p.fixedPhases : p.maxPhase;
+    for (int phase = 0; phase < phaseMax; ++phase) {
+        rc = launch_expect_local(ctx, ea);
+        if (rc) return rc;
+        sa.doPost = 1; sa.doPre = (phase + 1 < phaseMax); sa.phase = phase; sa.prePf = p.perturbFactorS;
+        sa.epoch = (s.epoch << 20) + (uint64_t)(phase + 1);
+        THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
+        span_begin(ctx, KF_PF);
+        pf_step_kernel<<<nb, 64, 0, ctx->stream>>>(d, sa);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+        if (p.fixedPhases <= 0) {
+            int act = 0;
+            THB_CUDA(ctx, cudaMemcpyAsync(&act, d.activeCount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (act == 0) break;
+        }
+    }
+    if (nPhaseOut) THB_CUDA(ctx, cudaMemcpyAsync(nPhaseOut, s.nPhase, sizeof(int) * s.nPar, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* offS)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r) return set_error(ctx, THB_E_STATE, "reconstruct_insert: no particles loaded");
+    if (mReco <= 0) return set_error(ctx, THB_E_ARG, "reconstruct_insert: mReco <= 0");
+    if (!ctx->pixM || !ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "reconstruct_insert: M pixels / stack missing");
+    if (s.imgBase < 0 || s.imgBase + s.nPar > ctx->stackM.nImg) return set_error(ctx, THB_E_STATE, "reconstruct_insert: particles exceed the M stack");
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->accs[i].d) vdim = ctx->accs[i].vdim;
+    if (!vdim) return set_error(ctx, THB_E_STATE, "reconstruct_insert: no accumulator allocated");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = s.nPar;
+    if (s.drawCap < mReco) {
+        cudaFree(s.drawR); cudaFree(s.drawT);
+        s.drawR = s.drawT = nullptr;
+        THB_CUDA(ctx, cudaMalloc(&s.drawR, sizeof(int) * n * mReco));
+        THB_CUDA(ctx, cudaMalloc(&s.drawT, sizeof(int) * n * mReco));
+        s.drawCap = mReco;
+    }
+    float* dw = (float*)scratch(ctx, 0, sizeof(float) * n + sizeof(double) * 2 * n + 64);
+    if (!dw) return THB_E_CUDA;
+    double* doff = (double*)(dw + ((n + 3) / 4) * 4);
+    if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    s.epoch += 1;
+    span_begin(ctx, KF_PF);
+    pf_draw_kernel<<<nblk(s.nPar), 64, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, mReco, parGra, s.drawR, s.drawT, dw);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+
+    InsertArgs a;
+    memset(&a, 0, sizeof(a));
+    a.acc = acc_table(ctx); a.vdim = vdim;
+    a.dat = ctx->stackM.dat; a.ctf = ctx->stackM.ctf; a.slotOfImg = ctx->stackM.slot;
+    a.pix = ctx->pixM; a.P = ctx->nPxlM; a.N = ctx->NM;
+    a.nImg = s.nPar; a.imgIdx = nullptr; a.imgBase = s.imgBase;
+    a.mReco = mReco; a.w = dw; a.offS = offS ? doff : nullptr;
+    const long long nn = s.nPar;
+    a.nr = View3{s.r, 1, nn, nn * s.prm.mLR};
+    a.nt = View3{s.t, 1, nn, nn * s.prm.mLT};
+    a.drawR = s.drawR; a.drawT = s.drawT;
+    int rc = launch_insert(ctx, a);
+    if (rc) return rc;
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_pf_get_draws(thb_ctx* ctx, int mReco, int* drawR, int* drawT)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.drawR || mReco > s.drawCap) return set_error(ctx, THB_E_STATE, "pf_get_draws: no draws of that size");
+    THB_CUDA(ctx, cudaMemcpy(drawR, s.drawR, sizeof(int) * (size_t)s.nPar * mReco, cudaMemcpyDeviceToHost));
+    THB_CUDA(ctx, cudaMemcpy(drawT, s.drawT, sizeof(int) * (size_t)s.nPar * mReco, cudaMemcpyDeviceToHost));
+    return THB_OK;
+}
+
+int thb_pf_op(thb_ctx* ctx, int op, double arg, const float* uR, const float* uT)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r) return set_error(ctx, THB_E_STATE, "pf_op: no particles loaded");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = s.nPar;
+    if (op == THB_PF_SET_U_KEEP_PEAK) {
+        if (!uR || !uT) return set_error(ctx, THB_E_ARG, "pf_op: uR/uT required");
+        THB_CUDA(ctx, cudaMemcpyAsync(s.uR, uR, sizeof(float) * n * s.prm.mLR, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(s.uT, uT, sizeof(float) * n * s.prm.mLT, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    s.epoch += 1;
+    span_begin(ctx, KF_PF);
+    pf_op_kernel<<<nblk(s.nPar), 64, 0, ctx->stream>>>(dev_view(ctx), op, arg, s.prm.transS, s.prm.transQ, s.epoch << 20);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+// thb_pf.cuh - the per-image particle filter (host side of the reference: class Particle),
+// restated as serial per-particle code that runs one particle per CUDA thread on the device-
+// resident SoA state.  Everything is host+device inline so that tests/ can compile the same
+// operators with g++ and compare them with the reference's Particle / DirectionalStat.
+//
+// reference (paths relative to the THUNDER tree):
+//   perturb            src/Particle.cpp:1149-1289        resample         src/Particle.cpp:1291-1478
+//   calVari            src/Particle.cpp:1004-1142        keepHalfHeightPeak :1964-2002
+//   calRank1st         src/Particle.cpp:990-1002         balanceWeight    :2309-2410
+//   reCentre           src/Particle.cpp:2473-2495        shuffle          :2202-2300
+//   rand               src/Particle.cpp:2109-2200        load             :401-556
+//   variR/variT/compressR :611-667
+//   sampleACG / inferACG / pdfACG   src/Geometry/DirectionalStat.cpp:19-250
+//   quaternion_mul     src/Geometry/Euler.cpp:13-26
+// Default Config.h switches in force: PARTICLE_PRIOR_ONE, PARTICLE_RECENTRE(_TRANSQ),
+// PARTICLE_ROT_MEAN_USING_STAT_CAL_VARI / _PERTURB, PARTICLE_BALANCE_WEIGHT_R/T; PARTICLE_RHO off.
+// The random stream is a counter-based Philox4x32-10 keyed by (seed, particle, epoch) instead of the
+// reference's thread-local urandom-seeded mt19937 (src/Functions/Random.cpp:51-100): draws are
+// distributed identically but are not the same numbers, so stochastic operators are tested
+// statistically and deterministic ones exactly.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "thb_math.cuh"
+
+namespace thb {
+namespace pf {
+
+enum { S_K1 = 0, S_K2, S_K3, S_S0, S_S1, S_RHO, S_TOPR, S_TOPT = 10, S_SCORE = 12, S_NPHASE = 13, S_VARIR = 14, S_VARIT = 15,
+       S_PEAKR = 16, S_NODEC = 17, S_VARID = 18, S_SPARE = 19, S_COUNT = 20 };
+
+// ------------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t k0, k1;
+    uint32_t c[4];
+    uint32_t o[4];
+    int have;
+    double spare;
+    bool hasSpare;
+
+    THB_HD void init(uint64_t seed, uint64_t stream, uint64_t epoch)
+    {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        c[0] = 0; c[1] = (uint32_t)epoch; c[2] = (uint32_t)stream; c[3] = (uint32_t)(stream >> 32) ^ (uint32_t)(epoch >> 32);
+        have = 0; hasSpare = false; spare = 0.0;
+    }
+    THB_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
+    {
+        const uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+    }
+    THB_HD void block()
+    {
+        uint32_t x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], a = k0, b = k1;
+        for (int r = 0; r < 10; ++r) {
+            uint32_t h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, x0, h0, l0);
+            mulhilo(0xCD9E8D57u, x2, h1, l1);
+            const uint32_t y0 = h1 ^ x1 ^ a, y1 = l1, y2 = h0 ^ x3 ^ b, y3 = l0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        o[0] = x0; o[1] = x1; o[2] = x2; o[3] = x3;
+        c[0]++;
+        have = 4;
+    }
+    THB_HD uint32_t u32()
+    {
+        if (have == 0) block();
+        return o[--have];
+    }
+    THB_HD double uniform()   // (0,1), 53 bits
+    {
+        const uint64_t hi = u32(), lo = u32();
+        const uint64_t v = ((hi << 32) | lo) >> 11;
+        return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    THB_HD uint32_t uniform_int(uint32_t n) { return n <= 1 ? 0u : (uint32_t)(uniform() * n) % n; }
+    THB_HD double normal()
+    {
+        if (hasSpare) { hasSpare = false; return spare; }
+        const double u1 = uniform(), u2 = uniform();
+        const double r = sqrt(-2.0 * log(u1));
+        double s, c2;
+        sincos(6.283185307179586 * u2, &s, &c2);
+        spare = r * s; hasSpare = true;
+        return r * c2;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// strided view of one particle in the SoA state
+struct View {
+    double* r; double* t; double* wR; double* wT; double* uR; double* uT; double* scal;
+    double* r2; double* t2; double* w2;      // resampling scratch, same layout as r / t / wR
+    long long n;   // stride between consecutive samples/components = number of particles
+    long long p;   // particle index
+    int mLR, mLT;
+    THB_HD double& R(int i, int c) const { return r[((long long)c * mLR + i) * n + p]; }
+    THB_HD double& T(int i, int c) const { return t[((long long)c * mLT + i) * n + p]; }
+    THB_HD double& R2(int i, int c) const { return r2[((long long)c * mLR + i) * n + p]; }
+    THB_HD double& T2(int i, int c) const { return t2[((long long)c * mLT + i) * n + p]; }
+    THB_HD double& W2(int i) const { return w2[(long long)i * n + p]; }
+    THB_HD double& WR(int i) const { return wR[(long long)i * n + p]; }
+    THB_HD double& WT(int i) const { return wT[(long long)i * n + p]; }
+    THB_HD double& UR(int i) const { return uR[(long long)i * n + p]; }
+    THB_HD double& UT(int i) const { return uT[(long long)i * n + p]; }
+    THB_HD double& S(int k) const { return scal[(long long)k * n + p]; }
+};
+
+THB_HD void quat_mul(double d[4], const double a[4], const double b[4])
+{
+    const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    const double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    d[0] = w; d[1] = x; d[2] = y; d[3] = z;
+}
+
+// 4x4 inverse by cofactors (row-major); returns the determinant
+THB_HD double inv4(const double m[16], double inv[16])
+{
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const double id = 1.0 / det;
+    for (int i = 0; i < 16; ++i) inv[i] *= id;
+    return det;
+}
+
+THB_HD double quad_form(const double Ai[16], const double x[4])
+{
+    double s = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < 4; ++j) row += Ai[i * 4 + j] * x[j];
+        s += x[i] * row;
+    }
+    return s;
+}
+
+// inferACG(dmat44& dst, const dmat4& src): fixed-point iteration, returns the LAST-BUT-ONE iterate
+// exactly as the reference does (dst = A).  DirectionalStat.cpp:93-145
+THB_HD void infer_acg(const View& v, double A[16])
+{
+    double B[16];
+    for (int i = 0; i < 16; ++i) B[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    double diff;
+    int iter = 0;
+    do {
+        for (int i = 0; i < 16; ++i) A[i] = B[i];
+        double Ai[16];
+        inv4(A, Ai);
+        for (int i = 0; i < 16; ++i) B[i] = 0.0;
+        double nf = 0.0;
+        for (int s = 0; s < v.mLR; ++s) {
+            const double x[4] = {v.R(s, 0), v.R(s, 1), v.R(s, 2), v.R(s, 3)};
+            const double u = quad_form(Ai, x);
+            const double iu = 1.0 / u;
+            for (int j = 0; j < 4; ++j)
+                for (int k = 0; k < 4; ++k) B[j * 4 + k] += x[j] * x[k] / u;
+            nf += iu;
+        }
+        const double sc = 4.0 / nf;
+        diff = 0.0;
+        for (int i = 0; i < 16; ++i) {
+            B[i] *= sc;
+            diff += fabs(A[i] - B[i]);
+        }
+    } while (diff > 1e-3 && ++iter < 500);
+}
+
+// eigenvector of the largest eigenvalue of a symmetric 4x4 (cyclic Jacobi); unit norm.
+// (the reference uses Eigen::SelfAdjointEigenSolver; the sign of the vector is immaterial, see perturb)
+THB_HD void sym4_top_eigvec(const double Ain[16], double vec[4])
+{
+    double a[16], V[16];
+    for (int i = 0; i < 16; ++i) { a[i] = Ain[i]; V[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int i = 0; i < 4; ++i)
+            for (int j = i + 1; j < 4; ++j) off += a[i * 4 + j] * a[i * 4 + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = a[p * 4 + q];
+                if (fabs(apq) < 1e-300) continue;
+                const double theta = (a[q * 4 + q] - a[p * 4 + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 4; ++k) {
+                    const double akp = a[k * 4 + p], akq = a[k * 4 + q];
+                    a[k * 4 + p] = c * akp - s * akq;
+                    a[k * 4 + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const double apk = a[p * 4 + k], aqk = a[q * 4 + k];
+                    a[p * 4 + k] = c * apk - s * aqk;
+                    a[q * 4 + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const double vkp = V[k * 4 + p], vkq = V[k * 4 + q];
+                    V[k * 4 + p] = c * vkp - s * vkq;
+                    V[k * 4 + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 4; ++i)
+        if (a[i * 4 + i] > a[best * 4 + best]) best = i;
+    double nrm = 0.0;
+    for (int k = 0; k < 4; ++k) { vec[k] = V[k * 4 + best]; nrm += vec[k] * vec[k]; }
+    nrm = 1.0 / sqrt(nrm);
+    for (int k = 0; k < 4; ++k) vec[k] *= nrm;
+}
+
+THB_HD void acg_mean(const View& v, double mean[4])
+{
+    double A[16];
+    infer_acg(v, A);
+    sym4_top_eigvec(A, mean);
+}
+
+// left-multiply every rotation by q (conj = use the conjugate of q)
+THB_HD void left_mul_all(const View& v, const double q[4], bool conj)
+{
+    double a[4] = {q[0], conj ? -q[1] : q[1], conj ? -q[2] : q[2], conj ? -q[3] : q[3]};
+    for (int i = 0; i < v.mLR; ++i) {
+        double x[4] = {v.R(i, 0), v.R(i, 1), v.R(i, 2), v.R(i, 3)}, y[4];
+        quat_mul(y, a, x);
+        for (int c = 0; c < 4; ++c) v.R(i, c) = y[c];
+    }
+}
+
+THB_HD void norm_w(const View& v)
+{
+    double s = 0.0;
+    for (int i = 0; i < v.mLR; ++i) s += v.WR(i);
+    for (int i = 0; i < v.mLR; ++i) v.WR(i) /= s;
+    s = 0.0;
+    for (int i = 0; i < v.mLT; ++i) s += v.WT(i);
+    for (int i = 0; i < v.mLT; ++i) v.WT(i) /= s;
+}
+
+// balanceWeight(PAR_R): wR = 1 / pdfACG(r, A), A = inferACG(r); pdfACG = det^-1/2 (x' A^-1 x)^-2
+THB_HD void balance_R(const View& v)
+{
+    double A[16], Ai[16];
+    infer_acg(v, A);
+    const double det = inv4(A, Ai);
+    const double c = pow(det, -0.5);
+    for (int i = 0; i < v.mLR; ++i) {
+        const double x[4] = {v.R(i, 0), v.R(i, 1), v.R(i, 2), v.R(i, 3)};
+        const double u = quad_form(Ai, x);
+        v.WR(i) = 1.0 / (c * pow(u, -2.0));
+    }
+    norm_w(v);
+}
+
+THB_HD void mean_sd(const View& v, int c, double& m, double& sd)
+{
+    double s = 0.0;
+    for (int i = 0; i < v.mLT; ++i) s += v.T(i, c);
+    m = s / v.mLT;
+    double q = 0.0;
+    for (int i = 0; i < v.mLT; ++i) { const double d = v.T(i, c) - m; q += d * d; }
+    sd = sqrt(q / (v.mLT - 1));   // gsl_stats_sd_m: N-1 denominator
+}
+
+// balanceWeight(PAR_T): wT = 1 / bivariate_gaussian_pdf(t - mean; s0, s1, rho = 0)
+THB_HD void balance_T(const View& v)
+{
+    double m0, m1, s0, s1;
+    mean_sd(v, 0, m0, s0);
+    mean_sd(v, 1, m1, s1);
+    for (int i = 0; i < v.mLT; ++i) {
+        const double u = (v.T(i, 0) - m0) / s0, w = (v.T(i, 1) - m1) / s1;
+        const double pdf = exp(-(u * u + w * w) / 2.0) / (2.0 * 3.14159265358979323846 * s0 * s1);
+        v.WT(i) = 1.0 / pdf;
+    }
+    norm_w(v);
+}
+
+// perturb(pf, PAR_R), MODE_3D
+THB_HD void perturb_R(const View& v, double pfac, Rng& g)
+{
+    const double k1 = pfac * pfac * fmin(1.0, v.S(S_K1)), k2 = pfac * pfac * fmin(1.0, v.S(S_K2)),
+                 k3 = pfac * pfac * fmin(1.0, v.S(S_K3));
+    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);   // LLT of diag(1,k1,k2,k3)
+    double mean[4];
+    acg_mean(v, mean);
+    const double mc[4] = {mean[0], -mean[1], -mean[2], -mean[3]};
+    for (int i = 0; i < v.mLR; ++i) {
+        double d[4] = {g.normal(), l1 * g.normal(), l2 * g.normal(), l3 * g.normal()};
+        const double nrm = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+        for (int c = 0; c < 4; ++c) d[c] *= nrm;
+        double x[4] = {v.R(i, 0), v.R(i, 1), v.R(i, 2), v.R(i, 3)}, y[4];
+        quat_mul(y, mc, x);      // quat = conj(mean) * quat
+        quat_mul(x, d, y);       // quat = pert * quat
+        quat_mul(y, mean, x);    // quat = mean * quat
+        for (int c = 0; c < 4; ++c) v.R(i, c) = y[c];
+    }
+    balance_R(v);
+}
+
+// perturb(pf, PAR_T) + reCentre + balanceWeight(PAR_T)
+THB_HD void perturb_T(const View& v, double pfac, double transS, double transQ, Rng& g)
+{
+    const double s0 = v.S(S_S0), s1 = v.S(S_S1);
+    for (int i = 0; i < v.mLT; ++i) {
+        const double x = s0 * g.normal(), y = s1 * g.normal();   // bivariate Gaussian, rho = 0
+        v.T(i, 0) += x * pfac;
+        v.T(i, 1) += y * pfac;
+    }
+    const double transM = transS * (-2.0 * log(transQ));   // transS * gsl_cdf_chisq_Qinv(transQ, 2)
+    for (int i = 0; i < v.mLT; ++i)
+        if (hypot(v.T(i, 0), v.T(i, 1)) > transM) {
+            v.T(i, 0) = transS * g.normal();
+            v.T(i, 1) = transS * g.normal();
+        }
+    balance_T(v);
+}
+
+THB_HD int argmax_uR(const View& v)
+{
+    int b = 0;
+    for (int i = 1; i < v.mLR; ++i)
+        if (v.UR(i) > v.UR(b)) b = i;
+    return b;
+}
+THB_HD int argmax_uT(const View& v)
+{
+    int b = 0;
+    for (int i = 1; i < v.mLT; ++i)
+        if (v.UT(i) > v.UT(b)) b = i;
+    return b;
+}
+
+// setUR/setUT from the E kernel's float marginals + keepHalfHeightPeak(PAR_R)
+// (OPTIMISER_PEAK_FACTOR_R on, _T off: src/Optimiser.cpp:1408-1421)
+THB_HD void set_u_keep_peak(const View& v, const float* uR, const float* uT)
+{
+    for (int i = 0; i < v.mLR; ++i) v.UR(i) = (double)uR[i];
+    for (int i = 0; i < v.mLT; ++i) v.UT(i) = (double)uT[i];
+    const double hh = v.UR(argmax_uR(v)) * v.S(S_PEAKR);
+    for (int i = 0; i < v.mLR; ++i) v.UR(i) = v.UR(i) < hh ? 0.0 : v.UR(i) - hh;
+}
+
+THB_HD void rank1st(const View& v)
+{
+    const int a = argmax_uR(v), b = argmax_uT(v);
+    for (int c = 0; c < 4; ++c) v.S(S_TOPR + c) = v.R(a, c);
+    for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = v.T(b, c);
+}
+
+// calVari(PAR_R) + calVari(PAR_T)
+THB_HD void cal_vari(const View& v, Rng& g)
+{
+    (void)g.uniform_int((uint32_t)v.mLR);   // the reference draws an (unused under C1) anchor index
+    double mean[4];
+    acg_mean(v, mean);
+    left_mul_all(v, mean, true);
+    double A[16];
+    infer_acg(v, A);
+    v.S(S_K1) = A[5] / A[0];
+    v.S(S_K2) = A[10] / A[0];
+    v.S(S_K3) = A[15] / A[0];
+    left_mul_all(v, mean, false);
+    double m, sd;
+    mean_sd(v, 0, m, sd); v.S(S_S0) = sd;
+    mean_sd(v, 1, m, sd); v.S(S_S1) = sd;
+    v.S(S_RHO) = 0.0;
+}
+
+// resample(n = mLR, PAR_R) and (mLT, PAR_T): shuffle, top, prior x likelihood, systematic resampling
+THB_HD void resample_R(const View& v, Rng& g)
+{
+    const int n = v.mLR;
+    for (int i = n - 1; i > 0; --i) {   // Fisher-Yates (gsl_ran_shuffle)
+        const int j = (int)g.uniform_int((uint32_t)(i + 1));
+        if (j != i) {
+            for (int c = 0; c < 4; ++c) { const double x = v.R(i, c); v.R(i, c) = v.R(j, c); v.R(j, c) = x; }
+            double x = v.WR(i); v.WR(i) = v.WR(j); v.WR(j) = x;
+            x = v.UR(i); v.UR(i) = v.UR(j); v.UR(j) = x;
+        }
+    }
+    const int top = argmax_uR(v);
+    for (int c = 0; c < 4; ++c) v.S(S_TOPR + c) = v.R(top, c);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) { v.WR(i) *= v.UR(i); s += v.WR(i); }
+    double cum = 0.0;
+    for (int i = 0; i < n; ++i) { v.WR(i) /= s; cum += v.WR(i); v.W2(i) = cum; }   // W2 = cdf
+    const double last = v.W2(n - 1);
+    const double u0 = g.uniform() * (1.0 / n);
+    int i = 0;
+    for (int j = 0; j < n; ++j) {
+        const double uj = u0 + j * 1.0 / n;
+        while (i < n - 1 && uj > v.W2(i) / last) ++i;
+        for (int c = 0; c < 4; ++c) v.R2(j, c) = v.R(i, c);
+        v.WR(j) = -1.0 / v.UR(i);       // PARTICLE_PRIOR_ONE: prior 1/u; stored negated until the copy-back below
+        // (WR(j) for j <= processed is no longer needed: cdf lives in W2; UR is read-only here)
+    }
+    for (int j = 0; j < n; ++j) {
+        for (int c = 0; c < 4; ++c) v.R(j, c) = v.R2(j, c);
+        v.WR(j) = -v.WR(j);
+    }
+}
+
+THB_HD void resample_T(const View& v, Rng& g)
+{
+    const int n = v.mLT;
+    for (int i = n - 1; i > 0; --i) {
+        const int j = (int)g.uniform_int((uint32_t)(i + 1));
+        if (j != i) {
+            for (int c = 0; c < 2; ++c) { const double x = v.T(i, c); v.T(i, c) = v.T(j, c); v.T(j, c) = x; }
+            double x = v.WT(i); v.WT(i) = v.WT(j); v.WT(j) = x;
+            x = v.UT(i); v.UT(i) = v.UT(j); v.UT(j) = x;
+        }
+    }
+    const int top = argmax_uT(v);
+    for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = v.T(top, c);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) { v.WT(i) *= v.UT(i); s += v.WT(i); }
+    double cum = 0.0;
+    for (int i = 0; i < n; ++i) { v.WT(i) /= s; cum += v.WT(i); v.W2(i) = cum; }
+    const double last = v.W2(n - 1);
+    const double u0 = g.uniform() * (1.0 / n);
+    int i = 0;
+    for (int j = 0; j < n; ++j) {
+        const double uj = u0 + j * 1.0 / n;
+        while (i < n - 1 && uj > v.W2(i) / last) ++i;
+        for (int c = 0; c < 2; ++c) v.T2(j, c) = v.T(i, c);
+        v.WT(j) = -1.0 / v.UT(i);
+    }
+    for (int j = 0; j < n; ++j) {
+        for (int c = 0; c < 2; ++c) v.T(j, c) = v.T2(j, c);
+        v.WT(j) = -v.WT(j);
+    }
+}
+
+THB_HD double vari_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), 1.0 / 6); }
+THB_HD double vari_T(const View& v) { return sqrt(v.S(S_S0) * v.S(S_S0) * v.S(S_S1) * v.S(S_S1)); }   // rho = 0
+THB_HD double compress_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), -1.0 / 6); }
+
+// Particle::load: ACG cloud about q (random hemisphere sign), Gaussian cloud about t, balanced weights,
+// calVari, peak factor reset (PEAK_FACTOR_MIN = 1e-3).
+THB_HD void load(const View& v, const double q[4], double k1, double k2, double k3, const double t[2], double s0,
+                 double s1, Rng& g)
+{
+    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);
+    v.S(S_K1) = k1; v.S(S_K2) = k2; v.S(S_K3) = k3;
+    for (int c = 0; c < 4; ++c) v.S(S_TOPR + c) = q[c];
+    for (int i = 0; i < v.mLR; ++i) {
+        double d[4] = {g.normal(), l1 * g.normal(), l2 * g.normal(), l3 * g.normal()};
+        const double nrm = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+        for (int c = 0; c < 4; ++c) d[c] *= nrm;
+        const double sgn = (2.0 * g.uniform() - 1.0) >= 0 ? 1.0 : -1.0;
+        const double qq[4] = {sgn * q[0], sgn * q[1], sgn * q[2], sgn * q[3]};
+        double y[4];
+        quat_mul(y, d, qq);
+        for (int c = 0; c < 4; ++c) v.R(i, c) = y[c];
+        v.WR(i) = 1.0 / v.mLR;
+        v.UR(i) = 1.0 / v.mLR;
+    }
+    for (int i = 0; i < v.mLT; ++i) { v.WT(i) = 1.0 / v.mLT; v.UT(i) = 1.0 / v.mLT; }
+    balance_R(v);
+    v.S(S_S0) = s0; v.S(S_S1) = s1;
+    for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = t[c];
+    for (int i = 0; i < v.mLT; ++i) {
+        v.T(i, 0) = s0 * g.normal() + t[0];
+        v.T(i, 1) = s1 * g.normal() + t[1];
+    }
+    balance_T(v);
+    cal_vari(v, g);
+    v.S(S_SCORE) = 1.0;
+    v.S(S_NPHASE) = 0.0;
+    v.S(S_VARIR) = 1.79769313486231570e308;
+    v.S(S_VARIT) = 1.79769313486231570e308;
+    v.S(S_VARID) = 1.79769313486231570e308;
+    v.S(S_PEAKR) = 1e-3;
+    v.S(S_NODEC) = 0.0;
+    v.S(S_SPARE) = 0.0;
+}
+
+// the stop rule of the phase loop (src/Optimiser.cpp:1510-1615, OPTIMISER_COMPRESS_CRITERIA);
+// returns true when the particle is finished.  variD is the constant defocus sigma (0 here).
+THB_HD bool stop_rule(const View& v, int phase, int minPhase, double decreaseFactor, int noDecreaseLimit)
+{
+    if (phase < minPhase) return false;
+    const double r = vari_R(v), t = vari_T(v), d = 0.0;
+    if (r < v.S(S_VARIR) * decreaseFactor || t < v.S(S_VARIT) * decreaseFactor || d < v.S(S_VARID) * decreaseFactor)
+        v.S(S_NODEC) = 0.0;
+    else
+        v.S(S_NODEC) += 1.0;
+    if (r < v.S(S_VARIR)) v.S(S_VARIR) = r;
+    if (t < v.S(S_VARIT)) v.S(S_VARIT) = t;
+    if (d < v.S(S_VARID)) v.S(S_VARID) = d;
+    return v.S(S_NODEC) == (double)noDecreaseLimit;
+}
+
+}  // namespace pf
+}  // namespace thb
