@@ -45,7 +45,7 @@ def prob():
     ctfM = np.stack([synth.ctf_values(pixM["iCol"].astype(float), pixM["iRow"].astype(float), N, 1.32, 3e5, *par["ctfpar"][l], 2.7e7, 0.1)
                      for l in range(nImg)])
     ph = -2 * np.pi * (pixM["iCol"][None] * par["tran"][:, :1] / N + pixM["iRow"][None] * par["tran"][:, 1:] / N)
-    datM = (ctfM * cleanM * np.exp(1j * ph) * par["scale"] + (rngM.normal(size=(nImg, PM)) + 1j * rngM.normal(size=(nImg, PM))) * np.sqrt(0.5)).astype(np.complex64)
+    datM = (ctfM * cleanM * np.exp(1j * ph) + (rngM.normal(size=(nImg, PM)) + 1j * rngM.normal(size=(nImg, PM))) * np.sqrt(par["sig2"] / 2)).astype(np.complex64)
     # starting guesses: truth disturbed by ~2 degrees and ~1 pixel
     k0 = 3e-4
     q_start = np.stack([synth.acg_cloud(par["quat"][l], k0, 1, rng)[0] for l in range(nImg)])

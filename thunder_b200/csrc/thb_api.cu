@@ -8,6 +8,8 @@
 #include <vector>
 #include "thb_context.h"
 #include "thb_kernels.cuh"
+#include "thb_expect2.cuh"
+#include <cstdlib>
 
 static thread_local std::string g_create_error;
 
@@ -97,9 +99,32 @@ AccTable acc_table(const thb_ctx* ctx)
     return t;
 }
 
+static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
+{
+    a.tiles = ctx->tilesE;
+    a.nTiles = ctx->nTilesE;
+    a.work = nullptr;
+    if (a.nR > E2_ROTS || a.nT > E_TC) {
+        a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
+        if (!a.work) return THB_E_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM_BYTES));
+        attr_set = true;
+    }
+    span_begin(ctx, KF_EXPECT);
+    expect_local_tma_kernel<<<a.nAct, E2_THREADS, E2_SMEM_BYTES, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
 int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a)
 {
     if (a.nAct <= 0) return THB_OK;
+    if (ctx->expectImpl == 2) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)
         return set_error(ctx, THB_E_ARG, "expect_local: nR*nT = %d too large for the local-search kernel", a.nR * a.nT);
@@ -173,6 +198,7 @@ int thb_create(thb_ctx** out, int device)
     thb_ctx* ctx = new thb_ctx();
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
+    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = atoi(e) == 1 ? 1 : 2;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return cuda_fail(nullptr, e, "cudaStreamCreate");
@@ -208,7 +234,7 @@ void thb_destroy(thb_ctx* ctx)
     }
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
-    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->tilesE);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
     for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
@@ -313,7 +339,7 @@ int thb_pixel_list(int N, int pf, float rU, float rL, int* iCol, int* iRow, int*
 // blocks boustrophedon (rows of blocks alternate direction), so the trilinear cells of consecutive
 // pixels stay inside a compact 3D neighbourhood.  Sums over pixels are order-independent up to fp32
 // rounding; per-pixel results handed back to the caller (thb_project) are un-permuted.
-static void blocked_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm)
+static void blocked_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm, std::vector<long long>* blockOf = nullptr)
 {
     const int B = 8;
     std::vector<long long> key(n);
@@ -327,14 +353,46 @@ static void blocked_order(int n, const int* a, const int* b, int unit, std::vect
     perm.resize(n);
     for (int i = 0; i < n; ++i) perm[i] = i;
     std::stable_sort(perm.begin(), perm.end(), [&](int l, int r) { return key[l] < key[r]; });
+    if (blockOf) {
+        blockOf->resize(n);
+        for (int i = 0; i < n; ++i) (*blockOf)[i] = key[perm[i]] >> 20;   // (by, sx): one value per 8x8 block
+    }
 }
 
-static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst, int** dperm)
+// tiles of the blocked order: maximal runs of pixels of one 8x8 block, with the rectangle they span
+static void build_tiles(int n, const int* a, const int* b, int unit, int pf, const std::vector<int>& perm,
+                        const std::vector<long long>& blockOf, std::vector<TileDesc>& tiles)
+{
+    tiles.clear();
+    int i = 0;
+    while (i < n) {
+        int j = i;
+        int amin = 1 << 30, amax = -(1 << 30), bmin = 1 << 30, bmax = -(1 << 30);
+        while (j < n && blockOf[j] == blockOf[i] && j - i < E2_TILE) {
+            const int x = a[perm[j]] / unit * pf, y = b[perm[j]] / unit * pf;   // padded units
+            amin = std::min(amin, x); amax = std::max(amax, x);
+            bmin = std::min(bmin, y); bmax = std::max(bmax, y);
+            ++j;
+        }
+        TileDesc t;
+        t.start = i; t.count = j - i;
+        t.ca = 0.5f * (float)(amin + amax); t.cb = 0.5f * (float)(bmin + bmax);
+        t.ha = 0.5f * (float)(amax - amin); t.hb = 0.5f * (float)(bmax - bmin);
+        t.pad0 = t.pad1 = 0;
+        tiles.push_back(t);
+        i = j;
+    }
+}
+
+static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst, int** dperm,
+                         std::vector<TileDesc>* tiles = nullptr)
 {
     if (nPxl <= 0 || !a || !b) return set_error(ctx, THB_E_ARG, "pixel list is empty or NULL");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int> perm;
-    blocked_order(nPxl, a, b, padded ? pf : 1, perm);
+    std::vector<long long> blockOf;
+    blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf);
+    if (tiles) build_tiles(nPxl, a, b, padded ? pf : 1, pf, perm, blockOf, *tiles);
     int* tmp = (int*)scratch(ctx, 0, sizeof(int) * 2 * (size_t)nPxl);
     if (!tmp) return THB_E_CUDA;
     THB_CUDA(ctx, cudaMemcpyAsync(tmp, a, sizeof(int) * nPxl, cudaMemcpyHostToDevice, ctx->stream));
@@ -357,8 +415,14 @@ int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
 {
     if (!ctx) return THB_E_ARG;
     if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_expect_pixels: bad N/pf");
-    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE);
+    std::vector<TileDesc> tiles;
+    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE, &tiles);
     if (rc) return rc;
+    cudaFree(ctx->tilesE);
+    ctx->tilesE = nullptr;
+    ctx->nTilesE = (int)tiles.size();
+    THB_CUDA(ctx, cudaMalloc(&ctx->tilesE, sizeof(TileDesc) * tiles.size()));
+    THB_CUDA(ctx, cudaMemcpy(ctx->tilesE, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice));
     if (ctx->nPxlE != nPxl) free_stack(ctx->stackE);   // a resident stack belongs to one pixel list
     ctx->N = N; ctx->pf = pf; ctx->nPxlE = nPxl;
     return THB_OK;
@@ -376,6 +440,7 @@ int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
 }
 
 static size_t vol_elems(int vdim) { return (size_t)(vdim / 2 + 1) * vdim * vdim; }
+static int vol_pitch(int vdim) { return (vdim / 2 + 2 + 3) & ~3; }
 
 int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
 {
@@ -384,14 +449,19 @@ int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
         return set_error(ctx, THB_E_ARG, "set_volume: bad slot/vdim");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     Volume3& v = ctx->vols[slot];
+    const int pitch = vol_pitch(vdim);
+    const size_t rows = (size_t)vdim * vdim;
     if (v.vdim != vdim) {
         cudaFree(v.d);
         v.d = nullptr;
         v.vdim = 0;
-        THB_CUDA(ctx, cudaMalloc(&v.d, vol_elems(vdim) * sizeof(float2)));
+        THB_CUDA(ctx, cudaMalloc(&v.d, rows * pitch * sizeof(float2)));
+        THB_CUDA(ctx, cudaMemsetAsync(v.d, 0, rows * pitch * sizeof(float2), ctx->stream));
         v.vdim = vdim;
+        v.pitch = pitch;
     }
-    THB_CUDA(ctx, cudaMemcpyAsync(v.d, volFT, vol_elems(vdim) * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t rowBytes = (size_t)(vdim / 2 + 1) * sizeof(float2);
+    THB_CUDA(ctx, cudaMemcpy2DAsync(v.d, (size_t)pitch * sizeof(float2), volFT, rowBytes, rowBytes, rows, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -402,7 +472,8 @@ int thb_get_volume(thb_ctx* ctx, int slot, float* volFT)
     if (slot < 0 || slot >= THB_MAX_SLOTS || !volFT || !ctx->vols[slot].d)
         return set_error(ctx, THB_E_STATE, "get_volume: slot %d has no volume", slot);
     const Volume3& v = ctx->vols[slot];
-    THB_CUDA(ctx, cudaMemcpyAsync(volFT, v.d, vol_elems(v.vdim) * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t rowBytes = (size_t)(v.vdim / 2 + 1) * sizeof(float2);
+    THB_CUDA(ctx, cudaMemcpy2DAsync(volFT, rowBytes, v.d, (size_t)v.pitch * sizeof(float2), rowBytes, (size_t)v.vdim * v.vdim, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -498,7 +569,7 @@ int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst
     THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * 4 * (size_t)nRot, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((P + 255) / 256, nRot);
     span_begin(ctx, KF_EXPECT);
-    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->pixE, ctx->permE, P, dq, dd);
+    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->vols[slot].pitch, ctx->pixE, ctx->permE, P, dq, dd);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -552,7 +623,7 @@ int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, 
     ExpectArgs a;
     memset(&a, 0, sizeof(a));
     a.vols = vol_table(ctx);
-    a.vdim = vdim;
+    a.vdim = vdim; a.pitch = vol_pitch(vdim);
     a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
     a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
     a.nAct = nAct; a.imgIdx = imgIdx ? didx : nullptr; a.imgBase = 0; a.active = nullptr;
@@ -621,7 +692,7 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
         THB_CUDA(ctx, cudaMemcpyAsync(didx, idx.data(), sizeof(int) * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
         ExpectArgs a;
         memset(&a, 0, sizeof(a));
-        a.vols = vol_table(ctx); a.vdim = vdim;
+        a.vols = vol_table(ctx); a.vdim = vdim; a.pitch = vol_pitch(vdim);
         a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
         a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
         a.nAct = nAct; a.imgIdx = didx; a.nR = nr; a.nT = nT;

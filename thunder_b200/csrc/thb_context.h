@@ -24,9 +24,13 @@ struct Stack {
     int* slot = nullptr;
 };
 
+// projector volume in HBM: FFTW half-complex rows of vdim/2+1 elements, stored with a row pitch of
+// `pitch` elements (multiple of 4 = 32 bytes, >= vdim/2+2) so that every row is 16-byte aligned for the
+// TMA bulk copies and a box row may over-read one element past the Nyquist column
 struct Volume3 {
     float2* d = nullptr;
     int vdim = 0;
+    int pitch = 0;
 };
 
 struct Accum {
@@ -75,6 +79,9 @@ struct thb_ctx {
     int4* pixM = nullptr;
     int* permE = nullptr;        // blocked position -> caller's pixel index
     int* permM = nullptr;
+    thb::TileDesc* tilesE = nullptr;   // 8x8-pixel tiles of the E pixel list (blocked order)
+    int nTilesE = 0;
+    int expectImpl = 2;          // 2: TMA-staged kernel (default), 1: the direct-gather kernel (THB_EXPECT_IMPL=1)
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];
     thb::Accum accs[thb::THB_MAX_SLOTS];

@@ -19,7 +19,7 @@ namespace thb {
 // ------------------------------------------------------------------------------------------------
 // trilinear gather of one complex sample (reference Volume::getByInterpolationFT, Volume.cpp:314-338)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 gather_ft(const float2* __restrict__ vol, int n, int nColFT, float x, float y,
+__device__ __forceinline__ float2 gather_ft(const float2* __restrict__ vol, int n, int nColFT /* row pitch */, float x, float y,
                                             float z)
 {
     int x0, y0, z0;
@@ -48,14 +48,14 @@ __device__ __forceinline__ float2 gather_ft(const float2* __restrict__ vol, int 
 // ------------------------------------------------------------------------------------------------
 // Projector::project for many rotations (src/Projector.cpp:356-374); lanes = pixels
 // ------------------------------------------------------------------------------------------------
-__global__ void project_kernel(const float2* __restrict__ vol, int n, const int4* __restrict__ pix,
+__global__ void project_kernel(const float2* __restrict__ vol, int n, int pitch, const int4* __restrict__ pix,
                                const int* __restrict__ perm, int P, const double* __restrict__ quat,
                                float2* __restrict__ dst)
 {
     const int r = blockIdx.y;
     double q[4] = {quat[4 * r], quat[4 * r + 1], quat[4 * r + 2], quat[4 * r + 3]};
     const Rot2 rot = quat_to_rot2(q);
-    const int nColFT = n / 2 + 1;
+    const int nColFT = pitch;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
         const int4 px = pix[i];
         float x, y, z;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(E_THREADS, 4) expect_local_kernel(const Expect
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
     const int slot = A.slotOfImg ? A.slotOfImg[img] : 0;
     const float2* __restrict__ vol = A.vols.p[slot];
-    const int n = A.vdim, nColFT = n / 2 + 1;
+    const int n = A.vdim, nColFT = A.pitch;
     const int P = A.P;
     const float2* __restrict__ dat = A.dat + (size_t)img * P;
     const float* __restrict__ ctf = A.ctf + (size_t)img * P;

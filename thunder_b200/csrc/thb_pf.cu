@@ -322,7 +322,7 @@ static int expect_args_from_pf(thb_ctx* ctx, ExpectArgs& a)
         return set_error(ctx, THB_E_STATE, "expectation: particles [%d,%d) exceed the E stack (%d images)", s.imgBase,
                          s.imgBase + s.nPar, ctx->stackE.nImg);
     memset(&a, 0, sizeof(a));
-    a.vols = vol_table(ctx); a.vdim = vdim;
+    a.vols = vol_table(ctx); a.vdim = vdim; a.pitch = (vdim / 2 + 2 + 3) & ~3;
     a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
     a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
     a.nAct = s.nPar; a.imgIdx = nullptr; a.imgBase = s.imgBase; a.active = s.active;

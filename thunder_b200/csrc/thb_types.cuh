@@ -35,9 +35,21 @@ struct __align__(16) PixelE {
 };
 static_assert(sizeof(PixelE) == 96, "PixelE must be 96 bytes");
 
+// 8x8-pixel tile of the blocked pixel order: pixels [start, start+count) and the rectangle they span
+// in padded units (centre ca,cb ; half extents ha,hb)
+struct TileDesc {
+    int start, count;
+    float ca, cb, ha, hb;
+    int pad0, pad1;
+};
+
 struct ExpectArgs {
     VolTable vols;
     int vdim;
+    int pitch;              // row pitch of the volumes in elements (>= vdim/2 + 2, multiple of 4)
+    const TileDesc* tiles;
+    int nTiles;
+    float* work;            // [nAct][nR*nT] scratch for multi-pass shapes (nR > 128 or nT > 9), else null
     const float2* dat;
     const float* ctf;
     const float* sig;

@@ -87,7 +87,7 @@ def make_particles(nImg, N, pix, project_fn, seed=1234, transS=2.0, snr_scale=1.
 
     pix: dict with iCol,iRow (int32).  project_fn(quats[n,4]) -> complex64 [n][nPxl] clean slices.
     Returns dict(dat, ctf, sigRcp, quat, tran, ctfpar).  Image = CTF * slice * shift + noise with
-    sigma^2 = 1 per complex component pair -> sigRcp = -0.5 / sigma^2 (src/Optimiser.cpp:6708)."""
+    sigma^2 = sig2 (returned) per complex pixel -> sigRcp = -0.5 / sigma^2 (src/Optimiser.cpp:6708)."""
     rng = np.random.default_rng(seed)
     iCol, iRow = pix["iCol"].astype(np.float64), pix["iRow"].astype(np.float64)
     P = len(iCol)
@@ -100,14 +100,16 @@ def make_particles(nImg, N, pix, project_fn, seed=1234, transS=2.0, snr_scale=1.
         ctf[l] = ctf_values(iCol, iRow, N, pixelSize, 3.0e5, dU[l], dV[l], th[l], 2.7e7, 0.1)
     phase = -2 * np.pi * (iCol[None, :] * tran[:, :1] / N + iRow[None, :] * tran[:, 1:] / N)
     shift = np.exp(1j * phase).astype(np.complex64)
-    sig2 = 1.0
-    # scale the signal so that the per-pixel SNR is ~0.05 * snr_scale
+    # Noise level chosen so that the per-pixel SNR is ~0.05 * snr_scale.  The SIGNAL keeps the amplitude
+    # of the projector volume (the E-step compares dat with ctf * projection, unscaled); the noise is
+    # scaled instead, so that the likelihood is consistent with how the data were made.
     spow = float(np.mean(np.abs(clean * ctf) ** 2)) + 1e-30
-    scale = np.sqrt(0.05 * snr_scale * sig2 / spow)
+    sig2 = spow / (0.05 * snr_scale)
+    scale = 1.0
     noise = (rng.normal(size=(nImg, P)) + 1j * rng.normal(size=(nImg, P))) * np.sqrt(sig2 / 2)
-    dat = (ctf * clean * shift * scale + noise).astype(np.complex64)
+    dat = (ctf * clean * shift + noise).astype(np.complex64)
     sigRcp = np.full((nImg, P), -0.5 / sig2, np.float32)
-    return dict(dat=dat, ctf=ctf, sigRcp=sigRcp, quat=quat, tran=tran, scale=scale,
+    return dict(dat=dat, ctf=ctf, sigRcp=sigRcp, quat=quat, tran=tran, scale=scale, sig2=sig2,
                 ctfpar=np.stack([dU, dV, th], axis=1))
 
 
