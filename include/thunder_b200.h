@@ -80,6 +80,13 @@ int64_t thb_launch_count(thb_ctx* ctx, int reset);
  * which = 0 expect, 1 insert, 2 particle filter, 3 pack/unpack, 4 allreduce ; launches returned in *n */
 double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset);
 int thb_enable_timing(thb_ctx* ctx, int on);
+/* tuning switches (development / A-B measurement): key "expect_impl": 2 = TMA-staged E kernel (default),
+ * 1 = direct-gather E kernel; key "insert_impl": see DESIGN.md.  Unknown key -> THB_E_ARG. */
+int thb_set_option(thb_ctx* ctx, const char* key, int value);
+/* staging counters of the E kernel since the last reset (enable with option "stats" = 1): tiles, tiles with a
+ * shared-memory box, sum of margins, staged elements, (rotation,tile) pairs on the L1/L2 path, all pairs,
+ * over-capacity tiles, box rows */
+int thb_expect_stats(thb_ctx* ctx, uint64_t out[8], int reset);
 /* CUDA-event stopwatch on the library's launch stream: stop == 0 records the start, stop != 0 records the
  * end, waits for it and returns the elapsed device time in *ms */
 int thb_timer(thb_ctx* ctx, int stop, float* ms);

@@ -54,6 +54,8 @@ def _sig(lib):
     f = lib.thb_launch_count; f.restype = C.c_int64; f.argtypes = [_p, _i]
     f = lib.thb_kernel_ms; f.restype = C.c_double; f.argtypes = [_p, _i, C.POINTER(C.c_int64), _i]
     f = lib.thb_enable_timing; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_set_option; f.restype = _i; f.argtypes = [_p, C.c_char_p, _i]
+    f = lib.thb_expect_stats; f.restype = _i; f.argtypes = [_p, _p, _i]
     f = lib.thb_timer; f.restype = _i; f.argtypes = [_p, _i, C.POINTER(C.c_float)]
     f = lib.thb_pixel_list; f.restype = _i; f.argtypes = [_i, _i, C.c_float, C.c_float] + [_p] * 6
     f = lib.thb_set_expect_pixels; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p]
@@ -165,6 +167,15 @@ class Context:
 
     def launch_count(self, reset=False):
         return int(self.lib.thb_launch_count(self.h, int(reset)))
+
+    def set_option(self, key: str, value: int):
+        self._chk(self.lib.thb_set_option(self.h, key.encode(), int(value)))
+
+    def expect_stats(self, reset=True):
+        out = np.zeros(8, np.uint64)
+        self._chk(self.lib.thb_expect_stats(self.h, _ptr(out), int(reset)))
+        keys = ("tiles", "tiles_boxed", "margin_sum", "staged_elems", "pairs_l2_path", "pairs", "over_capacity", "rows")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def enable_timing(self, on=True):
         self._chk(self.lib.thb_enable_timing(self.h, int(on)))

@@ -104,6 +104,7 @@ static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
     a.tiles = ctx->tilesE;
     a.nTiles = ctx->nTilesE;
     a.work = nullptr;
+    a.stats = ctx->statsOn ? ctx->dStats : nullptr;
     if (a.nR > E2_ROTS || a.nT > E_TC) {
         a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
         if (!a.work) return THB_E_CUDA;
@@ -151,7 +152,10 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a)
     split = std::min(split, std::max(tiles, 1));
     dim3 grid(a.nImg, split);
     span_begin(ctx, KF_INSERT);
-    insert_kernel<<<grid, M_THREADS, 0, ctx->stream>>>(a);
+    if (ctx->insertImpl == 2)
+        insert_kernel<2><<<grid, M_THREADS, 0, ctx->stream>>>(a);
+    else
+        insert_kernel<0><<<grid, M_THREADS, 0, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -199,6 +203,9 @@ int thb_create(thb_ctx** out, int device)
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
     if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("THB_INSERT_IMPL")) ctx->insertImpl = atoi(e);
+    if (const char* e = getenv("THB_TILE_W")) ctx->tileW = std::max(1, std::min(16, atoi(e)));
+    if (const char* e = getenv("THB_TILE_H")) ctx->tileH = std::max(1, std::min(E2_TILE / ctx->tileW, atoi(e)));
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return cuda_fail(nullptr, e, "cudaStreamCreate");
@@ -234,7 +241,7 @@ void thb_destroy(thb_ctx* ctx)
     }
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
-    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->tilesE);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
     for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->stream);
@@ -283,6 +290,46 @@ int thb_enable_timing(thb_ctx* ctx, int on)
     if (!ctx) return THB_E_ARG;
     resolve_spans(ctx);
     ctx->timing = on != 0;
+    return THB_OK;
+}
+
+int thb_set_option(thb_ctx* ctx, const char* key, int value)
+{
+    if (!ctx || !key) return THB_E_ARG;
+    if (!strcmp(key, "expect_impl")) {
+        if (value != 1 && value != 2) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 or 2");
+        ctx->expectImpl = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "tile_w") || !strcmp(key, "tile_h")) {   // takes effect at the next thb_set_expect_pixels
+        if (value < 1 || value > 16) return set_error(ctx, THB_E_ARG, "set_option: tile_w / tile_h must be in [1,16]");
+        (key[5] == 'w' ? ctx->tileW : ctx->tileH) = value;
+        if (ctx->tileW * ctx->tileH > E2_TILE) return set_error(ctx, THB_E_ARG, "set_option: tile_w * tile_h must be <= %d", E2_TILE);
+        return THB_OK;
+    }
+    if (!strcmp(key, "stats")) {
+        if (value && !ctx->dStats) {
+            THB_CUDA(ctx, cudaMalloc(&ctx->dStats, 8 * sizeof(unsigned long long)));
+            THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 8 * sizeof(unsigned long long)));
+        }
+        ctx->statsOn = value != 0;
+        return THB_OK;
+    }
+    if (!strcmp(key, "insert_impl")) {
+        ctx->insertImpl = value;
+        return THB_OK;
+    }
+    return set_error(ctx, THB_E_ARG, "set_option: unknown key %s", key);
+}
+
+int thb_expect_stats(thb_ctx* ctx, uint64_t out[8], int reset)
+{
+    if (!ctx || !out) return THB_E_ARG;
+    if (!ctx->dStats) return set_error(ctx, THB_E_STATE, "expect_stats: enable with thb_set_option(ctx, \"stats\", 1)");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    THB_CUDA(ctx, cudaMemcpy(out, ctx->dStats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 8 * sizeof(uint64_t)));
     return THB_OK;
 }
 
@@ -339,16 +386,16 @@ int thb_pixel_list(int N, int pf, float rU, float rL, int* iCol, int* iRow, int*
 // blocks boustrophedon (rows of blocks alternate direction), so the trilinear cells of consecutive
 // pixels stay inside a compact 3D neighbourhood.  Sums over pixels are order-independent up to fp32
 // rounding; per-pixel results handed back to the caller (thb_project) are un-permuted.
-static void blocked_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm, std::vector<long long>* blockOf = nullptr)
+static void blocked_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm, std::vector<long long>* blockOf = nullptr,
+                          int BW = 8, int BH = 8)
 {
-    const int B = 8;
     std::vector<long long> key(n);
     for (int i = 0; i < n; ++i) {
         const int x = a[i] / unit, y = b[i] / unit + (1 << 20);
-        const int by = y / B, bx = x / B;
+        const int by = y / BH, bx = x / BW;
         const int sx = (by & 1) ? (1 << 16) - bx : bx;
-        const int iy = y % B, ix = (iy & 1) ? B - 1 - x % B : x % B;
-        key[i] = (((long long)by << 40) | ((long long)sx << 20) | (long long)(iy << 4 | ix));
+        const int iy = y % BH, ix = (iy & 1) ? BW - 1 - x % BW : x % BW;
+        key[i] = (((long long)by << 40) | ((long long)sx << 20) | (long long)(iy << 5 | ix));
     }
     perm.resize(n);
     for (int i = 0; i < n; ++i) perm[i] = i;
@@ -385,13 +432,13 @@ static void build_tiles(int n, const int* a, const int* b, int unit, int pf, con
 }
 
 static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst, int** dperm,
-                         std::vector<TileDesc>* tiles = nullptr)
+                         std::vector<TileDesc>* tiles = nullptr, int BW = 8, int BH = 8)
 {
     if (nPxl <= 0 || !a || !b) return set_error(ctx, THB_E_ARG, "pixel list is empty or NULL");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int> perm;
     std::vector<long long> blockOf;
-    blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf);
+    blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf, BW, BH);
     if (tiles) build_tiles(nPxl, a, b, padded ? pf : 1, pf, perm, blockOf, *tiles);
     int* tmp = (int*)scratch(ctx, 0, sizeof(int) * 2 * (size_t)nPxl);
     if (!tmp) return THB_E_CUDA;
@@ -416,9 +463,9 @@ int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
     if (!ctx) return THB_E_ARG;
     if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_expect_pixels: bad N/pf");
     std::vector<TileDesc> tiles;
-    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE, &tiles);
+    int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE, &tiles, ctx->tileW, ctx->tileH);
     if (rc) return rc;
-    cudaFree(ctx->tilesE);
+    cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
     ctx->tilesE = nullptr;
     ctx->nTilesE = (int)tiles.size();
     THB_CUDA(ctx, cudaMalloc(&ctx->tilesE, sizeof(TileDesc) * tiles.size()));

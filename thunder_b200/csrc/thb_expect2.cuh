@@ -8,8 +8,12 @@
 //       conjugate phase ramp of each translation and pre-multiplied for the expanded likelihood,
 //   (b) warps 0-3 classify every rotation against the tile: the cells its slice touches are bounded
 //       by the image of the tile rectangle under the rotation; rotations whose cells lie within a
-//       margin of the cloud's medoid rotation are "core", the union of their bounds is the box,
-//   (c) every thread issues TMA bulk copies HBM/L2 -> shared memory, one per (y,z) row of the box,
+//       margin of the cloud's medoid rotation are "core".  The margin is the largest one whose staged
+//       region fits the box: every candidate margin is evaluated in parallel (one warp each).
+//   (c) the staged region is the bounding box of the core cells CUT BY THE SLAB around the medoid slice
+//       plane (the slices of a cloud fill a thin oblique slab, not its bounding box): each (y,z) row
+//       of the box keeps only the x-interval inside the slab, rows are packed back to back (block
+//       prefix sum) and copied HBM/L2 -> shared memory by the TMA engine, one bulk copy per row,
 //       completing on an mbarrier,
 //   (d) while the box is in flight, the non-core rotations (wide-cloud tails, tiles that straddle the
 //       Hermitian fold) are evaluated with pixels on the lanes and the 8-tap gather going to L1/L2,
@@ -132,25 +136,74 @@ __device__ __forceinline__ void tile_cells(const float c0[3], const float c1[3],
 
 constexpr int E2_THREADS = 256;
 constexpr int E2_ROTS = 128;
-constexpr int E2_TILE = 64;
-constexpr int E2_BOX_ELEMS = 11776;             // float2 elements (92 KB)
-constexpr int E2_HM_MAX = 10;
-constexpr size_t E2_SMEM_BYTES = (size_t)E2_BOX_ELEMS * 8 + E2_TILE * sizeof(PixelRec) + E2_ROTS * sizeof(Rot2) +
-                                 E2_ROTS * E_TC * sizeof(float);
+constexpr int E2_TILE = 128;                    // max pixels per tile
+constexpr int E2_BOX_ELEMS = 9984;              // float2 elements (78 KB)
+constexpr int E2_MAXROWS = 1536;                // (y,z) rows of a box
+constexpr int E2_HM_MAX = 10;                   // candidate margins 0..E2_HM_MAX
+constexpr int E2_NCAND = E2_HM_MAX + 1;
+
+struct __align__(16) RotClass {                 // per rotation, per tile
+    int lo[3], hi[3];
+    int need;                                   // margin this rotation needs around the medoid's cell range
+    float dist;                                 // its largest distance from the medoid slice plane
+};
+struct __align__(16) Cand {                     // per candidate margin
+    int lo[3], hi[3];
+    float dist;
+    float vol;                                  // estimated staged elements
+};
+
+constexpr size_t E2_OFF_TILE = (size_t)E2_BOX_ELEMS * 8;
+constexpr size_t E2_OFF_ROT = E2_OFF_TILE + E2_TILE * sizeof(PixelRec);
+constexpr size_t E2_OFF_ACC = E2_OFF_ROT + E2_ROTS * sizeof(Rot2);
+constexpr size_t E2_OFF_BIAS = E2_OFF_ACC + E2_ROTS * E_TC * sizeof(float);
+constexpr size_t E2_OFF_CLS = E2_OFF_BIAS + E2_MAXROWS * sizeof(int);
+constexpr size_t E2_SMEM_BYTES = E2_OFF_CLS + E2_ROTS * sizeof(RotClass);
+
+// sum of 9 values over the 32 lanes of a warp: on return lane l holds the total of value (l >> 2) & 7 in
+// `out` (values 0..7) and every lane holds the total of value 8 in `out8`
+__device__ __forceinline__ void warp_sum9(const float v[E_TC], int lane, float& out, float& out8)
+{
+    float w[4], x[2];
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b16 ? v[i] : v[i + 4];
+        const float keep = b16 ? v[i + 4] : v[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b8 ? w[i] : w[i + 2];
+        const float keep = b8 ? w[i + 2] : w[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = b4 ? x[0] : x[1];
+        const float keep = b4 ? x[1] : x[0];
+        out = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    out += __shfl_xor_sync(0xffffffffu, out, 2);
+    out += __shfl_xor_sync(0xffffffffu, out, 1);
+    float e = v[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    out8 = e;
+}
 
 __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const ExpectArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* box = reinterpret_cast<float2*>(smem_raw);
-    PixelRec* tile = reinterpret_cast<PixelRec*>(smem_raw + (size_t)E2_BOX_ELEMS * 8);
-    Rot2* sRot = reinterpret_cast<Rot2*>(smem_raw + (size_t)E2_BOX_ELEMS * 8 + E2_TILE * sizeof(PixelRec));
-    float* sAcc = reinterpret_cast<float*>(smem_raw + (size_t)E2_BOX_ELEMS * 8 + E2_TILE * sizeof(PixelRec) + E2_ROTS * sizeof(Rot2));
-    // log-likelihood table [nR][nT]: aliases the box when the shape is a single pass (it is filled after the last
-    // tile), else lives in the caller's scratch (passes re-stage the box)
+    PixelRec* tile = reinterpret_cast<PixelRec*>(smem_raw + E2_OFF_TILE);
+    Rot2* sRot = reinterpret_cast<Rot2*>(smem_raw + E2_OFF_ROT);
+    float* sAcc = reinterpret_cast<float*>(smem_raw + E2_OFF_ACC);
+    int* sBias = reinterpret_cast<int*>(smem_raw + E2_OFF_BIAS);
+    RotClass* sCls = reinterpret_cast<RotClass*>(smem_raw + E2_OFF_CLS);
     __shared__ __align__(8) uint64_t sBar;
     __shared__ float sRC[E_TC], sRR[E_TC];
-    __shared__ int sRed[4][6];
-    __shared__ unsigned char sCore[E2_ROTS];
+    __shared__ Cand sCand[E2_NCAND];
+    __shared__ int sWarpTot[E2_THREADS / 32];
     __shared__ int sOut[E2_ROTS];
     __shared__ int sNOut[2];
     __shared__ int sCentral;
@@ -173,6 +226,8 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
     const int rloc = (warp & 3) * 32 + lane;   // rotation slot of this thread within a pass
     const int ph = warp >> 2;                  // pixel half
     const int nRT = A.nR * A.nT;
+    // log-likelihood table [nR][nT]: aliases the box when the shape is a single pass (it is filled after the last
+    // tile), else lives in the caller's scratch (passes re-stage the box)
     float* sL = (A.nR <= E2_ROTS && A.nT <= E_TC) ? reinterpret_cast<float*>(smem_raw) : A.work + (size_t)p * nRT;
 
     if (tid == 0) {
@@ -190,7 +245,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
         const bool rvalid = rloc < nRc;
         // ---- rotations of this pass: matrices to shared memory, float quaternions for the medoid
         __syncthreads();
-        float4* sQ = reinterpret_cast<float4*>(tile);     // 128 x 16 B = 2 KB, inside the record area (6 KB)
+        float4* sQ = reinterpret_cast<float4*>(tile);     // 128 x 16 B = 2 KB, inside the record area
         if (ph == 0) {
             double q[4] = {1.0, 0.0, 0.0, 0.0};
             if (rvalid)
@@ -229,7 +284,9 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
             sCentral = bi;
         }
         __syncthreads();
-        float cc0[3], cc1[3], rc0[3], rc1[3];   // float copies: central rotation, own rotation
+        // float copies: medoid ("central") rotation, its slice-plane normal, own rotation and the
+        // coefficients of its distance from the medoid plane: n . (c0 a + c1 b) = al a + be b
+        float cc0[3], cc1[3], rc0[3], rc1[3], nc[3], al, be;
         {
             const Rot2 cr = sRot[sCentral];
 #pragma unroll
@@ -237,7 +294,13 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                 cc0[k] = (float)cr.c0[k]; cc1[k] = (float)cr.c1[k];
                 rc0[k] = (float)rot.c0[k]; rc1[k] = (float)rot.c1[k];
             }
+            nc[0] = cc0[1] * cc1[2] - cc0[2] * cc1[1];
+            nc[1] = cc0[2] * cc1[0] - cc0[0] * cc1[2];
+            nc[2] = cc0[0] * cc1[1] - cc0[1] * cc1[0];
+            al = nc[0] * rc0[0] + nc[1] * rc0[1] + nc[2] * rc0[2];
+            be = nc[0] * rc1[0] + nc[1] * rc1[1] + nc[2] * rc1[2];
         }
+        const float kappa = fabsf(nc[0]) + fabsf(nc[1]) + fabsf(nc[2]);
 
         for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
             __syncthreads();
@@ -261,10 +324,10 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
             for (int ti = 0; ti < A.nTiles; ++ti, ++tileSeq) {
                 const TileDesc td = A.tiles[ti];
                 const int cur = tileSeq & 1;
-                __syncthreads();   // (A) previous tile finished: box, records, out-list are free
-                if (ph == 1) {
+                __syncthreads();   // (A) previous tile finished: box, records, tables are free
+                {
                     // ---------------- (a) pixel records: 2 threads per pixel, translations split between them
-                    const int k = (tid - 128) >> 1, sub = tid & 1;
+                    const int k = tid >> 1, sub = tid & 1;
                     if (k < td.count) {
                         const int i = td.start + k;
                         const int4 c = A.pix[i];
@@ -289,121 +352,240 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                             rec.u[t] = make_float2(m2 * (d.x * co - d.y * s), m2 * (d.x * s + d.y * co));
                         }
                     }
-                } else {
+                }
+                // frame of the tile: the side of the Hermitian fold the medoid puts its centre on
+                const float sgn = (cc0[0] * td.ca + cc1[0] * td.cb) >= 0.0f ? 1.0f : -1.0f;
+                BoxRange cen;
+                tile_cells(cc0, cc1, td.ca, td.cb, td.ha, td.hb, sgn, cen);
+                if (ph == 0) {
                     // ---------------- (b) classify the rotations against this tile
-                    BoxRange cen, own;
-                    const float cx = cc0[0] * td.ca + cc1[0] * td.cb;
-                    const float sgn = cx >= 0.0f ? 1.0f : -1.0f;
-                    tile_cells(cc0, cc1, td.ca, td.cb, td.ha, td.hb, sgn, cen);
+                    BoxRange own;
                     tile_cells(rc0, rc1, td.ca, td.cb, td.ha, td.hb, sgn, own);
-                    // largest margin (in cells) such that the central range grown by it still fits the box
-                    int hm = -1;
-                    if (cen.lo[0] >= 0) {
-                        const int ex = cen.hi[0] - cen.lo[0] + 3, ey = cen.hi[1] - cen.lo[1] + 2, ez = cen.hi[2] - cen.lo[2] + 2;
-                        for (int h = E2_HM_MAX; h >= 0; --h)
-                            if ((ex + 2 * h) * (ey + 2 * h) * (ez + 2 * h) <= E2_BOX_ELEMS) { hm = h; break; }
-                    }
-                    bool core = rvalid && hm >= 0 && own.lo[0] >= 0;
+                    int need = 0;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        core = core && own.lo[k] >= cen.lo[k] - hm && own.hi[k] <= cen.hi[k] + hm;
-                    // the cells must exist in the volume (garbage quaternions do not reach shared memory)
-                    core = core && own.hi[0] + 1 <= half && own.lo[1] >= -half && own.hi[1] + 1 <= half && own.lo[2] >= -half &&
-                           own.hi[2] + 1 <= half;
-                    sCore[rloc] = core ? 1 : 0;
-                    if (rvalid && !core) sOut[atomicAdd(&sNOut[cur], 1)] = rloc;
+                    for (int k = 0; k < 3; ++k) need = max(need, max(cen.lo[k] - own.lo[k], own.hi[k] - cen.hi[k]));
+                    // the slice must stay on one side of the fold, and its cells must exist in the volume
+                    // (garbage quaternions do not reach shared memory)
+                    const bool ok = rvalid && cen.lo[0] >= 0 && own.lo[0] >= 0 && own.hi[0] + 1 <= half && own.lo[1] >= -half &&
+                                    own.hi[1] + 1 <= half && own.lo[2] >= -half && own.hi[2] + 1 <= half;
+                    RotClass rc;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { rc.lo[k] = own.lo[k]; rc.hi[k] = own.hi[k]; }
+                    rc.need = ok ? need : (1 << 20);
+                    rc.dist = fabsf(al * td.ca + be * td.cb) + fabsf(al) * td.ha + fabsf(be) * td.hb;
+                    sCls[rloc] = rc;
+                }
+                __syncthreads();   // (B) records and per-rotation classes visible
+                // ---------------- candidate margins, one warp each: union of the cell ranges and slab thickness of the
+                // rotations that need at most that margin, and the estimated size of the staged region
+                for (int h = warp; h < E2_NCAND; h += E2_THREADS / 32) {
                     const int big = 1 << 28;
+                    int lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+                    float dist = -1.0f;
+                    for (int r = lane; r < E2_ROTS; r += 32) {
+                        const RotClass rc = sCls[r];
+                        if (rc.need <= h) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) { lo[k] = min(lo[k], rc.lo[k]); hi[k] = max(hi[k], rc.hi[k]); }
+                            dist = fmaxf(dist, rc.dist);
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const int lo = __reduce_min_sync(0xffffffffu, core ? own.lo[k] : big);
-                        const int hi = __reduce_max_sync(0xffffffffu, core ? own.hi[k] : -big);
-                        if (lane == 0) { sRed[warp][k] = lo; sRed[warp][3 + k] = hi; }
+                        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+                        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
                     }
-                }
-                __syncthreads();   // (B) records, core flags, out-list, partial box bounds visible
-                if (tid == 0) sNOut[cur ^ 1] = 0;
-                int lo[3], hi[3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    lo[k] = min(min(sRed[0][k], sRed[1][k]), min(sRed[2][k], sRed[3][k]));
-                    hi[k] = max(max(sRed[0][3 + k], sRed[1][3 + k]), max(sRed[2][3 + k], sRed[3][3 + k]));
-                }
-                const bool haveBox = lo[0] <= hi[0];
-                const int xloE = lo[0] & ~1;
-                const int Lx = ((hi[0] + 2 - xloE) + 1) & ~1;     // cells lo..hi need taps lo..hi+1
-                const int ny = hi[1] - lo[1] + 2, nz = hi[2] - lo[2] + 2;
-                if (haveBox) {
-                    // ---------------- (c) stage the box: one TMA bulk copy per (y,z) row
-                    fence_proxy_async();
-                    const int rows = ny * nz;
-                    if (tid == 0) mbar_arrive_expect_tx(&sBar, (uint32_t)rows * (uint32_t)Lx * 8u);
-                    for (int r = tid; r < rows; r += E2_THREADS) {
-                        const int bz = r / ny, by = r - bz * ny;
-                        const int ym = wrap_idx(lo[1] + by, n), zm = wrap_idx(lo[2] + bz, n);
-                        tma_bulk_g2s(box + (size_t)r * Lx, vol + ((size_t)zm * n + ym) * pitch + xloE, (uint32_t)Lx * 8u, &sBar);
+                    for (int o = 16; o > 0; o >>= 1) dist = fmaxf(dist, __shfl_xor_sync(0xffffffffu, dist, o));
+                    if (lane == 0) {
+                        Cand c;
+                        float vol = 3.0e38f;
+                        if (lo[0] <= hi[0]) {
+                            const float ex = (float)(hi[0] - lo[0] + 4), ey = (float)(hi[1] - lo[1] + 2), ez = (float)(hi[2] - lo[2] + 2);
+                            // elements of (bounding box ^ slab): the slab passes through the middle of the box, where the
+                            // cross-section is largest; its projection on the face normal to axis k cannot exceed that face,
+                            // so section <= face_k / |n_k| for every k.  + up to 3.5 elements of alignment / rounding per row.
+                            const float thick = 2.0f * (dist + kappa + 0.05f);
+                            float section = 3.0e38f;
+                            if (fabsf(nc[0]) > 1e-3f) section = fminf(section, ey * ez / fabsf(nc[0]));
+                            if (fabsf(nc[1]) > 1e-3f) section = fminf(section, ex * ez / fabsf(nc[1]));
+                            if (fabsf(nc[2]) > 1e-3f) section = fminf(section, ex * ey / fabsf(nc[2]));
+                            float rowsNE = ey * ez;       // rows the slab reaches
+                            const float reach = thick + fabsf(nc[0]) * ex;
+                            if (fabsf(nc[1]) > 1e-3f) rowsNE = fminf(rowsNE, ez * (reach / fabsf(nc[1]) + 2.0f));
+                            if (fabsf(nc[2]) > 1e-3f) rowsNE = fminf(rowsNE, ey * (reach / fabsf(nc[2]) + 2.0f));
+                            vol = fminf(ex * ey * ez, section * thick) + 3.5f * rowsNE;
+                            if (ey * ez > (float)E2_MAXROWS) vol = 3.0e38f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { c.lo[k] = lo[k]; c.hi[k] = hi[k]; }
+                        c.dist = dist;
+                        c.vol = vol;
+                        sCand[h] = c;
                     }
                 }
+                __syncthreads();   // (B2) candidates visible
+                if (tid == 0) sNOut[cur ^ 1] = 0;
+                int hm = -1;
+                for (int h = E2_HM_MAX; h >= 0; --h)
+                    if (sCand[h].vol * 1.05f <= (float)E2_BOX_ELEMS) { hm = h; break; }
+                // ---------------- (c) rows of the box: x-interval of each (y,z) row inside the slab, packed by a prefix sum.
+                // The size above is an estimate; when the exact size does not fit, the margin is reduced and the rows redone.
+                int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
+                int xloE = 0, ny = 1, rows = 0, rpt = 0, total = 0, base = 0;
+                int rowXs[E2_MAXROWS / E2_THREADS], rowLen[E2_MAXROWS / E2_THREADS];
+                bool haveBox = false;
+                int retries = 0;
+                while (hm >= 0) {
+                    const Cand c = sCand[hm];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { lo[k] = c.lo[k]; hi[k] = c.hi[k]; }
+                    const float slabD = c.dist + kappa + 0.05f;
+                    xloE = lo[0] & ~1;
+                    const int xhiT = hi[0] + 1;
+                    ny = hi[1] - lo[1] + 2;
+                    rows = ny * (hi[2] - lo[2] + 2);
+                    rpt = (rows + E2_THREADS - 1) / E2_THREADS;     // rows per thread (<= 6)
+                    int mine = 0;
+#pragma unroll
+                    for (int j = 0; j < E2_MAXROWS / E2_THREADS; ++j) {
+                        rowXs[j] = 0;
+                        rowLen[j] = 0;
+                        const int r = tid * rpt + j;
+                        if (j < rpt && r < rows) {
+                            const int bz = r / ny, by = r - bz * ny;
+                            const float cyz = nc[1] * (float)(lo[1] + by) + nc[2] * (float)(lo[2] + bz);
+                            int xs = xloE, xe = xhiT;
+                            if (fabsf(nc[0]) > 1e-3f) {
+                                const float inv = 1.0f / nc[0];
+                                const float x1 = (-slabD - cyz) * inv, x2 = (slabD - cyz) * inv;
+                                const float xa = fminf(fmaxf(fminf(x1, x2), -1.0e6f), 1.0e6f), xb = fminf(fmaxf(fmaxf(x1, x2), -1.0e6f), 1.0e6f);
+                                xs = max(xs, ((int)floorf(xa)) & ~1);
+                                xe = min(xe, (int)ceilf(xb));
+                            } else if (fabsf(cyz) > slabD) {
+                                xe = xs - 1;
+                            }
+                            if (xe >= xs) {
+                                rowXs[j] = xs;
+                                rowLen[j] = (xe - xs + 2) & ~1;
+                            }
+                            mine += rowLen[j];
+                        }
+                    }
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (lane == 31) sWarpTot[warp] = incl;
+                    __syncthreads();   // (C) warp totals visible
+                    total = 0;
+                    base = incl - mine;
+#pragma unroll
+                    for (int w2 = 0; w2 < E2_THREADS / 32; ++w2) {
+                        const int v = sWarpTot[w2];
+                        if (w2 < warp) base += v;
+                        total += v;
+                    }
+                    if (total > 0 && total <= E2_BOX_ELEMS) { haveBox = true; break; }
+                    if (++retries >= 3) break;
+                    hm -= retries;          // 1, then 2 less
+                    __syncthreads();       // sWarpTot is rewritten
+                }
+                if (!haveBox) hm = -1;
+                // rotations beyond the margin -> list for path (d); no box at all -> every rotation takes path (d)
+                const bool core = haveBox && sCls[rloc].need <= hm;
+                if (ph == 0 && rvalid && haveBox && !core) sOut[atomicAdd(&sNOut[cur], 1)] = rloc;
+                if (A.stats && tid == 0) {
+                    atomicAdd(&A.stats[0], 1ull);                                   // tiles
+                    atomicAdd(&A.stats[1], haveBox ? 1ull : 0ull);                  // tiles with a staged box
+                    atomicAdd(&A.stats[2], (unsigned long long)(hm >= 0 ? hm : 0)); // sum of margins
+                    atomicAdd(&A.stats[3], (unsigned long long)(haveBox ? total : 0));          // staged elements
+                    atomicAdd(&A.stats[5], (unsigned long long)nRc);                // (rotation, tile) pairs
+                    atomicAdd(&A.stats[6], (unsigned long long)retries);            // margin reductions (estimate too optimistic)
+                    atomicAdd(&A.stats[7], (unsigned long long)rows);
+                }
+                if (haveBox) {
+                    fence_proxy_async();
+                    if (tid == 0) mbar_arrive_expect_tx(&sBar, (uint32_t)total * 8u);
+#pragma unroll
+                    for (int j = 0; j < E2_MAXROWS / E2_THREADS; ++j) {
+                        const int r = tid * rpt + j;
+                        if (j < rpt && r < rows) {
+                            sBias[r] = base - rowXs[j] - THB_FLOOR_BIAS;
+                            if (rowLen[j] > 0) {
+                                const int bz = r / ny, by = r - bz * ny;
+                                const int ym = wrap_idx(lo[1] + by, n), zm = wrap_idx(lo[2] + bz, n);
+                                tma_bulk_g2s(box + base, vol + ((size_t)zm * n + ym) * pitch + rowXs[j], (uint32_t)rowLen[j] * 8u, &sBar);
+                            }
+                            base += rowLen[j];
+                        }
+                    }
+                }
+                __syncthreads();   // (D) out-list and row table visible
+                if (A.stats && tid == 0) atomicAdd(&A.stats[4], (unsigned long long)(haveBox ? sNOut[cur] : nRc));   // pairs on path (d)
                 // ---------------- (d) non-core rotations: pixels on the lanes, gather from L1/L2
                 {
-                    const int nOut = sNOut[cur];
+                    const int nOut = haveBox ? sNOut[cur] : nRc;
                     for (int it = warp; it < nOut; it += E2_THREADS / 32) {
-                        const int rl = sOut[it];
+                        const int rl = haveBox ? sOut[it] : it;
                         const Rot2 ro = sRot[rl];
                         float v[E_TC];
 #pragma unroll
                         for (int t = 0; t < E_TC; ++t) v[t] = 0.0f;
+#pragma unroll 2
                         for (int k = lane; k < td.count; k += 32) {
                             const PixelRec& rec = tile[k];
                             float x, y, z;
                             slice_coord(ro, rec.a, rec.b, x, y, z);
                             const float2 pr = gather_ft_pitched(vol, n, pitch, x, y, z);
-                            const float m = rec.g * (pr.x * pr.x + pr.y * pr.y);
+                            const float m = rec.g * fmaf(pr.x, pr.x, pr.y * pr.y);
 #pragma unroll
-                            for (int t = 0; t < E_TC; ++t) v[t] += rec.u[t].x * pr.x + rec.u[t].y * pr.y + m;
+                            for (int t = 0; t < E_TC; ++t) v[t] += fmaf(rec.u[t].x, pr.x, fmaf(rec.u[t].y, pr.y, m));
                         }
-#pragma unroll
-                        for (int t = 0; t < E_TC; ++t) {
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v[t] += __shfl_xor_sync(0xffffffffu, v[t], o);
-                        }
-                        if (lane == 0) {
-#pragma unroll
-                            for (int t = 0; t < E_TC; ++t) sAcc[rl * E_TC + t] += v[t];   // one warp per (rotation, tile)
-                        }
+                        float s07, s8;
+                        warp_sum9(v, lane, s07, s8);
+                        if ((lane & 3) == 0) sAcc[rl * E_TC + ((lane >> 2) & 7)] += s07;   // one warp per (rotation, tile)
+                        if (lane == 1) sAcc[rl * E_TC + 8] += s8;
                     }
                 }
                 // ---------------- (e) core rotations: gather from the staged box
                 if (haveBox) {
                     mbar_wait(&sBar, barParity);
                     barParity ^= 1;
-                    if (sCore[rloc]) {
-                        const int sy = Lx, sz = Lx * ny;
+                    if (core) {
+                        // origin of the row table in biased cell coordinates (see fold_floor_fast)
+                        const int oy = lo[1] + THB_FLOOR_BIAS, oz = lo[2] + THB_FLOOR_BIAS;
 #pragma unroll 2
                         for (int k = ph; k < td.count; k += 2) {
                             const PixelRec& rec = tile[k];
                             float x, y, z;
                             slice_coord(rot, rec.a, rec.b, x, y, z);
-                            int x0, y0, z0;
+                            int xb, yb, zb;
                             float xd, yd, zd;
-                            const bool conj = fold_floor(x, y, z, x0, y0, z0, xd, yd, zd);
+                            const bool conj = fold_floor_fast(x, y, z, xb, yb, zb, xd, yd, zd);
                             float w[8];
                             tri_weights(xd, yd, zd, w);
-                            const float2* b0 = box + ((z0 - lo[2]) * ny + (y0 - lo[1])) * Lx + (x0 - xloE);
-                            const float2 v0 = b0[0], v1 = b0[1], v2 = b0[sy], v3 = b0[sy + 1];
-                            const float2 v4 = b0[sz], v5 = b0[sz + 1], v6 = b0[sz + sy], v7 = b0[sz + sy + 1];
-                            float re = 0.0f, im = 0.0f;
-                            re += v0.x * w[0]; im += v0.y * w[0];
-                            re += v1.x * w[1]; im += v1.y * w[1];
-                            re += v2.x * w[2]; im += v2.y * w[2];
-                            re += v3.x * w[3]; im += v3.y * w[3];
-                            re += v4.x * w[4]; im += v4.y * w[4];
-                            re += v5.x * w[5]; im += v5.y * w[5];
-                            re += v6.x * w[6]; im += v6.y * w[6];
-                            re += v7.x * w[7]; im += v7.y * w[7];
+                            const int* bi = sBias + (zb - oz) * ny + (yb - oy);
+                            const float2* r0 = box + (bi[0] + xb);
+                            const float2* r1 = box + (bi[1] + xb);
+                            const float2* r2 = box + (bi[ny] + xb);
+                            const float2* r3 = box + (bi[ny + 1] + xb);
+                            const float2 v0 = r0[0], v1 = r0[1], v2 = r1[0], v3 = r1[1];
+                            const float2 v4 = r2[0], v5 = r2[1], v6 = r3[0], v7 = r3[1];
+                            float re = v0.x * w[0], im = v0.y * w[0];
+                            re = fmaf(v1.x, w[1], re); im = fmaf(v1.y, w[1], im);
+                            re = fmaf(v2.x, w[2], re); im = fmaf(v2.y, w[2], im);
+                            re = fmaf(v3.x, w[3], re); im = fmaf(v3.y, w[3], im);
+                            re = fmaf(v4.x, w[4], re); im = fmaf(v4.y, w[4], im);
+                            re = fmaf(v5.x, w[5], re); im = fmaf(v5.y, w[5], im);
+                            re = fmaf(v6.x, w[6], re); im = fmaf(v6.y, w[6], im);
+                            re = fmaf(v7.x, w[7], re); im = fmaf(v7.y, w[7], im);
                             if (conj) im = -im;
-                            nrm += rec.g * (re * re + im * im);
+                            nrm = fmaf(rec.g, fmaf(re, re, im * im), nrm);
 #pragma unroll
-                            for (int t = 0; t < E_TC; ++t) acc[t] += rec.u[t].x * re + rec.u[t].y * im;
+                            for (int t = 0; t < E_TC; ++t) acc[t] = fmaf(rec.u[t].x, re, fmaf(rec.u[t].y, im, acc[t]));
                         }
                     }
                 }
@@ -411,7 +593,6 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
             // ---- end of the pass over the tiles: combine halves, fallback sums and the constant term
             __syncthreads();
             if (firstPass) {
-                // block sum of k0sum (double)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) k0sum += __shfl_xor_sync(0xffffffffu, k0sum, o);
                 if (lane == 0) redd[warp] = k0sum;
@@ -422,7 +603,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                 __syncthreads();
             }
             // halves: ph == 1 parks its sums in the record area, ph == 0 adds everything up
-            float* park = reinterpret_cast<float*>(tile);     // 128 x 10 floats = 5 KB <= 6 KB
+            float* park = reinterpret_cast<float*>(tile);     // 128 x 10 floats = 5 KB
             if (ph == 1) {
 #pragma unroll
                 for (int t = 0; t < E_TC; ++t) park[rloc * (E_TC + 1) + t] = acc[t];

@@ -250,10 +250,17 @@ __device__ __forceinline__ void red_add_v4(float4* p, float a, float b, float c)
 }
 
 
+// MODE 0 (default): draws of one image that share the SAME rotation (the support of a resampled particle
+// filter holds many exact duplicates) are merged before the scatter: the translated image values of the
+// group are summed and scattered once, T once with the group's multiplicity.  Same sums as draw-by-draw
+// insertion up to fp32 rounding order.  MODE 2: draw-by-draw (A/B measurement).
+template <int MODE>
 __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
 {
     __shared__ Rot2 sRot[M_MAXRECO];
     __shared__ float sRC[M_MAXRECO], sRR[M_MAXRECO];
+    __shared__ double sQ[M_MAXRECO][4];
+    __shared__ unsigned short sRep[M_MAXRECO], sOrder[M_MAXRECO], sGrpEnd[M_MAXRECO];
     __shared__ double redd[M_THREADS / 32];
 
     const int l = blockIdx.x;
@@ -264,23 +271,24 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
     const int P = A.P;
     const float wgt = A.w ? A.w[l] : A.wAll;
     const double ox = A.offS ? A.offS[2 * l] : 0.0, oy = A.offS ? A.offS[2 * l + 1] : 0.0;
+    const int tid = threadIdx.x;
 
     for (int mbase = 0; mbase < A.mReco; mbase += M_MAXRECO) {
         const int mcnt = min(M_MAXRECO, A.mReco - mbase);
         __syncthreads();
         double dx = 0.0, dy = 0.0, dz = 0.0;
-        if ((int)threadIdx.x < mcnt) {
-            const int m = mbase + threadIdx.x;
+        if (tid < mcnt) {
+            const int m = mbase + tid;
             const long long sr = A.drawR ? A.drawR[(size_t)l * A.mReco + m] : m;
             const long long st = A.drawT ? A.drawT[(size_t)l * A.mReco + m] : m;
             double q[4];
-            for (int c = 0; c < 4; ++c) q[c] = A.nr.at(l, sr, c);
+            for (int c = 0; c < 4; ++c) { q[c] = A.nr.at(l, sr, c); sQ[tid][c] = q[c]; }
             const Rot2 rot = quat_to_rot2(q);
-            sRot[threadIdx.x] = rot;
+            sRot[tid] = rot;
             const double tx = A.nt.at(l, st, 0) - ox, ty = A.nt.at(l, st, 1) - oy;
             // translate(dst, src, -(tran - offset)(0), -(tran - offset)(1), ...): RFLOAT arguments
-            sRC[threadIdx.x] = (float)(-tx) / (float)A.N;
-            sRR[threadIdx.x] = (float)(-ty) / (float)A.N;
+            sRC[tid] = (float)(-tx) / (float)A.N;
+            sRR[tid] = (float)(-ty) / (float)A.N;
             // insertDir(-rot3D * (tran - offset, 0))
             dx = -(rot.c0[0] * tx + rot.c1[0] * ty);
             dy = -(rot.c0[1] * tx + rot.c1[1] * ty);
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
             dx = block_reduce_sum(dx, redd);
             dy = block_reduce_sum(dy, redd);
             dz = block_reduce_sum(dz, redd);
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 atomicAdd(&A.acc.O[3 * slot + 0], dx);
                 atomicAdd(&A.acc.O[3 * slot + 1], dy);
                 atomicAdd(&A.acc.O[3 * slot + 2], dz);
@@ -298,24 +306,61 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
             }
         }
         __syncthreads();
+        // ---- group the draws by rotation: representative = first draw with bit-identical quaternion
+        if (tid < mcnt) {
+            int rep = tid;
+            if (MODE == 0) {
+                for (int j = 0; j < tid; ++j)
+                    if (sQ[j][0] == sQ[tid][0] && sQ[j][1] == sQ[tid][1] && sQ[j][2] == sQ[tid][2] && sQ[j][3] == sQ[tid][3]) {
+                        rep = j;
+                        break;
+                    }
+            }
+            sRep[tid] = (unsigned short)rep;
+        }
+        __syncthreads();
+        bool leader = false;
+        if (tid < mcnt) {
+            const int rep = sRep[tid];
+            int pos = 0, size = 0, gidx = 0;
+            for (int j = 0; j < mcnt; ++j) {
+                const int rj = sRep[j];
+                pos += (rj < rep) || (rj == rep && j < tid);
+                size += rj == tid;
+                gidx += (rj == j) && (j < tid);
+            }
+            sOrder[pos] = (unsigned short)tid;
+            leader = rep == tid;
+            if (leader) sGrpEnd[gidx] = (unsigned short)(pos + size);
+        }
+        const int nGrp = __syncthreads_count(leader);
 
-        for (int i = blockIdx.y * M_THREADS + threadIdx.x; i < P; i += gridDim.y * M_THREADS) {
+        for (int i = blockIdx.y * M_THREADS + tid; i < P; i += gridDim.y * M_THREADS) {
             const int4 c = A.pix[i];
             const float2 d = A.dat[(size_t)img * P + i];
             const float cf = A.ctf[(size_t)img * P + i];
             const double a = (double)c.x, b = (double)c.y;
             const float tval = (cf * cf) * wgt;
-            for (int m = 0; m < mcnt; ++m) {
-                const float ph = translate_phase(c.z, c.w, sRC[m], sRR[m]);
-                float s, co;
-                sincosf(ph, &s, &co);
-                // src * COMPLEX_POLAR(-ph) = d * (co - i s)
-                const float vx = d.x * co + d.y * s;
-                const float vy = d.y * co - d.x * s;
-                const float fx = (vx * cf) * wgt;
-                float fy = (vy * cf) * wgt;
+            int start = 0;
+            for (int g = 0; g < nGrp; ++g) {
+                const int end = sGrpEnd[g];
+                float fx = 0.0f, fy = 0.0f;
+                for (int k = start; k < end; ++k) {
+                    const int m = sOrder[k];
+                    const float ph = translate_phase(c.z, c.w, sRC[m], sRR[m]);
+                    float s, co;
+                    sincosf(ph, &s, &co);
+                    // src * COMPLEX_POLAR(-ph) = d * (co - i s)
+                    const float vx = d.x * co + d.y * s;
+                    const float vy = d.y * co - d.x * s;
+                    fx += (vx * cf) * wgt;
+                    fy += (vy * cf) * wgt;
+                }
+                const float tv = tval * (float)(end - start);
+                const Rot2& rot = sRot[sOrder[start]];
+                start = end;
                 float x, y, z;
-                slice_coord(sRot[m], a, b, x, y, z);
+                slice_coord(rot, a, b, x, y, z);
                 int x0, y0, z0;
                 float xd, yd, zd;
                 if (fold_floor(x, y, z, x0, y0, z0, xd, yd, zd)) fy = -fy;
@@ -326,8 +371,8 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     float4* row = acc + off[cc] + x0;
-                    red_add_v4(row, fx * w8[2 * cc], fy * w8[2 * cc], tval * w8[2 * cc]);
-                    red_add_v4(row + 1, fx * w8[2 * cc + 1], fy * w8[2 * cc + 1], tval * w8[2 * cc + 1]);
+                    red_add_v4(row, fx * w8[2 * cc], fy * w8[2 * cc], tv * w8[2 * cc]);
+                    red_add_v4(row + 1, fx * w8[2 * cc + 1], fy * w8[2 * cc + 1], tv * w8[2 * cc + 1]);
                 }
             }
         }

@@ -73,6 +73,27 @@ THB_HD bool fold_floor(float& x, float& y, float& z, int& x0, int& y0, int& z0, 
     return conj;
 }
 
+#if defined(__CUDACC__)
+// Same results as fold_floor, without the conversion pipe: for |v| < 2^22, (v + 1.5*2^23) rounded towards
+// -inf is 1.5*2^23 + floor(v) exactly, its bit pattern is 0x4B400000 + floor(v), and v - floor(v) is exact.
+// The integer outputs are BIASED by THB_FLOOR_BIAS (callers fold the bias into their origin).
+#define THB_FLOOR_BIAS 0x4B400000
+__device__ __forceinline__ bool fold_floor_fast(float& x, float& y, float& z, int& xb, int& yb, int& zb, float& xd, float& yd,
+                                                float& zd)
+{
+    bool conj = false;
+    if (!(x >= 0.0f)) {
+        x = -x; y = -y; z = -z;
+        conj = true;
+    }
+    const float M = 12582912.0f;
+    const float tx = __fadd_rd(x, M), ty = __fadd_rd(y, M), tz = __fadd_rd(z, M);
+    xd = x - (tx - M); yd = y - (ty - M); zd = z - (tz - M);
+    xb = __float_as_int(tx); yb = __float_as_int(ty); zb = __float_as_int(tz);
+    return conj;
+}
+#endif
+
 THB_HD void tri_weights(float xd, float yd, float zd, float w[8])
 {
     const float vx0 = 1.0f - xd, vx1 = xd;

@@ -50,6 +50,7 @@ struct ExpectArgs {
     const TileDesc* tiles;
     int nTiles;
     float* work;            // [nAct][nR*nT] scratch for multi-pass shapes (nR > 128 or nT > 9), else null
+    unsigned long long* stats;   // optional [8] counters of the staging decisions (null = off)
     const float2* dat;
     const float* ctf;
     const float* sig;

@@ -29,6 +29,7 @@ quat = np.stack([synth.acg_cloud(par["quat"][l], kconc, nR, rng) for l in range(
 tran = par["tran"][:, None, :] + rng.normal(scale=0.5, size=(nImg, nT, 2))
 wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
 ctx.enable_timing(True)
+ctx.set_option("stats", 1)
 for it in range(4):
     ctx.kernel_ms(capi.KF_EXPECT, reset=True)
     out = ctx.expect_local(quat, tran, wR, wT, want_logL=False)
@@ -36,6 +37,8 @@ for it in range(4):
     bytesE = nImg * (P * 16 + nR * P * 64.0)
     print(f"E: {ms:.2f} ms  {nImg / ms * 1e3:.0f} particle-phases/s  alg {bytesE / ms / 1e6:.0f} GB/s  "
           f"{nImg * nR * P / ms / 1e6:.1f} G pixel-rot/s", flush=True)
+    if it == 0:
+        print("   staging:", ctx.expect_stats(), flush=True)
 for s in (0, 1):
     ctx.reco_alloc(s, N * pf)
 nr = quat[:, rng.integers(0, nR, mReco)]; nt = tran[:, rng.integers(0, nT, mReco)]
