@@ -86,7 +86,7 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value);
 /* staging counters of the E kernel since the last reset (enable with option "stats" = 1): tiles, tiles with a
  * shared-memory box, sum of margins, staged elements, (rotation,tile) pairs on the L1/L2 path, all pairs,
  * over-capacity tiles, box rows */
-int thb_expect_stats(thb_ctx* ctx, uint64_t out[8], int reset);
+int thb_expect_stats(thb_ctx* ctx, uint64_t out[16], int reset);   /* [8..15]: cycles per kernel phase, summed over CTAs */
 /* CUDA-event stopwatch on the library's launch stream: stop == 0 records the start, stop != 0 records the
  * end, waits for it and returns the elapsed device time in *ms */
 int thb_timer(thb_ctx* ctx, int stop, float* ms);

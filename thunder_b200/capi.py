@@ -172,9 +172,10 @@ class Context:
         self._chk(self.lib.thb_set_option(self.h, key.encode(), int(value)))
 
     def expect_stats(self, reset=True):
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(16, np.uint64)
         self._chk(self.lib.thb_expect_stats(self.h, _ptr(out), int(reset)))
-        keys = ("tiles", "tiles_boxed", "margin_sum", "staged_elems", "pairs_l2_path", "pairs", "over_capacity", "rows")
+        keys = ("tiles", "tiles_boxed", "margin_sum", "staged_elems", "pairs_l2_path", "pairs", "margin_retries", "rows", "cyc_e_and_A", "cyc_records_classify", "cyc_candidates", "cyc_rows_scan_issue", "cyc_l2_path",
+                "cyc_tma_wait", "cyc_tail", "cyc_7")
         return dict(zip(keys, (int(v) for v in out)))
 
     def enable_timing(self, on=True):

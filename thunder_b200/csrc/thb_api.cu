@@ -309,8 +309,8 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
     }
     if (!strcmp(key, "stats")) {
         if (value && !ctx->dStats) {
-            THB_CUDA(ctx, cudaMalloc(&ctx->dStats, 8 * sizeof(unsigned long long)));
-            THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 8 * sizeof(unsigned long long)));
+            THB_CUDA(ctx, cudaMalloc(&ctx->dStats, 16 * sizeof(unsigned long long)));
+            THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 16 * sizeof(unsigned long long)));
         }
         ctx->statsOn = value != 0;
         return THB_OK;
@@ -322,14 +322,14 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
     return set_error(ctx, THB_E_ARG, "set_option: unknown key %s", key);
 }
 
-int thb_expect_stats(thb_ctx* ctx, uint64_t out[8], int reset)
+int thb_expect_stats(thb_ctx* ctx, uint64_t out[16], int reset)
 {
     if (!ctx || !out) return THB_E_ARG;
     if (!ctx->dStats) return set_error(ctx, THB_E_STATE, "expect_stats: enable with thb_set_option(ctx, \"stats\", 1)");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    THB_CUDA(ctx, cudaMemcpy(out, ctx->dStats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    if (reset) THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 8 * sizeof(uint64_t)));
+    THB_CUDA(ctx, cudaMemcpy(out, ctx->dStats, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 16 * sizeof(uint64_t)));
     return THB_OK;
 }
 

@@ -84,7 +84,7 @@ struct thb_ctx {
     int insertImpl = 0;
     unsigned long long* dStats = nullptr;   // [8] staging counters of the E kernel (option "stats")
     int statsOn = 0;
-    int tileW = 16, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
+    int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
     int expectImpl = 2;          // 2: TMA-staged kernel (default), 1: the direct-gather kernel (THB_EXPECT_IMPL=1)
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];

@@ -134,6 +134,11 @@ __device__ __forceinline__ void tile_cells(const float c0[3], const float c1[3],
     }
 }
 
+#ifndef THB_E2_TIMERS
+#define THB_E2_TIMERS 1
+#endif
+#define E2_TICK(slot) do { if (THB_E2_TIMERS && A.stats && tid == 0) { const long long now_ = clock64(); tacc[slot] += now_ - tlast; tlast = now_; } } while (0)
+
 constexpr int E2_THREADS = 256;
 constexpr int E2_ROTS = 128;
 constexpr int E2_TILE = 128;                    // max pixels per tile
@@ -237,6 +242,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
     }
     uint32_t barParity = 0;
     int tileSeq = 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();   // per-phase cycles of this CTA (thread 0)
     double k0sum = 0.0;          // sum_i sig_i |dat_i|^2, accumulated by the record builders of the first pass
     __syncthreads();
 
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                 const TileDesc td = A.tiles[ti];
                 const int cur = tileSeq & 1;
                 __syncthreads();   // (A) previous tile finished: box, records, tables are free
+                E2_TICK(0);
                 {
                     // ---------------- (a) pixel records: 2 threads per pixel, translations split between them
                     const int k = tid >> 1, sub = tid & 1;
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                     sCls[rloc] = rc;
                 }
                 __syncthreads();   // (B) records and per-rotation classes visible
+                E2_TICK(1);
                 // ---------------- candidate margins, one warp each: union of the cell ranges and slab thickness of the
                 // rotations that need at most that margin, and the estimated size of the staged region
                 for (int h = warp; h < E2_NCAND; h += E2_THREADS / 32) {
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                             const float ex = (float)(hi[0] - lo[0] + 4), ey = (float)(hi[1] - lo[1] + 2), ez = (float)(hi[2] - lo[2] + 2);
                             // elements of (bounding box ^ slab): the slab passes through the middle of the box, where the
                             // cross-section is largest; its projection on the face normal to axis k cannot exceed that face,
-                            // so section <= face_k / |n_k| for every k.  + up to 3.5 elements of alignment / rounding per row.
+                            // so section <= face_k / |n_k| for every k.  + about 2 elements of alignment / rounding per row.
                             const float thick = 2.0f * (dist + kappa + 0.05f);
                             float section = 3.0e38f;
                             if (fabsf(nc[0]) > 1e-3f) section = fminf(section, ey * ez / fabsf(nc[0]));
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                             const float reach = thick + fabsf(nc[0]) * ex;
                             if (fabsf(nc[1]) > 1e-3f) rowsNE = fminf(rowsNE, ez * (reach / fabsf(nc[1]) + 2.0f));
                             if (fabsf(nc[2]) > 1e-3f) rowsNE = fminf(rowsNE, ey * (reach / fabsf(nc[2]) + 2.0f));
-                            vol = fminf(ex * ey * ez, section * thick) + 3.5f * rowsNE;
+                            vol = fminf(ex * ey * ez, section * thick) + 2.0f * rowsNE;
                             if (ey * ez > (float)E2_MAXROWS) vol = 3.0e38f;
                         }
 #pragma unroll
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                     }
                 }
                 __syncthreads();   // (B2) candidates visible
+                E2_TICK(2);
                 if (tid == 0) sNOut[cur ^ 1] = 0;
                 int hm = -1;
                 for (int h = E2_HM_MAX; h >= 0; --h)
@@ -460,8 +469,9 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                                 const float inv = 1.0f / nc[0];
                                 const float x1 = (-slabD - cyz) * inv, x2 = (slabD - cyz) * inv;
                                 const float xa = fminf(fmaxf(fminf(x1, x2), -1.0e6f), 1.0e6f), xb = fminf(fmaxf(fmaxf(x1, x2), -1.0e6f), 1.0e6f);
-                                xs = max(xs, ((int)floorf(xa)) & ~1);
-                                xe = min(xe, (int)ceilf(xb));
+                                // taps are integers: those inside [xa, xb] are ceil(xa) .. floor(xb)
+                                xs = max(xs, ((int)ceilf(xa)) & ~1);
+                                xe = min(xe, (int)floorf(xb));
                             } else if (fabsf(cyz) > slabD) {
                                 xe = xs - 1;
                             }
@@ -524,6 +534,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                     }
                 }
                 __syncthreads();   // (D) out-list and row table visible
+                E2_TICK(3);
                 if (A.stats && tid == 0) atomicAdd(&A.stats[4], (unsigned long long)(haveBox ? sNOut[cur] : nRc));   // pairs on path (d)
                 // ---------------- (d) non-core rotations: pixels on the lanes, gather from L1/L2
                 {
@@ -552,7 +563,9 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
                 }
                 // ---------------- (e) core rotations: gather from the staged box
                 if (haveBox) {
+                    E2_TICK(4);
                     mbar_wait(&sBar, barParity);
+                    E2_TICK(5);
                     barParity ^= 1;
                     if (core) {
                         // origin of the row table in biased cell coordinates (see fold_floor_fast)
@@ -592,6 +605,7 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
             }
             // ---- end of the pass over the tiles: combine halves, fallback sums and the constant term
             __syncthreads();
+            E2_TICK(6);
             if (firstPass) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) k0sum += __shfl_xor_sync(0xffffffffu, k0sum, o);
@@ -647,6 +661,8 @@ __global__ void __launch_bounds__(E2_THREADS, 2) expect_local_tma_kernel(const E
     if (tid == 0) {
         if (A.uC) A.uC[p] = (float)uc;
         if (A.base) A.base[p] = m;
+        if (THB_E2_TIMERS && A.stats)
+            for (int i = 0; i < 8; ++i) atomicAdd(&A.stats[8 + i], (unsigned long long)tacc[i]);
     }
 }
 

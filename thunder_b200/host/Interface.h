@@ -1,0 +1,81 @@
+// Interface.h - host-side mirror of THUNDER's accelerator seam for the Optimiser hot path.
+//
+// The reference's Optimiser / Reconstructor call C++ free functions declared in gpu/interface/Interface.h
+// (compiled in with -DGPU_VERSION, include/Config.h:16-25).  This header declares the SAME function names
+// with the same argument order and meaning for the functions on the hot path, implemented on top of the
+// C ABI of libthunder_b200.so (include/thunder_b200.h).  THUNDER class types in the signatures are
+// replaced by their raw storage so that the file builds without the THUNDER tree:
+//     Volume&  ->  Complex* (FFTW half-complex, x fastest) + its dimension
+//     MPI_Comm& hemi / slav  ->  dropped: the half-map reduction is thb_allreduce over the context's
+//                                persistent NCCL communicator (thb_comm_init), a no-op with one rank
+//     CTFAttr* / nD / nC (CTF search, multi-class) -> accepted and ignored by this round's kernels
+// With -DTHB_WITH_THUNDER and the THUNDER include path, the Volume& / MPI_Comm& overloads of the
+// reference are provided too (inline, forwarding to the raw versions); see INTEGRATION.md.
+//
+// Reference declarations mirrored (gpu/interface/Interface.h): getAviDevice :16, ExpectPreidx :18,
+// ExpectFreeIdx :163, ExpectRotran :199, ExpectProject :210, ExpectGlobal3D :221, InsertFT :267-318.
+// Error behaviour: the reference prints and exit(1)s on any CUDA failure (gpu/config/Device.cuh.in:27-61);
+// these functions print the library's message and abort() the same way - the C ABI underneath returns codes.
+#pragma once
+#include <vector>
+#include "../../include/thunder_b200.h"
+
+#ifdef THB_WITH_THUNDER
+#include "Precision.h"      // RFLOAT, Complex (include/Precision.h:64-106)
+#else
+typedef float RFLOAT;                       // default build: SINGLE_PRECISION (CMakeLists.txt:48)
+struct Complex { RFLOAT dat[2]; };          // include/Precision.h:100-106
+#endif
+
+// devices this process may use (reference: every visible device with compute capability >= 3)
+void getAviDevice(std::vector<int>& gpus);
+
+// ---- E-step, pixel list (Optimiser.cpp:1702-1711).  The device arrays stay inside the library: *deviCol /
+// *deviRow receive opaque non-null tokens so that caller code which only forwards them keeps working.
+void ExpectPreidx(int gpuIdx, int** deviCol, int** deviRow, int* iCol, int* iRow, int npxl);
+void ExpectFreeIdx(int gpuIdx, int** deviCol, int** deviRow);
+
+// ---- E-step, global scan (Optimiser.cpp:1815-1863).  ExpectRotran / ExpectProject fill the host arrays
+// the reference fills (traP, rotMat, rotP) AND remember trans / rot / volume; ExpectGlobal3D then runs the
+// fused kernel on them (it does not re-read rotP / traP: the projections never leave the device).
+void ExpectRotran(Complex* traP, double* trans, double* rot, double* rotMat, const int* iCol, const int* iRow, int nR,
+                  int nT, int idim, int npxl);
+void ExpectProject(Complex* volume, Complex* rotP, double* rotMat, const int* iCol, const int* iRow, int nR, int pf,
+                   int interp, int vdim, int npxl);
+void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, RFLOAT* wC, RFLOAT* wR,
+                    RFLOAT* wT, double* pR, double* pT, RFLOAT* baseL, int kIdx, int nK, int nR, int nT, int npxl,
+                    int imgNum);
+
+// ---- E-step, local search.  The reference drives one image at a time through ExpectLocalP / RTD / PreI3D / M
+// under a per-device lock (Optimiser.cpp:2813-3300); the replacement is one batched call per phase.
+//   quat[nImg][nR][4], tran[nImg][nT][2], wR[nImg][nR], wT[nImg][nT] priors; outputs uC[nImg], uR, uT as the
+//   reference's wC / wR / wT of ExpectLocalM (weights relative to the per-image maximum), baseL[nImg]
+void ExpectLocalBatch(int gpuIdx, Complex* volume, int vdim, int pf, int idim, const int* iCol, const int* iRow, int npxl,
+                      Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, int imgNum, int nR, int nT, const double* quat,
+                      const double* tran, const double* wRprior, const double* wTprior, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
+                      RFLOAT* baseL);
+
+// ---- M-step (Reconstructor::insertI, Reconstructor.cpp:867-985).  F3D / T3D are accumulated INTO, as the
+// reference does (upload, insert, all-reduce over the hemisphere, download); T3D is the complex volume of the
+// CPU class whose real part carries T (Interface.cpp:581-619).  vdim = F3D.nSlcFT().
+void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP,
+              void* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD, int* nC, const int* iCol,
+              const int* iRow, RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim, int dimSize,
+              int imgNum);
+
+#ifdef THB_WITH_THUNDER
+#include "mpi.h"
+#include "Volume.h"
+inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
+                     RFLOAT* sigRcpP, CTFAttr* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD,
+                     const int* iCol, const int* iRow, RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim,
+                     int dimSize, int imgNum)
+{
+    InsertFT(&F3D[0], &T3D[0], (int)F3D.nSlcFT(), O3D, counter, datP, ctfP, sigRcpP, (void*)ctfaData, offS, w, nR, nT, nD,
+             (int*)0, iCol, iRow, pixelSize, cSearch, opf, npxl, mReco, idim, dimSize, imgNum);
+}
+#endif
+
+// the library context of device gpuIdx (created on first use; one per device per process)
+thb_ctx* thbContext(int gpuIdx);
+void thbShutdown();
