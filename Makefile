@@ -9,7 +9,9 @@ OUT       := thunder_b200/lib/libthunder_b200.so
 OBJS      := build/thb_api.o build/thb_pf.o build/thb_comm.o
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h include/*.h)
 
-all: $(OUT) oracle
+IFACE     := thunder_b200/lib/libthb_interface.so
+
+all: $(OUT) $(IFACE) oracle
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -22,6 +24,10 @@ build/thb_comm.o: $(CSRC)/thb_comm.cpp $(HDRS)
 $(OUT): $(OBJS)
 	@mkdir -p thunder_b200/lib
 	$(NVCC) $(ARCH) -shared -Xcompiler -fPIC -o $@ $(OBJS) -Xlinker --no-as-needed -lgomp -ldl
+
+# host-side mirror of the reference's accelerator seam (C++), on top of the C ABI
+$(IFACE): thunder_b200/host/Interface.cpp thunder_b200/host/Interface.h include/thunder_b200.h $(OUT)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Iinclude -o $@ thunder_b200/host/Interface.cpp -Lthunder_b200/lib -lthunder_b200 -Wl,-rpath,'$$ORIGIN'
 
 oracle: oracle/_port/libthb_oracle.so
 

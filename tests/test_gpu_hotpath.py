@@ -266,9 +266,10 @@ def test_error_paths(ctx):
 # ------------------------------------------------------------------------------------------- TMA-staged kernel
 @pytest.mark.parametrize("k,nR,nT", [(1e-7, 125, 9), (2e-5, 125, 9), (3e-4, 125, 9), (5e-2, 64, 9), (2e-5, 200, 9), (2e-5, 40, 13),
                                       (2e-5, 131, 20)])
-def test_expect_staged_equals_direct_and_oracle(ctx, problem, k, nR, nT):
-    """the shared-memory-box kernel (default) against the direct-gather kernel and the oracle, from clouds that
-    stay inside one box (k small) to clouds that spill into the L1/L2 path (k large), multi-pass shapes included"""
+def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT):
+    """the three E kernels (quad-layout direct gather = default, TMA-staged box, linear direct gather) against each
+    other and the oracle, from clouds that stay inside one staged box (k small) to clouds that spill into its
+    L1/L2 path (k large), multi-pass shapes (nR > 128, nT > 9) included"""
     pb = problem
     port, ref = _oracle()
     _setup_E(ctx, pb)
@@ -278,18 +279,27 @@ def test_expect_staged_equals_direct_and_oracle(ctx, problem, k, nR, nT):
     tran = pb["par"]["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
     wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
     try:
-        ctx.set_option("expect_impl", 2)
+        ctx.set_option("expect_impl", 3)      # default: direct gather from the quad layout
         a = ctx.expect_local(quat, tran, wR, wT)
-        ctx.set_option("expect_impl", 1)
+        ctx.set_option("expect_minb", 3)
+        a3 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_minb", 2)
+        ctx.set_option("expect_impl", 2)      # TMA-staged shared-memory box
+        c = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
         b = ctx.expect_local(quat, tran, wR, wT)
     finally:
-        ctx.set_option("expect_impl", 2)
-    # each kernel carries its own fp32 summation error (the direct kernel sums ~3000 terms sequentially)
+        ctx.set_option("expect_impl", 3)
+    # each kernel carries its own fp32 summation error (the linear-layout kernel sums ~3000 terms sequentially)
     tol = 2e-6 * np.abs(b["logL"]).max() + 1e-4
+    assert np.array_equal(a["logL"], a3["logL"])          # register allocation must not change results
     assert np.abs(a["logL"] - b["logL"]).max() <= 2 * tol
+    assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
+    assert np.abs(c["logL"] - a["logL"]).max() <= tol
     for l in (0, nImg - 1):
         o = port.expect_local(pb["vols"][pb["slot"][l]], pb["pf"], pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"],
                               pb["par"]["dat"][l], pb["par"]["ctf"][l], pb["par"]["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
         assert np.abs(a["logL"][l] - o["logL"]).max() <= tol
+        assert np.abs(c["logL"][l] - o["logL"]).max() <= tol
     big = b["uR"] > 1e-6 * b["uR"].max(axis=1, keepdims=True)
     assert np.all(np.abs(np.log(a["uR"][big]) - np.log(b["uR"][big])) <= 20 * np.finfo(np.float32).eps * np.abs(b["logL"]).max() + 2e-3)

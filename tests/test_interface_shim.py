@@ -1,0 +1,143 @@
+"""The host-side mirror of the reference's accelerator seam (thunder_b200/host/Interface.{h,cpp}): the same
+function names and argument order as gpu/interface/Interface.h for the hot path, on top of the C ABI.
+
+CPU: the library exports the mirrored names (C++ linkage) and, where the reference tree is present, the
+signatures are checked against the reference's own header text.  GPU: calling through the shims gives the
+oracle's numbers."""
+import ctypes as C
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from thunder_b200 import synth
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "thunder_b200" / "lib" / "libthb_interface.so"
+REF_HDR = Path(os.environ.get("THB_REFERENCE", "/root/reference")) / "gpu" / "interface" / "Interface.h"
+MIRRORED = ["getAviDevice", "ExpectPreidx", "ExpectFreeIdx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "InsertFT"]
+_p, _i = C.c_void_p, C.c_int
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+def test_shim_exports_mirrored_names():
+    assert LIB.exists(), "run `make` / __graft_entry__.build()"
+    out = subprocess.check_output(["nm", "-DC", os.fspath(LIB)]).decode()
+    for name in MIRRORED + ["ExpectLocalBatch"]:
+        assert re.search(rf"\bT {name}\(", out), name
+
+
+def _params(text, name):
+    """argument names of the first declaration of `name` in a header, in order"""
+    m = re.search(rf"\bvoid\s+{name}\s*\((.*?)\)\s*;", text, flags=re.S)
+    assert m, name
+    args = [a.strip() for a in m.group(1).replace("\n", " ").split(",")]
+    return [re.sub(r".*[\s\*&]", "", a) for a in args]
+
+
+@pytest.mark.skipif(not REF_HDR.exists(), reason="reference tree not present")
+def test_argument_order_matches_reference_header():
+    """same argument names in the same order as gpu/interface/Interface.h, THUNDER class arguments replaced as
+    thunder_b200/host/Interface.h documents (Volume& -> pointer + vdim, MPI_Comm& dropped)"""
+    ref = REF_HDR.read_text()
+    ours = (ROOT / "thunder_b200" / "host" / "Interface.h").read_text()
+    for name in ("ExpectPreidx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D"):
+        assert _params(ours, name) == _params(ref, name), name
+    want = [a for a in _params(ref, "InsertFT") if a not in ("hemi", "slav")]
+    got = [a for a in _params(ours, "InsertFT") if a != "vdim"]
+    assert got == want
+
+
+@pytest.fixture(scope="module")
+def shim():
+    L = C.CDLL(os.fspath(LIB))
+    L.thbi_device_count.restype = _i
+    if L.thbi_device_count() == 0:
+        pytest.skip("no GPU")
+    yield L
+    L.thbi_shutdown()
+
+
+@pytest.mark.gpu
+def test_scan_and_local_through_the_shims(shim):
+    from oracle import portapi as port
+    N, pf = 32, 2
+    rng = np.random.default_rng(5)
+    vol = synth.padded_ft(synth.phantom(N, 8, seed=2), pf)
+    pix = port.pixel_list(N, pf, 14.0, 1.0)
+    iCol, iRow = pix["iCol"], pix["iRow"]
+    P = len(iCol)
+    nImg, nR, nT = 5, 20, 7
+    par = synth.make_particles(nImg, N, pix, lambda q: np.stack([port.project(vol, pf, port.rotate3D(x), iCol, iRow) for x in q]),
+                               seed=3, snr_scale=4.0)
+    rot = synth.random_quats(nR, rng); rot[:nImg] = par["quat"]
+    trans = rng.normal(scale=1.5, size=(nT, 2))
+    pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
+    traP = np.zeros((nT, P), np.complex64); rotMat = np.zeros((nR, 9)); rotP = np.zeros((nR, P), np.complex64)
+    shim.thbi_ExpectRotran(_ptr(traP), _ptr(trans), _ptr(rot), _ptr(rotMat), _ptr(iCol), _ptr(iRow), nR, nT, N, P)
+    for r in range(nR):      # column-major 3x3, as the oracle's rotate3D (Euler.cpp:181-189)
+        assert np.allclose(rotMat[r], port.rotate3D(rot[r]), atol=1e-14)
+    volc = np.ascontiguousarray(vol)
+    shim.thbi_ExpectProject(_ptr(volc), _ptr(rotP), _ptr(rotMat), _ptr(iCol), _ptr(iRow), nR, pf, 1, N * pf, P)
+    nK = 2
+    wC = np.zeros((nImg, nK), np.float32); wR = np.zeros((nImg, nK, nR), np.float32); wT = np.zeros((nImg, nK, nT), np.float32)
+    baseL = np.zeros(nImg, np.float32)
+    dat = np.ascontiguousarray(par["dat"]); ctf = np.ascontiguousarray(par["ctf"]); sig = np.ascontiguousarray(par["sigRcp"])
+    for k in range(nK):      # the same volume as two "classes": equal weights, one shared baseline
+        shim.thbi_ExpectGlobal3D(_ptr(rotP), _ptr(traP), _ptr(dat), _ptr(ctf), _ptr(sig), _ptr(wC), _ptr(wR), _ptr(wT), _ptr(pR), _ptr(pT),
+                                 _ptr(baseL), k, nK, nR, nT, P, nImg)
+    for l in range(nImg):
+        o = port.expect_local(vol, pf, N, iCol, iRow, par["dat"][l], par["ctf"][l], par["sigRcp"][l], rot, trans, pR, pT)
+        assert abs(baseL[l] - o["base"]) <= 2e-6 * abs(o["base"]) + 1e-4
+        big = o["uR"] > 1e-5 * o["uR"].max()
+        for k in range(nK):
+            assert np.allclose(wR[l, k][big], o["uR"][big], rtol=5e-3)
+            assert np.allclose(wC[l, k], o["uC"], rtol=5e-3)
+        assert np.argmax(wR[l, 0]) == l          # the true orientation of image l is rotation l of the scan
+    # batched local search through the shim == the scan restricted to one image's own cloud
+    quat = np.stack([synth.acg_cloud(par["quat"][l], 1e-4, nR, rng) for l in range(nImg)])
+    tran = par["tran"][:, None, :] + rng.normal(scale=0.5, size=(nImg, nT, 2))
+    wRp = np.full((nImg, nR), 1.0 / nR); wTp = np.full((nImg, nT), 1.0 / nT)
+    uC = np.zeros(nImg, np.float32); uR = np.zeros((nImg, nR), np.float32); uT = np.zeros((nImg, nT), np.float32); bl = np.zeros(nImg, np.float32)
+    shim.thbi_ExpectLocalBatch(0, _ptr(volc), N * pf, pf, N, _ptr(iCol), _ptr(iRow), P, _ptr(dat), _ptr(ctf), _ptr(sig), nImg, nR, nT,
+                               _ptr(quat), _ptr(tran), _ptr(wRp), _ptr(wTp), _ptr(uC), _ptr(uR), _ptr(uT), _ptr(bl))
+    for l in range(nImg):
+        o = port.expect_local(vol, pf, N, iCol, iRow, par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l], tran[l], wRp[l], wTp[l])
+        assert abs(bl[l] - o["base"]) <= 2e-6 * abs(o["base"]) + 1e-4
+        big = o["uT"] > 1e-5 * o["uT"].max()
+        assert np.allclose(uT[l][big], o["uT"][big], rtol=5e-3)
+
+
+@pytest.mark.gpu
+def test_insertft_through_the_shim_accumulates_into_the_callers_volumes(shim):
+    from oracle import portapi as port
+    N, pf = 32, 2
+    rng = np.random.default_rng(8)
+    pixM = port.pixel_list(N, pf, 15.0, 0.0)
+    PM = len(pixM["iCol"])
+    nImg, mReco, vdim = 4, 5, N * pf
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    nr = synth.random_quats(nImg * mReco, rng).reshape(nImg, mReco, 4)
+    nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    w = np.full(nImg, 1.0 / mReco, np.float32)
+    offS = rng.normal(scale=0.5, size=(nImg, 2))
+    nVox = (vdim // 2 + 1) * vdim * vdim
+    F0 = (rng.normal(size=nVox) + 1j * rng.normal(size=nVox)).astype(np.complex64)     # contents already in the caller's volumes
+    T0 = rng.uniform(0, 1, nVox).astype(np.complex64)
+    F3D, T3D = F0.copy(), T0.copy()
+    O3D = np.array([1.0, 2.0, 3.0]); counter = np.array([7], np.int32)
+    shim.thbi_InsertFT(_ptr(F3D), _ptr(T3D), vdim, _ptr(O3D), _ptr(counter), _ptr(datM), _ptr(ctfM), _ptr(offS), _ptr(w), _ptr(nr), _ptr(nt),
+                       _ptr(pixM["iColPad"]), _ptr(pixM["iRowPad"]), pf, PM, mReco, N, nVox, nImg)
+    want = port.insert_loop(vdim, pf, N, datM, ctfM, w, offS, nr, nt, pixM["iCol"], pixM["iRow"])
+    rel = lambda a, b: np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+    assert rel(F3D - F0, want["F"].ravel()) <= 1e-6
+    assert rel((T3D - T0).real, want["T"].ravel()) <= 1e-6
+    assert np.allclose(O3D - [1.0, 2.0, 3.0], want["O"], rtol=1e-10, atol=1e-10)
+    assert counter[0] == 7 + nImg * mReco

@@ -9,6 +9,7 @@
 #include "thb_context.h"
 #include "thb_kernels.cuh"
 #include "thb_expect2.cuh"
+#include "thb_expect3.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -90,6 +91,53 @@ VolTable vol_table(const thb_ctx* ctx)
     return t;
 }
 
+VolTable quad_table(const thb_ctx* ctx)
+{
+    VolTable t;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) t.p[i] = reinterpret_cast<const float2*>(ctx->vols[i].quad);
+    return t;
+}
+
+// quad layout of slot `slot` (built lazily: only the quad kernel needs the 4x copy)
+static int ensure_quad(thb_ctx* ctx, int slot)
+{
+    Volume3& v = ctx->vols[slot];
+    if (!v.d || v.quad) return THB_OK;
+    const size_t elems = (size_t)v.vdim * v.vdim * (v.vdim / 2);
+    THB_CUDA(ctx, cudaMalloc(&v.quad, elems * sizeof(Quad)));
+    span_begin(ctx, KF_PACK);
+    build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, reinterpret_cast<Quad*>(v.quad));
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
+static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
+{
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) {
+        int rc = ensure_quad(ctx, i);
+        if (rc) return rc;
+    }
+    a.quads = quad_table(ctx);
+    a.work = nullptr;
+    const bool single = a.nR <= E3_ROTS && a.nT <= E_TC;
+    if (!single) {
+        a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
+        if (!a.work) return THB_E_CUDA;
+    }
+    const size_t smem = E3_SMEM_BYTES + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
+    span_begin(ctx, KF_EXPECT);
+    if (ctx->expectMinBlocks >= 3)
+        expect_direct_kernel<3><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+    else
+        expect_direct_kernel<2><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
 AccTable acc_table(const thb_ctx* ctx)
 {
     AccTable t;
@@ -125,6 +173,7 @@ static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
 int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a)
 {
     if (a.nAct <= 0) return THB_OK;
+    if (ctx->expectImpl == 3) return launch_expect_v3(ctx, a);
     if (ctx->expectImpl == 2) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)
@@ -202,7 +251,8 @@ int thb_create(thb_ctx** out, int device)
     thb_ctx* ctx = new thb_ctx();
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
-    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(3, atoi(e)));
+    if (const char* e = getenv("THB_EXPECT_MINB")) ctx->expectMinBlocks = atoi(e) >= 3 ? 3 : 2;
     if (const char* e = getenv("THB_INSERT_IMPL")) ctx->insertImpl = atoi(e);
     if (const char* e = getenv("THB_TILE_W")) ctx->tileW = std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("THB_TILE_H")) ctx->tileH = std::max(1, std::min(E2_TILE / ctx->tileW, atoi(e)));
@@ -237,6 +287,7 @@ void thb_destroy(thb_ctx* ctx)
     pf_free(ctx);
     for (int i = 0; i < THB_MAX_SLOTS; ++i) {
         cudaFree(ctx->vols[i].d);
+        cudaFree(ctx->vols[i].quad);
         cudaFree(ctx->accs[i].d);
     }
     free_stack(ctx->stackE);
@@ -297,7 +348,7 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
 {
     if (!ctx || !key) return THB_E_ARG;
     if (!strcmp(key, "expect_impl")) {
-        if (value != 1 && value != 2) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 or 2");
+        if (value < 1 || value > 3) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1, 2 or 3");
         ctx->expectImpl = value;
         return THB_OK;
     }
@@ -305,6 +356,10 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
         if (value < 1 || value > 16) return set_error(ctx, THB_E_ARG, "set_option: tile_w / tile_h must be in [1,16]");
         (key[5] == 'w' ? ctx->tileW : ctx->tileH) = value;
         if (ctx->tileW * ctx->tileH > E2_TILE) return set_error(ctx, THB_E_ARG, "set_option: tile_w * tile_h must be <= %d", E2_TILE);
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_minb")) {
+        ctx->expectMinBlocks = value >= 3 ? 3 : 2;
         return THB_OK;
     }
     if (!strcmp(key, "stats")) {
@@ -498,6 +553,11 @@ int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
     Volume3& v = ctx->vols[slot];
     const int pitch = vol_pitch(vdim);
     const size_t rows = (size_t)vdim * vdim;
+    if (v.quad) {   // the quad copy belongs to the previous contents
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(v.quad);
+        v.quad = nullptr;
+    }
     if (v.vdim != vdim) {
         cudaFree(v.d);
         v.d = nullptr;

@@ -31,6 +31,7 @@ struct Volume3 {
     float2* d = nullptr;
     int vdim = 0;
     int pitch = 0;
+    void* quad = nullptr;        // quad layout for the direct-gather kernel: n*n*(n/2) x 32 bytes (built on upload)
 };
 
 struct Accum {
@@ -85,7 +86,8 @@ struct thb_ctx {
     unsigned long long* dStats = nullptr;   // [8] staging counters of the E kernel (option "stats")
     int statsOn = 0;
     int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
-    int expectImpl = 2;          // 2: TMA-staged kernel (default), 1: the direct-gather kernel (THB_EXPECT_IMPL=1)
+    int expectImpl = 3;          // 3: direct gather from the quad layout (default), 2: TMA-staged box, 1: direct gather, linear layout
+    int expectMinBlocks = 2;     // CTAs per SM the quad kernel is compiled for (2 or 3)
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];
     thb::Accum accs[thb::THB_MAX_SLOTS];

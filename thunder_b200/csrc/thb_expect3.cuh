@@ -1,0 +1,240 @@
+// thb_expect3.cuh - fused E kernel, local-search shape, direct gather from a "quad" volume layout.
+//
+// One CTA per image, 256 threads = 8 warps: warp w serves rotation group (w & 3) - one rotation sample
+// per lane - and pixel half (w >> 2).  The image is walked in tiles of 128 pixels whose records (pixel
+// coordinates and the image turned by the conjugate phase ramp of each translation, pre-multiplied for the
+// expanded likelihood) are built once in shared memory and broadcast to all rotations.
+//
+// HBM layout of the projector volume for this kernel ("quad"): element (x, y, z) holds the four taps
+//   { V(x,y,z), V(x+1,y,z), V(x,y+1,z), V(x+1,y+1,z) }      32 bytes, y+1 wrapped as the reference wraps it
+// so that one 8-tap trilinear cell is TWO 256-bit loads (LDG.256: z and z+1) instead of eight 64-bit
+// ones.  The gather of a cloud of orientations is bound by the number of distinct L1 lines a warp-wide load
+// touches, not by bytes: fewer, wider loads move the same lines with a quarter of the instructions
+// (measured: tools/gpu/gatherbench.cu).  4x the volume bytes (2.2 GB at box 256) buys that.
+//
+// Likelihood in the expanded form (see thb_expect2.cuh): 2 FMAs per (sample, translation).
+// Coordinates, fold, floor, weights follow the reference exactly (src/Projector.cpp:356-374,
+// src/Image/Volume.cpp:314-338, include/Functions/Interpolation.h:187-200).
+#pragma once
+#include <cuda_runtime.h>
+#include "thb_math.cuh"
+#include "thb_types.cuh"
+#include "thb_expect2.cuh"   // PixelRec
+
+namespace thb {
+
+struct __align__(32) Quad { float2 v00, v10, v01, v11; };   // (x,y) (x+1,y) (x,y+1) (x+1,y+1)
+
+__device__ __forceinline__ Quad ldg_quad(const Quad* p)
+{
+    Quad q;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(q.v00.x), "=f"(q.v00.y), "=f"(q.v10.x), "=f"(q.v10.y), "=f"(q.v01.x), "=f"(q.v01.y), "=f"(q.v11.x), "=f"(q.v11.y)
+                 : "l"(p));
+    return q;
+}
+
+// linear pitched float2 volume -> quad layout [(z*n + y)*half + x], x in [0, half)
+__global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pitch, Quad* __restrict__ out)
+{
+    const int half = n / 2;
+    const size_t total = (size_t)n * n * half;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % half);
+        const size_t row = i / half;
+        const int y = (int)(row % n), z = (int)(row / n);
+        const int y1 = (y + 1 == n) ? 0 : y + 1;     // memory row of (y + 1): the wrap of Volume.h:567-575
+        const float2* r0 = vol + ((size_t)z * n + y) * pitch + x;
+        const float2* r1 = vol + ((size_t)z * n + y1) * pitch + x;
+        Quad q;
+        q.v00 = r0[0]; q.v10 = r0[1]; q.v01 = r1[0]; q.v11 = r1[1];
+        out[i] = q;
+    }
+}
+
+constexpr int E3_THREADS = 256;
+constexpr int E3_ROTS = 128;
+constexpr int E3_TILE = 128;
+constexpr size_t E3_SMEM_BYTES = E3_TILE * sizeof(PixelRec);     // + the [nR][nT] table for single-pass shapes
+
+template <int MINB>
+__global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const ExpectArgs A)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PixelRec* tile = reinterpret_cast<PixelRec*>(smem_raw);
+    __shared__ float sRC[E_TC], sRR[E_TC];
+    __shared__ float redf[E3_THREADS / 32];
+    __shared__ double redd[E3_THREADS / 32];
+
+    const int p = blockIdx.x;
+    if (A.active && !A.active[p]) return;
+    const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
+    const int slot = A.slotOfImg ? A.slotOfImg[img] : 0;
+    const Quad* __restrict__ vol = reinterpret_cast<const Quad*>(A.quads.p[slot]);
+    const int n = A.vdim, half = n / 2;
+    const int P = A.P;
+    const float2* __restrict__ dat = A.dat + (size_t)img * P;
+    const float* __restrict__ ctf = A.ctf + (size_t)img * P;
+    const float* __restrict__ sig = A.sig + (size_t)img * P;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rloc = (warp & 3) * 32 + lane;   // rotation slot of this thread within a pass
+    const int ph = warp >> 2;                  // pixel half
+    const int nRT = A.nR * A.nT;
+    const bool single = A.nR <= E3_ROTS && A.nT <= E_TC;
+    float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_SMEM_BYTES) : A.work + (size_t)p * nRT;
+    double k0sum = 0.0;          // sum_i sig_i |dat_i|^2
+    const int zstride = n * half;
+
+    for (int rbase = 0; rbase < A.nR; rbase += E3_ROTS) {
+        const int nRc = min(E3_ROTS, A.nR - rbase);
+        const bool rvalid = rloc < nRc;
+        Rot2 rot;
+        {
+            double q[4] = {1.0, 0.0, 0.0, 0.0};
+            if (rvalid)
+                for (int c = 0; c < 4; ++c) q[c] = A.quat.at(p, rbase + rloc, c);
+            rot = quat_to_rot2(q);
+        }
+        for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
+            __syncthreads();
+            if (tid < E_TC) {
+                const int t = tbase + tid;
+                float tx = 0.0f, ty = 0.0f;
+                if (t < A.nT) {
+                    tx = (float)A.tran.at(p, t, 0);
+                    ty = (float)A.tran.at(p, t, 1);
+                }
+                sRC[tid] = tx / (float)A.N;
+                sRR[tid] = ty / (float)A.N;
+            }
+            float acc[E_TC];
+#pragma unroll
+            for (int t = 0; t < E_TC; ++t) acc[t] = 0.0f;
+            float nrm = 0.0f;
+            const bool firstPass = (rbase == 0 && tbase == 0);
+
+            for (int tile0 = 0; tile0 < P; tile0 += E3_TILE) {
+                const int cnt = min(E3_TILE, P - tile0);
+                __syncthreads();   // previous tile consumed (also orders the sRC / sRR writes)
+                {
+                    // pixel records: 2 threads per pixel, translations split between them
+                    const int k = tid >> 1, sub = tid & 1;
+                    if (k < cnt) {
+                        const int i = tile0 + k;
+                        const int4 c = A.pix[i];
+                        const float2 d = dat[i];
+                        const float cf = ctf[i], sg = sig[i];
+                        const float m2 = -2.0f * sg * cf;
+                        PixelRec& rec = tile[k];
+                        if (sub == 0) {
+                            rec.a = (double)c.x;
+                            rec.b = (double)c.y;
+                            rec.g = sg * cf * cf;
+                            rec.pad = 0.0f;
+                            if (firstPass) k0sum += (double)(sg * (d.x * d.x + d.y * d.y));
+                        }
+#pragma unroll
+                        for (int t = 0; t < E_TC; ++t) {
+                            if ((t & 1) != sub) continue;
+                            const float phs = translate_phase(c.z, c.w, sRC[t], sRR[t]);
+                            float s, co;
+                            sincosf(phs, &s, &co);
+                            // tra = (cos(-ph), sin(-ph)); dat * conj(tra) = dat * (co + i s)
+                            rec.u[t] = make_float2(m2 * (d.x * co - d.y * s), m2 * (d.x * s + d.y * co));
+                        }
+                    }
+                }
+                __syncthreads();
+                if (rvalid) {
+#pragma unroll 2
+                    for (int k = ph; k < cnt; k += 2) {
+                        const PixelRec& rec = tile[k];
+                        float x, y, z;
+                        slice_coord(rot, rec.a, rec.b, x, y, z);
+                        int xb, yb, zb;
+                        float xd, yd, zd;
+                        const bool conj = fold_floor_fast(x, y, z, xb, yb, zb, xd, yd, zd);
+                        const int x0 = xb - THB_FLOOR_BIAS, y0 = yb - THB_FLOOR_BIAS, z0 = zb - THB_FLOOR_BIAS;
+                        const int ym = y0 < 0 ? y0 + n : y0;
+                        const int zm = z0 < 0 ? z0 + n : z0;
+                        const int zm1 = (z0 + 1 < 0) ? z0 + 1 + n : z0 + 1;
+                        const Quad* q0 = vol + ((size_t)zm * zstride + (size_t)ym * half + x0);
+                        const Quad* q1 = vol + ((size_t)zm1 * zstride + (size_t)ym * half + x0);
+                        const Quad a = ldg_quad(q0), b = ldg_quad(q1);
+                        float w[8];
+                        tri_weights(xd, yd, zd, w);
+                        float re = a.v00.x * w[0], im = a.v00.y * w[0];
+                        re = fmaf(a.v10.x, w[1], re); im = fmaf(a.v10.y, w[1], im);
+                        re = fmaf(a.v01.x, w[2], re); im = fmaf(a.v01.y, w[2], im);
+                        re = fmaf(a.v11.x, w[3], re); im = fmaf(a.v11.y, w[3], im);
+                        re = fmaf(b.v00.x, w[4], re); im = fmaf(b.v00.y, w[4], im);
+                        re = fmaf(b.v10.x, w[5], re); im = fmaf(b.v10.y, w[5], im);
+                        re = fmaf(b.v01.x, w[6], re); im = fmaf(b.v01.y, w[6], im);
+                        re = fmaf(b.v11.x, w[7], re); im = fmaf(b.v11.y, w[7], im);
+                        if (conj) im = -im;
+                        nrm = fmaf(rec.g, fmaf(re, re, im * im), nrm);
+#pragma unroll
+                        for (int t = 0; t < E_TC; ++t) acc[t] = fmaf(rec.u[t].x, re, fmaf(rec.u[t].y, im, acc[t]));
+                    }
+                }
+            }
+            // ---- end of the pass: constant term, halves
+            __syncthreads();
+            if (firstPass) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) k0sum += __shfl_xor_sync(0xffffffffu, k0sum, o);
+                if (lane == 0) redd[warp] = k0sum;
+                __syncthreads();
+                double s = 0.0;
+                for (int w2 = 0; w2 < E3_THREADS / 32; ++w2) s += redd[w2];
+                k0sum = s;
+                __syncthreads();
+            }
+            float* park = reinterpret_cast<float*>(tile);     // 128 x 10 floats = 5 KB
+            if (ph == 1) {
+#pragma unroll
+                for (int t = 0; t < E_TC; ++t) park[rloc * (E_TC + 1) + t] = acc[t];
+                park[rloc * (E_TC + 1) + E_TC] = nrm;
+            }
+            __syncthreads();
+            if (ph == 0 && rvalid) {
+                const double nn = (double)nrm + (double)park[rloc * (E_TC + 1) + E_TC];
+#pragma unroll
+                for (int t = 0; t < E_TC; ++t)
+                    if (tbase + t < A.nT)
+                        sL[(size_t)(rbase + rloc) * A.nT + tbase + t] =
+                            (float)(k0sum + nn + (double)acc[t] + (double)park[rloc * (E_TC + 1) + t]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- epilogue: baseline, weights, marginals (Optimiser.cpp:1383-1402) ----------
+    float m = -INFINITY;
+    for (int i = tid; i < nRT; i += E3_THREADS) m = fmaxf(m, sL[i]);
+    m = block_reduce_max(m, redf);
+    if (A.logL)
+        for (int i = tid; i < nRT; i += E3_THREADS) A.logL[(size_t)p * nRT + i] = sL[i];
+    __syncthreads();
+    for (int i = tid; i < nRT; i += E3_THREADS) sL[i] = expf(sL[i] - m);
+    __syncthreads();
+    double uc = 0.0;
+    for (int r = tid; r < A.nR; r += E3_THREADS) {
+        float s = 0.0f;
+        for (int t = 0; t < A.nT; ++t) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wT.at(p, t, 0));
+        if (A.uR) A.uR[(size_t)p * A.nR + r] = s;
+        uc += (double)s * A.wR.at(p, r, 0);
+    }
+    for (int t = tid; t < A.nT; t += E3_THREADS) {
+        float s = 0.0f;
+        for (int r = 0; r < A.nR; ++r) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wR.at(p, r, 0));
+        if (A.uT) A.uT[(size_t)p * A.nT + t] = s;
+    }
+    uc = block_reduce_sum(uc, redd);
+    if (tid == 0) {
+        if (A.uC) A.uC[p] = (float)uc;
+        if (A.base) A.base[p] = m;
+    }
+}
+
+}  // namespace thb

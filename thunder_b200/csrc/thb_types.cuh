@@ -45,6 +45,7 @@ struct TileDesc {
 
 struct ExpectArgs {
     VolTable vols;
+    VolTable quads;         // the same volumes in the quad layout (thb_expect3.cuh), or null
     int vdim;
     int pitch;              // row pitch of the volumes in elements (>= vdim/2 + 2, multiple of 4)
     const TileDesc* tiles;
