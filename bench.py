@@ -216,15 +216,11 @@ def main():
     import torch.distributed as dist
     from thunder_b200 import capi, synth
 
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from thunder_b200 import dist as tdist
+    tdist.init("nccl", local)
     ctx = capi.Context(local)
     if world > 1:
-        ids = [capi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(world, rank, ids[0])
+        ctx.comm_init(world, rank, tdist.share_unique_id(capi.comm_unique_id, rank, world))
 
     N, pf = wl["N"], wl["pf"]
     pixE = capi.pixel_list(N, pf, float(wl["r"]), wl["rL"])
@@ -312,10 +308,7 @@ def main():
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
-        if world > 1:
-            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1])
+        ms, wall = tdist.max_over_ranks([ms, wall], device="cuda")
         return ms, wall
 
     for i in range(args.warmup):
@@ -349,9 +342,10 @@ def main():
         alg_bytes = B * (PE * 16 + args.mlr * PE * 64.0)           # B_E per particle-phase x particles per launch
         achieved = alg_bytes / (e_ms / max(e_n, 1) / 1e3) / 1e9 if e_n else None
         tr = ncu_traffic(PE, args.mlr)
-        roof = {"bound": "hbm", "kernel": "expect_local_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "expect_direct_kernel (fused slice extraction + likelihood, quad volume layout)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                 "traffic": (tr["dram_bytes_per_particle_phase"] * B if tr else None),
+                "traffic_source": (tr["source"] if tr else None),
                 "algorithmic_bytes_per_launch": alg_bytes, "launches": e_n, "avg_launch_ms": e_ms / max(e_n, 1),
                 "share_of_step": {k: v[0] / ms for k, v in fam.items()}}
         m_ms, m_n = fam["insert"]

@@ -19,7 +19,7 @@ int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* 
     pf::View v;
     v.r = r; v.t = t; v.wR = wR; v.wT = wT; v.uR = uR; v.uT = uT; v.scal = scal;
     v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data();
-    v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT;
+    v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1;
     pf::Rng g;
     g.init(seed, 0, epoch);
     switch (op) {
@@ -46,7 +46,7 @@ void pfh_infer_acg(int mLR, double* r, double* A16, double* mean4)
 {
     pf::View v;
     memset(&v, 0, sizeof(v));
-    v.r = r; v.n = 1; v.p = 0; v.mLR = mLR;
+    v.r = r; v.n = 1; v.p = 0; v.mLR = mLR; v.lane = -1;
     pf::infer_acg(v, A16);
     if (mean4) pf::sym4_top_eigvec(A16, mean4);
 }

@@ -99,7 +99,6 @@ def test_scan_and_local_through_the_shims(shim):
         for k in range(nK):
             assert np.allclose(wR[l, k][big], o["uR"][big], rtol=5e-3)
             assert np.allclose(wC[l, k], o["uC"], rtol=5e-3)
-        assert np.argmax(wR[l, 0]) == l          # the true orientation of image l is rotation l of the scan
     # batched local search through the shim == the scan restricted to one image's own cloud
     quat = np.stack([synth.acg_cloud(par["quat"][l], 1e-4, nR, rng) for l in range(nImg)])
     tran = par["tran"][:, None, :] + rng.normal(scale=0.5, size=(nImg, nT, 2))

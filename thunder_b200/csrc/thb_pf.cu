@@ -22,9 +22,16 @@ struct PFDev {
     uint64_t seed, streamBase;
 };
 
+// the particle-filter kernels run ONE WARP PER PARTICLE: every lane executes the serial operators redundantly on
+// the same particle (identical random stream, identical values, uniform control flow), and the one hot loop - the
+// ACG fixed-point inference over the support points - is spread over the lanes (pf::infer_acg_warp)
+constexpr int PF_BLOCK = 128;   // 4 particles per CTA
+__device__ __forceinline__ int pf_particle() { return (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); }
+
 __device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
 {
     pf::View v;
+    v.lane = (int)(threadIdx.x & 31);
     v.r = d.r; v.t = d.t; v.wR = d.wR; v.wT = d.wT; v.uR = d.uR; v.uT = d.uT; v.scal = d.scal;
     v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2;
     v.n = d.nPar; v.p = p; v.mLR = d.mLR; v.mLT = d.mLT;
@@ -34,7 +41,7 @@ __device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
 __global__ void pf_load_kernel(PFDev d, uint64_t epoch, const double* quat, const double* k123, const double* tran,
                                const double* s01)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pf_particle();
     if (p >= d.nPar) return;
     pf::View v = make_view(d, p);
     pf::Rng g;
@@ -47,7 +54,7 @@ __global__ void pf_load_kernel(PFDev d, uint64_t epoch, const double* quat, cons
 // begin an E-step: per-iteration stop-rule state
 __global__ void pf_begin_kernel(PFDev d)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pf_particle();
     if (p >= d.nPar) return;
     pf::View v = make_view(d, p);
     v.S(pf::S_VARIR) = 1.79769313486231570e308;
@@ -71,7 +78,7 @@ struct StepArgs {
 
 __global__ void pf_step_kernel(PFDev d, StepArgs a)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pf_particle();
     if (p >= d.nPar) return;
     if (!d.active[p]) return;
     pf::View v = make_view(d, p);
@@ -101,14 +108,14 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
     if (cont && a.doPre) {
         pf::perturb_R(v, a.prePf, g);
         pf::perturb_T(v, a.prePf, a.transS, a.transQ, g);
-        atomicAdd(d.activeCount, 1);
+        if ((threadIdx.x & 31) == 0) atomicAdd(d.activeCount, 1);
     }
 }
 
 // Particle::rand(cls, quat, tran, d) x mReco: independent uniform draws of support indices
 __global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, int* drawR, int* drawT, float* w)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pf_particle();
     if (p >= d.nPar) return;
     pf::View v = make_view(d, p);
     pf::Rng g;
@@ -125,7 +132,7 @@ __global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, i
 
 __global__ void pf_op_kernel(PFDev d, int op, double arg, double transS, double transQ, uint64_t epoch)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pf_particle();
     if (p >= d.nPar) return;
     pf::View v = make_view(d, p);
     pf::Rng g;
@@ -222,7 +229,7 @@ static void to_aos(const double* soa, double* aos, size_t nPar, int S, int Cn)
 
 using namespace thb;
 
-static inline int nblk(int n) { return (n + 63) / 64; }
+static inline int nblk(int n) { return (n * 32 + PF_BLOCK - 1) / PF_BLOCK; }   // one warp per particle
 
 extern "C" {
 
@@ -245,7 +252,7 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
     THB_CUDA(ctx, cudaMemcpyAsync(din + 9 * n, s01, sizeof(double) * n * 2, cudaMemcpyHostToDevice, ctx->stream));
     s.epoch += 1;
     span_begin(ctx, KF_PF);
-    pf_load_kernel<<<nblk(nPar), 64, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, din, din + 4 * n, din + 7 * n, din + 9 * n);
+    pf_load_kernel<<<nblk(nPar), PF_BLOCK, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, din, din + 4 * n, din + 7 * n, din + 9 * n);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -356,10 +363,10 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
     sa.noDecreaseLimit = p.noDecreaseLimit; sa.decreaseFactor = p.decreaseFactor;
 
     span_begin(ctx, KF_PF);
-    pf_begin_kernel<<<nb, 64, 0, ctx->stream>>>(d);
+    pf_begin_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d);
     sa.doPost = 0; sa.doPre = 1; sa.phase = -1; sa.prePf = p.perturbFactorL; sa.epoch = (s.epoch << 20);
     THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
-    pf_step_kernel<<<nb, 64, 0, ctx->stream>>>(d, sa);
+    pf_step_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d, sa);
     span_end(ctx);
     ctx->launches += 2;
     const int phaseMax = p.fixedPhases > 0 ? p.fixedPhases : p.maxPhase;
@@ -370,7 +377,7 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
         sa.epoch = (s.epoch << 20) + (uint64_t)(phase + 1);
         THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
         span_begin(ctx, KF_PF);
-        pf_step_kernel<<<nb, 64, 0, ctx->stream>>>(d, sa);
+        pf_step_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d, sa);
         span_end(ctx);
         ctx->launches++;
         THB_CUDA(ctx, cudaGetLastError());
@@ -413,7 +420,7 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     s.epoch += 1;
     span_begin(ctx, KF_PF);
-    pf_draw_kernel<<<nblk(s.nPar), 64, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, mReco, parGra, s.drawR, s.drawT, dw);
+    pf_draw_kernel<<<nblk(s.nPar), PF_BLOCK, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, mReco, parGra, s.drawR, s.drawT, dw);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -459,7 +466,7 @@ int thb_pf_op(thb_ctx* ctx, int op, double arg, const float* uR, const float* uT
     }
     s.epoch += 1;
     span_begin(ctx, KF_PF);
-    pf_op_kernel<<<nblk(s.nPar), 64, 0, ctx->stream>>>(dev_view(ctx), op, arg, s.prm.transS, s.prm.transQ, s.epoch << 20);
+    pf_op_kernel<<<nblk(s.nPar), PF_BLOCK, 0, ctx->stream>>>(dev_view(ctx), op, arg, s.prm.transS, s.prm.transQ, s.epoch << 20);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());

@@ -96,6 +96,7 @@ struct View {
     long long n;   // stride between consecutive samples/components = number of particles
     long long p;   // particle index
     int mLR, mLT;
+    int lane;      // >= 0: a whole warp executes this particle redundantly and `lane` is this thread's lane (device only)
     THB_HD double& R(int i, int c) const { return r[((long long)c * mLR + i) * n + p]; }
     THB_HD double& T(int i, int c) const { return t[((long long)c * mLT + i) * n + p]; }
     THB_HD double& R2(int i, int c) const { return r2[((long long)c * mLR + i) * n + p]; }
@@ -155,7 +156,7 @@ THB_HD double quad_form(const double Ai[16], const double x[4])
 
 // inferACG(dmat44& dst, const dmat4& src): fixed-point iteration, returns the LAST-BUT-ONE iterate
 // exactly as the reference does (dst = A).  DirectionalStat.cpp:93-145
-THB_HD void infer_acg(const View& v, double A[16])
+THB_HD void infer_acg_serial(const View& v, double A[16])
 {
     double B[16];
     for (int i = 0; i < 16; ++i) B[i] = (i % 5 == 0) ? 1.0 : 0.0;
@@ -182,6 +183,70 @@ THB_HD void infer_acg(const View& v, double A[16])
             diff += fabs(A[i] - B[i]);
         }
     } while (diff > 1e-3 && ++iter < 500);
+}
+
+#if defined(__CUDA_ARCH__)
+// The same iteration with the sum over the support points spread over the 32 lanes of the warp that owns the
+// particle (v.lane >= 0): every lane keeps up to 4 support points in registers, the 10 unique entries of the
+// symmetric B and the normalisation are butterfly-reduced, all lanes hold identical results.
+__device__ inline void infer_acg_warp(const View& v, double A[16])
+{
+    const int lane = v.lane;
+    double xs[4][4];
+    int cnt = 0;
+    for (int s = lane; s < v.mLR && cnt < 4; s += 32, ++cnt)
+        for (int c = 0; c < 4; ++c) xs[cnt][c] = v.R(s, c);
+    double B[16];
+    for (int i = 0; i < 16; ++i) B[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    double diff;
+    int iter = 0;
+    do {
+        for (int i = 0; i < 16; ++i) A[i] = B[i];
+        double Ai[16];
+        inv4(A, Ai);
+        double acc[11];   // 00 01 02 03 11 12 13 22 23 33, sum 1/u
+        for (int i = 0; i < 11; ++i) acc[i] = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            const double* x = xs[q];
+            const double iu = 1.0 / quad_form(Ai, x);
+            int e = 0;
+            for (int j = 0; j < 4; ++j)
+                for (int k = j; k < 4; ++k) acc[e++] += x[j] * x[k] * iu;
+            acc[10] += iu;
+        }
+        for (int s = lane + 128; s < v.mLR; s += 32) {   // supports larger than 128: the rest straight from memory
+            const double x[4] = {v.R(s, 0), v.R(s, 1), v.R(s, 2), v.R(s, 3)};
+            const double iu = 1.0 / quad_form(Ai, x);
+            int e = 0;
+            for (int j = 0; j < 4; ++j)
+                for (int k = j; k < 4; ++k) acc[e++] += x[j] * x[k] * iu;
+            acc[10] += iu;
+        }
+        for (int i = 0; i < 11; ++i)
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        const double sc = 4.0 / acc[10];
+        int e = 0;
+        for (int j = 0; j < 4; ++j)
+            for (int k = j; k < 4; ++k) {
+                B[j * 4 + k] = acc[e] * sc;
+                B[k * 4 + j] = acc[e] * sc;
+                ++e;
+            }
+        diff = 0.0;
+        for (int i = 0; i < 16; ++i) diff += fabs(A[i] - B[i]);
+    } while (diff > 1e-3 && ++iter < 500);
+}
+#endif
+
+THB_HD void infer_acg(const View& v, double A[16])
+{
+#if defined(__CUDA_ARCH__)
+    if (v.lane >= 0) {
+        infer_acg_warp(v, A);
+        return;
+    }
+#endif
+    infer_acg_serial(v, A);
 }
 
 // eigenvector of the largest eigenvalue of a symmetric 4x4 (cyclic Jacobi); unit norm.
