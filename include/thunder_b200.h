@@ -16,6 +16,7 @@
  *   thb_set_insert_pixels     Reconstructor::setPreCal               src/Reconstructor.cpp (setPreCal), InsertFT args iCol/iRow
  *   thb_set_volume            ExpectLocalV3D / ManagedArrayTexture   gpu/interface/Interface.h:31-164
  *                             (Projector::projectee3D(), src/Projector.cpp:123-148)
+ *   thb_pack_stack            Optimiser::allocPreCal + CTF()         src/Optimiser.cpp:8043-8171, src/CTF.cpp:118-151
  *   thb_upload_stack          ExpectLocalP / the datP,ctfP,sigRcpP   src/Optimiser.cpp:8043-8171 (allocPreCal)
  *                             arguments of ExpectGlobal3D, InsertFT
  *   thb_project               Projector::project(Complex*,...)       src/Projector.cpp:356-374
@@ -117,6 +118,18 @@ int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const f
 int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity);
 int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf,
                         const float* sigRcp, const int* slotOfImg);
+
+/* a2 on the device - Optimiser::allocPreCal (src/Optimiser.cpp:8043-8171, image-major, OPTIMISER_CTF_ON_THE_FLY):
+ * fill images [base, base+nImg) of a reserved stack from their full half-complex FTs (_img for the E stack, _imgOri
+ * for the M stack; imgFT[nImg][(N/2+1)*N] complex64, FFTW layout):  dat = img[iPxl], sigRcp = sigRcpTab[group][iSig]
+ * (E stack only; the reference's _sigRcp = -0.5 / sigma^2, nGroup x nRing), ctf = CTF() of src/CTF.cpp:118-151 from
+ * ctfAttr[nImg][7] = {voltage, defocusU, defocusV, defocusTheta, Cs, amplitudeContrast, phaseShift}.
+ * iPxl / iSig come from thb_pixel_list; groupOfImg (0-based) may be NULL = group 0. */
+int thb_pack_stack(thb_ctx* ctx, int kind, int base, int nImg, const float* imgFT, const int* iPxl, const int* iSig,
+                   const float* sigRcpTab, int nGroup, int nRing, const int* groupOfImg, const float* ctfAttr,
+                   float pixelSize, const int* slotOfImg);
+/* a resident stack back in the caller's pixel order: dat[nImg][nPxl][2], ctf, sigRcp (any may be NULL) */
+int thb_download_stack(thb_ctx* ctx, int kind, int base, int nImg, float* dat, float* ctf, float* sigRcp);
 
 /* ---------------------------------------------------------------- a4/a5: slice extraction */
 /* dst[nRot][nPxl] complex64 (host) = Projector::project for each rotation (quat[nRot][4]) */

@@ -303,3 +303,139 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         assert np.abs(c["logL"][l] - o["logL"]).max() <= tol
     big = b["uR"] > 1e-6 * b["uR"].max(axis=1, keepdims=True)
     assert np.all(np.abs(np.log(a["uR"][big]) - np.log(b["uR"][big])) <= 20 * np.finfo(np.float32).eps * np.abs(b["logL"]).max() + 2e-3)
+
+
+# ------------------------------------------------------------------------------------------- a2: packing on the device
+def test_pack_stack_matches_allocPreCal(ctx):
+    """thb_pack_stack == Optimiser::allocPreCal (image-major) + CTF(): gather by iPxl, sigma table by iSig, CTF on the fly"""
+    port, ref = _oracle()
+    N, pf = 64, 2
+    rng = np.random.default_rng(31)
+    pixE = port.pixel_list(N, pf, 30.0, 1.0)
+    pixM = port.pixel_list(N, pf, 31.0, 0.0)
+    nImg, nGroup, nRing = 5, 3, N // 2 + 1
+    imgFT = (rng.normal(size=(nImg, N, N // 2 + 1)) + 1j * rng.normal(size=(nImg, N, N // 2 + 1))).astype(np.complex64)
+    sigRcpTab = (-0.5 / rng.uniform(0.5, 2.0, (nGroup, nRing))).astype(np.float32)
+    group = rng.integers(0, nGroup, nImg).astype(np.int32)
+    attr = np.stack([np.full(nImg, 3e5), rng.uniform(1e4, 3e4, nImg), rng.uniform(1e4, 3e4, nImg), rng.uniform(0, np.pi, nImg),
+                     np.full(nImg, 2.7e7), np.full(nImg, 0.1), rng.uniform(0, 0.3, nImg)], axis=1).astype(np.float32)
+    slot = np.array([0, 1, 1, 0, 1], np.int32)
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+    flat = imgFT.reshape(nImg, -1)
+    for kind, pix in ((capi.STACK_EXPECT, pixE), (capi.STACK_INSERT, pixM)):
+        ctx.stack_reserve(kind, nImg + 2)
+        E = kind == capi.STACK_EXPECT
+        ctx.pack_stack(kind, 1, imgFT, pix["iPxl"], attr, 1.32, iSig=pix["iSig"] if E else None, sigRcpTab=sigRcpTab if E else None,
+                       groupOfImg=group if E else None, slotOfImg=slot)
+        got = ctx.download_stack(kind, 1, nImg)
+        assert np.array_equal(got["dat"], flat[:, pix["iPxl"]])                       # a gather: bit-exact
+        if E:
+            assert np.array_equal(got["sigRcp"], sigRcpTab[group][:, pix["iSig"]])
+        for l in range(nImg):
+            want = port.ctf(1.32, *[float(x) for x in attr[l]], N, pix["iCol"], pix["iRow"])
+            assert np.abs(got["ctf"][l] - want).max() <= 4e-6                       # sinf / cosf of a phase of O(100) rad
+    # the packed E stack drives the kernel like an uploaded one
+    ctx.set_volume(0, synth.padded_ft(synth.phantom(N, 6, seed=9), pf)); ctx.set_volume(1, synth.padded_ft(synth.phantom(N, 6, seed=8), pf))
+    ctx.stack_reserve(capi.STACK_EXPECT, nImg)
+    ctx.pack_stack(capi.STACK_EXPECT, 0, imgFT, pixE["iPxl"], attr, 1.32, iSig=pixE["iSig"], sigRcpTab=sigRcpTab, groupOfImg=group, slotOfImg=slot)
+    packed = ctx.download_stack(capi.STACK_EXPECT, 0, nImg)
+    q = synth.random_quats(7, rng)[None].repeat(nImg, 0); t = rng.normal(size=(nImg, 3, 2))
+    a = ctx.expect_local(q, t, np.full((nImg, 7), 1 / 7), np.full((nImg, 3), 1 / 3))
+    ctx.upload_stack(capi.STACK_EXPECT, packed["dat"], packed["ctf"], packed["sigRcp"], slot)
+    b = ctx.expect_local(q, t, np.full((nImg, 7), 1 / 7), np.full((nImg, 3), 1 / 3))
+    assert np.array_equal(a["logL"], b["logL"])
+
+
+# ------------------------------------------------------------------------------------------- BASELINE size, box 256
+def test_box256_expect_and_insert_against_oracle():
+    """the benchmark configuration itself (box 256, pf 2, r = 127: 25 134 pixels, 125 x 9 samples, mReco 100) for a few
+    images against the oracle, plus size-independent properties of the full-size insert (linearity, T >= 0, Hermitian
+    consistency of the x = 0 plane is NOT enforced by insertP and therefore not asserted)"""
+    port, ref = _oracle()
+    N, pf = 256, 2
+    rng = np.random.default_rng(2560)
+    vol = synth.padded_ft(synth.phantom(N, 30), pf)
+    pixE = port.pixel_list(N, pf, float(N // 2 - 1), float(np.floor(N * 1.32 / 200.0)))
+    pixM = port.pixel_list(N, pf, float(N // 2 - 1), 0.0)
+    assert len(pixE["iCol"]) == 25134 and len(pixM["iCol"]) == 25135
+    c = capi.Context(0)
+    try:
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_volume(0, vol)
+        nImg, nR, nT = 2, 125, 9
+        par = synth.make_particles(nImg, N, pixE, lambda q: c.project(0, q), seed=11)
+        c.upload_stack(capi.STACK_EXPECT, par["dat"], par["ctf"], par["sigRcp"])
+        quat = np.stack([synth.acg_cloud(par["quat"][l], 2e-5, nR, rng) for l in range(nImg)])
+        tran = par["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
+        wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
+        out = c.expect_local(quat, tran, wR, wT)
+        for l in range(nImg):
+            o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
+            assert np.abs(out["logL"][l] - o["logL"]).max() <= 2e-6 * np.abs(o["logL"]).max() + 1e-4
+            assert np.argmax(out["uR"][l]) == np.argmax(o["uR"])
+        # slices at full size: project == oracle
+        got = c.project(0, quat[0, :3])
+        for i in range(3):
+            want = port.project(vol, pf, port.rotate3D(quat[0, i]), pixE["iCol"], pixE["iRow"])
+            assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+        del vol
+        # M at full size
+        PM = len(pixM["iCol"])
+        mReco = 100
+        datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+        ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+        nr = np.stack([synth.acg_cloud(par["quat"][l], 2e-5, mReco, rng) for l in range(nImg)])
+        nr[:, 50:] = nr[:, :50]                              # duplicated rotations: the merged-draw path
+        nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+        w = np.full(nImg, 1.0 / mReco, np.float32)
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        c.upload_stack(capi.STACK_INSERT, datM, ctfM)
+        c.reco_alloc(0, N * pf)
+        c.insert(w, nr, nt)
+        a = c.reco_download(0)
+        want = port.insert_loop(N * pf, pf, N, datM, ctfM, w, np.zeros((nImg, 2)), nr, nt, pixM["iCol"], pixM["iRow"])
+        assert a["counter"] == nImg * mReco
+        assert _rel_l2(a["F"], want["F"]) <= 1e-6 and _rel_l2(a["T"], want["T"]) <= 1e-6
+        assert a["T"].min() >= 0.0
+        c.set_option("insert_impl", 2)                         # draw-by-draw insertion gives the same volume
+        c.reco_reset(0)
+        c.insert(w, nr, nt)
+        b = c.reco_download(0)
+        c.set_option("insert_impl", 0)
+        assert _rel_l2(b["F"], a["F"]) <= 1e-6
+        c.insert(w, nr, nt)                                    # linearity: twice the list = twice the volume
+        b2 = c.reco_download(0)
+        assert _rel_l2(b2["F"], 2 * a["F"]) <= 1e-6 and b2["counter"] == 2 * a["counter"]
+    finally:
+        c.close()
+
+
+def test_edge_cases(ctx, problem):
+    """single pixel tile remainders, one rotation / one translation, a pixel list with the DC pixel (rL = 0), identity and
+    axis-aligned rotations (integer coordinates, samples exactly on the Hermitian fold x = 0)"""
+    pb = problem
+    port, ref = _oracle()
+    N, pf = pb["N"], pb["pf"]
+    pix0 = port.pixel_list(N, pf, 9.5, 0.0)                   # includes (0,0); 0 <= i
+    ctx.set_expect_pixels(N, pf, pix0["iCol"], pix0["iRow"])
+    ctx.set_volume(0, pb["vols"][0]); ctx.set_volume(1, pb["vols"][1])
+    rng = np.random.default_rng(4)
+    P = len(pix0["iCol"])
+    dat = (rng.normal(size=(1, P)) + 1j * rng.normal(size=(1, P))).astype(np.complex64)
+    ctf = rng.uniform(-1, 1, (1, P)).astype(np.float32); sig = np.full((1, P), -0.5, np.float32)
+    ctx.upload_stack(capi.STACK_EXPECT, dat, ctf, sig)
+    s2 = np.sqrt(0.5)
+    quat = np.array([[[1, 0, 0, 0], [s2, 0, 0, s2], [s2, s2, 0, 0], [s2, 0, s2, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [0.5, 0.5, 0.5, 0.5]]], float)
+    tran = np.zeros((1, 1, 2))
+    out = ctx.expect_local(quat, tran, np.full((1, 8), 1 / 8), np.ones((1, 1)))
+    o = port.expect_local(pb["vols"][0], pf, N, pix0["iCol"], pix0["iRow"], dat[0], ctf[0], sig[0], quat[0], tran[0], np.full(8, 1 / 8), np.ones(1))
+    assert np.abs(out["logL"][0] - o["logL"]).max() <= 2e-6 * np.abs(o["logL"]).max() + 1e-4
+    got = ctx.project(0, quat[0])
+    for i in range(8):
+        want = port.project(pb["vols"][0], pf, port.rotate3D(quat[0, i]), pix0["iCol"], pix0["iRow"])
+        assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max(), i
+    with pytest.raises(capi.ThbError):                         # empty inputs are refused, not silently accepted
+        ctx.expect_local(np.zeros((0, 1, 4)), np.zeros((0, 1, 2)), np.zeros((0, 1)), np.zeros((0, 1)))
+    with pytest.raises(capi.ThbError):
+        ctx.expect_local(quat, tran, np.full((1, 8), 1 / 8), np.ones((1, 1)), imgIdx=np.array([5], np.int32))

@@ -65,6 +65,8 @@ def _sig(lib):
     f = lib.thb_upload_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, _p, _p]
     f = lib.thb_stack_reserve; f.restype = _i; f.argtypes = [_p, _i, _i]
     f = lib.thb_upload_stack_at; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
+    f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
@@ -244,6 +246,25 @@ class Context:
         assert dat.dtype == np.complex64 and dat.flags.c_contiguous and ctf.dtype == np.float32 and ctf.flags.c_contiguous
         slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
         self._chk(self.lib.thb_upload_stack_at(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sigRcp), _ptr(slotOfImg)))
+
+    def pack_stack(self, kind, base, imgFT, iPxl, ctfAttr, pixelSize, iSig=None, sigRcpTab=None, groupOfImg=None, slotOfImg=None):
+        """Optimiser::allocPreCal on the device: imgFT[nImg][N][N/2+1] complex64 full half-FTs, ctfAttr[nImg][7]"""
+        imgFT = _arr(imgFT, np.complex64)
+        nImg = imgFT.shape[0]
+        iPxl = _arr(iPxl, np.int32); iSig = _arr(iSig, np.int32)
+        ctfAttr = _arr(ctfAttr, np.float32, (nImg, 7))
+        sigRcpTab = _arr(sigRcpTab, np.float32)
+        nGroup, nRing = (sigRcpTab.shape if sigRcpTab is not None else (0, 0))
+        groupOfImg = _arr(groupOfImg, np.int32, (nImg,)); slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
+        self._chk(self.lib.thb_pack_stack(self.h, kind, base, nImg, _ptr(imgFT), _ptr(iPxl), _ptr(iSig), _ptr(sigRcpTab), nGroup, nRing,
+                                          _ptr(groupOfImg), _ptr(ctfAttr), float(pixelSize), _ptr(slotOfImg)))
+
+    def download_stack(self, kind, base, nImg):
+        P = self.nPxlE if kind == STACK_EXPECT else self.nPxlM
+        dat = np.empty((nImg, P), np.complex64); ctf = np.empty((nImg, P), np.float32)
+        sig = np.empty((nImg, P), np.float32) if kind == STACK_EXPECT else None
+        self._chk(self.lib.thb_download_stack(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sig)))
+        return dict(dat=dat, ctf=ctf, sigRcp=sig)
 
     # ---- E
     def project(self, slot, quat):

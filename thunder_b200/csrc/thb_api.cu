@@ -654,6 +654,97 @@ int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float*
     return THB_OK;
 }
 
+// a2 on the device: images [base, base+nImg) of a reserved stack packed from full half-complex FTs
+int thb_pack_stack(thb_ctx* ctx, int kind, int base, int nImg, const float* imgFT, const int* iPxl, const int* iSig,
+                   const float* sigRcpTab, int nGroup, int nRing, const int* groupOfImg, const float* ctfAttr, float pixelSize,
+                   const int* slotOfImg)
+{
+    if (!ctx) return THB_E_ARG;
+    if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "pack_stack: bad kind");
+    const bool E = kind == THB_STACK_EXPECT;
+    const int P = E ? ctx->nPxlE : ctx->nPxlM;
+    const int N = E ? ctx->N : ctx->NM;
+    const int4* pix = E ? ctx->pixE : ctx->pixM;
+    const int* perm = E ? ctx->permE : ctx->permM;
+    Stack& s = E ? ctx->stackE : ctx->stackM;
+    if (P <= 0) return set_error(ctx, THB_E_STATE, "pack_stack: pixel list for this stack kind not set");
+    if (!s.dat) return set_error(ctx, THB_E_STATE, "pack_stack: stack not reserved (thb_stack_reserve)");
+    if (nImg <= 0 || !imgFT || !iPxl || !ctfAttr || pixelSize <= 0) return set_error(ctx, THB_E_ARG, "pack_stack: bad arguments");
+    if (E && (!iSig || !sigRcpTab || nGroup <= 0 || nRing <= 0)) return set_error(ctx, THB_E_ARG, "pack_stack: sigma table required for the E stack");
+    if (base < 0 || base + nImg > s.nImg) return set_error(ctx, THB_E_ARG, "pack_stack: images [%d,%d) exceed the capacity %d", base, base + nImg, s.nImg);
+    const size_t imgElems = (size_t)(N / 2 + 1) * N;
+    for (int i = 0; i < P; ++i)
+        if (iPxl[i] < 0 || (size_t)iPxl[i] >= imgElems || (E && (iSig[i] < 0 || iSig[i] >= nRing)))
+            return set_error(ctx, THB_E_ARG, "pack_stack: iPxl / iSig[%d] out of range", i);
+    for (int l = 0; l < nImg; ++l) {
+        if (groupOfImg && (groupOfImg[l] < 0 || groupOfImg[l] >= std::max(nGroup, 1))) return set_error(ctx, THB_E_ARG, "pack_stack: groupOfImg[%d] out of range", l);
+        if (slotOfImg && (slotOfImg[l] < 0 || slotOfImg[l] >= THB_MAX_SLOTS)) return set_error(ctx, THB_E_ARG, "pack_stack: slotOfImg[%d] out of range", l);
+    }
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int* dIdx = (int*)scratch(ctx, 0, sizeof(int) * (2 * (size_t)P + nImg) + sizeof(float) * ((size_t)std::max(nGroup, 1) * std::max(nRing, 1) + 7 * (size_t)nImg));
+    if (!dIdx) return THB_E_CUDA;
+    int* dPxl = dIdx; int* dSig = dPxl + P; int* dGrp = dSig + P;
+    float* dTab = (float*)(dGrp + nImg); float* dAttr = dTab + (size_t)std::max(nGroup, 1) * std::max(nRing, 1);
+    THB_CUDA(ctx, cudaMemcpyAsync(dPxl, iPxl, sizeof(int) * P, cudaMemcpyHostToDevice, ctx->stream));
+    if (E) {
+        THB_CUDA(ctx, cudaMemcpyAsync(dSig, iSig, sizeof(int) * P, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dTab, sigRcpTab, sizeof(float) * (size_t)nGroup * nRing, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (groupOfImg) THB_CUDA(ctx, cudaMemcpyAsync(dGrp, groupOfImg, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dAttr, ctfAttr, sizeof(float) * 7 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, ((size_t)256 << 20) / (imgElems * sizeof(float2))));
+    float2* dImg = (float2*)scratch(ctx, 4, (size_t)chunk * imgElems * sizeof(float2));
+    if (!dImg) return THB_E_CUDA;
+    for (int i0 = 0; i0 < nImg; i0 += chunk) {
+        const int c = std::min(chunk, nImg - i0);
+        THB_CUDA(ctx, cudaMemcpyAsync(dImg, imgFT + 2 * (size_t)i0 * imgElems, (size_t)c * imgElems * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        const size_t doff = (size_t)(base + i0) * P;
+        dim3 grid(std::min((P + 255) / 256, 64), c);
+        span_begin(ctx, KF_PACK);
+        pack_stack_kernel<<<grid, 256, 0, ctx->stream>>>(dImg, imgElems, pix, perm, dPxl, E ? dSig : nullptr, P, E ? dTab : nullptr, nRing,
+                                                         groupOfImg ? dGrp + i0 : nullptr, reinterpret_cast<const CtfAttr7*>(dAttr) + i0, pixelSize, N,
+                                                         s.dat + doff, s.ctf + doff, E ? s.sig + doff : nullptr);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+    }
+    if (slotOfImg)
+        THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+// resident stack back to the host in the caller's pixel order (any output may be NULL)
+int thb_download_stack(thb_ctx* ctx, int kind, int base, int nImg, float* dat, float* ctf, float* sigRcp)
+{
+    if (!ctx) return THB_E_ARG;
+    if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "download_stack: bad kind");
+    const bool E = kind == THB_STACK_EXPECT;
+    const int P = E ? ctx->nPxlE : ctx->nPxlM;
+    const int* perm = E ? ctx->permE : ctx->permM;
+    Stack& s = E ? ctx->stackE : ctx->stackM;
+    if (!s.dat) return set_error(ctx, THB_E_STATE, "download_stack: no stack");
+    if (nImg <= 0 || base < 0 || base + nImg > s.nImg) return set_error(ctx, THB_E_ARG, "download_stack: bad range");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)nImg * P;
+    float2* dd = (float2*)scratch(ctx, 4, n * sizeof(float2));
+    float* dc = (float*)scratch(ctx, 5, n * sizeof(float));
+    float* ds = (float*)scratch(ctx, 6, n * sizeof(float));
+    if (!dd || !dc || !ds) return THB_E_CUDA;
+    const size_t off = (size_t)base * P;
+    dim3 grid(std::min((P + 255) / 256, 64), nImg);
+    unpermute_stack_kernel<<<grid, 256, 0, ctx->stream>>>(s.dat + off, s.ctf + off, s.sig ? s.sig + off : nullptr, perm, P, dd, dc, ds);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    if (dat) THB_CUDA(ctx, cudaMemcpyAsync(dat, dd, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctf) THB_CUDA(ctx, cudaMemcpyAsync(ctf, dc, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sigRcp && s.sig) THB_CUDA(ctx, cudaMemcpyAsync(sigRcp, ds, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
 int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const float* ctf, const float* sigRcp,
                      const int* slotOfImg)
 {
