@@ -31,7 +31,10 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "particles/sec per Optimiser iteration (box 256^2)"
+try:
+    METRIC = json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+except Exception:
+    METRIC = "particles/sec per Optimiser iteration (box 256\u00b2) at 1/2/4/8 B200"
 UNIT = "particles/s"
 
 

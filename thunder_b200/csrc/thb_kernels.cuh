@@ -335,44 +335,64 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
         }
         const int nGrp = __syncthreads_count(leader);
 
-        for (int i = blockIdx.y * M_THREADS + tid; i < P; i += gridDim.y * M_THREADS) {
-            const int4 c = A.pix[i];
-            const float2 d = A.dat[(size_t)img * P + i];
-            const float cf = A.ctf[(size_t)img * P + i];
-            const double a = (double)c.x, b = (double)c.y;
-            const float tval = (cf * cf) * wgt;
+        // M_KP pixels per thread in registers; per rotation group the rotation and the draws' phase ramps are read from
+        // shared memory ONCE for all of them (the reduction traffic owns the memory-instruction queue of the SM)
+        for (int i0 = blockIdx.y * M_THREADS * M_KP; i0 < P; i0 += gridDim.y * M_THREADS * M_KP) {
+            int4 c[M_KP];
+            float2 d[M_KP];
+            float cf[M_KP];
+#pragma unroll
+            for (int k = 0; k < M_KP; ++k) {
+                const int i = i0 + k * M_THREADS + tid;
+                const bool ok = i < P;
+                c[k] = ok ? A.pix[i] : make_int4(0, 0, 0, 0);
+                d[k] = ok ? A.dat[(size_t)img * P + i] : make_float2(0.f, 0.f);
+                cf[k] = ok ? A.ctf[(size_t)img * P + i] : 0.f;
+            }
             int start = 0;
             for (int g = 0; g < nGrp; ++g) {
                 const int end = sGrpEnd[g];
-                float fx = 0.0f, fy = 0.0f;
-                for (int k = start; k < end; ++k) {
-                    const int m = sOrder[k];
-                    const float ph = translate_phase(c.z, c.w, sRC[m], sRR[m]);
-                    float s, co;
-                    sincosf(ph, &s, &co);
-                    // src * COMPLEX_POLAR(-ph) = d * (co - i s)
-                    const float vx = d.x * co + d.y * s;
-                    const float vy = d.y * co - d.x * s;
-                    fx += (vx * cf) * wgt;
-                    fy += (vy * cf) * wgt;
-                }
-                const float tv = tval * (float)(end - start);
-                const Rot2& rot = sRot[sOrder[start]];
-                start = end;
-                float x, y, z;
-                slice_coord(rot, a, b, x, y, z);
-                int x0, y0, z0;
-                float xd, yd, zd;
-                if (fold_floor(x, y, z, x0, y0, z0, xd, yd, zd)) fy = -fy;
-                float w8[8];
-                tri_weights(xd, yd, zd, w8);
-                int64_t off[4];
-                row_offsets(y0, z0, n, nColFT, off);
+                float fx[M_KP], fy[M_KP];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    float4* row = acc + off[cc] + x0;
-                    red_add_v4(row, fx * w8[2 * cc], fy * w8[2 * cc], tv * w8[2 * cc]);
-                    red_add_v4(row + 1, fx * w8[2 * cc + 1], fy * w8[2 * cc + 1], tv * w8[2 * cc + 1]);
+                for (int k = 0; k < M_KP; ++k) fx[k] = fy[k] = 0.0f;
+                for (int q = start; q < end; ++q) {
+                    const int m = sOrder[q];
+                    const float rc = sRC[m], rr = sRR[m];
+#pragma unroll
+                    for (int k = 0; k < M_KP; ++k) {
+                        const float ph = translate_phase(c[k].z, c[k].w, rc, rr);
+                        float s, co;
+                        sincosf(ph, &s, &co);
+                        // src * COMPLEX_POLAR(-ph) = d * (co - i s)
+                        const float vx = d[k].x * co + d[k].y * s;
+                        const float vy = d[k].y * co - d[k].x * s;
+                        fx[k] += (vx * cf[k]) * wgt;
+                        fy[k] += (vy * cf[k]) * wgt;
+                    }
+                }
+                const float mult = (float)(end - start);
+                const Rot2 rot = sRot[sOrder[start]];
+                start = end;
+#pragma unroll
+                for (int k = 0; k < M_KP; ++k) {
+                    if (i0 + k * M_THREADS + tid >= P) continue;
+                    const float tv = (cf[k] * cf[k]) * wgt * mult;
+                    float x, y, z;
+                    slice_coord(rot, (double)c[k].x, (double)c[k].y, x, y, z);
+                    int x0, y0, z0;
+                    float xd, yd, zd;
+                    float gy = fy[k];
+                    if (fold_floor(x, y, z, x0, y0, z0, xd, yd, zd)) gy = -gy;
+                    float w8[8];
+                    tri_weights(xd, yd, zd, w8);
+                    int64_t off[4];
+                    row_offsets(y0, z0, n, nColFT, off);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float4* row = acc + off[cc] + x0;
+                        red_add_v4(row, fx[k] * w8[2 * cc], gy * w8[2 * cc], tv * w8[2 * cc]);
+                        red_add_v4(row + 1, fx[k] * w8[2 * cc + 1], gy * w8[2 * cc + 1], tv * w8[2 * cc + 1]);
+                    }
                 }
             }
         }
@@ -446,11 +466,13 @@ __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_t imgSt
         if (dsig) dsig[d] = sigRcpTab[(size_t)g * nRing + iSig[s]];
         const float u = (float)hypot((double)((float)c.z / (pixelSize * (float)N)), (double)((float)c.w / (pixelSize * (float)N)));
         const float angle = (float)(atan2((double)c.w, (double)c.z) - (double)a.theta);
-        const float defocus = -(a.defocusU + a.defocusV + (a.defocusU - a.defocusV) * cosf(2 * angle)) / 2;
+        // the phase reaches hundreds of radians: keep the reference's unfused operation order (no FMA contraction),
+        // one ulp of ki is already 3e-5 in the CTF value
+        const float defocus = __fmul_rn(-__fadd_rn(__fadd_rn(a.defocusU, a.defocusV), __fmul_rn(__fadd_rn(a.defocusU, -a.defocusV), cosf(__fmul_rn(2.0f, angle)))), 0.5f);
         const double u2d = (double)u * u;
         const float u2 = (float)u2d, u4 = (float)(u2d * u2d);
-        const float ki = K1 * defocus * u2 + K2 * u4 - a.phaseShift;
-        dctf[d] = -w1 * sinf(ki) + w2 * cosf(ki);
+        const float ki = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(K1, defocus), u2), __fmul_rn(K2, u4)), -a.phaseShift);
+        dctf[d] = __fadd_rn(__fmul_rn(-w1, sinf(ki)), __fmul_rn(w2, cosf(ki)));
     }
 }
 

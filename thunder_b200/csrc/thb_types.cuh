@@ -11,6 +11,7 @@ constexpr int E_TILE = 128;      // pixels staged in shared memory per step
 constexpr int E_TC = 9;          // translations carried in registers per pass (mLT default = 9)
 constexpr int M_THREADS = 256;
 constexpr int M_MAXRECO = 128;
+constexpr int M_KP = 1;          // pixels per thread held in registers by the insert kernel
 
 struct VolTable { const float2* p[THB_MAX_SLOTS]; };
 struct AccTable { float4* p[THB_MAX_SLOTS]; double* O; int* counter; };
@@ -51,6 +52,8 @@ struct ExpectArgs {
     const TileDesc* tiles;
     int nTiles;
     float* work;            // [nAct][nR*nT] scratch for multi-pass shapes (nR > 128 or nT > 9), else null
+    int quadBrick;          // log2 of the brick edge of the quad layout (0 = plain rows)
+    int sortRot;            // hand rotation slots out in the order of the cloud along its widest axis
     unsigned long long* stats;   // optional [8] counters of the staging decisions (null = off)
     const float2* dat;
     const float* ctf;
