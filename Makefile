@@ -6,7 +6,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fopenmp -Xptxas -v
 CSRC      := thunder_b200/csrc
 OUT       := thunder_b200/lib/libthunder_b200.so
-OBJS      := build/thb_api.o build/thb_pf.o build/thb_comm.o
+OBJS      := build/thb_api.o build/thb_pf.o build/thb_reco.o build/thb_comm.o
 HDRS      := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h include/*.h)
 
 IFACE     := thunder_b200/lib/libthb_interface.so
@@ -23,7 +23,7 @@ build/thb_comm.o: $(CSRC)/thb_comm.cpp $(HDRS)
 
 $(OUT): $(OBJS)
 	@mkdir -p thunder_b200/lib
-	$(NVCC) $(ARCH) -shared -Xcompiler -fPIC -o $@ $(OBJS) -Xlinker --no-as-needed -lgomp -ldl
+	$(NVCC) $(ARCH) -shared -Xcompiler -fPIC -o $@ $(OBJS) -Xlinker --no-as-needed -lgomp -ldl -lcufft -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
 
 # host-side mirror of the reference's accelerator seam (C++), on top of the C ABI
 $(IFACE): thunder_b200/host/Interface.cpp thunder_b200/host/Interface.h include/thunder_b200.h $(OUT)

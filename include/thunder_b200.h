@@ -32,6 +32,8 @@
  *                             (NCCL twin: gpu/src/cuthunder.cu:5294-5324, 5903-5985)
  *   thb_reco_download         the F3D/T3D/O3D/counter out-arguments  gpu/interface/Interface.cpp:581-619
  *                             of InsertFT, + prepareTF normalisation src/Reconstructor.cpp:1056-1091, 2458-2483
+ *   thb_reconstruct           Reconstructor::reconstruct             src/Reconstructor.cpp:1129-1831 (GPU twin reconstructG :1835-2346)
+ *   thb_set_projectee         Projector::setProjectee                src/Projector.cpp:123-148
  *   thb_pf_* / thb_expectation Particle::perturb/resample/calVari/.. src/Particle.cpp:1004-1478, 1964-2002, 2309-2495
  *                             + the phase loop of                    src/Optimiser.cpp:1162-1660
  *   thb_reconstruct_insert    the insert loop of reconstructRef      src/Optimiser.cpp:7036-7241
@@ -172,6 +174,24 @@ int thb_comm_unique_id(char id[THB_UNIQUE_ID_BYTES]);
 int thb_comm_init(thb_ctx* ctx, int nRanks, int rank, const char id[THB_UNIQUE_ID_BYTES]);
 /* One sum-allreduce of every allocated accumulator (F|T interleaved, all slots) + O, counter. */
 int thb_allreduce(thb_ctx* ctx);
+
+/* ---------------------------------------------------------------- f1: reconstruct + setProjectee */
+/* set the accumulators of a slot from host arrays (restart / tests): F[(m/2+1)*m*m][2], T[(m/2+1)*m*m] */
+int thb_reco_upload(thb_ctx* ctx, int slot, const float* F, const float* T);
+/* Reconstructor::reconstruct (src/Reconstructor.cpp:1129-1831, MODE_3D, C1, default Config.h) on the accumulators of
+ * `slot` (after thb_insert / thb_allreduce), edge m = pf * size, size <= N:
+ *   normalise != 0: the prepareTF normalisation first (sf = 1 / T[0], src/Reconstructor.cpp:1056-1091);
+ *   fsc != NULL: MAP weighting of T by the half-map FSC (fsc[nFsc] per shell of the unpadded grid), joinHalf as setJoinHalf;
+ *   gridCorr: the iterative gridding correction (at most 30 pairs of 3D FFTs, cuFFT), else W = 1 / T;
+ *   then F * W -> inverse 3D FFT on the (pf N)^3 grid -> central N^3 -> / sinc^2.
+ * The accumulators are consumed (scaled / weighted in place, as the reference's _T3D / _F3D are).  The result stays on
+ * the device for thb_set_projectee and is copied to dstReal[N][N][N] (origin at index 0) when dstReal != NULL. */
+int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alpha, int gridCorr, int joinHalf,
+                    const float* fsc, int nFsc, int normalise, float* dstReal, int* nIterOut);
+/* Projector::setProjectee (src/Projector.cpp:123-148, gridCorrection :573-583): real volume N^3 -> zero-padded
+ * (pf N)^3 -> / sinc^2 -> forward 3D FFT into projector slot `slot`.  volReal == NULL: the result of the last
+ * thb_reconstruct (no host round trip). */
+int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int pf);
 
 /* ---------------------------------------------------------------- a9: device-resident particle filter */
 typedef struct thb_pf_params {

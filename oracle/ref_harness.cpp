@@ -316,6 +316,37 @@ void ref_reco_get(void* h, float* F, float* T, double* O3, int* counter)
 // normalise by 1/Re T[0], symmetrise (C1: identity)
 void ref_reco_prepareTF(void* h, int nThread) { ((RefReco*)h)->reco.prepareTF(nThread); }
 
+// set the accumulators directly (parity tests of reconstruct): F complex64, T real part
+void ref_reco_set(void* h, const float* F, const float* T)
+{
+    RefReco* r = (RefReco*)h;
+    size_t n = r->reco._F3D.sizeFT();
+    memcpy(&r->reco._F3D[0], F, n * sizeof(Complex));
+    for (size_t i = 0; i < n; i++) r->reco._T3D[i] = COMPLEX(T[i], 0);
+}
+
+// Reconstructor::reconstruct(Volume&, nThread) (src/Reconstructor.cpp:1129-1831) -> real N^3 volume (origin at index 0)
+// fsc == NULL: MAP off.  Returns the edge of the result.
+int ref_reco_reconstruct(void* h, float* dst, int gridCorr, int joinHalf, const float* fsc, int nFsc, int nThread)
+{
+    RefReco* r = (RefReco*)h;
+    r->reco.setGridCorr(gridCorr != 0);
+    r->reco.setJoinHalf(joinHalf != 0);
+    r->reco.setMAP(fsc != NULL);
+    if (fsc)
+    {
+        vec f(nFsc);
+        for (int i = 0; i < nFsc; i++) f(i) = fsc[i];
+        r->reco.setFSC(f);
+    }
+    Volume v;
+    r->reco.reconstruct(v, nThread);
+    if (dst) memcpy(dst, &v(0), v.sizeRL() * sizeof(RFLOAT));
+    return (int)v.nColRL();
+}
+
+int ref_reco_max_radius(void* h) { return ((RefReco*)h)->reco.maxRadius(); }
+
 // ---------------------------------------------------------------- Particle (reference class, as is)
 void* ref_particle_create(int nC, int nR, int nT, int nD, double transS, double transQ)
 {

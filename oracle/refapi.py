@@ -58,6 +58,11 @@ def lib():
         L.ref_reco_create.restype = _p
         L.ref_reco_create.argtypes = [_i, _i, _i, _i]
         L.ref_reco_destroy.argtypes = [_p]
+        L.ref_reco_set.argtypes = [_p, _p, _p]
+        L.ref_reco_reconstruct.restype = _i
+        L.ref_reco_reconstruct.argtypes = [_p, _p, _i, _i, _p, _i, _i]
+        L.ref_reco_max_radius.restype = _i
+        L.ref_reco_max_radius.argtypes = [_p]
         L.ref_reco_reset.argtypes = [_p, _i]
         L.ref_reco_set_precal.argtypes = [_p, _i, _p, _p, _p, _p]
         L.ref_reco_insertP.argtypes = [_p, _p, _p, _p, _f]
@@ -208,6 +213,21 @@ class Reconstructor:
         O = np.empty(3); cnt = np.zeros(1, np.int32)
         lib().ref_reco_get(self.h, _ptr(F), _ptr(T), _ptr(O), _ptr(cnt))
         return dict(F=F, T=T, O=O, counter=int(cnt[0]))
+
+    def set(self, F, T):
+        F = np.ascontiguousarray(F, np.complex64); T = np.ascontiguousarray(T, np.float32)
+        lib().ref_reco_set(self.h, _ptr(F), _ptr(T))
+
+    def max_radius(self):
+        return lib().ref_reco_max_radius(self.h)
+
+    def reconstruct(self, N, gridCorr=True, joinHalf=False, fsc=None, nThread=8):
+        """Reconstructor::reconstruct -> real volume [N][N][N] float32, origin at index 0"""
+        out = np.empty((N, N, N), np.float32)
+        f = None if fsc is None else np.ascontiguousarray(fsc, np.float32)
+        n = lib().ref_reco_reconstruct(self.h, _ptr(out), int(gridCorr), int(joinHalf), _ptr(f), 0 if f is None else len(f), nThread)
+        assert n == N, (n, N)
+        return out
 
     def prepareTF(self):
         lib().ref_reco_prepareTF(self.h, self.nThread)

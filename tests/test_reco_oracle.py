@@ -1,0 +1,103 @@
+"""SURVEY.md section 8(f) row 1.  CPU: the numpy restatement of Reconstructor::reconstruct / Projector::setProjectee
+(oracle/reco_port.py) pinned against the reference's own classes (oracle/_ref).  GPU: thb_reconstruct and
+thb_set_projectee (cuFFT + elementwise kernels) against both."""
+import numpy as np
+import pytest
+
+from thunder_b200 import synth
+
+
+def _accumulators(ref, N, pf, nImg, seed):
+    """back-projection of noiseless slices of a phantom at random orientations, by the reference's own classes.
+    nImg must cover Fourier space (~N^2/3 images): on under-sampled accumulators the reference's gridding iteration
+    itself diverges (max | |C| - 1 | grows to 1e3 within 15 iterations) and amplifies rounding differences between any
+    two FFT libraries to percents - observed between FFTW and pocketfft as well as cuFFT."""
+    rng = np.random.default_rng(seed)
+    vol = synth.phantom(N, 10, seed=3)
+    P = ref.Projector(pf)
+    P.set_from_real(vol)
+    volFT = P.padded_ft()
+    pixM = ref.pixel_list(N, pf, float(N // 2 - 2), 0.0)
+    PM = len(pixM["iCol"])
+    reco = ref.Reconstructor(N, N, pf, 8)
+    reco.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+    quats = synth.random_quats(nImg, rng)
+    dat = np.stack([P.project(ref.rotate3D(q), pixM["iCol"], pixM["iRow"]) for q in quats]).astype(np.complex64)
+    ctf = rng.uniform(0.3, 1.0, (nImg, PM)).astype(np.float32)
+    reco.insert_loop((dat * ctf).astype(np.complex64), ctf, np.ones(nImg, np.float32), np.zeros((nImg, 2)), quats[:, None, :],
+                     np.zeros((nImg, 1, 2)), pixM["iCol"], pixM["iRow"], N)
+    acc = reco.get()
+    P.close()
+    return vol, volFT, reco, acc
+
+
+CASES = [dict(gridCorr=True, fsc=False, joinHalf=False), dict(gridCorr=False, fsc=False, joinHalf=False),
+         dict(gridCorr=True, fsc=True, joinHalf=False), dict(gridCorr=True, fsc=True, joinHalf=True)]
+
+
+def test_numpy_restatement_matches_reference_classes(ref):
+    from oracle import reco_port
+    N, pf = 32, 2
+    vol, volFT, reco, acc = _accumulators(ref, N, pf, 400, 1)
+    mine = reco_port.set_projectee(vol, pf)
+    assert np.linalg.norm(mine - volFT) <= 2e-6 * np.linalg.norm(volFT)
+    fsc = np.linspace(0.99, 0.2, N // 2 + 1).astype(np.float32)
+    for case in CASES:
+        reco.set(acc["F"], acc["T"])
+        reco.prepareTF()
+        want = reco.reconstruct(N, gridCorr=case["gridCorr"], joinHalf=case["joinHalf"], fsc=fsc if case["fsc"] else None)
+        got, nit = reco_port.reconstruct(acc["F"], acc["T"], N, pf, grid_corr=case["gridCorr"], fsc=fsc if case["fsc"] else None,
+                                         join_half=case["joinHalf"])
+        assert np.linalg.norm(got - want) <= 5e-6 * np.linalg.norm(want), case
+        if not case["fsc"]:
+            assert np.corrcoef(want.ravel(), vol.ravel())[0, 1] > 0.999          # and it IS a reconstruction of the phantom
+    reco.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [32, 64])
+def test_device_reconstruct_and_set_projectee(ctx, N):
+    from oracle import reco_port, refapi
+    ref = refapi if refapi.available() else None
+    pf = 2
+    rng = np.random.default_rng(N)
+    m = N * pf
+    if ref is not None:
+        vol, volFT, reco, acc = _accumulators(ref, N, pf, 400 if N <= 32 else 1500, 2)
+    else:   # the reference library did not travel: synthetic accumulators with the statistics of a back-projection
+        vol = synth.phantom(N, 10, seed=3)
+        volFT = reco_port.set_projectee(vol, pf)
+        T = (np.abs(rng.normal(size=(m, m, m // 2 + 1))) * 5 + 1).astype(np.float32)
+        acc = dict(F=(volFT * T).astype(np.complex64), T=T)
+        reco = None
+    ctx.reco_alloc(0, m)
+    fsc = np.linspace(0.99, 0.2, N // 2 + 1).astype(np.float32)
+    for case in CASES:
+        f = fsc if case["fsc"] else None
+        ctx.reco_upload(0, acc["F"], acc["T"])
+        got, nit = ctx.reconstruct(0, N, pf, gridCorr=case["gridCorr"], joinHalf=case["joinHalf"], fsc=f)
+        want, nit0 = reco_port.reconstruct(acc["F"], acc["T"], N, pf, grid_corr=case["gridCorr"], fsc=f, join_half=case["joinHalf"])
+        assert nit == nit0, case
+        assert np.linalg.norm(got - want) <= 2e-5 * np.linalg.norm(want), case
+        if reco is not None:
+            reco.set(acc["F"], acc["T"])
+            reco.prepareTF()
+            want2 = reco.reconstruct(N, gridCorr=case["gridCorr"], joinHalf=case["joinHalf"], fsc=f)
+            assert np.linalg.norm(got - want2) <= 2e-5 * np.linalg.norm(want2), case
+    # setProjectee: explicit volume, and straight from the reconstruction kept on the device
+    ctx.set_projectee(1, vol, N, pf)
+    got = ctx.get_volume(1)
+    assert np.linalg.norm(got - volFT) <= 5e-6 * np.linalg.norm(volFT)
+    ctx.reco_upload(0, acc["F"], acc["T"])
+    rec, _ = ctx.reconstruct(0, N, pf)
+    ctx.set_projectee(1, None, N, pf)
+    got2 = ctx.get_volume(1)
+    want2 = reco_port.set_projectee(rec, pf)
+    assert np.linalg.norm(got2 - want2) <= 5e-6 * np.linalg.norm(want2)
+    # and the projector built that way drives the E kernel
+    pix = __import__("thunder_b200").capi.pixel_list(N, pf, N // 2 - 3.0, 1.0)
+    ctx.set_expect_pixels(N, pf, pix["iCol"], pix["iRow"])
+    sl = ctx.project(1, synth.random_quats(2, rng))
+    assert np.isfinite(sl).all() and np.abs(sl).max() > 0
+    if reco is not None:
+        reco.close()

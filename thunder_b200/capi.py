@@ -67,6 +67,9 @@ def _sig(lib):
     f = lib.thb_upload_stack_at; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
     f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
+    f = lib.thb_reco_upload; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
+    f = lib.thb_reconstruct; f.restype = _i; f.argtypes = [_p, _i, _i, _i, C.c_double, C.c_double, _i, _i, _p, _i, _i, _p, _p]
+    f = lib.thb_set_projectee; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
@@ -265,6 +268,24 @@ class Context:
         sig = np.empty((nImg, P), np.float32) if kind == STACK_EXPECT else None
         self._chk(self.lib.thb_download_stack(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sig)))
         return dict(dat=dat, ctf=ctf, sigRcp=sig)
+
+    # ---- reconstruct / setProjectee
+    def reco_upload(self, slot, F, T):
+        F = _arr(F, np.complex64); T = _arr(T, np.float32)
+        self._chk(self.lib.thb_reco_upload(self.h, slot, _ptr(F), _ptr(T)))
+
+    def reconstruct(self, slot, N, pf, a=1.9, alpha=15.0, gridCorr=True, joinHalf=False, fsc=None, normalise=True, want_volume=True):
+        fsc = _arr(fsc, np.float32)
+        out = np.empty((N, N, N), np.float32) if want_volume else None
+        nit = C.c_int(0)
+        self._chk(self.lib.thb_reconstruct(self.h, slot, N, pf, a, alpha, int(gridCorr), int(joinHalf), _ptr(fsc),
+                                           0 if fsc is None else len(fsc), int(normalise), _ptr(out), C.byref(nit)))
+        return out, nit.value
+
+    def set_projectee(self, slot, vol, N, pf):
+        vol = _arr(vol, np.float32, (N, N, N)) if vol is not None else None
+        self._chk(self.lib.thb_set_projectee(self.h, slot, _ptr(vol), N, pf))
+        self.vdim[slot] = N * pf
 
     # ---- E
     def project(self, slot, quat):

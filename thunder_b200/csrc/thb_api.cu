@@ -297,6 +297,7 @@ void thb_destroy(thb_ctx* ctx)
     resolve_spans(ctx);
     comm_destroy(ctx);
     pf_free(ctx);
+    reco_free(ctx);
     for (int i = 0; i < THB_MAX_SLOTS; ++i) {
         cudaFree(ctx->vols[i].d);
         cudaFree(ctx->vols[i].quad);

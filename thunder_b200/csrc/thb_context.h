@@ -100,6 +100,8 @@ struct thb_ctx {
     thb::Stack stackE, stackM;
     thb::PFState pf_;
 
+    void* reco = nullptr;        // thb::RecoState (cuFFT plans, kernel table, last reconstruction), thb_reco.cu
+
     // NCCL
     void* ncclComm = nullptr;
     int nRanks = 1, rank = 0;
@@ -144,5 +146,8 @@ void comm_destroy(thb_ctx* ctx);
 
 // particle filter (thb_pf.cu)
 void pf_free(thb_ctx* ctx);
+
+// reconstruct / setProjectee (thb_reco.cu)
+void reco_free(thb_ctx* ctx);
 
 }  // namespace thb
