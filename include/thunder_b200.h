@@ -34,6 +34,7 @@
  *                             of InsertFT, + prepareTF normalisation src/Reconstructor.cpp:1056-1091, 2458-2483
  *   thb_reconstruct           Reconstructor::reconstruct             src/Reconstructor.cpp:1129-1831 (GPU twin reconstructG :1835-2346)
  *   thb_set_projectee         Projector::setProjectee                src/Projector.cpp:123-148
+ *   thb_remask_pack           Optimiser::reCentreImg / reMaskImg     src/Optimiser.cpp:6065-6151 (GPU twin reMaskImgG)
  *   thb_pf_* / thb_expectation Particle::perturb/resample/calVari/.. src/Particle.cpp:1004-1478, 1964-2002, 2309-2495
  *                             + the phase loop of                    src/Optimiser.cpp:1162-1660
  *   thb_reconstruct_insert    the insert loop of reconstructRef      src/Optimiser.cpp:7036-7241
@@ -192,6 +193,16 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
  * (pf N)^3 -> / sinc^2 -> forward 3D FFT into projector slot `slot`.  volReal == NULL: the result of the last
  * thb_reconstruct (no host round trip). */
 int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int pf);
+
+/* ---------------------------------------------------------------- f2: re-centre + re-mask + pack */
+/* Optimiser::reCentreImg + reMaskImg (src/Optimiser.cpp:6065-6151) + allocPreCal on the device: E-stack images
+ * [base, base+nImg) rebuilt from the ORIGINAL image FTs imgOriFT[nImg][(N/2+1)*N]:
+ *   translate by offset[nImg][2] (the running _offset, already updated by the caller)  ->  2D c2r (batched cuFFT)  ->
+ *   x soft mask (radius maskRadiusPx = maskRadius / pixelSize, EDGE_WIDTH_RL = 6; skipped when zeroMask == 0)  ->  2D r2c  ->
+ *   the packing of thb_pack_stack.  imgOutFT (may be NULL) receives the masked image FTs (the reference's _img). */
+int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, const double* offset, float maskRadiusPx,
+                    int zeroMask, const int* iPxl, const int* iSig, const float* sigRcpTab, int nGroup, int nRing,
+                    const int* groupOfImg, const float* ctfAttr, float pixelSize, const int* slotOfImg, float* imgOutFT);
 
 /* ---------------------------------------------------------------- a9: device-resident particle filter */
 typedef struct thb_pf_params {

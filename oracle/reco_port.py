@@ -130,3 +130,36 @@ def set_projectee(vol, pf):
     r = np.sqrt((ii * ii + jj * jj + kk * kk).astype(np.float64)) / (pf * n)
     pad = (pad / tik_rl(r)).astype(np.float32)
     return np.fft.rfftn(pad).astype(np.complex64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Optimiser::reCentreImg (src/Optimiser.cpp:6065-6091) + reMaskImg (:6093-6151, zeroMask)
+#   translate(Image&, const Image&, ...)   src/Image/ImageFunctions.cpp:269-284
+#   softMask(Image& mask, r, ew)           src/Functions/Mask.cpp:333-350 ; EDGE_WIDTH_RL = 6 (include/Macro.h:99)
+EDGE_WIDTH_RL = 6
+
+
+def soft_mask(N, r, ew=EDGE_WIDTH_RL):
+    g = np.fft.fftfreq(N, 1.0 / N)
+    u = np.hypot(g[:, None], g[None, :]).astype(np.float32)
+    r = np.float32(r); ew = np.float32(ew)
+    edge = (0.5 + 0.5 * np.cos(((u - r) / ew).astype(np.float32).astype(np.float64) * np.pi)).astype(np.float32)
+    return np.where(u > r + ew, np.float32(0), np.where(u >= r, edge, np.float32(1))).astype(np.float32)
+
+
+def recentre_remask(img_ori_ft, offset, mask_radius_px, zero_mask=True):
+    """half-complex [N][N/2+1] complex64 -> the masked, re-centred image FT (what _img[l] holds after reCentreImg + reMaskImg)"""
+    src = np.asarray(img_ori_ft, np.complex64)
+    N = src.shape[0]
+    j = np.fft.fftfreq(N, 1.0 / N).astype(np.float32)[:, None]
+    i = np.arange(N // 2 + 1, dtype=np.float32)[None, :]
+    rCol = np.float32(np.float32(offset[0]) / np.float32(N)); rRow = np.float32(np.float32(offset[1]) / np.float32(N))
+    s = (i * rCol + j * rRow).astype(np.float32)
+    phase = (6.28318530717959 * s.astype(np.float64)).astype(np.float32)
+    polar = (np.cos(-phase.astype(np.float64)) + 1j * np.sin(-phase.astype(np.float64))).astype(np.complex64)
+    img = (src * polar).astype(np.complex64)
+    if not zero_mask:
+        return img
+    rl = np.fft.irfft2(img, s=(N, N)).astype(np.float32)
+    rl = (rl * soft_mask(N, mask_radius_px)).astype(np.float32)
+    return np.fft.rfft2(rl).astype(np.complex64)

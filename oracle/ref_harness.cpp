@@ -347,6 +347,28 @@ int ref_reco_reconstruct(void* h, float* dst, int gridCorr, int joinHalf, const 
 
 int ref_reco_max_radius(void* h) { return ((RefReco*)h)->reco.maxRadius(); }
 
+// ---------------------------------------------------------------- re-centre + re-mask of one image
+// Optimiser::reCentreImg (src/Optimiser.cpp:6065-6091): _img = translate(_imgOri, offset) ; Optimiser::reMaskImg
+// (:6093-6151, zeroMask): 2D c2r, x softMask(maskRadius / pixelSize, EDGE_WIDTH_RL), 2D r2c.
+// imgOriFT / imgFT: half-complex [N][N/2+1] complex64 (FFTW layout).
+void ref_recentre_remask(float* imgFT, const float* imgOriFT, int N, double offx, double offy, float maskRadiusPx, int zeroMask)
+{
+    Image ori(N, N, FT_SPACE), img(N, N, FT_SPACE);
+    memcpy(&ori[0], imgOriFT, ori.sizeFT() * sizeof(Complex));
+    translate(img, ori, offx, offy, 1);
+    if (zeroMask)
+    {
+        Image mask(N, N, RL_SPACE);
+        softMask(mask, maskRadiusPx, EDGE_WIDTH_RL, 1);
+        FFT fft;
+        fft.bw(img, 1);
+        MUL_RL(img, mask);
+        fft.fw(img, 1);
+        img.clearRL();
+    }
+    memcpy(imgFT, &img[0], img.sizeFT() * sizeof(Complex));
+}
+
 // ---------------------------------------------------------------- Particle (reference class, as is)
 void* ref_particle_create(int nC, int nR, int nT, int nD, double transS, double transQ)
 {

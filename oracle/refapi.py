@@ -58,6 +58,7 @@ def lib():
         L.ref_reco_create.restype = _p
         L.ref_reco_create.argtypes = [_i, _i, _i, _i]
         L.ref_reco_destroy.argtypes = [_p]
+        L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
         L.ref_reco_set.argtypes = [_p, _p, _p]
         L.ref_reco_reconstruct.restype = _i
         L.ref_reco_reconstruct.argtypes = [_p, _p, _i, _i, _p, _i, _i]
@@ -136,6 +137,15 @@ def ctf(pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, iCol, iRow):
     n = len(iCol)
     out = np.empty(n, np.float32)
     lib().ref_ctf(_ptr(out), pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, _ptr(iCol), _ptr(iRow), n)
+    return out
+
+
+def recentre_remask(imgOriFT, offset, maskRadiusPx, zeroMask=True):
+    """Optimiser::reCentreImg + reMaskImg for one image: half-complex [N][N/2+1] complex64 in and out"""
+    src = np.ascontiguousarray(imgOriFT, np.complex64)
+    N = src.shape[0]
+    out = np.empty_like(src)
+    lib().ref_recentre_remask(_ptr(out), _ptr(src), N, float(offset[0]), float(offset[1]), float(maskRadiusPx), int(zeroMask))
     return out
 
 

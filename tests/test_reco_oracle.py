@@ -101,3 +101,44 @@ def test_device_reconstruct_and_set_projectee(ctx, N):
     assert np.isfinite(sl).all() and np.abs(sl).max() > 0
     if reco is not None:
         reco.close()
+
+
+# ------------------------------------------------------------------------------------------- section 8(f) row 2
+def test_numpy_recentre_remask_matches_reference(ref):
+    from oracle import reco_port
+    rng = np.random.default_rng(0)
+    for N in (32, 64):
+        ft = np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)).astype(np.complex64)
+        for zm in (False, True):
+            want = ref.recentre_remask(ft, (1.3, -2.7), N * 0.35, zm)
+            got = reco_port.recentre_remask(ft, (1.3, -2.7), N * 0.35, zm)
+            assert np.linalg.norm(got - want) <= 1e-6 * np.linalg.norm(want)
+
+
+@pytest.mark.gpu
+def test_device_remask_pack(ctx):
+    """thb_remask_pack == reCentreImg + reMaskImg + allocPreCal: masked image FTs and the packed E stack"""
+    from oracle import reco_port, portapi as port
+    from thunder_b200 import capi
+    N, pf = 64, 2
+    rng = np.random.default_rng(5)
+    pixE = port.pixel_list(N, pf, 30.0, 1.0)
+    nImg, nGroup, nRing = 7, 2, N // 2 + 1
+    ori = np.stack([np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)) for _ in range(nImg)]).astype(np.complex64)
+    offset = rng.normal(scale=2.0, size=(nImg, 2))
+    sigRcpTab = (-0.5 / rng.uniform(0.5, 2.0, (nGroup, nRing))).astype(np.float32)
+    group = rng.integers(0, nGroup, nImg).astype(np.int32)
+    attr = np.stack([np.full(nImg, 3e5), rng.uniform(1e4, 3e4, nImg), rng.uniform(1e4, 3e4, nImg), rng.uniform(0, np.pi, nImg),
+                     np.full(nImg, 2.7e7), np.full(nImg, 0.1), np.zeros(nImg)], axis=1).astype(np.float32)
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.stack_reserve(capi.STACK_EXPECT, nImg + 1)
+    maskR = 0.35 * N
+    for zm in (True, False):
+        imgs = ctx.remask_pack(1, ori, offset, maskR, pixE["iPxl"], pixE["iSig"], sigRcpTab, attr, 1.32, zeroMask=zm, groupOfImg=group,
+                               want_images=True)
+        got = ctx.download_stack(capi.STACK_EXPECT, 1, nImg)
+        for l in range(nImg):
+            want = reco_port.recentre_remask(ori[l], offset[l], maskR, zm)
+            assert np.linalg.norm(imgs[l] - want) <= 2e-6 * np.linalg.norm(want), (zm, l)
+            assert np.array_equal(got["dat"][l], imgs[l].ravel()[pixE["iPxl"]])
+        assert np.array_equal(got["sigRcp"], sigRcpTab[group][:, pixE["iSig"]])

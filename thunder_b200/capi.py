@@ -70,6 +70,7 @@ def _sig(lib):
     f = lib.thb_reco_upload; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_reconstruct; f.restype = _i; f.argtypes = [_p, _i, _i, _i, C.c_double, C.c_double, _i, _i, _p, _i, _i, _p, _p]
     f = lib.thb_set_projectee; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i]
+    f = lib.thb_remask_pack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, C.c_float, _i, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p, _p]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
@@ -268,6 +269,21 @@ class Context:
         sig = np.empty((nImg, P), np.float32) if kind == STACK_EXPECT else None
         self._chk(self.lib.thb_download_stack(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sig)))
         return dict(dat=dat, ctf=ctf, sigRcp=sig)
+
+    def remask_pack(self, base, imgOriFT, offset, maskRadiusPx, iPxl, iSig, sigRcpTab, ctfAttr, pixelSize, zeroMask=True, groupOfImg=None,
+                    slotOfImg=None, want_images=False):
+        """Optimiser::reCentreImg + reMaskImg + allocPreCal on the device (SURVEY.md section 8f row 2)"""
+        imgOriFT = _arr(imgOriFT, np.complex64)
+        nImg = imgOriFT.shape[0]
+        offset = _arr(offset, np.float64, (nImg, 2))
+        iPxl = _arr(iPxl, np.int32); iSig = _arr(iSig, np.int32)
+        sigRcpTab = _arr(sigRcpTab, np.float32); ctfAttr = _arr(ctfAttr, np.float32, (nImg, 7))
+        groupOfImg = _arr(groupOfImg, np.int32, (nImg,)); slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
+        out = np.empty_like(imgOriFT) if want_images else None
+        self._chk(self.lib.thb_remask_pack(self.h, base, nImg, _ptr(imgOriFT), _ptr(offset), float(maskRadiusPx), int(zeroMask), _ptr(iPxl),
+                                           _ptr(iSig), _ptr(sigRcpTab), sigRcpTab.shape[0], sigRcpTab.shape[1], _ptr(groupOfImg), _ptr(ctfAttr),
+                                           float(pixelSize), _ptr(slotOfImg), _ptr(out)))
+        return out
 
     # ---- reconstruct / setProjectee (SURVEY.md section 8f row 1)
     def reco_upload(self, slot, F, T):

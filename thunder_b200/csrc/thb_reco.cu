@@ -15,6 +15,7 @@
 #include <cstring>
 #include <vector>
 #include "thb_context.h"
+#include "thb_pack.cuh"
 
 namespace thb {
 
@@ -192,6 +193,59 @@ __global__ void proj_pad_rl_kernel(const float* vol, int N, int n, int pf, float
     }
 }
 
+// ---- section 8(f) row 2: reCentreImg + reMaskImg on a batch of full half-complex image FTs [nImg][N][N/2+1]
+// translate(Image&, const Image&, ...) (src/Image/ImageFunctions.cpp:269-284): img = ori * polar(-2 pi (i rCol + j rRow))
+__global__ void img_translate_kernel(float2* img, int N, int nImg, const float* rColRow)
+{
+    const int nc = N / 2 + 1;
+    const size_t per = (size_t)nc * N, total = per * nImg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(idx / per);
+        const size_t r = idx - (size_t)l * per;
+        const int i = (int)(r % nc), j = signed_coord((int)(r / nc), N);
+        const float ph = translate_phase(i, j, rColRow[2 * l], rColRow[2 * l + 1]);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float2 v = img[idx];
+        // v * (cos(-ph), sin(-ph))
+        img[idx] = make_float2(v.x * cs + v.y * sn, v.y * cs - v.x * sn);
+    }
+}
+
+// x = 0 and x = N/2 columns of every image made Hermitian-consistent (what FFTW's c2r does implicitly, see above)
+__global__ void img_hermitian_cols_kernel(float2* img, int N, int nImg)
+{
+    const int nc = N / 2 + 1;
+    const size_t total = (size_t)2 * N * nImg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(t / (2 * N));
+        const int r = (int)(t % (2 * N));
+        const int i = r < N ? 0 : N / 2, jm = r < N ? r : r - N, jp = (N - jm) % N;
+        if (jm > jp) continue;
+        float2* base = img + (size_t)l * nc * N;
+        const float2 va = base[(size_t)jm * nc + i], vb = base[(size_t)jp * nc + i];
+        const float2 na = make_float2(0.5f * (va.x + vb.x), 0.5f * (va.y - vb.y));
+        base[(size_t)jm * nc + i] = na;
+        base[(size_t)jp * nc + i] = make_float2(na.x, -na.y);
+    }
+}
+
+// real space: x softMask(r, ew) (src/Functions/Mask.cpp:333-350) with the 1/N^2 of the backward transform
+__global__ void img_mask_kernel(float* rl, int N, int nImg, float r, float ew)
+{
+    const size_t per = (size_t)N * N, total = per * nImg;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t q = idx % per;
+        const int i = signed_coord((int)(q % N), N), j = signed_coord((int)(q / N), N);
+        const float u = (float)hypot((double)i, (double)j);
+        float w;
+        if (u > r + ew) w = 0.0f;
+        else if (u >= r) w = (float)(0.5 + 0.5 * cos((double)((u - r) / ew) * 3.14159265358979323846));
+        else w = 1.0f;
+        rl[idx] = (rl[idx] * (1.0f / (float)per)) * w;
+    }
+}
+
 __global__ void reco_upload_kernel(const float2* F, const float* T, size_t nVox, float4* acc)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nVox; i += (size_t)gridDim.x * blockDim.x)
@@ -237,6 +291,8 @@ struct RecoState {
     double tabA = -1, tabAlpha = -1;
     float nf = 1.0f;
     float* dVol = nullptr;      // last reconstruction, N^3 real
+    cufftHandle planImgC2R = 0, planImgR2C = 0;
+    int imgN = 0, imgBatch = 0;
     int volN = 0;
 };
 
@@ -253,6 +309,8 @@ void reco_free(thb_ctx* ctx)
     if (s->planC2R) cufftDestroy(s->planC2R);
     if (s->planR2C) cufftDestroy(s->planR2C);
     if (s->planProj) cufftDestroy(s->planProj);
+    if (s->planImgC2R) cufftDestroy(s->planImgC2R);
+    if (s->planImgR2C) cufftDestroy(s->planImgR2C);
     cudaFree(s->dTab);
     cudaFree(s->dVol);
     delete s;
@@ -394,6 +452,92 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
     if (dstReal) THB_CUDA(ctx, cudaMemcpyAsync(dstReal, s->dVol, sizeof(float) * (size_t)N * N * N, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (nIterOut) *nIterOut = nIter;
+    return THB_OK;
+}
+
+// section 8(f) row 2: E-stack images [base, base+nImg) rebuilt from the ORIGINAL image FTs: translate by the running
+// offset (reCentreImg), soft mask in real space (reMaskImg, batched 2D cuFFT), then the packing of thb_pack_stack.
+int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, const double* offset, float maskRadiusPx, int zeroMask,
+                    const int* iPxl, const int* iSig, const float* sigRcpTab, int nGroup, int nRing, const int* groupOfImg,
+                    const float* ctfAttr, float pixelSize, const int* slotOfImg, float* imgOutFT)
+{
+    if (!ctx) return THB_E_ARG;
+    const int P = ctx->nPxlE, N = ctx->N;
+    Stack& st = ctx->stackE;
+    if (P <= 0) return set_error(ctx, THB_E_STATE, "remask_pack: E pixel list not set");
+    if (!st.dat) return set_error(ctx, THB_E_STATE, "remask_pack: E stack not reserved (thb_stack_reserve)");
+    if (nImg <= 0 || !imgOriFT || !offset || !iPxl || !iSig || !sigRcpTab || !ctfAttr || nGroup <= 0 || nRing <= 0 || pixelSize <= 0)
+        return set_error(ctx, THB_E_ARG, "remask_pack: bad arguments");
+    if (base < 0 || base + nImg > st.nImg) return set_error(ctx, THB_E_ARG, "remask_pack: images [%d,%d) exceed the capacity %d", base, base + nImg, st.nImg);
+    const size_t imgElems = (size_t)(N / 2 + 1) * N;
+    for (int i = 0; i < P; ++i)
+        if (iPxl[i] < 0 || (size_t)iPxl[i] >= imgElems || iSig[i] < 0 || iSig[i] >= nRing) return set_error(ctx, THB_E_ARG, "remask_pack: iPxl / iSig[%d] out of range", i);
+    for (int l = 0; l < nImg; ++l) {
+        if (groupOfImg && (groupOfImg[l] < 0 || groupOfImg[l] >= nGroup)) return set_error(ctx, THB_E_ARG, "remask_pack: groupOfImg[%d] out of range", l);
+        if (slotOfImg && (slotOfImg[l] < 0 || slotOfImg[l] >= THB_MAX_SLOTS)) return set_error(ctx, THB_E_ARG, "remask_pack: slotOfImg[%d] out of range", l);
+    }
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    RecoState* s = reco_state(ctx);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, ((size_t)256 << 20) / (imgElems * sizeof(float2))));
+    if (zeroMask && (s->imgN != N || s->imgBatch != chunk)) {
+        if (s->planImgC2R) { cufftDestroy(s->planImgC2R); s->planImgC2R = 0; }
+        if (s->planImgR2C) { cufftDestroy(s->planImgR2C); s->planImgR2C = 0; }
+        s->imgN = 0;
+        int dims[2] = {N, N};
+        THB_FFT(ctx, cufftPlanMany(&s->planImgC2R, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, chunk));
+        THB_FFT(ctx, cufftPlanMany(&s->planImgR2C, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, chunk));
+        THB_FFT(ctx, cufftSetStream(s->planImgC2R, ctx->stream));
+        THB_FFT(ctx, cufftSetStream(s->planImgR2C, ctx->stream));
+        s->imgN = N;
+        s->imgBatch = chunk;
+    }
+    int* dIdx = (int*)scratch(ctx, 0, sizeof(int) * (2 * (size_t)P + nImg) + sizeof(float) * ((size_t)nGroup * nRing + 9 * (size_t)nImg));
+    float2* dImg = (float2*)scratch(ctx, 4, (size_t)chunk * imgElems * sizeof(float2));
+    float* dRl = (float*)scratch(ctx, 5, (size_t)chunk * N * N * sizeof(float));
+    if (!dIdx || !dImg || !dRl) return THB_E_CUDA;
+    int* dPxl = dIdx; int* dSig = dPxl + P; int* dGrp = dSig + P;
+    float* dTab = (float*)(dGrp + nImg); float* dAttr = dTab + (size_t)nGroup * nRing; float* dOff = dAttr + 7 * (size_t)nImg;
+    std::vector<float> rcr(2 * (size_t)nImg);
+    for (int l = 0; l < nImg; ++l) {   // RFLOAT rCol = nTransCol / nColRL
+        rcr[2 * l] = (float)offset[2 * l] / (float)N;
+        rcr[2 * l + 1] = (float)offset[2 * l + 1] / (float)N;
+    }
+    THB_CUDA(ctx, cudaMemcpyAsync(dPxl, iPxl, sizeof(int) * P, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dSig, iSig, sizeof(int) * P, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dTab, sigRcpTab, sizeof(float) * (size_t)nGroup * nRing, cudaMemcpyHostToDevice, ctx->stream));
+    if (groupOfImg) THB_CUDA(ctx, cudaMemcpyAsync(dGrp, groupOfImg, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dAttr, ctfAttr, sizeof(float) * 7 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dOff, rcr.data(), sizeof(float) * 2 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = ctx->smCount * 8;
+    for (int i0 = 0; i0 < nImg; i0 += chunk) {
+        const int c = std::min(chunk, nImg - i0);
+        THB_CUDA(ctx, cudaMemcpyAsync(dImg, imgOriFT + 2 * (size_t)i0 * imgElems, (size_t)c * imgElems * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+        span_begin(ctx, KF_PACK);
+        img_translate_kernel<<<grid, 256, 0, ctx->stream>>>(dImg, N, c, dOff + 2 * i0);
+        ctx->launches++;
+        if (zeroMask) {
+            if (c < chunk) THB_CUDA(ctx, cudaMemsetAsync(dImg + (size_t)c * imgElems, 0, (size_t)(chunk - c) * imgElems * sizeof(float2), ctx->stream));
+            img_hermitian_cols_kernel<<<grid, 256, 0, ctx->stream>>>(dImg, N, c);
+            THB_FFT(ctx, cufftExecC2R(s->planImgC2R, reinterpret_cast<cufftComplex*>(dImg), dRl));
+            img_mask_kernel<<<grid, 256, 0, ctx->stream>>>(dRl, N, c, maskRadiusPx, 6.0f /* EDGE_WIDTH_RL, include/Macro.h:99 */);
+            THB_FFT(ctx, cufftExecR2C(s->planImgR2C, dRl, reinterpret_cast<cufftComplex*>(dImg)));
+            ctx->launches += 2;
+        }
+        if (imgOutFT)
+            THB_CUDA(ctx, cudaMemcpyAsync(imgOutFT + 2 * (size_t)i0 * imgElems, dImg, (size_t)c * imgElems * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        const size_t doff = (size_t)(base + i0) * P;
+        dim3 pgrid(std::min((P + 255) / 256, 64), c);
+        pack_stack_kernel<<<pgrid, 256, 0, ctx->stream>>>(dImg, imgElems, ctx->pixE, ctx->permE, dPxl, dSig, P, dTab, nRing, groupOfImg ? dGrp + i0 : nullptr,
+                                                          reinterpret_cast<const CtfAttr7*>(dAttr) + i0, pixelSize, N, st.dat + doff, st.ctf + doff, st.sig + doff);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+    }
+    if (slotOfImg)
+        THB_CUDA(ctx, cudaMemcpyAsync(st.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        THB_CUDA(ctx, cudaMemsetAsync(st.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
 
