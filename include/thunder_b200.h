@@ -35,6 +35,7 @@
  *   thb_reconstruct           Reconstructor::reconstruct             src/Reconstructor.cpp:1129-1831 (GPU twin reconstructG :1835-2346)
  *   thb_set_projectee         Projector::setProjectee                src/Projector.cpp:123-148
  *   thb_remask_pack           Optimiser::reCentreImg / reMaskImg     src/Optimiser.cpp:6065-6151 (GPU twin reMaskImgG)
+ *   thb_sigma_accumulate      Optimiser::allReduceSigma (image loop) src/Optimiser.cpp:6397-6709
  *   thb_pf_* / thb_expectation Particle::perturb/resample/calVari/.. src/Particle.cpp:1004-1478, 1964-2002, 2309-2495
  *                             + the phase loop of                    src/Optimiser.cpp:1162-1660
  *   thb_reconstruct_insert    the insert loop of reconstructRef      src/Optimiser.cpp:7036-7241
@@ -203,6 +204,19 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
 int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, const double* offset, float maskRadiusPx,
                     int zeroMask, const int* iPxl, const int* iSig, const float* sigRcpTab, int nGroup, int nRing,
                     const int* groupOfImg, const float* ctfAttr, float pixelSize, const int* slotOfImg, float* imgOutFT);
+
+/* ---------------------------------------------------------------- f3: sigma^2 refresh */
+/* The image loop of Optimiser::allReduceSigma (src/Optimiser.cpp:6428-6600; OPTIMISER_SIGMA_RANK1ST, MODE_3D, no CTF search) on
+ * the resident stacks: for image l (imgIdx[l] or l) with its best orientation quat[l][4], translation tran[l][2] and running
+ * offset offS[l][2] (NULL = 0), the ring-averaged power of  masked image - ctf * translated slice  (E stack, translation
+ * tran), of  original image - ctf * translated slice  (M stack, translation tran - offS) and the signal / data spectra of the
+ * SVD ratio, summed per group.  iSigE / iSigM: the ring of every pixel of the two pixel lists (thb_pixel_list).  The sigma
+ * pixel set is {|k|^2 < rSig^2, rint|k| < rSig}; rings the E list does not reach (below its rL) stay zero.
+ * Outputs [nGroup][rSig + 1] doubles, last column = weight sum: exactly the matrices the reference all-reduces over the
+ * hemisphere; the final normalisation and mixing (:6651-6709) are a few hundred flops on the caller's side. */
+int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double* quat, const double* tran, const double* offS,
+                         const int* groupOfImg, int nGroup, int rSig, const int* iSigE, const int* iSigM, double* sigM,
+                         double* sigN, double* svd);
 
 /* ---------------------------------------------------------------- a9: device-resident particle filter */
 typedef struct thb_pf_params {

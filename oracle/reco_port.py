@@ -91,7 +91,7 @@ def reconstruct(F, T, N, pf, size=None, a=1.9, alpha=15.0, grid_corr=True, fsc=N
         diff_c, n_no_dec = np.float32(3.4028235e38), 0
         for it in range(MAX_N_ITER_BALANCE):
             C = (T * W).astype(np.float32)
-            c_rl = np.fft.irfftn(C.astype(np.complex64), s=(m, m, m)).astype(np.float32)      # unnormalised c2r scaled by 1/m^3
+            c_rl = np.fft.irfftn(C.astype(np.complex64), s=(m, m, m), axes=(0, 1, 2)).astype(np.float32)      # unnormalised c2r scaled by 1/m^3
             c_rl = (c_rl * kern).astype(np.float32)
             Cft = np.fft.rfftn(c_rl).astype(np.complex64)
             absC = np.abs(Cft).astype(np.float32)
@@ -108,7 +108,7 @@ def reconstruct(F, T, N, pf, size=None, a=1.9, alpha=15.0, grid_corr=True, fsc=N
     kz = k[idx[0], 0, 0] % M
     jy = j[0, idx[1], 0] % M
     pad[kz, jy, idx[2]] = (F * W)[idx]
-    rl = np.fft.irfftn(pad, s=(M, M, M)).astype(np.float32)
+    rl = np.fft.irfftn(pad, s=(M, M, M), axes=(0, 1, 2)).astype(np.float32)
     g = np.fft.fftfreq(N, 1.0 / N).astype(np.int64)
     sel = g % M
     out = rl[np.ix_(sel, sel, sel)]
@@ -160,6 +160,6 @@ def recentre_remask(img_ori_ft, offset, mask_radius_px, zero_mask=True):
     img = (src * polar).astype(np.complex64)
     if not zero_mask:
         return img
-    rl = np.fft.irfft2(img, s=(N, N)).astype(np.float32)
+    rl = np.fft.irfft2(img, s=(N, N), axes=(0, 1)).astype(np.float32)
     rl = (rl * soft_mask(N, mask_radius_px)).astype(np.float32)
     return np.fft.rfft2(rl).astype(np.complex64)

@@ -35,6 +35,7 @@
 
 #include "CTF.h"
 #include "FFT.h"
+#include "Spectrum.h"
 #include "ImageFunctions.h"
 #include "Euler.h"
 #include "Random.h"
@@ -367,6 +368,59 @@ void ref_recentre_remask(float* imgFT, const float* imgOriFT, int N, double offx
         img.clearRL();
     }
     memcpy(imgFT, &img[0], img.sizeFT() * sizeof(Complex));
+}
+
+// ---------------------------------------------------------------- sigma^2 refresh, per-image part
+// Body of the image loop of Optimiser::allReduceSigma (src/Optimiser.cpp:6428-6600) with the reference's own functions,
+// OPTIMISER_SIGMA_RANK1ST (one orientation per image: its rank-1st), MODE_3D, OPTIMISER_CTF_ON_THE_FLY, no CTF search,
+// OPTIMISER_RECENTRE_IMAGE_EACH_ITERATION (the original image is compared at tran - offset), w = 1, per-group sums.
+// sigM / sigN / svd: [nGroup][rSig + 1] float, last column = weight sum; the caller does the all-reduce and :6651-6709.
+void ref_sigma_accumulate(void* projH, int nImg, int N, int rSig, const float* imgFT, const float* imgOriFT, const double* quat,
+                          const double* tran, const double* offS, const float* ctfAttr7, float pixelSize, const int* group,
+                          int nGroup, float* sigM, float* sigN, float* svd)
+{
+    RefProjector* P = (RefProjector*)projH;
+    const size_t nFT = (size_t)(N / 2 + 1) * N;
+    for (int i = 0; i < nGroup * (rSig + 1); i++) sigM[i] = sigN[i] = svd[i] = 0;
+    for (int l = 0; l < nImg; l++)
+    {
+        Image img(N, N, FT_SPACE), imgOri(N, N, FT_SPACE), imgM(N, N, FT_SPACE), imgN(N, N, FT_SPACE), ctf(N, N, FT_SPACE);
+        memcpy(&img[0], imgFT + 2 * nFT * l, nFT * sizeof(Complex));
+        memcpy(&imgOri[0], imgOriFT + 2 * nFT * l, nFT * sizeof(Complex));
+        SET_0_FT(imgM);
+        SET_0_FT(imgN);
+        SET_0_FT(ctf);
+        dmat33 rot3D;
+        rotate3D(rot3D, dvec4(quat[4 * l], quat[4 * l + 1], quat[4 * l + 2], quat[4 * l + 3]));
+        dvec2 t(tran[2 * l], tran[2 * l + 1]), off(offS[2 * l], offS[2 * l + 1]);
+        P->proj.project(imgM, rot3D, t, 1);
+        P->proj.project(imgN, rot3D, t - off, 1);
+        const float* a = ctfAttr7 + 7 * l;
+        CTF(ctf, pixelSize, a[0], a[1], a[2], a[3], a[4], a[5], a[6], CEIL(rSig) + 1, 1);
+        FOR_EACH_PIXEL_FT(imgM)
+            imgM[i] *= REAL(ctf[i]);
+        FOR_EACH_PIXEL_FT(imgN)
+            imgN[i] *= REAL(ctf[i]);
+        vec vSigM(rSig), vSigN(rSig), sSVD(rSig), dSVD(rSig);
+        powerSpectrum(sSVD, imgM, rSig, 1);
+        powerSpectrum(dSVD, img, rSig, 1);
+        NEG_FT(imgM);
+        NEG_FT(imgN);
+        ADD_FT(imgM, img);
+        ADD_FT(imgN, imgOri);
+        powerSpectrum(vSigM, imgM, rSig, 1);
+        powerSpectrum(vSigN, imgN, rSig, 1);
+        const int g = group ? group[l] : 0;
+        for (int i = 0; i < rSig; i++)
+        {
+            sigM[g * (rSig + 1) + i] += vSigM(i) / 2;
+            sigN[g * (rSig + 1) + i] += vSigN(i) / 2;
+            svd[g * (rSig + 1) + i] += sqrt(sSVD(i) / dSVD(i));
+        }
+        sigM[g * (rSig + 1) + rSig] += 1;
+        sigN[g * (rSig + 1) + rSig] += 1;
+        svd[g * (rSig + 1) + rSig] += 1;
+    }
 }
 
 // ---------------------------------------------------------------- Particle (reference class, as is)

@@ -59,6 +59,7 @@ def lib():
         L.ref_reco_create.argtypes = [_i, _i, _i, _i]
         L.ref_reco_destroy.argtypes = [_p]
         L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
+        L.ref_sigma_accumulate.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p, _p, _p]
         L.ref_reco_set.argtypes = [_p, _p, _p]
         L.ref_reco_reconstruct.restype = _i
         L.ref_reco_reconstruct.argtypes = [_p, _p, _i, _i, _p, _i, _i]
@@ -137,6 +138,20 @@ def ctf(pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, iCol, iRow):
     n = len(iCol)
     out = np.empty(n, np.float32)
     lib().ref_ctf(_ptr(out), pixelSize, voltage, dU, dV, theta, Cs, ac, ps, N, _ptr(iCol), _ptr(iRow), n)
+    return out
+
+
+def sigma_accumulate(P, imgFT, imgOriFT, quat, tran, offS, ctfAttr, pixelSize, group, nGroup, rSig):
+    """per-image part of Optimiser::allReduceSigma with the reference's own functions; P: Projector with max radius rSig.
+    Returns sigM, sigN, svd [nGroup][rSig+1] float32 (last column: weight sums)."""
+    imgFT = np.ascontiguousarray(imgFT, np.complex64); imgOriFT = np.ascontiguousarray(imgOriFT, np.complex64)
+    nImg, N = imgFT.shape[0], imgFT.shape[1]
+    quat = np.ascontiguousarray(quat, np.float64); tran = np.ascontiguousarray(tran, np.float64); offS = np.ascontiguousarray(offS, np.float64)
+    attr = np.ascontiguousarray(ctfAttr, np.float32); group = np.ascontiguousarray(group, np.int32)
+    out = [np.zeros((nGroup, rSig + 1), np.float32) for _ in range(3)]
+    lib().ref_projector_set_max_radius(P.h, rSig)
+    lib().ref_sigma_accumulate(P.h, nImg, N, rSig, _ptr(imgFT), _ptr(imgOriFT), _ptr(quat), _ptr(tran), _ptr(offS), _ptr(attr), float(pixelSize),
+                               _ptr(group), nGroup, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]))
     return out
 
 

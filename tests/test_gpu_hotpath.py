@@ -288,18 +288,23 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     try:
         ctx.set_option("expect_impl", 3)      # default: direct gather from the quad layout
         a = ctx.expect_local(quat, tran, wR, wT)
-        ctx.set_option("expect_minb", 3)
+        ctx.set_option("quad_oct", 0)         # 32-byte quad layout, two occupancy variants
         a3 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_minb", 3)
+        a4 = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_minb", 2)
+        ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_impl", 2)      # TMA-staged shared-memory box
         c = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
         b = ctx.expect_local(quat, tran, wR, wT)
     finally:
         ctx.set_option("expect_impl", 3)
+        ctx.set_option("quad_oct", 1)
+        ctx.set_option("expect_minb", 2)
     # each kernel carries its own fp32 summation error (the linear-layout kernel sums ~3000 terms sequentially)
     tol = 2e-6 * np.abs(b["logL"]).max() + 1e-4
-    assert np.array_equal(a["logL"], a3["logL"])          # register allocation must not change results
+    assert np.array_equal(a["logL"], a3["logL"]) and np.array_equal(a["logL"], a4["logL"])   # layouts / occupancy: same bits
     assert np.abs(a["logL"] - b["logL"]).max() <= 2 * tol
     assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
     assert np.abs(c["logL"] - a["logL"]).max() <= tol

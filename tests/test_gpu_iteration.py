@@ -253,3 +253,83 @@ def test_adaptive_stop_rule_runs(ctx, prob):
     nph = ctx.expectation(want_phases=True)
     assert nph.min() >= 4 and nph.max() <= 20
     assert len(np.unique(nph)) > 1
+
+
+def test_closed_loop_iterations_on_device():
+    """The whole loop without leaving the device: E-step (device particle filter + fused kernel) -> insert -> (all-reduce)
+    -> reconstruct -> setProjectee -> next E-step, two half sets, two iterations, starting from a blurred reference.
+    Checks that the pieces fit: the reconstructed half maps correlate with the phantom and with each other."""
+    from oracle import reco_port
+    N, pf = 64, 2
+    rng = np.random.default_rng(2024)
+    truth = synth.phantom(N, 14, seed=6)
+    truthFT = reco_port.set_projectee(truth, pf)
+    pixE = capi.pixel_list(N, pf, 28.0, 1.0)
+    pixM = capi.pixel_list(N, pf, 30.0, 0.0)
+    PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
+    nImg = 600
+    slot = (np.arange(nImg) % 2).astype(np.int32)
+    c = capi.Context(0)
+    try:
+        c.set_volume(0, truthFT)
+        quat = synth.random_quats(nImg, rng)
+        tran = rng.normal(scale=1.5, size=(nImg, 2))
+        dU = rng.uniform(1.0e4, 3.0e4, nImg); dV = dU + rng.uniform(0, 500.0, nImg); th = rng.uniform(0, np.pi, nImg)
+
+        def simulate(pix):
+            c.set_expect_pixels(N, pf, pix["iCol"], pix["iRow"])
+            clean = c.project(0, quat)
+            ctf = np.stack([synth.ctf_values(pix["iCol"].astype(float), pix["iRow"].astype(float), N, 1.32, 3e5, dU[l], dV[l], th[l], 2.7e7, 0.1)
+                            for l in range(nImg)]).astype(np.float32)
+            ph = -2 * np.pi * (pix["iCol"][None] * tran[:, :1] / N + pix["iRow"][None] * tran[:, 1:] / N)
+            sig2 = float(np.mean(np.abs(clean * ctf) ** 2)) / 1.0                     # per-pixel SNR 1
+            noise = (rng.normal(size=clean.shape) + 1j * rng.normal(size=clean.shape)) * np.sqrt(sig2 / 2)
+            return (ctf * clean * np.exp(1j * ph) + noise).astype(np.complex64), ctf, sig2
+
+        datM, ctfM, _ = simulate(pixM)
+        datE, ctfE, sig2 = simulate(pixE)
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        c.upload_stack(capi.STACK_EXPECT, datE, ctfE, np.full((nImg, PE), -0.5 / sig2, np.float32), slot)
+        c.upload_stack(capi.STACK_INSERT, datM, ctfM, slotOfImg=slot)
+        # initial reference: the phantom blurred (Gaussian, half amplitude at ~shell 11 of 32)
+        g = np.fft.fftfreq(N)[:, None, None] ** 2 + np.fft.fftfreq(N)[None, :, None] ** 2 + np.fft.rfftfreq(N)[None, None, :] ** 2
+        blurred = np.fft.irfftn(np.fft.rfftn(truth) * np.exp(-g / (2 * 0.15 ** 2)), s=(N, N, N), axes=(0, 1, 2)).astype(np.float32)
+        truthF = np.fft.rfftn(truth).astype(np.complex64)
+        for s in (0, 1):
+            c.set_projectee(s, blurred, N, pf)
+            c.reco_alloc(s, N * pf)
+        k0 = 1e-4
+        q_start = np.stack([synth.acg_cloud(quat[l], k0, 1, rng)[0] for l in range(nImg)])
+        t_start = tran + rng.normal(scale=0.5, size=(nImg, 2))
+        k123 = np.full((nImg, 3), k0); s01 = np.full((nImg, 2), 1.0)
+        c.pf_set_image_base(0, 0)
+        fsc_truth, fsc_half, err = [], [], []
+        for it in range(3):
+            prm = _params(fixed=6, seed=100 + it)
+            c.pf_load(prm, q_start, k123, t_start, s01)
+            c.expectation()
+            sc = c.pf_get_scal()
+            q_start, t_start = sc[:, 6:10].copy(), sc[:, 10:12].copy()       # next iteration starts from this one's best
+            k123 = np.maximum(sc[:, 0:3], 1e-6); s01 = np.maximum(sc[:, 3:5], 0.1)
+            for s in (0, 1):
+                c.reco_reset(s)
+            c.reconstruct_insert(20)
+            c.allreduce()
+            vols = []
+            for s in (0, 1):
+                v, nit = c.reconstruct(s, N, pf)
+                assert np.isfinite(v).all()
+                c.set_projectee(s, None, N, pf)                               # the next E-step projects from the new map
+                vols.append(v)
+            vF = [np.fft.rfftn(v).astype(np.complex64) for v in vols]
+            ft = [synth.fsc(x, truthF, N // 2 - 4) for x in vF]
+            f = synth.fsc(vF[0], vF[1], N // 2 - 4)
+            fsc_truth.append(ft); fsc_half.append(f); err.append(float(np.median(_ang_deg(q_start, quat))))
+            print(f"\niteration {it}: FSC with the phantom at shells 2/8/16 " + " ".join(f"{x[2]:.3f}/{x[8]:.3f}/{x[16]:.3f}" for x in ft)
+                  + f", half-map FSC {f[2]:.3f}/{f[8]:.3f}/{f[16]:.3f}, median orientation error {err[-1]:.2f} deg")
+        assert err[-1] < 5.0 and err[-1] <= err[0] + 1.0                      # the loop holds the orientations
+        assert min(x[1:9].min() for x in fsc_truth[-1]) > 0.9                 # ... and the maps stay the phantom
+        assert fsc_half[-1][1:9].min() > 0.9
+    finally:
+        c.close()

@@ -142,3 +142,44 @@ def test_device_remask_pack(ctx):
             assert np.linalg.norm(imgs[l] - want) <= 2e-6 * np.linalg.norm(want), (zm, l)
             assert np.array_equal(got["dat"][l], imgs[l].ravel()[pixE["iPxl"]])
         assert np.array_equal(got["sigRcp"], sigRcpTab[group][:, pixE["iSig"]])
+
+
+# ------------------------------------------------------------------------------------------- section 8(f) row 3
+@pytest.mark.gpu
+def test_device_sigma_accumulate(ctx):
+    """thb_sigma_accumulate == the image loop of Optimiser::allReduceSigma driven through the reference's own functions
+    (Projector::project(Image&, rot, t), CTF(Image&), powerSpectrum, NEG_FT / ADD_FT)"""
+    from oracle import refapi
+    from thunder_b200 import capi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, pf, rSig = 64, 2, 24
+    rng = np.random.default_rng(77)
+    vol = synth.phantom(N, 10, seed=4)
+    P = refapi.Projector(pf)
+    P.set_from_real(vol)
+    volFT = P.padded_ft()
+    pixE = capi.pixel_list(N, pf, float(rSig), 0.0)          # the sigma pixel set: rL = 0, r = rSig
+    pixM = capi.pixel_list(N, pf, 29.0, 0.0)                 # the M list reaches further out
+    nImg, nGroup = 9, 3
+    img = np.stack([np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)) for _ in range(nImg)]).astype(np.complex64)
+    ori = np.stack([np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)) for _ in range(nImg)]).astype(np.complex64)
+    img *= np.float32(np.abs(volFT).mean() * 3 / np.abs(img).mean()); ori *= np.float32(np.abs(volFT).mean() * 3 / np.abs(ori).mean())
+    quat = synth.random_quats(nImg, rng)
+    tran = rng.normal(scale=1.5, size=(nImg, 2)); offS = rng.normal(scale=1.0, size=(nImg, 2))
+    group = rng.integers(0, nGroup, nImg).astype(np.int32)
+    attr = np.stack([np.full(nImg, 3e5), rng.uniform(1e4, 3e4, nImg), rng.uniform(1e4, 3e4, nImg), rng.uniform(0, np.pi, nImg),
+                     np.full(nImg, 2.7e7), np.full(nImg, 0.1), np.zeros(nImg)], axis=1).astype(np.float32)
+    want = refapi.sigma_accumulate(P, img, ori, quat, tran, offS, attr, 1.32, group, nGroup, rSig)
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+    ctx.set_volume(0, volFT)
+    tab = np.full((1, N), -0.5, np.float32)
+    ctx.stack_reserve(capi.STACK_EXPECT, nImg); ctx.stack_reserve(capi.STACK_INSERT, nImg)
+    ctx.pack_stack(capi.STACK_EXPECT, 0, img, pixE["iPxl"], attr, 1.32, iSig=pixE["iSig"], sigRcpTab=tab)
+    ctx.pack_stack(capi.STACK_INSERT, 0, ori, pixM["iPxl"], attr, 1.32)
+    got = ctx.sigma_accumulate(quat, tran, offS, group, nGroup, rSig, pixE["iSig"], pixM["iSig"])
+    for name, g, w in zip(("sigM", "sigN", "svd"), got, want):
+        assert np.array_equal(g[:, -1], w[:, -1]), name                        # weight sums: images per group
+        assert np.allclose(g[:, :rSig], w[:, :rSig], rtol=2e-4, atol=0), name
+    P.close()

@@ -71,6 +71,7 @@ def _sig(lib):
     f = lib.thb_reconstruct; f.restype = _i; f.argtypes = [_p, _i, _i, _i, C.c_double, C.c_double, _i, _i, _p, _i, _i, _p, _p]
     f = lib.thb_set_projectee; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i]
     f = lib.thb_remask_pack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, C.c_float, _i, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p, _p]
+    f = lib.thb_sigma_accumulate; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
@@ -283,6 +284,17 @@ class Context:
         self._chk(self.lib.thb_remask_pack(self.h, base, nImg, _ptr(imgOriFT), _ptr(offset), float(maskRadiusPx), int(zeroMask), _ptr(iPxl),
                                            _ptr(iSig), _ptr(sigRcpTab), sigRcpTab.shape[0], sigRcpTab.shape[1], _ptr(groupOfImg), _ptr(ctfAttr),
                                            float(pixelSize), _ptr(slotOfImg), _ptr(out)))
+        return out
+
+    def sigma_accumulate(self, quat, tran, offS, groupOfImg, nGroup, rSig, iSigE, iSigM, imgIdx=None):
+        """image loop of Optimiser::allReduceSigma (SURVEY.md section 8f row 3) -> sigM, sigN, svd [nGroup][rSig+1]"""
+        quat = _arr(quat, np.float64); nImg = quat.shape[0]
+        tran = _arr(tran, np.float64, (nImg, 2)); offS = _arr(offS, np.float64, (nImg, 2))
+        groupOfImg = _arr(groupOfImg, np.int32, (nImg,)); imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        iSigE = _arr(iSigE, np.int32); iSigM = _arr(iSigM, np.int32)
+        out = [np.zeros((nGroup, rSig + 1)) for _ in range(3)]
+        self._chk(self.lib.thb_sigma_accumulate(self.h, nImg, _ptr(imgIdx), _ptr(quat), _ptr(tran), _ptr(offS), _ptr(groupOfImg), nGroup, rSig,
+                                                _ptr(iSigE), _ptr(iSigM), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
         return out
 
     # ---- reconstruct / setProjectee (SURVEY.md section 8f row 1)

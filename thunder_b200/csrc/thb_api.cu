@@ -103,7 +103,7 @@ static int ensure_quad(thb_ctx* ctx, int slot)
 {
     Volume3& v = ctx->vols[slot];
     if (!v.d) return THB_OK;
-    if (v.quad && v.quadBrick == ctx->quadBrick) return THB_OK;
+    if (v.quad && v.quadBrick == ctx->quadBrick && v.quadOct == ctx->quadOct) return THB_OK;
     if ((v.vdim / 2) % (1 << ctx->quadBrick)) ctx->quadBrick = 0;   // tiny volumes: plain rows
     if (v.quad) {
         THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -111,10 +111,19 @@ static int ensure_quad(thb_ctx* ctx, int slot)
         v.quad = nullptr;
     }
     const size_t elems = (size_t)v.vdim * v.vdim * (v.vdim / 2);
-    THB_CUDA(ctx, cudaMalloc(&v.quad, elems * sizeof(Quad)));
+    if (ctx->quadOct && cudaMalloc(&v.quad, elems * sizeof(Quad) * 2) != cudaSuccess) {
+        cudaGetLastError();          // not enough HBM for the 64-byte layout: use the 32-byte one
+        v.quad = nullptr;
+        ctx->quadOct = 0;
+    }
+    if (!ctx->quadOct) THB_CUDA(ctx, cudaMalloc(&v.quad, elems * sizeof(Quad)));
     span_begin(ctx, KF_PACK);
-    build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
+    if (ctx->quadOct)
+        build_oct_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
+    else
+        build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
     v.quadBrick = ctx->quadBrick;
+    v.quadOct = ctx->quadOct;
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -138,10 +147,12 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     }
     const size_t smem = E3_SMEM_BYTES + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
-    if (ctx->expectMinBlocks >= 3)
-        expect_direct_kernel<3><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+    if (ctx->quadOct)
+        expect_direct_kernel<2, true><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+    else if (ctx->expectMinBlocks >= 3)
+        expect_direct_kernel<3, false><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
     else
-        expect_direct_kernel<2><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+        expect_direct_kernel<2, false><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -263,6 +274,7 @@ int thb_create(thb_ctx** out, int device)
     ctx->smCount = prop.multiProcessorCount;
     if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("THB_QUAD_BRICK")) ctx->quadBrick = std::max(0, std::min(4, atoi(e)));
+    if (const char* e = getenv("THB_QUAD_OCT")) ctx->quadOct = atoi(e) != 0;
     if (const char* e = getenv("THB_SORT_ROT")) ctx->sortRot = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_MINB")) ctx->expectMinBlocks = atoi(e) >= 3 ? 3 : 2;
     if (const char* e = getenv("THB_INSERT_IMPL")) ctx->insertImpl = atoi(e);
@@ -374,6 +386,10 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
     if (!strcmp(key, "quad_brick")) {
         if (value < 0 || value > 4) return set_error(ctx, THB_E_ARG, "set_option: quad_brick must be in [0,4]");
         ctx->quadBrick = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "quad_oct")) {
+        ctx->quadOct = value != 0;
         return THB_OK;
     }
     if (!strcmp(key, "sort_rot")) {

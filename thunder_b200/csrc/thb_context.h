@@ -32,6 +32,7 @@ struct Volume3 {
     int vdim = 0;
     int pitch = 0;
     int quadBrick = -1;          // brick setting the quad copy was built with
+    int quadOct = -1;            // 0: quad (32 B / voxel), 1: oct (64 B / voxel) copy
     void* quad = nullptr;        // quad layout for the direct-gather kernel: n*n*(n/2) x 32 bytes (built on upload)
 };
 
@@ -89,6 +90,8 @@ struct thb_ctx {
     int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
     int expectImpl = 3;          // 3: direct gather from the quad layout (default), 2: TMA-staged box, 1: direct gather, linear layout
     int quadBrick = 2;           // log2 brick edge of the quad layout (option "quad_brick"; 4x4x4 bricks measured best)
+    int quadOct = 1;             // option "quad_oct": whole trilinear cell in one 64-byte element (8x volume bytes; default,
+                                 // falls back to the 32-byte quad when HBM is short)
     int sortRot = 0;             // option "sort_rot"
     int expectMinBlocks = 2;     // CTAs per SM the quad kernel is compiled for (2 or 3)
 

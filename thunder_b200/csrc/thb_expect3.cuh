@@ -44,6 +44,31 @@ __device__ __forceinline__ size_t quad_index(int x, int ym, int zm, int n, int L
     return (brick << (3 * LB)) | (size_t)((((zm & m) << LB) | (ym & m)) << LB | (x & m));
 }
 
+// "oct" variant of the layout: element (x, y, z) = { quad(x, y, z), quad(x, y, z+1) }, 64 bytes, z+1 wrapped as the
+// reference wraps it: the whole trilinear cell is one 64-byte aligned chunk (two LDG.256 to one line, one DRAM burst
+// of 64 bytes instead of two scattered 32-byte sectors).  8x the volume bytes (4.3 GB at box 256).
+__global__ void build_oct_kernel(const float2* __restrict__ vol, int n, int pitch, int LB, Quad* __restrict__ out)
+{
+    const int half = n / 2;
+    const size_t total = (size_t)n * n * half;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % half);
+        const size_t row = i / half;
+        const int y = (int)(row % n), z = (int)(row / n);
+        const int y1 = (y + 1 == n) ? 0 : y + 1, z1 = (z + 1 == n) ? 0 : z + 1;
+        const float2* r00 = vol + ((size_t)z * n + y) * pitch + x;
+        const float2* r01 = vol + ((size_t)z * n + y1) * pitch + x;
+        const float2* r10 = vol + ((size_t)z1 * n + y) * pitch + x;
+        const float2* r11 = vol + ((size_t)z1 * n + y1) * pitch + x;
+        Quad a, b;
+        a.v00 = r00[0]; a.v10 = r00[1]; a.v01 = r01[0]; a.v11 = r01[1];
+        b.v00 = r10[0]; b.v10 = r10[1]; b.v01 = r11[0]; b.v11 = r11[1];
+        const size_t o = 2 * quad_index(x, y, z, n, LB);
+        out[o] = a;
+        out[o + 1] = b;
+    }
+}
+
 // linear pitched float2 volume -> quad layout, x in [0, half)
 __global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pitch, int LB, Quad* __restrict__ out)
 {
@@ -67,7 +92,7 @@ constexpr int E3_ROTS = 128;
 constexpr int E3_TILE = 128;
 constexpr size_t E3_SMEM_BYTES = E3_TILE * sizeof(PixelRec);     // + the [nR][nT] table for single-pass shapes
 
-template <int MINB>
+template <int MINB, bool OCT>
 __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const ExpectArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -219,8 +244,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         const int ym = y0 < 0 ? y0 + n : y0;
                         const int zm = z0 < 0 ? z0 + n : z0;
                         const int zm1 = (z0 + 1 < 0) ? z0 + 1 + n : z0 + 1;
-                        const Quad* q0 = vol + quad_index(x0, ym, zm, n, LB);
-                        const Quad* q1 = vol + quad_index(x0, ym, zm1, n, LB);
+                        const Quad* q0 = OCT ? vol + 2 * quad_index(x0, ym, zm, n, LB) : vol + quad_index(x0, ym, zm, n, LB);
+                        const Quad* q1 = OCT ? q0 + 1 : vol + quad_index(x0, ym, zm1, n, LB);
                         const Quad a = ldg_quad(q0), b = ldg_quad(q1);
                         float w[8];
                         tri_weights(xd, yd, zd, w);

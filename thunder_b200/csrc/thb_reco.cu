@@ -246,6 +246,107 @@ __global__ void img_mask_kernel(float* rl, int N, int nImg, float r, float ew)
     }
 }
 
+// ---- section 8(f) row 3: per-image part of Optimiser::allReduceSigma (src/Optimiser.cpp:6428-6600) on the resident stacks.
+// One CTA per image.  E-stack pixel i (ring uE): model = ctf * polar(-phase(t)) * slice ; M-stack pixel (ring uM < rSig,
+// |k|^2 < rSig^2): the same slice at t - offset.  Ring sums in shared memory, then ring averages (the ring populations
+// cntE / cntM are properties of the pixel lists) and the per-group sums the reference all-reduces.
+__device__ __forceinline__ float2 gather_lin(const float2* __restrict__ vol, int n, int pitch, float x, float y, float z)
+{
+    int x0, y0, z0;
+    float xd, yd, zd;
+    const bool conj = fold_floor(x, y, z, x0, y0, z0, xd, yd, zd);
+    float w[8];
+    tri_weights(xd, yd, zd, w);
+    int64_t off[4];
+    row_offsets(y0, z0, n, pitch, off);
+    float re = 0.0f, im = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float2 a = __ldg(vol + off[c] + x0), b = __ldg(vol + off[c] + x0 + 1);
+        re += a.x * w[2 * c]; im += a.y * w[2 * c];
+        re += b.x * w[2 * c + 1]; im += b.y * w[2 * c + 1];
+    }
+    return make_float2(re, conj ? -im : im);
+}
+
+struct SigmaArgs {
+    const float2* vols[THB_MAX_SLOTS];
+    int vdim, pitch, N, rSig, nGroup;
+    const float2* datE; const float* ctfE; const int* slotE; const int4* pixE; const int* ringE; int PE;
+    const float2* datM; const float* ctfM; const int4* pixM; const int* ringM; int PM;   // ringM < 0: pixel not in the sigma set
+    const int* imgIdx; const double* quat; const double* tran; const double* offS; const int* group;
+    const float* cntE; const float* cntM;
+    double* sigM; double* sigN; double* svd;      // [nGroup][rSig + 1]
+};
+
+__global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
+{
+    extern __shared__ float sRing[];               // [4][rSig]: vSigM, sSVD, dSVD, vSigN
+    const int l = blockIdx.x, tid = threadIdx.x, rS = A.rSig;
+    const int img = A.imgIdx ? A.imgIdx[l] : l;
+    for (int i = tid; i < 4 * rS; i += blockDim.x) sRing[i] = 0.0f;
+    __syncthreads();
+    const float2* __restrict__ vol = A.vols[A.slotE ? A.slotE[img] : 0];
+    double q[4] = {A.quat[4 * l], A.quat[4 * l + 1], A.quat[4 * l + 2], A.quat[4 * l + 3]};
+    const Rot2 rot = quat_to_rot2(q);
+    const float tx = (float)A.tran[2 * l], ty = (float)A.tran[2 * l + 1];
+    const float ox = (float)(A.tran[2 * l] - A.offS[2 * l]), oy = (float)(A.tran[2 * l + 1] - A.offS[2 * l + 1]);
+    const float invN = 1.0f;   // placeholder to keep the divisions below explicit
+    (void)invN;
+    for (int i = tid; i < A.PE; i += blockDim.x) {
+        const int u = A.ringE[i];
+        if (u < 0 || u >= rS) continue;
+        const int4 c = A.pixE[i];
+        float x, y, z;
+        slice_coord(rot, (double)c.x, (double)c.y, x, y, z);
+        const float2 p = gather_lin(vol, A.vdim, A.pitch, x, y, z);
+        const float ph = translate_phase(c.z, c.w, tx / (float)A.N, ty / (float)A.N);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        // p * polar(-ph), then * ctf
+        const float cf = A.ctfE[(size_t)img * A.PE + i];
+        const float mx = (p.x * cs + p.y * sn) * cf, my = (p.y * cs - p.x * sn) * cf;
+        const float2 d = A.datE[(size_t)img * A.PE + i];
+        const float rx = d.x - mx, ry = d.y - my;
+        atomicAdd(&sRing[u], rx * rx + ry * ry);
+        atomicAdd(&sRing[rS + u], mx * mx + my * my);
+        atomicAdd(&sRing[2 * rS + u], d.x * d.x + d.y * d.y);
+    }
+    for (int i = tid; i < A.PM; i += blockDim.x) {
+        const int u = A.ringM[i];
+        if (u < 0 || u >= rS) continue;
+        const int4 c = A.pixM[i];
+        float x, y, z;
+        slice_coord(rot, (double)c.x, (double)c.y, x, y, z);
+        const float2 p = gather_lin(vol, A.vdim, A.pitch, x, y, z);
+        const float ph = translate_phase(c.z, c.w, ox / (float)A.N, oy / (float)A.N);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float cf = A.ctfM[(size_t)img * A.PM + i];
+        const float mx = (p.x * cs + p.y * sn) * cf, my = (p.y * cs - p.x * sn) * cf;
+        const float2 d = A.datM[(size_t)img * A.PM + i];
+        const float rx = d.x - mx, ry = d.y - my;
+        atomicAdd(&sRing[3 * rS + u], rx * rx + ry * ry);
+    }
+    __syncthreads();
+    const int g = A.group ? A.group[l] : 0;
+    const size_t row = (size_t)g * (rS + 1);
+    for (int u = tid; u < rS; u += blockDim.x) {
+        const float cE = A.cntE[u], cM = A.cntM[u];
+        if (cE > 0.0f) {
+            const float vM = sRing[u] / cE, sS = sRing[rS + u] / cE, dS = sRing[2 * rS + u] / cE;
+            atomicAdd(&A.sigM[row + u], (double)(vM / 2));
+            atomicAdd(&A.svd[row + u], (double)sqrtf(sS / dS));
+        }
+        if (cM > 0.0f) atomicAdd(&A.sigN[row + u], (double)((sRing[3 * rS + u] / cM) / 2));
+    }
+    if (tid == 0) {
+        atomicAdd(&A.sigM[row + rS], 1.0);
+        atomicAdd(&A.sigN[row + rS], 1.0);
+        atomicAdd(&A.svd[row + rS], 1.0);
+    }
+}
+
 __global__ void reco_upload_kernel(const float2* F, const float* T, size_t nVox, float4* acc)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nVox; i += (size_t)gridDim.x * blockDim.x)
@@ -537,6 +638,82 @@ int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, con
         THB_CUDA(ctx, cudaMemcpyAsync(st.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     else
         THB_CUDA(ctx, cudaMemsetAsync(st.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+// section 8(f) row 3: the image loop of Optimiser::allReduceSigma on the resident stacks
+int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double* quat, const double* tran, const double* offS,
+                         const int* groupOfImg, int nGroup, int rSig, const int* iSigE, const int* iSigM, double* sigM, double* sigN,
+                         double* svd)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->pixE || !ctx->pixM || !ctx->stackE.dat || !ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "sigma_accumulate: pixel lists / stacks missing");
+    if (nImg <= 0 || !quat || !tran || !iSigE || !iSigM || !sigM || !sigN || !svd || nGroup <= 0 || rSig <= 0)
+        return set_error(ctx, THB_E_ARG, "sigma_accumulate: bad arguments");
+    if (!imgIdx && (nImg > ctx->stackE.nImg || nImg > ctx->stackM.nImg)) return set_error(ctx, THB_E_ARG, "sigma_accumulate: nImg exceeds the stacks");
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->vols[i].d) vdim = ctx->vols[i].vdim;
+    if (!vdim) return set_error(ctx, THB_E_STATE, "sigma_accumulate: no projector volume");
+    for (int l = 0; l < nImg; ++l) {
+        if (imgIdx && (imgIdx[l] < 0 || imgIdx[l] >= ctx->stackE.nImg || imgIdx[l] >= ctx->stackM.nImg)) return set_error(ctx, THB_E_ARG, "sigma_accumulate: imgIdx[%d] outside the stacks", l);
+        if (groupOfImg && (groupOfImg[l] < 0 || groupOfImg[l] >= nGroup)) return set_error(ctx, THB_E_ARG, "sigma_accumulate: groupOfImg[%d] out of range", l);
+    }
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int PE = ctx->nPxlE, PM = ctx->nPxlM, pfM = ctx->pfM;
+    // rings in the device (blocked) pixel order; ring populations of the sigma pixel set {|k|^2 < rSig^2, rint|k| < rSig}
+    std::vector<int> permE(PE), permM(PM), ringE(PE), ringM(PM);
+    std::vector<int4> pixM(PM);
+    THB_CUDA(ctx, cudaMemcpy(permE.data(), ctx->permE, sizeof(int) * PE, cudaMemcpyDeviceToHost));
+    THB_CUDA(ctx, cudaMemcpy(permM.data(), ctx->permM, sizeof(int) * PM, cudaMemcpyDeviceToHost));
+    THB_CUDA(ctx, cudaMemcpy(pixM.data(), ctx->pixM, sizeof(int4) * PM, cudaMemcpyDeviceToHost));
+    std::vector<float> cntE(rSig, 0.f), cntM(rSig, 0.f);
+    for (int i = 0; i < PE; ++i) {
+        ringE[i] = iSigE[permE[i]];
+        if (ringE[i] >= 0 && ringE[i] < rSig) cntE[ringE[i]] += 1.f;
+    }
+    for (int i = 0; i < PM; ++i) {
+        const long long a = pixM[i].z, b = pixM[i].w;      // unpadded iCol, iRow
+        const int u = iSigM[permM[i]];
+        ringM[i] = (a * a + b * b < (long long)rSig * rSig && u < rSig) ? u : -1;
+        if (ringM[i] >= 0) cntM[ringM[i]] += 1.f;
+    }
+    (void)pfM;
+    const size_t nOut = (size_t)nGroup * (rSig + 1);
+    unsigned char* buf = (unsigned char*)scratch(ctx, 0, sizeof(double) * (3 * nOut + 8 * (size_t)nImg) + sizeof(int) * ((size_t)PE + PM + 2 * (size_t)nImg) + sizeof(float) * 2 * (size_t)rSig + 64);
+    if (!buf) return THB_E_CUDA;
+    double* dOut = (double*)buf;
+    double* dQ = dOut + 3 * nOut; double* dT = dQ + 4 * (size_t)nImg; double* dO = dT + 2 * (size_t)nImg;
+    int* dRingE = (int*)(dO + 2 * (size_t)nImg); int* dRingM = dRingE + PE; int* dIdx = dRingM + PM; int* dGrp = dIdx + nImg;
+    float* dCntE = (float*)(dGrp + nImg); float* dCntM = dCntE + rSig;
+    std::vector<double> zeroOff(2 * (size_t)nImg, 0.0);
+    THB_CUDA(ctx, cudaMemsetAsync(dOut, 0, sizeof(double) * 3 * nOut, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dQ, quat, sizeof(double) * 4 * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dT, tran, sizeof(double) * 2 * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dO, offS ? offS : zeroOff.data(), sizeof(double) * 2 * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dRingE, ringE.data(), sizeof(int) * PE, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dRingM, ringM.data(), sizeof(int) * PM, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(dIdx, imgIdx, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    if (groupOfImg) THB_CUDA(ctx, cudaMemcpyAsync(dGrp, groupOfImg, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dCntE, cntE.data(), sizeof(float) * rSig, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dCntM, cntM.data(), sizeof(float) * rSig, cudaMemcpyHostToDevice, ctx->stream));
+    SigmaArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) a.vols[i] = ctx->vols[i].d;
+    a.vdim = vdim; a.pitch = (vdim / 2 + 2 + 3) & ~3; a.N = ctx->N; a.rSig = rSig; a.nGroup = nGroup;
+    a.datE = ctx->stackE.dat; a.ctfE = ctx->stackE.ctf; a.slotE = ctx->stackE.slot; a.pixE = ctx->pixE; a.ringE = dRingE; a.PE = PE;
+    a.datM = ctx->stackM.dat; a.ctfM = ctx->stackM.ctf; a.pixM = ctx->pixM; a.ringM = dRingM; a.PM = PM;
+    a.imgIdx = imgIdx ? dIdx : nullptr; a.quat = dQ; a.tran = dT; a.offS = dO; a.group = groupOfImg ? dGrp : nullptr;
+    a.cntE = dCntE; a.cntM = dCntM; a.sigM = dOut; a.sigN = dOut + nOut; a.svd = dOut + 2 * nOut;
+    span_begin(ctx, KF_PACK);
+    sigma_kernel<<<nImg, 256, sizeof(float) * 4 * rSig, ctx->stream>>>(a);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaMemcpyAsync(sigM, dOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(sigN, dOut + nOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(svd, dOut + 2 * nOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
