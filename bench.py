@@ -279,18 +279,28 @@ def main():
     k123 = np.full((B, 3), wl["k0"]); s01 = np.full((B, 2), 1.0)
     nBatches = max(nRes // B, 1)
 
+    def upload_async(i):
+        """e2e: batch i of the host stack -> its place in the resident stacks, on the copy stream"""
+        base = (i % nBatches) * B
+        ctx.upload_stack_at_async(capi.STACK_EXPECT, base, hb["datE"], hb["ctfE"], hb["sigE"], slot_b)
+        ctx.upload_stack_at_async(capi.STACK_INSERT, base, hb["datM"], hb["ctfM"], None, slot_b)
+
     def step(i, e2e=False):
         base = (i % nBatches) * B
         if e2e:
-            ctx.upload_stack_at(capi.STACK_EXPECT, base, hb["datE"], hb["ctfE"], hb["sigE"], slot_b)
-            ctx.upload_stack_at(capi.STACK_INSERT, base, hb["datM"], hb["ctfM"], None, slot_b)
+            ctx.upload_wait()                   # this batch: enqueued during the previous step
+            if nBatches > 1:
+                upload_async(i + 1)             # next batch: overlaps this batch's kernels (double buffering over the stack)
         ctx.pf_set_image_base(base, rank * nRes + base)
         ctx.pf_load(prm, q_start, k123, t_start, s01)
         ctx.expectation()
         ctx.reconstruct_insert(args.mreco)
         ctx.allreduce()
         if e2e:
-            return ctx.pf_get_scal()
+            res = ctx.pf_get_scal()
+            if nBatches == 1:
+                upload_async(i + 1)             # a single resident batch cannot be double-buffered: upload after the step
+            return res
         return None
 
     def barrier():
@@ -299,15 +309,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    acc_out = None
+
     def timed(nsteps, first, e2e):
+        nonlocal acc_out
+        if e2e and acc_out is None:
+            m = N * pf
+            acc_out = []
+            for s_ in (0, 1):
+                tF = torch.empty((m, m, m // 2 + 1), dtype=torch.complex64).pin_memory()
+                tT = torch.empty((m, m, m // 2 + 1), dtype=torch.float32).pin_memory()
+                keep.extend([tF, tT])
+                acc_out.append((tF.numpy(), tT.numpy()))
+        if e2e:
+            upload_async(first)                 # prologue of the pipeline (one upload per timed step follows inside)
         barrier()
         ctx.timer_start()
         t0 = time.perf_counter()
         for i in range(nsteps):
             step(first + i, e2e)
         if e2e:
-            for s in (0, 1):
-                ctx.reco_download(s)
+            ctx.upload_wait()                   # the upload enqueued by the last step is inside the timed region
+            for s_ in (0, 1):
+                ctx.reco_download(s_, out=acc_out[s_])
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
@@ -332,12 +356,14 @@ def main():
     e2e = None
     if not args.no_e2e:
         k2 = max(1, min(args.steps, 2))
-        step(0, e2e=True)                                        # warm the e2e path (staging buffers)
+        upload_async(0)
+        step(0, e2e=True)                                        # warm the e2e path (staging buffers, copy stream)
+        ctx.upload_wait()
         ms2, wall2 = timed(k2, 1, e2e=True)
         h2d = B * (PE * 16 + PM * 12) + B * 11 * 8
         d2h = B * 20 * 8 + (2 * (N * pf // 2 + 1) * (N * pf) ** 2 * 12) // k2
         e2e = {"value": world * B * k2 / (wall2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": k2, "note": "host wall clock around pinned-host upload + iteration + result download"}
+               "steps": k2, "note": "host wall clock around: pinned-host upload of every batch (second stream, overlapping the previous batch's kernels) + iteration + particle results to the host each step + both half-map accumulators to pinned host memory once"}
 
     # ---- outside the metric (reported separately): the once-per-iteration reconstruction of both
     # half maps from the accumulators and the refresh of the projector volumes, all on the device (section 8f row 1)
@@ -362,7 +388,7 @@ def main():
         alg_bytes = B * (PE * 16 + args.mlr * PE * 64.0)           # B_E per particle-phase x particles per launch
         achieved = alg_bytes / (e_ms / max(e_n, 1) / 1e3) / 1e9 if e_n else None
         tr = ncu_traffic(PE, args.mlr)
-        roof = {"bound": "hbm", "kernel": "expect_direct_kernel (fused slice extraction + likelihood, quad volume layout)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "expect_direct_kernel<2,1> (fused slice extraction + likelihood, whole-cell \"oct\" volume layout)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                 "traffic": (tr["dram_bytes_per_particle_phase"] * B if tr else None),
                 "traffic_source": (tr["source"] if tr else None),

@@ -122,6 +122,13 @@ int thb_upload_stack(thb_ctx* ctx, int kind, int nImg, const float* dat, const f
 int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity);
 int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf,
                         const float* sigRcp, const int* slotOfImg);
+/* The same on a second stream, returning at once, so that the upload of the next batch overlaps the kernels of
+ * the current one (the reference pins the caller's arrays and streams them per call, gpu/src/cuthunder.cu:5370-5412).
+ * Contract: page-locked host arrays that stay valid, and images [base, base+nImg) untouched by any other call,
+ * until thb_upload_wait() has returned; thb_upload_wait also orders all later work on the context after the upload. */
+int thb_upload_stack_at_async(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf,
+                              const float* sigRcp, const int* slotOfImg);
+int thb_upload_wait(thb_ctx* ctx);
 
 /* a2 on the device - Optimiser::allocPreCal (src/Optimiser.cpp:8043-8171, image-major, OPTIMISER_CTF_ON_THE_FLY):
  * fill images [base, base+nImg) of a reserved stack from their full half-complex FTs (_img for the E stack, _imgOri
@@ -211,7 +218,9 @@ int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, con
  * offset offS[l][2] (NULL = 0), the ring-averaged power of  masked image - ctf * translated slice  (E stack, translation
  * tran), of  original image - ctf * translated slice  (M stack, translation tran - offS) and the signal / data spectra of the
  * SVD ratio, summed per group.  iSigE / iSigM: the ring of every pixel of the two pixel lists (thb_pixel_list).  The sigma
- * pixel set is {|k|^2 < rSig^2, rint|k| < rSig}; rings the E list does not reach (below its rL) stay zero.
+ * pixel set is {|k|^2 < rSig^2, rint|k| < rSig}; rings the E list does not reach (below its rL) stay zero.  The packed lists
+ * hold one of each Hermitian pair on the i = 0 column (src/Optimiser.cpp:8015) while powerSpectrum() walks the whole half
+ * plane: those pixels are counted twice, which is exact for the FTs of real images.
  * Outputs [nGroup][rSig + 1] doubles, last column = weight sum: exactly the matrices the reference all-reduces over the
  * hemisphere; the final normalisation and mixing (:6651-6709) are a few hundred flops on the caller's side. */
 int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double* quat, const double* tran, const double* offS,

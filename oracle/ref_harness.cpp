@@ -255,6 +255,19 @@ void ref_projector_project(void* h, float* dst, const double* mat9_colmajor, con
     p->proj.project((Complex*)dst, mat_from_colmajor(mat9_colmajor), iCol, iRow, nPxl, 1);
 }
 
+// Projector::project(Image&, const dmat33&, const dvec2&, nThread), src/Projector.cpp:452-464: the whole-image form that
+// Optimiser::allReduceSigma uses; out = the half-complex image [N][N/2+1]
+void ref_projector_project_image(void* h, int N, const double* quat, const double* tran, float* out)
+{
+    RefProjector* p = (RefProjector*)h;
+    Image img(N, N, FT_SPACE);
+    SET_0_FT(img);
+    dmat33 rot;
+    rotate3D(rot, dvec4(quat[0], quat[1], quat[2], quat[3]));
+    p->proj.project(img, rot, dvec2(tran[0], tran[1]), 1);
+    memcpy(out, &img[0], (size_t)(N / 2 + 1) * N * sizeof(Complex));
+}
+
 // ---------------------------------------------------------------- Reconstructor
 void* ref_reco_create(int size, int N, int pf, int nThread)
 {

@@ -58,6 +58,7 @@ def lib():
         L.ref_reco_create.restype = _p
         L.ref_reco_create.argtypes = [_i, _i, _i, _i]
         L.ref_reco_destroy.argtypes = [_p]
+        L.ref_projector_project_image.argtypes = [_p, _i, _p, _p, _p]
         L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
         L.ref_sigma_accumulate.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p, _p, _p]
         L.ref_reco_set.argtypes = [_p, _p, _p]
@@ -205,6 +206,14 @@ class Projector:
         out = np.empty(len(iCol), np.complex64)
         m = np.ascontiguousarray(mat9, np.float64)
         lib().ref_projector_project(self.h, _ptr(out), _ptr(m), _ptr(iCol), _ptr(iRow), len(iCol))
+        return out
+
+    def project_image(self, N, quat, tran, maxRadius):
+        """Projector::project(Image&, rot, t): half-complex [N][N/2+1], pixels with |k| < maxRadius"""
+        out = np.empty((N, N // 2 + 1), np.complex64)
+        q = np.ascontiguousarray(quat, np.float64); t = np.ascontiguousarray(tran, np.float64)
+        lib().ref_projector_set_max_radius(self.h, int(maxRadius))
+        lib().ref_projector_project_image(self.h, N, _ptr(q), _ptr(t), _ptr(out))
         return out
 
 

@@ -539,3 +539,33 @@ def test_box512_config4_offsets_beyond_4GB():
         assert _rel_l2(a["F"], want["F"]) <= 1e-6 and _rel_l2(a["T"], want["T"]) <= 1e-6
     finally:
         c.close()
+
+
+def test_async_upload_matches_blocking_upload(ctx):
+    """thb_upload_stack_at_async + thb_upload_wait (second stream, overlaps kernels) fills the resident stack exactly like
+    thb_upload_stack_at"""
+    import torch
+    port, ref = _oracle()
+    N, pf = 64, 2
+    rng = np.random.default_rng(5)
+    pixE = port.pixel_list(N, pf, 30.0, 1.0)
+    P, nImg = len(pixE["iCol"]), 24
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.set_volume(0, synth.padded_ft(synth.phantom(N, 6, seed=9), pf)); ctx.set_volume(1, synth.padded_ft(synth.phantom(N, 6, seed=8), pf))
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    tens = [pin((rng.normal(size=(nImg, P)) + 1j * rng.normal(size=(nImg, P))).astype(np.complex64)),
+            pin(rng.uniform(-1, 1, (nImg, P)).astype(np.float32)), pin((-0.5 / rng.uniform(0.5, 2, (nImg, P))).astype(np.float32))]
+    dat, ctf, sig = [t.numpy() for t in tens]
+    slot = (np.arange(nImg) % 2).astype(np.int32)
+    ctx.stack_reserve(capi.STACK_EXPECT, 2 * nImg)
+    ctx.upload_stack_at(capi.STACK_EXPECT, 0, dat, ctf, sig, slot)
+    q = synth.random_quats(5, rng)[None].repeat(nImg, 0); t = rng.normal(size=(nImg, 3, 2))
+    wR, wT = np.full((nImg, 5), 0.2), np.full((nImg, 3), 1 / 3)
+    ctx.upload_stack_at_async(capi.STACK_EXPECT, nImg, dat, ctf, sig, slot)       # in flight while the kernel below runs
+    a = ctx.expect_local(q, t, wR, wT)
+    ctx.upload_wait()
+    b = ctx.expect_local(q, t, wR, wT, imgIdx=np.arange(nImg, 2 * nImg, dtype=np.int32))
+    assert np.array_equal(a["logL"], b["logL"])
+    got = ctx.download_stack(capi.STACK_EXPECT, nImg, nImg)
+    assert np.array_equal(got["dat"], dat) and np.array_equal(got["ctf"], ctf) and np.array_equal(got["sigRcp"], sig)
+    ctx.upload_wait()                                                             # nothing pending: a no-op

@@ -264,7 +264,8 @@ def test_closed_loop_iterations_on_device():
     rng = np.random.default_rng(2024)
     truth = synth.phantom(N, 14, seed=6)
     truthFT = reco_port.set_projectee(truth, pf)
-    pixE = capi.pixel_list(N, pf, 28.0, 1.0)
+    # the E-step frequency limit follows the resolution at which the half maps still agree (Optimiser's _r): shell 14 of 32
+    pixE = capi.pixel_list(N, pf, 14.0, 1.0)
     pixM = capi.pixel_list(N, pf, 30.0, 0.0)
     PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
     nImg = 600

@@ -65,6 +65,8 @@ def _sig(lib):
     f = lib.thb_upload_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p, _p, _p]
     f = lib.thb_stack_reserve; f.restype = _i; f.argtypes = [_p, _i, _i]
     f = lib.thb_upload_stack_at; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_upload_stack_at_async; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
+    f = lib.thb_upload_wait; f.restype = _i; f.argtypes = [_p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
     f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
     f = lib.thb_reco_upload; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
@@ -252,6 +254,18 @@ class Context:
         slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
         self._chk(self.lib.thb_upload_stack_at(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sigRcp), _ptr(slotOfImg)))
 
+    def upload_stack_at_async(self, kind, base, dat, ctf, sigRcp=None, slotOfImg=None):
+        """second-stream upload; the (pinned) arrays must stay alive and unchanged until upload_wait()"""
+        nImg, P = dat.shape
+        assert dat.dtype == np.complex64 and dat.flags.c_contiguous and ctf.dtype == np.float32 and ctf.flags.c_contiguous
+        slotOfImg = _arr(slotOfImg, np.int32, (nImg,))
+        self._async_keep = getattr(self, "_async_keep", []) + [dat, ctf, sigRcp, slotOfImg]
+        self._chk(self.lib.thb_upload_stack_at_async(self.h, kind, base, nImg, _ptr(dat), _ptr(ctf), _ptr(sigRcp), _ptr(slotOfImg)))
+
+    def upload_wait(self):
+        self._chk(self.lib.thb_upload_wait(self.h))
+        self._async_keep = []
+
     def pack_stack(self, kind, base, imgFT, iPxl, ctfAttr, pixelSize, iSig=None, sigRcpTab=None, groupOfImg=None, slotOfImg=None):
         """Optimiser::allocPreCal on the device: imgFT[nImg][N][N/2+1] complex64 full half-FTs, ctfAttr[nImg][7]"""
         imgFT = _arr(imgFT, np.complex64)
@@ -366,11 +380,17 @@ class Context:
         imgIdx = _arr(imgIdx, np.int32, (nImg,))
         self._chk(self.lib.thb_insert(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt)))
 
-    def reco_download(self, slot, normalise=False, want_F=True, want_T=True):
+    def reco_download(self, slot, normalise=False, want_F=True, want_T=True, out=None):
+        """out = (F, T): preallocated (e.g. page-locked) destination arrays"""
         m = self.accdim[slot]
         shape = (m, m, m // 2 + 1)
-        F = np.empty(shape, np.complex64) if want_F else None
-        T = np.empty(shape, np.float32) if want_T else None
+        if out is not None:
+            F, T = out
+            assert F.shape == shape and F.dtype == np.complex64 and F.flags.c_contiguous
+            assert T.shape == shape and T.dtype == np.float32 and T.flags.c_contiguous
+        else:
+            F = np.empty(shape, np.complex64) if want_F else None
+            T = np.empty(shape, np.float32) if want_T else None
         O = np.empty(3, np.float64)
         cnt = np.zeros(1, np.int32)
         self._chk(self.lib.thb_reco_download(self.h, slot, _ptr(F), _ptr(T), _ptr(O), _ptr(cnt), int(normalise)))

@@ -319,7 +319,9 @@ void thb_destroy(thb_ctx* ctx)
     free_stack(ctx->stackM);
     cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
-    for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < THB_N_SCRATCH; ++i) cudaFree(ctx->scratch[i]);
+    if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -644,8 +646,8 @@ int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity)
     return THB_OK;
 }
 
-int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf, const float* sigRcp,
-                        const int* slotOfImg)
+static int upload_stack_impl(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                             const int* slotOfImg, bool async)
 {
     if (!ctx) return THB_E_ARG;
     if (kind != THB_STACK_EXPECT && kind != THB_STACK_INSERT) return set_error(ctx, THB_E_ARG, "upload_stack: bad kind");
@@ -663,32 +665,73 @@ int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float*
                 return set_error(ctx, THB_E_ARG, "upload_stack: slotOfImg[%d] = %d out of range", i, slotOfImg[i]);
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     // stage chunks of images in HBM, then permute each chunk into the resident blocked layout
+    cudaStream_t st = ctx->stream;
+    int sb = 4;
+    if (async) {
+        if (!ctx->copyStream) {
+            THB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+            THB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
+        }
+        st = ctx->copyStream;
+        sb = 8;
+    }
     const size_t perImg = (size_t)P * 16;
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, ((size_t)256 << 20) / perImg));
-    float2* sdat = (float2*)scratch(ctx, 4, (size_t)chunk * P * sizeof(float2));
-    float* sctf = (float*)scratch(ctx, 5, (size_t)chunk * P * sizeof(float));
-    float* ssig = kind == THB_STACK_EXPECT ? (float*)scratch(ctx, 6, (size_t)chunk * P * sizeof(float)) : nullptr;
+    float2* sdat = (float2*)scratch(ctx, sb, (size_t)chunk * P * sizeof(float2));
+    float* sctf = (float*)scratch(ctx, sb + 1, (size_t)chunk * P * sizeof(float));
+    float* ssig = kind == THB_STACK_EXPECT ? (float*)scratch(ctx, sb + 2, (size_t)chunk * P * sizeof(float)) : nullptr;
     if (!sdat || !sctf || (kind == THB_STACK_EXPECT && !ssig)) return THB_E_CUDA;
     for (int i0 = 0; i0 < nImg; i0 += chunk) {
         const int c = std::min(chunk, nImg - i0);
         const size_t off = (size_t)i0 * P, n = (size_t)c * P;
-        THB_CUDA(ctx, cudaMemcpyAsync(sdat, dat + 2 * off, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(sctf, ctf + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        if (ssig) THB_CUDA(ctx, cudaMemcpyAsync(ssig, sigRcp + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(sdat, dat + 2 * off, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+        THB_CUDA(ctx, cudaMemcpyAsync(sctf, ctf + off, n * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (ssig) THB_CUDA(ctx, cudaMemcpyAsync(ssig, sigRcp + off, n * sizeof(float), cudaMemcpyHostToDevice, st));
         const size_t doff = (size_t)(base + i0) * P;
         dim3 grid(std::min((P + 255) / 256, 64), c);
-        span_begin(ctx, KF_PACK);
-        permute_stack_kernel<<<grid, 256, 0, ctx->stream>>>(sdat, sctf, ssig, perm, P, c, s.dat + doff, s.ctf + doff,
-                                                            ssig ? s.sig + doff : nullptr);
-        span_end(ctx);
+        if (!async) span_begin(ctx, KF_PACK);
+        permute_stack_kernel<<<grid, 256, 0, st>>>(sdat, sctf, ssig, perm, P, c, s.dat + doff, s.ctf + doff,
+                                                   ssig ? s.sig + doff : nullptr);
+        if (!async) span_end(ctx);
         ctx->launches++;
         THB_CUDA(ctx, cudaGetLastError());
     }
     if (slotOfImg)
-        THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, st));
     else
-        THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+        THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), st));
+    if (async) {
+        THB_CUDA(ctx, cudaEventRecord(ctx->copyDone, st));
+        ctx->copyPending = true;
+        return THB_OK;
+    }
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_upload_stack_at(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                        const int* slotOfImg)
+{
+    return upload_stack_impl(ctx, kind, base, nImg, dat, ctf, sigRcp, slotOfImg, false);
+}
+
+// The same upload on a second stream, returning at once: the copies and the re-layout overlap whatever the compute stream is
+// doing (the previous batch's kernels).  Contract: the host arrays stay valid and the images [base, base+nImg) are neither
+// read nor written by other calls until thb_upload_wait() returns.
+int thb_upload_stack_at_async(thb_ctx* ctx, int kind, int base, int nImg, const float* dat, const float* ctf, const float* sigRcp,
+                              const int* slotOfImg)
+{
+    return upload_stack_impl(ctx, kind, base, nImg, dat, ctf, sigRcp, slotOfImg, true);
+}
+
+int thb_upload_wait(thb_ctx* ctx)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->copyPending) return THB_OK;
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0));
+    THB_CUDA(ctx, cudaEventSynchronize(ctx->copyDone));
+    ctx->copyPending = false;
     return THB_OK;
 }
 

@@ -70,6 +70,7 @@ struct PFState {
 
 }  // namespace thb
 
+#define THB_N_SCRATCH 11
 struct thb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -118,8 +119,12 @@ struct thb_ctx {
     int64_t famN[thb::KF_COUNT] = {0, 0, 0, 0, 0};
 
     // scratch device buffers (grown on demand)
-    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratchCap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* scratch[THB_N_SCRATCH] = {};
+    size_t scratchCap[THB_N_SCRATCH] = {};
+    // second stream for host->device image uploads that overlap the kernels of the previous batch
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t copyDone = nullptr;
+    bool copyPending = false;
 };
 
 namespace thb {

@@ -269,6 +269,7 @@ __device__ __forceinline__ float2 gather_lin(const float2* __restrict__ vol, int
     return make_float2(re, conj ? -im : im);
 }
 
+#define SIGMA_DUP (1 << 30)
 struct SigmaArgs {
     const float2* vols[THB_MAX_SLOTS];
     int vdim, pitch, N, rSig, nGroup;
@@ -294,8 +295,10 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
     const float invN = 1.0f;   // placeholder to keep the divisions below explicit
     (void)invN;
     for (int i = tid; i < A.PE; i += blockDim.x) {
-        const int u = A.ringE[i];
-        if (u < 0 || u >= rS) continue;
+        int u = A.ringE[i];
+        if (u < 0) continue;
+        const float wgt = (u & SIGMA_DUP) ? 2.0f : 1.0f;
+        u &= ~SIGMA_DUP;
         const int4 c = A.pixE[i];
         float x, y, z;
         slice_coord(rot, (double)c.x, (double)c.y, x, y, z);
@@ -308,13 +311,15 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
         const float mx = (p.x * cs + p.y * sn) * cf, my = (p.y * cs - p.x * sn) * cf;
         const float2 d = A.datE[(size_t)img * A.PE + i];
         const float rx = d.x - mx, ry = d.y - my;
-        atomicAdd(&sRing[u], rx * rx + ry * ry);
-        atomicAdd(&sRing[rS + u], mx * mx + my * my);
-        atomicAdd(&sRing[2 * rS + u], d.x * d.x + d.y * d.y);
+        atomicAdd(&sRing[u], wgt * (rx * rx + ry * ry));
+        atomicAdd(&sRing[rS + u], wgt * (mx * mx + my * my));
+        atomicAdd(&sRing[2 * rS + u], wgt * (d.x * d.x + d.y * d.y));
     }
     for (int i = tid; i < A.PM; i += blockDim.x) {
-        const int u = A.ringM[i];
-        if (u < 0 || u >= rS) continue;
+        int u = A.ringM[i];
+        if (u < 0) continue;
+        const float wgt = (u & SIGMA_DUP) ? 2.0f : 1.0f;
+        u &= ~SIGMA_DUP;
         const int4 c = A.pixM[i];
         float x, y, z;
         slice_coord(rot, (double)c.x, (double)c.y, x, y, z);
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
         const float mx = (p.x * cs + p.y * sn) * cf, my = (p.y * cs - p.x * sn) * cf;
         const float2 d = A.datM[(size_t)img * A.PM + i];
         const float rx = d.x - mx, ry = d.y - my;
-        atomicAdd(&sRing[3 * rS + u], rx * rx + ry * ry);
+        atomicAdd(&sRing[3 * rS + u], wgt * (rx * rx + ry * ry));
     }
     __syncthreads();
     const int g = A.group ? A.group[l] : 0;
@@ -668,17 +673,21 @@ int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double
     THB_CUDA(ctx, cudaMemcpy(permE.data(), ctx->permE, sizeof(int) * PE, cudaMemcpyDeviceToHost));
     THB_CUDA(ctx, cudaMemcpy(permM.data(), ctx->permM, sizeof(int) * PM, cudaMemcpyDeviceToHost));
     THB_CUDA(ctx, cudaMemcpy(pixM.data(), ctx->pixM, sizeof(int4) * PM, cudaMemcpyDeviceToHost));
+    // powerSpectrum() walks the whole half plane, the packed lists leave out (i = 0, j < 0) (allocPreCalIdx,
+    // src/Optimiser.cpp:8015): the mirror pixel (0, j > 0) has the same modulus for the Hermitian images on this path and
+    // is counted twice (SIGMA_DUP flag)
+    std::vector<int4> pixE(PE);
+    THB_CUDA(ctx, cudaMemcpy(pixE.data(), ctx->pixE, sizeof(int4) * PE, cudaMemcpyDeviceToHost));
     std::vector<float> cntE(rSig, 0.f), cntM(rSig, 0.f);
-    for (int i = 0; i < PE; ++i) {
-        ringE[i] = iSigE[permE[i]];
-        if (ringE[i] >= 0 && ringE[i] < rSig) cntE[ringE[i]] += 1.f;
-    }
-    for (int i = 0; i < PM; ++i) {
-        const long long a = pixM[i].z, b = pixM[i].w;      // unpadded iCol, iRow
-        const int u = iSigM[permM[i]];
-        ringM[i] = (a * a + b * b < (long long)rSig * rSig && u < rSig) ? u : -1;
-        if (ringM[i] >= 0) cntM[ringM[i]] += 1.f;
-    }
+    auto ring_of = [&](const int4& c, int u, std::vector<float>& cnt) {
+        const long long a = c.z, b = c.w;                  // unpadded iCol, iRow
+        if (!(a * a + b * b < (long long)rSig * rSig && u >= 0 && u < rSig)) return -1;
+        const bool dup = a == 0 && b > 0;
+        cnt[u] += dup ? 2.f : 1.f;
+        return dup ? (u | SIGMA_DUP) : u;
+    };
+    for (int i = 0; i < PE; ++i) ringE[i] = ring_of(pixE[i], iSigE[permE[i]], cntE);
+    for (int i = 0; i < PM; ++i) ringM[i] = ring_of(pixM[i], iSigM[permM[i]], cntM);
     (void)pfM;
     const size_t nOut = (size_t)nGroup * (rSig + 1);
     unsigned char* buf = (unsigned char*)scratch(ctx, 0, sizeof(double) * (3 * nOut + 8 * (size_t)nImg) + sizeof(int) * ((size_t)PE + PM + 2 * (size_t)nImg) + sizeof(float) * 2 * (size_t)rSig + 64);
