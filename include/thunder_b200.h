@@ -111,6 +111,18 @@ int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
 
 /* Projector volume for slot (class x half-set), half-complex (vdim/2+1) x vdim x vdim complex64. */
 int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim);
+/* MODE_2D (2D classification, demo_2D.json): the references are padded class-average FTs [vdim][vdim/2+1] (thb_set_volume with
+ * the same arguments; slot = class), the rotations of every entry point are in-plane and passed as [..][2] = (cos, sin) - the
+ * first two components of the reference's Particle rotation, rotate2D(dmat22&, dvec2) src/Geometry/Euler.cpp:125-131, and the
+ * layout ExpectGlobal2D / InsertI2D receive (gpu/interface/Interface.h:176-198, 239-264) - the accumulators are images
+ * (thb_reco_download returns F, T as [vdim][vdim/2+1], O as (ox, oy, 0)), thb_expect_scan compares EVERY image with class
+ * `slot`, and thb_insert_classes scatters each draw into the accumulator of its own class.  Same kernels as MODE_3D:
+ * bilinear gather / scatter = the trilinear cell of a two-plane volume at z = 0 (Projector::project src/Projector.cpp:337-354,
+ * Image::getByInterpolationFT src/Image/Image.cpp:345-368, Reconstructor::insertP src/Reconstructor.cpp:708-780).  The device
+ * particle filter, thb_reconstruct and thb_set_projectee are MODE_3D only.  Switching the mode drops volumes and accumulators. */
+enum { THB_MODE_3D = 0, THB_MODE_2D = 1 };
+int thb_set_mode(thb_ctx* ctx, int mode);
+int thb_get_mode(const thb_ctx* ctx);
 int thb_get_volume(thb_ctx* ctx, int slot, float* volFT);      /* round trip of the device layout */
 
 /* Resident packed stack, image-major [nImg][nPxl].  sigRcp may be NULL for THB_STACK_INSERT.
@@ -176,6 +188,9 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
                const double* nr, const double* nt);
 /* F[(vdimPad/2+1)*vdimPad^2][2], T[...] real part, O[3], counter.  normalise != 0 applies
  * sf = 1/T[0] to T and F (RECONSTRUCTOR_NORMALISE_T_F). Any pointer may be NULL. */
+/* MODE_2D: the same with the class of every draw, nc[nImg][mReco] (InsertI2D's nC): the accumulator slot of the draw */
+int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
+                       const int* nc, const double* nr, const double* nt);
 int thb_reco_download(thb_ctx* ctx, int slot, float* F, float* T, double* O, int* counter, int normalise);
 
 /* ---------------------------------------------------------------- a15: half-map allreduce */

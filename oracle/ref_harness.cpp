@@ -436,6 +436,74 @@ void ref_sigma_accumulate(void* projH, int nImg, int N, int rSig, const float* i
     }
 }
 
+
+// ---------------------------------------------------------------- MODE_2D (2D classification, demo_2D.json)
+// Projector in MODE_2D holding an already padded half-complex class average [pfN][pfN/2+1] verbatim
+void* ref_projector2d_create(int pf, const float* imgFT, int pfN)
+{
+    RefProjector* p = new RefProjector();
+    p->proj.setMode(MODE_2D);
+    p->proj.setInterp(LINEAR_INTERP);
+    p->proj.setPf(pf);
+    p->proj._projectee2D.alloc(pfN, pfN, FT_SPACE);
+    memcpy(&p->proj._projectee2D[0], imgFT, p->proj._projectee2D.sizeFT() * sizeof(Complex));
+    p->proj._maxRadius = pfN / pf / 2 - 1;
+    return p;
+}
+
+// rotate2D(dmat22&, dvec2) (src/Geometry/Euler.cpp:125-131) + Projector::project(Complex*, const dmat22&, iCol, iRow, nPxl,
+// nThread) (src/Projector.cpp:337-354)
+void ref_projector2d_project(void* h, float* dst, const double* cs, const int* iCol, const int* iRow, int nPxl)
+{
+    dmat22 rot;
+    rotate2D(rot, dvec2(cs[0], cs[1]));
+    ((RefProjector*)h)->proj.project((Complex*)dst, rot, iCol, iRow, nPxl, 1);
+}
+
+void* ref_reco2d_create(int size, int N, int pf, int nThread)
+{
+    RefReco* r = new RefReco();
+    r->reco.setMPIEnv(3, 1, MPI_COMM_SELF, MPI_COMM_SELF);
+    r->reco.init(MODE_2D, size, N, pf, NULL, 1.9, 15);
+    r->reco.allocSpace(nThread);
+    return r;
+}
+
+int ref_reco2d_pad_size(void* h) { return (int)((RefReco*)h)->reco._F2D.nRowFT(); }
+
+// the M-step body of Optimiser::reconstructRef in MODE_2D (src/Optimiser.cpp:7072-7148) for one draw of one image:
+// translate(-(t - offset)) of the unmasked packed image, Reconstructor::insertP(src, ctf, dmat22, w, NULL)
+// (src/Reconstructor.cpp:708-780), insertDir(-rot2D * (t - offset))
+void ref_reco2d_insert_draw(void* h, const float* datP, const float* ctfP, int N, const int* iCol, const int* iRow, int nPxl,
+                            const double* cs, const double* tran, const double* off, float w)
+{
+    RefReco* r = (RefReco*)h;
+    std::vector<Complex> tmp(nPxl);
+    dvec2 t(tran[0] - (off ? off[0] : 0.0), tran[1] - (off ? off[1] : 0.0));
+    translate(tmp.data(), (const Complex*)datP, -t(0), -t(1), N, N, iCol, iRow, nPxl, 1);
+    dmat22 rot;
+    rotate2D(rot, dvec2(cs[0], cs[1]));
+    r->reco.insertP(tmp.data(), ctfP, rot, w, NULL);
+    dvec2 dir = -rot * t;
+    r->reco.insertDir(dir);
+}
+
+void ref_reco2d_get(void* h, float* F, float* T, double* O3, int* counter)
+{
+    RefReco* r = (RefReco*)h;
+    size_t n = r->reco._F2D.sizeFT();
+    if (F) memcpy(F, &r->reco._F2D[0], n * sizeof(Complex));
+    if (T)
+        for (size_t i = 0; i < n; i++) T[i] = REAL(r->reco._T2D[i]);
+    if (O3)
+    {
+        O3[0] = r->reco._ox;
+        O3[1] = r->reco._oy;
+        O3[2] = r->reco._oz;
+    }
+    if (counter) *counter = r->reco._counter;
+}
+
 // ---------------------------------------------------------------- Particle (reference class, as is)
 void* ref_particle_create(int nC, int nR, int nT, int nD, double transS, double transQ)
 {

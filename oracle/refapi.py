@@ -59,6 +59,15 @@ def lib():
         L.ref_reco_create.argtypes = [_i, _i, _i, _i]
         L.ref_reco_destroy.argtypes = [_p]
         L.ref_projector_project_image.argtypes = [_p, _i, _p, _p, _p]
+        L.ref_projector2d_create.restype = _p
+        L.ref_projector2d_create.argtypes = [_i, _p, _i]
+        L.ref_projector2d_project.argtypes = [_p, _p, _p, _p, _p, _i]
+        L.ref_reco2d_create.restype = _p
+        L.ref_reco2d_create.argtypes = [_i, _i, _i, _i]
+        L.ref_reco2d_pad_size.restype = _i
+        L.ref_reco2d_pad_size.argtypes = [_p]
+        L.ref_reco2d_insert_draw.argtypes = [_p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _f]
+        L.ref_reco2d_get.argtypes = [_p, _p, _p, _p, _p]
         L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
         L.ref_sigma_accumulate.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p, _p, _p]
         L.ref_reco_set.argtypes = [_p, _p, _p]
@@ -344,3 +353,57 @@ def expectation_local(pars, proj, datP, ctfP, sigRcpP, iCol, iRow, N, mLR, mLT, 
                                 mLT, pfL, pfS, minPhase, maxPhase, noDecreaseLimit, decreaseFactor, fixedPhases, simd,
                                 nThread, _ptr(nPhase), _ptr(dvp))
     return nPhase, dvp
+
+
+# ---------------------------------------------------------------------------------------------- MODE_2D
+class Projector2D:
+    """reference Projector in MODE_2D around a padded class average [pfN][pfN/2+1]"""
+
+    def __init__(self, pf, imgFT):
+        v = np.ascontiguousarray(imgFT, np.complex64)
+        self.h = lib().ref_projector2d_create(pf, _ptr(v), v.shape[0])
+
+    def close(self):
+        if self.h:
+            lib().ref_projector_destroy(self.h)
+            self.h = None
+
+    def project(self, cs, iCol, iRow):
+        out = np.empty(len(iCol), np.complex64)
+        cs = np.ascontiguousarray(cs, np.float64)
+        iCol = np.ascontiguousarray(iCol, np.int32); iRow = np.ascontiguousarray(iRow, np.int32)
+        lib().ref_projector2d_project(self.h, _ptr(out), _ptr(cs), _ptr(iCol), _ptr(iRow), len(iCol))
+        return out
+
+
+class Reconstructor2D:
+    def __init__(self, size, N, pf=2):
+        self.h = lib().ref_reco2d_create(size, N, pf, 1)
+        self.N = N
+
+    def close(self):
+        if self.h:
+            lib().ref_reco_destroy(self.h)
+            self.h = None
+
+    def pad_size(self):
+        return lib().ref_reco2d_pad_size(self.h)
+
+    def set_precal(self, iColPad, iRowPad, iPxl, iSig):
+        self._keep = [np.ascontiguousarray(a, np.int32) for a in (iColPad, iRowPad, iPxl, iSig)]
+        lib().ref_reco_set_precal(self.h, len(self._keep[0]), *[_ptr(a) for a in self._keep])
+
+    def insert_draw(self, dat, ctf, iCol, iRow, cs, tran, off, w):
+        dat = np.ascontiguousarray(dat, np.complex64); ctf = np.ascontiguousarray(ctf, np.float32)
+        iCol = np.ascontiguousarray(iCol, np.int32); iRow = np.ascontiguousarray(iRow, np.int32)
+        cs = np.ascontiguousarray(cs, np.float64); tran = np.ascontiguousarray(tran, np.float64)
+        off = np.ascontiguousarray(off, np.float64) if off is not None else None
+        lib().ref_reco2d_insert_draw(self.h, _ptr(dat), _ptr(ctf), self.N, _ptr(iCol), _ptr(iRow), len(iCol), _ptr(cs), _ptr(tran),
+                                     _ptr(off) if off is not None else None, float(w))
+
+    def get(self):
+        m = self.pad_size()
+        F = np.empty((m, m // 2 + 1), np.complex64); T = np.empty((m, m // 2 + 1), np.float32)
+        O = np.zeros(3); cnt = np.zeros(1, np.int32)
+        lib().ref_reco2d_get(self.h, _ptr(F), _ptr(T), _ptr(O), _ptr(cnt))
+        return dict(F=F, T=T, O=O, counter=int(cnt[0]))

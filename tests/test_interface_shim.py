@@ -18,7 +18,8 @@ from thunder_b200 import synth
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "thunder_b200" / "lib" / "libthb_interface.so"
 REF_HDR = Path(os.environ.get("THB_REFERENCE", "/root/reference")) / "gpu" / "interface" / "Interface.h"
-MIRRORED = ["getAviDevice", "ExpectPreidx", "ExpectFreeIdx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "InsertFT"]
+MIRRORED = ["getAviDevice", "ExpectPreidx", "ExpectFreeIdx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "InsertFT",
+            "ExpectGlobal2D", "InsertI2D"]
 _p, _i = C.c_void_p, C.c_int
 
 
@@ -47,8 +48,9 @@ def test_argument_order_matches_reference_header():
     thunder_b200/host/Interface.h documents (Volume& -> pointer + vdim, MPI_Comm& dropped)"""
     ref = REF_HDR.read_text()
     ours = (ROOT / "thunder_b200" / "host" / "Interface.h").read_text()
-    for name in ("ExpectPreidx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D"):
+    for name in ("ExpectPreidx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "ExpectGlobal2D"):
         assert _params(ours, name) == _params(ref, name), name
+    assert _params(ours, "InsertI2D") == [a for a in _params(ref, "InsertI2D") if a not in ("hemi", "slav")]
     want = [a for a in _params(ref, "InsertFT") if a not in ("hemi", "slav")]
     got = [a for a in _params(ours, "InsertFT") if a != "vdim"]
     assert got == want
@@ -140,3 +142,61 @@ def test_insertft_through_the_shim_accumulates_into_the_callers_volumes(shim):
     assert rel((T3D - T0).real, want["T"].ravel()) <= 1e-6
     assert np.allclose(O3D - [1.0, 2.0, 3.0], want["O"], rtol=1e-10, atol=1e-10)
     assert counter[0] == 7 + nImg * mReco
+
+
+@pytest.mark.gpu
+def test_2d_classification_through_the_shims(shim):
+    """ExpectGlobal2D / InsertI2D (MODE_2D): every image against every class with one shared baseline; draws scattered
+    into the accumulator of their class and ADDED to the caller's arrays.  Checked against oracle/port2d.py, itself pinned to
+    the reference's MODE_2D Projector / Reconstructor (tests/test_mode2d.py)."""
+    from oracle import port2d
+    from tests.test_mode2d import _setup, _unit
+    s = _setup(N=32, pf=2, k=3, nImg=5, seed=11, rE=14.0, rM=15.0)
+    N, pf, nK, nImg, rng = s["N"], s["pf"], s["k"], s["nImg"], s["rng"]
+    iCol, iRow, P = s["pixE"]["iCol"], s["pixE"]["iRow"], s["PE"]
+    vdim = N * pf
+    vol = np.ascontiguousarray(np.stack(s["refs"]))
+    nR, nT = 12, 4
+    rot = np.ascontiguousarray(_unit(np.linspace(-np.pi, np.pi, nR, endpoint=False))); trans = rng.normal(scale=1.5, size=(nT, 2))
+    pR = rng.uniform(0.5, 1.5, nR); pT = rng.uniform(0.5, 1.5, nT)
+    wC = np.zeros((nImg, nK), np.float32); wR = np.zeros((nImg, nK, nR), np.float32); wT = np.zeros((nImg, nK, nT), np.float32)
+    shim.thbi_ExpectGlobal2D(_ptr(vol), _ptr(s["datE"]), _ptr(s["ctfE"]), _ptr(s["sigE"]), _ptr(trans), _ptr(wC), _ptr(wR), _ptr(wT), _ptr(pR),
+                             _ptr(pT), _ptr(rot), _ptr(iCol), _ptr(iRow), nK, nR, nT, pf, N, vdim, P, nImg)
+    for l in range(nImg):
+        L = np.empty((nK, nR, nT))
+        for k in range(nK):
+            for r in range(nR):
+                p = port2d.project2d(s["refs"][k], pf, rot[r], iCol, iRow)
+                for t in range(nT):
+                    d = s["datE"][l].astype(np.complex128) - s["ctfE"][l] * port2d.translate(p, trans[t, 0], trans[t, 1], N, iCol, iRow).astype(np.complex128)
+                    L[k, r, t] = np.sum((d.real ** 2 + d.imag ** 2) * s["sigE"][l].astype(np.float64))
+        e = np.exp(L - L.max())
+        want_R = e @ pT; want_T = np.einsum("krt,r->kt", e, pR); want_C = np.einsum("krt,r,t->k", e, pR, pT)
+        big = want_R > 1e-4 * want_R.max()
+        assert np.allclose(wR[l][big], want_R[big], rtol=5e-3)
+        bigT = want_T > 1e-4 * want_T.max()
+        assert np.allclose(wT[l][bigT], want_T[bigT], rtol=5e-3)
+        assert np.allclose(wC[l], want_C, rtol=5e-3, atol=1e-4 * want_C.max())
+    # ---- M
+    pixM, PM = s["pixM"], s["PM"]
+    mReco = 4
+    nr = np.ascontiguousarray(_unit(rng.uniform(-np.pi, np.pi, (nImg, mReco)))); nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    nc = rng.integers(0, nK, (nImg, mReco)).astype(np.int32)
+    w = np.full(nImg, 1.0 / mReco, np.float32); offS = rng.normal(scale=0.5, size=(nImg, 2))
+    n2 = vdim * (vdim // 2 + 1)
+    F0 = (rng.normal(size=(nK, n2)) + 1j * rng.normal(size=(nK, n2))).astype(np.complex64); T0 = rng.uniform(0, 1, (nK, n2)).astype(np.float32)
+    F2D, T2D = F0.copy(), T0.copy()
+    O2D = np.arange(2.0 * nK); counter = np.full(nK, 3, np.int32)
+    shim.thbi_InsertI2D(_ptr(F2D), _ptr(T2D), _ptr(O2D), _ptr(counter), _ptr(s["datM"]), _ptr(s["ctfM"]), _ptr(w), _ptr(offS), _ptr(nc), _ptr(nr),
+                        _ptr(nt), _ptr(pixM["iColPad"]), _ptr(pixM["iRowPad"]), nK, pf, PM, mReco, N, vdim, nImg)
+    recos = [port2d.Reco2D(vdim) for _ in range(nK)]
+    for l in range(nImg):
+        for m in range(mReco):
+            recos[nc[l, m]].insert_draw(s["datM"][l], s["ctfM"][l], N, pixM["iCol"], pixM["iRow"], pixM["iColPad"], pixM["iRowPad"], nr[l, m], nt[l, m],
+                                        offS[l], w[l])
+    for k in range(nK):
+        assert counter[k] == 3 + recos[k].counter
+        assert np.allclose(O2D[2 * k:2 * k + 2] - [2.0 * k, 2.0 * k + 1], recos[k].O[:2], atol=1e-9)
+        if recos[k].counter:
+            assert np.abs((F2D[k] - F0[k]) - recos[k].F.ravel()).max() <= 3e-5 * np.abs(recos[k].F).max() + 1e-6
+            assert np.abs((T2D[k] - T0[k]) - recos[k].T.ravel()).max() <= 3e-5 * np.abs(recos[k].T).max() + 1e-6

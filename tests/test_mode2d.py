@@ -1,0 +1,223 @@
+"""MODE_2D (2D classification, BASELINE config 5): the in-plane twins of the hot path.
+
+CPU (`-m "not gpu"`): oracle/port2d.py (numpy restatement) pinned to the reference's own Projector / Reconstructor in MODE_2D.
+GPU (`-m gpu`): thb_project / thb_expect_local / thb_expect_scan / thb_insert(_classes) in MODE_2D against the reference.
+"""
+import numpy as np
+import pytest
+
+from thunder_b200 import capi, synth
+
+
+def _ref():
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    return refapi
+
+
+def _class_averages(N, pf, k, seed):
+    """k padded class-average FTs [pf N][pf N / 2 + 1]: random blobs, zero outside a disc (like a masked average)"""
+    rng = np.random.default_rng(seed)
+    n = N * pf
+    yy, xx = np.mgrid[-n // 2:n // 2, -n // 2:n // 2]
+    out = []
+    for _ in range(k):
+        img = np.zeros((n, n))
+        for _b in range(7):
+            cx, cy = rng.uniform(-0.25 * N, 0.25 * N, 2); s = rng.uniform(1.5, 5.0)
+            img += rng.uniform(0.5, 1.5) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+        out.append(np.fft.rfft2(np.fft.ifftshift(img)).astype(np.complex64))
+    return out
+
+
+def _unit(phi):
+    return np.stack([np.cos(phi), np.sin(phi)], axis=-1)
+
+
+def _setup(N=64, pf=2, k=3, nImg=12, seed=5, rE=28.0, rM=30.0):
+    rng = np.random.default_rng(seed)
+    refs = _class_averages(N, pf, k, seed)
+    pixE = capi.pixel_list(N, pf, rE, 1.0)
+    pixM = capi.pixel_list(N, pf, rM, 0.0)
+    PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
+    datE = (rng.normal(size=(nImg, PE)) + 1j * rng.normal(size=(nImg, PE))).astype(np.complex64) * np.float32(30)
+    ctfE = rng.uniform(-1, 1, (nImg, PE)).astype(np.float32)
+    sigE = (-0.5 / rng.uniform(50, 200, (nImg, PE))).astype(np.float32)
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    cls = rng.integers(0, k, nImg).astype(np.int32)
+    return dict(N=N, pf=pf, k=k, nImg=nImg, rng=rng, refs=refs, pixE=pixE, pixM=pixM, PE=PE, PM=PM, datE=datE, ctfE=ctfE, sigE=sigE,
+                datM=datM, ctfM=ctfM, cls=cls)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: restatement == reference
+def test_port2d_project_matches_reference():
+    ref = _ref()
+    from oracle import port2d
+    s = _setup()
+    P = ref.Projector2D(s["pf"], s["refs"][0])
+    for phi in (0.0, 0.3, 1.7, 3.0, -2.2, np.pi / 2):
+        cs = _unit(phi)
+        want = P.project(cs, s["pixE"]["iCol"], s["pixE"]["iRow"])
+        got = port2d.project2d(s["refs"][0], s["pf"], cs, s["pixE"]["iCol"], s["pixE"]["iRow"])
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    P.close()
+
+
+def test_port2d_insert_matches_reference():
+    ref = _ref()
+    from oracle import port2d
+    s = _setup(nImg=4)
+    N, pf, pixM = s["N"], s["pf"], s["pixM"]
+    R = ref.Reconstructor2D(N, N, pf)
+    R.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+    m = R.pad_size()
+    assert m == N * pf
+    mine = port2d.Reco2D(m)
+    rng = s["rng"]
+    for l in range(s["nImg"]):
+        for _ in range(3):
+            cs = _unit(rng.uniform(-np.pi, np.pi)); t = rng.normal(size=2) * 2; off = rng.normal(size=2)
+            R.insert_draw(s["datM"][l], s["ctfM"][l], pixM["iCol"], pixM["iRow"], cs, t, off, 0.25)
+            mine.insert_draw(s["datM"][l], s["ctfM"][l], N, pixM["iCol"], pixM["iRow"], pixM["iColPad"], pixM["iRowPad"], cs, t, off, 0.25)
+    got = R.get()
+    assert got["counter"] == mine.counter == 12
+    assert np.allclose(got["O"], mine.O, rtol=1e-12, atol=1e-12)
+    assert np.abs(got["F"] - mine.F).max() <= 2e-5 * np.abs(mine.F).max()
+    assert np.abs(got["T"] - mine.T).max() <= 2e-5 * np.abs(mine.T).max()
+    R.close()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture()
+def ctx2d():
+    c = capi.Context(0)
+    c.set_mode(capi.MODE_2D)
+    yield c
+    c.close()
+
+
+def _load(c, s, slotOfImg=None):
+    c.set_expect_pixels(s["N"], s["pf"], s["pixE"]["iCol"], s["pixE"]["iRow"])
+    c.set_insert_pixels(s["N"], s["pf"], s["pixM"]["iColPad"], s["pixM"]["iRowPad"])
+    for k, r in enumerate(s["refs"]):
+        c.set_volume(k, r)
+    c.upload_stack(capi.STACK_EXPECT, s["datE"], s["ctfE"], s["sigE"], slotOfImg)
+    c.upload_stack(capi.STACK_INSERT, s["datM"], s["ctfM"], slotOfImg=slotOfImg)
+
+
+@pytest.mark.gpu
+def test_project2d_matches_reference(ctx2d):
+    ref = _ref()
+    s = _setup()
+    _load(ctx2d, s)
+    phis = np.array([0.0, 0.3, 1.7, 3.0, -2.2, np.pi / 2, 1e-9, -1e-9])
+    for k in range(s["k"]):
+        assert np.array_equal(ctx2d.get_volume(k), s["refs"][k])
+        got = ctx2d.project(k, _unit(phis))
+        P = ref.Projector2D(s["pf"], s["refs"][k])
+        for i, phi in enumerate(phis):
+            want = P.project(_unit(phi), s["pixE"]["iCol"], s["pixE"]["iRow"])
+            assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+        P.close()
+
+
+def _ref_logL(ref, s, P, l, cs, t):
+    """Optimiser::expectation's inner evaluation with the reference's functions: project, translate, logDataVSPrior"""
+    from oracle import port2d
+    p = P.project(cs, s["pixE"]["iCol"], s["pixE"]["iRow"])
+    p = port2d.translate(p, t[0], t[1], s["N"], s["pixE"]["iCol"], s["pixE"]["iRow"])
+    d = s["datE"][l].astype(np.complex128) - s["ctfE"][l].astype(np.float64) * p.astype(np.complex128)
+    return float(np.sum((d.real ** 2 + d.imag ** 2) * s["sigE"][l].astype(np.float64)))
+
+
+@pytest.mark.gpu
+def test_expect_local_2d_matches_reference(ctx2d):
+    ref = _ref()
+    s = _setup()
+    _load(ctx2d, s, s["cls"])
+    rng = s["rng"]
+    nImg, nR, nT = s["nImg"], 9, 5
+    cs = _unit(rng.uniform(-np.pi, np.pi, (nImg, nR))); t = rng.normal(size=(nImg, nT, 2)) * 1.5
+    wR = rng.uniform(0.5, 1.5, (nImg, nR)); wT = rng.uniform(0.5, 1.5, (nImg, nT))
+    out = ctx2d.expect_local(cs, t, wR, wT)
+    Ps = [ref.Projector2D(s["pf"], r) for r in s["refs"]]
+    for l in range(nImg):
+        want = np.array([[_ref_logL(ref, s, Ps[s["cls"][l]], l, cs[l, r], t[l, tt]) for tt in range(nT)] for r in range(nR)])
+        assert np.abs(out["logL"][l] - want).max() <= 2e-5 * np.abs(want).max() + 1e-4
+        e = np.exp(out["logL"][l].astype(np.float64) - out["base"][l])
+        assert np.allclose(out["uR"][l], e @ wT[l], rtol=1e-4)
+        assert np.allclose(out["uT"][l], wR[l] @ e, rtol=1e-4)
+    for P in Ps:
+        P.close()
+
+
+@pytest.mark.gpu
+def test_expect_scan_2d_every_image_against_every_class(ctx2d):
+    """the classification scan (src/Optimiser.cpp:756-914): shared in-plane rotations x translations, all images x all classes"""
+    ref = _ref()
+    s = _setup(nImg=7)
+    _load(ctx2d, s, s["cls"])
+    rng = s["rng"]
+    nR, nT = 20, 6
+    cs = _unit(np.linspace(-np.pi, np.pi, nR, endpoint=False)); t = rng.normal(size=(nT, 2)) * 2
+    pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
+    for k in range(s["k"]):
+        out = ctx2d.expect_scan(k, cs, t, pR, pT, want_logL=True)
+        P = ref.Projector2D(s["pf"], s["refs"][k])
+        for l in (0, 3, 6):
+            want = np.array([[_ref_logL(ref, s, P, l, cs[r], t[tt]) for tt in range(nT)] for r in range(nR)])
+            assert np.abs(out["logL"][l] - want).max() <= 2e-5 * np.abs(want).max() + 1e-4
+            assert out["base"][l] == out["logL"][l].max()
+        P.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_draw_classes", [False, True])
+def test_insert_2d_matches_reference(ctx2d, per_draw_classes):
+    ref = _ref()
+    s = _setup(nImg=6)
+    N, pf, pixM, k = s["N"], s["pf"], s["pixM"], s["k"]
+    _load(ctx2d, s, s["cls"])
+    for c in range(k):
+        ctx2d.reco_alloc(c, N * pf)
+    rng = s["rng"]
+    nImg, mReco = s["nImg"], 5
+    cs = _unit(rng.uniform(-np.pi, np.pi, (nImg, mReco)))
+    cs[:, 3] = cs[:, 1]                                          # duplicate rotations: the merged-draw path
+    t = rng.normal(size=(nImg, mReco, 2)) * 2; off = rng.normal(size=(nImg, 2))
+    w = np.full(nImg, 1.0 / mReco, np.float32)
+    nc = rng.integers(0, k, (nImg, mReco)).astype(np.int32) if per_draw_classes else np.repeat(s["cls"][:, None], mReco, 1)
+    if per_draw_classes:
+        ctx2d.insert_classes(w, nc, cs, t, offS=off)
+    else:
+        ctx2d.insert(w, cs, t, offS=off)
+    Rs = []
+    for c in range(k):
+        R = ref.Reconstructor2D(N, N, pf)
+        R.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+        Rs.append(R)
+    for l in range(nImg):
+        for m in range(mReco):
+            Rs[nc[l, m]].insert_draw(s["datM"][l], s["ctfM"][l], pixM["iCol"], pixM["iRow"], cs[l, m], t[l, m], off[l], w[l])
+    for c in range(k):
+        want = Rs[c].get(); got = ctx2d.reco_download(c)
+        assert got["F"].shape == (N * pf, N * pf // 2 + 1)
+        assert got["counter"] == want["counter"]
+        assert np.allclose(got["O"], want["O"], rtol=1e-10, atol=1e-10)
+        if want["counter"]:
+            assert np.abs(got["F"] - want["F"]).max() <= 2e-5 * np.abs(want["F"]).max()
+            assert np.abs(got["T"] - want["T"]).max() <= 2e-5 * np.abs(want["T"]).max()
+        Rs[c].close()
+
+
+@pytest.mark.gpu
+def test_mode_switch_and_guards(ctx2d):
+    s = _setup(nImg=2)
+    _load(ctx2d, s)
+    with pytest.raises(capi.ThbError):
+        ctx2d.set_projectee(0, None, s["N"], s["pf"])
+    ctx2d.set_mode(capi.MODE_3D)                                  # drops the 2D references
+    with pytest.raises(capi.ThbError):
+        ctx2d.project(0, np.array([[1.0, 0, 0, 0]]))

@@ -16,6 +16,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libthunder_b200.so"
 
 UNIQUE_ID_BYTES = 128
+MODE_3D, MODE_2D = 0, 1
 STACK_EXPECT, STACK_INSERT = 0, 1
 KF_EXPECT, KF_INSERT, KF_PF, KF_PACK, KF_COMM = range(5)
 PF_PERTURB_R, PF_PERTURB_T, PF_SET_U_KEEP_PEAK, PF_RANK1ST, PF_CALVARI, PF_RESAMPLE, PF_BALANCE_R, PF_BALANCE_T = range(1, 9)
@@ -67,6 +68,9 @@ def _sig(lib):
     f = lib.thb_upload_stack_at; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
     f = lib.thb_upload_stack_at_async; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
     f = lib.thb_upload_wait; f.restype = _i; f.argtypes = [_p]
+    f = lib.thb_set_mode; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_get_mode; f.restype = _i; f.argtypes = [_p]
+    f = lib.thb_insert_classes; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
     f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
     f = lib.thb_reco_upload; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
@@ -214,17 +218,23 @@ class Context:
         self._chk(self.lib.thb_set_insert_pixels(self.h, N, pf, len(a), _ptr(a), _ptr(b)))
         self.nPxlM = len(a)
 
+    def set_mode(self, mode):
+        """MODE_3D (default) / MODE_2D: 2D classification - image references, in-plane rotations passed as (cos, sin)"""
+        self._chk(self.lib.thb_set_mode(self.h, int(mode)))
+        self.mode2D = int(mode) == MODE_2D
+        self.vdim, self.accdim = {}, {}
+
     def set_volume(self, slot, volFT):
-        """volFT: complex64 [vdim][vdim][vdim/2+1] (z, y, x) half-complex."""
+        """volFT: complex64 [vdim][vdim][vdim/2+1] (z, y, x) half-complex; MODE_2D: [vdim][vdim/2+1]"""
         v = np.ascontiguousarray(volFT, dtype=np.complex64)
         vdim = v.shape[0]
-        assert v.shape == (vdim, vdim, vdim // 2 + 1), v.shape
+        assert v.shape == ((vdim, vdim // 2 + 1) if getattr(self, "mode2D", False) else (vdim, vdim, vdim // 2 + 1)), v.shape
         self._chk(self.lib.thb_set_volume(self.h, slot, _ptr(v), vdim))
         self.vdim[slot] = vdim
 
     def get_volume(self, slot):
         vdim = self.vdim[slot]
-        out = np.empty((vdim, vdim, vdim // 2 + 1), np.complex64)
+        out = np.empty((vdim, vdim // 2 + 1) if getattr(self, "mode2D", False) else (vdim, vdim, vdim // 2 + 1), np.complex64)
         self._chk(self.lib.thb_get_volume(self.h, slot, _ptr(out)))
         return out
 
@@ -380,10 +390,20 @@ class Context:
         imgIdx = _arr(imgIdx, np.int32, (nImg,))
         self._chk(self.lib.thb_insert(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt)))
 
+    def insert_classes(self, w, nc, nr, nt, offS=None, imgIdx=None):
+        """MODE_2D: nc[nImg][mReco] = class (accumulator slot) of every draw, nr[nImg][mReco][2] = (cos, sin)"""
+        nr = _arr(nr, np.float64)
+        nImg, mReco, _ = nr.shape
+        nt = _arr(nt, np.float64, (nImg, mReco, 2)); nc = _arr(nc, np.int32, (nImg, mReco))
+        w = _arr(w, np.float32, (nImg,))
+        offS = _arr(offS, np.float64, (nImg, 2))
+        imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        self._chk(self.lib.thb_insert_classes(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nc), _ptr(nr), _ptr(nt)))
+
     def reco_download(self, slot, normalise=False, want_F=True, want_T=True, out=None):
         """out = (F, T): preallocated (e.g. page-locked) destination arrays"""
         m = self.accdim[slot]
-        shape = (m, m, m // 2 + 1)
+        shape = (m, m // 2 + 1) if getattr(self, "mode2D", False) else (m, m, m // 2 + 1)
         if out is not None:
             F, T = out
             assert F.shape == shape and F.dtype == np.complex64 and F.flags.c_contiguous

@@ -191,11 +191,14 @@ static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
     return THB_OK;
 }
 
-int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a)
+int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
 {
+    ExpectArgs a = a_in;
     if (a.nAct <= 0) return THB_OK;
-    if (ctx->expectImpl == 3) return launch_expect_v3(ctx, a);
-    if (ctx->expectImpl == 2) return launch_expect_v2(ctx, a);
+    a.mode2D = ctx->mode2D;
+    if (!ctx->mode2D) a.slotAll = -1;
+    if (ctx->expectImpl == 3 && !ctx->mode2D) return launch_expect_v3(ctx, a);
+    if (ctx->expectImpl == 2 && !ctx->mode2D) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)
         return set_error(ctx, THB_E_ARG, "expect_local: nR*nT = %d too large for the local-search kernel", a.nR * a.nT);
@@ -592,7 +595,9 @@ int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     Volume3& v = ctx->vols[slot];
     const int pitch = vol_pitch(vdim);
-    const size_t rows = (size_t)vdim * vdim;
+    // MODE_2D: the reference image is plane 0 of a two-plane volume whose plane 1 stays zero (thb_math.cuh, make_rot2)
+    const size_t rows = ctx->mode2D ? (size_t)vdim : (size_t)vdim * vdim;
+    const size_t rowsAlloc = ctx->mode2D ? 2 * (size_t)vdim : rows;
     if (v.quad) {   // the quad copy belongs to the previous contents
         THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(v.quad);
@@ -602,8 +607,8 @@ int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim)
         cudaFree(v.d);
         v.d = nullptr;
         v.vdim = 0;
-        THB_CUDA(ctx, cudaMalloc(&v.d, rows * pitch * sizeof(float2)));
-        THB_CUDA(ctx, cudaMemsetAsync(v.d, 0, rows * pitch * sizeof(float2), ctx->stream));
+        THB_CUDA(ctx, cudaMalloc(&v.d, rowsAlloc * pitch * sizeof(float2)));
+        THB_CUDA(ctx, cudaMemsetAsync(v.d, 0, rowsAlloc * pitch * sizeof(float2), ctx->stream));
         v.vdim = vdim;
         v.pitch = pitch;
     }
@@ -620,7 +625,8 @@ int thb_get_volume(thb_ctx* ctx, int slot, float* volFT)
         return set_error(ctx, THB_E_STATE, "get_volume: slot %d has no volume", slot);
     const Volume3& v = ctx->vols[slot];
     const size_t rowBytes = (size_t)(v.vdim / 2 + 1) * sizeof(float2);
-    THB_CUDA(ctx, cudaMemcpy2DAsync(volFT, rowBytes, v.d, (size_t)v.pitch * sizeof(float2), rowBytes, (size_t)v.vdim * v.vdim, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpy2DAsync(volFT, rowBytes, v.d, (size_t)v.pitch * sizeof(float2), rowBytes,
+                                    ctx->mode2D ? (size_t)v.vdim : (size_t)v.vdim * v.vdim, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -842,13 +848,14 @@ int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst
     if (nRot <= 0 || !quat || !dst) return set_error(ctx, THB_E_ARG, "project: bad arguments");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int P = ctx->nPxlE;
-    double* dq = (double*)scratch(ctx, 0, sizeof(double) * 4 * (size_t)nRot);
+    const int qc = ctx->mode2D ? 2 : 4;
+    double* dq = (double*)scratch(ctx, 0, sizeof(double) * qc * (size_t)nRot);
     float2* dd = (float2*)scratch(ctx, 1, sizeof(float2) * (size_t)nRot * P);
     if (!dq || !dd) return THB_E_CUDA;
-    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * 4 * (size_t)nRot, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * qc * (size_t)nRot, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((P + 255) / 256, nRot);
     span_begin(ctx, KF_EXPECT);
-    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->vols[slot].pitch, ctx->pixE, ctx->permE, P, dq, dd);
+    project_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->vols[slot].d, ctx->vols[slot].vdim, ctx->vols[slot].pitch, ctx->pixE, ctx->permE, P, dq, dd, ctx->mode2D);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -886,7 +893,8 @@ int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, 
     if (!imgIdx && nAct > ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "expect_local: nAct exceeds the stack");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    const size_t nq = (size_t)nAct * nR * 4, nt = (size_t)nAct * nT * 2, nwr = (size_t)nAct * nR, nwt = (size_t)nAct * nT;
+    const int qc = ctx->mode2D ? 2 : 4;      // MODE_2D: quat[nAct][nR][2] = (cos, sin)
+    const size_t nq = (size_t)nAct * nR * qc, nt = (size_t)nAct * nT * 2, nwr = (size_t)nAct * nR, nwt = (size_t)nAct * nT;
     double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + nt + nwr + nwt) + sizeof(int) * (size_t)nAct);
     const size_t nout = nwr + nwt + 2 * (size_t)nAct + (logL ? nwr * nT : 0);
     float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
@@ -906,8 +914,8 @@ int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, 
     a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
     a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
     a.nAct = nAct; a.imgIdx = imgIdx ? didx : nullptr; a.imgBase = 0; a.active = nullptr;
-    a.nR = nR; a.nT = nT;
-    a.quat = View3{dq, (long long)nR * 4, 4, 1};
+    a.nR = nR; a.nT = nT; a.slotAll = -1;
+    a.quat = View3{dq, (long long)nR * qc, qc, 1};
     a.tran = View3{dt, (long long)nT * 2, 2, 1};
     a.wR = View3{dwr, (long long)nR, 1, 0};
     a.wT = View3{dwt, (long long)nT, 1, 0};
@@ -941,7 +949,8 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
     std::vector<int> hslot(nImg);
     THB_CUDA(ctx, cudaMemcpy(hslot.data(), ctx->stackE.slot, sizeof(int) * nImg, cudaMemcpyDeviceToHost));
     std::vector<int> idx;
-    for (int i = 0; i < nImg; ++i) if (hslot[i] == slot) idx.push_back(i);
+    // MODE_2D (classification, src/Optimiser.cpp:756-914): every image is compared with every class reference
+    for (int i = 0; i < nImg; ++i) if (ctx->mode2D || hslot[i] == slot) idx.push_back(i);
     const int nAct = (int)idx.size();
     if (wC) memset(wC, 0, sizeof(float) * nImg);
     if (wR) memset(wR, 0, sizeof(float) * (size_t)nImg * nR);
@@ -955,6 +964,7 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
     std::vector<float> aR((size_t)nAct * nR, 0.f), aT((size_t)nAct * nT, 0.f), aC(nAct, 0.f), abase(nAct, -INFINITY);
     if (logL) clog.resize((size_t)nAct * rChunk * nT);
 
+    const int qc = ctx->mode2D ? 2 : 4;
     double* din = (double*)scratch(ctx, 0, sizeof(double) * ((size_t)rChunk * 4 + nT * 2 + rChunk + nT) + sizeof(int) * (size_t)nAct);
     if (!din) return THB_E_CUDA;
     for (int r0 = 0; r0 < nR; r0 += rChunk) {
@@ -964,7 +974,7 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
         const size_t nout = (size_t)nAct * nr + (size_t)nAct * nT + 2 * (size_t)nAct + (logL ? (size_t)nAct * nr * nT : 0);
         float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
         if (!dout) return THB_E_CUDA;
-        THB_CUDA(ctx, cudaMemcpyAsync(dq, quat + (size_t)r0 * 4, sizeof(double) * 4 * nr, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dq, quat + (size_t)r0 * qc, sizeof(double) * qc * nr, cudaMemcpyHostToDevice, ctx->stream));
         THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * 2 * nT, cudaMemcpyHostToDevice, ctx->stream));
         THB_CUDA(ctx, cudaMemcpyAsync(dwr, pR + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->stream));
         THB_CUDA(ctx, cudaMemcpyAsync(dwt, pT, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
@@ -975,7 +985,8 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
         a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
         a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
         a.nAct = nAct; a.imgIdx = didx; a.nR = nr; a.nT = nT;
-        a.quat = View3{dq, 0, 4, 1};
+        a.slotAll = ctx->mode2D ? slot : -1;
+        a.quat = View3{dq, 0, qc, 1};
         a.tran = View3{dt, 0, 2, 1};
         a.wR = View3{dwr, 0, 1, 0};
         a.wT = View3{dwt, 0, 1, 0};
@@ -1023,7 +1034,7 @@ int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad)
     if (a.vdim != vdimPad) {
         cudaFree(a.d);
         a = Accum();
-        const size_t n = vol_elems(vdimPad);
+        const size_t n = ctx->mode2D ? 2 * (size_t)(vdimPad / 2 + 1) * vdimPad : vol_elems(vdimPad);   // MODE_2D: two planes
         THB_CUDA(ctx, cudaMalloc(&a.d, n * sizeof(float4)));
         a.vdim = vdimPad;
         a.nVox = n;
@@ -1043,10 +1054,14 @@ int thb_reco_reset(thb_ctx* ctx, int slot)
     return THB_OK;
 }
 
-int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const double* nr,
-               const double* nt)
+static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,
+                       const double* nr, const double* nt)
 {
     if (!ctx) return THB_E_ARG;
+    if (nc && !ctx->mode2D) return set_error(ctx, THB_E_STATE, "insert_classes: per-draw classes are a MODE_2D feature (thb_set_mode)");
+    if (nc)
+        for (size_t i = 0; i < (size_t)nImg * mReco; ++i)
+            if (nc[i] < 0 || nc[i] >= THB_MAX_SLOTS || !ctx->accs[nc[i]].d) return set_error(ctx, THB_E_ARG, "insert_classes: nc[%zu] = %d has no accumulator", i, nc[i]);
     if (!ctx->pixM) return set_error(ctx, THB_E_STATE, "insert: M pixel list not set");
     if (!ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "insert: M stack not uploaded");
     if (nImg <= 0 || mReco <= 0 || !w || !nr || !nt) return set_error(ctx, THB_E_ARG, "insert: bad arguments");
@@ -1063,12 +1078,15 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
     if (!imgIdx && nImg > ctx->stackM.nImg) return set_error(ctx, THB_E_ARG, "insert: nImg exceeds the stack");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
 
-    const size_t nq = (size_t)nImg * mReco * 4, ntt = (size_t)nImg * mReco * 2;
-    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * (size_t)nImg);
+    const int qc = ctx->mode2D ? 2 : 4;      // MODE_2D: nr[nImg][mReco][2] = (cos, sin), as InsertI2D receives it
+    const size_t nq = (size_t)nImg * mReco * qc, ntt = (size_t)nImg * mReco * 2;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * ((size_t)nImg + (size_t)nImg * mReco));
     if (!din) return THB_E_CUDA;
     double* dq = din; double* dt = dq + nq; double* doff = dt + ntt;
     float* dw = (float*)(doff + 2 * (size_t)nImg);
     int* didx = (int*)(dw + nImg);
+    int* dnc = didx + nImg;
+    if (nc) THB_CUDA(ctx, cudaMemcpyAsync(dnc, nc, sizeof(int) * (size_t)nImg * mReco, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dq, nr, sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dt, nt, sizeof(double) * ntt, cudaMemcpyHostToDevice, ctx->stream));
     if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
@@ -1083,20 +1101,59 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
     a.pix = ctx->pixM; a.P = ctx->nPxlM; a.N = ctx->NM;
     a.nImg = nImg; a.imgIdx = imgIdx ? didx : nullptr; a.imgBase = 0;
     a.mReco = mReco; a.w = dw; a.wAll = 0.f; a.offS = offS ? doff : nullptr;
-    a.nr = View3{dq, (long long)mReco * 4, 4, 1};
+    a.nr = View3{dq, (long long)mReco * qc, qc, 1};
     a.nt = View3{dt, (long long)mReco * 2, 2, 1};
+    a.mode2D = ctx->mode2D;
+    a.drawC = nc ? dnc : nullptr;
     int rc = launch_insert(ctx, a);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
 
+int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const double* nr,
+               const double* nt)
+{
+    return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nullptr, nr, nt);
+}
+
+int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,
+                       const double* nr, const double* nt)
+{
+    if (ctx && !nc) return set_error(ctx, THB_E_ARG, "insert_classes: nc == NULL");
+    return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nc, nr, nt);
+}
+
+// MODE_3D (default) <-> MODE_2D.  The projector references and the accumulators have different shapes in the two modes, so
+// switching drops them; pixel lists and resident stacks are mode-independent and stay.
+int thb_set_mode(thb_ctx* ctx, int mode)
+{
+    if (!ctx) return THB_E_ARG;
+    if (mode != THB_MODE_3D && mode != THB_MODE_2D) return set_error(ctx, THB_E_ARG, "set_mode: mode %d", mode);
+    const int m2 = mode == THB_MODE_2D;
+    if (m2 == ctx->mode2D) return THB_OK;
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) {
+        cudaFree(ctx->vols[i].d);
+        cudaFree(ctx->vols[i].quad);
+        ctx->vols[i] = Volume3();
+        cudaFree(ctx->accs[i].d);
+        ctx->accs[i] = Accum();
+    }
+    ctx->mode2D = m2;
+    return THB_OK;
+}
+
+int thb_get_mode(const thb_ctx* ctx) { return ctx && ctx->mode2D ? THB_MODE_2D : THB_MODE_3D; }
+
 int thb_reco_download(thb_ctx* ctx, int slot, float* F, float* T, double* O, int* counter, int normalise)
 {
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reco_download: slot %d not allocated", slot);
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const Accum& a = ctx->accs[slot];
+    const Accum& a0 = ctx->accs[slot];
+    struct { float4* d; size_t nVox; } a = {a0.d, ctx->mode2D ? a0.nVox / 2 : a0.nVox};     // MODE_2D: plane 0 is the image
     if (F || T) {
         float2* dF = nullptr; float* dT = nullptr;
         if (F) { dF = (float2*)scratch(ctx, 2, a.nVox * sizeof(float2)); if (!dF) return THB_E_CUDA; }

@@ -85,6 +85,7 @@ struct thb_ctx {
     int* permM = nullptr;
     thb::TileDesc* tilesE = nullptr;   // 8x8-pixel tiles of the E pixel list (blocked order)
     int nTilesE = 0;
+    int mode2D = 0;              // thb_set_mode: references are images, rotations in-plane (MODE_2D of the reference)
     int insertImpl = 0;
     unsigned long long* dStats = nullptr;   // [8] staging counters of the E kernel (option "stats")
     int statsOn = 0;

@@ -51,11 +51,13 @@ __device__ __forceinline__ float2 gather_ft(const float2* __restrict__ vol, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void project_kernel(const float2* __restrict__ vol, int n, int pitch, const int4* __restrict__ pix,
                                const int* __restrict__ perm, int P, const double* __restrict__ quat,
-                               float2* __restrict__ dst)
+                               float2* __restrict__ dst, int mode2D)
 {
     const int r = blockIdx.y;
-    double q[4] = {quat[4 * r], quat[4 * r + 1], quat[4 * r + 2], quat[4 * r + 3]};
-    const Rot2 rot = quat_to_rot2(q);
+    double q[4] = {1.0, 0.0, 0.0, 0.0};
+    const int nc = mode2D ? 2 : 4;          // MODE_2D rotation arrays are [..][2] = (cos, sin)
+    for (int c = 0; c < nc; ++c) q[c] = quat[nc * r + c];
+    const Rot2 rot = make_rot2(q, mode2D);
     const int nColFT = pitch;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
         const int4 px = pix[i];
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(E_THREADS, 4) expect_local_kernel(const Expect
     const int p = blockIdx.x;
     if (A.active && !A.active[p]) return;
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
-    const int slot = A.slotOfImg ? A.slotOfImg[img] : 0;
+    const int slot = A.slotAll >= 0 ? A.slotAll : (A.slotOfImg ? A.slotOfImg[img] : 0);
     const float2* __restrict__ vol = A.vols.p[slot];
     const int n = A.vdim, nColFT = A.pitch;
     const int P = A.P;
@@ -132,8 +134,8 @@ __global__ void __launch_bounds__(E_THREADS, 4) expect_local_kernel(const Expect
         {
             double q[4] = {1.0, 0.0, 0.0, 0.0};
             if (rvalid)
-                for (int c = 0; c < 4; ++c) q[c] = A.quat.at(p, r, c);
-            rot = quat_to_rot2(q);
+                for (int c = 0; c < (A.mode2D ? 2 : 4); ++c) q[c] = A.quat.at(p, r, c);
+            rot = make_rot2(q, A.mode2D);
         }
         for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
             __syncthreads();
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
     __shared__ Rot2 sRot[M_MAXRECO];
     __shared__ float sRC[M_MAXRECO], sRR[M_MAXRECO];
     __shared__ double sQ[M_MAXRECO][4];
-    __shared__ unsigned short sRep[M_MAXRECO], sOrder[M_MAXRECO], sGrpEnd[M_MAXRECO];
+    __shared__ unsigned short sRep[M_MAXRECO], sOrder[M_MAXRECO], sGrpEnd[M_MAXRECO], sCls[M_MAXRECO];
     __shared__ double redd[M_THREADS / 32];
 
     const int l = blockIdx.x;
@@ -282,9 +284,16 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
             const int m = mbase + tid;
             const long long sr = A.drawR ? A.drawR[(size_t)l * A.mReco + m] : m;
             const long long st = A.drawT ? A.drawT[(size_t)l * A.mReco + m] : m;
-            double q[4];
-            for (int c = 0; c < 4; ++c) { q[c] = A.nr.at(l, sr, c); sQ[tid][c] = q[c]; }
-            const Rot2 rot = quat_to_rot2(q);
+            double q[4] = {1.0, 0.0, 0.0, 0.0};
+            for (int c = 0; c < (A.mode2D ? 2 : 4); ++c) q[c] = A.nr.at(l, sr, c);
+            // MODE_2D with several classes: the draw's class (InsertI2D's nC) picks the accumulator and keeps draws of
+            // different classes in different merge groups (the class rides in the unused third component of the key)
+            const int cls = A.drawC ? A.drawC[(size_t)l * A.mReco + m] : slot;
+            if (A.drawC) q[2] = (double)cls;
+            sCls[tid] = (unsigned short)cls;
+            for (int c = 0; c < 4; ++c) sQ[tid][c] = q[c];
+            if (A.drawC) q[2] = 0.0;
+            const Rot2 rot = make_rot2(q, A.mode2D);
             sRot[tid] = rot;
             const double tx = A.nt.at(l, st, 0) - ox, ty = A.nt.at(l, st, 1) - oy;
             // translate(dst, src, -(tran - offset)(0), -(tran - offset)(1), ...): RFLOAT arguments
@@ -295,7 +304,15 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
             dy = -(rot.c0[1] * tx + rot.c1[1] * ty);
             dz = -(rot.c0[2] * tx + rot.c1[2] * ty);
         }
-        if (blockIdx.y == 0) {
+        if (blockIdx.y == 0 && A.drawC) {
+            if (tid < mcnt) {
+                const int cls = sCls[tid];
+                atomicAdd(&A.acc.O[3 * cls + 0], dx);
+                atomicAdd(&A.acc.O[3 * cls + 1], dy);
+                atomicAdd(&A.acc.O[3 * cls + 2], dz);
+                atomicAdd(&A.acc.counter[cls], 1);
+            }
+        } else if (blockIdx.y == 0) {
             dx = block_reduce_sum(dx, redd);
             dy = block_reduce_sum(dy, redd);
             dz = block_reduce_sum(dz, redd);
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
                 }
                 const float mult = (float)(end - start);
                 const Rot2 rot = sRot[sOrder[start]];
+                float4* __restrict__ accg = A.drawC ? A.acc.p[sCls[sOrder[start]]] : acc;
                 start = end;
 #pragma unroll
                 for (int k = 0; k < M_KP; ++k) {
@@ -390,7 +408,8 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
                     row_offsets(y0, z0, n, nColFT, off);
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
-                        float4* row = acc + off[cc] + x0;
+                        if (A.mode2D && cc == 2) break;          // z0 = 0, zd = 0: plane 1 only ever receives zeros
+                        float4* row = accg + off[cc] + x0;
                         red_add_v4(row, fx[k] * w8[2 * cc], gy * w8[2 * cc], tv * w8[2 * cc]);
                         red_add_v4(row + 1, fx[k] * w8[2 * cc + 1], gy * w8[2 * cc + 1], tv * w8[2 * cc + 1]);
                     }

@@ -50,6 +50,19 @@ THB_HD Rot2 quat_to_rot2(const double q[4])
     return r;
 }
 
+// MODE_2D (src/Geometry/Euler.cpp:125-131, rotate2D(dmat22&, dvec2)): the in-plane rotation [[c, -s], [s, c]] of the unit
+// vector (c, s) = (quat[0], quat[1]), written as the first two columns of a 3x3 whose z row is zero: the slice coordinate is
+// then (c a - s b, s a + c b, 0) in the same double arithmetic as the reference's dmat22 * dvec2, and every 3D kernel works on
+// a reference image stored as plane 0 of a two-plane volume (zd = 0: the bilinear weights times exactly 1 and 0)
+THB_HD Rot2 make_rot2(const double q[4], int mode2D)
+{
+    if (!mode2D) return quat_to_rot2(q);
+    Rot2 r;
+    r.c0[0] = q[0]; r.c0[1] = q[1]; r.c0[2] = 0.0;
+    r.c1[0] = -q[1]; r.c1[1] = q[0]; r.c1[2] = 0.0;
+    return r;
+}
+
 // One trilinear cell in a half-complex volume of dimension n (nColFT = n/2+1):
 // element offsets of the 8 corners (order [k][j][i], i fastest, as the reference's w[2][2][2])
 // and their weights.  conj = the value (gather) / the inserted value (scatter) must be conjugated.

@@ -239,6 +239,7 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
     if (!ctx) return THB_E_ARG;
     if (nPar <= 0 || !p || !quat || !k123 || !tran || !s01 || p->mLR < 2 || p->mLT < 2)
         return set_error(ctx, THB_E_ARG, "pf_load: bad arguments");
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "pf_load: the device particle filter is MODE_3D only; drive MODE_2D through thb_expect_local / thb_expect_scan");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = pf_alloc(ctx, nPar, *p);
     if (rc) return rc;

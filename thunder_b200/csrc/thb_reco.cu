@@ -272,7 +272,7 @@ __device__ __forceinline__ float2 gather_lin(const float2* __restrict__ vol, int
 #define SIGMA_DUP (1 << 30)
 struct SigmaArgs {
     const float2* vols[THB_MAX_SLOTS];
-    int vdim, pitch, N, rSig, nGroup;
+    int vdim, pitch, N, rSig, nGroup, mode2D;
     const float2* datE; const float* ctfE; const int* slotE; const int4* pixE; const int* ringE; int PE;
     const float2* datM; const float* ctfM; const int4* pixM; const int* ringM; int PM;   // ringM < 0: pixel not in the sigma set
     const int* imgIdx; const double* quat; const double* tran; const double* offS; const int* group;
@@ -288,8 +288,9 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
     for (int i = tid; i < 4 * rS; i += blockDim.x) sRing[i] = 0.0f;
     __syncthreads();
     const float2* __restrict__ vol = A.vols[A.slotE ? A.slotE[img] : 0];
-    double q[4] = {A.quat[4 * l], A.quat[4 * l + 1], A.quat[4 * l + 2], A.quat[4 * l + 3]};
-    const Rot2 rot = quat_to_rot2(q);
+    double q[4] = {1.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < (A.mode2D ? 2 : 4); ++c) q[c] = A.quat[(A.mode2D ? 2 : 4) * l + c];
+    const Rot2 rot = make_rot2(q, A.mode2D);
     const float tx = (float)A.tran[2 * l], ty = (float)A.tran[2 * l + 1];
     const float ox = (float)(A.tran[2 * l] - A.offS[2 * l]), oy = (float)(A.tran[2 * l + 1] - A.offS[2 * l + 1]);
     const float invN = 1.0f;   // placeholder to keep the divisions below explicit
@@ -462,6 +463,7 @@ int thb_reco_upload(thb_ctx* ctx, int slot, const float* F, const float* T)
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reco_upload: slot %d not allocated", slot);
     if (!F || !T) return set_error(ctx, THB_E_ARG, "reco_upload: NULL arrays");
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "reco_upload: MODE_3D only");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     const Accum& a = ctx->accs[slot];
     float2* dF = (float2*)scratch(ctx, 2, a.nVox * sizeof(float2));
@@ -481,6 +483,7 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
 {
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reconstruct: slot %d not allocated", slot);
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "reconstruct: MODE_3D only");
     const Accum& acc = ctx->accs[slot];
     const int m = acc.vdim;
     if (N <= 0 || (N & 1) || pf <= 0 || m % pf || m / pf > N) return set_error(ctx, THB_E_ARG, "reconstruct: accumulator dimension %d does not fit N = %d, pf = %d", m, N, pf);
@@ -698,7 +701,7 @@ int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double
     float* dCntE = (float*)(dGrp + nImg); float* dCntM = dCntE + rSig;
     std::vector<double> zeroOff(2 * (size_t)nImg, 0.0);
     THB_CUDA(ctx, cudaMemsetAsync(dOut, 0, sizeof(double) * 3 * nOut, ctx->stream));
-    THB_CUDA(ctx, cudaMemcpyAsync(dQ, quat, sizeof(double) * 4 * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dQ, quat, sizeof(double) * (ctx->mode2D ? 2 : 4) * nImg, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dT, tran, sizeof(double) * 2 * nImg, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dO, offS ? offS : zeroOff.data(), sizeof(double) * 2 * nImg, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dRingE, ringE.data(), sizeof(int) * PE, cudaMemcpyHostToDevice, ctx->stream));
@@ -714,6 +717,7 @@ int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double
     a.datE = ctx->stackE.dat; a.ctfE = ctx->stackE.ctf; a.slotE = ctx->stackE.slot; a.pixE = ctx->pixE; a.ringE = dRingE; a.PE = PE;
     a.datM = ctx->stackM.dat; a.ctfM = ctx->stackM.ctf; a.pixM = ctx->pixM; a.ringM = dRingM; a.PM = PM;
     a.imgIdx = imgIdx ? dIdx : nullptr; a.quat = dQ; a.tran = dT; a.offS = dO; a.group = groupOfImg ? dGrp : nullptr;
+    a.mode2D = ctx->mode2D;
     a.cntE = dCntE; a.cntM = dCntM; a.sigM = dOut; a.sigN = dOut + nOut; a.svd = dOut + 2 * nOut;
     span_begin(ctx, KF_PACK);
     sigma_kernel<<<nImg, 256, sizeof(float) * 4 * rSig, ctx->stream>>>(a);
@@ -731,6 +735,7 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
 {
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || N <= 0 || (N & 1) || pf <= 0) return set_error(ctx, THB_E_ARG, "set_projectee: bad arguments");
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "set_projectee: MODE_3D only");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     RecoState* s = reco_state(ctx);
     const size_t nIn = (size_t)N * N * N;

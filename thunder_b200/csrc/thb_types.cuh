@@ -5,7 +5,7 @@
 
 namespace thb {
 
-constexpr int THB_MAX_SLOTS = 16;
+constexpr int THB_MAX_SLOTS = 32;   // volume / accumulator slots: half maps in 3D, classes in 2D (demo_2D.json: k = 20)
 constexpr int E_THREADS = 128;   // one rotation sample per thread
 constexpr int E_TILE = 128;      // pixels staged in shared memory per step
 constexpr int E_TC = 9;          // translations carried in registers per pass (mLT default = 9)
@@ -61,6 +61,8 @@ struct ExpectArgs {
     const int* slotOfImg;
     const int4* pix;
     int P, N;
+    int mode2D;             // MODE_2D: quat = (cos, sin, -, -) of the in-plane rotation, references are 2-plane volumes
+    int slotAll;            // >= 0: every image against this slot (2D classification scan), else slotOfImg
     int nAct;
     const int* imgIdx;      // may be null: image = particle index + imgBase
     int imgBase;
@@ -82,6 +84,7 @@ struct InsertArgs {
     const int* slotOfImg;
     const int4* pix;
     int P, N;
+    int mode2D;
     int nImg;
     const int* imgIdx;        // may be null
     int imgBase;
@@ -92,6 +95,7 @@ struct InsertArgs {
     View3 nr, nt;             // [nImg][mReco][4], [nImg][mReco][2]
     const int* drawR;         // optional [nImg][mReco] indices into nr/nt sample axis (particle filter draws)
     const int* drawT;
+    const int* drawC;         // optional [nImg][mReco] accumulator slot of every draw (MODE_2D classes), else slotOfImg
 };
 
 }  // namespace thb

@@ -113,6 +113,7 @@ void ExpectProject(Complex* volume, Complex* rotP, double* rotMat, const int* iC
 {
     (void)rotMat; (void)interp; (void)iCol; (void)iRow; (void)nR; (void)npxl;
     thb_ctx* ctx = thbContext(0);
+    CHK(ctx, thb_set_mode(ctx, THB_MODE_3D));
     CHK(ctx, thb_set_expect_pixels(ctx, g_scan.idim, pf, g_scan.npxl, g_scan.iCol.data(), g_scan.iRow.data()));
     CHK(ctx, thb_set_volume(ctx, 0, reinterpret_cast<const float*>(volume), vdim));
     g_scan.volume = volume; g_scan.vdim = vdim; g_scan.pf = pf;
@@ -121,20 +122,11 @@ void ExpectProject(Complex* volume, Complex* rotP, double* rotMat, const int* iC
         CHK(ctx, thb_project(ctx, 0, g_scan.nR, g_scan.rot.data(), reinterpret_cast<float*>(rotP)));
 }
 
-void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
-                    double* pR, double* pT, RFLOAT* baseL, int kIdx, int nK, int nR, int nT, int npxl, int imgNum)
+// classes share one baseline per image: weights of earlier classes are rescaled when a later class raises it
+// (kernel_setBaseLine, gpu/src/Kernel.cu:1096-1135; CPU: Optimiser.cpp:846-870)
+static void mergeClass(const std::vector<float>& cC, const std::vector<float>& cR, const std::vector<float>& cT, const std::vector<float>& cB,
+                       RFLOAT* wC, RFLOAT* wR, RFLOAT* wT, RFLOAT* baseL, int kIdx, int nK, int nR, int nT, int imgNum)
 {
-    (void)rotP; (void)traP; (void)npxl;
-    thb_ctx* ctx = thbContext(0);
-    if (g_scan.stackDat != datP || g_scan.stackImgs != imgNum) {
-        CHK(ctx, thb_upload_stack(ctx, THB_STACK_EXPECT, imgNum, reinterpret_cast<const float*>(datP), ctfP, sigRcpP, nullptr));
-        g_scan.stackDat = datP; g_scan.stackImgs = imgNum;
-    }
-    std::vector<float> cC(imgNum), cR((size_t)imgNum * nR), cT((size_t)imgNum * nT), cB(imgNum);
-    CHK(ctx, thb_expect_scan(ctx, 0, nR, nT, g_scan.rot.data(), g_scan.trans.data(), pR, pT, cC.data(), cR.data(), cT.data(),
-                             cB.data(), nullptr));
-    // classes share one baseline per image: weights of earlier classes are rescaled when a later class raises it
-    // (kernel_setBaseLine, gpu/src/Kernel.cu:1096-1135; CPU: Optimiser.cpp:846-870)
     for (int l = 0; l < imgNum; ++l) {
         float scaleOld = 1.f, scaleNew = 1.f;
         if (kIdx == 0) {
@@ -157,12 +149,84 @@ void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, R
     }
 }
 
+void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
+                    double* pR, double* pT, RFLOAT* baseL, int kIdx, int nK, int nR, int nT, int npxl, int imgNum)
+{
+    (void)rotP; (void)traP; (void)npxl;
+    thb_ctx* ctx = thbContext(0);
+    if (g_scan.stackDat != datP || g_scan.stackImgs != imgNum) {
+        CHK(ctx, thb_upload_stack(ctx, THB_STACK_EXPECT, imgNum, reinterpret_cast<const float*>(datP), ctfP, sigRcpP, nullptr));
+        g_scan.stackDat = datP; g_scan.stackImgs = imgNum;
+    }
+    std::vector<float> cC(imgNum), cR((size_t)imgNum * nR), cT((size_t)imgNum * nT), cB(imgNum);
+    CHK(ctx, thb_expect_scan(ctx, 0, nR, nT, g_scan.rot.data(), g_scan.trans.data(), pR, pT, cC.data(), cR.data(), cT.data(),
+                             cB.data(), nullptr));
+    mergeClass(cC, cR, cT, cB, wC, wR, wT, baseL, kIdx, nK, nR, nT, imgNum);
+}
+
+// MODE_2D classification scan (gpu/interface/Interface.h:176-198; call site src/Optimiser.cpp:1873-1920): vol = nK padded
+// class averages [vdim][vdim/2+1], rot = nR x (cos, sin), every image against every class, one baseline per image
+void ExpectGlobal2D(Complex* vol, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, double* trans, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
+                    double* pR, double* pT, double* rot, const int* iCol, const int* iRow, int nK, int nR, int nT, int pf, int interp,
+                    int idim, int vdim, int npxl, int imgNum)
+{
+    (void)interp;
+    thb_ctx* ctx = thbContext(0);
+    CHK(ctx, thb_set_mode(ctx, THB_MODE_2D));
+    CHK(ctx, thb_set_expect_pixels(ctx, idim, pf, npxl, iCol, iRow));
+    const size_t sizeModel = (size_t)(vdim / 2 + 1) * vdim;
+    for (int k = 0; k < nK; ++k) CHK(ctx, thb_set_volume(ctx, k, reinterpret_cast<const float*>(vol + k * sizeModel), vdim));
+    CHK(ctx, thb_upload_stack(ctx, THB_STACK_EXPECT, imgNum, reinterpret_cast<const float*>(datP), ctfP, sigRcpP, nullptr));
+    g_scan.stackDat = nullptr;
+    std::vector<float> cC(imgNum), cR((size_t)imgNum * nR), cT((size_t)imgNum * nT), cB(imgNum), baseL(imgNum);
+    for (int k = 0; k < nK; ++k) {
+        CHK(ctx, thb_expect_scan(ctx, k, nR, nT, rot, trans, pR, pT, cC.data(), cR.data(), cT.data(), cB.data(), nullptr));
+        mergeClass(cC, cR, cT, cB, wC, wR, wT, baseL.data(), k, nK, nR, nT, imgNum);
+    }
+}
+
+// MODE_2D M-step (gpu/interface/Interface.h:239-265; call site src/Optimiser.cpp:6770-6850): F2D [nk][vdim][vdim/2+1] complex,
+// T2D the same as reals, O2D [nk][2], counter [nk]; nC / nR / nT: class, (cos, sin) and translation of every draw
+void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, RFLOAT* w, double* offS,
+               int* nC, double* nR, double* nT, double* nD, void* ctfaData, const int* iCol, const int* iRow, RFLOAT pixelSize,
+               bool cSearch, int nk, int opf, int npxl, int mReco, int idim, int vdim, int imgNum)
+{
+    (void)sigRcpP; (void)nD; (void)ctfaData; (void)pixelSize;
+    thb_ctx* ctx = thbContext(0);
+    if (cSearch) {
+        fprintf(stderr, "thunder_b200 [InsertI2D]: CTF search (cSearch) is not on the accelerated path of this build\n");
+        abort();
+    }
+    CHK(ctx, thb_set_mode(ctx, THB_MODE_2D));
+    CHK(ctx, thb_set_insert_pixels(ctx, idim, opf, npxl, iCol, iRow));
+    CHK(ctx, thb_upload_stack(ctx, THB_STACK_INSERT, imgNum, reinterpret_cast<const float*>(datP), ctfP, nullptr, nullptr));
+    for (int k = 0; k < nk; ++k) CHK(ctx, thb_reco_alloc(ctx, k, vdim));
+    CHK(ctx, thb_insert_classes(ctx, imgNum, nullptr, mReco, w, offS, nC, nR, nT));
+    CHK(ctx, thb_allreduce(ctx));
+    const size_t n = (size_t)(vdim / 2 + 1) * vdim;
+    std::vector<float> F(2 * n), T(n);
+    for (int k = 0; k < nk; ++k) {
+        double O[3];
+        int cnt = 0;
+        CHK(ctx, thb_reco_download(ctx, k, F.data(), T.data(), O, &cnt, 0));
+        for (size_t i = 0; i < n; ++i) {
+            F2D[k * n + i].dat[0] += F[2 * i];
+            F2D[k * n + i].dat[1] += F[2 * i + 1];
+            T2D[k * n + i] += T[i];
+        }
+        O2D[2 * k] += O[0];
+        O2D[2 * k + 1] += O[1];
+        counter[k] += cnt;
+    }
+}
+
 void ExpectLocalBatch(int gpuIdx, Complex* volume, int vdim, int pf, int idim, const int* iCol, const int* iRow, int npxl, Complex* datP,
                       RFLOAT* ctfP, RFLOAT* sigRcpP, int imgNum, int nR, int nT, const double* quat, const double* tran,
                       const double* wRprior, const double* wTprior, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT, RFLOAT* baseL)
 {
     thb_ctx* ctx = thbContext(gpuIdx);
     if (volume) {
+        CHK(ctx, thb_set_mode(ctx, THB_MODE_3D));
         CHK(ctx, thb_set_expect_pixels(ctx, idim, pf, npxl, iCol, iRow));
         CHK(ctx, thb_set_volume(ctx, 0, reinterpret_cast<const float*>(volume), vdim));
     }
@@ -185,6 +249,7 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
         fprintf(stderr, "thunder_b200 [InsertFT]: dimSize %d does not match vdim %d\n", dimSize, vdim);
         abort();
     }
+    CHK(ctx, thb_set_mode(ctx, THB_MODE_3D));
     CHK(ctx, thb_set_insert_pixels(ctx, idim, opf, npxl, iCol, iRow));   // Reconstructor's _iCol/_iRow are padded (x pf)
     CHK(ctx, thb_upload_stack(ctx, THB_STACK_INSERT, imgNum, reinterpret_cast<const float*>(datP), ctfP, nullptr, nullptr));
     CHK(ctx, thb_reco_alloc(ctx, 0, vdim));
@@ -239,6 +304,19 @@ void thbi_InsertFT(float* F3D, float* T3D, int vdim, double* O3D, int* counter, 
 {
     InsertFT(reinterpret_cast<Complex*>(F3D), reinterpret_cast<Complex*>(T3D), vdim, O3D, counter, reinterpret_cast<Complex*>(datP), ctfP,
              nullptr, nullptr, offS, w, nR, nT, nullptr, nullptr, iCol, iRow, 1.32f, false, opf, npxl, mReco, idim, dimSize, imgNum);
+}
+void thbi_ExpectGlobal2D(float* vol, float* datP, float* ctfP, float* sigRcpP, double* trans, float* wC, float* wR, float* wT, double* pR,
+                         double* pT, double* rot, const int* iCol, const int* iRow, int nK, int nR, int nT, int pf, int idim, int vdim,
+                         int npxl, int imgNum)
+{
+    ExpectGlobal2D(reinterpret_cast<Complex*>(vol), reinterpret_cast<Complex*>(datP), ctfP, sigRcpP, trans, wC, wR, wT, pR, pT, rot, iCol,
+                   iRow, nK, nR, nT, pf, 1, idim, vdim, npxl, imgNum);
+}
+void thbi_InsertI2D(float* F2D, float* T2D, double* O2D, int* counter, float* datP, float* ctfP, float* w, double* offS, int* nC, double* nR,
+                    double* nT, const int* iCol, const int* iRow, int nk, int opf, int npxl, int mReco, int idim, int vdim, int imgNum)
+{
+    InsertI2D(reinterpret_cast<Complex*>(F2D), T2D, O2D, counter, reinterpret_cast<Complex*>(datP), ctfP, nullptr, w, offS, nC, nR, nT,
+              nullptr, nullptr, iCol, iRow, 1.32f, false, nk, opf, npxl, mReco, idim, vdim, imgNum);
 }
 void thbi_shutdown() { thbShutdown(); }
 }

@@ -63,6 +63,17 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
               const int* iRow, RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim, int dimSize,
               int imgNum);
 
+// ---- MODE_2D (2D classification).  Same argument lists as gpu/interface/Interface.h:176-198 (ExpectGlobal2D) and :239-265
+// (InsertI2D, minus the two MPI communicators: see the THB_WITH_THUNDER overload below and thb_comm_init): vol = nK padded
+// class averages, rot = nR x (cos, sin); every image is compared with every class and the classes share one baseline per
+// image; InsertI2D scatters each draw into the accumulator of its class nC and ADDS the result to F2D / T2D / O2D / counter.
+void ExpectGlobal2D(Complex* vol, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, double* trans, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
+                    double* pR, double* pT, double* rot, const int* iCol, const int* iRow, int nK, int nR, int nT, int pf, int interp,
+                    int idim, int vdim, int npxl, int imgNum);
+void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, RFLOAT* w, double* offS,
+               int* nC, double* nR, double* nT, double* nD, void* ctfaData, const int* iCol, const int* iRow, RFLOAT pixelSize,
+               bool cSearch, int nk, int opf, int npxl, int mReco, int idim, int vdim, int imgNum);
+
 #ifdef THB_WITH_THUNDER
 #include "mpi.h"
 #include "Volume.h"
@@ -73,6 +84,14 @@ inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Co
 {
     InsertFT(&F3D[0], &T3D[0], (int)F3D.nSlcFT(), O3D, counter, datP, ctfP, sigRcpP, (void*)ctfaData, offS, w, nR, nT, nD,
              (int*)0, iCol, iRow, pixelSize, cSearch, opf, npxl, mReco, idim, dimSize, imgNum);
+}
+inline void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
+                      RFLOAT* sigRcpP, RFLOAT* w, double* offS, int* nC, double* nR, double* nT, double* nD, CTFAttr* ctfaData,
+                      const int* iCol, const int* iRow, RFLOAT pixelSize, bool cSearch, int nk, int opf, int npxl, int mReco, int idim,
+                      int vdim, int imgNum)
+{
+    InsertI2D(F2D, T2D, O2D, counter, datP, ctfP, sigRcpP, w, offS, nC, nR, nT, nD, (void*)ctfaData, iCol, iRow, pixelSize, cSearch, nk,
+              opf, npxl, mReco, idim, vdim, imgNum);
 }
 #endif
 
