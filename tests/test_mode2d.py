@@ -90,10 +90,12 @@ def test_port2d_insert_matches_reference():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-@pytest.fixture()
-def ctx2d():
+@pytest.fixture(params=[3, 1], ids=["cell-kernel", "linear-kernel"])
+def ctx2d(request):
+    """both E kernels serve MODE_2D: the default one (bilinear cell = one 256-bit load) and the linear-layout one"""
     c = capi.Context(0)
     c.set_mode(capi.MODE_2D)
+    c.set_option("expect_impl", request.param)
     yield c
     c.close()
 

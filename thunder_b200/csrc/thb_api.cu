@@ -103,6 +103,20 @@ static int ensure_quad(thb_ctx* ctx, int slot)
 {
     Volume3& v = ctx->vols[slot];
     if (!v.d) return THB_OK;
+    if (ctx->mode2D) {
+        // class average: the bilinear cell of every (x, y) in plain rows, one 256-bit load per sample
+        if (v.quad) return THB_OK;
+        const size_t elems2 = (size_t)v.vdim * (v.vdim / 2);
+        THB_CUDA(ctx, cudaMalloc(&v.quad, elems2 * sizeof(Quad)));
+        span_begin(ctx, KF_PACK);
+        build_quad_kernel<<<ctx->smCount * 2, 256, 0, ctx->stream>>>(v.d, v.vdim, 1, v.pitch, 0, reinterpret_cast<Quad*>(v.quad));
+        span_end(ctx);
+        ctx->launches++;
+        v.quadBrick = 0;
+        v.quadOct = 0;
+        THB_CUDA(ctx, cudaGetLastError());
+        return THB_OK;
+    }
     if (v.quad && v.quadBrick == ctx->quadBrick && v.quadOct == ctx->quadOct) return THB_OK;
     if ((v.vdim / 2) % (1 << ctx->quadBrick)) ctx->quadBrick = 0;   // tiny volumes: plain rows
     if (v.quad) {
@@ -121,7 +135,7 @@ static int ensure_quad(thb_ctx* ctx, int slot)
     if (ctx->quadOct)
         build_oct_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
     else
-        build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
+        build_quad_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.vdim, v.pitch, ctx->quadBrick, reinterpret_cast<Quad*>(v.quad));
     v.quadBrick = ctx->quadBrick;
     v.quadOct = ctx->quadOct;
     span_end(ctx);
@@ -137,8 +151,8 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
         if (rc) return rc;
     }
     a.quads = quad_table(ctx);
-    a.quadBrick = ctx->quadBrick;
-    a.sortRot = ctx->sortRot;
+    a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
+    a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
     a.work = nullptr;
     const bool single = a.nR <= E3_ROTS && a.nT <= E_TC;
     if (!single) {
@@ -147,7 +161,9 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     }
     const size_t smem = E3_SMEM_BYTES + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
-    if (ctx->quadOct)
+    if (ctx->mode2D)
+        expect_direct_kernel<2, false, true><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+    else if (ctx->quadOct)
         expect_direct_kernel<2, true><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
     else if (ctx->expectMinBlocks >= 3)
         expect_direct_kernel<3, false><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
@@ -197,7 +213,7 @@ int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
     if (a.nAct <= 0) return THB_OK;
     a.mode2D = ctx->mode2D;
     if (!ctx->mode2D) a.slotAll = -1;
-    if (ctx->expectImpl == 3 && !ctx->mode2D) return launch_expect_v3(ctx, a);
+    if (ctx->expectImpl == 3) return launch_expect_v3(ctx, a);
     if (ctx->expectImpl == 2 && !ctx->mode2D) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)

@@ -70,10 +70,10 @@ __global__ void build_oct_kernel(const float2* __restrict__ vol, int n, int pitc
 }
 
 // linear pitched float2 volume -> quad layout, x in [0, half)
-__global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int pitch, int LB, Quad* __restrict__ out)
+__global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int nz, int pitch, int LB, Quad* __restrict__ out)
 {
     const int half = n / 2;
-    const size_t total = (size_t)n * n * half;
+    const size_t total = (size_t)nz * n * half;          // nz = n, or 1 for a MODE_2D class average (LB = 0)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % half);
         const size_t row = i / half;
@@ -92,7 +92,7 @@ constexpr int E3_ROTS = 128;
 constexpr int E3_TILE = 128;
 constexpr size_t E3_SMEM_BYTES = E3_TILE * sizeof(PixelRec);     // + the [nR][nT] table for single-pass shapes
 
-template <int MINB, bool OCT>
+template <int MINB, bool OCT, bool M2D = false>
 __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const ExpectArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     const int p = blockIdx.x;
     if (A.active && !A.active[p]) return;
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
-    const int slot = A.slotOfImg ? A.slotOfImg[img] : 0;
+    const int slot = (M2D && A.slotAll >= 0) ? A.slotAll : (A.slotOfImg ? A.slotOfImg[img] : 0);
     const Quad* __restrict__ vol = reinterpret_cast<const Quad*>(A.quads.p[slot]);
     const int n = A.vdim, half = n / 2;
     const int P = A.P;
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
         {
             double q[4] = {1.0, 0.0, 0.0, 0.0};
             if (rvalid)
-                for (int c = 0; c < 4; ++c) q[c] = A.quat.at(p, rbase + rsrc, c);
-            rot = quat_to_rot2(q);
+                for (int c = 0; c < (M2D ? 2 : 4); ++c) q[c] = A.quat.at(p, rbase + rsrc, c);
+            rot = make_rot2(q, M2D);
         }
         for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
             __syncthreads();
@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         const int zm1 = (z0 + 1 < 0) ? z0 + 1 + n : z0 + 1;
                         const Quad* q0 = OCT ? vol + 2 * quad_index(x0, ym, zm, n, LB) : vol + quad_index(x0, ym, zm, n, LB);
                         const Quad* q1 = OCT ? q0 + 1 : vol + quad_index(x0, ym, zm1, n, LB);
-                        const Quad a = ldg_quad(q0), b = ldg_quad(q1);
+                        // MODE_2D: z = 0 exactly, the second plane carries weight 0 and does not exist
+                        const Quad a = ldg_quad(q0), b = M2D ? Quad{} : ldg_quad(q1);
                         float w[8];
                         tri_weights(xd, yd, zd, w);
                         float re = a.v00.x * w[0], im = a.v00.y * w[0];
