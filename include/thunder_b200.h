@@ -242,6 +242,22 @@ int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double
                          const int* groupOfImg, int nGroup, int rSig, const int* iSigE, const int* iSigM, double* sigM,
                          double* sigN, double* svd);
 
+/* Point-group symmetrisation of the accumulators after the all-reduce, as prepareTF does (Reconstructor::symmetrizeF / T / O,
+ * src/Reconstructor.cpp:2676-2716 = SYMMETRIZE_FT, include/Geometry/Transformation.h:105-194): F, T += their trilinear
+ * interpolation at R_e v for each of the nElem symmetry elements (R[nElem][9], column-major dmat33 as Symmetry::get(L, R, i)
+ * returns them; C1: nElem = 0), for rotated positions inside `radius` (the reference passes maxRadius * pf + 1);
+ * O += sum_e R_e O; counter *= 1 + nElem.  MODE_3D. */
+int thb_symmetrize(thb_ctx* ctx, int slot, int nElem, const double* R, double radius);
+
+/* Optimiser::normCorrection (src/Optimiser.cpp:6201-6393, OPTIMISER_NORM_MASK as in include/Config.h:171), image loop:
+ * norm[l] = sum over the half plane {rL^2 <= |k|^2 < rNorm^2} of |masked image - ctf * slice at quat[l] translated by tran[l]|^2
+ * on the resident E stack (its pixel list must reach rNorm).  The median over ALL particles (an MPI all-reduce in the reference,
+ * :6352-6369) and s_l = sqrt(median / norm_l) stay with the caller; thb_scale_images applies s_l to the images of both
+ * resident stacks (_img[l] *= s, _imgOri[l] *= s, :6381-6391). */
+int thb_norm_residual(thb_ctx* ctx, int nImg, const int* imgIdx, const double* quat, const double* tran, float rL, float rNorm,
+                      double* norm);
+int thb_scale_images(thb_ctx* ctx, int nImg, const int* imgIdx, const float* scale);
+
 /* ---------------------------------------------------------------- a9: device-resident particle filter */
 typedef struct thb_pf_params {
     int mLR, mLT;               /* support sizes (rotation, translation) */

@@ -36,6 +36,7 @@
 #include "CTF.h"
 #include "FFT.h"
 #include "Spectrum.h"
+#include "Symmetry.h"
 #include "ImageFunctions.h"
 #include "Euler.h"
 #include "Random.h"
@@ -436,6 +437,71 @@ void ref_sigma_accumulate(void* projH, int nImg, int N, int rSig, const float* i
     }
 }
 
+
+// Symmetry elements of a point group (include/Geometry/Symmetry.h): R matrices, column-major; returns their number
+int ref_symmetry_elements(const char* name, double* R9, int maxElem)
+{
+    Symmetry sym(name);
+    int n = sym.nSymmetryElement();
+    for (int i = 0; i < n && i < maxElem; i++)
+    {
+        dmat33 L, R;
+        sym.get(L, R, i);
+        memcpy(R9 + 9 * i, R.data(), 9 * sizeof(double));
+    }
+    return n;
+}
+
+// Reconstructor::symmetrizeF / symmetrizeT / symmetrizeO (src/Reconstructor.cpp:2676-2716) on the accumulators as they are
+void ref_reco_symmetrize(void* h, const char* name, int nThread)
+{
+    RefReco* r = (RefReco*)h;
+    Symmetry sym(name);
+    r->reco._sym = &sym;
+    r->reco.symmetrizeT(nThread);
+    r->reco.symmetrizeF(nThread);
+    r->reco.symmetrizeO();
+    r->reco._sym = NULL;
+}
+
+void ref_reco_set_O(void* h, const double* O3, int counter)
+{
+    RefReco* r = (RefReco*)h;
+    r->reco._ox = O3[0]; r->reco._oy = O3[1]; r->reco._oz = O3[2];
+    r->reco._counter = counter;
+}
+
+// image loop of Optimiser::normCorrection (src/Optimiser.cpp:6201-6350, MODE_3D, OPTIMISER_NORM_MASK, no CTF search) with the
+// reference's functions: norm[l] = sum_{rL^2 <= |k|^2 < rNorm^2} |_img[l] - CTF * project(rot, tran)|^2 (RFLOAT accumulator)
+void ref_norm_residual(void* projH, int nImg, int N, float rL, float rNorm, const float* imgFT, const double* quat,
+                       const double* tran, const float* ctfAttr7, float pixelSize, float* norm)
+{
+    RefProjector* P = (RefProjector*)projH;
+    const size_t nFT = (size_t)(N / 2 + 1) * N;
+    for (int l = 0; l < nImg; l++)
+    {
+        Image img(N, N, FT_SPACE), mask(N, N, FT_SPACE), ctf(N, N, FT_SPACE);
+        memcpy(&mask[0], imgFT + 2 * nFT * l, nFT * sizeof(Complex));
+        SET_0_FT(img);
+        SET_0_FT(ctf);
+        dmat33 rot3D;
+        rotate3D(rot3D, dvec4(quat[4 * l], quat[4 * l + 1], quat[4 * l + 2], quat[4 * l + 3]));
+        P->proj.project(img, rot3D, dvec2(tran[2 * l], tran[2 * l + 1]), 1);
+        const float* a = ctfAttr7 + 7 * l;
+        CTF(ctf, pixelSize, a[0], a[1], a[2], a[3], a[4], a[5], a[6], CEIL(rNorm) + 1, 1);
+        FOR_EACH_PIXEL_FT(img)
+            img[i] *= REAL(ctf[i]);
+        NEG_FT(img);
+        ADD_FT(img, mask);
+        RFLOAT s = 0;
+        IMAGE_FOR_EACH_PIXEL_FT(img)
+        {
+            if ((QUAD(i, j) >= TSGSL_pow_2(rL)) && (QUAD(i, j) < TSGSL_pow_2(rNorm)))
+                s += ABS2(img.getFTHalf(i, j));
+        }
+        norm[l] = s;
+    }
+}
 
 // ---------------------------------------------------------------- MODE_2D (2D classification, demo_2D.json)
 // Projector in MODE_2D holding an already padded half-complex class average [pfN][pfN/2+1] verbatim

@@ -68,6 +68,11 @@ def lib():
         L.ref_reco2d_pad_size.argtypes = [_p]
         L.ref_reco2d_insert_draw.argtypes = [_p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _f]
         L.ref_reco2d_get.argtypes = [_p, _p, _p, _p, _p]
+        L.ref_symmetry_elements.restype = _i
+        L.ref_symmetry_elements.argtypes = [C.c_char_p, _p, _i]
+        L.ref_reco_symmetrize.argtypes = [_p, C.c_char_p, _i]
+        L.ref_reco_set_O.argtypes = [_p, _p, _i]
+        L.ref_norm_residual.argtypes = [_p, _i, _i, _f, _f, _p, _p, _p, _p, _f, _p]
         L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
         L.ref_sigma_accumulate.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p, _p, _p]
         L.ref_reco_set.argtypes = [_p, _p, _p]
@@ -162,6 +167,25 @@ def sigma_accumulate(P, imgFT, imgOriFT, quat, tran, offS, ctfAttr, pixelSize, g
     lib().ref_projector_set_max_radius(P.h, rSig)
     lib().ref_sigma_accumulate(P.h, nImg, N, rSig, _ptr(imgFT), _ptr(imgOriFT), _ptr(quat), _ptr(tran), _ptr(offS), _ptr(attr), float(pixelSize),
                                _ptr(group), nGroup, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]))
+    return out
+
+
+def symmetry_elements(name):
+    """R matrices [nElem][9] (column-major dmat33) of the reference's Symmetry(name), e.g. C4, D2, T, O, I"""
+    R = np.zeros((128, 9))
+    n = lib().ref_symmetry_elements(name.encode(), _ptr(R), 128)
+    return R[:n].copy()
+
+
+def norm_residual(P, imgFT, quat, tran, ctfAttr, pixelSize, rL, rNorm):
+    """image loop of Optimiser::normCorrection with the reference's functions; P: Projector whose max radius covers rNorm"""
+    imgFT = np.ascontiguousarray(imgFT, np.complex64)
+    nImg, N = imgFT.shape[0], imgFT.shape[1]
+    quat = np.ascontiguousarray(quat, np.float64); tran = np.ascontiguousarray(tran, np.float64)
+    attr = np.ascontiguousarray(ctfAttr, np.float32)
+    out = np.zeros(nImg, np.float32)
+    lib().ref_projector_set_max_radius(P.h, int(np.ceil(rNorm)) + 1)
+    lib().ref_norm_residual(P.h, nImg, N, float(rL), float(rNorm), _ptr(imgFT), _ptr(quat), _ptr(tran), _ptr(attr), float(pixelSize), _ptr(out))
     return out
 
 
@@ -263,6 +287,13 @@ class Reconstructor:
 
     def max_radius(self):
         return lib().ref_reco_max_radius(self.h)
+
+    def symmetrize(self, name, O=None, counter=0):
+        """Reconstructor::symmetrizeT / F / O on the current accumulators"""
+        if O is not None:
+            O = np.ascontiguousarray(O, np.float64)
+            lib().ref_reco_set_O(self.h, _ptr(O), int(counter))
+        lib().ref_reco_symmetrize(self.h, name.encode(), self.nThread)
 
     def reconstruct(self, N, gridCorr=True, joinHalf=False, fsc=None, nThread=8):
         """Reconstructor::reconstruct -> real volume [N][N][N] float32, origin at index 0"""

@@ -183,3 +183,87 @@ def test_device_sigma_accumulate(ctx):
         assert np.array_equal(g[:, -1], w[:, -1]), name                        # weight sums: images per group
         assert np.allclose(g[:, :rSig], w[:, :rSig], rtol=2e-4, atol=0), name
     P.close()
+
+
+@pytest.mark.gpu
+def test_device_norm_correction(ctx):
+    """thb_norm_residual == the image loop of Optimiser::normCorrection through the reference's own functions;
+    thb_scale_images == the rescaling of _img / _imgOri that follows"""
+    from oracle import refapi
+    from thunder_b200 import capi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, pf, r, rL, rNorm = 64, 2, 26.0, 2.0, 21.3
+    rng = np.random.default_rng(78)
+    P = refapi.Projector(pf)
+    P.set_from_real(synth.phantom(N, 10, seed=4))
+    volFT = P.padded_ft()
+    pixE = capi.pixel_list(N, pf, r, rL)
+    pixM = capi.pixel_list(N, pf, 29.0, 0.0)
+    nImg = 7
+    img = np.stack([np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)) for _ in range(nImg)]).astype(np.complex64)
+    img *= np.float32(np.abs(volFT).mean() * 3 / np.abs(img).mean())
+    quat = synth.random_quats(nImg, rng); tran = rng.normal(scale=1.5, size=(nImg, 2))
+    attr = np.stack([np.full(nImg, 3e5), rng.uniform(1e4, 3e4, nImg), rng.uniform(1e4, 3e4, nImg), rng.uniform(0, np.pi, nImg),
+                     np.full(nImg, 2.7e7), np.full(nImg, 0.1), np.zeros(nImg)], axis=1).astype(np.float32)
+    want = refapi.norm_residual(P, img, quat, tran, attr, 1.32, rL, rNorm)
+    ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+    ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+    ctx.set_volume(0, volFT)
+    ctx.stack_reserve(capi.STACK_EXPECT, nImg); ctx.stack_reserve(capi.STACK_INSERT, nImg)
+    ctx.pack_stack(capi.STACK_EXPECT, 0, img, pixE["iPxl"], attr, 1.32, iSig=pixE["iSig"], sigRcpTab=np.full((1, N), -0.5, np.float32))
+    ctx.pack_stack(capi.STACK_INSERT, 0, img, pixM["iPxl"], attr, 1.32)
+    got = ctx.norm_residual(quat, tran, rL, rNorm)
+    assert np.allclose(got, want, rtol=2e-4, atol=0)
+    # rescale to the median, as :6371-6391
+    scale = np.sqrt(np.median(got) / got).astype(np.float32)
+    before = [ctx.download_stack(k, 0, nImg) for k in (capi.STACK_EXPECT, capi.STACK_INSERT)]
+    ctx.scale_images(scale)
+    after = [ctx.download_stack(k, 0, nImg) for k in (capi.STACK_EXPECT, capi.STACK_INSERT)]
+    for b, a in zip(before, after):
+        assert np.array_equal(a["dat"], (b["dat"] * scale[:, None]).astype(np.complex64))
+        assert np.array_equal(a["ctf"], b["ctf"])
+    P.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["C4", "D2", "T"])
+def test_device_symmetrize(ctx, group):
+    """thb_symmetrize == Reconstructor::symmetrizeT / symmetrizeF / symmetrizeO (SYMMETRIZE_FT) on the same accumulators"""
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, pf = 32, 2
+    rng = np.random.default_rng(90)
+    R = refapi.Reconstructor(N, N, pf)
+    m = R.pad_size()
+    shape = (m, m, m // 2 + 1)
+    # a smooth Hermitian-consistent F (FT of a real volume) and a positive T, as accumulators look after the all-reduce
+    vol = synth.phantom(N, 8, seed=12)
+    F = np.fft.rfftn(np.pad(vol, [(0, m - N)] * 3)).astype(np.complex64)
+    T = (np.abs(np.fft.rfftn(np.pad(synth.phantom(N, 5, seed=13), [(0, m - N)] * 3))) + 1.0).astype(np.float32)
+    assert F.shape == shape
+    O = np.array([1.5, -0.25, 0.75]); counter = 17
+    R.set(F, T)
+    R.symmetrize(group, O, counter)
+    want = R.get()
+    elems = refapi.symmetry_elements(group)
+    ctx.reco_alloc(0, m)
+    ctx.reco_upload(0, F, T)
+    ctx.symmetrize(0, elems, R.max_radius() * pf + 1)
+    got = ctx.reco_download(0)
+    # voxels whose integer |v|^2 equals r^2 exactly sit on the cut `|R v|^2 < r^2`: there the last bit of the rotated
+    # coordinates (Eigen's evaluation order vs. ours, 1e-13 on 841) decides whether the element contributes, in the reference
+    # as much as here.  They are compared for membership in {with, without the borderline elements}, the rest to 2e-6.
+    r = R.max_radius() * pf + 1
+    kk, jj, ii = np.meshgrid(np.fft.fftfreq(m, 1 / m), np.fft.fftfreq(m, 1 / m), np.arange(m // 2 + 1), indexing="ij")
+    edge = (ii * ii + jj * jj + kk * kk) == r * r
+    assert 0 < edge.sum() < 2000
+    assert np.abs(got["F"] - want["F"])[~edge].max() <= 2e-6 * np.abs(want["F"]).max()
+    assert np.abs(got["T"] - want["T"])[~edge].max() <= 2e-6 * np.abs(want["T"]).max()
+    assert np.abs(got["T"] - want["T"])[edge].max() <= len(elems) * np.abs(T).max()
+    # O and counter start at zero on the device: the linear map is checked on the reference's numbers
+    Rm = elems.reshape(-1, 3, 3).transpose(0, 2, 1)                 # column-major -> matrices
+    assert np.allclose(want["O"], O + sum(r @ O for r in Rm), atol=1e-12)
+    assert want["counter"] == counter * (1 + len(elems))
+    R.close()

@@ -69,6 +69,9 @@ def _sig(lib):
     f = lib.thb_upload_stack_at_async; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p]
     f = lib.thb_upload_wait; f.restype = _i; f.argtypes = [_p]
     f = lib.thb_set_mode; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_symmetrize; f.restype = _i; f.argtypes = [_p, _i, _i, _p, C.c_double]
+    f = lib.thb_norm_residual; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p, C.c_float, C.c_float, _p]
+    f = lib.thb_scale_images; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_get_mode; f.restype = _i; f.argtypes = [_p]
     f = lib.thb_insert_classes; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
@@ -320,6 +323,25 @@ class Context:
         self._chk(self.lib.thb_sigma_accumulate(self.h, nImg, _ptr(imgIdx), _ptr(quat), _ptr(tran), _ptr(offS), _ptr(groupOfImg), nGroup, rSig,
                                                 _ptr(iSigE), _ptr(iSigM), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
         return out
+
+    def symmetrize(self, slot, R, radius):
+        """Reconstructor::symmetrizeF / T / O: R[nElem][9] column-major symmetry elements, radius = maxRadius * pf + 1"""
+        R = _arr(R, np.float64)
+        nElem = 0 if R is None else R.shape[0]
+        self._chk(self.lib.thb_symmetrize(self.h, slot, nElem, _ptr(R) if nElem else None, float(radius)))
+
+    def norm_residual(self, quat, tran, rL, rNorm, imgIdx=None):
+        """image loop of Optimiser::normCorrection: sum of |masked image - ctf * translated slice|^2 over rL <= |k| < rNorm"""
+        quat = _arr(quat, np.float64); nImg = quat.shape[0]
+        tran = _arr(tran, np.float64, (nImg, 2)); imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        out = np.zeros(nImg)
+        self._chk(self.lib.thb_norm_residual(self.h, nImg, _ptr(imgIdx), _ptr(quat), _ptr(tran), float(rL), float(rNorm), _ptr(out)))
+        return out
+
+    def scale_images(self, scale, imgIdx=None):
+        scale = _arr(scale, np.float32); nImg = scale.shape[0]
+        imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        self._chk(self.lib.thb_scale_images(self.h, nImg, _ptr(imgIdx), _ptr(scale)))
 
     # ---- reconstruct / setProjectee (SURVEY.md section 8f row 1)
     def reco_upload(self, slot, F, T):

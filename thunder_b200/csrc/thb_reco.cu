@@ -13,6 +13,7 @@
 #include <cufft.h>
 #include <cmath>
 #include <cstring>
+#include <climits>
 #include <vector>
 #include "thb_context.h"
 #include "thb_pack.cuh"
@@ -350,6 +351,100 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
         atomicAdd(&A.sigM[row + rS], 1.0);
         atomicAdd(&A.sigN[row + rS], 1.0);
         atomicAdd(&A.svd[row + rS], 1.0);
+    }
+}
+
+// Reconstructor::symmetrizeF / symmetrizeT (src/Reconstructor.cpp:2676-2690) = SYMMETRIZE_FT (include/Geometry/
+// Transformation.h:105-131, 170-194): dst(v) = src(v) + sum_e src interpolated at R_e v, for every voxel v of the half volume
+// whose rotated position lies inside radius r.  F (complex, conjugated on the Hermitian fold) and T (real) of a voxel travel
+// together in the float4 accumulator, so one gather serves both.
+__global__ void __launch_bounds__(256) symmetrize_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int n, int nElem,
+                                                         const double* __restrict__ R, double r2)
+{
+    const int nColFT = n / 2 + 1;
+    const size_t total = (size_t)nColFT * n * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % nColFT);
+        const size_t row = idx / nColFT;
+        const int jm = (int)(row % n), km = (int)(row / n);
+        const double a = (double)i, b = (double)(jm < n / 2 ? jm : jm - n), c = (double)(km < n / 2 ? km : km - n);
+        float4 v = src[idx];
+        for (int e = 0; e < nElem; ++e) {
+            const double* m = R + 9 * e;                               // column-major, as Eigen's dmat33
+            const double ox = m[0] * a + m[3] * b + m[6] * c, oy = m[1] * a + m[4] * b + m[7] * c, oz = m[2] * a + m[5] * b + m[8] * c;
+            if (!(ox * ox + oy * oy + oz * oz < r2)) continue;
+            float x = (float)ox, y = (float)oy, z = (float)oz;
+            int x0, y0, z0;
+            float xd, yd, zd;
+            const bool conj = fold_floor(x, y, z, x0, y0, z0, xd, yd, zd);
+            float w[8];
+            tri_weights(xd, yd, zd, w);
+            int64_t off[4];
+            row_offsets(y0, z0, n, nColFT, off);
+            float re = 0.0f, im = 0.0f, t = 0.0f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float4 p = __ldg(src + off[cc] + x0), q = __ldg(src + off[cc] + x0 + 1);
+                re += p.x * w[2 * cc]; im += p.y * w[2 * cc]; t += p.z * w[2 * cc];
+                re += q.x * w[2 * cc + 1]; im += q.y * w[2 * cc + 1]; t += q.z * w[2 * cc + 1];
+            }
+            v.x += re; v.y += conj ? -im : im; v.z += t;
+        }
+        dst[idx] = v;
+    }
+}
+
+// Optimiser::normCorrection (src/Optimiser.cpp:6201-6393, OPTIMISER_NORM_MASK): norm[l] = sum over the half plane
+// {rL^2 <= |k|^2 < rNorm^2} of |masked image - ctf * translated slice at the image's best orientation|^2; the mirror pixel of
+// the i = 0 column counted twice, as in sigma_kernel
+__global__ void __launch_bounds__(256) norm_kernel(const SigmaArgs A, float rL2, float rN2, double* __restrict__ norm)
+{
+    __shared__ double red[8];
+    const int l = blockIdx.x, tid = threadIdx.x;
+    const int img = A.imgIdx ? A.imgIdx[l] : l;
+    const float2* __restrict__ vol = A.vols[A.slotE ? A.slotE[img] : 0];
+    double q[4] = {1.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < (A.mode2D ? 2 : 4); ++c) q[c] = A.quat[(A.mode2D ? 2 : 4) * l + c];
+    const Rot2 rot = make_rot2(q, A.mode2D);
+    const float tx = (float)A.tran[2 * l], ty = (float)A.tran[2 * l + 1];
+    float s = 0.0f;
+    for (int i = tid; i < A.PE; i += blockDim.x) {
+        const int4 c = A.pixE[i];
+        const float u = (float)(c.z * c.z + c.w * c.w);
+        if (!(u >= rL2 && u < rN2)) continue;
+        float x, y, z;
+        slice_coord(rot, (double)c.x, (double)c.y, x, y, z);
+        const float2 p = gather_lin(vol, A.vdim, A.pitch, x, y, z);
+        const float ph = translate_phase(c.z, c.w, tx / (float)A.N, ty / (float)A.N);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float cf = A.ctfE[(size_t)img * A.PE + i];
+        const float mx = (p.x * cs + p.y * sn) * cf, my = (p.y * cs - p.x * sn) * cf;
+        const float2 d = A.datE[(size_t)img * A.PE + i];
+        const float rx = d.x - mx, ry = d.y - my;
+        s += ((c.z == 0 && c.w > 0) ? 2.0f : 1.0f) * (rx * rx + ry * ry);
+    }
+    double v = (double)s;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        norm[l] = t;
+    }
+}
+
+// _img[l] *= s, _imgOri[l] *= s (src/Optimiser.cpp:6381-6391) on the resident stacks
+__global__ void scale_images_kernel(float2* __restrict__ datE, int PE, float2* __restrict__ datM, int PM, const int* __restrict__ imgIdx,
+                                    const float* __restrict__ scale)
+{
+    const int l = blockIdx.y;
+    const int img = imgIdx ? imgIdx[l] : l;
+    const float s = scale[l];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(PE, PM); i += gridDim.x * blockDim.x) {
+        if (datE && i < PE) { float2 v = datE[(size_t)img * PE + i]; datE[(size_t)img * PE + i] = make_float2(v.x * s, v.y * s); }
+        if (datM && i < PM) { float2 v = datM[(size_t)img * PM + i]; datM[(size_t)img * PM + i] = make_float2(v.x * s, v.y * s); }
     }
 }
 
@@ -727,6 +822,113 @@ int thb_sigma_accumulate(thb_ctx* ctx, int nImg, const int* imgIdx, const double
     THB_CUDA(ctx, cudaMemcpyAsync(sigM, dOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(sigN, dOut + nOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(svd, dOut + 2 * nOut, sizeof(double) * nOut, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_symmetrize(thb_ctx* ctx, int slot, int nElem, const double* R, double radius)
+{
+    if (!ctx) return THB_E_ARG;
+    if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "symmetrize: slot %d not allocated", slot);
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "symmetrize: MODE_3D only");
+    if (nElem < 0 || (nElem > 0 && !R) || !(radius > 0)) return set_error(ctx, THB_E_ARG, "symmetrize: bad arguments");
+    if (nElem == 0) return THB_OK;                                   // C1
+    Accum& a = ctx->accs[slot];
+    if (radius > a.vdim / 2 - 1) return set_error(ctx, THB_E_ARG, "symmetrize: radius %g reaches outside the accumulator (%d)", radius, a.vdim);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    float4* out = nullptr;
+    THB_CUDA(ctx, cudaMalloc(&out, a.nVox * sizeof(float4)));
+    double* dR = (double*)scratch(ctx, 0, sizeof(double) * 9 * (size_t)nElem);
+    if (!dR) { cudaFree(out); return THB_E_CUDA; }
+    THB_CUDA(ctx, cudaMemcpyAsync(dR, R, sizeof(double) * 9 * (size_t)nElem, cudaMemcpyHostToDevice, ctx->stream));
+    span_begin(ctx, KF_PACK);
+    symmetrize_kernel<<<ctx->smCount * 16, 256, 0, ctx->stream>>>(a.d, out, a.vdim, nElem, dR, radius * radius);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    // symmetrizeO (src/Reconstructor.cpp:2692-2716): O += sum_e R_e O, counter *= 1 + nElem
+    double O[3];
+    int cnt = 0;
+    THB_CUDA(ctx, cudaMemcpyAsync(O, ctx->dO + 3 * slot, sizeof(O), cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->dCounter + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double res[3] = {O[0], O[1], O[2]};
+    for (int e = 0; e < nElem; ++e) {
+        const double* m = R + 9 * e;
+        for (int k = 0; k < 3; ++k) res[k] += m[k] * O[0] + m[3 + k] * O[1] + m[6 + k] * O[2];
+    }
+    cnt *= 1 + nElem;
+    THB_CUDA(ctx, cudaMemcpyAsync(ctx->dO + 3 * slot, res, sizeof(res), cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(ctx->dCounter + slot, &cnt, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(a.d);
+    a.d = out;
+    return THB_OK;
+}
+
+int thb_norm_residual(thb_ctx* ctx, int nImg, const int* imgIdx, const double* quat, const double* tran, float rL, float rNorm,
+                      double* norm)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->pixE || !ctx->stackE.dat) return set_error(ctx, THB_E_STATE, "norm_residual: E pixel list / stack missing");
+    if (nImg <= 0 || !quat || !tran || !norm) return set_error(ctx, THB_E_ARG, "norm_residual: bad arguments");
+    if (!imgIdx && nImg > ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "norm_residual: nImg exceeds the stack");
+    if (imgIdx)
+        for (int l = 0; l < nImg; ++l)
+            if (imgIdx[l] < 0 || imgIdx[l] >= ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "norm_residual: imgIdx[%d] outside the stack", l);
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->vols[i].d) vdim = ctx->vols[i].vdim;
+    if (!vdim) return set_error(ctx, THB_E_STATE, "norm_residual: no projector volume");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int qc = ctx->mode2D ? 2 : 4;
+    double* buf = (double*)scratch(ctx, 0, sizeof(double) * (size_t)nImg * (qc + 3) + sizeof(int) * (size_t)nImg);
+    if (!buf) return THB_E_CUDA;
+    double* dQ = buf; double* dT = dQ + (size_t)qc * nImg; double* dN = dT + 2 * (size_t)nImg;
+    int* dIdx = (int*)(dN + nImg);
+    THB_CUDA(ctx, cudaMemcpyAsync(dQ, quat, sizeof(double) * qc * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dT, tran, sizeof(double) * 2 * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(dIdx, imgIdx, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    SigmaArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < THB_MAX_SLOTS; ++i) a.vols[i] = ctx->vols[i].d;
+    a.vdim = vdim; a.pitch = (vdim / 2 + 2 + 3) & ~3; a.N = ctx->N; a.mode2D = ctx->mode2D;
+    a.datE = ctx->stackE.dat; a.ctfE = ctx->stackE.ctf; a.slotE = ctx->stackE.slot; a.pixE = ctx->pixE; a.PE = ctx->nPxlE;
+    a.imgIdx = imgIdx ? dIdx : nullptr; a.quat = dQ; a.tran = dT;
+    span_begin(ctx, KF_PACK);
+    norm_kernel<<<nImg, 256, 0, ctx->stream>>>(a, rL * rL, rNorm * rNorm, dN);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaMemcpyAsync(norm, dN, sizeof(double) * nImg, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_scale_images(thb_ctx* ctx, int nImg, const int* imgIdx, const float* scale)
+{
+    if (!ctx) return THB_E_ARG;
+    if (nImg <= 0 || !scale) return set_error(ctx, THB_E_ARG, "scale_images: bad arguments");
+    if (!ctx->stackE.dat && !ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "scale_images: no resident stack");
+    const int cap = std::min(ctx->stackE.dat ? ctx->stackE.nImg : INT_MAX, ctx->stackM.dat ? ctx->stackM.nImg : INT_MAX);
+    if (!imgIdx && nImg > cap) return set_error(ctx, THB_E_ARG, "scale_images: nImg exceeds the stacks");
+    if (imgIdx)
+        for (int l = 0; l < nImg; ++l)
+            if (imgIdx[l] < 0 || imgIdx[l] >= cap) return set_error(ctx, THB_E_ARG, "scale_images: imgIdx[%d] outside the stacks", l);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    float* dS = (float*)scratch(ctx, 0, (sizeof(float) + sizeof(int)) * (size_t)nImg);
+    if (!dS) return THB_E_CUDA;
+    int* dIdx = (int*)(dS + nImg);
+    THB_CUDA(ctx, cudaMemcpyAsync(dS, scale, sizeof(float) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(dIdx, imgIdx, sizeof(int) * nImg, cudaMemcpyHostToDevice, ctx->stream));
+    const int P = std::max(ctx->stackE.dat ? ctx->nPxlE : 0, ctx->stackM.dat ? ctx->nPxlM : 0);
+    dim3 grid(std::min((P + 255) / 256, 64), nImg);
+    span_begin(ctx, KF_PACK);
+    scale_images_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->stackE.dat, ctx->stackE.dat ? ctx->nPxlE : 0, ctx->stackM.dat,
+                                                       ctx->stackM.dat ? ctx->nPxlM : 0, imgIdx ? dIdx : nullptr, dS);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
