@@ -294,6 +294,11 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         a4 = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_minb", 2)
         ctx.set_option("quad_oct", 1)
+        ctx.set_option("expect_impl", 4)      # two lanes per sample (half the L1 tag cycles), cell and quad layouts
+        p4 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 0)
+        p4q = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_impl", 2)      # TMA-staged shared-memory box
         c = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
@@ -306,6 +311,9 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     tol = 2e-6 * np.abs(b["logL"]).max() + 1e-4
     assert np.array_equal(a["logL"], a3["logL"]) and np.array_equal(a["logL"], a4["logL"])   # layouts / occupancy: same bits
     assert np.abs(a["logL"] - b["logL"]).max() <= 2 * tol
+    assert np.array_equal(p4["logL"], p4q["logL"])
+    assert np.abs(p4["logL"] - a["logL"]).max() <= tol
+    assert np.allclose(p4["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p4["base"] - a["base"]).max() <= tol
     assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
     assert np.abs(c["logL"] - a["logL"]).max() <= tol
     for l in (0, nImg - 1):
