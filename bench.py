@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--mlt", type=int, default=9)
     ap.add_argument("--mreco", type=int, default=100)
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic particles generated on the host")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="particles of the CPU baseline sample (0 = one per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles of the CPU baseline sample (0 = one per host thread per step for --impl reference, three for cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -147,7 +147,9 @@ def run_reference(args, wl, steps, warmup, rank, world, sample_only=False):
     N, pf = wl["N"], wl["pf"]
     pixE = ref.pixel_list(N, pf, float(wl["r"]), wl["rL"])
     pixM = ref.pixel_list(N, pf, float(wl["r"]), 0.0)
-    nS = args.cpu_sample or cores
+    # bounded sample: the reference arm runs one particle per host thread per step, the cpu_baseline leg of our arm runs
+    # one pass over three per thread (10-20 s of CPU work on the 16-core GPU box)
+    nS = args.cpu_sample or (3 * cores if sample_only else cores)
     rng = np.random.default_rng(5)
     vol = synth.padded_ft(synth.phantom(N, 30), pf)
     P = ref.Projector(pf)
