@@ -299,6 +299,11 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         ctx.set_option("quad_oct", 0)
         p4q = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("quad_oct", 1)
+        ctx.set_option("expect_impl", 5)      # pixels on the lanes (DRAM page locality), cell and quad layouts
+        p5 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 0)
+        p5q = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_impl", 2)      # TMA-staged shared-memory box
         c = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
@@ -314,6 +319,9 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     assert np.array_equal(p4["logL"], p4q["logL"])
     assert np.abs(p4["logL"] - a["logL"]).max() <= tol
     assert np.allclose(p4["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p4["base"] - a["base"]).max() <= tol
+    assert np.array_equal(p5["logL"], p5q["logL"])
+    assert np.abs(p5["logL"] - a["logL"]).max() <= tol
+    assert np.allclose(p5["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p5["base"] - a["base"]).max() <= tol
     assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
     assert np.abs(c["logL"] - a["logL"]).max() <= tol
     for l in (0, nImg - 1):

@@ -11,6 +11,7 @@
 #include "thb_expect2.cuh"
 #include "thb_expect3.cuh"
 #include "thb_expect4.cuh"
+#include "thb_expect5.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -160,9 +161,16 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
         a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
         if (!a.work) return THB_E_CUDA;
     }
-    const size_t smem = E3_SMEM_BYTES + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
+    const size_t smem = (ctx->expectImpl == 5 ? E5_SMEM_BYTES : E3_SMEM_BYTES) + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
-    if (ctx->expectImpl == 4) {
+    if (ctx->expectImpl == 5) {
+        if (ctx->mode2D)
+            expect_pix_kernel<false, true><<<a.nAct, E5_THREADS, smem, ctx->stream>>>(a);
+        else if (ctx->quadOct)
+            expect_pix_kernel<true, false><<<a.nAct, E5_THREADS, smem, ctx->stream>>>(a);
+        else
+            expect_pix_kernel<false, false><<<a.nAct, E5_THREADS, smem, ctx->stream>>>(a);
+    } else if (ctx->expectImpl == 4) {
         if (ctx->mode2D)
             expect_pair_kernel<false, true><<<a.nAct, E4_THREADS, smem, ctx->stream>>>(a);
         else if (ctx->quadOct)
@@ -221,7 +229,7 @@ int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
     if (a.nAct <= 0) return THB_OK;
     a.mode2D = ctx->mode2D;
     if (!ctx->mode2D) a.slotAll = -1;
-    if (ctx->expectImpl == 3 || ctx->expectImpl == 4) return launch_expect_v3(ctx, a);
+    if (ctx->expectImpl >= 3) return launch_expect_v3(ctx, a);
     if (ctx->expectImpl == 2 && !ctx->mode2D) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)
@@ -299,7 +307,7 @@ int thb_create(thb_ctx** out, int device)
     thb_ctx* ctx = new thb_ctx();
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
-    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(5, atoi(e)));
     if (const char* e = getenv("THB_QUAD_BRICK")) ctx->quadBrick = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("THB_QUAD_OCT")) ctx->quadOct = atoi(e) != 0;
     if (const char* e = getenv("THB_SORT_ROT")) ctx->sortRot = atoi(e) != 0;
@@ -402,7 +410,7 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
 {
     if (!ctx || !key) return THB_E_ARG;
     if (!strcmp(key, "expect_impl")) {
-        if (value < 1 || value > 4) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1, 2, 3 or 4");
+        if (value < 1 || value > 5) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 .. 5");
         ctx->expectImpl = value;
         return THB_OK;
     }
