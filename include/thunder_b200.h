@@ -118,8 +118,10 @@ int thb_set_volume(thb_ctx* ctx, int slot, const float* volFT, int vdim);
  * (thb_reco_download returns F, T as [vdim][vdim/2+1], O as (ox, oy, 0)), thb_expect_scan compares EVERY image with class
  * `slot`, and thb_insert_classes scatters each draw into the accumulator of its own class.  Same kernels as MODE_3D:
  * bilinear gather / scatter = the trilinear cell of a two-plane volume at z = 0 (Projector::project src/Projector.cpp:337-354,
- * Image::getByInterpolationFT src/Image/Image.cpp:345-368, Reconstructor::insertP src/Reconstructor.cpp:708-780).  The device
- * particle filter, thb_reconstruct and thb_set_projectee are MODE_3D only.  Switching the mode drops volumes and accumulators. */
+ * Image::getByInterpolationFT src/Image/Image.cpp:345-368, Reconstructor::insertP src/Reconstructor.cpp:708-780).
+ * thb_reconstruct / thb_set_projectee work on images in this mode (the MODE_2D branches of Reconstructor::reconstruct,
+ * Projector::setProjectee(Image) src/Projector.cpp:97-121: dstReal / volReal are N x N).  The device particle filter and
+ * thb_symmetrize are MODE_3D only.  Switching the mode drops volumes and accumulators. */
 enum { THB_MODE_3D = 0, THB_MODE_2D = 1 };
 int thb_set_mode(thb_ctx* ctx, int mode);
 int thb_get_mode(const thb_ctx* ctx);

@@ -471,6 +471,48 @@ void ref_reco_set_O(void* h, const double* O3, int counter)
     r->reco._counter = counter;
 }
 
+// MODE_2D twins of ref_reco_set / ref_reco_reconstruct and of Projector::setProjectee(Image) (src/Projector.cpp:97-121)
+void ref_reco2d_set(void* h, const float* F, const float* T)
+{
+    RefReco* r = (RefReco*)h;
+    size_t n = r->reco._F2D.sizeFT();
+    memcpy(&r->reco._F2D[0], F, n * sizeof(Complex));
+    for (size_t i = 0; i < n; i++) r->reco._T2D[i] = COMPLEX(T[i], 0);
+}
+
+int ref_reco2d_reconstruct(void* h, float* dst, int gridCorr, int joinHalf, const float* fsc, int nFsc, int nThread)
+{
+    RefReco* r = (RefReco*)h;
+    r->reco.setGridCorr(gridCorr != 0);
+    r->reco.setJoinHalf(joinHalf != 0);
+    r->reco.setMAP(fsc != NULL);
+    if (fsc)
+    {
+        vec f(nFsc);
+        for (int i = 0; i < nFsc; i++) f(i) = fsc[i];
+        r->reco.setFSC(f);
+    }
+    Volume v;
+    r->reco.reconstruct(v, nThread);                    // N x N x 1 in MODE_2D
+    if (dst) memcpy(dst, &v(0), v.sizeRL() * sizeof(RFLOAT));
+    return (int)v.nColRL();
+}
+
+// real-space N x N image -> FFT -> Projector::setProjectee(Image); returns the padded dimension, out = padded FT
+int ref_projector2d_set_from_real(void* h, const float* imgRL, int N, float* outFT)
+{
+    RefProjector* p = (RefProjector*)h;
+    Image im(N, N, RL_SPACE);
+    for (size_t i = 0; i < im.sizeRL(); i++) im(i) = imgRL[i];
+    FFT fft;
+    fft.fw(im, 1);
+    im.clearRL();
+    p->proj.setProjectee(im.copyImage(), 1);
+    const int n = (int)p->proj._projectee2D.nRowFT();
+    if (outFT) memcpy(outFT, &p->proj._projectee2D[0], p->proj._projectee2D.sizeFT() * sizeof(Complex));
+    return n;
+}
+
 // image loop of Optimiser::normCorrection (src/Optimiser.cpp:6201-6350, MODE_3D, OPTIMISER_NORM_MASK, no CTF search) with the
 // reference's functions: norm[l] = sum_{rL^2 <= |k|^2 < rNorm^2} |_img[l] - CTF * project(rot, tran)|^2 (RFLOAT accumulator)
 void ref_norm_residual(void* projH, int nImg, int N, float rL, float rNorm, const float* imgFT, const double* quat,

@@ -68,6 +68,11 @@ def lib():
         L.ref_reco2d_pad_size.argtypes = [_p]
         L.ref_reco2d_insert_draw.argtypes = [_p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _f]
         L.ref_reco2d_get.argtypes = [_p, _p, _p, _p, _p]
+        L.ref_reco2d_set.argtypes = [_p, _p, _p]
+        L.ref_reco2d_reconstruct.restype = _i
+        L.ref_reco2d_reconstruct.argtypes = [_p, _p, _i, _i, _p, _i, _i]
+        L.ref_projector2d_set_from_real.restype = _i
+        L.ref_projector2d_set_from_real.argtypes = [_p, _p, _i, _p]
         L.ref_symmetry_elements.restype = _i
         L.ref_symmetry_elements.argtypes = [C.c_char_p, _p, _i]
         L.ref_reco_symmetrize.argtypes = [_p, C.c_char_p, _i]
@@ -399,6 +404,15 @@ class Projector2D:
             lib().ref_projector_destroy(self.h)
             self.h = None
 
+    def set_from_real(self, img, pf):
+        """Projector::setProjectee(Image): pad, grid correction, FFT; returns the padded FT [pf N][pf N / 2 + 1]"""
+        img = np.ascontiguousarray(img, np.float32)
+        N = img.shape[0]
+        out = np.empty((N * pf, N * pf // 2 + 1), np.complex64)
+        n = lib().ref_projector2d_set_from_real(self.h, _ptr(img), N, _ptr(out))
+        assert n == N * pf
+        return out
+
     def project(self, cs, iCol, iRow):
         out = np.empty(len(iCol), np.complex64)
         cs = np.ascontiguousarray(cs, np.float64)
@@ -431,6 +445,21 @@ class Reconstructor2D:
         off = np.ascontiguousarray(off, np.float64) if off is not None else None
         lib().ref_reco2d_insert_draw(self.h, _ptr(dat), _ptr(ctf), self.N, _ptr(iCol), _ptr(iRow), len(iCol), _ptr(cs), _ptr(tran),
                                      _ptr(off) if off is not None else None, float(w))
+
+    def set(self, F, T):
+        F = np.ascontiguousarray(F, np.complex64); T = np.ascontiguousarray(T, np.float32)
+        lib().ref_reco2d_set(self.h, _ptr(F), _ptr(T))
+
+    def prepareTF(self):
+        lib().ref_reco_prepareTF(self.h, 1)
+
+    def reconstruct(self, gridCorr=True, joinHalf=False, fsc=None):
+        """Reconstructor::reconstruct in MODE_2D -> the N x N class average (origin at index 0)"""
+        out = np.empty((self.N, self.N), np.float32)
+        f = None if fsc is None else np.ascontiguousarray(fsc, np.float32)
+        n = lib().ref_reco2d_reconstruct(self.h, _ptr(out), int(gridCorr), int(joinHalf), _ptr(f), 0 if f is None else len(f), 1)
+        assert n == self.N
+        return out
 
     def get(self):
         m = self.pad_size()

@@ -215,11 +215,48 @@ def test_insert_2d_matches_reference(ctx2d, per_draw_classes):
 
 
 @pytest.mark.gpu
+def test_reconstruct_and_set_projectee_2d(ctx2d):
+    """class averages on the device: thb_reconstruct / thb_set_projectee in MODE_2D == Reconstructor::reconstruct (MODE_2D
+    branches) / Projector::setProjectee(Image) on the same accumulators"""
+    ref = _ref()
+    s = _setup(nImg=160, seed=21)
+    N, pf, rng = s["N"], s["pf"], s["rng"]
+    _load(ctx2d, s)
+    ctx2d.reco_alloc(0, N * pf)
+    mReco = 6
+    cs = _unit(rng.uniform(-np.pi, np.pi, (s["nImg"], mReco))); t = rng.normal(size=(s["nImg"], mReco, 2))
+    ctx2d.insert(np.full(s["nImg"], 1.0 / mReco, np.float32), cs, t)
+    acc = ctx2d.reco_download(0)
+    R = ref.Reconstructor2D(N, N, pf)
+    fsc = np.linspace(0.99, 0.2, N // 2 + 1).astype(np.float32)
+    for gridCorr, f, joinHalf in ((True, None, False), (False, None, False), (True, fsc, True)):
+        ctx2d.reco_upload(0, acc["F"], acc["T"])
+        got, nit = ctx2d.reconstruct(0, N, pf, gridCorr=gridCorr, joinHalf=joinHalf, fsc=f)
+        assert got.shape == (N, N) and (nit > 0) == gridCorr
+        R.set(acc["F"], acc["T"])
+        R.prepareTF()
+        want = R.reconstruct(gridCorr=gridCorr, joinHalf=joinHalf, fsc=f)
+        assert np.linalg.norm(got - want) <= 2e-5 * np.linalg.norm(want), (gridCorr, joinHalf)
+    # the projector reference rebuilt from the class average kept on the device, and from an explicit image
+    ctx2d.set_projectee(1, None, N, pf)
+    P = ref.Projector2D(pf, np.zeros((N * pf, N * pf // 2 + 1), np.complex64))
+    want_ft = P.set_from_real(got, pf)
+    assert np.linalg.norm(ctx2d.get_volume(1) - want_ft) <= 5e-6 * np.linalg.norm(want_ft)
+    ctx2d.set_projectee(2, want, N, pf)
+    assert np.linalg.norm(ctx2d.get_volume(2) - P.set_from_real(want, pf)) <= 5e-6 * np.linalg.norm(want_ft)
+    sl = ctx2d.project(1, _unit(np.array([0.4])))
+    assert np.abs(sl[0] - P.project(_unit(0.4), s["pixE"]["iCol"], s["pixE"]["iRow"])).max() <= 1e-5 * np.abs(sl).max()
+    P.close(); R.close()
+
+
+@pytest.mark.gpu
 def test_mode_switch_and_guards(ctx2d):
     s = _setup(nImg=2)
     _load(ctx2d, s)
     with pytest.raises(capi.ThbError):
-        ctx2d.set_projectee(0, None, s["N"], s["pf"])
+        ctx2d.pf_load(capi.PFParams(mLR=9, mLT=9, transS=2.0, transQ=0.01, perturbFactorL=2.0, perturbFactorS=0.5, minPhase=3, maxPhase=10,
+                                    fixedPhases=0, decreaseFactor=0.95, noDecreaseLimit=1, seed=1),
+                      np.tile([1.0, 0, 0, 0], (2, 1)), np.full((2, 3), 1e-4), np.zeros((2, 2)), np.ones((2, 2)))
     ctx2d.set_mode(capi.MODE_3D)                                  # drops the 2D references
     with pytest.raises(capi.ThbError):
         ctx2d.project(0, np.array([[1.0, 0, 0, 0]]))

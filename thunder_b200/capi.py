@@ -350,14 +350,14 @@ class Context:
 
     def reconstruct(self, slot, N, pf, a=1.9, alpha=15.0, gridCorr=True, joinHalf=False, fsc=None, normalise=True, want_volume=True):
         fsc = _arr(fsc, np.float32)
-        out = np.empty((N, N, N), np.float32) if want_volume else None
+        out = np.empty((N, N) if getattr(self, "mode2D", False) else (N, N, N), np.float32) if want_volume else None
         nit = C.c_int(0)
         self._chk(self.lib.thb_reconstruct(self.h, slot, N, pf, a, alpha, int(gridCorr), int(joinHalf), _ptr(fsc),
                                            0 if fsc is None else len(fsc), int(normalise), _ptr(out), C.byref(nit)))
         return out, nit.value
 
     def set_projectee(self, slot, vol, N, pf):
-        vol = _arr(vol, np.float32, (N, N, N)) if vol is not None else None
+        vol = _arr(vol, np.float32, (N, N) if getattr(self, "mode2D", False) else (N, N, N)) if vol is not None else None
         self._chk(self.lib.thb_set_projectee(self.h, slot, _ptr(vol), N, pf))
         self.vdim[slot] = N * pf
 

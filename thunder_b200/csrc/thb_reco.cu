@@ -78,10 +78,10 @@ __global__ void reco_init_kernel(float4* acc, float* W, size_t nVox, int m, int 
 // not keep them conjugate.  FFTW's c2r (the reference) transforms y,z first and then drops the imaginary part of
 // those two planes, which equals replacing P(0,j,k) by (P(0,j,k) + conj P(0,-j,-k)) / 2.  cuFFT may take another
 // route for some sizes, so the planes are made consistent explicitly: identical to FFTW for any input.
-__global__ void reco_hermitian_planes_kernel(float2* C, int m)
+__global__ void reco_hermitian_planes_kernel(float2* C, int m, int nz)      // nz = m, or 1 for an image (MODE_2D)
 {
     const int nc = m / 2 + 1;
-    const size_t plane = (size_t)m * m;
+    const size_t plane = (size_t)m * nz;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * plane; t += (size_t)gridDim.x * blockDim.x) {
         const int i = t < plane ? 0 : m / 2;
         const size_t r = t < plane ? t : t - plane;
@@ -103,9 +103,9 @@ __global__ void reco_make_c_kernel(const float4* acc, const float* W, float2* C,
 }
 
 // real space: C(x) *= kernelRL(|x|^2 / (N pf)^2) / nf, with the 1/m^3 of the backward transform
-__global__ void reco_kernel_rl_kernel(float* c, int m, const float* tab, float tabStep, float nf, float M2, float invVol)
+__global__ void reco_kernel_rl_kernel(float* c, int m, int nz, const float* tab, float tabStep, float nf, float M2, float invVol)
 {
-    const size_t total = (size_t)m * m * m;
+    const size_t total = (size_t)m * m * nz;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int i = signed_coord((int)(idx % m), m);
         const size_t row = idx / m;
@@ -163,9 +163,9 @@ __global__ void reco_pad_ft_kernel(const float4* acc, const float* W, size_t nVo
 }
 
 // dst (N^3) = central part of padReal (M^3, scaled by 1/M^3) / TIK_RL(|x| / (pf N))
-__global__ void reco_extract_kernel(const float* padReal, int M, int N, int pf, float invVol, float* dst)
+__global__ void reco_extract_kernel(const float* padReal, int M, int N, int nz, int pf, float invVol, float* dst)
 {
-    const size_t total = (size_t)N * N * N;
+    const size_t total = (size_t)N * N * nz;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int i = signed_coord((int)(idx % N), N);
         const size_t row = idx / N;
@@ -179,9 +179,9 @@ __global__ void reco_extract_kernel(const float* padReal, int M, int N, int pf, 
 }
 
 // setProjectee: pad (n^3, zeroed) <- vol (N^3) at the same signed coordinates, / TIK_RL(|x| / (pf n))
-__global__ void proj_pad_rl_kernel(const float* vol, int N, int n, int pf, float* pad)
+__global__ void proj_pad_rl_kernel(const float* vol, int N, int nz, int n, int pf, float* pad)
 {
-    const size_t total = (size_t)N * N * N;
+    const size_t total = (size_t)N * N * nz;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int i = signed_coord((int)(idx % N), N);
         const size_t row = idx / N;
@@ -486,16 +486,16 @@ static double mkb_rl_r2(double r2, double a, double alpha)
 
 struct RecoState {
     cufftHandle planC2R = 0, planR2C = 0;
-    int planDim = 0;
+    int planDim = 0, planRank = 0;
     cufftHandle planProj = 0;
-    int projDim = 0, projPitch = 0;
+    int projDim = 0, projPitch = 0, projRank = 0;
     float* dTab = nullptr;
     double tabA = -1, tabAlpha = -1;
     float nf = 1.0f;
     float* dVol = nullptr;      // last reconstruction, N^3 real
     cufftHandle planImgC2R = 0, planImgR2C = 0;
     int imgN = 0, imgBatch = 0;
-    int volN = 0;
+    int volN = 0, volRank = 3;
 };
 
 static RecoState* reco_state(thb_ctx* ctx)
@@ -519,14 +519,20 @@ void reco_free(thb_ctx* ctx)
     ctx->reco = nullptr;
 }
 
-static int ensure_plans(thb_ctx* ctx, RecoState* s, int m)
+static int ensure_plans(thb_ctx* ctx, RecoState* s, int m, int rank)
 {
-    if (s->planDim == m) return THB_OK;
+    if (s->planDim == m && s->planRank == rank) return THB_OK;
     if (s->planC2R) { cufftDestroy(s->planC2R); s->planC2R = 0; }
     if (s->planR2C) { cufftDestroy(s->planR2C); s->planR2C = 0; }
     s->planDim = 0;
-    THB_FFT(ctx, cufftPlan3d(&s->planC2R, m, m, m, CUFFT_C2R));
-    THB_FFT(ctx, cufftPlan3d(&s->planR2C, m, m, m, CUFFT_R2C));
+    if (rank == 3) {
+        THB_FFT(ctx, cufftPlan3d(&s->planC2R, m, m, m, CUFFT_C2R));
+        THB_FFT(ctx, cufftPlan3d(&s->planR2C, m, m, m, CUFFT_R2C));
+    } else {
+        THB_FFT(ctx, cufftPlan2d(&s->planC2R, m, m, CUFFT_C2R));
+        THB_FFT(ctx, cufftPlan2d(&s->planR2C, m, m, CUFFT_R2C));
+    }
+    s->planRank = rank;
     THB_FFT(ctx, cufftSetStream(s->planC2R, ctx->stream));
     THB_FFT(ctx, cufftSetStream(s->planR2C, ctx->stream));
     s->planDim = m;
@@ -558,9 +564,10 @@ int thb_reco_upload(thb_ctx* ctx, int slot, const float* F, const float* T)
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reco_upload: slot %d not allocated", slot);
     if (!F || !T) return set_error(ctx, THB_E_ARG, "reco_upload: NULL arrays");
-    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "reco_upload: MODE_3D only");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const Accum& a = ctx->accs[slot];
+    const Accum& a0 = ctx->accs[slot];
+    struct { float4* d; size_t nVox; } a = {a0.d, ctx->mode2D ? a0.nVox / 2 : a0.nVox};     // MODE_2D: F, T are images = plane 0
+    if (ctx->mode2D) THB_CUDA(ctx, cudaMemsetAsync(a0.d, 0, a0.nVox * sizeof(float4), ctx->stream));
     float2* dF = (float2*)scratch(ctx, 2, a.nVox * sizeof(float2));
     float* dT = (float*)scratch(ctx, 3, a.nVox * sizeof(float));
     if (!dF || !dT) return THB_E_CUDA;
@@ -578,7 +585,9 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
 {
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->accs[slot].d) return set_error(ctx, THB_E_STATE, "reconstruct: slot %d not allocated", slot);
-    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "reconstruct: MODE_3D only");
+    // MODE_2D: the same steps on images (Reconstructor::reconstruct, the MODE_2D branches of src/Reconstructor.cpp:1129-1831):
+    // plane 0 of the two-plane accumulator, 2D transforms, dstReal = the N x N class average
+    const int rank = ctx->mode2D ? 2 : 3;
     const Accum& acc = ctx->accs[slot];
     const int m = acc.vdim;
     if (N <= 0 || (N & 1) || pf <= 0 || m % pf || m / pf > N) return set_error(ctx, THB_E_ARG, "reconstruct: accumulator dimension %d does not fit N = %d, pf = %d", m, N, pf);
@@ -588,8 +597,9 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
     const int size = m / pf, M = N * pf;
     const int maxRadius = size / 2 - (int)std::ceil(a);       // Reconstructor::init, src/Reconstructor.cpp:88
     if (maxRadius <= 0) return set_error(ctx, THB_E_ARG, "reconstruct: volume too small for the kernel radius");
-    const size_t nVox = acc.nVox, nReal = (size_t)m * m * m;
-    const size_t nVoxM = (size_t)(M / 2 + 1) * M * M, nRealM = (size_t)M * M * M;
+    const int mz = rank == 3 ? m : 1, Mz = rank == 3 ? M : 1, Nz = rank == 3 ? N : 1;
+    const size_t nVox = rank == 3 ? acc.nVox : acc.nVox / 2, nReal = (size_t)m * m * mz;
+    const size_t nVoxM = (size_t)(M / 2 + 1) * M * Mz, nRealM = (size_t)M * M * Mz;
     int rc;
     if ((rc = ensure_table(ctx, s, a, alpha))) return rc;
     float* W = (float*)scratch(ctx, 1, nVox * sizeof(float));
@@ -610,14 +620,14 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
     ctx->launches++;
     int nIter = 0;
     if (gridCorr) {
-        if ((rc = ensure_plans(ctx, s, m))) return rc;
+        if ((rc = ensure_plans(ctx, s, m, rank))) return rc;
         float diffC = 3.40282347e38f, diffPrev;
         int noDecrease = 0;
         for (int it = 0; it < 30; ++it) {                     // MAX_N_ITER_BALANCE
             reco_make_c_kernel<<<grid, 256, 0, ctx->stream>>>(acc.d, W, C, nVox);
-            reco_hermitian_planes_kernel<<<grid, 256, 0, ctx->stream>>>(C, m);
+            reco_hermitian_planes_kernel<<<grid, 256, 0, ctx->stream>>>(C, m, mz);
             THB_FFT(ctx, cufftExecC2R(s->planC2R, reinterpret_cast<cufftComplex*>(C), R));
-            reco_kernel_rl_kernel<<<grid, 256, 0, ctx->stream>>>(R, m, s->dTab, 1.0f / (float)RECO_TAB_N, s->nf, (float)M * (float)M,
+            reco_kernel_rl_kernel<<<grid, 256, 0, ctx->stream>>>(R, m, mz, s->dTab, 1.0f / (float)RECO_TAB_N, s->nf, (float)M * (float)M,
                                                                  (float)(1.0 / (double)nReal));
             THB_FFT(ctx, cufftExecR2C(s->planR2C, R, reinterpret_cast<cufftComplex*>(C)));
             THB_CUDA(ctx, cudaMemsetAsync(dDiff, 0, sizeof(int), ctx->stream));
@@ -637,23 +647,24 @@ int thb_reconstruct(thb_ctx* ctx, int slot, int N, int pf, double a, double alph
         ctx->launches++;
     }
     // padDst = F * W on the (N pf)^3 grid, inverse transform, crop, sinc^2 correction
-    if ((rc = ensure_plans(ctx, s, M))) return rc;
+    if ((rc = ensure_plans(ctx, s, M, rank))) return rc;
     THB_CUDA(ctx, cudaMemsetAsync(C, 0, nVoxM * sizeof(float2), ctx->stream));
     reco_pad_ft_kernel<<<grid, 256, 0, ctx->stream>>>(acc.d, W, nVox, m, M, pf, maxRadius, C);
-    reco_hermitian_planes_kernel<<<grid, 256, 0, ctx->stream>>>(C, M);
+    reco_hermitian_planes_kernel<<<grid, 256, 0, ctx->stream>>>(C, M, Mz);
     THB_FFT(ctx, cufftExecC2R(s->planC2R, reinterpret_cast<cufftComplex*>(C), R));
-    if (s->volN != N) {
+    if (s->volN != N || s->volRank != rank) {
         cudaFree(s->dVol);
         s->dVol = nullptr;
         s->volN = 0;
-        THB_CUDA(ctx, cudaMalloc(&s->dVol, sizeof(float) * (size_t)N * N * N));
+        THB_CUDA(ctx, cudaMalloc(&s->dVol, sizeof(float) * (size_t)N * N * Nz));
         s->volN = N;
+        s->volRank = rank;
     }
-    reco_extract_kernel<<<grid, 256, 0, ctx->stream>>>(R, M, N, pf, (float)(1.0 / (double)nRealM), s->dVol);
+    reco_extract_kernel<<<grid, 256, 0, ctx->stream>>>(R, M, N, Nz, pf, (float)(1.0 / (double)nRealM), s->dVol);
     ctx->launches += 3;
     span_end(ctx);
     THB_CUDA(ctx, cudaGetLastError());
-    if (dstReal) THB_CUDA(ctx, cudaMemcpyAsync(dstReal, s->dVol, sizeof(float) * (size_t)N * N * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dstReal) THB_CUDA(ctx, cudaMemcpyAsync(dstReal, s->dVol, sizeof(float) * (size_t)N * N * Nz, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (nIterOut) *nIterOut = nIter;
     return THB_OK;
@@ -937,10 +948,13 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
 {
     if (!ctx) return THB_E_ARG;
     if (slot < 0 || slot >= THB_MAX_SLOTS || N <= 0 || (N & 1) || pf <= 0) return set_error(ctx, THB_E_ARG, "set_projectee: bad arguments");
-    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "set_projectee: MODE_3D only");
+    // MODE_2D: Projector::setProjectee(Image) (src/Projector.cpp:97-121): volReal = the N x N class average, the result is
+    // plane 0 of the two-plane reference
+    const int rank = ctx->mode2D ? 2 : 3;
+    const int Nz = rank == 3 ? N : 1;
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     RecoState* s = reco_state(ctx);
-    const size_t nIn = (size_t)N * N * N;
+    const size_t nIn = (size_t)N * N * Nz;
     const float* dIn = nullptr;
     if (volReal) {
         float* tmp = (float*)scratch(ctx, 1, nIn * sizeof(float));
@@ -948,7 +962,7 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
         THB_CUDA(ctx, cudaMemcpyAsync(tmp, volReal, nIn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         dIn = tmp;
     } else {
-        if (!s->dVol || s->volN != N) return set_error(ctx, THB_E_STATE, "set_projectee: no reconstruction of edge %d on the device", N);
+        if (!s->dVol || s->volN != N || s->volRank != rank) return set_error(ctx, THB_E_STATE, "set_projectee: no reconstruction of edge %d on the device", N);
         dIn = s->dVol;
     }
     const int n = N * pf;
@@ -959,7 +973,8 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
         cudaFree(v.quad);
         v.quad = nullptr;
     }
-    const size_t rows = (size_t)n * n;
+    const int nz = rank == 3 ? n : 1;
+    const size_t rows = rank == 3 ? (size_t)n * n : 2 * (size_t)n;          // MODE_2D: two planes, the second stays zero
     if (v.vdim != n) {
         cudaFree(v.d);
         v.d = nullptr;
@@ -969,20 +984,26 @@ int thb_set_projectee(thb_ctx* ctx, int slot, const float* volReal, int N, int p
         v.pitch = pitch;
     }
     THB_CUDA(ctx, cudaMemsetAsync(v.d, 0, rows * pitch * sizeof(float2), ctx->stream));
-    float* R = (float*)scratch(ctx, 3, (size_t)n * n * n * sizeof(float));
+    float* R = (float*)scratch(ctx, 3, (size_t)n * n * nz * sizeof(float));
     if (!R) return THB_E_CUDA;
-    THB_CUDA(ctx, cudaMemsetAsync(R, 0, (size_t)n * n * n * sizeof(float), ctx->stream));
+    THB_CUDA(ctx, cudaMemsetAsync(R, 0, (size_t)n * n * nz * sizeof(float), ctx->stream));
     span_begin(ctx, KF_PACK);
-    proj_pad_rl_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(dIn, N, n, pf, R);
+    proj_pad_rl_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(dIn, N, Nz, n, pf, R);
     ctx->launches++;
-    if (s->projDim != n || s->projPitch != pitch) {
+    if (s->projDim != n || s->projPitch != pitch || s->projRank != rank) {
         if (s->planProj) { cufftDestroy(s->planProj); s->planProj = 0; }
         s->projDim = 0;
-        int dims[3] = {n, n, n}, inembed[3] = {n, n, n}, onembed[3] = {n, n, pitch};
-        THB_FFT(ctx, cufftPlanMany(&s->planProj, 3, dims, inembed, 1, n * n * n, onembed, 1, n * n * pitch, CUFFT_R2C, 1));
+        if (rank == 3) {
+            int dims[3] = {n, n, n}, inembed[3] = {n, n, n}, onembed[3] = {n, n, pitch};
+            THB_FFT(ctx, cufftPlanMany(&s->planProj, 3, dims, inembed, 1, n * n * n, onembed, 1, n * n * pitch, CUFFT_R2C, 1));
+        } else {
+            int dims[2] = {n, n}, inembed[2] = {n, n}, onembed[2] = {n, pitch};
+            THB_FFT(ctx, cufftPlanMany(&s->planProj, 2, dims, inembed, 1, n * n, onembed, 1, n * pitch, CUFFT_R2C, 1));
+        }
         THB_FFT(ctx, cufftSetStream(s->planProj, ctx->stream));
         s->projDim = n;
         s->projPitch = pitch;
+        s->projRank = rank;
     }
     THB_FFT(ctx, cufftExecR2C(s->planProj, R, reinterpret_cast<cufftComplex*>(v.d)));
     span_end(ctx);
