@@ -87,6 +87,39 @@ __global__ void build_quad_kernel(const float2* __restrict__ vol, int n, int nz,
     }
 }
 
+// Epilogue shared by the direct-gather E kernels: baseline (the reference's running baseline ends at the maximum), exp, and the
+// prior-weighted marginals uR, uT, uC exactly as src/Optimiser.cpp:1383-1402.  sL = the [nR][nT] log-likelihood table.
+template <int THREADS>
+__device__ __forceinline__ void expect_epilogue(const ExpectArgs& A, int p, float* sL, float* redf, double* redd)
+{
+    const int tid = threadIdx.x, nRT = A.nR * A.nT;
+    float m = -INFINITY;
+    for (int i = tid; i < nRT; i += THREADS) m = fmaxf(m, sL[i]);
+    m = block_reduce_max(m, redf);
+    if (A.logL)
+        for (int i = tid; i < nRT; i += THREADS) A.logL[(size_t)p * nRT + i] = sL[i];
+    __syncthreads();
+    for (int i = tid; i < nRT; i += THREADS) sL[i] = expf(sL[i] - m);
+    __syncthreads();
+    double uc = 0.0;
+    for (int r = tid; r < A.nR; r += THREADS) {
+        float s = 0.0f;
+        for (int t = 0; t < A.nT; ++t) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wT.at(p, t, 0));
+        if (A.uR) A.uR[(size_t)p * A.nR + r] = s;
+        uc += (double)s * A.wR.at(p, r, 0);
+    }
+    for (int t = tid; t < A.nT; t += THREADS) {
+        float s = 0.0f;
+        for (int r = 0; r < A.nR; ++r) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wR.at(p, r, 0));
+        if (A.uT) A.uT[(size_t)p * A.nT + t] = s;
+    }
+    uc = block_reduce_sum(uc, redd);
+    if (tid == 0) {
+        if (A.uC) A.uC[p] = (float)uc;
+        if (A.base) A.base[p] = m;
+    }
+}
+
 constexpr int E3_THREADS = 256;
 constexpr int E3_ROTS = 128;
 constexpr int E3_TILE = 128;
@@ -296,32 +329,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     }
     __syncthreads();
 
-    // ---------------- epilogue: baseline, weights, marginals (Optimiser.cpp:1383-1402) ----------
-    float m = -INFINITY;
-    for (int i = tid; i < nRT; i += E3_THREADS) m = fmaxf(m, sL[i]);
-    m = block_reduce_max(m, redf);
-    if (A.logL)
-        for (int i = tid; i < nRT; i += E3_THREADS) A.logL[(size_t)p * nRT + i] = sL[i];
-    __syncthreads();
-    for (int i = tid; i < nRT; i += E3_THREADS) sL[i] = expf(sL[i] - m);
-    __syncthreads();
-    double uc = 0.0;
-    for (int r = tid; r < A.nR; r += E3_THREADS) {
-        float s = 0.0f;
-        for (int t = 0; t < A.nT; ++t) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wT.at(p, t, 0));
-        if (A.uR) A.uR[(size_t)p * A.nR + r] = s;
-        uc += (double)s * A.wR.at(p, r, 0);
-    }
-    for (int t = tid; t < A.nT; t += E3_THREADS) {
-        float s = 0.0f;
-        for (int r = 0; r < A.nR; ++r) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wR.at(p, r, 0));
-        if (A.uT) A.uT[(size_t)p * A.nT + t] = s;
-    }
-    uc = block_reduce_sum(uc, redd);
-    if (tid == 0) {
-        if (A.uC) A.uC[p] = (float)uc;
-        if (A.base) A.base[p] = m;
-    }
+    expect_epilogue<E3_THREADS>(A, p, sL, redf, redd);
 }
 
 }  // namespace thb

@@ -186,32 +186,7 @@ __global__ void __launch_bounds__(E5_THREADS, 2) expect_pix_kernel(const ExpectA
     }
     __syncthreads();
 
-    // ---------------- epilogue: baseline, weights, marginals (Optimiser.cpp:1383-1402) ----------
-    float m = -INFINITY;
-    for (int i = tid; i < nRT; i += E5_THREADS) m = fmaxf(m, sL[i]);
-    m = block_reduce_max(m, redf);
-    if (A.logL)
-        for (int i = tid; i < nRT; i += E5_THREADS) A.logL[(size_t)p * nRT + i] = sL[i];
-    __syncthreads();
-    for (int i = tid; i < nRT; i += E5_THREADS) sL[i] = expf(sL[i] - m);
-    __syncthreads();
-    double uc = 0.0;
-    for (int r = tid; r < A.nR; r += E5_THREADS) {
-        float s = 0.0f;
-        for (int t = 0; t < A.nT; ++t) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wT.at(p, t, 0));
-        if (A.uR) A.uR[(size_t)p * A.nR + r] = s;
-        uc += (double)s * A.wR.at(p, r, 0);
-    }
-    for (int t = tid; t < A.nT; t += E5_THREADS) {
-        float s = 0.0f;
-        for (int r = 0; r < A.nR; ++r) s = (float)((double)s + (double)sL[r * A.nT + t] * A.wR.at(p, r, 0));
-        if (A.uT) A.uT[(size_t)p * A.nT + t] = s;
-    }
-    uc = block_reduce_sum(uc, redd);
-    if (tid == 0) {
-        if (A.uC) A.uC[p] = (float)uc;
-        if (A.base) A.base[p] = m;
-    }
+    expect_epilogue<E5_THREADS>(A, p, sL, redf, redd);
 }
 
 }  // namespace thb

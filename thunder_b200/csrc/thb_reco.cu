@@ -294,8 +294,6 @@ __global__ void __launch_bounds__(256) sigma_kernel(const SigmaArgs A)
     const Rot2 rot = make_rot2(q, A.mode2D);
     const float tx = (float)A.tran[2 * l], ty = (float)A.tran[2 * l + 1];
     const float ox = (float)(A.tran[2 * l] - A.offS[2 * l]), oy = (float)(A.tran[2 * l + 1] - A.offS[2 * l + 1]);
-    const float invN = 1.0f;   // placeholder to keep the divisions below explicit
-    (void)invN;
     for (int i = tid; i < A.PE; i += blockDim.x) {
         int u = A.ringE[i];
         if (u < 0) continue;
