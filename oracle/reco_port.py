@@ -163,3 +163,43 @@ def recentre_remask(img_ori_ft, offset, mask_radius_px, zero_mask=True):
     rl = np.fft.irfft2(img, s=(N, N), axes=(0, 1)).astype(np.float32)
     rl = (rl * soft_mask(N, mask_radius_px)).astype(np.float32)
     return np.fft.rfft2(rl).astype(np.complex64)
+
+
+def symmetrize(F, T, elems, r):
+    """Reconstructor::symmetrizeF / symmetrizeT (src/Reconstructor.cpp:2676-2690) = SYMMETRIZE_FT / VOL_TRANSFORM_MAT_FT
+    (include/Geometry/Transformation.h:105-131, 170-194): out(v) = src(v) + sum_e src interpolated at R_e v for every voxel of
+    the half volume whose rotated position lies inside radius r.  F complex64 [n][n][n/2+1], T float32 (the real part of the
+    reference's complex T volume), elems [nElem][9] column-major dmat33 (Symmetry::get), r = maxRadius * pf + 1."""
+    f32 = np.float32
+    n = F.shape[0]
+    nc = n // 2 + 1
+    km, jm, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(nc), indexing="ij")
+    a = i.astype(np.float64)
+    b = np.where(jm < n // 2, jm, jm - n).astype(np.float64)
+    c = np.where(km < n // 2, km, km - n).astype(np.float64)
+    outF = F.astype(np.complex64).copy()
+    outT = T.astype(f32).copy()
+    for e in np.asarray(elems, np.float64).reshape(-1, 9):
+        ox = e[0] * a + e[3] * b + e[6] * c
+        oy = e[1] * a + e[4] * b + e[7] * c
+        oz = e[2] * a + e[5] * b + e[8] * c
+        ok = ox * ox + oy * oy + oz * oz < r * r
+        x, y, z = ox.astype(f32), oy.astype(f32), oz.astype(f32)
+        cj = ~(x >= 0)
+        x = np.where(cj, -x, x); y = np.where(cj, -y, y); z = np.where(cj, -z, z)
+        fx, fy, fz = np.floor(x), np.floor(y), np.floor(z)
+        x0, y0, z0 = fx.astype(np.int64), fy.astype(np.int64), fz.astype(np.int64)
+        xd, yd, zd = (x - fx).astype(f32), (y - fy).astype(f32), (z - fz).astype(f32)
+        accF = np.zeros(F.shape, np.complex64)
+        accT = np.zeros(F.shape, f32)
+        for dk in (0, 1):
+            for dj in (0, 1):
+                for di in (0, 1):
+                    w = ((xd if di else f32(1) - xd) * (yd if dj else f32(1) - yd)).astype(f32) * (zd if dk else f32(1) - zd)
+                    xi = np.clip(x0 + di, 0, nc - 1)                       # only reached by voxels outside r (masked below)
+                    accF = (accF + (F[(z0 + dk) % n, (y0 + dj) % n, xi] * w.astype(f32)).astype(np.complex64)).astype(np.complex64)
+                    accT = (accT + T[(z0 + dk) % n, (y0 + dj) % n, xi] * w.astype(f32)).astype(f32)
+        accF = np.where(cj, np.conj(accF), accF)
+        outF = (outF + np.where(ok, accF, 0)).astype(np.complex64)
+        outT = (outT + np.where(ok, accT, 0)).astype(f32)
+    return outF, outT

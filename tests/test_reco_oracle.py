@@ -267,3 +267,61 @@ def test_device_symmetrize(ctx, group):
     assert np.allclose(want["O"], O + sum(r @ O for r in Rm), atol=1e-12)
     assert want["counter"] == counter * (1 + len(elems))
     R.close()
+
+
+# ------------------------------------------------------------------------------------------- CPU pins of the restatements
+def _sigma_problem(N=32, rSig=12, nImg=4, seed=5):
+    from oracle import refapi
+    rng = np.random.default_rng(seed)
+    P = refapi.Projector(2)
+    P.set_from_real(synth.phantom(N, 6, seed=4))
+    volFT = P.padded_ft()
+    mk = lambda: np.stack([np.fft.rfft2(rng.normal(size=(N, N)).astype(np.float32)) for _ in range(nImg)]).astype(np.complex64)
+    img, ori = mk(), mk()
+    sc = np.float32(np.abs(volFT).mean() * 3 / np.abs(img).mean())
+    img *= sc; ori *= sc
+    quat = synth.random_quats(nImg, rng); tran = rng.normal(scale=1.5, size=(nImg, 2)); offS = rng.normal(size=(nImg, 2))
+    attr = np.stack([np.full(nImg, 3e5), rng.uniform(1e4, 3e4, nImg), rng.uniform(1e4, 3e4, nImg), rng.uniform(0, np.pi, nImg),
+                     np.full(nImg, 2.7e7), np.full(nImg, 0.1), np.zeros(nImg)], axis=1).astype(np.float32)
+    return P, volFT, img, ori, quat, tran, offS, attr
+
+
+def test_sigma_and_norm_restatements_match_reference():
+    """oracle/sigma_port.py == the image loops of allReduceSigma / normCorrection driven through the reference's own functions"""
+    from oracle import refapi, sigma_port
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, rSig, nGroup = 32, 12, 2
+    P, volFT, img, ori, quat, tran, offS, attr = _sigma_problem(N, rSig)
+    group = np.array([0, 1, 1, 0], np.int32)
+    want = refapi.sigma_accumulate(P, img, ori, quat, tran, offS, attr, 1.32, group, nGroup, rSig)
+    got = sigma_port.sigma_accumulate(volFT, 2, img, ori, quat, tran, offS, attr, 1.32, group, nGroup, rSig)
+    for g, w in zip(got, want):
+        assert np.array_equal(g[:, -1], w[:, -1])
+        assert np.allclose(g[:, :rSig], w[:, :rSig], rtol=2e-4)
+    wantN = refapi.norm_residual(P, img, quat, tran, attr, 1.32, 1.0, 10.4)
+    gotN = sigma_port.norm_residual(volFT, 2, img, quat, tran, attr, 1.32, 1.0, 10.4)
+    assert np.allclose(gotN, wantN, rtol=2e-4)
+    P.close()
+
+
+@pytest.mark.parametrize("group", ["C4", "D2"])
+def test_symmetrize_restatement_matches_reference(group):
+    from oracle import refapi, reco_port
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, pf = 16, 2
+    R = refapi.Reconstructor(N, N, pf)
+    m = R.pad_size()
+    F = np.fft.rfftn(np.pad(synth.phantom(N, 5, seed=12), [(0, m - N)] * 3)).astype(np.complex64)
+    T = (np.abs(np.fft.rfftn(np.pad(synth.phantom(N, 4, seed=13), [(0, m - N)] * 3))) + 1.0).astype(np.float32)
+    R.set(F, T)
+    R.symmetrize(group)
+    want = R.get()
+    r = R.max_radius() * pf + 1
+    gF, gT = reco_port.symmetrize(F, T, refapi.symmetry_elements(group), r)
+    kk, jj, ii = np.meshgrid(np.fft.fftfreq(m, 1 / m), np.fft.fftfreq(m, 1 / m), np.arange(m // 2 + 1), indexing="ij")
+    edge = (ii * ii + jj * jj + kk * kk) == r * r          # membership of the cut is decided by the last bit there
+    assert np.abs(gF - want["F"])[~edge].max() <= 2e-6 * np.abs(want["F"]).max()
+    assert np.abs(gT - want["T"])[~edge].max() <= 2e-6 * np.abs(want["T"]).max()
+    R.close()
