@@ -67,7 +67,7 @@ def workload(args):
 
 def config_dict(args, wl, nPxlE, nPxlM, n_gpus):
     return {
-        "workload": f"100k synthetic particles, box {wl['N']}, {args.mlr * args.phases} orientation samples "
+        "workload": f"{args.particles // 1000}k synthetic particles, box {wl['N']}, {args.mlr * args.phases} orientation samples "
                     f"({args.mlr} rot x {args.phases} phases) x {args.mlt} translations, mReco {args.mreco}, "
                     f"{n_gpus}xB200" + (" with NCCL half-map allreduce" if n_gpus > 1 else ""),
         "particles_resident_per_gpu": args.particles // n_gpus, "batch_per_gpu_per_step": args.batch,
@@ -233,11 +233,18 @@ def main():
     PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
     ctx.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
     ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
-    vol = synth.padded_ft(synth.phantom(N, 30), pf)
-    vol_b = (vol * np.float32(0.98)).astype(np.complex64)     # second half-set reference (distinct buffer)
-    ctx.set_volume(0, vol)
-    ctx.set_volume(1, vol_b)
-    del vol_b
+    if N <= 256:
+        vol = synth.padded_ft(synth.phantom(N, 30), pf)
+        vol_b = (vol * np.float32(0.98)).astype(np.complex64)     # second half-set reference (distinct buffer)
+        ctx.set_volume(0, vol)
+        ctx.set_volume(1, vol_b)
+        del vol, vol_b
+    else:
+        # large boxes (config 4: box 512 -> 1024^3 padded): pad, grid-correct and transform on the device (thb_set_projectee)
+        ph = synth.phantom(N, 8)
+        ctx.set_projectee(0, ph, N, pf)
+        ctx.set_projectee(1, (ph * np.float32(0.98)).astype(np.float32), N, pf)
+        del ph
     for s in (0, 1):
         ctx.reco_alloc(s, N * pf)
 
