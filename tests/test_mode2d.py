@@ -156,13 +156,14 @@ def test_expect_local_2d_matches_reference(ctx2d):
 
 
 @pytest.mark.gpu
-def test_expect_scan_2d_every_image_against_every_class(ctx2d):
+@pytest.mark.parametrize("nT", [6, 12])            # 12 > 9: the 15-translations-per-pass variant of the default kernel
+def test_expect_scan_2d_every_image_against_every_class(ctx2d, nT):
     """the classification scan (src/Optimiser.cpp:756-914): shared in-plane rotations x translations, all images x all classes"""
     ref = _ref()
     s = _setup(nImg=7)
     _load(ctx2d, s, s["cls"])
     rng = s["rng"]
-    nR, nT = 20, 6
+    nR = 20
     cs = _unit(np.linspace(-np.pi, np.pi, nR, endpoint=False)); t = rng.normal(size=(nT, 2)) * 2
     pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
     for k in range(s["k"]):

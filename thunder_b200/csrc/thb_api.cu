@@ -156,12 +156,17 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
     a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
     a.work = nullptr;
-    const bool single = a.nR <= E3_ROTS && a.nT <= E_TC;
+    // more translations than one pass of the local-search kernel carries (the scans: nT = 30 in demo_2D.json): the variant
+    // with 15 per pass halves the number of passes over the gather
+    const bool wideT = ctx->expectImpl == 3 && a.nT > E_TC;
+    const int tc = wideT ? E3_TC_SCAN : E_TC;
+    const bool single = a.nR <= E3_ROTS && a.nT <= tc;
     if (!single) {
         a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
         if (!a.work) return THB_E_CUDA;
     }
-    const size_t smem = (ctx->expectImpl == 5 ? E5_SMEM_BYTES : E3_SMEM_BYTES) + (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
+    const size_t smem = (ctx->expectImpl == 5 ? E5_SMEM_BYTES : wideT ? E3_TILE * sizeof(PixelRecT<E3_TC_SCAN>) : E3_SMEM_BYTES) +
+                        (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
     if (ctx->expectImpl == 5) {
         if (ctx->mode2D)
@@ -177,6 +182,13 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
             expect_pair_kernel<true, false><<<a.nAct, E4_THREADS, smem, ctx->stream>>>(a);
         else
             expect_pair_kernel<false, false><<<a.nAct, E4_THREADS, smem, ctx->stream>>>(a);
+    } else if (wideT) {
+        if (ctx->mode2D)
+            expect_direct_kernel<2, false, true, E3_TC_SCAN><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+        else if (ctx->quadOct)
+            expect_direct_kernel<2, true, false, E3_TC_SCAN><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
+        else
+            expect_direct_kernel<2, false, false, E3_TC_SCAN><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
     } else if (ctx->mode2D)
         expect_direct_kernel<2, false, true><<<a.nAct, E3_THREADS, smem, ctx->stream>>>(a);
     else if (ctx->quadOct)

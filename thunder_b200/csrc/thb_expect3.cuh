@@ -123,14 +123,24 @@ __device__ __forceinline__ void expect_epilogue(const ExpectArgs& A, int p, floa
 constexpr int E3_THREADS = 256;
 constexpr int E3_ROTS = 128;
 constexpr int E3_TILE = 128;
+// pixel record with TC translations per pass: TC = 9 = mLT of the local search (the default); the classification / global
+// scans carry 15 so that 30 translations take two passes over the gather instead of four
+template <int TC>
+struct __align__(16) PixelRecT {
+    double a, b;        // pf*iCol, pf*iRow
+    float g, pad;       // sig * ctf^2
+    float2 u[TC];       // -2 sig ctf dat conj(tra_t)
+};
+static_assert(sizeof(PixelRecT<E_TC>) == sizeof(PixelRec), "PixelRecT<9> is PixelRec");
+constexpr int E3_TC_SCAN = 15;
 constexpr size_t E3_SMEM_BYTES = E3_TILE * sizeof(PixelRec);     // + the [nR][nT] table for single-pass shapes
 
-template <int MINB, bool OCT, bool M2D = false>
+template <int MINB, bool OCT, bool M2D = false, int TC = E_TC>
 __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const ExpectArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    PixelRec* tile = reinterpret_cast<PixelRec*>(smem_raw);
-    __shared__ float sRC[E_TC], sRR[E_TC];
+    PixelRecT<TC>* tile = reinterpret_cast<PixelRecT<TC>*>(smem_raw);
+    __shared__ float sRC[TC], sRR[TC];
     __shared__ float redf[E3_THREADS / 32];
     __shared__ double redd[E3_THREADS / 32];
 
@@ -145,16 +155,20 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     const float* __restrict__ ctf = A.ctf + (size_t)img * P;
     const float* __restrict__ sig = A.sig + (size_t)img * P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rloc = (warp & 3) * 32 + lane;   // rotation slot of this thread within a pass
-    const int ph = warp >> 2;                  // pixel half
     const int nRT = A.nR * A.nT;
-    const bool single = A.nR <= E3_ROTS && A.nT <= E_TC;
-    float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_SMEM_BYTES) : A.work + (size_t)p * nRT;
+    const bool single = A.nR <= E3_ROTS && A.nT <= TC;
+    float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_TILE * sizeof(PixelRecT<TC>)) : A.work + (size_t)p * nRT;
     double k0sum = 0.0;          // sum_i sig_i |dat_i|^2
     const int LB = A.quadBrick;
 
     for (int rbase = 0; rbase < A.nR; rbase += E3_ROTS) {
         const int nRc = min(E3_ROTS, A.nR - rbase);
+        // the 8 warps are split into G rotation groups (32 rotations each) x 8 / G pixel parts: a full cloud of 125 uses
+        // 4 x 2, the small supports of the scans' chunks, of demo_3D.json's mLR = 25 or of MODE_2D's mLR = 9 use 1 x 8
+        const int G = nRc > 64 ? 4 : nRc > 32 ? 2 : 1;
+        const int nParts = (E3_THREADS / 32) / G;
+        const int rloc = (warp % G) * 32 + lane;   // rotation slot of this thread within the pass
+        const int ph = warp / G;                   // pixel part
         const bool rvalid = rloc < nRc;
         // Rotation slots are handed out in the order of the cloud along its widest axis, so that the 32 lanes of a warp
         // hold a compact sub-cloud: a warp-wide load then touches fewer distinct lines.  rsrc = rotation of this slot.
@@ -214,9 +228,9 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                 for (int c = 0; c < (M2D ? 2 : 4); ++c) q[c] = A.quat.at(p, rbase + rsrc, c);
             rot = make_rot2(q, M2D);
         }
-        for (int tbase = 0; tbase < A.nT; tbase += E_TC) {
+        for (int tbase = 0; tbase < A.nT; tbase += TC) {
             __syncthreads();
-            if (tid < E_TC) {
+            if (tid < TC) {
                 const int t = tbase + tid;
                 float tx = 0.0f, ty = 0.0f;
                 if (t < A.nT) {
@@ -226,9 +240,9 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                 sRC[tid] = tx / (float)A.N;
                 sRR[tid] = ty / (float)A.N;
             }
-            float acc[E_TC];
+            float acc[TC];
 #pragma unroll
-            for (int t = 0; t < E_TC; ++t) acc[t] = 0.0f;
+            for (int t = 0; t < TC; ++t) acc[t] = 0.0f;
             float nrm = 0.0f;
             const bool firstPass = (rbase == 0 && tbase == 0);
 
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         const float2 d = dat[i];
                         const float cf = ctf[i], sg = sig[i];
                         const float m2 = -2.0f * sg * cf;
-                        PixelRec& rec = tile[k];
+                        PixelRecT<TC>& rec = tile[k];
                         if (sub == 0) {
                             rec.a = (double)c.x;
                             rec.b = (double)c.y;
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                             if (firstPass) k0sum += (double)(sg * (d.x * d.x + d.y * d.y));
                         }
 #pragma unroll
-                        for (int t = 0; t < E_TC; ++t) {
+                        for (int t = 0; t < TC; ++t) {
                             if ((t & 1) != sub) continue;
                             const float phs = translate_phase(c.z, c.w, sRC[t], sRR[t]);
                             float s, co;
@@ -266,8 +280,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                 __syncthreads();
                 if (rvalid) {
 #pragma unroll 2
-                    for (int k = ph; k < cnt; k += 2) {
-                        const PixelRec& rec = tile[k];
+                    for (int k = ph; k < cnt; k += nParts) {
+                        const PixelRecT<TC>& rec = tile[k];
                         float x, y, z;
                         slice_coord(rot, rec.a, rec.b, x, y, z);
                         int xb, yb, zb;
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         if (conj) im = -im;
                         nrm = fmaf(rec.g, fmaf(re, re, im * im), nrm);
 #pragma unroll
-                        for (int t = 0; t < E_TC; ++t) acc[t] = fmaf(rec.u[t].x, re, fmaf(rec.u[t].y, im, acc[t]));
+                        for (int t = 0; t < TC; ++t) acc[t] = fmaf(rec.u[t].x, re, fmaf(rec.u[t].y, im, acc[t]));
                     }
                 }
             }
@@ -310,20 +324,27 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                 k0sum = s;
                 __syncthreads();
             }
-            float* park = reinterpret_cast<float*>(tile);     // 128 x 10 floats = 5 KB
-            if (ph == 1) {
+            // partial sums of pixel parts 1 .. nParts-1 are parked in the record area ((nParts-1) x 32 G x (TC+1) floats <= 14 KB)
+            float* park = reinterpret_cast<float*>(tile);
+            if (ph > 0) {
+                float* pk = park + ((size_t)(ph - 1) * (32 * G) + rloc) * (TC + 1);
 #pragma unroll
-                for (int t = 0; t < E_TC; ++t) park[rloc * (E_TC + 1) + t] = acc[t];
-                park[rloc * (E_TC + 1) + E_TC] = nrm;
+                for (int t = 0; t < TC; ++t) pk[t] = acc[t];
+                pk[TC] = nrm;
             }
             __syncthreads();
             if (ph == 0 && rvalid) {
-                const double nn = (double)nrm + (double)park[rloc * (E_TC + 1) + E_TC];
+                const float* pk0 = park + (size_t)rloc * (TC + 1);
+                const size_t pstride = (size_t)(32 * G) * (TC + 1);
+                double nn = (double)nrm;
+                for (int j = 1; j < nParts; ++j) nn += (double)pk0[(j - 1) * pstride + TC];
 #pragma unroll
-                for (int t = 0; t < E_TC; ++t)
-                    if (tbase + t < A.nT)
-                        sL[(size_t)(rbase + rsrc) * A.nT + tbase + t] =
-                            (float)(k0sum + nn + (double)acc[t] + (double)park[rloc * (E_TC + 1) + t]);
+                for (int t = 0; t < TC; ++t) {
+                    if (tbase + t >= A.nT) continue;
+                    double tot = (double)acc[t];
+                    for (int j = 1; j < nParts; ++j) tot += (double)pk0[(j - 1) * pstride + t];
+                    sL[(size_t)(rbase + rsrc) * A.nT + tbase + t] = (float)(k0sum + nn + tot);
+                }
             }
         }
     }
