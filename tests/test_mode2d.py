@@ -89,6 +89,28 @@ def test_port2d_insert_matches_reference():
     R.close()
 
 
+def test_port2d_matches_golden_fixture():
+    """the committed MODE_2D fixture (tests/golden/make_golden_2d.py: outputs of the reference's own Projector / Reconstructor
+    in MODE_2D) pins oracle/port2d.py also where the reference library is not built"""
+    from pathlib import Path
+    from oracle import port2d
+    g = np.load(Path(__file__).resolve().parent / "golden" / "mode2d_n16.npz")
+    N, pf = int(g["N"]), int(g["pf"])
+    for c, want in zip(g["cs"], g["slices"]):
+        got = port2d.project2d(g["refFT"], pf, c, g["pixE_iCol"], g["pixE_iRow"])
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    mine = port2d.Reco2D(N * pf)
+    nImg, mReco = g["ncs"].shape[:2]
+    for l in range(nImg):
+        for m in range(mReco):
+            mine.insert_draw(g["datM"][l], g["ctfM"][l], N, g["pixM_iCol"], g["pixM_iRow"], g["pixM_iColPad"], g["pixM_iRowPad"],
+                             g["ncs"][l, m], g["nt"][l, m], g["off"][l], g["w"][l])
+    assert mine.counter == int(g["counter"])
+    assert np.allclose(mine.O, g["O"], atol=1e-12)
+    assert np.abs(mine.F - g["F"]).max() <= 2e-5 * np.abs(g["F"]).max()
+    assert np.abs(mine.T - g["T"]).max() <= 2e-5 * np.abs(g["T"]).max()
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.fixture(params=[3, 1], ids=["cell-kernel", "linear-kernel"])
 def ctx2d(request):
