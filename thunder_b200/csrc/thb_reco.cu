@@ -847,8 +847,9 @@ int thb_symmetrize(thb_ctx* ctx, int slot, int nElem, const double* R, double ra
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     float4* out = nullptr;
     THB_CUDA(ctx, cudaMalloc(&out, a.nVox * sizeof(float4)));
+    struct Guard { float4* p; ~Guard() { cudaFree(p); } } guard{out};     // the new buffer on an error return, the old one on success
     double* dR = (double*)scratch(ctx, 0, sizeof(double) * 9 * (size_t)nElem);
-    if (!dR) { cudaFree(out); return THB_E_CUDA; }
+    if (!dR) return THB_E_CUDA;
     THB_CUDA(ctx, cudaMemcpyAsync(dR, R, sizeof(double) * 9 * (size_t)nElem, cudaMemcpyHostToDevice, ctx->stream));
     span_begin(ctx, KF_PACK);
     symmetrize_kernel<<<ctx->smCount * 16, 256, 0, ctx->stream>>>(a.d, out, a.vdim, nElem, dR, radius * radius);
@@ -870,7 +871,7 @@ int thb_symmetrize(thb_ctx* ctx, int slot, int nElem, const double* R, double ra
     THB_CUDA(ctx, cudaMemcpyAsync(ctx->dO + 3 * slot, res, sizeof(res), cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(ctx->dCounter + slot, &cnt, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(a.d);
+    guard.p = a.d;
     a.d = out;
     return THB_OK;
 }
