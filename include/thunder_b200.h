@@ -190,6 +190,11 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
                const double* nr, const double* nt);
 /* F[(vdimPad/2+1)*vdimPad^2][2], T[...] real part, O[3], counter.  normalise != 0 applies
  * sf = 1/T[0] to T and F (RECONSTRUCTOR_NORMALISE_T_F). Any pointer may be NULL. */
+/* 3D classification (k > 1; the nC of InsertFT, gpu/interface/Interface.h:267-291, as reconstructRef fills it,
+ * src/Optimiser.cpp:6862-6950): nr / nt hold mReco = the largest per-image count of draws of this class, nDraw[nImg] says how
+ * many of them each image really has (0 .. mReco); only those are inserted and counted */
+int thb_insert_counts(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
+                      const int* nDraw, const double* nr, const double* nt);
 /* MODE_2D: the same with the class of every draw, nc[nImg][mReco] (InsertI2D's nC): the accumulator slot of the draw */
 int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
                        const int* nc, const double* nr, const double* nt);

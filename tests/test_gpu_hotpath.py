@@ -585,3 +585,38 @@ def test_async_upload_matches_blocking_upload(ctx):
     got = ctx.download_stack(capi.STACK_EXPECT, nImg, nImg)
     assert np.array_equal(got["dat"], dat) and np.array_equal(got["ctf"], ctf) and np.array_equal(got["sigRcp"], sig)
     ctx.upload_wait()                                                             # nothing pending: a no-op
+
+
+def test_insert_counts_3d_classification():
+    """thb_insert_counts (the nC of the reference's InsertFT in 3D classification): only the first nDraw[l] rows of image l are
+    inserted == inserting every image with its own truncated list"""
+    port, ref = _oracle()
+    N, pf = 32, 2
+    rng = np.random.default_rng(17)
+    pixM = port.pixel_list(N, pf, 15.0, 0.0)
+    PM = len(pixM["iCol"])
+    nImg, mReco = 6, 5
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    nr = synth.random_quats(nImg * mReco, rng).reshape(nImg, mReco, 4); nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    w = np.full(nImg, 1.0 / mReco, np.float32); offS = rng.normal(scale=0.5, size=(nImg, 2))
+    nDraw = np.array([5, 0, 3, 1, 7, 2], np.int32)                 # 7 > mReco: clipped to mReco
+    ctx = capi.Context(0)                                           # private context: its only accumulator is slot 0
+    try:
+        ctx.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        ctx.upload_stack(capi.STACK_INSERT, datM, ctfM)
+        ctx.reco_alloc(0, N * pf)
+        ctx.insert_counts(w, nDraw, nr, nt, offS=offS)
+        got = ctx.reco_download(0)
+        ctx.reco_reset(0)
+        for l in range(nImg):
+            c = min(int(nDraw[l]), mReco)
+            if c:
+                ctx.insert(w[l:l + 1], nr[l:l + 1, :c], nt[l:l + 1, :c], offS=offS[l:l + 1], imgIdx=np.array([l], np.int32))
+        want = ctx.reco_download(0)
+    finally:
+        ctx.close()
+    assert got["counter"] == want["counter"] == int(np.minimum(nDraw, mReco).sum())
+    assert np.allclose(got["O"], want["O"], rtol=1e-12, atol=1e-12)
+    assert np.abs(got["F"] - want["F"]).max() <= 2e-6 * np.abs(want["F"]).max()
+    assert np.abs(got["T"] - want["T"]).max() <= 2e-6 * np.abs(want["T"]).max()

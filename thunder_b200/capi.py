@@ -74,6 +74,7 @@ def _sig(lib):
     f = lib.thb_scale_images; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_get_mode; f.restype = _i; f.argtypes = [_p]
     f = lib.thb_insert_classes; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
+    f = lib.thb_insert_counts; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
     f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
     f = lib.thb_reco_upload; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
@@ -411,6 +412,16 @@ class Context:
         offS = _arr(offS, np.float64, (nImg, 2))
         imgIdx = _arr(imgIdx, np.int32, (nImg,))
         self._chk(self.lib.thb_insert(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt)))
+
+    def insert_counts(self, w, nDraw, nr, nt, offS=None, imgIdx=None):
+        """3D classification: only the first nDraw[l] of the mReco rows of image l are inserted"""
+        nr = _arr(nr, np.float64)
+        nImg, mReco, _ = nr.shape
+        nt = _arr(nt, np.float64, (nImg, mReco, 2)); nDraw = _arr(nDraw, np.int32, (nImg,))
+        w = _arr(w, np.float32, (nImg,))
+        offS = _arr(offS, np.float64, (nImg, 2))
+        imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        self._chk(self.lib.thb_insert_counts(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nDraw), _ptr(nr), _ptr(nt)))
 
     def insert_classes(self, w, nc, nr, nt, offS=None, imgIdx=None):
         """MODE_2D: nc[nImg][mReco] = class (accumulator slot) of every draw, nr[nImg][mReco][2] = (cos, sin)"""

@@ -1099,7 +1099,7 @@ int thb_reco_reset(thb_ctx* ctx, int slot)
 }
 
 static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,
-                       const double* nr, const double* nt)
+                       const double* nr, const double* nt, const int* nDraw = nullptr)
 {
     if (!ctx) return THB_E_ARG;
     if (nc && !ctx->mode2D) return set_error(ctx, THB_E_STATE, "insert_classes: per-draw classes are a MODE_2D feature (thb_set_mode)");
@@ -1124,13 +1124,15 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
 
     const int qc = ctx->mode2D ? 2 : 4;      // MODE_2D: nr[nImg][mReco][2] = (cos, sin), as InsertI2D receives it
     const size_t nq = (size_t)nImg * mReco * qc, ntt = (size_t)nImg * mReco * 2;
-    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * ((size_t)nImg + (size_t)nImg * mReco));
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * (2 * (size_t)nImg + (size_t)nImg * mReco));
     if (!din) return THB_E_CUDA;
     double* dq = din; double* dt = dq + nq; double* doff = dt + ntt;
     float* dw = (float*)(doff + 2 * (size_t)nImg);
     int* didx = (int*)(dw + nImg);
     int* dnc = didx + nImg;
+    int* dcount = dnc + (size_t)nImg * mReco;
     if (nc) THB_CUDA(ctx, cudaMemcpyAsync(dnc, nc, sizeof(int) * (size_t)nImg * mReco, cudaMemcpyHostToDevice, ctx->stream));
+    if (nDraw) THB_CUDA(ctx, cudaMemcpyAsync(dcount, nDraw, sizeof(int) * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dq, nr, sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
     THB_CUDA(ctx, cudaMemcpyAsync(dt, nt, sizeof(double) * ntt, cudaMemcpyHostToDevice, ctx->stream));
     if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
@@ -1149,6 +1151,7 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
     a.nt = View3{dt, (long long)mReco * 2, 2, 1};
     a.mode2D = ctx->mode2D;
     a.drawC = nc ? dnc : nullptr;
+    a.drawCount = nDraw ? dcount : nullptr;
     int rc = launch_insert(ctx, a);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1159,6 +1162,13 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
                const double* nt)
 {
     return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nullptr, nr, nt);
+}
+
+int thb_insert_counts(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nDraw,
+                      const double* nr, const double* nt)
+{
+    if (ctx && !nDraw) return set_error(ctx, THB_E_ARG, "insert_counts: nDraw == NULL");
+    return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nullptr, nr, nt, nDraw);
 }
 
 int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,

@@ -276,8 +276,11 @@ __global__ void __launch_bounds__(M_THREADS) insert_kernel(const InsertArgs A)
     const double ox = A.offS ? A.offS[2 * l] : 0.0, oy = A.offS ? A.offS[2 * l + 1] : 0.0;
     const int tid = threadIdx.x;
 
-    for (int mbase = 0; mbase < A.mReco; mbase += M_MAXRECO) {
-        const int mcnt = min(M_MAXRECO, A.mReco - mbase);
+    // 3D classification (src/Optimiser.cpp:6862-6950): the caller passes max-count draws per image and the number of them
+    // that belong to this class; the rest of the image's rows are not read
+    const int mTot = A.drawCount ? max(0, min(A.mReco, A.drawCount[l])) : A.mReco;
+    for (int mbase = 0; mbase < mTot; mbase += M_MAXRECO) {
+        const int mcnt = min(M_MAXRECO, mTot - mbase);
         __syncthreads();
         double dx = 0.0, dy = 0.0, dz = 0.0;
         if (tid < mcnt) {

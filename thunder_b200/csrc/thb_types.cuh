@@ -96,6 +96,7 @@ struct InsertArgs {
     const int* drawR;         // optional [nImg][mReco] indices into nr/nt sample axis (particle filter draws)
     const int* drawT;
     const int* drawC;         // optional [nImg][mReco] accumulator slot of every draw (MODE_2D classes), else slotOfImg
+    const int* drawCount;     // optional [nImg]: only the first drawCount[l] <= mReco draws of image l are inserted
 };
 
 }  // namespace thb

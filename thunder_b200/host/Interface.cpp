@@ -238,7 +238,7 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
               void* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD, int* nC, const int* iCol, const int* iRow,
               RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim, int dimSize, int imgNum)
 {
-    (void)sigRcpP; (void)ctfaData; (void)nD; (void)nC; (void)pixelSize;
+    (void)sigRcpP; (void)ctfaData; (void)nD; (void)pixelSize;
     thb_ctx* ctx = thbContext(0);
     if (cSearch) {
         fprintf(stderr, "thunder_b200 [InsertFT]: CTF search (cSearch) is not on the accelerated path of this build\n");
@@ -253,7 +253,10 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
     CHK(ctx, thb_set_insert_pixels(ctx, idim, opf, npxl, iCol, iRow));   // Reconstructor's _iCol/_iRow are padded (x pf)
     CHK(ctx, thb_upload_stack(ctx, THB_STACK_INSERT, imgNum, reinterpret_cast<const float*>(datP), ctfP, nullptr, nullptr));
     CHK(ctx, thb_reco_alloc(ctx, 0, vdim));
-    CHK(ctx, thb_insert(ctx, imgNum, nullptr, mReco, w, offS, nR, nT));
+    if (nC)   // 3D classification: nC[l] of the mReco rows of image l belong to this class (Optimiser.cpp:6862-6950)
+        CHK(ctx, thb_insert_counts(ctx, imgNum, nullptr, mReco, w, offS, nC, nR, nT));
+    else
+        CHK(ctx, thb_insert(ctx, imgNum, nullptr, mReco, w, offS, nR, nT));
     CHK(ctx, thb_allreduce(ctx));                                         // hemisphere sum (no-op with one rank)
     std::vector<float> F(2 * nVox), T(nVox);
     double O[3];

@@ -85,6 +85,14 @@ inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Co
     InsertFT(&F3D[0], &T3D[0], (int)F3D.nSlcFT(), O3D, counter, datP, ctfP, sigRcpP, (void*)ctfaData, offS, w, nR, nT, nD,
              (int*)0, iCol, iRow, pixelSize, cSearch, opf, npxl, mReco, idim, dimSize, imgNum);
 }
+inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
+                     RFLOAT* sigRcpP, CTFAttr* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD, int* nC,
+                     const int* iCol, const int* iRow, RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim,
+                     int dimSize, int imgNum)      // 3D classification: nC[l] draws of image l belong to this class
+{
+    InsertFT(&F3D[0], &T3D[0], (int)F3D.nSlcFT(), O3D, counter, datP, ctfP, sigRcpP, (void*)ctfaData, offS, w, nR, nT, nD,
+             nC, iCol, iRow, pixelSize, cSearch, opf, npxl, mReco, idim, dimSize, imgNum);
+}
 inline void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
                       RFLOAT* sigRcpP, RFLOAT* w, double* offS, int* nC, double* nR, double* nT, double* nD, CTFAttr* ctfaData,
                       const int* iCol, const int* iRow, RFLOAT pixelSize, bool cSearch, int nk, int opf, int npxl, int mReco, int idim,
