@@ -545,6 +545,25 @@ void ref_norm_residual(void* projH, int nImg, int N, float rL, float rNorm, cons
     }
 }
 
+// von Mises-like family of the MODE_2D particle filter (src/Geometry/DirectionalStat.cpp:252-390), as is
+void ref_sample_vms(double k, int n, double* cs)
+{
+    dmat4 d(n, 4);                                   // the dmat4 overload is the one Particle::perturb calls (and the one that links)
+    sampleVMS(d, dvec4(1, 0, 0, 0), k, n);
+    for (int i = 0; i < n; i++) { cs[2 * i] = d(i, 0); cs[2 * i + 1] = d(i, 1); }
+}
+
+void ref_infer_vms(int n, const double* cs, double* mu2, double* k)
+{
+    dmat2 src(n, 2);
+    for (int i = 0; i < n; i++) { src(i, 0) = cs[2 * i]; src(i, 1) = cs[2 * i + 1]; }
+    dvec2 mu;
+    inferVMS(mu, *k, src);
+    mu2[0] = mu(0); mu2[1] = mu(1);
+}
+
+double ref_pdf_vms(const double* x2, const double* mu2, double k) { return pdfVMS(dvec2(x2[0], x2[1]), dvec2(mu2[0], mu2[1]), k); }
+
 // ---------------------------------------------------------------- MODE_2D (2D classification, demo_2D.json)
 // Projector in MODE_2D holding an already padded half-complex class average [pfN][pfN/2+1] verbatim
 void* ref_projector2d_create(int pf, const float* imgFT, int pfN)

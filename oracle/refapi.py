@@ -77,6 +77,10 @@ def lib():
         L.ref_symmetry_elements.argtypes = [C.c_char_p, _p, _i]
         L.ref_reco_symmetrize.argtypes = [_p, C.c_char_p, _i]
         L.ref_reco_set_O.argtypes = [_p, _p, _i]
+        L.ref_sample_vms.argtypes = [_d, _i, _p]
+        L.ref_infer_vms.argtypes = [_i, _p, _p, _p]
+        L.ref_pdf_vms.restype = _d
+        L.ref_pdf_vms.argtypes = [_p, _p, _d]
         L.ref_norm_residual.argtypes = [_p, _i, _i, _f, _f, _p, _p, _p, _p, _f, _p]
         L.ref_recentre_remask.argtypes = [_p, _p, _i, _d, _d, _f, _i]
         L.ref_sigma_accumulate.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _f, _p, _i, _p, _p, _p]
@@ -173,6 +177,25 @@ def sigma_accumulate(P, imgFT, imgOriFT, quat, tran, offS, ctfAttr, pixelSize, g
     lib().ref_sigma_accumulate(P.h, nImg, N, rSig, _ptr(imgFT), _ptr(imgOriFT), _ptr(quat), _ptr(tran), _ptr(offS), _ptr(attr), float(pixelSize),
                                _ptr(group), nGroup, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]))
     return out
+
+
+def sample_vms(k, n):
+    """sampleVMS about mu = (1, 0): [n][2]"""
+    out = np.zeros((n, 2))
+    lib().ref_sample_vms(float(k), int(n), _ptr(out))
+    return out
+
+
+def infer_vms(cs):
+    cs = np.ascontiguousarray(cs, np.float64)
+    mu = np.zeros(2); k = np.zeros(1)
+    lib().ref_infer_vms(cs.shape[0], _ptr(cs), _ptr(mu), _ptr(k))
+    return mu, float(k[0])
+
+
+def pdf_vms(x, mu, k):
+    x = np.ascontiguousarray(x, np.float64); mu = np.ascontiguousarray(mu, np.float64)
+    return float(lib().ref_pdf_vms(_ptr(x), _ptr(mu), float(k)))
 
 
 def symmetry_elements(name):

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "thb_pf.cuh"
+#include "thb_pf2d.cuh"
 
 using namespace thb;
 
@@ -57,6 +58,36 @@ void pfh_rng(unsigned long long seed, unsigned long long stream, unsigned long l
     g.init(seed, stream, epoch);
     for (int i = 0; i < n; i++) uni[i] = g.uniform();
     for (int i = 0; i < n; i++) nor[i] = g.normal();
+}
+
+// ---- MODE_2D rotation operators (thb_pf2d.cuh)
+void pfh_sample_vms(unsigned long long seed, double k, int n, double* cs)
+{
+    pf::Rng g;
+    g.init(seed, 0, 1);
+    for (int i = 0; i < n; i++) pf::sample_vms(g, k, cs[2 * i], cs[2 * i + 1]);
+}
+
+void pfh_infer_vms(int mLR, double* r, double* mu2, double* k)
+{
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.r = r; v.n = 1; v.p = 0; v.mLR = mLR; v.lane = -1;
+    pf::infer_vms(v, mu2, *k);
+}
+
+double pfh_pdf_vms(const double* x2, const double* mu2, double k) { return pf::pdf_vms(x2, mu2, k); }
+
+void pfh_perturb_r_2d(int mLR, double* r, double k1, double pfac, unsigned long long seed)
+{
+    std::vector<double> scal(20, 0.0);
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.r = r; v.scal = scal.data(); v.n = 1; v.p = 0; v.mLR = mLR; v.lane = -1;
+    scal[pf::S_K1] = k1;
+    pf::Rng g;
+    g.init(seed, 0, 2);
+    pf::perturb_R_2d(v, pfac, g);
 }
 
 }  // extern "C"

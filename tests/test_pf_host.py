@@ -21,7 +21,8 @@ _p, _i, _d = C.c_void_p, C.c_int, C.c_double
 @pytest.fixture(scope="module")
 def pfh():
     hdr = ROOT / "thunder_b200" / "csrc" / "thb_pf.cuh"
-    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, hdr.stat().st_mtime):
+    hdr2 = ROOT / "thunder_b200" / "csrc" / "thb_pf2d.cuh"
+    if not LIB.exists() or LIB.stat().st_mtime < max(SRC.stat().st_mtime, hdr.stat().st_mtime, hdr2.stat().st_mtime):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "thunder_b200" / "csrc"),
                                "-o", os.fspath(LIB), os.fspath(SRC)])
     L = C.CDLL(os.fspath(LIB))
@@ -29,6 +30,11 @@ def pfh():
     L.pfh_run.argtypes = [_i, _d, _i, _i] + [_p] * 9 + [_d, _d, C.c_ulonglong, C.c_ulonglong]
     L.pfh_infer_acg.argtypes = [_i, _p, _p, _p]
     L.pfh_rng.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _p, _p]
+    L.pfh_sample_vms.argtypes = [C.c_ulonglong, _d, _i, _p]
+    L.pfh_infer_vms.argtypes = [_i, _p, _p, _p]
+    L.pfh_pdf_vms.restype = _d
+    L.pfh_pdf_vms.argtypes = [_p, _p, _d]
+    L.pfh_perturb_r_2d.argtypes = [_i, _p, _d, _d, C.c_ulonglong]
     return L
 
 
@@ -227,3 +233,51 @@ def test_load_and_stop_rule(pfh, ref):
     assert H.run(101, 2.0) == 0
     assert H.run(101, 3.0) == 0
     assert H.run(101, 4.0) == 1
+
+
+# ------------------------------------------------------------------------------------------- MODE_2D rotation operators
+def test_vms_operators_match_reference(pfh):
+    """thb_pf2d.cuh against the reference's von Mises-like family (src/Geometry/DirectionalStat.cpp:252-390): inferVMS and pdfVMS
+    are deterministic (1e-12); sampleVMS draws from a different random stream by design, so the sample's mean resultant length
+    (the statistic inferVMS uses) and its circular symmetry are compared within sampling error"""
+    from oracle import refapi as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(4)
+    pt = lambda a: a.ctypes.data_as(_p)
+    # infer: component-major layout r[c * mLR + i]
+    for n in (9, 100):
+        phi = rng.normal(scale=0.3, size=n) + 1.0
+        cs = np.stack([np.cos(phi), np.sin(phi)], 1)
+        r = np.zeros((4, n)); r[0], r[1] = cs[:, 0], cs[:, 1]
+        mu = np.zeros(2); k = np.zeros(1)
+        pfh.pfh_infer_vms(n, pt(r), pt(mu), pt(k))
+        mu0, k0 = ref.infer_vms(cs)
+        assert np.allclose(mu, mu0, atol=1e-12) and abs(k[0] - k0) <= 1e-12
+    # pdf: both branches (kappa < 5: Bessel form, else the Gaussian approximation)
+    for k in (0.9, 0.5, 0.2, 0.05, 0.01):
+        for ang in (0.0, 0.4, 2.5):
+            x = np.array([np.cos(ang), np.sin(ang)]); mu = np.array([np.cos(0.1), np.sin(0.1)])
+            want = ref.pdf_vms(x, mu, k)
+            assert abs(pfh.pfh_pdf_vms(pt(x), pt(mu), k) - want) <= 1e-10 * max(want, 1e-300) + 1e-300
+    # sampling: uniform branch (kappa < 0.1), rejection branch at several concentrations
+    n = 40000
+    for k in (0.97, 0.6, 0.2, 0.02, 1e-3):
+        mine = np.zeros((n, 2))
+        pfh.pfh_sample_vms(12345, k, n, pt(mine))
+        theirs = ref.sample_vms(k, n)
+        assert np.allclose(np.hypot(mine[:, 0], mine[:, 1]), 1.0, atol=1e-12)
+        R1, R0 = mine[:, 0].mean(), theirs[:, 0].mean()                      # mean resultant length along mu = (1, 0)
+        se = max(mine[:, 0].std(), theirs[:, 0].std()) * np.sqrt(2.0 / n)
+        assert abs(R1 - R0) <= 5 * se + 1e-9, (k, R1, R0)
+        assert abs(mine[:, 1].mean()) <= 5 * mine[:, 1].std() / np.sqrt(n) + 1e-9   # symmetric about the mode
+        assert abs(mine[:, 1].std() - theirs[:, 1].std()) <= 0.03 * theirs[:, 1].std() + 1e-9
+    # perturb: every support point turned by its own draw; k1 re-inferred from the cloud grows accordingly
+    m = 2000
+    phi0 = 0.7
+    r = np.zeros((4, m)); r[0], r[1] = np.cos(phi0), np.sin(phi0)
+    pfh.pfh_perturb_r_2d(m, pt(r), 0.01, 2.0, 99)
+    assert np.allclose(np.hypot(r[0], r[1]), 1.0, atol=1e-12) and not r[2:].any()
+    d = np.arctan2(r[1], r[0]) - phi0
+    ref_d = ref.sample_vms(min(1.0, 0.01 * 2.0), m)
+    assert abs(np.std(d) - np.std(np.arctan2(ref_d[:, 1], ref_d[:, 0]))) <= 0.1 * np.std(d)
