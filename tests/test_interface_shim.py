@@ -200,3 +200,21 @@ def test_2d_classification_through_the_shims(shim):
         if recos[k].counter:
             assert np.abs((F2D[k] - F0[k]) - recos[k].F.ravel()).max() <= 3e-5 * np.abs(recos[k].F).max() + 1e-6
             assert np.abs((T2D[k] - T0[k]) - recos[k].T.ravel()).max() <= 3e-5 * np.abs(recos[k].T).max() + 1e-6
+
+
+@pytest.mark.skipif(not REF_HDR.exists(), reason="reference tree not present")
+def test_reference_typed_overloads_compile_against_thunder_headers():
+    """-DTHB_WITH_THUNDER: the Volume& / MPI_Comm& / CTFAttr* overloads of InsertFT (with and without nC) and InsertI2D, i.e. the
+    exact call expressions of Reconstructor::insertI and Optimiser::reconstructRef, compile against THUNDER's OWN headers
+    (syntax-only; tests/host_bind/bind.cpp)"""
+    ref = REF_HDR.parents[2]
+    out = ROOT / "oracle" / "_ref"
+    if not (out / "gen" / "THUNDERConfig.h").exists() or not (out / "deps" / "include").exists():
+        pytest.skip("oracle/_ref build tree not present (oracle/build_ref.sh)")
+    inc = [ROOT / "thunder_b200" / "host", ROOT / "include", ROOT / "oracle" / "ref_shim", out / "gen", ref / "include",
+           ref / "include" / "Functions", ref / "include" / "Geometry", ref / "include" / "Image", ref / "external" / "Eigen3",
+           ref / "external" / "easylogging", ref / "external" / "jsoncpp", out / "deps" / "include", out / "deps" / "boost_1_60_0"]
+    cmd = ["g++", "-std=c++11", "-fopenmp", "-mavx", "-fsyntax-only", "-w", "-DTHB_WITH_THUNDER", "-DSINGLE_PRECISION"]
+    cmd += [f"-I{os.fspath(i)}" for i in inc] + [os.fspath(ROOT / "tests" / "host_bind" / "bind.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]

@@ -77,6 +77,7 @@ void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, Complex* da
 #ifdef THB_WITH_THUNDER
 #include "mpi.h"
 #include "Volume.h"
+#include "Database.h"      // CTFAttr (include/Database.h:302), as gpu/interface/Interface.h:10 includes it
 inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
                      RFLOAT* sigRcpP, CTFAttr* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD,
                      const int* iCol, const int* iRow, RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim,
