@@ -214,7 +214,17 @@ def test_reference_typed_overloads_compile_against_thunder_headers():
     inc = [ROOT / "thunder_b200" / "host", ROOT / "include", ROOT / "oracle" / "ref_shim", out / "gen", ref / "include",
            ref / "include" / "Functions", ref / "include" / "Geometry", ref / "include" / "Image", ref / "external" / "Eigen3",
            ref / "external" / "easylogging", ref / "external" / "jsoncpp", out / "deps" / "include", out / "deps" / "boost_1_60_0"]
-    cmd = ["g++", "-std=c++11", "-fopenmp", "-mavx", "-fsyntax-only", "-w", "-DTHB_WITH_THUNDER", "-DSINGLE_PRECISION"]
-    cmd += [f"-I{os.fspath(i)}" for i in inc] + [os.fspath(ROOT / "tests" / "host_bind" / "bind.cpp")]
+    obj = ROOT / "tests" / "host_bind" / "bind.o"
+    cmd = ["g++", "-std=c++11", "-fopenmp", "-mavx", "-c", "-w", "-DTHB_WITH_THUNDER", "-DSINGLE_PRECISION"]
+    cmd += [f"-I{os.fspath(i)}" for i in inc] + [os.fspath(ROOT / "tests" / "host_bind" / "bind.cpp"), "-o", os.fspath(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-1500:]
+    # ... and LINK: every seam symbol the THUNDER-typed translation unit references (mangled with THUNDER's own types, e.g.
+    # Complex = struct _complex_float_t) is one the shim library exports
+    want = [l.split()[-1] for l in subprocess.check_output(["nm", "-u", os.fspath(obj)]).decode().splitlines()
+            if re.search(r"_Z\d+(Insert|Expect)", l)]
+    have = set(l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", os.fspath(LIB)]).decode().splitlines())
+    assert len(want) >= 2
+    for sym in want:
+        assert sym in have, sym
+    obj.unlink()

@@ -24,7 +24,9 @@
 #include "Precision.h"      // RFLOAT, Complex (include/Precision.h:64-106)
 #else
 typedef float RFLOAT;                       // default build: SINGLE_PRECISION (CMakeLists.txt:48)
-struct Complex { RFLOAT dat[2]; };          // include/Precision.h:100-106
+// include/Precision.h:100-106, with the reference's struct tag: a typedef of a NAMED struct mangles by the tag, so the symbols
+// this library exports (ExpectRotran(_complex_float_t*, ...)) are the ones THUNDER's objects reference
+typedef struct _complex_float_t { float dat[2]; } Complex;
 #endif
 
 // devices this process may use (reference: every visible device with compute capability >= 3)
