@@ -14,3 +14,18 @@ void drive(Volume& F3D, Volume& T3D, MPI_Comm& hemi, MPI_Comm& slav, Complex* da
     InsertI2D(F2D, T2D, O2D, counter, hemi, slav, datP, ctfP, sigP, w, offS, nc, nr, nt, nd, ca, iCol, iRow, 1.32f, false, 1, 2, 100, 10,
               64, 128, 4);
 }
+
+// the E-step seam as Optimiser::expectationG calls it (src/Optimiser.cpp:1702-1711, 1815-1920)
+void drive_expect(Complex* vol, Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, double* trans, double* rot,
+                  double* rotMat, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT, double* pR, double* pT, RFLOAT* baseL, int* iCol, int* iRow)
+{
+    std::vector<int> gpus;
+    getAviDevice(gpus);
+    int* dCol = 0; int* dRow = 0;
+    ExpectPreidx(0, &dCol, &dRow, iCol, iRow, 100);
+    ExpectRotran(traP, trans, rot, rotMat, iCol, iRow, 10, 5, 64, 100);
+    ExpectProject(vol, rotP, rotMat, iCol, iRow, 10, 2, 1, 128, 100);
+    ExpectGlobal3D(rotP, traP, datP, ctfP, sigRcpP, wC, wR, wT, pR, pT, baseL, 0, 1, 10, 5, 100, 4);
+    ExpectGlobal2D(vol, datP, ctfP, sigRcpP, trans, wC, wR, wT, pR, pT, rot, iCol, iRow, 2, 10, 5, 2, 1, 64, 128, 100, 4);
+    ExpectFreeIdx(0, &dCol, &dRow);
+}
