@@ -61,3 +61,37 @@ def test_product_does_not_touch_oracle():
     import subprocess
     out = subprocess.check_output(["ldd", str(ROOT / "thunder_b200" / "lib" / "libthunder_b200.so")]).decode()
     assert "oracle" not in out and "thunder_ref" not in out
+
+
+def test_ctypes_binding_matches_the_header():
+    """every prototype of include/thunder_b200.h against the ctypes signature thunder_b200/capi.py declares for it: same number
+    of parameters, pointer parameters bound as pointers, int / float / double / uint64 as such (catches binding drift)"""
+    import ctypes as C
+    import re
+    from thunder_b200 import capi
+    lib = capi.load()
+    text = (ROOT / "include" / "thunder_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|void|const char\*)\s+(thb_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 40
+    checked = 0
+    for name, args in protos:
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue                                     # not used from Python
+        params = [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() not in ("", "void") else []
+        assert len(params) == len(fn.argtypes), (name, len(params), len(fn.argtypes))
+        for prm, ct in zip(params, fn.argtypes):
+            is_ptr = "*" in prm or "[" in prm
+            if is_ptr:
+                assert ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "_type_"), (name, prm, ct)
+            elif re.match(r"^(const\s+)?double\b", prm):
+                assert ct is C.c_double, (name, prm, ct)
+            elif re.match(r"^(const\s+)?float\b", prm):
+                assert ct is C.c_float, (name, prm, ct)
+            elif re.match(r"^(const\s+)?uint64_t\b", prm):
+                assert ct in (C.c_uint64, C.c_ulonglong, C.c_ulong), (name, prm, ct)
+            elif re.match(r"^(const\s+)?int\b", prm):
+                assert ct is C.c_int, (name, prm, ct)
+        checked += 1
+    assert checked >= 35
