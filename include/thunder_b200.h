@@ -39,6 +39,18 @@
  *   thb_pf_* / thb_expectation Particle::perturb/resample/calVari/.. src/Particle.cpp:1004-1478, 1964-2002, 2309-2495
  *                             + the phase loop of                    src/Optimiser.cpp:1162-1660
  *   thb_reconstruct_insert    the insert loop of reconstructRef      src/Optimiser.cpp:7036-7241
+ *   thb_insert_counts         InsertFT with nC (3D classification)   gpu/interface/Interface.h:267-291, src/Optimiser.cpp:6862-6950
+ *   thb_set_mode,             MODE_2D: ExpectGlobal2D, InsertI2D     gpu/interface/Interface.h:176-198, 239-265
+ *   thb_insert_classes        (Projector / Reconstructor 2D twins)   src/Projector.cpp:337-354, src/Reconstructor.cpp:708-780
+ *   thb_symmetrize            Reconstructor::symmetrizeF/T/O         src/Reconstructor.cpp:2676-2716, include/Geometry/Transformation.h:105-194
+ *   thb_norm_residual,        Optimiser::normCorrection              src/Optimiser.cpp:6201-6393
+ *   thb_scale_images
+ *   thb_upload_stack_at(_async), the per-call host pinning + H2D     gpu/src/cuthunder.cu:5370-5412
+ *   thb_upload_wait, thb_download_stack / thb_reco_upload            (test / staging helpers of the same arrays)
+ *   thb_create / thb_destroy  device selection and per-call set-up   gpu/interface/Interface.h:16 (getAviDevice), gpu/src/cuthunder.cu:5294-5324
+ *   thb_device_count
+ *   thb_last_error, thb_timer, thb_enable_timing, thb_kernel_ms, thb_launch_count, thb_set_option, thb_expect_stats,
+ *   thb_synchronize, thb_version: no counterpart in the reference (error channel, accounting and tuning of this library)
  *
  * Data conventions (identical to the reference seam):
  *   complex = float[2] (re, im); packed image arrays are image-major [img][nPxl];
