@@ -545,7 +545,7 @@ void ref_norm_residual(void* projH, int nImg, int N, float rL, float rNorm, cons
     }
 }
 
-// von Mises-like family of the MODE_2D particle filter (src/Geometry/DirectionalStat.cpp:252-390), as is
+// von Mises-like family of the MODE_2D particle filter (src/Geometry/DirectionalStat.cpp:252-384), as is
 void ref_sample_vms(double k, int n, double* cs)
 {
     dmat4 d(n, 4);                                   // the dmat4 overload is the one Particle::perturb calls (and the one that links)

@@ -237,7 +237,7 @@ def test_load_and_stop_rule(pfh, ref):
 
 # ------------------------------------------------------------------------------------------- MODE_2D rotation operators
 def test_vms_operators_match_reference(pfh):
-    """thb_pf2d.cuh against the reference's von Mises-like family (src/Geometry/DirectionalStat.cpp:252-390): inferVMS and pdfVMS
+    """thb_pf2d.cuh against the reference's von Mises-like family (src/Geometry/DirectionalStat.cpp:252-384): inferVMS and pdfVMS
     are deterministic (1e-12); sampleVMS draws from a different random stream by design, so the sample's mean resultant length
     (the statistic inferVMS uses) and its circular symmetry are compared within sampling error"""
     from oracle import refapi as ref

@@ -8,7 +8,7 @@
 //   perturb   r_i <- r_i (x) d_i,  d_i ~ von Mises-like VMS((1, 0), k = min(PERTURB_K_MAX, k1 * pf))   (quaternion_mul of two
 //             (c, s, 0, 0) vectors = complex multiplication)
 //   calVari   k1 = 1 - | mean(r_i) |                                                                   (inferVMS)
-//   sampleVMS / inferVMS / pdfVMS: src/Geometry/DirectionalStat.cpp:252-390; the concentration the reference samples with is
+//   sampleVMS / inferVMS / pdfVMS: src/Geometry/DirectionalStat.cpp:252-384; the concentration the reference samples with is
 //   kappa(k) = (1 - k)(1 + 2k - k^2) / (k (2 - k)), uniform on the circle below kappa = 0.1, Best-Fisher rejection above.
 #pragma once
 #include "thb_pf.cuh"
