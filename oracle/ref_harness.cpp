@@ -564,6 +564,27 @@ void ref_infer_vms(int n, const double* cs, double* mu2, double* k)
 
 double ref_pdf_vms(const double* x2, const double* mu2, double k) { return pdfVMS(dvec2(x2[0], x2[1]), dvec2(mu2[0], mu2[1]), k); }
 
+// Particle::balanceWeight(PAR_R) in MODE_2D (src/Particle.cpp:2315-2329) with the reference's own inferVMS / pdfVMS
+void ref_balance_r_2d(int n, const double* cs, double* w)
+{
+    dmat2 src(n, 2);
+    for (int i = 0; i < n; i++) { src(i, 0) = cs[2 * i]; src(i, 1) = cs[2 * i + 1]; }
+    dvec2 mu;
+    double k;
+    inferVMS(mu, k, src);
+    for (int i = 0; i < n; i++) w[i] = 1.0 / pdfVMS(dvec2(src(i, 0), src(i, 1)), mu, k);
+}
+
+// Particle::resample(nOut, PAR_C) of the reference class itself (MODE_2D particle with nIn classes)
+int ref_particle_resample_c(int nIn, const int* c, const double* wC, const double* uC, int nOut, int* cOut, double* wOut)
+{
+    Particle p(MODE_2D, nIn, 1, 1, 1, 2.0, 0.01, NULL);
+    for (int i = 0; i < nIn; i++) { p._c(i) = c[i]; p._wC(i) = wC[i]; p._uC(i) = uC[i]; }
+    p.resample(nOut, PAR_C);
+    for (int j = 0; j < nOut; j++) { cOut[j] = (int)p._c(j); wOut[j] = p._wC(j); }
+    return (int)p._topC;
+}
+
 // ---------------------------------------------------------------- MODE_2D (2D classification, demo_2D.json)
 // Projector in MODE_2D holding an already padded half-complex class average [pfN][pfN/2+1] verbatim
 void* ref_projector2d_create(int pf, const float* imgFT, int pfN)

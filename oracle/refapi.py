@@ -77,6 +77,9 @@ def lib():
         L.ref_symmetry_elements.argtypes = [C.c_char_p, _p, _i]
         L.ref_reco_symmetrize.argtypes = [_p, C.c_char_p, _i]
         L.ref_reco_set_O.argtypes = [_p, _p, _i]
+        L.ref_balance_r_2d.argtypes = [_i, _p, _p]
+        L.ref_particle_resample_c.restype = _i
+        L.ref_particle_resample_c.argtypes = [_i, _p, _p, _p, _i, _p, _p]
         L.ref_sample_vms.argtypes = [_d, _i, _p]
         L.ref_infer_vms.argtypes = [_i, _p, _p, _p]
         L.ref_pdf_vms.restype = _d
@@ -196,6 +199,21 @@ def infer_vms(cs):
 def pdf_vms(x, mu, k):
     x = np.ascontiguousarray(x, np.float64); mu = np.ascontiguousarray(mu, np.float64)
     return float(lib().ref_pdf_vms(_ptr(x), _ptr(mu), float(k)))
+
+
+def balance_r_2d(cs):
+    cs = np.ascontiguousarray(cs, np.float64)
+    w = np.zeros(cs.shape[0])
+    lib().ref_balance_r_2d(cs.shape[0], _ptr(cs), _ptr(w))
+    return w
+
+
+def particle_resample_c(c, wC, uC, nOut):
+    """Particle::resample(nOut, PAR_C) of a MODE_2D reference particle -> (classes, priors, top class)"""
+    c = np.ascontiguousarray(c, np.int32); wC = np.ascontiguousarray(wC, np.float64); uC = np.ascontiguousarray(uC, np.float64)
+    cOut = np.zeros(nOut, np.int32); wOut = np.zeros(nOut)
+    top = lib().ref_particle_resample_c(len(c), _ptr(c), _ptr(wC), _ptr(uC), int(nOut), _ptr(cOut), _ptr(wOut))
+    return cOut, wOut, int(top)
 
 
 def symmetry_elements(name):

@@ -90,4 +90,19 @@ void pfh_perturb_r_2d(int mLR, double* r, double k1, double pfac, unsigned long 
     pf::perturb_R_2d(v, pfac, g);
 }
 
+void pfh_balance_r_2d(int mLR, double* r, double* wR)
+{
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.r = r; v.wR = wR; v.n = 1; v.p = 0; v.mLR = mLR; v.lane = -1;
+    pf::balance_R_2d(v);
+}
+
+int pfh_resample_c(int nIn, int* c, double* wC, double* uC, int nOut, int* cOut, double* wOut, unsigned long long seed)
+{
+    pf::Rng g;
+    g.init(seed, 0, 3);
+    return pf::resample_C(c, wC, uC, nIn, nOut, cOut, wOut, g);
+}
+
 }  // extern "C"

@@ -35,6 +35,9 @@ def pfh():
     L.pfh_pdf_vms.restype = _d
     L.pfh_pdf_vms.argtypes = [_p, _p, _d]
     L.pfh_perturb_r_2d.argtypes = [_i, _p, _d, _d, C.c_ulonglong]
+    L.pfh_balance_r_2d.argtypes = [_i, _p, _p]
+    L.pfh_resample_c.restype = _i
+    L.pfh_resample_c.argtypes = [_i, _p, _p, _p, _i, _p, _p, C.c_ulonglong]
     return L
 
 
@@ -281,3 +284,41 @@ def test_vms_operators_match_reference(pfh):
     d = np.arctan2(r[1], r[0]) - phi0
     ref_d = ref.sample_vms(min(1.0, 0.01 * 2.0), m)
     assert abs(np.std(d) - np.std(np.arctan2(ref_d[:, 1], ref_d[:, 0]))) <= 0.1 * np.std(d)
+
+
+def test_class_resampling_and_2d_balance_match_reference(pfh):
+    """resample(n, PAR_C) and balanceWeight(PAR_R) of a MODE_2D particle: the balance is deterministic (1e-10 against inferVMS /
+    pdfVMS composed as the reference does); the class resampling draws its shuffle and u0 from another stream, so ours and the
+    reference's (run on the reference's own Particle class) are both checked for the invariants of systematic resampling:
+    count_i in {floor, ceil}(n w_i u_i / sum), prior 1 / u of the source class, top class = argmax u"""
+    from oracle import refapi as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(8)
+    pt = lambda a: a.ctypes.data_as(_p)
+    n = 50
+    phi = rng.normal(scale=0.4, size=n) - 0.5
+    cs = np.stack([np.cos(phi), np.sin(phi)], 1)
+    r = np.zeros((4, n)); r[0], r[1] = cs[:, 0], cs[:, 1]
+    w = np.zeros(n)
+    pfh.pfh_balance_r_2d(n, pt(r), pt(w))
+    assert np.allclose(w, ref.balance_r_2d(cs), rtol=1e-10)
+
+    nIn, nOut = 20, 12
+    c0 = np.arange(nIn, dtype=np.int32); wC0 = rng.uniform(0.5, 1.5, nIn); uC0 = rng.uniform(0.0, 1.0, nIn) ** 3
+    expect = nOut * wC0 * uC0 / np.sum(wC0 * uC0)
+
+    def check(cOut, wOut, top):
+        cnt = np.bincount(cOut, minlength=nIn)
+        assert cnt.sum() == nOut
+        assert np.all(cnt >= np.floor(expect - 1e-9)) and np.all(cnt <= np.ceil(expect + 1e-9))
+        want = 1.0 / uC0[cOut]                                   # the reference normalises all weights at the end of resample()
+        assert np.allclose(wOut / wOut.sum(), want / want.sum(), rtol=1e-12)
+        assert top == int(np.argmax(uC0))
+
+    for seed in range(5):
+        c, wC, uC = c0.copy(), wC0.copy(), uC0.copy()
+        cOut = np.zeros(nOut, np.int32); wOut = np.zeros(nOut)
+        top = pfh.pfh_resample_c(nIn, pt(c), pt(wC), pt(uC), nOut, pt(cOut), pt(wOut), 1000 + seed)
+        check(cOut, wOut, top)
+        check(*ref.particle_resample_c(c0, wC0, uC0, nOut))

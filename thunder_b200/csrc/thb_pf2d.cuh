@@ -93,5 +93,50 @@ THB_HD void cal_vari_R_2d(const View& v)
     v.S(S_K1) = k;
 }
 
+// Particle::balanceWeight(PAR_R) in MODE_2D (src/Particle.cpp:2315-2329): w_i = 1 / pdfVMS(r_i; mu, k), (mu, k) inferred from
+// the support itself
+THB_HD void balance_R_2d(const View& v)
+{
+    double mu[2], k;
+    infer_vms(v, mu, k);
+    for (int i = 0; i < v.mLR; ++i) {
+        const double x[2] = {v.R(i, 0), v.R(i, 1)};
+        v.WR(i) = 1.0 / pdf_vms(x, mu, k);
+    }
+}
+
+// Particle::resample(nOut, PAR_C) (src/Particle.cpp:1296-1341) on plain arrays: shuffle (gsl_ran_shuffle = Fisher-Yates), top
+// class = the class of the largest uC, w *= u, systematic resampling of nOut classes with one uniform u0 in [0, 1/nOut), new
+// prior 1 / uC of the source (PARTICLE_PRIOR_ONE).  c / wC / uC [nIn] are permuted in place; returns the top class.
+THB_HD int resample_C(int* c, double* wC, double* uC, int nIn, int nOut, int* cOut, double* wOut, Rng& g)
+{
+    for (int i = nIn - 1; i > 0; --i) {
+        const int j = (int)g.uniform_int((uint32_t)(i + 1));
+        if (j != i) {
+            const int ci = c[i]; c[i] = c[j]; c[j] = ci;
+            double x = wC[i]; wC[i] = wC[j]; wC[j] = x;
+            x = uC[i]; uC[i] = uC[j]; uC[j] = x;
+        }
+    }
+    int top = 0;
+    for (int i = 1; i < nIn; ++i) if (uC[i] > uC[top]) top = i;
+    const int topC = c[top];
+    double s = 0.0;
+    for (int i = 0; i < nIn; ++i) { wC[i] *= uC[i]; s += wC[i]; }
+    for (int i = 0; i < nIn; ++i) wC[i] /= s;
+    double last = 0.0;
+    for (int i = 0; i < nIn; ++i) last += wC[i];
+    const double u0 = g.uniform() * (1.0 / nOut);
+    int i = 0;
+    double cum = wC[0];
+    for (int j = 0; j < nOut; ++j) {
+        const double uj = u0 + j * 1.0 / nOut;
+        while (i < nIn - 1 && uj > cum / last) { ++i; cum += wC[i]; }
+        cOut[j] = c[i];
+        wOut[j] = 1.0 / uC[i];
+    }
+    return topC;
+}
+
 }  // namespace pf
 }  // namespace thb
