@@ -97,8 +97,9 @@ int64_t thb_launch_count(thb_ctx* ctx, int reset);
  * which = 0 expect, 1 insert, 2 particle filter, 3 pack/unpack, 4 allreduce ; launches returned in *n */
 double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset);
 int thb_enable_timing(thb_ctx* ctx, int on);
-/* tuning switches (development / A-B measurement): key "expect_impl": 2 = TMA-staged E kernel (default),
- * 1 = direct-gather E kernel; key "insert_impl": see DESIGN.md.  Unknown key -> THB_E_ARG. */
+/* tuning switches (development / A-B measurement): key "expect_impl": 3 = direct gather from the cell layout (default),
+ * 2 = TMA-staged box, 1 = direct gather from the linear layout, 4 / 5 = paired-lane / pixels-on-lanes variants;
+ * "quad_oct", "quad_brick", "sort_rot", "expect_minb", "insert_impl", "stats": see DESIGN.md.  Unknown key -> THB_E_ARG. */
 int thb_set_option(thb_ctx* ctx, const char* key, int value);
 /* staging counters of the E kernel since the last reset (enable with option "stats" = 1): tiles, tiles with a
  * shared-memory box, sum of margins, staged elements, (rotation,tile) pairs on the L1/L2 path, all pairs,

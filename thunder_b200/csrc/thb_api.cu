@@ -148,10 +148,19 @@ static int ensure_quad(thb_ctx* ctx, int slot)
 
 static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
 {
-    for (int i = 0; i < THB_MAX_SLOTS; ++i) {
-        int rc = ensure_quad(ctx, i);
-        if (rc) return rc;
+    // the cell layout (64-byte oct or 32-byte quad) is ONE decision for all slots: when the oct copy of a later slot does not
+    // fit, ensure_quad falls back to the quad layout and the slots built before it are rebuilt in a second sweep
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        const int octBefore = ctx->quadOct;
+        for (int i = 0; i < THB_MAX_SLOTS; ++i) {
+            int rc = ensure_quad(ctx, i);
+            if (rc) return rc;
+        }
+        if (ctx->quadOct == octBefore) break;
     }
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->vols[i].d && !ctx->mode2D && ctx->vols[i].quadOct != ctx->quadOct)
+            return set_error(ctx, THB_E_STATE, "expect: volume slot %d is not in the layout the launch uses", i);
     a.quads = quad_table(ctx);
     a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
     a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
@@ -222,11 +231,8 @@ static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
         a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT);
         if (!a.work) return THB_E_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM_BYTES));
-        attr_set = true;
-    }
+    // the opt-in is per device, and cheap: set it at every launch (a process may hold contexts on several GPUs)
+    THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)E2_SMEM_BYTES));
     span_begin(ctx, KF_EXPECT);
     expect_local_tma_kernel<<<a.nAct, E2_THREADS, E2_SMEM_BYTES, ctx->stream>>>(a);
     span_end(ctx);
@@ -246,11 +252,7 @@ int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
     if (smem > 200 * 1024)
         return set_error(ctx, THB_E_ARG, "expect_local: nR*nT = %d too large for the local-search kernel", a.nR * a.nT);
-    static bool attr_set = false;
-    if (!attr_set) {
-        THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    THB_CUDA(ctx, cudaFuncSetAttribute(expect_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     span_begin(ctx, KF_EXPECT);
     expect_local_kernel<<<a.nAct, E_THREADS, smem, ctx->stream>>>(a);
     span_end(ctx);
@@ -607,8 +609,10 @@ int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
     std::vector<TileDesc> tiles;
     int rc = upload_pixels(ctx, pf, nPxl, iCol, iRow, 0, &ctx->pixE, &ctx->permE, &tiles, ctx->tileW, ctx->tileH);
     if (rc) return rc;
-    cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
+    // the staging counters (option "stats") are independent of the pixel list: they are cleared, not released
+    cudaFree(ctx->tilesE);
     ctx->tilesE = nullptr;
+    if (ctx->dStats) THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 16 * sizeof(unsigned long long)));
     ctx->nTilesE = (int)tiles.size();
     THB_CUDA(ctx, cudaMalloc(&ctx->tilesE, sizeof(TileDesc) * tiles.size()));
     THB_CUDA(ctx, cudaMemcpy(ctx->tilesE, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice));
@@ -692,6 +696,7 @@ int thb_stack_reserve(thb_ctx* ctx, int kind, int capacity)
     if (kind == THB_STACK_EXPECT) THB_CUDA(ctx, cudaMalloc(&s.sig, n * sizeof(float)));
     THB_CUDA(ctx, cudaMalloc(&s.slot, (size_t)capacity * sizeof(int)));
     THB_CUDA(ctx, cudaMemsetAsync(s.slot, 0, (size_t)capacity * sizeof(int), ctx->stream));
+    s.hslot.assign((size_t)capacity, 0);
     s.nImg = capacity;
     return THB_OK;
 }
@@ -750,6 +755,7 @@ static int upload_stack_impl(thb_ctx* ctx, int kind, int base, int nImg, const f
         THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, st));
     else
         THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), st));
+    for (int i = 0; i < nImg; ++i) s.hslot[(size_t)base + i] = slotOfImg ? slotOfImg[i] : 0;
     if (async) {
         THB_CUDA(ctx, cudaEventRecord(ctx->copyDone, st));
         ctx->copyPending = true;
@@ -843,6 +849,7 @@ int thb_pack_stack(thb_ctx* ctx, int kind, int base, int nImg, const float* imgF
         THB_CUDA(ctx, cudaMemcpyAsync(s.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     else
         THB_CUDA(ctx, cudaMemsetAsync(s.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    for (int i = 0; i < nImg; ++i) s.hslot[(size_t)base + i] = slotOfImg ? slotOfImg[i] : 0;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
@@ -908,7 +915,9 @@ int thb_project(thb_ctx* ctx, int slot, int nRot, const double* quat, float* dst
     return THB_OK;
 }
 
-static int check_expect_state(thb_ctx* ctx, const char* who)
+}  // extern "C"
+namespace thb {
+int check_expect_state(thb_ctx* ctx, const char* who)
 {
     if (!ctx->pixE) return set_error(ctx, THB_E_STATE, "%s: E pixel list not set", who);
     if (!ctx->stackE.dat) return set_error(ctx, THB_E_STATE, "%s: E stack not uploaded", who);
@@ -922,6 +931,8 @@ static int check_expect_state(thb_ctx* ctx, const char* who)
     if (vdim < ctx->pf * ctx->N) return set_error(ctx, THB_E_STATE, "%s: volume dimension %d < pf*N = %d", who, vdim, ctx->pf * ctx->N);
     return vdim;
 }
+}  // namespace thb
+extern "C" {
 
 int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, const double* quat, const double* tran,
                      const double* wR, const double* wT, float* uR, float* uT, float* uC, float* base, float* logL)
@@ -990,8 +1001,7 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->vols[slot].d) return set_error(ctx, THB_E_STATE, "expect_scan: no volume in slot %d", slot);
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     const int nImg = ctx->stackE.nImg;
-    std::vector<int> hslot(nImg);
-    THB_CUDA(ctx, cudaMemcpy(hslot.data(), ctx->stackE.slot, sizeof(int) * nImg, cudaMemcpyDeviceToHost));
+    const std::vector<int>& hslot = ctx->stackE.hslot;
     std::vector<int> idx;
     // MODE_2D (classification, src/Optimiser.cpp:756-914): every image is compared with every class reference
     for (int i = 0; i < nImg; ++i) if (ctx->mode2D || hslot[i] == slot) idx.push_back(i);
@@ -1098,17 +1108,46 @@ int thb_reco_reset(thb_ctx* ctx, int slot)
     return THB_OK;
 }
 
+}  // extern "C"
+namespace thb {
+// every image of an insert goes to the accumulator of its slot: all of them must be allocated, with one common edge
+// that holds the M pixel list (a null accumulator would be a sticky illegal-address error inside the kernel)
+int check_insert_slots(thb_ctx* ctx, int nImg, const int* imgIdx, int imgBase, const char* who)
+{
+    int vdim = 0;
+    for (int i = 0; i < THB_MAX_SLOTS; ++i)
+        if (ctx->accs[i].d) {
+            if (vdim && ctx->accs[i].vdim != vdim) return set_error(ctx, THB_E_STATE, "%s: accumulators of different size", who);
+            vdim = ctx->accs[i].vdim;
+        }
+    if (!vdim) return set_error(ctx, THB_E_STATE, "%s: no accumulator allocated (thb_reco_alloc)", who);
+    const std::vector<int>& hs = ctx->stackM.hslot;
+    for (int l = 0; l < nImg; ++l) {
+        const size_t img = imgIdx ? (size_t)imgIdx[l] : (size_t)imgBase + l;
+        if (img >= hs.size()) return set_error(ctx, THB_E_ARG, "%s: image %zu outside the M stack", who, img);
+        const int s = hs[img];
+        if (s < 0 || s >= THB_MAX_SLOTS || !ctx->accs[s].d)
+            return set_error(ctx, THB_E_STATE, "%s: image %zu uses slot %d, which has no accumulator (thb_reco_alloc)", who, img, s);
+    }
+    return THB_OK;
+}
+}  // namespace thb
+extern "C" {
+
 static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,
                        const double* nr, const double* nt, const int* nDraw = nullptr)
 {
     if (!ctx) return THB_E_ARG;
+    if (nImg <= 0 || mReco <= 0 || !w || !nr || !nt) return set_error(ctx, THB_E_ARG, "insert: bad arguments");
     if (nc && !ctx->mode2D) return set_error(ctx, THB_E_STATE, "insert_classes: per-draw classes are a MODE_2D feature (thb_set_mode)");
     if (nc)
         for (size_t i = 0; i < (size_t)nImg * mReco; ++i)
             if (nc[i] < 0 || nc[i] >= THB_MAX_SLOTS || !ctx->accs[nc[i]].d) return set_error(ctx, THB_E_ARG, "insert_classes: nc[%zu] = %d has no accumulator", i, nc[i]);
     if (!ctx->pixM) return set_error(ctx, THB_E_STATE, "insert: M pixel list not set");
     if (!ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "insert: M stack not uploaded");
-    if (nImg <= 0 || mReco <= 0 || !w || !nr || !nt) return set_error(ctx, THB_E_ARG, "insert: bad arguments");
+    if (nDraw)
+        for (int i = 0; i < nImg; ++i)
+            if (nDraw[i] < 0 || nDraw[i] > mReco) return set_error(ctx, THB_E_ARG, "insert_counts: nDraw[%d] = %d outside [0, mReco]", i, nDraw[i]);
     int vdim = 0;
     for (int i = 0; i < THB_MAX_SLOTS; ++i)
         if (ctx->accs[i].d) {
@@ -1120,6 +1159,10 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
         for (int i = 0; i < nImg; ++i)
             if (imgIdx[i] < 0 || imgIdx[i] >= ctx->stackM.nImg) return set_error(ctx, THB_E_ARG, "insert: imgIdx[%d] outside the stack", i);
     if (!imgIdx && nImg > ctx->stackM.nImg) return set_error(ctx, THB_E_ARG, "insert: nImg exceeds the stack");
+    if (!nc) {
+        int rc = check_insert_slots(ctx, nImg, imgIdx, 0, "insert");
+        if (rc) return rc;
+    }
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const int qc = ctx->mode2D ? 2 : 4;      // MODE_2D: nr[nImg][mReco][2] = (cos, sin), as InsertI2D receives it

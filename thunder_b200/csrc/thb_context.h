@@ -22,6 +22,7 @@ struct Stack {
     float* ctf = nullptr;
     float* sig = nullptr;
     int* slot = nullptr;
+    std::vector<int> hslot;      // host copy of slot[] (validation of the slots a launch will touch)
 };
 
 // projector volume in HBM: FFTW half-complex rows of vdim/2+1 elements, stored with a row pitch of
@@ -146,6 +147,8 @@ void resolve_spans(thb_ctx* ctx);
 // launches (thb_launch.cu)
 int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a);
 int launch_insert(thb_ctx* ctx, const InsertArgs& a);
+int check_expect_state(thb_ctx* ctx, const char* who);   // returns the common volume edge, or a negative error
+int check_insert_slots(thb_ctx* ctx, int nImg, const int* imgIdx, int imgBase, const char* who);
 VolTable vol_table(const thb_ctx* ctx);
 AccTable acc_table(const thb_ctx* ctx);
 

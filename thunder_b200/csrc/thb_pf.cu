@@ -187,7 +187,13 @@ static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
         s.prm = p;
         return THB_OK;
     }
-    pf_free(ctx);
+    {   // a reallocation must not lose the image pairing and the position in the random stream (thb_pf_set_image_base may
+        // legitimately precede the first thb_pf_load)
+        const int imgBase = s.imgBase;
+        const uint64_t streamBase = s.streamBase, epoch = s.epoch;
+        pf_free(ctx);
+        s.imgBase = imgBase; s.streamBase = streamBase; s.epoch = epoch;
+    }
     const size_t n = nPar;
     const int mw = p.mLR > p.mLT ? p.mLR : p.mLT;
     THB_CUDA(ctx, cudaMalloc(&s.r, sizeof(double) * n * 4 * p.mLR));
@@ -322,10 +328,8 @@ int thb_pf_set(thb_ctx* ctx, const double* r, const double* t, const double* wR,
 static int expect_args_from_pf(thb_ctx* ctx, ExpectArgs& a)
 {
     PFState& s = ctx->pf_;
-    int vdim = 0;
-    for (int i = 0; i < THB_MAX_SLOTS; ++i)
-        if (ctx->vols[i].d) vdim = ctx->vols[i].vdim;
-    if (!vdim || !ctx->pixE || !ctx->stackE.dat) return set_error(ctx, THB_E_STATE, "expectation: volume / pixels / E stack missing");
+    const int vdim = check_expect_state(ctx, "expectation");    // same volume edge in every slot, >= pf * N
+    if (vdim < 0) return vdim;
     if (s.imgBase < 0 || s.imgBase + s.nPar > ctx->stackE.nImg)
         return set_error(ctx, THB_E_STATE, "expectation: particles [%d,%d) exceed the E stack (%d images)", s.imgBase,
                          s.imgBase + s.nPar, ctx->stackE.nImg);
@@ -402,10 +406,13 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     if (mReco <= 0) return set_error(ctx, THB_E_ARG, "reconstruct_insert: mReco <= 0");
     if (!ctx->pixM || !ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "reconstruct_insert: M pixels / stack missing");
     if (s.imgBase < 0 || s.imgBase + s.nPar > ctx->stackM.nImg) return set_error(ctx, THB_E_STATE, "reconstruct_insert: particles exceed the M stack");
+    {
+        int rc = check_insert_slots(ctx, s.nPar, nullptr, s.imgBase, "reconstruct_insert");
+        if (rc) return rc;
+    }
     int vdim = 0;
     for (int i = 0; i < THB_MAX_SLOTS; ++i)
         if (ctx->accs[i].d) vdim = ctx->accs[i].vdim;
-    if (!vdim) return set_error(ctx, THB_E_STATE, "reconstruct_insert: no accumulator allocated");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = s.nPar;
     if (s.drawCap < mReco) {
