@@ -16,10 +16,10 @@ int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* 
             const float* uRf, const float* uTf, double* scal, double transS, double transQ, unsigned long long seed,
             unsigned long long epoch)
 {
-    std::vector<double> r2(4 * mLR), t2(2 * mLT), w2(mLR > mLT ? mLR : mLT);
+    std::vector<double> r2(4 * mLR), t2(2 * mLT), w2(mLR > mLT ? mLR : mLT), w3(w2.size()), w4(w2.size());
     pf::View v;
     v.r = r; v.t = t; v.wR = wR; v.wT = wT; v.uR = uR; v.uT = uT; v.scal = scal;
-    v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data();
+    v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
     v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1;
     pf::Rng g;
     g.init(seed, 0, epoch);

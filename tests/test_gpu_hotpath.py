@@ -242,6 +242,57 @@ def test_insert_random_two_halves(ctx, problem):
     assert after["counter"] == 2 * before["counter"]
 
 
+def test_insert_slab_ordering_thin_slabs_and_axis_rotations(ctx, problem):
+    """the slab-ordered M kernel (thb_insert2.cuh): every sample must be scattered exactly once whatever the slab thickness -
+    1, 3, 7 planes and the automatic one - including the slices on which its interval arithmetic degenerates (identity: z = 0
+    everywhere; quarter turns about x / y / z: slices along the axes, x = 0 for a whole image, folds on pixel boundaries) and
+    duplicated draws (merged groups); against the oracle and against the image-ordered kernel of round 1"""
+    pb = problem
+    port, ref = _oracle()
+    N, pf = pb["N"], pb["pf"]
+    rng = np.random.default_rng(2024)
+    PM = len(pb["pixM"]["iCol"])
+    nImg, mReco = pb["nImg"], 12
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    nr = np.stack([synth.acg_cloud(pb["par"]["quat"][l], 1e-2, mReco, rng) for l in range(nImg)])
+    h = np.sqrt(0.5)
+    axis = np.array([[1, 0, 0, 0], [h, h, 0, 0], [h, 0, h, 0], [h, 0, 0, h], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1],
+                     [0.5, 0.5, 0.5, 0.5]], float)
+    nr[0, :8] = axis
+    nr[1, :8] = axis[::-1]
+    nr[2, 6:] = nr[2, :6]                  # duplicated rotations: merged groups
+    nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    w = (rng.uniform(0.5, 1.0, nImg) / mReco).astype(np.float32)
+    offS = rng.normal(scale=0.5, size=(nImg, 2))
+    ctx.set_insert_pixels(N, pf, pb["pixM"]["iColPad"], pb["pixM"]["iRowPad"])
+    ctx.upload_stack(capi.STACK_INSERT, datM, ctfM, slotOfImg=pb["slot"])
+    want = {}
+    for s in (0, 1):
+        ctx.reco_alloc(s, N * pf)
+        sel = np.nonzero(pb["slot"] == s)[0]
+        want[s] = port.insert_loop(N * pf, pf, N, datM[sel], ctfM[sel], w[sel], offS[sel], nr[sel], nt[sel],
+                                   pb["pixM"]["iCol"], pb["pixM"]["iRow"])
+    try:
+        for impl, planes in ((0, 0), (0, 1), (0, 3), (0, 7), (0, 50), (3, 5), (1, 0)):
+            ctx.set_option("insert_impl", impl)
+            ctx.set_option("insert_slab_planes", planes)
+            for s in (0, 1):
+                ctx.reco_reset(s)
+            ctx.insert(w, nr, nt, offS=offS)
+            for s in (0, 1):
+                got = ctx.reco_download(s)
+                assert got["counter"] == want[s]["counter"], (impl, planes)
+                assert np.allclose(got["O"], want[s]["O"], rtol=1e-11, atol=1e-11)
+                # T is a sum of non-negative terms: a sample scattered twice or dropped shows up at full size
+                assert _rel_l2(got["T"], want[s]["T"]) <= 1e-6, (impl, planes)
+                assert _rel_l2(got["F"], want[s]["F"]) <= 1e-6, (impl, planes)
+                assert abs(float(got["T"].sum(dtype=np.float64)) / float(want[s]["T"].sum(dtype=np.float64)) - 1) <= 1e-6
+    finally:
+        ctx.set_option("insert_impl", 0)
+        ctx.set_option("insert_slab_planes", 0)
+
+
 def test_reference_library_agrees(ctx, problem):
     """where the reference-built oracle travelled to this box: Projector / Reconstructor classes directly"""
     port, ref = _oracle()

@@ -12,6 +12,7 @@
 #include "thb_expect3.cuh"
 #include "thb_expect4.cuh"
 #include "thb_expect5.cuh"
+#include "thb_insert2.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -261,9 +262,9 @@ int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
     return THB_OK;
 }
 
-int launch_insert(thb_ctx* ctx, const InsertArgs& a)
+// round-1 image-ordered kernel: MODE_2D, per-draw classes, shapes beyond the slab kernel's tables, A/B measurements
+static int launch_insert_legacy(thb_ctx* ctx, const InsertArgs& a)
 {
-    if (a.nImg <= 0) return THB_OK;
     // enough CTAs to fill the chip even for a handful of images
     int split = 1;
     const int tiles = (a.P + M_THREADS * M_KP - 1) / (M_THREADS * M_KP);
@@ -278,6 +279,76 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a)
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
+int launch_insert(thb_ctx* ctx, const InsertArgs& a, const int* hImgIdx)
+{
+    if (a.nImg <= 0) return THB_OK;
+    const bool slab = !ctx->mode2D && !a.drawC && (ctx->insertImpl == 0 || ctx->insertImpl == 3) && a.mReco <= M2_MAXD &&
+                      ctx->segM && ctx->nSegM <= M2_MAXSEG;
+    if (!slab) return launch_insert_legacy(ctx, a);
+    // ---- slab insert (thb_insert2.cuh): grid (image, slab), images of one slot adjacent, slab thickness from the L2 budget
+    const int n = a.vdim;
+    const size_t accBytes = (size_t)(n / 2 + 1) * n * n * sizeof(float4);
+    const size_t budget = (size_t)std::max(ctx->insertSlabMB, 1) << 20;
+    int nSlab = (int)((accBytes + budget - 1) / budget);
+    int th = ctx->insertSlabPlanes > 0 ? ctx->insertSlabPlanes : (n + nSlab - 1) / nSlab;
+    th = std::max(1, std::min(th, n));
+    nSlab = (n + th - 1) / th;
+    const int maxD = (a.mReco + 3) & ~3;
+    const size_t stride = prep_stride(maxD);
+    const int chunk = 16384;
+    std::vector<int> order;
+    for (int l0 = 0; l0 < a.nImg; l0 += chunk) {
+        const int c = std::min(chunk, a.nImg - l0);
+        // images of one slot adjacent in the grid, so that one (slot, slab) block of accumulator is live at a time
+        order.resize(c);
+        bool mixed = false;
+        {
+            const std::vector<int>& hs = ctx->stackM.hslot;
+            auto slotOf = [&](int l) {
+                const size_t img = hImgIdx ? (size_t)hImgIdx[l] : (size_t)a.imgBase + l;
+                return img < hs.size() ? hs[img] : 0;
+            };
+            const int s0 = slotOf(l0);
+            for (int l = 0; l < c; ++l) { order[l] = l; mixed |= slotOf(l0 + l) != s0; }
+            if (mixed) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return slotOf(l0 + x) < slotOf(l0 + y); });
+        }
+        unsigned char* prep = (unsigned char*)scratch(ctx, 11, stride * (size_t)c);
+        if (!prep) return THB_E_CUDA;
+        int* dOrder = nullptr;
+        if (mixed) {
+            dOrder = (int*)scratch(ctx, 12, sizeof(int) * (size_t)c);
+            if (!dOrder) return THB_E_CUDA;
+            THB_CUDA(ctx, cudaMemcpyAsync(dOrder, order.data(), sizeof(int) * (size_t)c, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        InsertSlabArgs s;
+        memset(&s, 0, sizeof(s));
+        s.a = a;
+        s.a.nImg = c;
+        // the chunk's rows of the per-image arrays
+        if (a.imgIdx) s.a.imgIdx = a.imgIdx + l0; else s.a.imgBase = a.imgBase + l0;
+        if (a.w) s.a.w = a.w + l0;
+        if (a.offS) s.a.offS = a.offS + 2 * (size_t)l0;
+        s.a.nr.p = a.nr.p + (size_t)l0 * a.nr.sP;
+        s.a.nt.p = a.nt.p + (size_t)l0 * a.nt.sP;
+        if (a.drawR) s.a.drawR = a.drawR + (size_t)l0 * a.mReco;
+        if (a.drawT) s.a.drawT = a.drawT + (size_t)l0 * a.mReco;
+        if (a.drawCount) s.a.drawCount = a.drawCount + l0;
+        s.seg = (const Seg*)ctx->segM; s.nSeg = ctx->nSegM; s.order = dOrder; s.prep = prep; s.maxD = maxD;
+        s.pf = ctx->pfM; s.rMaxPad = ctx->rMaxPadM; s.zMin = -(n / 2); s.th = th;
+        span_begin(ctx, KF_INSERT);
+        if (ctx->insertImpl == 3)
+            insert_prep_kernel<2><<<c, 128, 0, ctx->stream>>>(s);     // no merging of equal rotations (A/B)
+        else
+            insert_prep_kernel<0><<<c, 128, 0, ctx->stream>>>(s);
+        insert_slab_kernel<<<dim3(c, nSlab), M2_THREADS, 0, ctx->stream>>>(s);
+        span_end(ctx);
+        ctx->launches += 2;
+        THB_CUDA(ctx, cudaGetLastError());
+        if (mixed && l0 + chunk < a.nImg) THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `order` scratch is reused
+    }
     return THB_OK;
 }
 
@@ -327,6 +398,7 @@ int thb_create(thb_ctx** out, int device)
     if (const char* e = getenv("THB_SORT_ROT")) ctx->sortRot = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_MINB")) ctx->expectMinBlocks = atoi(e) >= 3 ? 3 : 2;
     if (const char* e = getenv("THB_INSERT_IMPL")) ctx->insertImpl = atoi(e);
+    if (const char* e = getenv("THB_INSERT_SLAB_MB")) ctx->insertSlabMB = std::max(1, atoi(e));
     if (const char* e = getenv("THB_TILE_W")) ctx->tileW = std::max(1, std::min(16, atoi(e)));
     if (const char* e = getenv("THB_TILE_H")) ctx->tileH = std::max(1, std::min(E2_TILE / ctx->tileW, atoi(e)));
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -366,7 +438,7 @@ void thb_destroy(thb_ctx* ctx)
     }
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
-    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->segM); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
     for (int i = 0; i < THB_N_SCRATCH; ++i) cudaFree(ctx->scratch[i]);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -457,6 +529,16 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
             THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 16 * sizeof(unsigned long long)));
         }
         ctx->statsOn = value != 0;
+        return THB_OK;
+    }
+    if (!strcmp(key, "insert_slab_mb")) {
+        if (value < 1) return set_error(ctx, THB_E_ARG, "set_option: insert_slab_mb must be >= 1");
+        ctx->insertSlabMB = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "insert_slab_planes")) {
+        if (value < 0) return set_error(ctx, THB_E_ARG, "set_option: insert_slab_planes must be >= 0");
+        ctx->insertSlabPlanes = value;
         return THB_OK;
     }
     if (!strcmp(key, "insert_impl")) {
@@ -575,14 +657,37 @@ static void build_tiles(int n, const int* a, const int* b, int unit, int pf, con
     }
 }
 
+// Row-major order: rows j ascending, columns i ascending inside a row, cut into runs of consecutive columns
+// {j, iFirst, count, startIdx} (for the reference's pixel lists with rL = 0: one run per row, and the order is the caller's own)
+static void rowmajor_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm, std::vector<Seg>& segs)
+{
+    perm.resize(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int l, int r) {
+        const int yl = b[l] / unit, yr = b[r] / unit;
+        return yl != yr ? yl < yr : a[l] / unit < a[r] / unit;
+    });
+    segs.clear();
+    for (int k = 0; k < n; ++k) {
+        const int x = a[perm[k]] / unit, y = b[perm[k]] / unit;
+        if (!segs.empty() && segs.back().j == y && segs.back().iFirst + segs.back().count == x && segs.back().count < 32767)
+            segs.back().count++;
+        else
+            segs.push_back(Seg{y, x, 1, k});
+    }
+}
+
 static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int* b, int padded, int4** dst, int** dperm,
-                         std::vector<TileDesc>* tiles = nullptr, int BW = 8, int BH = 8)
+                         std::vector<TileDesc>* tiles = nullptr, int BW = 8, int BH = 8, std::vector<Seg>* segs = nullptr)
 {
     if (nPxl <= 0 || !a || !b) return set_error(ctx, THB_E_ARG, "pixel list is empty or NULL");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<int> perm;
     std::vector<long long> blockOf;
-    blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf, BW, BH);
+    if (segs)
+        rowmajor_order(nPxl, a, b, padded ? pf : 1, perm, *segs);
+    else
+        blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf, BW, BH);
     if (tiles) build_tiles(nPxl, a, b, padded ? pf : 1, pf, perm, blockOf, *tiles);
     int* tmp = (int*)scratch(ctx, 0, sizeof(int) * 2 * (size_t)nPxl);
     if (!tmp) return THB_E_CUDA;
@@ -625,8 +730,18 @@ int thb_set_insert_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
 {
     if (!ctx) return THB_E_ARG;
     if (N <= 0 || pf <= 0) return set_error(ctx, THB_E_ARG, "set_insert_pixels: bad N/pf");
-    int rc = upload_pixels(ctx, pf, nPxl, iColPad, iRowPad, 1, &ctx->pixM, &ctx->permM);
+    // the M pixel list is kept in row-major runs (the slab insert walks index intervals along rows, thb_insert2.cuh)
+    std::vector<Seg> segs;
+    int rc = upload_pixels(ctx, pf, nPxl, iColPad, iRowPad, 1, &ctx->pixM, &ctx->permM, nullptr, 8, 8, &segs);
     if (rc) return rc;
+    cudaFree(ctx->segM);
+    ctx->segM = nullptr;
+    ctx->nSegM = (int)segs.size();
+    THB_CUDA(ctx, cudaMalloc(&ctx->segM, sizeof(Seg) * segs.size()));
+    THB_CUDA(ctx, cudaMemcpy(ctx->segM, segs.data(), sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice));
+    double rmax = 0.0;
+    for (int i = 0; i < nPxl; ++i) rmax = std::max(rmax, hypot((double)iColPad[i], (double)iRowPad[i]));
+    ctx->rMaxPadM = (float)rmax;
     if (ctx->nPxlM != nPxl) free_stack(ctx->stackM);
     ctx->NM = N; ctx->pfM = pf; ctx->nPxlM = nPxl;
     return THB_OK;
@@ -1147,7 +1262,7 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
     if (!ctx->stackM.dat) return set_error(ctx, THB_E_STATE, "insert: M stack not uploaded");
     if (nDraw)
         for (int i = 0; i < nImg; ++i)
-            if (nDraw[i] < 0 || nDraw[i] > mReco) return set_error(ctx, THB_E_ARG, "insert_counts: nDraw[%d] = %d outside [0, mReco]", i, nDraw[i]);
+            if (nDraw[i] < 0) return set_error(ctx, THB_E_ARG, "insert_counts: nDraw[%d] = %d is negative", i, nDraw[i]);   // > mReco: clipped
     int vdim = 0;
     for (int i = 0; i < THB_MAX_SLOTS; ++i)
         if (ctx->accs[i].d) {
@@ -1195,7 +1310,7 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
     a.mode2D = ctx->mode2D;
     a.drawC = nc ? dnc : nullptr;
     a.drawCount = nDraw ? dcount : nullptr;
-    int rc = launch_insert(ctx, a);
+    int rc = launch_insert(ctx, a, imgIdx);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;

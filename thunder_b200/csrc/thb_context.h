@@ -71,7 +71,7 @@ struct PFState {
 
 }  // namespace thb
 
-#define THB_N_SCRATCH 11
+#define THB_N_SCRATCH 14
 struct thb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -84,6 +84,11 @@ struct thb_ctx {
     int4* pixM = nullptr;
     int* permE = nullptr;        // blocked position -> caller's pixel index
     int* permM = nullptr;
+    void* segM = nullptr;        // thb::Seg[]: row-major runs {j, iFirst, count, start} of the M pixel list (slab insert, thb_insert2.cuh)
+    int nSegM = 0;
+    float rMaxPadM = 0.f;        // largest |(pf i, pf j)| of the M pixel list
+    int insertSlabMB = 48;       // option "insert_slab_mb": accumulator bytes one slab of the slab insert may span
+    int insertSlabPlanes = 0;    // option "insert_slab_planes": slab thickness override (tests), 0 = from insert_slab_mb
     thb::TileDesc* tilesE = nullptr;   // 8x8-pixel tiles of the E pixel list (blocked order)
     int nTilesE = 0;
     int mode2D = 0;              // thb_set_mode: references are images, rotations in-plane (MODE_2D of the reference)
@@ -146,7 +151,7 @@ void resolve_spans(thb_ctx* ctx);
 
 // launches (thb_launch.cu)
 int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a);
-int launch_insert(thb_ctx* ctx, const InsertArgs& a);
+int launch_insert(thb_ctx* ctx, const InsertArgs& a, const int* hImgIdx /* host copy of a.imgIdx, or null */);
 int check_expect_state(thb_ctx* ctx, const char* who);   // returns the common volume edge, or a negative error
 int check_insert_slots(thb_ctx* ctx, int nImg, const int* imgIdx, int imgBase, const char* who);
 VolTable vol_table(const thb_ctx* ctx);

@@ -13,7 +13,7 @@
 namespace thb {
 
 struct PFDev {
-    double *r, *t, *wR, *wT, *uR, *uT, *scal, *r2, *t2, *w2;
+    double *r, *t, *wR, *wT, *uR, *uT, *scal, *r2, *t2, *w2, *w3, *w4;
     const float *uRf, *uTf;
     unsigned char* active;
     int* nPhase;
@@ -33,7 +33,7 @@ __device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
     pf::View v;
     v.lane = (int)(threadIdx.x & 31);
     v.r = d.r; v.t = d.t; v.wR = d.wR; v.wT = d.wT; v.uR = d.uR; v.uT = d.uT; v.scal = d.scal;
-    v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2;
+    v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2; v.w3 = d.w3; v.w4 = d.w4;
     v.n = d.nPar; v.p = p; v.mLR = d.mLR; v.mLT = d.mLT;
     return v;
 }
@@ -166,13 +166,16 @@ static PFDev dev_view(thb_ctx* ctx)
     PFDev d;
     const size_t n = s.nPar;
     d.r = s.r; d.t = s.t; d.wR = s.wR; d.wT = s.wT; d.scal = s.scal;
-    // dbl: [uR mLR][uT mLT][r2 4 mLR][t2 2 mLT][w2 max(mLR,mLT)] x nPar doubles
+    // dbl: [uR mLR][uT mLT][r2 4 mLR][t2 2 mLT][w2, w3, w4: max(mLR,mLT) each] x nPar doubles
     double* q = s.dbl;
     d.uR = q; q += n * s.prm.mLR;
     d.uT = q; q += n * s.prm.mLT;
     d.r2 = q; q += n * 4 * s.prm.mLR;
     d.t2 = q; q += n * 2 * s.prm.mLT;
-    d.w2 = q;
+    const size_t mw = s.prm.mLR > s.prm.mLT ? s.prm.mLR : s.prm.mLT;
+    d.w2 = q; q += n * mw;
+    d.w3 = q; q += n * mw;
+    d.w4 = q;
     d.uRf = s.uR; d.uTf = s.uT;
     d.active = s.active; d.nPhase = s.nPhase; d.activeCount = (int*)s.vari;
     d.nPar = s.nPar; d.mLR = s.prm.mLR; d.mLT = s.prm.mLT;
@@ -201,7 +204,7 @@ static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
     THB_CUDA(ctx, cudaMalloc(&s.wR, sizeof(double) * n * p.mLR));
     THB_CUDA(ctx, cudaMalloc(&s.wT, sizeof(double) * n * p.mLT));
     THB_CUDA(ctx, cudaMalloc(&s.scal, sizeof(double) * n * pf::S_COUNT));
-    THB_CUDA(ctx, cudaMalloc(&s.dbl, sizeof(double) * n * (size_t)(5 * p.mLR + 3 * p.mLT + mw)));
+    THB_CUDA(ctx, cudaMalloc(&s.dbl, sizeof(double) * n * (size_t)(5 * p.mLR + 3 * p.mLT + 3 * mw)));
     THB_CUDA(ctx, cudaMalloc(&s.uR, sizeof(float) * n * p.mLR));
     THB_CUDA(ctx, cudaMalloc(&s.uT, sizeof(float) * n * p.mLT));
     THB_CUDA(ctx, cudaMalloc(&s.uC, sizeof(float) * n));
@@ -444,7 +447,7 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     a.nr = View3{s.r, 1, nn, nn * s.prm.mLR};
     a.nt = View3{s.t, 1, nn, nn * s.prm.mLT};
     a.drawR = s.drawR; a.drawT = s.drawT;
-    int rc = launch_insert(ctx, a);
+    int rc = launch_insert(ctx, a, nullptr);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;

@@ -14,10 +14,19 @@
 //   quaternion_mul     src/Geometry/Euler.cpp:13-26
 // Default Config.h switches in force: PARTICLE_PRIOR_ONE, PARTICLE_RECENTRE(_TRANSQ),
 // PARTICLE_ROT_MEAN_USING_STAT_CAL_VARI / _PERTURB, PARTICLE_BALANCE_WEIGHT_R/T; PARTICLE_RHO off.
-// The random stream is a counter-based Philox4x32-10 keyed by (seed, particle, epoch) instead of the
-// reference's thread-local urandom-seeded mt19937 (src/Functions/Random.cpp:51-100): draws are
-// distributed identically but are not the same numbers, so stochastic operators are tested
-// statistically and deterministic ones exactly.
+// Random numbers.  The BIT generator is a counter-based Philox4x32-10 keyed by (seed, particle, epoch) instead of the
+// reference's thread-local urandom-seeded mt19937 (src/Functions/Random.cpp:51-100); everything ABOVE the bit generator
+// is GSL 2.4's published algorithm, the one the reference calls (external/packages/gsl-2.4, pinned by the reference tree):
+//   gsl_rng_uniform        get() / 2^32 for a 32-bit generator          rng/gsl_rng.h:164-168, rng/mt.c (mt_get_double)
+//   gsl_rng_uniform_pos    rejects 0                                     rng/gsl_rng.h:170-181
+//   gsl_rng_uniform_int    scale = range / n, reject k >= n              rng/gsl_rng.h:189-212
+//   gsl_ran_gaussian       polar Box-Muller, returns sigma y sqrt(..)    randist/gauss.c:47-65
+//   gsl_ran_bivariate_gaussian  one polar pair for both coordinates     randist/bigauss.c:34-57
+//   gsl_ran_flat           a (1 - u) + b u                               randist/flat.c:32-40
+//   gsl_ran_shuffle        i = n-1 .. 1: swap(i, uniform_int(i + 1))     randist/shuffle.c:66-78
+// and the operators below consume them in the reference's order.  With the reference's engine swapped for the same bit
+// generator (oracle/ref_harness.cpp: ref_rng_replay) the two particle filters therefore see the SAME random numbers, and
+// every operator - stochastic ones included - is compared exactly (tests/test_pf_host.py, tests/test_gpu_iteration.py).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -35,14 +44,12 @@ struct Rng {
     uint32_t c[4];
     uint32_t o[4];
     int have;
-    double spare;
-    bool hasSpare;
 
     THB_HD void init(uint64_t seed, uint64_t stream, uint64_t epoch)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         c[0] = 0; c[1] = (uint32_t)epoch; c[2] = (uint32_t)stream; c[3] = (uint32_t)(stream >> 32) ^ (uint32_t)(epoch >> 32);
-        have = 0; hasSpare = false; spare = 0.0;
+        have = 0;
     }
     THB_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
     {
@@ -69,23 +76,48 @@ struct Rng {
         if (have == 0) block();
         return o[--have];
     }
-    THB_HD double uniform()   // (0,1), 53 bits
+    THB_HD double uniform() { return (double)u32() * (1.0 / 4294967296.0); }   // gsl_rng_uniform: [0, 1), 32 bits
+    THB_HD double uniform_pos()
     {
-        const uint64_t hi = u32(), lo = u32();
-        const uint64_t v = ((hi << 32) | lo) >> 11;
-        return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+        double x;
+        do { x = uniform(); } while (x == 0.0);
+        return x;
     }
-    THB_HD uint32_t uniform_int(uint32_t n) { return n <= 1 ? 0u : (uint32_t)(uniform() * n) % n; }
-    THB_HD double normal()
+    THB_HD uint32_t uniform_int(uint32_t n)     // gsl_rng_uniform_int: consumes at least one draw, also for n = 1
     {
-        if (hasSpare) { hasSpare = false; return spare; }
-        const double u1 = uniform(), u2 = uniform();
-        const double r = sqrt(-2.0 * log(u1));
-        double s, c2;
-        sincos(6.283185307179586 * u2, &s, &c2);
-        spare = r * s; hasSpare = true;
-        return r * c2;
+        const uint32_t scale = 0xffffffffu / n;
+        uint32_t k;
+        do { k = u32() / scale; } while (k >= n);
+        return k;
     }
+    THB_HD double flat(double a, double b)
+    {
+        const double u = uniform();
+        return a * (1.0 - u) + b * u;
+    }
+    THB_HD double gaussian(double sigma)
+    {
+        double x, y, r2;
+        do {
+            x = -1.0 + 2.0 * uniform_pos();
+            y = -1.0 + 2.0 * uniform_pos();
+            r2 = x * x + y * y;
+        } while (r2 > 1.0 || r2 == 0.0);
+        return sigma * y * sqrt(-2.0 * log(r2) / r2);
+    }
+    THB_HD void bivariate_gaussian(double sx, double sy, double rho, double& x, double& y)
+    {
+        double u, v, r2;
+        do {
+            u = -1.0 + 2.0 * uniform();
+            v = -1.0 + 2.0 * uniform();
+            r2 = u * u + v * v;
+        } while (r2 > 1.0 || r2 == 0.0);
+        const double scale = sqrt(-2.0 * log(r2) / r2);
+        x = sx * u * scale;
+        y = sy * (rho * u + sqrt(1.0 - rho * rho) * v) * scale;
+    }
+    THB_HD double normal() { return gaussian(1.0); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -93,6 +125,7 @@ struct Rng {
 struct View {
     double* r; double* t; double* wR; double* wT; double* uR; double* uT; double* scal;
     double* r2; double* t2; double* w2;      // resampling scratch, same layout as r / t / wR
+    double* w3; double* w4;                  // two more rows of max(mLR, mLT) (the shuffle's scatter)
     long long n;   // stride between consecutive samples/components = number of particles
     long long p;   // particle index
     int mLR, mLT;
@@ -102,6 +135,8 @@ struct View {
     THB_HD double& R2(int i, int c) const { return r2[((long long)c * mLR + i) * n + p]; }
     THB_HD double& T2(int i, int c) const { return t2[((long long)c * mLT + i) * n + p]; }
     THB_HD double& W2(int i) const { return w2[(long long)i * n + p]; }
+    THB_HD double& W3(int i) const { return w3[(long long)i * n + p]; }
+    THB_HD double& W4(int i) const { return w4[(long long)i * n + p]; }
     THB_HD double& WR(int i) const { return wR[(long long)i * n + p]; }
     THB_HD double& WT(int i) const { return wT[(long long)i * n + p]; }
     THB_HD double& UR(int i) const { return uR[(long long)i * n + p]; }
@@ -360,19 +395,28 @@ THB_HD void balance_T(const View& v)
     norm_w(v);
 }
 
+// sampleACG(dst, k1, k2, k3, n) into the scratch rows R2 (src/Geometry/DirectionalStat.cpp:39-62): L = diag(1, sqrt k) of the LLT
+THB_HD void sample_acg_r2(const View& v, double k1, double k2, double k3, Rng& g)
+{
+    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);
+    for (int i = 0; i < v.mLR; ++i) {
+        double d[4];
+        d[0] = g.gaussian(1.0); d[1] = g.gaussian(1.0); d[2] = g.gaussian(1.0); d[3] = g.gaussian(1.0);
+        d[1] *= l1; d[2] *= l2; d[3] *= l3;
+        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+        for (int c = 0; c < 4; ++c) v.R2(i, c) = d[c] / nrm;
+    }
+}
+
 // perturb(pf, PAR_R), MODE_3D
 THB_HD void perturb_R(const View& v, double pfac, Rng& g)
 {
-    const double k1 = pfac * pfac * fmin(1.0, v.S(S_K1)), k2 = pfac * pfac * fmin(1.0, v.S(S_K2)),
-                 k3 = pfac * pfac * fmin(1.0, v.S(S_K3));
-    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);   // LLT of diag(1,k1,k2,k3)
+    sample_acg_r2(v, pfac * pfac * fmin(1.0, v.S(S_K1)), pfac * pfac * fmin(1.0, v.S(S_K2)), pfac * pfac * fmin(1.0, v.S(S_K3)), g);
     double mean[4];
     acg_mean(v, mean);
     const double mc[4] = {mean[0], -mean[1], -mean[2], -mean[3]};
     for (int i = 0; i < v.mLR; ++i) {
-        double d[4] = {g.normal(), l1 * g.normal(), l2 * g.normal(), l3 * g.normal()};
-        const double nrm = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
-        for (int c = 0; c < 4; ++c) d[c] *= nrm;
+        const double d[4] = {v.R2(i, 0), v.R2(i, 1), v.R2(i, 2), v.R2(i, 3)};
         double x[4] = {v.R(i, 0), v.R(i, 1), v.R(i, 2), v.R(i, 3)}, y[4];
         quat_mul(y, mc, x);      // quat = conj(mean) * quat
         quat_mul(x, d, y);       // quat = pert * quat
@@ -385,17 +429,20 @@ THB_HD void perturb_R(const View& v, double pfac, Rng& g)
 // perturb(pf, PAR_T) + reCentre + balanceWeight(PAR_T)
 THB_HD void perturb_T(const View& v, double pfac, double transS, double transQ, Rng& g)
 {
-    const double s0 = v.S(S_S0), s1 = v.S(S_S1);
+    const double s0 = v.S(S_S0), s1 = v.S(S_S1), rho = v.S(S_RHO);
     for (int i = 0; i < v.mLT; ++i) {
-        const double x = s0 * g.normal(), y = s1 * g.normal();   // bivariate Gaussian, rho = 0
+        double x, y;
+        g.bivariate_gaussian(s0, s1, rho / s0 / s1, x, y);
         v.T(i, 0) += x * pfac;
         v.T(i, 1) += y * pfac;
     }
     const double transM = transS * (-2.0 * log(transQ));   // transS * gsl_cdf_chisq_Qinv(transQ, 2)
     for (int i = 0; i < v.mLT; ++i)
         if (hypot(v.T(i, 0), v.T(i, 1)) > transM) {
-            v.T(i, 0) = transS * g.normal();
-            v.T(i, 1) = transS * g.normal();
+            double x, y;
+            g.bivariate_gaussian(transS, transS, 0.0, x, y);
+            v.T(i, 0) = x;
+            v.T(i, 1) = y;
         }
     balance_T(v);
 }
@@ -432,8 +479,8 @@ THB_HD void rank1st(const View& v)
     for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = v.T(b, c);
 }
 
-// calVari(PAR_R) + calVari(PAR_T)
-THB_HD void cal_vari(const View& v, Rng& g)
+// calVari(PAR_R), MODE_3D
+THB_HD void cal_vari_R(const View& v, Rng& g)
 {
     (void)g.uniform_int((uint32_t)v.mLR);   // the reference draws an (unused under C1) anchor index
     double mean[4];
@@ -445,23 +492,43 @@ THB_HD void cal_vari(const View& v, Rng& g)
     v.S(S_K2) = A[10] / A[0];
     v.S(S_K3) = A[15] / A[0];
     left_mul_all(v, mean, false);
+}
+
+// calVari(PAR_T): PARTICLE_RHO off -> rho = 0
+THB_HD void cal_vari_T(const View& v)
+{
     double m, sd;
     mean_sd(v, 0, m, sd); v.S(S_S0) = sd;
     mean_sd(v, 1, m, sd); v.S(S_S1) = sd;
     v.S(S_RHO) = 0.0;
 }
 
+THB_HD void cal_vari(const View& v, Rng& g)
+{
+    cal_vari_R(v, g);
+    cal_vari_T(v);
+}
+
 // resample(n = mLR, PAR_R) and (mLT, PAR_T): shuffle, top, prior x likelihood, systematic resampling
 THB_HD void resample_R(const View& v, Rng& g)
 {
     const int n = v.mLR;
-    for (int i = n - 1; i > 0; --i) {   // Fisher-Yates (gsl_ran_shuffle)
+    // Particle::shuffle (src/Particle.cpp:2202-2300): gsl_ran_shuffle of the identity gives s, then new[s(i)] = old[i]
+    for (int i = 0; i < n; ++i) v.W2(i) = (double)i;
+    for (int i = n - 1; i > 0; --i) {
         const int j = (int)g.uniform_int((uint32_t)(i + 1));
-        if (j != i) {
-            for (int c = 0; c < 4; ++c) { const double x = v.R(i, c); v.R(i, c) = v.R(j, c); v.R(j, c) = x; }
-            double x = v.WR(i); v.WR(i) = v.WR(j); v.WR(j) = x;
-            x = v.UR(i); v.UR(i) = v.UR(j); v.UR(j) = x;
-        }
+        const double x = v.W2(i); v.W2(i) = v.W2(j); v.W2(j) = x;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int d = (int)v.W2(i);
+        for (int c = 0; c < 4; ++c) v.R2(d, c) = v.R(i, c);
+        v.W3(d) = v.WR(i);
+        v.W4(d) = v.UR(i);
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int c = 0; c < 4; ++c) v.R(i, c) = v.R2(i, c);
+        v.WR(i) = v.W3(i);
+        v.UR(i) = v.W4(i);
     }
     const int top = argmax_uR(v);
     for (int c = 0; c < 4; ++c) v.S(S_TOPR + c) = v.R(top, c);
@@ -470,7 +537,7 @@ THB_HD void resample_R(const View& v, Rng& g)
     double cum = 0.0;
     for (int i = 0; i < n; ++i) { v.WR(i) /= s; cum += v.WR(i); v.W2(i) = cum; }   // W2 = cdf
     const double last = v.W2(n - 1);
-    const double u0 = g.uniform() * (1.0 / n);
+    const double u0 = g.flat(0.0, 1.0 / n);
     int i = 0;
     for (int j = 0; j < n; ++j) {
         const double uj = u0 + j * 1.0 / n;
@@ -488,13 +555,21 @@ THB_HD void resample_R(const View& v, Rng& g)
 THB_HD void resample_T(const View& v, Rng& g)
 {
     const int n = v.mLT;
+    for (int i = 0; i < n; ++i) v.W2(i) = (double)i;
     for (int i = n - 1; i > 0; --i) {
         const int j = (int)g.uniform_int((uint32_t)(i + 1));
-        if (j != i) {
-            for (int c = 0; c < 2; ++c) { const double x = v.T(i, c); v.T(i, c) = v.T(j, c); v.T(j, c) = x; }
-            double x = v.WT(i); v.WT(i) = v.WT(j); v.WT(j) = x;
-            x = v.UT(i); v.UT(i) = v.UT(j); v.UT(j) = x;
-        }
+        const double x = v.W2(i); v.W2(i) = v.W2(j); v.W2(j) = x;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int d = (int)v.W2(i);
+        for (int c = 0; c < 2; ++c) v.T2(d, c) = v.T(i, c);
+        v.W3(d) = v.WT(i);
+        v.W4(d) = v.UT(i);
+    }
+    for (int i = 0; i < n; ++i) {
+        for (int c = 0; c < 2; ++c) v.T(i, c) = v.T2(i, c);
+        v.WT(i) = v.W3(i);
+        v.UT(i) = v.W4(i);
     }
     const int top = argmax_uT(v);
     for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = v.T(top, c);
@@ -503,7 +578,7 @@ THB_HD void resample_T(const View& v, Rng& g)
     double cum = 0.0;
     for (int i = 0; i < n; ++i) { v.WT(i) /= s; cum += v.WT(i); v.W2(i) = cum; }
     const double last = v.W2(n - 1);
-    const double u0 = g.uniform() * (1.0 / n);
+    const double u0 = g.flat(0.0, 1.0 / n);
     int i = 0;
     for (int j = 0; j < n; ++j) {
         const double uj = u0 + j * 1.0 / n;
@@ -521,20 +596,20 @@ THB_HD double vari_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K
 THB_HD double vari_T(const View& v) { return sqrt(v.S(S_S0) * v.S(S_S0) * v.S(S_S1) * v.S(S_S1)); }   // rho = 0
 THB_HD double compress_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), -1.0 / 6); }
 
-// Particle::load: ACG cloud about q (random hemisphere sign), Gaussian cloud about t, balanced weights,
-// calVari, peak factor reset (PEAK_FACTOR_MIN = 1e-3).
+// Particle::load (src/Particle.cpp:401-556), in the reference's order of random draws: all ACG samples, then one sign per
+// support point, balanceWeight / calVari of the rotations, the translations (one bivariate draw each), their balanceWeight /
+// calVari, and the nD defocus factors (d + gaussian(s): drawn even when there is no CTF search, nD = 1); peak factor reset
+// (PEAK_FACTOR_MIN = 1e-3).
 THB_HD void load(const View& v, const double q[4], double k1, double k2, double k3, const double t[2], double s0,
-                 double s1, Rng& g)
+                 double s1, Rng& g, int nD = 1, double sD = 0.0)
 {
-    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);
     v.S(S_K1) = k1; v.S(S_K2) = k2; v.S(S_K3) = k3;
     for (int c = 0; c < 4; ++c) v.S(S_TOPR + c) = q[c];
+    sample_acg_r2(v, k1, k2, k3, g);
     for (int i = 0; i < v.mLR; ++i) {
-        double d[4] = {g.normal(), l1 * g.normal(), l2 * g.normal(), l3 * g.normal()};
-        const double nrm = 1.0 / sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
-        for (int c = 0; c < 4; ++c) d[c] *= nrm;
-        const double sgn = (2.0 * g.uniform() - 1.0) >= 0 ? 1.0 : -1.0;
+        const double sgn = g.flat(-1.0, 1.0) >= 0 ? 1.0 : -1.0;
         const double qq[4] = {sgn * q[0], sgn * q[1], sgn * q[2], sgn * q[3]};
+        const double d[4] = {v.R2(i, 0), v.R2(i, 1), v.R2(i, 2), v.R2(i, 3)};
         double y[4];
         quat_mul(y, d, qq);
         for (int c = 0; c < 4; ++c) v.R(i, c) = y[c];
@@ -543,14 +618,18 @@ THB_HD void load(const View& v, const double q[4], double k1, double k2, double 
     }
     for (int i = 0; i < v.mLT; ++i) { v.WT(i) = 1.0 / v.mLT; v.UT(i) = 1.0 / v.mLT; }
     balance_R(v);
+    cal_vari_R(v, g);
     v.S(S_S0) = s0; v.S(S_S1) = s1;
     for (int c = 0; c < 2; ++c) v.S(S_TOPT + c) = t[c];
     for (int i = 0; i < v.mLT; ++i) {
-        v.T(i, 0) = s0 * g.normal() + t[0];
-        v.T(i, 1) = s1 * g.normal() + t[1];
+        double x, y;
+        g.bivariate_gaussian(s0, s1, 0.0, x, y);
+        v.T(i, 0) = x + t[0];
+        v.T(i, 1) = y + t[1];
     }
     balance_T(v);
-    cal_vari(v, g);
+    cal_vari_T(v);
+    for (int i = 0; i < nD; ++i) (void)g.gaussian(sD);
     v.S(S_SCORE) = 1.0;
     v.S(S_NPHASE) = 0.0;
     v.S(S_VARIR) = 1.79769313486231570e308;
