@@ -41,7 +41,7 @@ UNIT = "particles/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=100000, help="particles in the whole job (resident stack)")
@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--mlr", type=int, default=125)
     ap.add_argument("--mlt", type=int, default=9)
     ap.add_argument("--mreco", type=int, default=100)
-    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic particles generated on the host")
+    ap.add_argument("--pool", type=int, default=0, help="distinct synthetic particles generated on the host (0 = one batch: every particle of a step is distinct)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles of the CPU baseline sample (0 = one per host thread per step for --impl reference, three for cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -251,7 +251,7 @@ def main():
     # ---- synthetic pool (host), tiled into the resident stack
     B = args.batch
     nRes = max(args.particles // world, B)
-    pool = min(args.pool, B)
+    pool = min(args.pool, B) if args.pool > 0 else B
     rng = np.random.default_rng(1000 + rank)
     slot_pool = (np.arange(pool) % 2).astype(np.int32)
     par = synth.make_particles(pool, N, pixE, lambda q: ctx.project(0, q), seed=100 + rank)
@@ -364,7 +364,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        k2 = max(1, min(args.steps, 2))
+        k2 = max(1, args.steps)                                  # as many end-to-end steps as device-timed ones
         upload_async(0)
         step(0, e2e=True)                                        # warm the e2e path (staging buffers, copy stream)
         ctx.upload_wait()

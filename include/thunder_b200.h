@@ -304,6 +304,20 @@ int thb_pf_set(thb_ctx* ctx, const double* r, const double* t, const double* wR,
 /* particle p <-> image imgBase + p of the resident stacks; streamBase offsets the per-particle random
  * stream (use the global index of the first particle so that ranks / batches draw different numbers) */
 int thb_pf_set_image_base(thb_ctx* ctx, int imgBase, uint64_t streamBase);
+/* Reproducibility.  The random numbers of particle p in a call are GSL 2.4's distributions (the ones the reference calls,
+ * src/Particle.cpp, src/Geometry/DirectionalStat.cpp:39-62) over a Philox4x32-10 bit stream keyed by (seed, streamBase + p,
+ * epoch): thb_pf_load, thb_expectation, thb_reconstruct_insert and thb_pf_op each advance the context's epoch counter e by one
+ * and use the key (e << 20) (+ phase + 1 for the operators after the likelihoods of a phase).  thb_pf_set_epoch sets e, so that
+ * a run - or the reference's Particle class with the same bit generator plugged in (as the parity tests do) - can replay it. */
+int thb_pf_set_epoch(thb_ctx* ctx, uint64_t epoch);
+/* keep the marginal weights uR / uT of the first nPhases phases of the following thb_expectation calls (0 = off);
+ * thb_pf_get_trace copies them out: uR[nPhases][nPar][mLR], uT[nPhases][nPar][mLT], base[nPhases][nPar] (the largest
+ * log-likelihood of the phase, which the weights are relative to); any pointer may be NULL */
+int thb_pf_trace(thb_ctx* ctx, int nPhases);
+int thb_pf_get_trace(thb_ctx* ctx, int nPhases, float* uR, float* uT, float* base);
+/* and the traced supports: st[nPhases][2][nPar][4 mLR + 2 mLT] = (r[mLR][4], t[mLT][2]) after the perturbation ([..][0]) and after
+ * the resampling ([..][1]) of every traced phase */
+int thb_pf_get_trace_states(thb_ctx* ctx, int nPhases, double* st);
 /* the support indices drawn by the last thb_reconstruct_insert: drawR/drawT [nPar][mReco] */
 int thb_pf_get_draws(thb_ctx* ctx, int mReco, int* drawR, int* drawT);
 /* E-step of one iteration over all loaded particles (particle p <-> image imgBase + p of the E stack):

@@ -64,8 +64,59 @@ static unsigned long g_seed_epoch = 1;
 struct TlsRng { gsl_rng* eng; unsigned long epoch; };
 static __thread TlsRng t_rng = {NULL, 0};
 
+// ------------------------------------------------------------------------------------------
+// Replay bit generator.  To compare the device particle filter with the reference's Particle class draw by draw, the
+// reference's engine can be swapped for a counter-based Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random
+// numbers: as easy as 1, 2, 3", SC'11) keyed by (seed, stream = particle, epoch = call / phase) - the bit generator the
+// CUDA library uses - wrapped as a gsl_rng_type with the range of mt19937 (0 .. 2^32 - 1, get_double = get / 2^32), so that
+// every GSL distribution the reference calls (gsl_ran_gaussian, gsl_ran_bivariate_gaussian, gsl_ran_flat, gsl_ran_shuffle,
+// gsl_rng_uniform_int) runs unchanged on top of it.  Restated here from the published algorithm, independent of the product.
+// ------------------------------------------------------------------------------------------
+struct PhiloxState { uint32_t k0, k1, c[4], o[4]; int have; };
+
+static void philox_block(PhiloxState* p)
+{
+    uint32_t x0 = p->c[0], x1 = p->c[1], x2 = p->c[2], x3 = p->c[3], a = p->k0, b = p->k1;
+    for (int r = 0; r < 10; r++)
+    {
+        const uint64_t m0 = (uint64_t)0xD2511F53u * x0, m1 = (uint64_t)0xCD9E8D57u * x2;
+        const uint32_t y0 = (uint32_t)(m1 >> 32) ^ x1 ^ a, y1 = (uint32_t)m1, y2 = (uint32_t)(m0 >> 32) ^ x3 ^ b, y3 = (uint32_t)m0;
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    p->o[0] = x0; p->o[1] = x1; p->o[2] = x2; p->o[3] = x3;
+    p->c[0]++;
+    p->have = 4;
+}
+static void philox_key(PhiloxState* p, unsigned long long seed, unsigned long long stream, unsigned long long epoch)
+{
+    p->k0 = (uint32_t)seed; p->k1 = (uint32_t)(seed >> 32);
+    p->c[0] = 0; p->c[1] = (uint32_t)epoch; p->c[2] = (uint32_t)stream;
+    p->c[3] = (uint32_t)(stream >> 32) ^ (uint32_t)(epoch >> 32);
+    p->have = 0;
+}
+static void philox_set(void* st, unsigned long int seed) { philox_key((PhiloxState*)st, seed, 0, 0); }
+static unsigned long int philox_get(void* st)
+{
+    PhiloxState* p = (PhiloxState*)st;
+    if (p->have == 0) philox_block(p);
+    return p->o[--p->have];            // words of a block are handed out last to first
+}
+static double philox_get_double(void* st) { return philox_get(st) / 4294967296.0; }
+static const gsl_rng_type philox_type = {"thb_philox4x32_10", 0xffffffffUL, 0, sizeof(PhiloxState), &philox_set, &philox_get,
+                                         &philox_get_double};
+
+static int g_replay = 0;
+static unsigned long long g_rp_seed = 0, g_rp_stream = 0, g_rp_epoch = 0, g_rp_stride = 1;   // keys of the loops below (stream + stride * image index)
+static __thread gsl_rng* t_replay = NULL;
+
 gsl_rng* get_random_engine()
 {
+    if (g_replay)
+    {
+        if (!t_replay) t_replay = gsl_rng_alloc(&philox_type);
+        return t_replay;
+    }
     if (!t_rng.eng) t_rng.eng = gsl_rng_alloc(gsl_rng_mt19937);
     if (t_rng.epoch != g_seed_epoch)
     {
@@ -73,6 +124,12 @@ gsl_rng* get_random_engine()
         t_rng.epoch = g_seed_epoch;
     }
     return t_rng.eng;
+}
+
+static inline void replay_key(unsigned long long seed, unsigned long long stream, unsigned long long epoch)
+{
+    if (!t_replay) t_replay = gsl_rng_alloc(&philox_type);
+    philox_key((PhiloxState*)t_replay->state, seed, stream, epoch);
 }
 
 static void quiet_loggers()
@@ -132,6 +189,32 @@ void ref_set_seed(unsigned long seed)
 }
 
 int ref_sizeof_rfloat() { return (int)sizeof(RFLOAT); }
+
+// replay mode of the random engine (see PhiloxState above).  ref_rng_key keys the CALLING thread's engine (class-level calls
+// from Python); ref_rng_replay_loop sets the keys the driver loops below use per image: stream + l, epoch
+void ref_rng_replay(int on) { g_replay = on; }
+void ref_rng_key(unsigned long long seed, unsigned long long stream, unsigned long long epoch) { replay_key(seed, stream, epoch); }
+void ref_rng_replay_loop(unsigned long long seed, unsigned long long stream, unsigned long long epoch)
+{
+    g_rp_seed = seed; g_rp_stream = stream; g_rp_epoch = epoch;
+}
+void ref_rng_replay_stride(unsigned long long stride) { g_rp_stride = stride; }   // image l of a loop <-> stream + stride * l
+// n raw draws of the calling thread's engine through GSL's own entry points (the pin of the product's restatement of them):
+// kind 0 gsl_rng_uniform, 1 gsl_ran_gaussian(sigma = a), 2 gsl_rng_uniform_int(n = a), 3 gsl_ran_flat(a, b),
+// 4 gsl_ran_bivariate_gaussian(a, b, rho = 0.3): x, y interleaved
+void ref_rng_draw(int kind, int n, double a, double b, double* out)
+{
+    gsl_rng* e = get_random_engine();
+    for (int i = 0; i < n; i++)
+        switch (kind)
+        {
+            case 0: out[i] = gsl_rng_uniform(e); break;
+            case 1: out[i] = gsl_ran_gaussian(e, a); break;
+            case 2: out[i] = (double)gsl_rng_uniform_int(e, (unsigned long)a); break;
+            case 3: out[i] = gsl_ran_flat(e, a, b); break;
+            case 4: gsl_ran_bivariate_gaussian(e, a, b, 0.3, out + 2 * i, out + 2 * i + 1); break;
+        }
+}
 
 // ---------------------------------------------------------------- pixel list
 // Optimiser::allocPreCalIdx (reference src/Optimiser.cpp:7991-8041), run on a minimal
@@ -818,11 +901,40 @@ double ref_pdfACG(const double* x4, const double* A16_rowmajor)
 //   nPhaseOut   phases actually run per image
 //   dvpOut      optional [nImg][mLR*mLT] log-likelihoods of the LAST phase run (for parity)
 // ------------------------------------------------------------------------------------------
+void ref_expectation_local_trace(void** pars, int nImg, void* projH, const float* datP, const float* ctfP,
+                           const float* sigRcpP, const int* iCol, const int* iRow, int nPxl, int N, int mLR,
+                           int mLT, double perturbFactorL, double perturbFactorS, int minPhase, int maxPhase,
+                           int noDecreaseLimit, double decreaseFactor, int fixedPhases, int simd,
+                           int nThread, int* nPhaseOut, float* dvpOut, const float* uRIn, const float* uTIn, float* uROwn,
+                           float* uTOwn, int nTrace, double* condOut, const double* rIn, const double* tIn, double* rPert,
+                           double* tPert, double* rRes, double* tRes);
+
 void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP, const float* ctfP,
                            const float* sigRcpP, const int* iCol, const int* iRow, int nPxl, int N, int mLR,
                            int mLT, double perturbFactorL, double perturbFactorS, int minPhase, int maxPhase,
                            int noDecreaseLimit, double decreaseFactor, int fixedPhases, int simd,
                            int nThread, int* nPhaseOut, float* dvpOut)
+{
+    ref_expectation_local_trace(pars, nImg, projH, datP, ctfP, sigRcpP, iCol, iRow, nPxl, N, mLR, mLT, perturbFactorL,
+                                perturbFactorS, minPhase, maxPhase, noDecreaseLimit, decreaseFactor, fixedPhases, simd, nThread,
+                                nPhaseOut, dvpOut, NULL, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+}
+
+// The same loop with a trace.  Replay mode (ref_rng_replay(1), ref_rng_replay_loop(seed, stream, epoch)): the engine of image
+// l is keyed (seed, stream + l, epoch) before the first perturbation and (seed, stream + l, epoch + phase + 1) before the
+// post-likelihood operators of every phase - the points at which the CUDA library keys its own generator.
+//   uROwn / uTOwn   out, [nTrace][nImg][mLR / mLT]: the marginal weights THIS loop computed in each phase (relative to its
+//                   final baseline = the maximum), from the reference's project / translate / logDataVSPrior
+//   uRIn / uTIn     in, same shape, optional: weights handed to setUR / setUT INSTEAD of the loop's own (the device's, so that
+//                   both filters resample from bit-identical weights and their states can be compared exactly; the loop's
+//                   own weights are still computed, from ITS state, and returned for the comparison with the device's)
+void ref_expectation_local_trace(void** pars, int nImg, void* projH, const float* datP, const float* ctfP,
+                           const float* sigRcpP, const int* iCol, const int* iRow, int nPxl, int N, int mLR,
+                           int mLT, double perturbFactorL, double perturbFactorS, int minPhase, int maxPhase,
+                           int noDecreaseLimit, double decreaseFactor, int fixedPhases, int simd,
+                           int nThread, int* nPhaseOut, float* dvpOut, const float* uRIn, const float* uTIn, float* uROwn,
+                           float* uTOwn, int nTrace, double* condOut, const double* rIn, const double* tIn, double* rPert,
+                           double* tPert, double* rRes, double* tRes)
 {
     RefProjector* P = (RefProjector*)projH;
     if (nThread <= 0) nThread = omp_get_max_threads();
@@ -851,6 +963,7 @@ void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP
         {
             if (phase == 0)
             {
+                if (g_replay) replay_key(g_rp_seed, g_rp_stream + g_rp_stride * (unsigned long long)l, g_rp_epoch);
                 par.perturb(perturbFactorL, PAR_R);
                 par.perturb(perturbFactorL, PAR_T);
             }
@@ -858,6 +971,22 @@ void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP
             {
                 par.perturb(perturbFactorS, PAR_R);
                 par.perturb(perturbFactorS, PAR_T);
+            }
+
+            if (phase < nTrace)
+            {
+                if (rPert) for (int i = 0; i < mLR; i++) for (int j = 0; j < 4; j++) rPert[(((size_t)phase * nImg + l) * mLR + i) * 4 + j] = par._r(i, j);
+                if (tPert) for (int i = 0; i < mLT; i++) for (int j = 0; j < 2; j++) tPert[(((size_t)phase * nImg + l) * mLT + i) * 2 + j] = par._t(i, j);
+                if (rIn)
+                {
+                    for (int i = 0; i < mLR; i++) for (int j = 0; j < 4; j++) par._r(i, j) = rIn[(((size_t)phase * nImg + l) * mLR + i) * 4 + j];
+                    par.balanceWeight(PAR_R);
+                }
+                if (tIn)
+                {
+                    for (int i = 0; i < mLT; i++) for (int j = 0; j < 2; j++) par._t(i, j) = tIn[(((size_t)phase * nImg + l) * mLT + i) * 2 + j];
+                    par.balanceWeight(PAR_T);
+                }
             }
 
             RFLOAT baseLine = GSL_NAN;
@@ -911,6 +1040,15 @@ void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP
                 }
             }
 
+            if (phase < nTrace)
+            {
+                if (uROwn) for (int iR = 0; iR < mLR; iR++) uROwn[((size_t)phase * nImg + l) * mLR + iR] = wR(iR);
+                if (uTOwn) for (int iT = 0; iT < mLT; iT++) uTOwn[((size_t)phase * nImg + l) * mLT + iT] = wT(iT);
+                if (uRIn) for (int iR = 0; iR < mLR; iR++) wR(iR) = uRIn[((size_t)phase * nImg + l) * mLR + iR];
+                if (uTIn) for (int iT = 0; iT < mLT; iT++) wT(iT) = uTIn[((size_t)phase * nImg + l) * mLT + iT];
+            }
+            if (g_replay) replay_key(g_rp_seed, g_rp_stream + g_rp_stride * (unsigned long long)l, g_rp_epoch + (unsigned long long)phase + 1);
+
             par.setUC(wC(0), 0);
             for (int iR = 0; iR < mLR; iR++) par.setUR(wR(iR), iR);
             par.keepHalfHeightPeak(PAR_R);
@@ -923,6 +1061,20 @@ void ref_expectation_local(void** pars, int nImg, void* projH, const float* datP
             par.calVari(PAR_T);
             par.resample(mLR, PAR_R);
             par.resample(mLT, PAR_T);
+
+            if (phase < nTrace)
+            {
+                if (rRes) for (int i = 0; i < mLR; i++) for (int j = 0; j < 4; j++) rRes[(((size_t)phase * nImg + l) * mLR + i) * 4 + j] = par._r(i, j);
+                if (tRes) for (int i = 0; i < mLT; i++) for (int j = 0; j < 2; j++) tRes[(((size_t)phase * nImg + l) * mLT + i) * 2 + j] = par._t(i, j);
+            }
+            if (condOut && phase < nTrace)
+            {
+                dmat44 A;
+                inferACG(A, par._r);
+                Eigen::SelfAdjointEigenSolver<dmat44> es(A);
+                const double lo = es.eigenvalues()(0), hi = es.eigenvalues()(3);
+                condOut[(size_t)phase * nImg + l] = (lo > 0) ? hi / lo : 1e300;
+            }
 
             phasesRun = phase + 1;
 
@@ -976,6 +1128,8 @@ void ref_insert_loop(void* recoH, void** pars, int nImg, const float* datP, cons
         Complex* transImgP = poolTransImgP + (size_t)nPxl * omp_get_thread_num();
         const Complex* orignImgP = (const Complex*)datP + (size_t)nPxl * l;
         dvec2 offset(offS ? offS[2 * l] : 0, offS ? offS[2 * l + 1] : 0);
+
+        if (g_replay && pars) replay_key(g_rp_seed, g_rp_stream + g_rp_stride * (unsigned long long)l, g_rp_epoch);
 
         for (int m = 0; m < mReco; m++)
         {

@@ -125,6 +125,13 @@ def lib():
         L.ref_expectation_local.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _i, _d, _i,
                                             _i, _i, _p, _p]
         L.ref_insert_loop.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i]
+        L.ref_expectation_local_trace.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _i, _d, _i,
+                                                  _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]
+        L.ref_rng_replay.argtypes = [_i]
+        L.ref_rng_key.argtypes = [C.c_ulonglong] * 3
+        L.ref_rng_replay_loop.argtypes = [C.c_ulonglong] * 3
+        L.ref_rng_draw.argtypes = [_i, _i, _d, _d, _p]
+        L.ref_rng_replay_stride.argtypes = [C.c_ulonglong]
         if hasattr(L, "ref_inferACG"):
             L.ref_inferACG.argtypes = [_p, _i, _p, _p, _p]
             L.ref_pdfACG.restype = _d
@@ -430,6 +437,66 @@ def expectation_local(pars, proj, datP, ctfP, sigRcpP, iCol, iRow, N, mLR, mLT, 
                                 mLT, pfL, pfS, minPhase, maxPhase, noDecreaseLimit, decreaseFactor, fixedPhases, simd,
                                 nThread, _ptr(nPhase), _ptr(dvp))
     return nPhase, dvp
+
+
+def expectation_local_trace(pars, proj, datP, ctfP, sigRcpP, iCol, iRow, N, mLR, mLT, fixedPhases, pfL=2.0, pfS=0.5, uRIn=None,
+                            uTIn=None, simd=1, nThread=1, rIn=None, tIn=None, want_states=False):
+    """the phase loop with its marginal weights per phase returned (own) and, optionally, replaced by uRIn / uTIn
+    [phase][nImg][mLR / mLT] before setUR / setUT (ref_expectation_local_trace in ref_harness.cpp)"""
+    datP = np.ascontiguousarray(datP, np.complex64)
+    nImg, P = datP.shape
+    ctfP = np.ascontiguousarray(ctfP, np.float32); sigRcpP = np.ascontiguousarray(sigRcpP, np.float32)
+    parr = (_p * nImg)(*[p.h for p in pars])
+    nPhase = np.zeros(nImg, np.int32)
+    uROwn = np.zeros((fixedPhases, nImg, mLR), np.float32); uTOwn = np.zeros((fixedPhases, nImg, mLT), np.float32)
+    f = lambda a, shp: None if a is None else np.ascontiguousarray(a, np.float32).reshape(shp)
+    uRIn = f(uRIn, uROwn.shape); uTIn = f(uTIn, uTOwn.shape)
+    cond = np.zeros((fixedPhases, nImg))
+    g = lambda a, shp: None if a is None else np.ascontiguousarray(a, np.float64).reshape(shp)
+    shR, shT = (fixedPhases, nImg, mLR, 4), (fixedPhases, nImg, mLT, 2)
+    rIn = g(rIn, shR); tIn = g(tIn, shT)
+    rPert = np.zeros(shR) if want_states else None; tPert = np.zeros(shT) if want_states else None
+    rRes = np.zeros(shR) if want_states else None; tRes = np.zeros(shT) if want_states else None
+    lib().ref_expectation_local_trace(parr, nImg, proj.h, _ptr(datP), _ptr(ctfP), _ptr(sigRcpP), _ptr(iCol), _ptr(iRow), P, N, mLR,
+                                      mLT, pfL, pfS, 3, 100, 1, 0.95, fixedPhases, simd, nThread, _ptr(nPhase), None, _ptr(uRIn),
+                                      _ptr(uTIn), _ptr(uROwn), _ptr(uTOwn), fixedPhases, _ptr(cond), _ptr(rIn), _ptr(tIn), _ptr(rPert),
+                                      _ptr(tPert), _ptr(rRes), _ptr(tRes))
+    if want_states:
+        return uROwn, uTOwn, cond, dict(rPert=rPert, tPert=tPert, rRes=rRes, tRes=tRes)
+    return uROwn, uTOwn, cond
+
+
+class replay:
+    """context manager: the reference's random engine swapped for the Philox bit generator of the CUDA library (ref_harness.cpp)"""
+
+    def __init__(self, seed=0, stream=0, epoch=0):
+        self.key = (seed, stream, epoch)
+
+    def __enter__(self):
+        lib().ref_rng_replay(1)
+        lib().ref_rng_key(*self.key)
+        lib().ref_rng_replay_loop(*self.key)
+        lib().ref_rng_replay_stride(1)
+        return self
+
+    def __exit__(self, *a):
+        lib().ref_rng_replay(0)
+
+
+def rng_key(seed, stream, epoch):
+    lib().ref_rng_key(seed, stream, epoch)
+
+
+def rng_replay_loop(seed, stream, epoch, stride=1):
+    """image l of the driver loops draws from the stream (seed, stream + stride * l, epoch)"""
+    lib().ref_rng_replay_loop(seed, stream, epoch)
+    lib().ref_rng_replay_stride(stride)
+
+
+def rng_draw(kind, n, a=0.0, b=0.0):
+    out = np.zeros(2 * n if kind == 4 else n)
+    lib().ref_rng_draw(kind, n, a, b, _ptr(out))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- MODE_2D

@@ -29,3 +29,32 @@ void drive_expect(Complex* vol, Complex* rotP, Complex* traP, Complex* datP, RFL
     ExpectGlobal2D(vol, datP, ctfP, sigRcpP, trans, wC, wR, wT, pR, pT, rot, iCol, iRow, 2, 10, 5, 2, 1, 64, 128, 100, 4);
     ExpectFreeIdx(0, &dCol, &dRow);
 }
+
+// the local-search seam in the order Optimiser::expectationG calls it (src/Optimiser.cpp:2169-2342 set-up, 2484-2700 per phase)
+void drive_local(Complex* vol, Complex* datP, RFLOAT* ctfP, RFLOAT* defO, RFLOAT* sigRcpP, RFLOAT* freQ, int* iCol, int* iRow)
+{
+    int* dCol = 0; int* dRow = 0;
+    ExpectPreidx(0, &dCol, &dRow, iCol, iRow, 100);
+    RFLOAT* devfreQ = 0;
+    ExpectPrefre(0, &devfreQ, freQ, 100);
+    ManagedArrayTexture* mgr = new ManagedArrayTexture();
+    mgr->Init(1, 128, 0);
+    Complex* devdatP = 0; RFLOAT* devctfP = 0; RFLOAT* devdefO = 0; RFLOAT* devsigP = 0;
+    ExpectLocalIn(0, &devdatP, &devctfP, &devdefO, &devsigP, 100, 4, 1);
+    ManagedCalPoint* mcp = new ManagedCalPoint();
+    mcp->Init(1, 1, 0, 125, 9, 1, 100);
+    RFLOAT *wC, *wR, *wT, *wD; double *oldR, *oldT, *oldD, *trans, *rot, *dpara;
+    ExpectLocalHostA(0, &wC, &wR, &wT, &wD, &oldR, &oldT, &oldD, &trans, &rot, &dpara, 125, 9, 1, 1);
+    ExpectLocalV3D(0, mgr, vol, 128);
+    ExpectLocalV2D(0, mgr, vol, 128 * 65);
+    ExpectLocalP(0, devdatP, devctfP, devdefO, devsigP, datP, ctfP, defO, sigRcpP, 0, 3, 100, 1);
+    ExpectLocalRTD(0, mcp, oldR, oldT, oldD, trans, rot, dpara);
+    ExpectLocalPreI3D(0, 0, mgr, mcp, devdefO, devfreQ, dCol, dRow, 0.f, 0.1f, 0.f, 0.f, 2, 64, 128, 100, 1);
+    ExpectLocalPreI2D(0, 0, mgr, mcp, devdefO, devfreQ, dCol, dRow, 0.f, 0.1f, 0.f, 0.f, 2, 64, 128, 100, 1);
+    ExpectLocalM(0, 0, mcp, devdatP, devctfP, devsigP, wC, wR, wT, wD, 1.0, 100);
+    ExpectLocalHostF(0, &wC, &wR, &wT, &wD, &oldR, &oldT, &oldD, &trans, &rot, &dpara, 1);
+    ExpectLocalFin(0, &devdatP, &devctfP, &devdefO, &devfreQ, &devsigP, 1);
+    delete mcp;
+    delete mgr;
+    ExpectFreeIdx(0, &dCol, &dRow);
+}

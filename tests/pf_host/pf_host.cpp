@@ -12,9 +12,20 @@ using namespace thb;
 extern "C" {
 
 // arrays are component-major for one particle: r[c*mLR+i], t[c*mLT+i]; scal[20]; uR/uT double in/out
+int pfh_run_s(int op, double arg, int mLR, int mLT, double* r, double* t, double* wR, double* wT, double* uR, double* uT,
+              const float* uRf, const float* uTf, double* scal, double transS, double transQ, unsigned long long seed,
+              unsigned long long stream, unsigned long long epoch);
 int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* wR, double* wT, double* uR, double* uT,
             const float* uRf, const float* uTf, double* scal, double transS, double transQ, unsigned long long seed,
             unsigned long long epoch)
+{
+    return pfh_run_s(op, arg, mLR, mLT, r, t, wR, wT, uR, uT, uRf, uTf, scal, transS, transQ, seed, 0, epoch);
+}
+
+// the same with the random stream (= particle index on the device) given
+int pfh_run_s(int op, double arg, int mLR, int mLT, double* r, double* t, double* wR, double* wT, double* uR, double* uT,
+              const float* uRf, const float* uTf, double* scal, double transS, double transQ, unsigned long long seed,
+              unsigned long long stream, unsigned long long epoch)
 {
     std::vector<double> r2(4 * mLR), t2(2 * mLT), w2(mLR > mLT ? mLR : mLT), w3(w2.size()), w4(w2.size());
     pf::View v;
@@ -22,7 +33,7 @@ int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* 
     v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
     v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1;
     pf::Rng g;
-    g.init(seed, 0, epoch);
+    g.init(seed, stream, epoch);
     switch (op) {
         case 1: pf::perturb_R(v, arg, g); break;
         case 2: pf::perturb_T(v, arg, transS, transQ, g); break;
@@ -38,6 +49,17 @@ int pfh_run(int op, double arg, int mLR, int mLT, double* r, double* t, double* 
             break;
         }
         case 101: return pf::stop_rule(v, (int)arg, 3, 0.95, 1) ? 1 : 0;
+        case 102: {   // Particle::rand x arg (<= mLR): (class, rotation, translation, defocus) indices; uR[i] = 1000 rotation + translation
+            const int m = (int)arg;
+            for (int i = 0; i < m && i < mLR; ++i) {
+                (void)g.uniform_int(1);
+                const double a = (double)g.uniform_int((uint32_t)mLR);
+                const double b = (double)g.uniform_int((uint32_t)mLT);
+                (void)g.uniform_int(1);
+                uR[i] = 1000.0 * a + b;
+            }
+            break;
+        }
         default: return -1;
     }
     return 0;
@@ -58,6 +80,22 @@ void pfh_rng(unsigned long long seed, unsigned long long stream, unsigned long l
     g.init(seed, stream, epoch);
     for (int i = 0; i < n; i++) uni[i] = g.uniform();
     for (int i = 0; i < n; i++) nor[i] = g.normal();
+}
+
+// the GSL entry points restated in pf::Rng, by kind as ref_rng_draw of oracle/ref_harness.cpp
+void pfh_rng_draw(unsigned long long seed, unsigned long long stream, unsigned long long epoch, int kind, int n, double a, double b,
+                  double* out)
+{
+    pf::Rng g;
+    g.init(seed, stream, epoch);
+    for (int i = 0; i < n; i++)
+        switch (kind) {
+            case 0: out[i] = g.uniform(); break;
+            case 1: out[i] = g.gaussian(a); break;
+            case 2: out[i] = (double)g.uniform_int((uint32_t)a); break;
+            case 3: out[i] = g.flat(a, b); break;
+            case 4: g.bivariate_gaussian(a, b, 0.3, out[2 * i], out[2 * i + 1]); break;
+        }
 }
 
 // ---- MODE_2D rotation operators (thb_pf2d.cuh)

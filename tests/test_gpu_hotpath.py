@@ -35,6 +35,7 @@ def _rel_l2(a, b):
 # ------------------------------------------------------------------------------------------- golden, N = 16
 def test_project_golden(ctx, golden):
     N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.drop_volumes()          # the session context may hold volumes of another size from earlier tests
     ctx.set_expect_pixels(N, pf, golden["pixE_iCol"], golden["pixE_iRow"])
     ctx.set_volume(0, golden["volFT"])
     assert np.array_equal(ctx.get_volume(0), golden["volFT"])
@@ -47,6 +48,7 @@ def test_project_golden(ctx, golden):
 
 def test_expect_local_golden(ctx, golden):
     N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.drop_volumes()          # the session context may hold volumes of another size from earlier tests
     ctx.set_expect_pixels(N, pf, golden["pixE_iCol"], golden["pixE_iRow"])
     ctx.set_volume(0, golden["volFT"])
     ctx.upload_stack(capi.STACK_EXPECT, golden["dat"][None], golden["ctf"][None], golden["sigRcp"][None])
@@ -61,6 +63,7 @@ def test_expect_local_golden(ctx, golden):
 
 def test_insert_golden(ctx, golden):
     N, pf = int(golden["N"]), int(golden["pf"])
+    ctx.drop_volumes()
     ctx.set_insert_pixels(N, pf, golden["pixM_iColPad"], golden["pixM_iRowPad"])
     ctx.upload_stack(capi.STACK_INSERT, golden["datM"], golden["ctfM"])
     ctx.reco_alloc(0, N * pf)

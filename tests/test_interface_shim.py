@@ -19,7 +19,10 @@ ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "thunder_b200" / "lib" / "libthb_interface.so"
 REF_HDR = Path(os.environ.get("THB_REFERENCE", "/root/reference")) / "gpu" / "interface" / "Interface.h"
 MIRRORED = ["getAviDevice", "ExpectPreidx", "ExpectFreeIdx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "InsertFT",
-            "ExpectGlobal2D", "InsertI2D"]
+            "ExpectGlobal2D", "InsertI2D", "ExpectPrefre", "ExpectLocalIn", "ExpectLocalV2D", "ExpectLocalV3D", "ExpectLocalP",
+            "ExpectLocalHostA", "ExpectLocalRTD", "ExpectLocalPreI2D", "ExpectLocalPreI3D", "ExpectLocalM", "ExpectLocalHostF",
+            "ExpectLocalFin"]
+LOCAL_SEAM = MIRRORED[9:]
 _p, _i = C.c_void_p, C.c_int
 
 
@@ -36,6 +39,7 @@ def test_shim_exports_mirrored_names():
 
 def _params(text, name):
     """argument names of the first declaration of `name` in a header, in order"""
+    text = re.sub(r"//[^\n]*", "", text)          # the reference's header carries commented-out parameters (ExpectLocalM)
     m = re.search(rf"\bvoid\s+{name}\s*\((.*?)\)\s*;", text, flags=re.S)
     assert m, name
     args = [a.strip() for a in m.group(1).replace("\n", " ").split(",")]
@@ -48,7 +52,7 @@ def test_argument_order_matches_reference_header():
     thunder_b200/host/Interface.h documents (Volume& -> pointer + vdim, MPI_Comm& dropped)"""
     ref = REF_HDR.read_text()
     ours = (ROOT / "thunder_b200" / "host" / "Interface.h").read_text()
-    for name in ("ExpectPreidx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "ExpectGlobal2D"):
+    for name in ["ExpectPreidx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "ExpectGlobal2D"] + LOCAL_SEAM:
         assert _params(ours, name) == _params(ref, name), name
     assert _params(ours, "InsertI2D") == [a for a in _params(ref, "InsertI2D") if a not in ("hemi", "slav")]
     want = [a for a in _params(ref, "InsertFT") if a not in ("hemi", "slav")]
@@ -228,3 +232,47 @@ def test_reference_typed_overloads_compile_against_thunder_headers():
     for sym in want:
         assert sym in have, sym
     obj.unlink()
+
+
+@pytest.mark.gpu
+def test_local_search_through_the_reference_protocol(shim):
+    """ExpectLocalIn / V3D / P / HostA / RTD / PreI3D / M / HostF / Fin called in the reference's own order (one image in flight
+    per slot, one synchronous ExpectLocalM per image and phase, src/Optimiser.cpp:2484-2700) give the oracle's marginal weights -
+    and the same numbers as the batched entry point"""
+    from oracle import portapi as port
+    N, pf = 32, 2
+    rng = np.random.default_rng(15)
+    vol = synth.padded_ft(synth.phantom(N, 8, seed=2), pf)
+    pix = port.pixel_list(N, pf, 14.0, 1.0)
+    iCol, iRow = np.ascontiguousarray(pix["iCol"]), np.ascontiguousarray(pix["iRow"])
+    P = len(iCol)
+    nImg, nPhase, nR, nT = 5, 3, 37, 9
+    par = synth.make_particles(nImg, N, pix, lambda q: np.stack([port.project(vol, pf, port.rotate3D(x), iCol, iRow) for x in q]),
+                               seed=3, snr_scale=4.0)
+    quat = np.stack([[synth.acg_cloud(par["quat"][l], 1e-4 * (ph + 1), nR, rng) for ph in range(nPhase)] for l in range(nImg)])
+    tran = par["tran"][:, None, None, :] + rng.normal(scale=0.5, size=(nImg, nPhase, nT, 2))
+    wRp = rng.uniform(0.5, 1.5, (nImg, nPhase, nR)); wRp /= wRp.sum(-1, keepdims=True)
+    wTp = rng.uniform(0.5, 1.5, (nImg, nPhase, nT)); wTp /= wTp.sum(-1, keepdims=True)
+    volc = np.ascontiguousarray(vol)
+    dat = np.ascontiguousarray(par["dat"]); ctf = np.ascontiguousarray(par["ctf"]); sig = np.ascontiguousarray(par["sigRcp"])
+    wC = np.zeros((nImg, nPhase), np.float32); wR = np.zeros((nImg, nPhase, nR), np.float32); wT = np.zeros((nImg, nPhase, nT), np.float32)
+    oldC = 1.0
+    shim.thbi_ExpectLocalProtocol.argtypes = [_i, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, C.c_double, _i, _p, _p, _p]
+    shim.thbi_ExpectLocalProtocol(0, _ptr(volc), N * pf, pf, N, _ptr(iCol), _ptr(iRow), P, _ptr(dat), _ptr(ctf), _ptr(sig), nImg, nPhase, nR, nT,
+                                  _ptr(quat), _ptr(tran), _ptr(wRp), _ptr(wTp), oldC, 2, _ptr(wC), _ptr(wR), _ptr(wT))
+    for l in range(nImg):
+        for ph in range(nPhase):
+            o = port.expect_local(vol, pf, N, iCol, iRow, par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l, ph], tran[l, ph], wRp[l, ph],
+                                  wTp[l, ph])
+            big = o["uR"] > 1e-5 * o["uR"].max()
+            assert np.allclose(wR[l, ph][big], o["uR"][big], rtol=5e-3), (l, ph)
+            big = o["uT"] > 1e-5 * o["uT"].max()
+            assert np.allclose(wT[l, ph][big], o["uT"][big], rtol=5e-3), (l, ph)
+            assert np.allclose(wC[l, ph], o["uC"], rtol=5e-3)
+    # the batched entry point on the supports of the last phase: the same numbers
+    ph = nPhase - 1
+    uC = np.zeros(nImg, np.float32); uR = np.zeros((nImg, nR), np.float32); uT = np.zeros((nImg, nT), np.float32); bl = np.zeros(nImg, np.float32)
+    q2 = np.ascontiguousarray(quat[:, ph]); t2 = np.ascontiguousarray(tran[:, ph]); r2 = np.ascontiguousarray(wRp[:, ph]); s2 = np.ascontiguousarray(wTp[:, ph])
+    shim.thbi_ExpectLocalBatch(0, _ptr(volc), N * pf, pf, N, _ptr(iCol), _ptr(iRow), P, _ptr(dat), _ptr(ctf), _ptr(sig), nImg, nR, nT,
+                               _ptr(q2), _ptr(t2), _ptr(r2), _ptr(s2), _ptr(uC), _ptr(uR), _ptr(uT), _ptr(bl))
+    assert np.allclose(uR, wR[:, ph], rtol=2e-4, atol=1e-30) and np.allclose(uT, wT[:, ph], rtol=2e-4, atol=1e-30)

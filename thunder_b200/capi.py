@@ -84,6 +84,10 @@ def _sig(lib):
     f = lib.thb_sigma_accumulate; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
+    f = lib.thb_pf_set_epoch; f.restype = _i; f.argtypes = [_p, C.c_uint64]
+    f = lib.thb_pf_trace; f.restype = _i; f.argtypes = [_p, _i]
+    f = lib.thb_pf_get_trace; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p]
+    f = lib.thb_pf_get_trace_states; f.restype = _i; f.argtypes = [_p, _i, _p]
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
     f = lib.thb_expect_local; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i] + [_p] * 9
     f = lib.thb_expect_scan; f.restype = _i; f.argtypes = [_p, _i, _i, _i] + [_p] * 9
@@ -162,6 +166,7 @@ class Context:
         self.accdim = {}
         self.pf_params = None
         self.nPar = 0
+        self.mode2D = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -221,6 +226,12 @@ class Context:
         a = _arr(iColPad, np.int32); b = _arr(iRowPad, np.int32)
         self._chk(self.lib.thb_set_insert_pixels(self.h, N, pf, len(a), _ptr(a), _ptr(b)))
         self.nPxlM = len(a)
+
+    def drop_volumes(self):
+        """release every projector volume and accumulator (a mode round trip does that), keeping pixel lists and stacks"""
+        m = MODE_2D if self.mode2D else MODE_3D
+        self.set_mode(MODE_3D if self.mode2D else MODE_2D)
+        self.set_mode(m)
 
     def set_mode(self, mode):
         """MODE_3D (default) / MODE_2D: 2D classification - image references, in-plane rotations passed as (cos, sin)"""
@@ -485,6 +496,29 @@ class Context:
 
     def pf_set_image_base(self, imgBase, streamBase=0):
         self._chk(self.lib.thb_pf_set_image_base(self.h, int(imgBase), int(streamBase)))
+
+    def pf_set_epoch(self, epoch):
+        self._chk(self.lib.thb_pf_set_epoch(self.h, int(epoch)))
+
+    def pf_trace(self, nPhases):
+        self._chk(self.lib.thb_pf_trace(self.h, int(nPhases)))
+
+    def pf_get_trace(self, nPhases):
+        R, T = self.pf_params.mLR, self.pf_params.mLT
+        uR = np.empty((nPhases, self.nPar, R), np.float32); uT = np.empty((nPhases, self.nPar, T), np.float32)
+        base = np.empty((nPhases, self.nPar), np.float32)
+        self._chk(self.lib.thb_pf_get_trace(self.h, int(nPhases), _ptr(uR), _ptr(uT), _ptr(base)))
+        self.trace_base = base
+        return uR, uT
+
+    def pf_get_trace_states(self, nPhases):
+        """supports of the traced phases: dict(rPert, tPert, rRes, tRes) of [nPhases][nPar][mLR][4] / [..][mLT][2]"""
+        R, T, n = self.pf_params.mLR, self.pf_params.mLT, self.nPar
+        st = np.empty((nPhases, 2, n, 4 * R + 2 * T))
+        self._chk(self.lib.thb_pf_get_trace_states(self.h, int(nPhases), _ptr(st)))
+        r = st[..., :4 * R].reshape(nPhases, 2, n, R, 4); t = st[..., 4 * R:].reshape(nPhases, 2, n, T, 2)
+        return dict(rPert=np.ascontiguousarray(r[:, 0]), tPert=np.ascontiguousarray(t[:, 0]), rRes=np.ascontiguousarray(r[:, 1]),
+                    tRes=np.ascontiguousarray(t[:, 1]))
 
     def pf_get_draws(self, mReco):
         dR = np.empty((self.nPar, mReco), np.int32); dT = np.empty((self.nPar, mReco), np.int32)

@@ -13,6 +13,7 @@
 #include "thb_expect4.cuh"
 #include "thb_expect5.cuh"
 #include "thb_insert2.cuh"
+#include "thb_expect6.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -166,6 +167,30 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
     a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
     a.work = nullptr;
+    // a handful of images (the reference's one-image-at-a-time seam, the tail of an adaptive E-step): one CTA per image would
+    // leave the chip idle - spread every image over (pixel chunk, rotation group) CTAs instead (thb_expect6.cuh)
+    if (ctx->expectImpl == 3 && (ctx->expectSpread == 1 || (ctx->expectSpread < 0 && a.nAct * 4 <= ctx->smCount))) {
+        const int nRT = a.nR * a.nT;
+        double* table = (double*)scratch(ctx, 13, sizeof(double) * (size_t)a.nAct * nRT);
+        a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * nRT);
+        if (!table || !a.work) return THB_E_CUDA;
+        THB_CUDA(ctx, cudaMemsetAsync(table, 0, sizeof(double) * (size_t)a.nAct * nRT, ctx->stream));
+        const int nGroups = (a.nR + 31) / 32, tiles = (a.P + E3_TILE - 1) / E3_TILE;
+        const int nChunk = std::max(1, std::min(tiles, (2 * ctx->smCount + nGroups * a.nAct - 1) / (nGroups * a.nAct)));
+        const dim3 grid(nChunk, nGroups, a.nAct);
+        span_begin(ctx, KF_EXPECT);
+        if (ctx->mode2D)
+            expect_spread_kernel<false, true><<<grid, E6_THREADS, E3_SMEM_BYTES, ctx->stream>>>(a, table, nChunk);
+        else if (ctx->quadOct)
+            expect_spread_kernel<true, false><<<grid, E6_THREADS, E3_SMEM_BYTES, ctx->stream>>>(a, table, nChunk);
+        else
+            expect_spread_kernel<false, false><<<grid, E6_THREADS, E3_SMEM_BYTES, ctx->stream>>>(a, table, nChunk);
+        expect_table_epilogue_kernel<<<a.nAct, 256, 0, ctx->stream>>>(a, table, a.work);
+        span_end(ctx);
+        ctx->launches += 2;
+        THB_CUDA(ctx, cudaGetLastError());
+        return THB_OK;
+    }
     // more translations than one pass of the local-search kernel carries (the scans: nT = 30 in demo_2D.json): the variant
     // with 15 per pass halves the number of passes over the gather
     const bool wideT = ctx->expectImpl == 3 && a.nT > E_TC;
@@ -529,6 +554,10 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
             THB_CUDA(ctx, cudaMemset(ctx->dStats, 0, 16 * sizeof(unsigned long long)));
         }
         ctx->statsOn = value != 0;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_spread")) {   // -1: automatic (few images), 0: never, 1: always
+        ctx->expectSpread = value < 0 ? -1 : (value ? 1 : 0);
         return THB_OK;
     }
     if (!strcmp(key, "insert_slab_mb")) {

@@ -67,6 +67,11 @@ struct PFState {
     int* drawT = nullptr;
     int drawCap = 0;
     uint64_t epoch = 0;          // advances the counter-based RNG stream between calls
+    float* traceR = nullptr;     // option "pf_trace": the marginal weights of every phase, [traceCap][nPar][mLR] / [..][mLT]
+    float* traceT = nullptr;
+    float* traceB = nullptr;     // [traceCap][nPar]: the baselines (largest log-likelihood of the phase)
+    double* traceSt = nullptr;   // and the support: [traceCap][2: after the perturbation, after the resampling][nPar][4 mLR + 2 mLT]
+    int traceCap = 0, traceN = 0, traceWant = 0;
 };
 
 }  // namespace thb
@@ -101,6 +106,7 @@ struct thb_ctx {
     int quadOct = 1;             // option "quad_oct": whole trilinear cell in one 64-byte element (8x volume bytes; default,
                                  // falls back to the 32-byte quad when HBM is short)
     int sortRot = 0;             // option "sort_rot"
+    int expectSpread = -1;       // option "expect_spread": spread each image over many CTAs (-1: when a launch has few images)
     int expectMinBlocks = 2;     // CTAs per SM the quad kernel is compiled for (2 or 3)
 
     thb::Volume3 vols[thb::THB_MAX_SLOTS];

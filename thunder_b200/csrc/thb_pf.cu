@@ -70,11 +70,24 @@ struct StepArgs {
     int doPost, doPre;
     int phase;              // phase whose likelihoods were just computed (doPost)
     double prePf;           // perturbation factor of the next perturb (doPre)
+    double* traceRes;       // optional [nPar][4 mLR + 2 mLT]: the support after the resampling (doPost)
+    double* tracePert;      // optional, same shape: the support after the perturbation (doPre)
     double transS, transQ;
     int minPhase, maxPhase, fixedPhases, noDecreaseLimit;
     double decreaseFactor;
     uint64_t epoch;
 };
+
+// support of particle v.p -> dst[p][4 mLR + 2 mLT] as r[mLR][4], t[mLT][2] (test trace; every lane writes the same values)
+__device__ void pf_trace_store(const pf::View& v, double* dst)
+{
+    double* o = dst + (size_t)v.p * (4 * v.mLR + 2 * v.mLT);
+    for (int i = 0; i < v.mLR; ++i)
+        for (int c = 0; c < 4; ++c) o[4 * i + c] = v.R(i, c);
+    o += 4 * v.mLR;
+    for (int i = 0; i < v.mLT; ++i)
+        for (int c = 0; c < 2; ++c) o[2 * i + c] = v.T(i, c);
+}
 
 __global__ void pf_step_kernel(PFDev d, StepArgs a)
 {
@@ -92,6 +105,7 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
         pf::resample_R(v, g);
         pf::resample_T(v, g);
         pf::norm_w(v);
+        if (a.traceRes) pf_trace_store(v, a.traceRes);
         d.nPhase[p] = a.phase + 1;
         v.S(pf::S_NPHASE) = (double)(a.phase + 1);
         bool done;
@@ -108,6 +122,7 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
     if (cont && a.doPre) {
         pf::perturb_R(v, a.prePf, g);
         pf::perturb_T(v, a.prePf, a.transS, a.transQ, g);
+        if (a.tracePert) pf_trace_store(v, a.tracePert);
         if ((threadIdx.x & 31) == 0) atomicAdd(d.activeCount, 1);
     }
 }
@@ -156,7 +171,7 @@ void pf_free(thb_ctx* ctx)
     cudaFree(s.r); cudaFree(s.t); cudaFree(s.wR); cudaFree(s.wT); cudaFree(s.scal);
     cudaFree(s.uR); cudaFree(s.uT); cudaFree(s.uC); cudaFree(s.base); cudaFree(s.active); cudaFree(s.nPhase);
     cudaFree(s.vari); cudaFree(s.drawR); cudaFree(s.drawT);
-    cudaFree(s.dbl);
+    cudaFree(s.dbl); cudaFree(s.traceR); cudaFree(s.traceT); cudaFree(s.traceSt); cudaFree(s.traceB);
     s = PFState();
 }
 
@@ -192,10 +207,10 @@ static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
     }
     {   // a reallocation must not lose the image pairing and the position in the random stream (thb_pf_set_image_base may
         // legitimately precede the first thb_pf_load)
-        const int imgBase = s.imgBase;
+        const int imgBase = s.imgBase, traceWant = s.traceWant;
         const uint64_t streamBase = s.streamBase, epoch = s.epoch;
         pf_free(ctx);
-        s.imgBase = imgBase; s.streamBase = streamBase; s.epoch = epoch;
+        s.imgBase = imgBase; s.streamBase = streamBase; s.epoch = epoch; s.traceWant = traceWant;
     }
     const size_t n = nPar;
     const int mw = p.mLR > p.mLT ? p.mLR : p.mLT;
@@ -370,10 +385,26 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
     sa.minPhase = p.minPhase; sa.maxPhase = p.maxPhase; sa.fixedPhases = p.fixedPhases;
     sa.noDecreaseLimit = p.noDecreaseLimit; sa.decreaseFactor = p.decreaseFactor;
 
+    s.traceN = 0;
+    if (s.traceWant > 0 && s.traceCap != s.traceWant) {
+        cudaFree(s.traceR); cudaFree(s.traceT); cudaFree(s.traceSt); cudaFree(s.traceB);
+        s.traceR = s.traceT = s.traceB = nullptr;
+        s.traceSt = nullptr;
+        s.traceCap = 0;
+        THB_CUDA(ctx, cudaMalloc(&s.traceR, sizeof(float) * (size_t)s.traceWant * s.nPar * p.mLR));
+        THB_CUDA(ctx, cudaMalloc(&s.traceT, sizeof(float) * (size_t)s.traceWant * s.nPar * p.mLT));
+        THB_CUDA(ctx, cudaMalloc(&s.traceB, sizeof(float) * (size_t)s.traceWant * s.nPar));
+        THB_CUDA(ctx, cudaMalloc(&s.traceSt, sizeof(double) * (size_t)s.traceWant * 2 * s.nPar * (4 * p.mLR + 2 * p.mLT)));
+        s.traceCap = s.traceWant;
+    }
+    const size_t stSz = (size_t)s.nPar * (4 * p.mLR + 2 * p.mLT);
+    const bool tracing = s.traceWant > 0 && s.traceSt;
+    if (tracing) THB_CUDA(ctx, cudaMemsetAsync(s.traceSt, 0, sizeof(double) * (size_t)s.traceCap * 2 * stSz, ctx->stream));
     span_begin(ctx, KF_PF);
     pf_begin_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d);
     sa.doPost = 0; sa.doPre = 1; sa.phase = -1; sa.prePf = p.perturbFactorL; sa.epoch = (s.epoch << 20);
     THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
+    sa.tracePert = tracing ? s.traceSt : nullptr;
     pf_step_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d, sa);
     span_end(ctx);
     ctx->launches += 2;
@@ -381,7 +412,15 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
     for (int phase = 0; phase < phaseMax; ++phase) {
         rc = launch_expect_local(ctx, ea);
         if (rc) return rc;
+        if (s.traceWant > 0 && phase < s.traceCap) {     // test option: keep the weights of this phase
+            THB_CUDA(ctx, cudaMemcpyAsync(s.traceR + (size_t)phase * s.nPar * p.mLR, s.uR, sizeof(float) * (size_t)s.nPar * p.mLR, cudaMemcpyDeviceToDevice, ctx->stream));
+            THB_CUDA(ctx, cudaMemcpyAsync(s.traceT + (size_t)phase * s.nPar * p.mLT, s.uT, sizeof(float) * (size_t)s.nPar * p.mLT, cudaMemcpyDeviceToDevice, ctx->stream));
+            THB_CUDA(ctx, cudaMemcpyAsync(s.traceB + (size_t)phase * s.nPar, s.base, sizeof(float) * (size_t)s.nPar, cudaMemcpyDeviceToDevice, ctx->stream));
+            s.traceN = phase + 1;
+        }
         sa.doPost = 1; sa.doPre = (phase + 1 < phaseMax); sa.phase = phase; sa.prePf = p.perturbFactorS;
+        sa.traceRes = (tracing && phase < s.traceCap) ? s.traceSt + ((size_t)phase * 2 + 1) * stSz : nullptr;
+        sa.tracePert = (tracing && phase + 1 < s.traceCap) ? s.traceSt + ((size_t)(phase + 1) * 2) * stSz : nullptr;
         sa.epoch = (s.epoch << 20) + (uint64_t)(phase + 1);
         THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
         span_begin(ctx, KF_PF);
@@ -450,6 +489,44 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     int rc = launch_insert(ctx, a, nullptr);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_pf_set_epoch(thb_ctx* ctx, uint64_t epoch)
+{
+    if (!ctx) return THB_E_ARG;
+    ctx->pf_.epoch = epoch;
+    return THB_OK;
+}
+
+int thb_pf_trace(thb_ctx* ctx, int nPhases)
+{
+    if (!ctx || nPhases < 0) return THB_E_ARG;
+    ctx->pf_.traceWant = nPhases;
+    return THB_OK;
+}
+
+int thb_pf_get_trace(thb_ctx* ctx, int nPhases, float* uR, float* uT, float* base)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.traceR || nPhases <= 0 || nPhases > s.traceN) return set_error(ctx, THB_E_STATE, "pf_get_trace: %d phases asked, %d traced", nPhases, s.traceN);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (uR) THB_CUDA(ctx, cudaMemcpy(uR, s.traceR, sizeof(float) * (size_t)nPhases * s.nPar * s.prm.mLR, cudaMemcpyDeviceToHost));
+    if (uT) THB_CUDA(ctx, cudaMemcpy(uT, s.traceT, sizeof(float) * (size_t)nPhases * s.nPar * s.prm.mLT, cudaMemcpyDeviceToHost));
+    if (base) THB_CUDA(ctx, cudaMemcpy(base, s.traceB, sizeof(float) * (size_t)nPhases * s.nPar, cudaMemcpyDeviceToHost));
+    return THB_OK;
+}
+
+int thb_pf_get_trace_states(thb_ctx* ctx, int nPhases, double* st)
+{
+    if (!ctx || !st) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.traceSt || nPhases <= 0 || nPhases > s.traceN) return set_error(ctx, THB_E_STATE, "pf_get_trace_states: %d phases asked, %d traced", nPhases, s.traceN);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    THB_CUDA(ctx, cudaMemcpy(st, s.traceSt, sizeof(double) * (size_t)nPhases * 2 * s.nPar * (4 * s.prm.mLR + 2 * s.prm.mLT), cudaMemcpyDeviceToHost));
     return THB_OK;
 }
 

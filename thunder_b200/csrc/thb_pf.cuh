@@ -25,7 +25,7 @@
 //   gsl_ran_flat           a (1 - u) + b u                               randist/flat.c:32-40
 //   gsl_ran_shuffle        i = n-1 .. 1: swap(i, uniform_int(i + 1))     randist/shuffle.c:66-78
 // and the operators below consume them in the reference's order.  With the reference's engine swapped for the same bit
-// generator (oracle/ref_harness.cpp: ref_rng_replay) the two particle filters therefore see the SAME random numbers, and
+// generator (the test harness of the reference build does that) the two particle filters therefore see the SAME random numbers, and
 // every operator - stochastic ones included - is compared exactly (tests/test_pf_host.py, tests/test_gpu_iteration.py).
 #pragma once
 #include <math.h>

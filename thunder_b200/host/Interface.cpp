@@ -81,6 +81,181 @@ void ExpectPreidx(int gpuIdx, int** deviCol, int** deviRow, int* iCol, int* iRow
     if (deviRow) *deviRow = iRow;
 }
 
+// ------------------------------------------------------------------------------------------------ local search, reference protocol
+namespace {
+struct LocalState {
+    int nPxl = 0, slots = 0, pf = 0, idim = 0;
+    bool pixelsSet = false;
+} g_local[64];
+LocalState& localOf(int gpuIdx) { return g_local[gpuIdx & 63]; }
+int g_token;    // address handed out as the opaque device pointer
+}  // namespace
+
+void ExpectPrefre(int gpuIdx, RFLOAT** devfreQ, RFLOAT*, int)
+{
+    // the frequency table feeds the on-the-fly CTF of the CTF search only (src/Optimiser.cpp:2173-2185)
+    (void)gpuIdx;
+    if (devfreQ) *devfreQ = (RFLOAT*)&g_token;
+}
+
+void ExpectLocalIn(int gpuIdx, Complex** devdatP, RFLOAT** devctfP, RFLOAT** devdefO, RFLOAT** devsigP, int nPxl, int cpyNumL,
+                   int searchType)
+{
+    thb_ctx* c = thbContext(gpuIdx);
+    if (searchType == 2) { fprintf(stderr, "thunder_b200 [ExpectLocalIn]: CTF search (SEARCH_TYPE_CTF) is not implemented\n"); abort(); }
+    LocalState& L = localOf(gpuIdx);
+    if (g_scan.npxl != nPxl || g_scan.iCol.empty()) { fprintf(stderr, "thunder_b200 [ExpectLocalIn]: ExpectPreidx must come first (pixel list of %d pixels)\n", nPxl); abort(); }
+    L.nPxl = nPxl; L.slots = cpyNumL > 0 ? cpyNumL : 1; L.pixelsSet = false;
+    if (devdatP) *devdatP = (Complex*)&g_token;
+    if (devctfP) *devctfP = (RFLOAT*)&g_token;
+    if (devdefO) *devdefO = (RFLOAT*)&g_token;
+    if (devsigP) *devsigP = (RFLOAT*)&g_token;
+    (void)c;
+}
+
+void ExpectLocalV3D(int gpuIdx, ManagedArrayTexture* mgr, Complex* volume, int vdim)
+{
+    thb_ctx* c = thbContext(gpuIdx);
+    if (thb_get_mode(c) != THB_MODE_3D) CHK(c, thb_set_mode(c, THB_MODE_3D));
+    mgr->slot = 0;
+    CHK(c, thb_set_volume(c, 0, (const float*)volume, vdim));
+}
+
+void ExpectLocalV2D(int gpuIdx, ManagedArrayTexture* mgr, Complex* volume, int dimSize)
+{
+    // the caller creates one manager per class in class order (src/Optimiser.cpp:2216-2230): slot = creation order per device
+    thb_ctx* c = thbContext(gpuIdx);
+    if (thb_get_mode(c) != THB_MODE_2D) CHK(c, thb_set_mode(c, THB_MODE_2D));
+    (void)dimSize;
+    CHK(c, thb_set_volume(c, mgr->slot, (const float*)volume, mgr->getVdim()));
+}
+
+static void local_pixels(thb_ctx* c, LocalState& L, int pf, int idim)
+{
+    if (L.pixelsSet && L.pf == pf && L.idim == idim) return;
+    CHK(c, thb_set_expect_pixels(c, idim, pf, L.nPxl, g_scan.iCol.data(), g_scan.iRow.data()));
+    CHK(c, thb_stack_reserve(c, THB_STACK_EXPECT, L.slots));
+    L.pf = pf; L.idim = idim; L.pixelsSet = true;
+}
+
+// image slots need the pixel list, which needs pf and the image size: the reference passes them only to ExpectLocalPreI*, so the
+// images given to ExpectLocalP before the first ExpectLocalPreI* call of a device are kept as host pointers and uploaded there
+namespace {
+struct PendingImg { const Complex* dat; const RFLOAT* ctf; const RFLOAT* sig; };
+std::map<long long, PendingImg> g_pending;    // key = gpuIdx * 4096 + slot
+}
+
+static void upload_slot(thb_ctx* c, int slot, int npxl, const PendingImg& im)
+{
+    (void)npxl;
+    CHK(c, thb_upload_stack_at(c, THB_STACK_EXPECT, slot, 1, (const float*)im.dat, im.ctf, im.sig, nullptr));
+}
+
+void ExpectLocalP(int gpuIdx, Complex*, RFLOAT*, RFLOAT*, RFLOAT*, Complex* datP, RFLOAT* ctfP, RFLOAT* defO, RFLOAT* sigP,
+                  int threadId, int imgId, int npxl, int cSearch)
+{
+    thb_ctx* c = thbContext(gpuIdx);
+    if (cSearch == 2) { fprintf(stderr, "thunder_b200 [ExpectLocalP]: CTF search is not implemented\n"); abort(); }
+    (void)defO;
+    LocalState& L = localOf(gpuIdx);
+    PendingImg im{datP + (size_t)imgId * npxl, ctfP + (size_t)imgId * npxl, sigP + (size_t)imgId * npxl};
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (L.pixelsSet) upload_slot(c, threadId, npxl, im);
+    else g_pending[(long long)gpuIdx * 4096 + threadId] = im;
+}
+
+void ExpectLocalHostA(int, RFLOAT** wC, RFLOAT** wR, RFLOAT** wT, RFLOAT** wD, double** oldR, double** oldT, double** oldD,
+                      double** trans, double** rot, double** dpara, int mR, int mT, int mD, int cSearch)
+{
+    (void)cSearch;
+    const int nD = mD > 0 ? mD : 1;
+    *wC = (RFLOAT*)calloc(1, sizeof(RFLOAT)); *wR = (RFLOAT*)calloc(mR, sizeof(RFLOAT)); *wT = (RFLOAT*)calloc(mT, sizeof(RFLOAT));
+    *wD = (RFLOAT*)calloc(nD, sizeof(RFLOAT));
+    *oldR = (double*)calloc(mR, sizeof(double)); *oldT = (double*)calloc(mT, sizeof(double)); *oldD = (double*)calloc(nD, sizeof(double));
+    *trans = (double*)calloc((size_t)mT * 2, sizeof(double)); *rot = (double*)calloc((size_t)mR * 4, sizeof(double));
+    *dpara = (double*)calloc(nD, sizeof(double));
+}
+
+void ExpectLocalHostF(int, RFLOAT** wC, RFLOAT** wR, RFLOAT** wT, RFLOAT** wD, double** oldR, double** oldT, double** oldD,
+                      double** trans, double** rot, double** dpara, int)
+{
+    free(*wC); free(*wR); free(*wT); free(*wD); free(*oldR); free(*oldT); free(*oldD); free(*trans); free(*rot); free(*dpara);
+    *wC = *wR = *wT = *wD = nullptr; *oldR = *oldT = *oldD = *trans = *rot = *dpara = nullptr;
+}
+
+void ExpectLocalRTD(int, ManagedCalPoint* mcp, double* oldR, double* oldT, double* oldD, double* trans, double* rot, double* dpara)
+{
+    mcp->oldR = oldR; mcp->oldT = oldT; mcp->oldD = oldD; mcp->trans = trans; mcp->rot = rot; mcp->dpara = dpara;
+}
+
+static void local_prei(int gpuIdx, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, int pf, int idim, int npxl)
+{
+    thb_ctx* c = thbContext(gpuIdx);
+    LocalState& L = localOf(gpuIdx);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!L.pixelsSet || L.pf != pf || L.idim != idim) {
+        local_pixels(c, L, pf, idim);
+        for (auto it = g_pending.begin(); it != g_pending.end();) {
+            if (it->first / 4096 == gpuIdx) { upload_slot(c, (int)(it->first % 4096), npxl, it->second); it = g_pending.erase(it); }
+            else ++it;
+        }
+    }
+    mcp->mgr = mgr;
+}
+
+void ExpectLocalPreI3D(int gpuIdx, int, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT*, RFLOAT*, int*, int*, RFLOAT, RFLOAT,
+                       RFLOAT, RFLOAT, int pf, int idim, int, int npxl, int)
+{
+    local_prei(gpuIdx, mgr, mcp, pf, idim, npxl);
+}
+
+void ExpectLocalPreI2D(int gpuIdx, int, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT*, RFLOAT*, int*, int*, RFLOAT, RFLOAT,
+                       RFLOAT, RFLOAT, int pf, int idim, int, int npxl, int)
+{
+    local_prei(gpuIdx, mgr, mcp, pf, idim, npxl);
+}
+
+void ExpectLocalM(int gpuIdx, int datShift, ManagedCalPoint* mcp, Complex*, RFLOAT*, RFLOAT*, RFLOAT* wC, RFLOAT* wR, RFLOAT* wT,
+                  RFLOAT* wD, double oldC, int npxl)
+{
+    thb_ctx* c = thbContext(gpuIdx);
+    (void)npxl;
+    const int nR = mcp->getNR(), nT = mcp->getNT();
+    if (!mcp->rot || !mcp->trans || !mcp->oldR || !mcp->oldT) { fprintf(stderr, "thunder_b200 [ExpectLocalM]: ExpectLocalRTD must come first\n"); abort(); }
+    const int img = datShift;
+    // MODE_2D: rot[mR][4] holds (cos, sin, 0, 0) per row (Particle::quaternion of a 2D particle); the C ABI takes [mR][2]
+    std::vector<double> cs;
+    const double* q = mcp->rot;
+    if (thb_get_mode(c) == THB_MODE_2D) {
+        cs.resize((size_t)nR * 2);
+        for (int r = 0; r < nR; ++r) { cs[2 * r] = mcp->rot[4 * r]; cs[2 * r + 1] = mcp->rot[4 * r + 1]; }
+        q = cs.data();
+    }
+    float uC = 0.f;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);      // one launch per device at a time, as the caller's omp lock already guarantees
+        CHK(c, thb_expect_local(c, 1, &img, nR, nT, q, mcp->trans, mcp->oldR, mcp->oldT, wR, wT, &uC, nullptr, nullptr));
+    }
+    // the reference's sums carry the prior weights of the OTHER dimensions (src/Optimiser.cpp:1383-1402): wC += s wR wT wD,
+    // wR += s wC wT wD, ...; without CTF search there is one defocus sample of prior weight oldD[0]
+    const double pD = mcp->oldD ? mcp->oldD[0] : 1.0;
+    for (int r = 0; r < nR; ++r) wR[r] = (RFLOAT)(wR[r] * oldC * pD);
+    for (int t = 0; t < nT; ++t) wT[t] = (RFLOAT)(wT[t] * oldC * pD);
+    wC[0] = (RFLOAT)(uC * pD);
+    if (wD) wD[0] = (RFLOAT)(uC * oldC);
+}
+
+void ExpectLocalFin(int gpuIdx, Complex** devdatP, RFLOAT** devctfP, RFLOAT** devdefO, RFLOAT** devfreQ, RFLOAT** devsigP, int)
+{
+    LocalState& L = localOf(gpuIdx);
+    L = LocalState();
+    if (devdatP) *devdatP = nullptr;
+    if (devctfP) *devctfP = nullptr;
+    if (devdefO) *devdefO = nullptr;
+    if (devfreQ) *devfreQ = nullptr;
+    if (devsigP) *devsigP = nullptr;
+}
+
 void ExpectFreeIdx(int, int** deviCol, int** deviRow)
 {
     if (deviCol) *deviCol = nullptr;
@@ -301,6 +476,48 @@ void thbi_ExpectLocalBatch(int gpuIdx, float* volume, int vdim, int pf, int idim
 {
     ExpectLocalBatch(gpuIdx, reinterpret_cast<Complex*>(volume), vdim, pf, idim, iCol, iRow, npxl, reinterpret_cast<Complex*>(datP), ctfP,
                      sigRcpP, imgNum, nR, nT, quat, tran, wRprior, wTprior, wC, wR, wT, baseL);
+}
+// The local search driven through the reference's own call sequence (src/Optimiser.cpp:2169-2293 set-up, :2813-3300 per image
+// and phase, :3320-3400 tear-down), one image in flight per thread slot, nPhase calls of RTD / PreI3D / M per image with the
+// support quat[img][phase] / tran[img][phase] the caller's Particle objects would hand over.  Results per (image, phase).
+void thbi_ExpectLocalProtocol(int gpuIdx, float* volume, int vdim, int pf, int idim, int* iCol, int* iRow, int npxl, float* datP,
+                              float* ctfP, float* sigRcpP, int imgNum, int nPhase, int nR, int nT, const double* quat, const double* tran,
+                              const double* wRprior, const double* wTprior, double oldC, int nSlots, float* wC, float* wR, float* wT)
+{
+    int* deviCol = nullptr; int* deviRow = nullptr;
+    ExpectPreidx(gpuIdx, &deviCol, &deviRow, iCol, iRow, npxl);
+    Complex* devdatP = nullptr; RFLOAT *devctfP = nullptr, *devdefO = nullptr, *devsigP = nullptr, *devfreQ = nullptr;
+    ExpectLocalIn(gpuIdx, &devdatP, &devctfP, &devdefO, &devsigP, npxl, nSlots, 1 /* SEARCH_TYPE_LOCAL */);
+    ManagedArrayTexture* mgr = new ManagedArrayTexture();
+    mgr->Init(1 /* MODE_3D */, vdim, gpuIdx);
+    ExpectLocalV3D(gpuIdx, mgr, reinterpret_cast<Complex*>(volume), vdim);
+    ManagedCalPoint* mcp = new ManagedCalPoint();
+    mcp->Init(1, 1, gpuIdx, nR, nT, 1, npxl);
+    RFLOAT *hwC, *hwR, *hwT, *hwD; double *oldR, *oldT, *oldD, *trans, *rot, *dpara;
+    ExpectLocalHostA(gpuIdx, &hwC, &hwR, &hwT, &hwD, &oldR, &oldT, &oldD, &trans, &rot, &dpara, nR, nT, 1, 1);
+    for (int l = 0; l < imgNum; ++l) {
+        const int slot = l % nSlots;                 // the reference: threadId % cpyNum
+        ExpectLocalP(gpuIdx, devdatP, devctfP, devdefO, devsigP, reinterpret_cast<Complex*>(datP), ctfP, nullptr, sigRcpP, slot, l, npxl, 1);
+        for (int ph = 0; ph < nPhase; ++ph) {
+            const size_t o = (size_t)l * nPhase + ph;
+            for (int r = 0; r < nR; ++r) oldR[r] = wRprior[o * nR + r];
+            for (int t = 0; t < nT; ++t) oldT[t] = wTprior[o * nT + t];
+            oldD[0] = 1.0;
+            memcpy(trans, tran + o * nT * 2, sizeof(double) * nT * 2);
+            memcpy(rot, quat + o * nR * 4, sizeof(double) * nR * 4);
+            ExpectLocalRTD(gpuIdx, mcp, oldR, oldT, oldD, trans, rot, dpara);
+            ExpectLocalPreI3D(gpuIdx, slot, mgr, mcp, devdefO, devfreQ, deviCol, deviRow, 0.f, 0.1f, 0.f, 0.f, pf, idim, vdim, npxl, 1);
+            ExpectLocalM(gpuIdx, slot, mcp, devdatP, devctfP, devsigP, hwC, hwR, hwT, hwD, oldC, npxl);
+            wC[o] = hwC[0];
+            memcpy(wR + o * nR, hwR, sizeof(float) * nR);
+            memcpy(wT + o * nT, hwT, sizeof(float) * nT);
+        }
+    }
+    ExpectLocalHostF(gpuIdx, &hwC, &hwR, &hwT, &hwD, &oldR, &oldT, &oldD, &trans, &rot, &dpara, 1);
+    ExpectLocalFin(gpuIdx, &devdatP, &devctfP, &devdefO, &devfreQ, &devsigP, 1);
+    delete mcp;
+    delete mgr;
+    ExpectFreeIdx(gpuIdx, &deviCol, &deviRow);
 }
 void thbi_InsertFT(float* F3D, float* T3D, int vdim, double* O3D, int* counter, float* datP, float* ctfP, double* offS, float* w, double* nR,
                    double* nT, const int* iCol, const int* iRow, int opf, int npxl, int mReco, int idim, int dimSize, int imgNum)

@@ -48,8 +48,72 @@ void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, R
                     RFLOAT* wT, double* pR, double* pT, RFLOAT* baseL, int kIdx, int nK, int nR, int nT, int npxl,
                     int imgNum);
 
-// ---- E-step, local search.  The reference drives one image at a time through ExpectLocalP / RTD / PreI3D / M
-// under a per-device lock (Optimiser.cpp:2813-3300); the replacement is one batched call per phase.
+// ---- E-step, local search, THE REFERENCE'S OWN PROTOCOL (gpu/interface/Interface.h:31-164, callers src/Optimiser.cpp:2169-3300):
+// one image at a time per device - ExpectLocalP copies image imgId into the device slot of the calling thread, then for every
+// phase ExpectLocalRTD hands over the support (rot[mR][4], trans[mT][2]) and the prior weights (oldR, oldT, oldD),
+// ExpectLocalPreI3D names the references, and ExpectLocalM returns the marginal weights wC / wR / wT / wD to the caller's host
+// arrays before it returns (the caller resamples from them at once).  Same names, argument order and meaning; what differs is
+// inside: the image slots, the pixel list and the projector volume live in the library's context of the device, the
+// projections never exist as arrays (ExpectLocalPreI3D only records its arguments), and ExpectLocalM is ONE launch of the fused
+// kernel spread over the whole chip for that image (thb_expect6.cuh).  The opaque device pointers handed back through
+// Complex** / RFLOAT** are non-null tokens, as with ExpectPreidx.  CTF search (cSearch / searchType == 2: the defocus
+// dimension) is not implemented: these functions abort with a message, as the reference's seam does on any error.
+class ManagedArrayTexture {            // gpu/include/ManagedArrayTexture.h:13-30: here, a handle on the context's volume slot
+public:
+    ~ManagedArrayTexture() {}
+    void Init(int mode, int vdim, int gpuIdx) { _mode = mode; _vdim = vdim; _gpu = gpuIdx; }
+    int getMode() const { return _mode; }
+    int getVdim() const { return _vdim; }
+    int getDeviceId() const { return _gpu; }
+    int slot = 0;                      // volume slot of the library context (class index in MODE_2D)
+private:
+    int _mode = 1, _vdim = 0, _gpu = 0;
+};
+class ManagedCalPoint {                // gpu/include/ManagedCalPoint.h:13-80: here, the support and priors of the image in flight
+public:
+    ~ManagedCalPoint() {}
+    void Init(int mode, int cSearch, int gpuIdx, int nR, int nT, int mD, int npxl)
+    {
+        _mode = mode; _cSearch = cSearch; _gpu = gpuIdx; _nR = nR; _nT = nT; _mD = mD; _npxl = npxl;
+    }
+    int getMode() const { return _mode; }
+    int getCSearch() const { return _cSearch; }
+    int getDeviceId() const { return _gpu; }
+    int getNR() const { return _nR; }
+    int getNT() const { return _nT; }
+    int getMD() const { return _mD; }
+    // what ExpectLocalRTD / ExpectLocalPreI3D were given for the image in flight (host arrays of the caller, read by ExpectLocalM)
+    const double *oldR = nullptr, *oldT = nullptr, *oldD = nullptr, *trans = nullptr, *rot = nullptr, *dpara = nullptr;
+    const ManagedArrayTexture* mgr = nullptr;
+private:
+    int _mode = 1, _cSearch = 0, _gpu = 0, _nR = 0, _nT = 0, _mD = 1, _npxl = 0;
+};
+void ExpectPrefre(int gpuIdx, RFLOAT** devfreQ, RFLOAT* freQ, int npxl);
+void ExpectLocalIn(int gpuIdx, Complex** devdatP, RFLOAT** devctfP, RFLOAT** devdefO, RFLOAT** devsigP, int nPxl, int cpyNumL,
+                   int searchType);
+void ExpectLocalV2D(int gpuIdx, ManagedArrayTexture* mgr, Complex* volume, int dimSize);
+void ExpectLocalV3D(int gpuIdx, ManagedArrayTexture* mgr, Complex* volume, int vdim);
+void ExpectLocalP(int gpuIdx, Complex* devdatP, RFLOAT* devctfP, RFLOAT* devdefO, RFLOAT* devsigP, Complex* datP, RFLOAT* ctfP,
+                  RFLOAT* defO, RFLOAT* sigP, int threadId, int imgId, int npxl, int cSearch);
+void ExpectLocalHostA(int gpuIdx, RFLOAT** wC, RFLOAT** wR, RFLOAT** wT, RFLOAT** wD, double** oldR, double** oldT, double** oldD,
+                      double** trans, double** rot, double** dpara, int mR, int mT, int mD, int cSearch);
+void ExpectLocalRTD(int gpuIdx, ManagedCalPoint* mcp, double* oldR, double* oldT, double* oldD, double* trans, double* rot,
+                    double* dpara);
+void ExpectLocalPreI2D(int gpuIdx, int datShift, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT* devdefO, RFLOAT* devfreQ,
+                       int* deviCol, int* deviRow, RFLOAT phaseShift, RFLOAT conT, RFLOAT k1, RFLOAT k2, int pf, int idim, int vdim,
+                       int npxl, int interp);
+void ExpectLocalPreI3D(int gpuIdx, int datShift, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT* devdefO, RFLOAT* devfreQ,
+                       int* deviCol, int* deviRow, RFLOAT phaseShift, RFLOAT conT, RFLOAT k1, RFLOAT k2, int pf, int idim, int vdim,
+                       int npxl, int interp);
+void ExpectLocalM(int gpuIdx, int datShift, ManagedCalPoint* mcp, Complex* devdatP, RFLOAT* devctfP, RFLOAT* devsigP, RFLOAT* wC,
+                  RFLOAT* wR, RFLOAT* wT, RFLOAT* wD, double oldC, int npxl);
+void ExpectLocalHostF(int gpuIdx, RFLOAT** wC, RFLOAT** wR, RFLOAT** wT, RFLOAT** wD, double** oldR, double** oldT, double** oldD,
+                      double** trans, double** rot, double** dpara, int cSearch);
+void ExpectLocalFin(int gpuIdx, Complex** devdatP, RFLOAT** devctfP, RFLOAT** devdefO, RFLOAT** devfreQ, RFLOAT** devsigP,
+                    int cSearch);
+
+// ---- E-step, local search, batched: what a maintainer should call instead where the caller can hand over many images at once
+// (the reference crosses PCIe once per image per phase; INTEGRATION.md shows the patch of the loop): one call per phase.
 //   quat[nImg][nR][4], tran[nImg][nT][2], wR[nImg][nR], wT[nImg][nT] priors; outputs uC[nImg], uR, uT as the
 //   reference's wC / wR / wT of ExpectLocalM (weights relative to the per-image maximum), baseL[nImg]
 void ExpectLocalBatch(int gpuIdx, Complex* volume, int vdim, int pf, int idim, const int* iCol, const int* iRow, int npxl,
