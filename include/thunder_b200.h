@@ -22,6 +22,10 @@
  *   thb_project               Projector::project(Complex*,...)       src/Projector.cpp:356-374
  *   thb_expect_local          ExpectLocalRTD + ExpectLocalPreI3D +   gpu/interface/Interface.h:31-164
  *                             ExpectLocalM (one call, many images)   (CPU loop: src/Optimiser.cpp:1162-1402)
+ *   thb_set_frequency,        ExpectPrefre, defO of ExpectLocalP,    gpu/interface/Interface.h:24-164
+ *   thb_upload_stack_defocus, k1/k2/.. of ExpectLocalPreI3D, wD of   (CPU loop with SEARCH_TYPE_CTF: src/Optimiser.cpp:1248-1273,
+ *   thb_expect_local_ctf      ExpectLocalM                            1328-1402; allocPreCal :8125-8168)
+ *   thb_insert_ctf            InsertFT with cSearch                  gpu/interface/Interface.h:267-318, src/Optimiser.cpp:7171-7215
  *   thb_expect_scan           ExpectRotran + ExpectProject +         gpu/interface/Interface.h:199-221
  *                             ExpectGlobal3D                         (CPU loop: src/Optimiser.cpp:633-914)
  *   thb_reco_alloc/reset      Reconstructor::allocSpace / reset      src/Reconstructor.cpp:92-143
@@ -184,6 +188,22 @@ int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, 
                      const double* tran, const double* wR, const double* wT, float* uR, float* uT,
                      float* uC, float* base, float* logL);
 
+/* ---------------------------------------------------------------- a6/a8 with the defocus dimension: CTF search */
+/* SEARCH_TYPE_CTF (src/Optimiser.cpp:1159-1273, 1328-1402; the reference's seam: ExpectPrefre, the defO of ExpectLocalP, the
+ * k1 / k2 / phaseShift / conT of ExpectLocalPreI3D, the dpara / oldD of ExpectLocalRTD, the wD of ExpectLocalM,
+ * gpu/interface/Interface.h:24-164).  The CTF of every defocus factor d is computed on the fly,
+ *   ki = K1 defocusP d f^2 + K2 f^4 - phaseShift ,  ctf = -sqrt(1 - ac^2) sin ki + ac cos ki      (src/Optimiser.cpp:1253-1268)
+ * from what allocPreCal prepares (:8125-8168): freQ[nPxl] = |k| / (N pixelSize) (thb_set_frequency, E pixel order of the caller),
+ * defP[nImg][nPxl] = the per-pixel defocus of every image (thb_upload_stack_defocus, images [base, base + nImg) of the E stack),
+ * ctfK[nAct][4] = {K1, K2, phaseShift, amplitudeContrast}.  dpar[nAct][nD] defocus factors, wD[nAct][nD] their prior weights;
+ * uR / uT / uD / uC carry the prior weights of the other dimensions as the reference's wR / wT / wD / wC do (:1383-1402);
+ * logL[nAct][nR][nT][nD] optional. */
+int thb_set_frequency(thb_ctx* ctx, const float* freQ);
+int thb_upload_stack_defocus(thb_ctx* ctx, int base, int nImg, const float* defP);
+int thb_expect_local_ctf(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, int nD, const double* quat, const double* tran,
+                         const double* dpar, const double* wR, const double* wT, const double* wD, const float* ctfK, float* uR,
+                         float* uT, float* uD, float* uC, float* base, float* logL);
+
 /* ---------------------------------------------------------------- a7: global scan shape */
 /* One shared set of nR rotations x nT translations against every image of the E stack that uses
  * `slot`.  pR[nR], pT[nT] prior weights.  Outputs (host): wC[nImg], wR[nImg][nR], wT[nImg][nT],
@@ -208,6 +228,11 @@ int thb_insert(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float
  * many of them each image really has (0 .. mReco); only those are inserted and counted */
 int thb_insert_counts(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
                       const int* nDraw, const double* nr, const double* nt);
+/* CTF search (cSearch of InsertFT, src/Optimiser.cpp:7171-7215): nd[nImg][mReco] defocus factor of every draw; its CTF is
+ * CTF(pixelSize, voltage, defocusU d, defocusV d, theta, Cs, amplitudeContrast, phaseShift) (src/CTF.cpp:118-151) computed on the
+ * fly from ctfAttr[nImg][7] (the layout of thb_pack_stack) instead of the resident ctf array.  MODE_3D, mReco <= 256. */
+int thb_insert_ctf(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const double* nr,
+                   const double* nt, const double* nd, const float* ctfAttr, float pixelSize);
 /* MODE_2D: the same with the class of every draw, nc[nImg][mReco] (InsertI2D's nC): the accumulator slot of the draw */
 int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS,
                        const int* nc, const double* nr, const double* nt);

@@ -1162,4 +1162,128 @@ void ref_insert_loop(void* recoH, void** pars, int nImg, const float* datP, cons
     TSFFTW_free(poolTransImgP);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTF search (SEARCH_TYPE_CTF).  (1) what Optimiser::allocPreCal prepares for it (src/Optimiser.cpp:8125-8168), one image;
+// (2) one phase of the likelihood loop with the defocus dimension (:1236-1402) for explicit supports and prior weights;
+// (3) the insert loop of reconstructRef with cSearch (:7067-7241): the CTF of every draw from its own defocus factor.
+// ------------------------------------------------------------------------------------------
+void ref_precal_ctf(float voltage, float defocusU, float defocusV, float defocusTheta, float Cs, int N, float pixelSize,
+                    const int* iCol, const int* iRow, int nPxl, float* frequency, float* defocusP, float* K1K2)
+{
+    for (int i = 0; i < nPxl; i++)
+        frequency[i] = NORM(iCol[i], iRow[i]) / N / pixelSize;
+    for (int i = 0; i < nPxl; i++)
+    {
+        RFLOAT angle = atan2(iRow[i], iCol[i]) - defocusTheta;
+        RFLOAT defocus = -(defocusU + defocusV + (defocusU - defocusV) * cos(2 * angle)) / 2;
+        defocusP[i] = defocus;
+    }
+    RFLOAT lambda = 12.2643274 / sqrt(voltage * (1 + voltage * 0.978466e-6));
+    K1K2[0] = M_PI * lambda;
+    K1K2[1] = M_PI_2 * Cs * TSGSL_pow_3(lambda);
+}
+
+void ref_expect_ctf(void* projH, const float* datP, const float* sigRcpP, const float* defocusP, const float* frequency, float K1,
+                    float K2, float phaseShift, float amplitudeContrast, const double* quat, const double* tran, const double* dpar,
+                    const double* pwR, const double* pwT, const double* pwD, double pwC, const int* iCol, const int* iRow, int nPxl,
+                    int N, int nR, int nT, int nD, int simd, float* wCout, float* wRout, float* wTout, float* wDout, float* baseOut,
+                    float* logL)
+{
+    RefProjector* P = (RefProjector*)projH;
+    Complex* priRotP = (Complex*)TSFFTW_malloc((size_t)nPxl * sizeof(Complex));
+    Complex* priAllP = (Complex*)TSFFTW_malloc((size_t)nPxl * sizeof(Complex));
+    Complex* traP = (Complex*)TSFFTW_malloc((size_t)nT * nPxl * sizeof(Complex));
+    RFLOAT* ctfP = (RFLOAT*)TSFFTW_malloc((size_t)nD * nPxl * sizeof(RFLOAT));
+    Complex* dat = (Complex*)datP;
+
+    for (int iT = 0; iT < nT; iT++)
+        translate(traP + (size_t)iT * nPxl, tran[2 * iT], tran[2 * iT + 1], N, N, iCol, iRow, nPxl, 1);
+
+    for (int iD = 0; iD < nD; iD++)
+    {
+        double d = dpar[iD];
+        for (int i = 0; i < nPxl; i++)
+        {
+            RFLOAT ki = K1 * defocusP[i] * d * TSGSL_pow_2(frequency[i]) + K2 * TSGSL_pow_4(frequency[i]) - phaseShift;
+            ctfP[(size_t)nPxl * iD + i] = -TS_SQRT(1 - TSGSL_pow_2(amplitudeContrast)) * TS_SIN(ki) + amplitudeContrast * TS_COS(ki);
+        }
+    }
+
+    RFLOAT baseLine = GSL_NAN;
+    vec wC = vec::Zero(1), wR = vec::Zero(nR), wT = vec::Zero(nT), wD = vec::Zero(nD);
+    for (int iR = 0; iR < nR; iR++)
+    {
+        dmat33 rot3D;
+        rotate3D(rot3D, dvec4(quat[4 * iR], quat[4 * iR + 1], quat[4 * iR + 2], quat[4 * iR + 3]));
+        P->proj.project(priRotP, rot3D, iCol, iRow, nPxl, 1);
+        for (int iT = 0; iT < nT; iT++)
+        {
+            for (int i = 0; i < nPxl; i++) priAllP[i] = traP[(size_t)nPxl * iT + i] * priRotP[i];
+            for (int iD = 0; iD < nD; iD++)
+            {
+                RFLOAT w = simd ? logDataVSPrior_m_huabin_SIMD256(dat, priAllP, ctfP + (size_t)iD * nPxl, sigRcpP, nPxl)
+                                : logDataVSPrior_m_huabin(dat, priAllP, ctfP + (size_t)iD * nPxl, sigRcpP, nPxl);
+                if (logL) logL[((size_t)iR * nT + iT) * nD + iD] = w;
+                baseLine = TSGSL_isnan(baseLine) ? w : baseLine;
+                if (w > baseLine)
+                {
+                    RFLOAT nf = exp(baseLine - w);
+                    wC *= nf; wR *= nf; wT *= nf; wD *= nf;
+                    baseLine = w;
+                }
+                RFLOAT s = exp(w - baseLine);
+                wC(0) += s * (pwR[iR] * pwT[iT] * pwD[iD]);
+                wR(iR) += s * (pwC * pwT[iT] * pwD[iD]);
+                wT(iT) += s * (pwC * pwR[iR] * pwD[iD]);
+                wD(iD) += s * (pwC * pwR[iR] * pwT[iT]);
+            }
+        }
+    }
+    wCout[0] = wC(0);
+    for (int i = 0; i < nR; i++) wRout[i] = wR(i);
+    for (int i = 0; i < nT; i++) wTout[i] = wT(i);
+    for (int i = 0; i < nD; i++) wDout[i] = wD(i);
+    *baseOut = baseLine;
+    TSFFTW_free(priRotP); TSFFTW_free(priAllP); TSFFTW_free(traP); TSFFTW_free(ctfP);
+}
+
+void ref_insert_loop_ctf(void* recoH, int nImg, const float* datP, const float* wImg, const double* offS, const double* nr,
+                         const double* nt, const double* nd, const float* ctfAttr, float pixelSize, const int* iCol,
+                         const int* iRow, int nPxl, int N, int mReco, int nThread)
+{
+    RefReco* R = (RefReco*)recoH;
+    if (nThread <= 0) nThread = omp_get_max_threads();
+    Complex* poolTransImgP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    RFLOAT* poolCtf = (RFLOAT*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(RFLOAT));
+
+    #pragma omp parallel for num_threads(nThread)
+    for (int l = 0; l < nImg; l++)
+    {
+        RFLOAT w = wImg[l];
+        Complex* transImgP = poolTransImgP + (size_t)nPxl * omp_get_thread_num();
+        RFLOAT* ctf = poolCtf + (size_t)nPxl * omp_get_thread_num();
+        const Complex* orignImgP = (const Complex*)datP + (size_t)nPxl * l;
+        dvec2 offset(offS ? offS[2 * l] : 0, offS ? offS[2 * l + 1] : 0);
+        const float* a = ctfAttr + 7 * (size_t)l;     // voltage, defocusU, defocusV, defocusTheta, Cs, amplitudeContrast, phaseShift
+        for (int m = 0; m < mReco; m++)
+        {
+            const double* q = nr + ((size_t)l * mReco + m) * 4;
+            const double* t = nt + ((size_t)l * mReco + m) * 2;
+            double d = nd[(size_t)l * mReco + m];
+            dvec4 quat(q[0], q[1], q[2], q[3]);
+            dvec2 tran(t[0], t[1]);
+            dmat33 rot3D;
+            rotate3D(rot3D, quat);
+            translate(transImgP, orignImgP, -(tran - offset)(0), -(tran - offset)(1), N, N, iCol, iRow, nPxl, 1);
+            CTF(ctf, pixelSize, a[0], a[1] * d, a[2] * d, a[3], a[4], a[5], a[6], N, N, iCol, iRow, nPxl, 1);
+            R->reco.insertP(transImgP, ctf, rot3D, w, NULL);
+            dvec3 dir = -rot3D * dvec3((tran - offset)[0], (tran - offset)[1], 0);
+            R->reco.insertDir(dir);
+        }
+    }
+    TSFFTW_free(poolTransImgP);
+    TSFFTW_free(poolCtf);
+}
+
 }  // extern "C"

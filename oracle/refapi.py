@@ -127,6 +127,9 @@ def lib():
         L.ref_insert_loop.argtypes = [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i]
         L.ref_expectation_local_trace.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _i, _i, _i, _d, _i,
                                                   _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]
+        L.ref_precal_ctf.argtypes = [_f] * 5 + [_i, _f, _p, _p, _i, _p, _p, _p]
+        L.ref_expect_ctf.argtypes = [_p] * 5 + [_f] * 4 + [_p] * 6 + [_d, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 6
+        L.ref_insert_loop_ctf.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i]
         L.ref_rng_replay.argtypes = [_i]
         L.ref_rng_key.argtypes = [C.c_ulonglong] * 3
         L.ref_rng_replay_loop.argtypes = [C.c_ulonglong] * 3
@@ -359,6 +362,17 @@ class Reconstructor:
     def prepareTF(self):
         lib().ref_reco_prepareTF(self.h, self.nThread)
 
+    def insert_loop_ctf(self, dat, w, offS, nr, nt, nd, ctfAttr, pixelSize, iCol, iRow, N, nThread=1):
+        """the insert loop with cSearch: per-draw defocus factors nd[nImg][mReco], ctfAttr[nImg][7]"""
+        dat = np.ascontiguousarray(dat, np.complex64)
+        nImg, P = dat.shape
+        nr = np.ascontiguousarray(nr, np.float64); nt = np.ascontiguousarray(nt, np.float64); nd = np.ascontiguousarray(nd, np.float64)
+        mReco = nr.shape[1]
+        w = np.ascontiguousarray(w, np.float32); ctfAttr = np.ascontiguousarray(ctfAttr, np.float32)
+        offS = None if offS is None else np.ascontiguousarray(offS, np.float64)
+        lib().ref_insert_loop_ctf(self.h, nImg, _ptr(dat), _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt), _ptr(nd), _ptr(ctfAttr), pixelSize,
+                                  _ptr(iCol), _ptr(iRow), P, N, mReco, nThread)
+
     def insert_loop(self, dat, ctf_, w, offS, nr, nt, iCol, iRow, N, nThread=1, pars=None):
         dat = np.ascontiguousarray(dat, np.complex64); ctf_ = np.ascontiguousarray(ctf_, np.float32)
         nImg, P = dat.shape
@@ -464,6 +478,29 @@ def expectation_local_trace(pars, proj, datP, ctfP, sigRcpP, iCol, iRow, N, mLR,
     if want_states:
         return uROwn, uTOwn, cond, dict(rPert=rPert, tPert=tPert, rRes=rRes, tRes=tRes)
     return uROwn, uTOwn, cond
+
+
+def precal_ctf(voltage, dU, dV, theta, Cs, N, pixelSize, iCol, iRow):
+    """allocPreCal for the CTF search, one image: frequency[nPxl], defocusP[nPxl], (K1, K2)"""
+    n = len(iCol)
+    f = np.zeros(n, np.float32); dp = np.zeros(n, np.float32); k = np.zeros(2, np.float32)
+    lib().ref_precal_ctf(voltage, dU, dV, theta, Cs, N, pixelSize, _ptr(iCol), _ptr(iRow), n, _ptr(f), _ptr(dp), _ptr(k))
+    return f, dp, k
+
+
+def expect_ctf(proj, dat, sigRcp, defP, freq, K1, K2, phaseShift, ac, quat, tran, dpar, wR, wT, wD, wC, iCol, iRow, N, simd=1):
+    """one phase of the likelihood loop with the defocus dimension, one image (ref_expect_ctf in ref_harness.cpp)"""
+    dat = np.ascontiguousarray(dat, np.complex64); sigRcp = np.ascontiguousarray(sigRcp, np.float32)
+    defP = np.ascontiguousarray(defP, np.float32); freq = np.ascontiguousarray(freq, np.float32)
+    quat = np.ascontiguousarray(quat, np.float64); tran = np.ascontiguousarray(tran, np.float64); dpar = np.ascontiguousarray(dpar, np.float64)
+    wR = np.ascontiguousarray(wR, np.float64); wT = np.ascontiguousarray(wT, np.float64); wD = np.ascontiguousarray(wD, np.float64)
+    nR, nT, nD, P = len(quat), len(tran), len(dpar), len(iCol)
+    oC = np.zeros(1, np.float32); oR = np.zeros(nR, np.float32); oT = np.zeros(nT, np.float32); oD = np.zeros(nD, np.float32)
+    base = np.zeros(1, np.float32); logL = np.zeros((nR, nT, nD), np.float32)
+    lib().ref_expect_ctf(proj.h, _ptr(dat), _ptr(sigRcp), _ptr(defP), _ptr(freq), K1, K2, phaseShift, ac, _ptr(quat), _ptr(tran), _ptr(dpar),
+                         _ptr(wR), _ptr(wT), _ptr(wD), float(wC), _ptr(iCol), _ptr(iRow), P, N, nR, nT, nD, simd, _ptr(oC), _ptr(oR), _ptr(oT),
+                         _ptr(oD), _ptr(base), _ptr(logL))
+    return dict(uC=oC[0], uR=oR, uT=oT, uD=oD, base=base[0], logL=logL)
 
 
 class replay:

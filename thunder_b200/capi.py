@@ -74,6 +74,10 @@ def _sig(lib):
     f = lib.thb_scale_images; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_get_mode; f.restype = _i; f.argtypes = [_p]
     f = lib.thb_insert_classes; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
+    f = lib.thb_insert_ctf; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p, _p, C.c_float]
+    f = lib.thb_set_frequency; f.restype = _i; f.argtypes = [_p, _p]
+    f = lib.thb_upload_stack_defocus; f.restype = _i; f.argtypes = [_p, _i, _i, _p]
+    f = lib.thb_expect_local_ctf; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i, _i] + [_p] * 13
     f = lib.thb_insert_counts; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pack_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, C.c_float, _p]
     f = lib.thb_download_stack; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _p, _p, _p]
@@ -423,6 +427,37 @@ class Context:
         offS = _arr(offS, np.float64, (nImg, 2))
         imgIdx = _arr(imgIdx, np.int32, (nImg,))
         self._chk(self.lib.thb_insert(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt)))
+
+    def insert_ctf(self, w, nr, nt, nd, ctfAttr, pixelSize, offS=None, imgIdx=None):
+        """CTF search: per-draw defocus factors nd[nImg][mReco], ctfAttr[nImg][7]"""
+        nr = _arr(nr, np.float64)
+        nImg, mReco, _ = nr.shape
+        nt = _arr(nt, np.float64, (nImg, mReco, 2)); nd = _arr(nd, np.float64, (nImg, mReco))
+        w = _arr(w, np.float32, (nImg,)); offS = _arr(offS, np.float64, (nImg, 2)); imgIdx = _arr(imgIdx, np.int32, (nImg,))
+        ctfAttr = _arr(ctfAttr, np.float32, (nImg, 7))
+        self._chk(self.lib.thb_insert_ctf(self.h, nImg, _ptr(imgIdx), mReco, _ptr(w), _ptr(offS), _ptr(nr), _ptr(nt), _ptr(nd), _ptr(ctfAttr),
+                                          float(pixelSize)))
+
+    def set_frequency(self, freQ):
+        self._chk(self.lib.thb_set_frequency(self.h, _ptr(_arr(freQ, np.float32, (self.nPxlE,)))))
+
+    def upload_stack_defocus(self, base, defP):
+        defP = _arr(defP, np.float32)
+        self._chk(self.lib.thb_upload_stack_defocus(self.h, int(base), defP.shape[0], _ptr(defP)))
+
+    def expect_local_ctf(self, quat, tran, dpar, wR, wT, wD, ctfK, imgIdx=None, want_logL=True):
+        quat = _arr(quat, np.float64)
+        nAct, nR, _ = quat.shape
+        tran = _arr(tran, np.float64); nT = tran.shape[1]
+        dpar = _arr(dpar, np.float64); nD = dpar.shape[1]
+        wR = _arr(wR, np.float64, (nAct, nR)); wT = _arr(wT, np.float64, (nAct, nT)); wD = _arr(wD, np.float64, (nAct, nD))
+        ctfK = _arr(ctfK, np.float32, (nAct, 4)); imgIdx = _arr(imgIdx, np.int32, (nAct,))
+        uR = np.empty((nAct, nR), np.float32); uT = np.empty((nAct, nT), np.float32); uD = np.empty((nAct, nD), np.float32)
+        uC = np.empty(nAct, np.float32); base = np.empty(nAct, np.float32)
+        logL = np.empty((nAct, nR, nT, nD), np.float32) if want_logL else None
+        self._chk(self.lib.thb_expect_local_ctf(self.h, nAct, _ptr(imgIdx), nR, nT, nD, _ptr(quat), _ptr(tran), _ptr(dpar), _ptr(wR), _ptr(wT),
+                                                _ptr(wD), _ptr(ctfK), _ptr(uR), _ptr(uT), _ptr(uD), _ptr(uC), _ptr(base), _ptr(logL)))
+        return dict(uR=uR, uT=uT, uD=uD, uC=uC, base=base, logL=logL)
 
     def insert_counts(self, w, nDraw, nr, nt, offS=None, imgIdx=None):
         """3D classification: only the first nDraw[l] of the mReco rows of image l are inserted"""

@@ -167,6 +167,21 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
     a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
     a.work = nullptr;
+    if (a.nD > 0) {
+        // CTF search: the defocus dimension inside the kernel (the CTF of every defocus factor on the fly), table in global scratch
+        if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "expect: CTF search is MODE_3D only");
+        a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * a.nR * a.nT * a.nD);
+        if (!a.work) return THB_E_CUDA;
+        span_begin(ctx, KF_EXPECT);
+        if (ctx->quadOct)
+            expect_direct_kernel<2, true, false, E_TC, true><<<a.nAct, E3_THREADS, E3_SMEM_BYTES, ctx->stream>>>(a);
+        else
+            expect_direct_kernel<2, false, false, E_TC, true><<<a.nAct, E3_THREADS, E3_SMEM_BYTES, ctx->stream>>>(a);
+        span_end(ctx);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+        return THB_OK;
+    }
     // a handful of images (the reference's one-image-at-a-time seam, the tail of an adaptive E-step): one CTA per image would
     // leave the chip idle - spread every image over (pixel chunk, rotation group) CTAs instead (thb_expect6.cuh)
     if (ctx->expectImpl == 3 && (ctx->expectSpread == 1 || (ctx->expectSpread < 0 && a.nAct * 4 <= ctx->smCount))) {
@@ -312,6 +327,7 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a, const int* hImgIdx)
     if (a.nImg <= 0) return THB_OK;
     const bool slab = !ctx->mode2D && !a.drawC && (ctx->insertImpl == 0 || ctx->insertImpl == 3) && a.mReco <= M2_MAXD &&
                       ctx->segM && ctx->nSegM <= M2_MAXSEG;
+    if (!slab && a.nd.p) return set_error(ctx, THB_E_STATE, "insert: the CTF search (per-draw CTF) needs the slab kernel (MODE_3D, mReco <= %d)", M2_MAXD);
     if (!slab) return launch_insert_legacy(ctx, a);
     // ---- slab insert (thb_insert2.cuh): grid (image, slab), images of one slot adjacent, slab thickness from the L2 budget
     const int n = a.vdim;
@@ -361,6 +377,7 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a, const int* hImgIdx)
         if (a.drawR) s.a.drawR = a.drawR + (size_t)l0 * a.mReco;
         if (a.drawT) s.a.drawT = a.drawT + (size_t)l0 * a.mReco;
         if (a.drawCount) s.a.drawCount = a.drawCount + l0;
+        if (a.nd.p) { s.a.nd.p = a.nd.p + (size_t)l0 * a.nd.sP; s.a.ctfAttr = a.ctfAttr + 7 * (size_t)l0; }
         s.seg = (const Seg*)ctx->segM; s.nSeg = ctx->nSegM; s.order = dOrder; s.prep = prep; s.maxD = maxD;
         s.pf = ctx->pfM; s.rMaxPad = ctx->rMaxPadM; s.zMin = -(n / 2); s.th = th;
         span_begin(ctx, KF_INSERT);
@@ -443,7 +460,7 @@ int thb_create(thb_ctx** out, int device)
 
 static void free_stack(Stack& s)
 {
-    cudaFree(s.dat); cudaFree(s.ctf); cudaFree(s.sig); cudaFree(s.slot);
+    cudaFree(s.dat); cudaFree(s.ctf); cudaFree(s.sig); cudaFree(s.def); cudaFree(s.slot);
     s = Stack();
 }
 
@@ -463,7 +480,7 @@ void thb_destroy(thb_ctx* ctx)
     }
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
-    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->segM); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
+    cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->segM); cudaFree(ctx->freqE); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
     cudaFree(ctx->dO); cudaFree(ctx->dCounter);
     for (int i = 0; i < THB_N_SCRATCH; ++i) cudaFree(ctx->scratch[i]);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -751,6 +768,8 @@ int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
     THB_CUDA(ctx, cudaMalloc(&ctx->tilesE, sizeof(TileDesc) * tiles.size()));
     THB_CUDA(ctx, cudaMemcpy(ctx->tilesE, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice));
     if (ctx->nPxlE != nPxl) free_stack(ctx->stackE);   // a resident stack belongs to one pixel list
+    cudaFree(ctx->freqE);                              // ... and so does the frequency table of the CTF search
+    ctx->freqE = nullptr;
     ctx->N = N; ctx->pf = pf; ctx->nPxlE = nPxl;
     return THB_OK;
 }
@@ -1131,6 +1150,117 @@ int thb_expect_local(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, 
     return THB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ CTF search (SEARCH_TYPE_CTF)
+__global__ void permute_float_kernel(const float* __restrict__ src, const int* __restrict__ perm, int P, int nImg, float* __restrict__ dst)
+{
+    const int l = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) dst[(size_t)l * P + i] = src[(size_t)l * P + perm[i]];
+}
+
+int thb_set_frequency(thb_ctx* ctx, const float* freQ)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->pixE || !freQ) return set_error(ctx, THB_E_STATE, "set_frequency: E pixel list not set / NULL table");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int P = ctx->nPxlE;
+    float* tmp = (float*)scratch(ctx, 0, sizeof(float) * (size_t)P);
+    if (!tmp) return THB_E_CUDA;
+    if (!ctx->freqE) THB_CUDA(ctx, cudaMalloc(&ctx->freqE, sizeof(float) * (size_t)P));
+    THB_CUDA(ctx, cudaMemcpyAsync(tmp, freQ, sizeof(float) * (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+    permute_float_kernel<<<dim3(std::min((P + 255) / 256, 64), 1), 256, 0, ctx->stream>>>(tmp, ctx->permE, P, 1, ctx->freqE);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_upload_stack_defocus(thb_ctx* ctx, int base, int nImg, const float* defP)
+{
+    if (!ctx) return THB_E_ARG;
+    Stack& s = ctx->stackE;
+    if (!s.dat) return set_error(ctx, THB_E_STATE, "upload_stack_defocus: E stack not reserved");
+    if (nImg <= 0 || !defP || base < 0 || base + nImg > s.nImg) return set_error(ctx, THB_E_ARG, "upload_stack_defocus: bad range / NULL array");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int P = ctx->nPxlE;
+    if (!s.def) THB_CUDA(ctx, cudaMalloc(&s.def, sizeof(float) * (size_t)s.nImg * P));
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, ((size_t)256 << 20) / ((size_t)P * 4)));
+    float* tmp = (float*)scratch(ctx, 4, sizeof(float) * (size_t)chunk * P);
+    if (!tmp) return THB_E_CUDA;
+    for (int i0 = 0; i0 < nImg; i0 += chunk) {
+        const int c = std::min(chunk, nImg - i0);
+        THB_CUDA(ctx, cudaMemcpyAsync(tmp, defP + (size_t)i0 * P, sizeof(float) * (size_t)c * P, cudaMemcpyHostToDevice, ctx->stream));
+        permute_float_kernel<<<dim3(std::min((P + 255) / 256, 64), c), 256, 0, ctx->stream>>>(tmp, ctx->permE, P, c, s.def + (size_t)(base + i0) * P);
+        ctx->launches++;
+        THB_CUDA(ctx, cudaGetLastError());
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return THB_OK;
+}
+
+int thb_expect_local_ctf(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int nT, int nD, const double* quat, const double* tran,
+                         const double* dpar, const double* wR, const double* wT, const double* wD, const float* ctfK, float* uR, float* uT,
+                         float* uD, float* uC, float* base, float* logL)
+{
+    if (!ctx) return THB_E_ARG;
+    const int vdim = check_expect_state(ctx, "expect_local_ctf");
+    if (vdim < 0) return vdim;
+    if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "expect_local_ctf: MODE_3D only");
+    if (!ctx->freqE || !ctx->stackE.def) return set_error(ctx, THB_E_STATE, "expect_local_ctf: frequency table / per-pixel defocus not uploaded (thb_set_frequency, thb_upload_stack_defocus)");
+    if (nAct <= 0 || nR <= 0 || nT <= 0 || nD <= 0 || !quat || !tran || !dpar || !wR || !wT || !wD || !ctfK)
+        return set_error(ctx, THB_E_ARG, "expect_local_ctf: bad arguments");
+    if (imgIdx)
+        for (int i = 0; i < nAct; ++i)
+            if (imgIdx[i] < 0 || imgIdx[i] >= ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "expect_local_ctf: imgIdx[%d] outside the stack", i);
+    if (!imgIdx && nAct > ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "expect_local_ctf: nAct exceeds the stack");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nq = (size_t)nAct * nR * 4, nt = (size_t)nAct * nT * 2, nwr = (size_t)nAct * nR, nwt = (size_t)nAct * nT, nwd = (size_t)nAct * nD;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + nt + nwr + nwt + 2 * nwd) + sizeof(float) * 4 * (size_t)nAct + sizeof(int) * (size_t)nAct);
+    const size_t nL = nwr * nT * nD;
+    const size_t nout = nwr + nwt + nwd + 2 * (size_t)nAct + (logL ? nL : 0);
+    float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
+    if (!din || !dout) return THB_E_CUDA;
+    double* dq = din; double* dt = dq + nq; double* dwr = dt + nt; double* dwt = dwr + nwr; double* dwd = dwt + nwt; double* dd = dwd + nwd;
+    float* dk = (float*)(dd + nwd);
+    int* didx = (int*)(dk + 4 * (size_t)nAct);
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwr, wR, sizeof(double) * nwr, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwt, wT, sizeof(double) * nwt, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwd, wD, sizeof(double) * nwd, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dd, dpar, sizeof(double) * nwd, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dk, ctfK, sizeof(float) * 4 * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
+    if (imgIdx) THB_CUDA(ctx, cudaMemcpyAsync(didx, imgIdx, sizeof(int) * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
+    ExpectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vols = vol_table(ctx);
+    a.vdim = vdim; a.pitch = vol_pitch(vdim);
+    a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
+    a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
+    a.nAct = nAct; a.imgIdx = imgIdx ? didx : nullptr; a.nR = nR; a.nT = nT; a.slotAll = -1;
+    a.quat = View3{dq, (long long)nR * 4, 4, 1};
+    a.tran = View3{dt, (long long)nT * 2, 2, 1};
+    a.wR = View3{dwr, (long long)nR, 1, 0};
+    a.wT = View3{dwt, (long long)nT, 1, 0};
+    a.nD = nD; a.defP = ctx->stackE.def; a.freq = ctx->freqE; a.ctfK = dk;
+    a.dpar = View3{dd, (long long)nD, 1, 0};
+    a.wD = View3{dwd, (long long)nD, 1, 0};
+    a.uR = dout; a.uT = a.uR + nwr; a.uD = a.uT + nwt; a.uC = a.uD + nwd; a.base = a.uC + nAct;
+    a.logL = logL ? a.base + nAct : nullptr;
+    const int saved = ctx->expectImpl;
+    ctx->expectImpl = 3;                         // the CTF search lives in the default (cell-layout) kernel only
+    int rc = launch_expect_local(ctx, a);
+    ctx->expectImpl = saved;
+    if (rc) return rc;
+    if (uR) THB_CUDA(ctx, cudaMemcpyAsync(uR, a.uR, sizeof(float) * nwr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uT) THB_CUDA(ctx, cudaMemcpyAsync(uT, a.uT, sizeof(float) * nwt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uD) THB_CUDA(ctx, cudaMemcpyAsync(uD, a.uD, sizeof(float) * nwd, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uC) THB_CUDA(ctx, cudaMemcpyAsync(uC, a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+    if (base) THB_CUDA(ctx, cudaMemcpyAsync(base, a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logL) THB_CUDA(ctx, cudaMemcpyAsync(logL, a.logL, sizeof(float) * nL, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
 // Global-scan shape (src/Optimiser.cpp:633-914): one shared rotation/translation set against every
 // image.  Round 1: the same fused kernel with particle-stride 0 views; rotations beyond one CTA's
 // shared-memory budget are processed in chunks and merged on the host with the reference's
@@ -1279,7 +1409,8 @@ int check_insert_slots(thb_ctx* ctx, int nImg, const int* imgIdx, int imgBase, c
 extern "C" {
 
 static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,
-                       const double* nr, const double* nt, const int* nDraw = nullptr)
+                       const double* nr, const double* nt, const int* nDraw = nullptr, const double* nd = nullptr,
+                       const float* ctfAttr = nullptr, float pixelSize = 0.f)
 {
     if (!ctx) return THB_E_ARG;
     if (nImg <= 0 || mReco <= 0 || !w || !nr || !nt) return set_error(ctx, THB_E_ARG, "insert: bad arguments");
@@ -1311,10 +1442,16 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
 
     const int qc = ctx->mode2D ? 2 : 4;      // MODE_2D: nr[nImg][mReco][2] = (cos, sin), as InsertI2D receives it
     const size_t nq = (size_t)nImg * mReco * qc, ntt = (size_t)nImg * mReco * 2;
-    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg) + sizeof(float) * nImg + sizeof(int) * (2 * (size_t)nImg + (size_t)nImg * mReco));
+    const size_t nnd = nd ? (size_t)nImg * mReco : 0;
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * (nq + ntt + 2 * (size_t)nImg + nnd) + sizeof(float) * (8 * (size_t)nImg) + sizeof(int) * (2 * (size_t)nImg + (size_t)nImg * mReco));
     if (!din) return THB_E_CUDA;
-    double* dq = din; double* dt = dq + nq; double* doff = dt + ntt;
-    float* dw = (float*)(doff + 2 * (size_t)nImg);
+    double* dq = din; double* dt = dq + nq; double* doff = dt + ntt; double* dnd = doff + 2 * (size_t)nImg;
+    float* dattr = (float*)(dnd + nnd);
+    float* dw = dattr + 7 * (size_t)nImg;
+    if (nd) {
+        THB_CUDA(ctx, cudaMemcpyAsync(dnd, nd, sizeof(double) * nnd, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(dattr, ctfAttr, sizeof(float) * 7 * (size_t)nImg, cudaMemcpyHostToDevice, ctx->stream));
+    }
     int* didx = (int*)(dw + nImg);
     int* dnc = didx + nImg;
     int* dcount = dnc + (size_t)nImg * mReco;
@@ -1339,6 +1476,11 @@ static int insert_impl(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, con
     a.mode2D = ctx->mode2D;
     a.drawC = nc ? dnc : nullptr;
     a.drawCount = nDraw ? dcount : nullptr;
+    if (nd) {
+        a.nd = View3{dnd, (long long)mReco, 1, 0};
+        a.ctfAttr = dattr;
+        a.pixelSize = pixelSize;
+    }
     int rc = launch_insert(ctx, a, imgIdx);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1356,6 +1498,14 @@ int thb_insert_counts(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, cons
 {
     if (ctx && !nDraw) return set_error(ctx, THB_E_ARG, "insert_counts: nDraw == NULL");
     return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nullptr, nr, nt, nDraw);
+}
+
+// CTF search: every draw carries its own defocus factor, its CTF is computed on the fly (src/Optimiser.cpp:7171-7215)
+int thb_insert_ctf(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const double* nr,
+                   const double* nt, const double* nd, const float* ctfAttr, float pixelSize)
+{
+    if (ctx && (!nd || !ctfAttr || !(pixelSize > 0))) return set_error(ctx, THB_E_ARG, "insert_ctf: nd / ctfAttr NULL or pixelSize <= 0");
+    return insert_impl(ctx, nImg, imgIdx, mReco, w, offS, nullptr, nr, nt, nullptr, nd, ctfAttr, pixelSize);
 }
 
 int thb_insert_classes(thb_ctx* ctx, int nImg, const int* imgIdx, int mReco, const float* w, const double* offS, const int* nc,

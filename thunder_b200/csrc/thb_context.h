@@ -21,6 +21,7 @@ struct Stack {
     float2* dat = nullptr;
     float* ctf = nullptr;
     float* sig = nullptr;
+    float* def = nullptr;        // E stack, CTF search only: per-pixel defocus (_defocusP)
     int* slot = nullptr;
     std::vector<int> hslot;      // host copy of slot[] (validation of the slots a launch will touch)
 };
@@ -89,6 +90,7 @@ struct thb_ctx {
     int4* pixM = nullptr;
     int* permE = nullptr;        // blocked position -> caller's pixel index
     int* permM = nullptr;
+    float* freqE = nullptr;      // CTF search: |k| / (N pixelSize) of the E pixel list (_frequency), blocked order
     void* segM = nullptr;        // thb::Seg[]: row-major runs {j, iFirst, count, start} of the M pixel list (slab insert, thb_insert2.cuh)
     int nSegM = 0;
     float rMaxPadM = 0.f;        // largest |(pf i, pf j)| of the M pixel list

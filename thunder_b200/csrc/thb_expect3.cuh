@@ -120,6 +120,60 @@ __device__ __forceinline__ void expect_epilogue(const ExpectArgs& A, int p, floa
     }
 }
 
+// CTF of one pixel for the defocus factor d, exactly the mixed float / double expression of src/Optimiser.cpp:1253-1268:
+//   RFLOAT ki = K1 * defocusP * d * TSGSL_pow_2(f) + K2 * TSGSL_pow_4(f) - phaseShift      (d is a double: the first product is
+//   a float, everything up to the assignment a double; TSGSL_pow_n return (float)(double power), src/Precision.cpp:263-276)
+//   ctf = -TS_SQRT(1 - TSGSL_pow_2(ac)) * TS_SIN(ki) + ac * TS_COS(ki)
+__device__ __forceinline__ float ctf_search_value(float defP, float f, double d, float K1, float K2, float phaseShift, float w1, float ac)
+{
+    const double f2d = (double)f * (double)f;
+    const float pow2f = (float)f2d, pow4f = (float)(f2d * f2d);
+    const float p1 = __fmul_rn(K1, defP), p2 = __fmul_rn(K2, pow4f);
+    const float ki = (float)(__dsub_rn(__dadd_rn(__dmul_rn(__dmul_rn((double)p1, d), (double)pow2f), (double)p2), (double)phaseShift));
+    return __fadd_rn(__fmul_rn(-w1, sinf(ki)), __fmul_rn(ac, cosf(ki)));
+}
+
+// Epilogue with the defocus dimension: sL = the [nR][nT][nD] table; marginals carry the prior weights of the OTHER dimensions
+// (src/Optimiser.cpp:1383-1402): uR += s wT wD, uT += s wR wD, uD += s wR wT, uC += s wR wT wD
+template <int THREADS>
+__device__ __forceinline__ void expect_epilogue_ctf(const ExpectArgs& A, int p, float* sL, float* redf, double* redd)
+{
+    const int tid = threadIdx.x, nD = A.nD, nTD = A.nT * nD, nRT = A.nR * nTD;
+    float m = -INFINITY;
+    for (int i = tid; i < nRT; i += THREADS) m = fmaxf(m, sL[i]);
+    m = block_reduce_max(m, redf);
+    if (A.logL)
+        for (int i = tid; i < nRT; i += THREADS) A.logL[(size_t)p * nRT + i] = sL[i];
+    __syncthreads();
+    for (int i = tid; i < nRT; i += THREADS) sL[i] = expf(sL[i] - m);
+    __syncthreads();
+    double uc = 0.0;
+    for (int r = tid; r < A.nR; r += THREADS) {
+        double s = 0.0;
+        for (int t = 0; t < A.nT; ++t)
+            for (int d = 0; d < nD; ++d) s += (double)sL[(r * A.nT + t) * nD + d] * A.wT.at(p, t, 0) * A.wD.at(p, d, 0);
+        if (A.uR) A.uR[(size_t)p * A.nR + r] = (float)s;
+        uc += s * A.wR.at(p, r, 0);
+    }
+    for (int t = tid; t < A.nT; t += THREADS) {
+        double s = 0.0;
+        for (int r = 0; r < A.nR; ++r)
+            for (int d = 0; d < nD; ++d) s += (double)sL[(r * A.nT + t) * nD + d] * A.wR.at(p, r, 0) * A.wD.at(p, d, 0);
+        if (A.uT) A.uT[(size_t)p * A.nT + t] = (float)s;
+    }
+    for (int d = tid; d < nD; d += THREADS) {
+        double s = 0.0;
+        for (int r = 0; r < A.nR; ++r)
+            for (int t = 0; t < A.nT; ++t) s += (double)sL[(r * A.nT + t) * nD + d] * A.wR.at(p, r, 0) * A.wT.at(p, t, 0);
+        if (A.uD) A.uD[(size_t)p * nD + d] = (float)s;
+    }
+    uc = block_reduce_sum(uc, redd);
+    if (tid == 0) {
+        if (A.uC) A.uC[p] = (float)uc;
+        if (A.base) A.base[p] = m;
+    }
+}
+
 constexpr int E3_THREADS = 256;
 constexpr int E3_ROTS = 128;
 constexpr int E3_TILE = 128;
@@ -135,7 +189,7 @@ static_assert(sizeof(PixelRecT<E_TC>) == sizeof(PixelRec), "PixelRecT<9> is Pixe
 constexpr int E3_TC_SCAN = 15;
 constexpr size_t E3_SMEM_BYTES = E3_TILE * sizeof(PixelRec);     // + the [nR][nT] table for single-pass shapes
 
-template <int MINB, bool OCT, bool M2D = false, int TC = E_TC>
+template <int MINB, bool OCT, bool M2D = false, int TC = E_TC, bool CTFS = false>
 __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const ExpectArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -155,9 +209,16 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     const float* __restrict__ ctf = A.ctf + (size_t)img * P;
     const float* __restrict__ sig = A.sig + (size_t)img * P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nRT = A.nR * A.nT;
-    const bool single = A.nR <= E3_ROTS && A.nT <= TC;
+    const int nD = CTFS ? A.nD : 1;
+    const int nRT = A.nR * A.nT * nD;
+    const bool single = !CTFS && A.nR <= E3_ROTS && A.nT <= TC;
     float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_TILE * sizeof(PixelRecT<TC>)) : A.work + (size_t)p * nRT;
+    const float* __restrict__ defP = CTFS ? A.defP + (size_t)img * P : nullptr;
+    float cK1 = 0.f, cK2 = 0.f, cPs = 0.f, cAc = 0.f, cW1 = 0.f;
+    if (CTFS) {
+        cK1 = A.ctfK[4 * p]; cK2 = A.ctfK[4 * p + 1]; cPs = A.ctfK[4 * p + 2]; cAc = A.ctfK[4 * p + 3];
+        cW1 = sqrtf(1.0f - (float)((double)cAc * (double)cAc));
+    }
     double k0sum = 0.0;          // sum_i sig_i |dat_i|^2
     const int LB = A.quadBrick;
 
@@ -228,7 +289,9 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                 for (int c = 0; c < (M2D ? 2 : 4); ++c) q[c] = A.quat.at(p, rbase + rsrc, c);
             rot = make_rot2(q, M2D);
         }
+        for (int iD = 0; iD < nD; ++iD)
         for (int tbase = 0; tbase < A.nT; tbase += TC) {
+            const double dfac = CTFS ? A.dpar.at(p, iD, 0) : 1.0;
             __syncthreads();
             if (tid < TC) {
                 const int t = tbase + tid;
@@ -244,7 +307,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
 #pragma unroll
             for (int t = 0; t < TC; ++t) acc[t] = 0.0f;
             float nrm = 0.0f;
-            const bool firstPass = (rbase == 0 && tbase == 0);
+            const bool firstPass = (rbase == 0 && tbase == 0 && iD == 0);
 
             for (int tile0 = 0; tile0 < P; tile0 += E3_TILE) {
                 const int cnt = min(E3_TILE, P - tile0);
@@ -256,7 +319,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                         const int i = tile0 + k;
                         const int4 c = A.pix[i];
                         const float2 d = dat[i];
-                        const float cf = ctf[i], sg = sig[i];
+                        const float cf = CTFS ? ctf_search_value(defP[i], A.freq[i], dfac, cK1, cK2, cPs, cW1, cAc) : ctf[i];
+                        const float sg = sig[i];
                         const float m2 = -2.0f * sg * cf;
                         PixelRecT<TC>& rec = tile[k];
                         if (sub == 0) {
@@ -343,14 +407,17 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
                     if (tbase + t >= A.nT) continue;
                     double tot = (double)acc[t];
                     for (int j = 1; j < nParts; ++j) tot += (double)pk0[(j - 1) * pstride + t];
-                    sL[(size_t)(rbase + rsrc) * A.nT + tbase + t] = (float)(k0sum + nn + tot);
+                    sL[((size_t)(rbase + rsrc) * A.nT + tbase + t) * nD + iD] = (float)(k0sum + nn + tot);
                 }
             }
         }
     }
     __syncthreads();
 
-    expect_epilogue<E3_THREADS>(A, p, sL, redf, redd);
+    if (CTFS)
+        expect_epilogue_ctf<E3_THREADS>(A, p, sL, redf, redd);
+    else
+        expect_epilogue<E3_THREADS>(A, p, sL, redf, redd);
 }
 
 }  // namespace thb

@@ -36,9 +36,10 @@ constexpr int M2_MAXSEG = 512;      // row segments of the M pixel list (box 512
 constexpr int M2_ENT = 1024;        // (group, segment) entries flattened per round
 
 // per-image output of insert_prep_kernel, `stride` bytes apart:
-//   PrepHdr | Rot2 rot[maxD] | int grpEnd[maxD] | float2 ramp[maxD]        (draws sorted by group; grpEnd = end position)
+//   PrepHdr | Rot2 rot[maxD] | int grpEnd[maxD] | float4 ramp[maxD]        (draws sorted by group; grpEnd = end position;
+//   ramp = phase-ramp slopes of the draw's translation and, with CTF search, its defocusU d, defocusV d)
 struct PrepHdr { int nGrp, nDraw; float wgt; int slot; };
-__host__ __device__ inline size_t prep_stride(int maxD) { return sizeof(PrepHdr) + (size_t)maxD * (sizeof(Rot2) + sizeof(int) + sizeof(float2)); }
+__host__ __device__ inline size_t prep_stride(int maxD) { return sizeof(PrepHdr) + (size_t)maxD * (sizeof(Rot2) + sizeof(int) + sizeof(float4)); }
 
 struct InsertSlabArgs {
     InsertArgs a;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128) insert_prep_kernel(const InsertSlabArgs S
     PrepHdr* hdr = reinterpret_cast<PrepHdr*>(base);
     Rot2* gRot = reinterpret_cast<Rot2*>(base + sizeof(PrepHdr));
     int* gEnd = reinterpret_cast<int*>(gRot + S.maxD);
-    float2* ramp = reinterpret_cast<float2*>(gEnd + S.maxD);
+    float4* ramp = reinterpret_cast<float4*>(gEnd + S.maxD);
 
     const int mTot = A.drawCount ? max(0, min(A.mReco, A.drawCount[l])) : A.mReco;
     int nGrpTot = 0;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) insert_prep_kernel(const InsertSlabArgs S
         __syncthreads();
         double dx = 0.0, dy = 0.0, dz = 0.0;
         Rot2 rot;
-        float rc = 0.f, rr = 0.f;
+        float rc = 0.f, rr = 0.f, dUs = 0.f, dVs = 0.f;
         if (tid < mcnt) {
             const int m = mbase + tid;
             const long long sr = A.drawR ? A.drawR[(size_t)l * A.mReco + m] : m;
@@ -90,6 +91,11 @@ __global__ void __launch_bounds__(128) insert_prep_kernel(const InsertSlabArgs S
             const double tx = A.nt.at(l, st, 0) - ox, ty = A.nt.at(l, st, 1) - oy;
             rc = (float)(-tx) / (float)A.N;      // translate(dst, src, -(tran - offset)(0), ...): RFLOAT arguments
             rr = (float)(-ty) / (float)A.N;
+            if (A.nd.p) {     // CTF(ctf, pixelSize, voltage, defocusU * d, defocusV * d, ...): RFLOAT arguments (src/Optimiser.cpp:7173-7187)
+                const double dfac = A.nd.at(l, m, 0);
+                dUs = (float)((double)A.ctfAttr[7 * l + 1] * dfac);
+                dVs = (float)((double)A.ctfAttr[7 * l + 2] * dfac);
+            }
             dx = -(rot.c0[0] * tx + rot.c1[0] * ty);   // insertDir(-rot3D * (tran - offset, 0))
             dy = -(rot.c0[1] * tx + rot.c1[1] * ty);
             dz = -(rot.c0[2] * tx + rot.c1[2] * ty);
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(128) insert_prep_kernel(const InsertSlabArgs S
                 size += rj == tid;
                 gidx += (rj == j) && (j < tid);
             }
-            ramp[mbase + pos] = make_float2(rc, rr);
+            ramp[mbase + pos] = make_float4(rc, rr, dUs, dVs);
             leader = rep == tid;
             if (leader) {
                 gRot[nGrpTot + gidx] = rot;
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(M2_THREADS, 2) insert_slab_kernel(const Insert
     const InsertArgs& A = S.a;
     __shared__ Rot2 sRot[M2_MAXD];
     __shared__ int sEnd[M2_MAXD];
-    __shared__ float2 sRamp[M2_MAXD];
+    __shared__ float4 sRamp[M2_MAXD];
     __shared__ Seg sSeg[M2_MAXSEG];
     __shared__ SlabRec sRec[M2_ENT];
     __shared__ int sPre[M2_ENT + 1];
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(M2_THREADS, 2) insert_slab_kernel(const Insert
     const PrepHdr hdr = *reinterpret_cast<const PrepHdr*>(base);
     const Rot2* gRot = reinterpret_cast<const Rot2*>(base + sizeof(PrepHdr));
     const int* gEnd = reinterpret_cast<const int*>(gRot + S.maxD);
-    const float2* ramp = reinterpret_cast<const float2*>(gEnd + S.maxD);
+    const float4* ramp = reinterpret_cast<const float4*>(gEnd + S.maxD);
     const int nGrp = hdr.nGrp;
     if (nGrp == 0) return;
 
@@ -188,6 +194,14 @@ __global__ void __launch_bounds__(M2_THREADS, 2) insert_slab_kernel(const Insert
     const float wgt = hdr.wgt;
     const float2* __restrict__ dat = A.dat + (size_t)img * P;
     const float* __restrict__ ctf = A.ctf + (size_t)img * P;
+    const bool cSearch = A.nd.p != nullptr;
+    CtfConst ck{};
+    float cTheta = 0.f;
+    if (cSearch) {
+        const float* at = A.ctfAttr + 7 * (size_t)l;
+        ck = ctf_const(at[0], at[4], at[5], at[6]);
+        cTheta = at[3];
+    }
 
     const int GB = max(1, min(nGrp, M2_ENT / S.nSeg));     // rotation groups per round
     for (int g0 = 0; g0 < nGrp; g0 += GB) {
@@ -253,21 +267,27 @@ __global__ void __launch_bounds__(M2_THREADS, 2) insert_slab_kernel(const Insert
             const bool conj = fold_floor(x, y, z, x0, y0, z0, xd, yd, zd);
             if (z0 < zlo || z0 >= zhi) continue;
             const float2 d = dat[p];
-            const float cf = ctf[p];
-            float fx = 0.f, fy = 0.f;
+            float cf = ctf[p];
+            float fx = 0.f, fy = 0.f, tv = 0.f;
             const int start = g ? sEnd[g - 1] : 0, end = sEnd[g];
+            CtfPixel cp{};
+            if (cSearch) cp = ctf_pixel(c.z, c.w, A.pixelSize, A.N, cTheta);
             for (int q = start; q < end; ++q) {
-                const float2 rp = sRamp[q];
+                const float4 rp = sRamp[q];
                 const float ph = translate_phase(c.z, c.w, rp.x, rp.y);
                 float s, co;
                 sincosf(ph, &s, &co);
                 // src * COMPLEX_POLAR(-ph) = d * (co - i s)
                 const float vx = d.x * co + d.y * s;
                 const float vy = d.y * co - d.x * s;
+                if (cSearch) {
+                    cf = ctf_eval(cp, ck, rp.z, rp.w);        // this draw's own CTF
+                    tv += (cf * cf) * wgt;
+                }
                 fx += (vx * cf) * wgt;
                 fy += (vy * cf) * wgt;
             }
-            const float tv = (cf * cf) * wgt * (float)(end - start);
+            if (!cSearch) tv = (cf * cf) * wgt * (float)(end - start);
             if (conj) fy = -fy;
             float w8[8];
             tri_weights(xd, yd, zd, w8);

@@ -10,6 +10,37 @@ namespace thb {
 // same float / double mix).  Output in the resident blocked order: d*[l][i] describes the caller's pixel perm[i].
 struct CtfAttr7 { float voltage, defocusU, defocusV, theta, Cs, ac, phaseShift; };
 
+// CTF() of src/CTF.cpp:118-151 for one pixel (iCol, iRow), split into what does not depend on the defocus values (the CTF search of
+// the insert evaluates it once per draw with defocusU d, defocusV d) and the rest; same float / double mix and unfused order
+struct CtfPixel { float u2, u4, c2; };     // |k|^2, |k|^4 in physical units, cos(2 (angle - theta))
+__device__ __forceinline__ CtfPixel ctf_pixel(int iCol, int iRow, float pixelSize, int N, float theta)
+{
+    const float u = (float)hypot((double)((float)iCol / (pixelSize * (float)N)), (double)((float)iRow / (pixelSize * (float)N)));
+    const float angle = (float)(atan2((double)iRow, (double)iCol) - (double)theta);
+    const double u2d = (double)u * u;
+    CtfPixel c;
+    c.u2 = (float)u2d; c.u4 = (float)(u2d * u2d); c.c2 = cosf(__fmul_rn(2.0f, angle));
+    return c;
+}
+struct CtfConst { float K1, K2, w1, w2, phaseShift; };
+__device__ __forceinline__ CtfConst ctf_const(float voltage, float Cs, float ac, float phaseShift)
+{
+    const float lambda = (float)(12.2643247 / sqrt((double)voltage * (1 + (double)voltage * 0.978466e-6)));
+    CtfConst k;
+    k.w1 = sqrtf(1 - (float)((double)ac * (double)ac));
+    k.w2 = ac;
+    k.K1 = (float)(3.14159265358979323846 * lambda);
+    k.K2 = (float)(1.57079632679489661923 * Cs * (float)((double)lambda * lambda * lambda));
+    k.phaseShift = phaseShift;
+    return k;
+}
+__device__ __forceinline__ float ctf_eval(const CtfPixel& c, const CtfConst& k, float dU, float dV)
+{
+    const float defocus = __fmul_rn(-__fadd_rn(__fadd_rn(dU, dV), __fmul_rn(__fadd_rn(dU, -dV), c.c2)), 0.5f);
+    const float ki = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(k.K1, defocus), c.u2), __fmul_rn(k.K2, c.u4)), -k.phaseShift);
+    return __fadd_rn(__fmul_rn(-k.w1, sinf(ki)), __fmul_rn(k.w2, cosf(ki)));
+}
+
 static __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_t imgStride, const int4* __restrict__ pix,
                                   const int* __restrict__ perm, const int* __restrict__ iPxl, const int* __restrict__ iSig, int P,
                                   const float* __restrict__ sigRcpTab, int nRing, const int* __restrict__ group,
@@ -18,11 +49,7 @@ static __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_
 {
     const int l = blockIdx.y;
     const CtfAttr7 a = attr[l];
-    const float lambda = (float)(12.2643247 / sqrt((double)a.voltage * (1 + (double)a.voltage * 0.978466e-6)));
-    const float w1 = sqrtf(1 - (float)((double)a.ac * (double)a.ac));
-    const float w2 = a.ac;
-    const float K1 = (float)(3.14159265358979323846 * lambda);
-    const float K2 = (float)(1.57079632679489661923 * a.Cs * (float)((double)lambda * lambda * lambda));
+    const CtfConst k = ctf_const(a.voltage, a.Cs, a.ac, a.phaseShift);
     const int g = group ? group[l] : 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
         const int s = perm[i];
@@ -30,15 +57,9 @@ static __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_
         const size_t d = (size_t)l * P + i;
         ddat[d] = imgFT[(size_t)l * imgStride + iPxl[s]];
         if (dsig) dsig[d] = sigRcpTab[(size_t)g * nRing + iSig[s]];
-        const float u = (float)hypot((double)((float)c.z / (pixelSize * (float)N)), (double)((float)c.w / (pixelSize * (float)N)));
-        const float angle = (float)(atan2((double)c.w, (double)c.z) - (double)a.theta);
-        // the phase reaches hundreds of radians: keep the reference's unfused operation order (no FMA contraction),
-        // one ulp of ki is already 3e-5 in the CTF value
-        const float defocus = __fmul_rn(-__fadd_rn(__fadd_rn(a.defocusU, a.defocusV), __fmul_rn(__fadd_rn(a.defocusU, -a.defocusV), cosf(__fmul_rn(2.0f, angle)))), 0.5f);
-        const double u2d = (double)u * u;
-        const float u2 = (float)u2d, u4 = (float)(u2d * u2d);
-        const float ki = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(K1, defocus), u2), __fmul_rn(K2, u4)), -a.phaseShift);
-        dctf[d] = __fadd_rn(__fmul_rn(-w1, sinf(ki)), __fmul_rn(w2, cosf(ki)));
+        // the phase reaches hundreds of radians: the reference's unfused operation order is kept (ctf_eval), one ulp of ki is
+        // already 3e-5 in the CTF value
+        dctf[d] = ctf_eval(ctf_pixel(c.z, c.w, pixelSize, N, a.theta), k, a.defocusU, a.defocusV);
     }
 }
 

@@ -73,7 +73,15 @@ struct ExpectArgs {
     float* uT;      // [nAct][nT]
     float* uC;      // [nAct]
     float* base;    // [nAct]
-    float* logL;    // [nAct][nR][nT] or null
+    float* logL;    // [nAct][nR][nT] or null  ([nAct][nR][nT][nD] with CTF search)
+    // ---- CTF search (SEARCH_TYPE_CTF, src/Optimiser.cpp:1248-1273, 1383-1402): nD defocus factors per image, the CTF of every one
+    // computed on the fly from the per-pixel defocus and frequency (allocPreCal, :8125-8168); nD == 0: off
+    int nD;
+    const float* defP;      // [nImg][P]   _defocusP, resident with the E stack (blocked pixel order)
+    const float* freq;      // [P]         _frequency
+    View3 dpar, wD;         // [nAct][nD]  defocus factors and their prior weights
+    const float* ctfK;      // [nAct][4]   K1, K2, phaseShift, amplitudeContrast of the image
+    float* uD;              // [nAct][nD]
 };
 
 struct InsertArgs {
@@ -97,6 +105,10 @@ struct InsertArgs {
     const int* drawT;
     const int* drawC;         // optional [nImg][mReco] accumulator slot of every draw (MODE_2D classes), else slotOfImg
     const int* drawCount;     // optional [nImg]: only the first drawCount[l] <= mReco draws of image l are inserted
+    // ---- CTF search (cSearch of InsertFT, src/Optimiser.cpp:7171-7215): the CTF of every draw from its own defocus factor
+    View3 nd;                 // [nImg][mReco][1] defocus factors, p == null: off
+    const float* ctfAttr;     // [nImg][7] voltage, defocusU, defocusV, defocusTheta, Cs, amplitudeContrast, phaseShift
+    float pixelSize;
 };
 
 }  // namespace thb

@@ -86,15 +86,21 @@ namespace {
 struct LocalState {
     int nPxl = 0, slots = 0, pf = 0, idim = 0;
     bool pixelsSet = false;
+    bool cSearch = false;
+    std::vector<float> freq;            // ExpectPrefre: _frequency of the pixel list
+    bool freqSet = false;
 } g_local[64];
 LocalState& localOf(int gpuIdx) { return g_local[gpuIdx & 63]; }
 int g_token;    // address handed out as the opaque device pointer
 }  // namespace
 
-void ExpectPrefre(int gpuIdx, RFLOAT** devfreQ, RFLOAT*, int)
+void ExpectPrefre(int gpuIdx, RFLOAT** devfreQ, RFLOAT* freQ, int npxl)
 {
-    // the frequency table feeds the on-the-fly CTF of the CTF search only (src/Optimiser.cpp:2173-2185)
-    (void)gpuIdx;
+    // the frequency table feeds the on-the-fly CTF of the CTF search only (src/Optimiser.cpp:2173-2185); it goes to the device
+    // together with the pixel list (local_pixels)
+    LocalState& L = localOf(gpuIdx);
+    L.freq.assign(freQ, freQ + npxl);
+    L.freqSet = false;
     if (devfreQ) *devfreQ = (RFLOAT*)&g_token;
 }
 
@@ -102,8 +108,9 @@ void ExpectLocalIn(int gpuIdx, Complex** devdatP, RFLOAT** devctfP, RFLOAT** dev
                    int searchType)
 {
     thb_ctx* c = thbContext(gpuIdx);
-    if (searchType == 2) { fprintf(stderr, "thunder_b200 [ExpectLocalIn]: CTF search (SEARCH_TYPE_CTF) is not implemented\n"); abort(); }
     LocalState& L = localOf(gpuIdx);
+    L.cSearch = searchType == 2;           // SEARCH_TYPE_CTF (include/Optimiser.h: SEARCH_TYPE_GLOBAL 0, _LOCAL 1, _CTF 2)
+    if (L.cSearch && (int)L.freq.size() != nPxl) { fprintf(stderr, "thunder_b200 [ExpectLocalIn]: CTF search: ExpectPrefre must come first\n"); abort(); }
     if (g_scan.npxl != nPxl || g_scan.iCol.empty()) { fprintf(stderr, "thunder_b200 [ExpectLocalIn]: ExpectPreidx must come first (pixel list of %d pixels)\n", nPxl); abort(); }
     L.nPxl = nPxl; L.slots = cpyNumL > 0 ? cpyNumL : 1; L.pixelsSet = false;
     if (devdatP) *devdatP = (Complex*)&g_token;
@@ -135,13 +142,14 @@ static void local_pixels(thb_ctx* c, LocalState& L, int pf, int idim)
     if (L.pixelsSet && L.pf == pf && L.idim == idim) return;
     CHK(c, thb_set_expect_pixels(c, idim, pf, L.nPxl, g_scan.iCol.data(), g_scan.iRow.data()));
     CHK(c, thb_stack_reserve(c, THB_STACK_EXPECT, L.slots));
+    if (L.cSearch) CHK(c, thb_set_frequency(c, L.freq.data()));
     L.pf = pf; L.idim = idim; L.pixelsSet = true;
 }
 
 // image slots need the pixel list, which needs pf and the image size: the reference passes them only to ExpectLocalPreI*, so the
 // images given to ExpectLocalP before the first ExpectLocalPreI* call of a device are kept as host pointers and uploaded there
 namespace {
-struct PendingImg { const Complex* dat; const RFLOAT* ctf; const RFLOAT* sig; };
+struct PendingImg { const Complex* dat; const RFLOAT* ctf; const RFLOAT* sig; const RFLOAT* def; };
 std::map<long long, PendingImg> g_pending;    // key = gpuIdx * 4096 + slot
 }
 
@@ -149,16 +157,21 @@ static void upload_slot(thb_ctx* c, int slot, int npxl, const PendingImg& im)
 {
     (void)npxl;
     CHK(c, thb_upload_stack_at(c, THB_STACK_EXPECT, slot, 1, (const float*)im.dat, im.ctf, im.sig, nullptr));
+    if (im.def) CHK(c, thb_upload_stack_defocus(c, slot, 1, im.def));
 }
 
 void ExpectLocalP(int gpuIdx, Complex*, RFLOAT*, RFLOAT*, RFLOAT*, Complex* datP, RFLOAT* ctfP, RFLOAT* defO, RFLOAT* sigP,
                   int threadId, int imgId, int npxl, int cSearch)
 {
     thb_ctx* c = thbContext(gpuIdx);
-    if (cSearch == 2) { fprintf(stderr, "thunder_b200 [ExpectLocalP]: CTF search is not implemented\n"); abort(); }
-    (void)defO;
     LocalState& L = localOf(gpuIdx);
-    PendingImg im{datP + (size_t)imgId * npxl, ctfP + (size_t)imgId * npxl, sigP + (size_t)imgId * npxl};
+    // CTF search: the per-pixel defocus of the image instead of its CTF (the reference passes ctfP all the same; it may be the
+    // stale array of the previous search type, and is not read)
+    const bool cs = cSearch == 2;
+    PendingImg im{datP + (size_t)imgId * npxl, ctfP ? ctfP + (size_t)imgId * npxl : nullptr, sigP + (size_t)imgId * npxl,
+                  cs && defO ? defO + (size_t)imgId * npxl : nullptr};
+    std::vector<float> zeros;
+    if (!im.ctf) { zeros.assign(npxl, 0.f); im.ctf = zeros.data(); }
     std::lock_guard<std::mutex> lk(g_mu);
     if (L.pixelsSet) upload_slot(c, threadId, npxl, im);
     else g_pending[(long long)gpuIdx * 4096 + threadId] = im;
@@ -188,8 +201,10 @@ void ExpectLocalRTD(int, ManagedCalPoint* mcp, double* oldR, double* oldT, doubl
     mcp->oldR = oldR; mcp->oldT = oldT; mcp->oldD = oldD; mcp->trans = trans; mcp->rot = rot; mcp->dpara = dpara;
 }
 
-static void local_prei(int gpuIdx, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, int pf, int idim, int npxl)
+static void local_prei(int gpuIdx, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, int pf, int idim, int npxl, RFLOAT phaseShift = 0,
+                       RFLOAT conT = 0, RFLOAT k1 = 0, RFLOAT k2 = 0)
 {
+    mcp->ctfK[0] = k1; mcp->ctfK[1] = k2; mcp->ctfK[2] = phaseShift; mcp->ctfK[3] = conT;
     thb_ctx* c = thbContext(gpuIdx);
     LocalState& L = localOf(gpuIdx);
     std::lock_guard<std::mutex> lk(g_mu);
@@ -203,10 +218,10 @@ static void local_prei(int gpuIdx, ManagedArrayTexture* mgr, ManagedCalPoint* mc
     mcp->mgr = mgr;
 }
 
-void ExpectLocalPreI3D(int gpuIdx, int, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT*, RFLOAT*, int*, int*, RFLOAT, RFLOAT,
-                       RFLOAT, RFLOAT, int pf, int idim, int, int npxl, int)
+void ExpectLocalPreI3D(int gpuIdx, int, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT*, RFLOAT*, int*, int*, RFLOAT phaseShift,
+                       RFLOAT conT, RFLOAT k1, RFLOAT k2, int pf, int idim, int, int npxl, int)
 {
-    local_prei(gpuIdx, mgr, mcp, pf, idim, npxl);
+    local_prei(gpuIdx, mgr, mcp, pf, idim, npxl, phaseShift, conT, k1, k2);
 }
 
 void ExpectLocalPreI2D(int gpuIdx, int, ManagedArrayTexture* mgr, ManagedCalPoint* mcp, RFLOAT*, RFLOAT*, int*, int*, RFLOAT, RFLOAT,
@@ -232,6 +247,19 @@ void ExpectLocalM(int gpuIdx, int datShift, ManagedCalPoint* mcp, Complex*, RFLO
         q = cs.data();
     }
     float uC = 0.f;
+    if (mcp->getCSearch() == 2) {
+        // CTF search: the defocus dimension (mD factors dpara with prior weights oldD), CTF on the fly from k1 / k2 / phaseShift / conT
+        const int nD = mcp->getMD();
+        if (!mcp->dpara || !mcp->oldD || !wD) { fprintf(stderr, "thunder_b200 [ExpectLocalM]: CTF search needs dpara / oldD / wD\n"); abort(); }
+        std::lock_guard<std::mutex> lk(g_mu);
+        CHK(c, thb_expect_local_ctf(c, 1, &img, nR, nT, nD, q, mcp->trans, mcp->dpara, mcp->oldR, mcp->oldT, mcp->oldD, mcp->ctfK, wR, wT, wD,
+                                    &uC, nullptr, nullptr));
+        for (int r = 0; r < nR; ++r) wR[r] = (RFLOAT)(wR[r] * oldC);
+        for (int t = 0; t < nT; ++t) wT[t] = (RFLOAT)(wT[t] * oldC);
+        for (int d = 0; d < nD; ++d) wD[d] = (RFLOAT)(wD[d] * oldC);
+        wC[0] = uC;
+        return;
+    }
     {
         std::lock_guard<std::mutex> lk(g_mu);      // one launch per device at a time, as the caller's omp lock already guarantees
         CHK(c, thb_expect_local(c, 1, &img, nR, nT, q, mcp->trans, mcp->oldR, mcp->oldT, wR, wT, &uC, nullptr, nullptr));
@@ -413,10 +441,14 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
               void* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD, int* nC, const int* iCol, const int* iRow,
               RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim, int dimSize, int imgNum)
 {
-    (void)sigRcpP; (void)ctfaData; (void)nD; (void)pixelSize;
+    (void)sigRcpP;
     thb_ctx* ctx = thbContext(0);
-    if (cSearch) {
-        fprintf(stderr, "thunder_b200 [InsertFT]: CTF search (cSearch) is not on the accelerated path of this build\n");
+    if (cSearch && (!ctfaData || !nD)) {
+        fprintf(stderr, "thunder_b200 [InsertFT]: cSearch needs ctfaData and nD\n");
+        abort();
+    }
+    if (cSearch && nC) {
+        fprintf(stderr, "thunder_b200 [InsertFT]: CTF search together with per-class draw counts is not implemented\n");
         abort();
     }
     const size_t nVox = (size_t)(vdim / 2 + 1) * vdim * vdim;
@@ -428,7 +460,9 @@ void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, C
     CHK(ctx, thb_set_insert_pixels(ctx, idim, opf, npxl, iCol, iRow));   // Reconstructor's _iCol/_iRow are padded (x pf)
     CHK(ctx, thb_upload_stack(ctx, THB_STACK_INSERT, imgNum, reinterpret_cast<const float*>(datP), ctfP, nullptr, nullptr));
     CHK(ctx, thb_reco_alloc(ctx, 0, vdim));
-    if (nC)   // 3D classification: nC[l] of the mReco rows of image l belong to this class (Optimiser.cpp:6862-6950)
+    if (cSearch)   // CTFAttr = 7 consecutive RFLOATs (include/Database.h:302-338): the layout thb_insert_ctf takes; one CTF per draw
+        CHK(ctx, thb_insert_ctf(ctx, imgNum, nullptr, mReco, w, offS, nR, nT, nD, reinterpret_cast<const float*>(ctfaData), pixelSize));
+    else if (nC)   // 3D classification: nC[l] of the mReco rows of image l belong to this class (Optimiser.cpp:6862-6950)
         CHK(ctx, thb_insert_counts(ctx, imgNum, nullptr, mReco, w, offS, nC, nR, nT));
     else
         CHK(ctx, thb_insert(ctx, imgNum, nullptr, mReco, w, offS, nR, nT));

@@ -8,7 +8,7 @@
 //     Volume&  ->  Complex* (FFTW half-complex, x fastest) + its dimension
 //     MPI_Comm& hemi / slav  ->  dropped: the half-map reduction is thb_allreduce over the context's
 //                                persistent NCCL communicator (thb_comm_init), a no-op with one rank
-//     CTFAttr* / nD / nC (CTF search, multi-class) -> accepted and ignored by this round's kernels
+//     CTFAttr* -> void* (7 consecutive RFLOATs per image, include/Database.h:302-338), read when cSearch is set
 // With -DTHB_WITH_THUNDER and the THUNDER include path, the Volume& / MPI_Comm& overloads of the
 // reference are provided too (inline, forwarding to the raw versions); see INTEGRATION.md.
 //
@@ -56,8 +56,9 @@ void ExpectGlobal3D(Complex* rotP, Complex* traP, Complex* datP, RFLOAT* ctfP, R
 // inside: the image slots, the pixel list and the projector volume live in the library's context of the device, the
 // projections never exist as arrays (ExpectLocalPreI3D only records its arguments), and ExpectLocalM is ONE launch of the fused
 // kernel spread over the whole chip for that image (thb_expect6.cuh).  The opaque device pointers handed back through
-// Complex** / RFLOAT** are non-null tokens, as with ExpectPreidx.  CTF search (cSearch / searchType == 2: the defocus
-// dimension) is not implemented: these functions abort with a message, as the reference's seam does on any error.
+// Complex** / RFLOAT** are non-null tokens, as with ExpectPreidx.  CTF search (searchType / cSearch == 2): ExpectPrefre's
+// frequency table, the defO of ExpectLocalP, the k1 / k2 / phaseShift / conT of ExpectLocalPreI3D and the dpara / oldD of
+// ExpectLocalRTD feed the defocus dimension of the fused kernel (thb_expect_local_ctf), ExpectLocalM returns wD as well.
 class ManagedArrayTexture {            // gpu/include/ManagedArrayTexture.h:13-30: here, a handle on the context's volume slot
 public:
     ~ManagedArrayTexture() {}
@@ -85,6 +86,7 @@ public:
     // what ExpectLocalRTD / ExpectLocalPreI3D were given for the image in flight (host arrays of the caller, read by ExpectLocalM)
     const double *oldR = nullptr, *oldT = nullptr, *oldD = nullptr, *trans = nullptr, *rot = nullptr, *dpara = nullptr;
     const ManagedArrayTexture* mgr = nullptr;
+    float ctfK[4] = {0, 0, 0, 0};      // k1, k2, phaseShift, conT of ExpectLocalPreI3D (CTF search)
 private:
     int _mode = 1, _cSearch = 0, _gpu = 0, _nR = 0, _nT = 0, _mD = 1, _npxl = 0;
 };
