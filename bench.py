@@ -405,8 +405,13 @@ def main():
                 "share_of_step": {k: v[0] / ms for k, v in fam.items()}}
         m_ms, m_n = fam["insert"]
         if m_n:
-            roof["insert_kernel"] = {"achieved": B * (PM * 12 + args.mreco * PM * 8 * 12 * 2.0) / (m_ms / m_n / 1e3) / 1e9,
-                                     "avg_launch_ms": m_ms / m_n}
+            ti = (tr or {}).get("insert_kernel") or {}
+            roof["insert_kernel"] = {"kernel": "insert_slab_kernel (fused translate + CTF + trilinear scatter of F and T, z-slab order: the reductions "
+                                               "resolve in L2, so the physical DRAM traffic is a small fraction of the algorithmic read-modify-write bytes)",
+                                     "achieved": B * (PM * 12 + args.mreco * PM * 8 * 12 * 2.0) / (m_ms / m_n / 1e3) / 1e9, "unit": "GB/s (algorithmic)",
+                                     "avg_launch_ms": m_ms / m_n,
+                                     "traffic": (ti["dram_bytes_per_particle"] * B if "dram_bytes_per_particle" in ti else None),
+                                     "traffic_source": ti.get("source")}
         cb = None
         if not args.no_cpu_baseline:
             try:

@@ -313,12 +313,24 @@ typedef struct thb_pf_params {
     double decreaseFactor;      /* PARTICLE_FILTER_DECREASE_FACTOR */
     int noDecreaseLimit;        /* N_PHASE_WITH_NO_VARI_DECREASE */
     uint64_t seed;
+    /* CTF search (SEARCH_TYPE_CTF): mLD > 0 adds the defocus dimension - Particle::initD(mLD, ctfRefineS) after the first
+     * perturbation, perturb(perturbFactorSCTF, PAR_D) after the later ones, calRank1st / calVari / resample of PAR_D after those of
+     * the rotations and translations (src/Optimiser.cpp:1193-1215, 1483-1488) - needs thb_pf_set_ctf, thb_set_frequency and
+     * thb_upload_stack_defocus; mLD <= max(mLR, mLT).  0: no CTF search. */
+    int mLD;
+    double ctfRefineS, perturbFactorSCTF;
 } thb_pf_params;
 
 /* Initialise nPar particles from (quat[nPar][4], k1,k2,k3[nPar], tran[nPar][2], s0,s1[nPar]) -
  * Particle::load semantics (src/Particle.cpp:401-556): ACG cloud about quat, Gaussian cloud about tran. */
 int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* quat, const double* k123,
                 const double* tran, const double* s01);
+/* CTF search: per particle the constants of the on-the-fly CTF of the E-step, ctfK[nPar][4] = {K1, K2, phaseShift,
+ * amplitudeContrast} (allocPreCal, src/Optimiser.cpp:8163-8167), and the attributes the M-step computes the CTF of every draw
+ * from, ctfAttr[nPar][7] (the layout of thb_pack_stack), with the pixel size.  Call after thb_pf_load. */
+int thb_pf_set_ctf(thb_ctx* ctx, const float* ctfK, const float* ctfAttr, float pixelSize);
+/* defocus factors of the loaded particles: d[nPar][mLD + 1] (the last one = the most likely, _topD), wD[nPar][mLD], sD[nPar] */
+int thb_pf_get_d(thb_ctx* ctx, double* d, double* wD, double* sD);
 /* Read back particle state.  Any pointer may be NULL.
  *   r[nPar][mLR][4], t[nPar][mLT][2], wR[nPar][mLR], wT[nPar][mLT],
  *   scal[nPar][20] = k1,k2,k3,s0,s1,rho,topR[4],topT[2],score,nPhase,variR,variT,peakFactorR,
@@ -345,6 +357,7 @@ int thb_pf_get_trace(thb_ctx* ctx, int nPhases, float* uR, float* uT, float* bas
 int thb_pf_get_trace_states(thb_ctx* ctx, int nPhases, double* st);
 /* the support indices drawn by the last thb_reconstruct_insert: drawR/drawT [nPar][mReco] */
 int thb_pf_get_draws(thb_ctx* ctx, int mReco, int* drawR, int* drawT);
+int thb_pf_get_draws_d(thb_ctx* ctx, int mReco, int* drawD);      /* CTF search: the defocus-factor index of every draw */
 /* E-step of one iteration over all loaded particles (particle p <-> image imgBase + p of the E stack):
  * phase loop of Optimiser::expectation with the particle filter on the device. */
 int thb_expectation(thb_ctx* ctx, int* nPhaseOut /* [nPar] or NULL */);

@@ -826,6 +826,7 @@ void ref_particle_set_u(void* h, int which /*0 C,1 R,2 T,3 D*/, const double* u,
     }
 }
 
+void ref_particle_initD(void* h, int nD, double sD) { ((Particle*)h)->initD(nD, sD); }
 void ref_particle_perturb(void* h, double pf, int pt) { ((Particle*)h)->perturb(pf, (ParticleType)pt); }
 void ref_particle_resample(void* h, int n, int pt) { ((Particle*)h)->resample(n, (ParticleType)pt); }
 void ref_particle_calVari(void* h, int pt) { ((Particle*)h)->calVari((ParticleType)pt); }

@@ -113,6 +113,7 @@ def lib():
         for name in ("perturb",):
             getattr(L, "ref_particle_" + name).argtypes = [_p, _d, _i]
         L.ref_particle_resample.argtypes = [_p, _i, _i]
+        L.ref_particle_initD.argtypes = [_p, _i, _d]
         for name in ("calVari", "calRank1st", "keepHalfHeightPeak", "setPeakFactor", "shuffle", "balanceWeight"):
             getattr(L, "ref_particle_" + name).argtypes = [_p, _i]
         for name in ("resetPeakFactor", "normW", "calScore"):
@@ -415,6 +416,12 @@ class Particle:
         r = np.empty((nR, 4)); t = np.empty((nT, 2)); wR = np.empty(nR); wT = np.empty(nT); uR = np.empty(nR); uT = np.empty(nT)
         lib().ref_particle_get(self.h, None, _ptr(r), _ptr(t), None, None, _ptr(wR), _ptr(wT), None, None, _ptr(uR), _ptr(uT), None)
         return dict(r=r, t=t, wR=wR, wT=wT, uR=uR, uT=uT)
+
+    def get_d(self):
+        nC, nR, nT, nD = self.counts()
+        d = np.empty(nD); wD = np.empty(nD); uD = np.empty(nD)
+        lib().ref_particle_get(self.h, None, None, None, _ptr(d), None, None, None, _ptr(wD), None, None, None, _ptr(uD))
+        return dict(d=d, wD=wD, uD=uD)
 
     def set(self, r=None, t=None, wR=None, wT=None):
         f = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)

@@ -32,6 +32,7 @@ int pfh_run_s(int op, double arg, int mLR, int mLT, double* r, double* t, double
     v.r = r; v.t = t; v.wR = wR; v.wT = wT; v.uR = uR; v.uT = uT; v.scal = scal;
     v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
     v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1;
+    v.mLD = 0; v.d = v.wD = v.uD = nullptr;
     pf::Rng g;
     g.init(seed, stream, epoch);
     switch (op) {
@@ -80,6 +81,31 @@ void pfh_rng(unsigned long long seed, unsigned long long stream, unsigned long l
     g.init(seed, stream, epoch);
     for (int i = 0; i < n; i++) uni[i] = g.uniform();
     for (int i = 0; i < n; i++) nor[i] = g.normal();
+}
+
+// the defocus dimension (CTF search): d[mLD + 1] (last = the top one), wD / uD [mLD], scal[20]
+int pfh_run_d(int op, double arg, int mLD, double* d, double* wD, double* uD, const float* uDf, double* scal, unsigned long long seed,
+              unsigned long long stream, unsigned long long epoch)
+{
+    const int mw = mLD > 4 ? mLD : 4;
+    std::vector<double> r2(4 * mw), w2(mw), w3(mw), w4(mw), wR(mw, 1.0), wT(mw, 1.0);
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.d = d; v.wD = wD; v.uD = uD; v.scal = scal; v.r2 = r2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
+    v.wR = wR.data(); v.wT = wT.data();
+    v.n = 1; v.p = 0; v.mLR = mw; v.mLT = 1; v.mLD = mLD; v.lane = -1;
+    pf::Rng g;
+    g.init(seed, stream, epoch);
+    switch (op) {
+        case 200: pf::init_D(v, arg, g); break;
+        case 201: pf::perturb_D(v, arg, g); break;
+        case 202: pf::cal_vari_D(v); break;
+        case 203: pf::resample_D(v, g); pf::norm_w(v); break;
+        case 204: pf::balance_D(v); break;
+        case 205: for (int i = 0; i < mLD; ++i) v.UD(i) = (double)uDf[i]; pf::rank1st_D(v); break;
+        default: return -1;
+    }
+    return 0;
 }
 
 // the GSL entry points restated in pf::Rng, by kind as ref_rng_draw of oracle/ref_harness.cpp

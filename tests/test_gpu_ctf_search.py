@@ -113,3 +113,85 @@ def test_insert_with_per_draw_ctf():
             assert np.allclose(got["O"], want["O"], rtol=1e-10, atol=1e-10)
     finally:
         c.close()
+
+
+def test_ctf_search_through_the_device_particle_filter():
+    """SEARCH_TYPE_CTF end to end on the device: thb_expectation with mLD = 9 (initD, the defocus dimension of the fused kernel, perturb /
+    calVari / resample of PAR_D) recovers a 3 % defocus error of the nominal CTF parameters, and thb_reconstruct_insert (one CTF per
+    draw, from the draw's own defocus factor) equals thb_insert_ctf fed with the draws it made.  The operators of the defocus dimension
+    are pinned to the reference's Particle class draw by draw on the CPU (tests/test_pf_host.py::test_defocus_dimension_replay_exact)."""
+    ref = _ref()
+    from oracle import portapi as port
+    N, pf = 64, 2
+    rng = np.random.default_rng(606)
+    vol = synth.padded_ft(synth.phantom(N, 14, seed=3), pf)
+    pixE = port.pixel_list(N, pf, 28.0, 1.0)
+    pixM = port.pixel_list(N, pf, 30.0, 0.0)
+    PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
+    n, mLR, mLT, mLD, phases, mReco = 64, 125, 9, 9, 6, 20
+    volt, Cs, ac, ps, pixelSize = 3.0e5, 2.7e7, 0.1, 0.0, 1.32
+    d_true = 1.03
+    c = capi.Context(0)
+    try:
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        c.set_volume(0, vol)
+        c.reco_alloc(0, N * pf)
+        quat = synth.random_quats(n, rng)
+        tran = rng.normal(scale=1.0, size=(n, 2))
+        dU = rng.uniform(1.5e4, 2.5e4, n); dV = dU + rng.uniform(0, 300, n); th = rng.uniform(0, np.pi, n)
+        attr = np.stack([np.full(n, volt), dU, dV, th, np.full(n, Cs), np.full(n, ac), np.full(n, ps)], axis=1).astype(np.float32)
+
+        def simulate(pix):
+            c.set_expect_pixels(N, pf, pix["iCol"], pix["iRow"])
+            clean = c.project(0, quat)
+            ctf = np.stack([synth.ctf_values(pix["iCol"].astype(float), pix["iRow"].astype(float), N, pixelSize, volt, dU[l] * d_true, dV[l] * d_true,
+                                             th[l], Cs, ac, ps) for l in range(n)]).astype(np.float32)
+            phs = -2 * np.pi * (pix["iCol"][None] * tran[:, :1] / N + pix["iRow"][None] * tran[:, 1:] / N)
+            sig2 = float(np.mean(np.abs(clean * ctf) ** 2)) / 2.0
+            noise = (rng.normal(size=clean.shape) + 1j * rng.normal(size=clean.shape)) * np.sqrt(sig2 / 2)
+            return (ctf * clean * np.exp(1j * phs) + noise).astype(np.complex64), ctf, sig2
+        datM, ctfM, _ = simulate(pixM)
+        datE, ctfE, sig2 = simulate(pixE)
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.upload_stack(capi.STACK_EXPECT, datE, ctfE, np.full((n, PE), -0.5 / sig2, np.float32))
+        c.upload_stack(capi.STACK_INSERT, datM, ctfM)
+        freq = None
+        defP = np.zeros((n, PE), np.float32); ctfK = np.zeros((n, 4), np.float32)
+        for l in range(n):
+            f, dp, k = ref.precal_ctf(volt, dU[l], dV[l], th[l], Cs, N, pixelSize, pixE["iCol"], pixE["iRow"])     # NOMINAL parameters
+            freq = f; defP[l] = dp; ctfK[l] = (k[0], k[1], ps, ac)
+        c.set_frequency(freq)
+        c.upload_stack_defocus(0, defP)
+        prm = capi.PFParams(mLR=mLR, mLT=mLT, transS=2.0, transQ=0.01, perturbFactorL=2.0, perturbFactorS=0.5, minPhase=3, maxPhase=100,
+                            fixedPhases=phases, decreaseFactor=0.95, noDecreaseLimit=1, seed=99, mLD=mLD, ctfRefineS=0.02, perturbFactorSCTF=0.5)
+        k0 = 1e-4
+        q_start = np.stack([synth.acg_cloud(quat[l], k0, 1, rng)[0] for l in range(n)])
+        c.pf_set_image_base(0, 0)
+        c.pf_load(prm, q_start, np.full((n, 3), k0), tran + rng.normal(scale=0.3, size=(n, 2)), np.full((n, 2), 0.5))
+        c.pf_set_ctf(ctfK, attr, pixelSize)
+        c.expectation()
+        D = c.pf_get_d()
+        print(f"\nCTF search: true defocus factor {d_true}; most likely factor after {phases} phases: median {np.median(D['topD']):.4f}, "
+              f"quartiles {np.percentile(D['topD'], 25):.4f} .. {np.percentile(D['topD'], 75):.4f}; sigma of the support median {np.median(D['sD']):.4f}")
+        assert abs(np.median(D["topD"]) - d_true) < 0.01 and np.median(np.abs(D["topD"] - d_true)) < 0.012
+        assert np.allclose(D["wD"].sum(1), 1.0)
+        # M: per-draw CTF through the particle filter == explicit lists
+        c.reconstruct_insert(mReco)
+        a = c.reco_download(0)
+        st = c.pf_get()
+        dR, dT = c.pf_get_draws(mReco); dD = c.pf_get_draws_d(mReco)
+        rows = np.arange(n)[:, None]
+        c.reco_reset(0)
+        c.insert_ctf(np.full(n, 1.0 / mReco, np.float32), st["r"][rows, dR], st["t"][rows, dT], D["d"][rows, dD], attr, pixelSize)
+        b = c.reco_download(0)
+        rel = lambda x, y: np.linalg.norm((x - y).ravel()) / np.linalg.norm(y.ravel())
+        assert a["counter"] == b["counter"] == n * mReco
+        assert rel(a["F"], b["F"]) <= 1e-6 and rel(a["T"], b["T"]) <= 1e-6
+        # ... and differs from the insert with the nominal CTF (the search does change the volume)
+        c.reco_reset(0)
+        c.insert(np.full(n, 1.0 / mReco, np.float32), st["r"][rows, dR], st["t"][rows, dT])
+        nominal = c.reco_download(0)
+        assert rel(a["F"], nominal["F"]) > 1e-3
+    finally:
+        c.close()

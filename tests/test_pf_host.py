@@ -31,6 +31,8 @@ def pfh():
     L.pfh_infer_acg.argtypes = [_i, _p, _p, _p]
     L.pfh_rng.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _p, _p]
     L.pfh_rng_draw.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _i, _d, _d, _p]
+    L.pfh_run_d.restype = _i
+    L.pfh_run_d.argtypes = [_i, _d, _i, _p, _p, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]
     L.pfh_sample_vms.argtypes = [C.c_ulonglong, _d, _i, _p]
     L.pfh_infer_vms.argtypes = [_i, _p, _p, _p]
     L.pfh_pdf_vms.restype = _d
@@ -455,3 +457,40 @@ def test_phase_sequence_replay_exact(pfh, ref):
         P.close()
     print("largest support-point difference over the sequences:", _worst[0], "in", _worst[1], "comparisons;", _worst[2], "rank-deficient clouds skipped")
     assert _worst[2] <= _worst[1] // 20
+
+
+def test_defocus_dimension_replay_exact(pfh, ref):
+    """the CTF search's defocus dimension (initD, perturb / balanceWeight / calVari / calRank1st / resample of PAR_D) against the
+    reference's Particle with the same random numbers: exact to 1e-12 (one-dimensional Gaussian statistics, nothing ill-posed)"""
+    rng = np.random.default_rng(91)
+    for trial in range(4):
+        mLD = (9, 5, 2, 9)[trial]
+        seed = 700 + trial
+        P = ref.Particle(25, 9)
+        q0 = synth.random_quats(1, rng)[0]
+        d = np.zeros(mLD + 1); wD = np.zeros(mLD); uD = np.zeros(mLD); scal = np.zeros(20)
+        pt = lambda a: None if a is None else a.ctypes.data_as(_p)
+        epoch = 0
+        with ref.replay(seed, 0, 0):
+            P.load(25, 9, q0, 3e-4, 3e-4, 3e-4, np.zeros(2), 1.0, 1.0)
+
+            def both(op, arg, fn, uDf=None):
+                nonlocal epoch
+                epoch += 1
+                assert pfh.pfh_run_d(op, arg, mLD, pt(d), pt(wD), pt(uD), pt(uDf), pt(scal), seed, 3, epoch) == 0
+                ref.rng_key(seed, 3, epoch)
+                fn()
+                g = P.get_d()
+                assert np.abs(g["d"] - d[:mLD]).max() <= 1e-12, (op, np.abs(g["d"] - d[:mLD]).max())
+                assert np.allclose(g["wD"] / g["wD"].sum(), wD / wD.sum(), rtol=1e-10), op
+
+            both(200, 0.05, lambda: P.initD(mLD, 0.05))
+            for phase in range(5):
+                uDf = np.exp(-0.5 * ((d[:mLD] - 1.01) / 0.03) ** 2).astype(np.float32) + np.float32(1e-3)
+                both(205, 0.0, lambda: (P.set_u(3, uDf.astype(np.float64)), P.calRank1st(P.PAR_D)), uDf)
+                both(202, 0.0, lambda: P.calVari(P.PAR_D))
+                assert abs(scal[19] - P.variD()) <= 1e-14
+                both(203, 0.0, lambda: P.resample(mLD, P.PAR_D))
+                assert abs(d[mLD] - P.scalars()[14]) <= 1e-14                 # _topD
+                both(201, 0.5, lambda: P.perturb(0.5, P.PAR_D))
+        P.close()

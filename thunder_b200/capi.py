@@ -36,6 +36,7 @@ class PFParams(C.Structure):
         ("decreaseFactor", C.c_double),
         ("noDecreaseLimit", C.c_int),
         ("seed", C.c_uint64),
+        ("mLD", C.c_int), ("ctfRefineS", C.c_double), ("perturbFactorSCTF", C.c_double),
     ]
 
 
@@ -88,6 +89,9 @@ def _sig(lib):
     f = lib.thb_sigma_accumulate; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
+    f = lib.thb_pf_get_draws_d; f.restype = _i; f.argtypes = [_p, _i, _p]
+    f = lib.thb_pf_set_ctf; f.restype = _i; f.argtypes = [_p, _p, _p, C.c_float]
+    f = lib.thb_pf_get_d; f.restype = _i; f.argtypes = [_p, _p, _p, _p]
     f = lib.thb_pf_set_epoch; f.restype = _i; f.argtypes = [_p, C.c_uint64]
     f = lib.thb_pf_trace; f.restype = _i; f.argtypes = [_p, _i]
     f = lib.thb_pf_get_trace; f.restype = _i; f.argtypes = [_p, _i, _p, _p, _p]
@@ -532,6 +536,16 @@ class Context:
     def pf_set_image_base(self, imgBase, streamBase=0):
         self._chk(self.lib.thb_pf_set_image_base(self.h, int(imgBase), int(streamBase)))
 
+    def pf_set_ctf(self, ctfK, ctfAttr, pixelSize):
+        ctfK = _arr(ctfK, np.float32, (self.nPar, 4)); ctfAttr = _arr(ctfAttr, np.float32, (self.nPar, 7))
+        self._chk(self.lib.thb_pf_set_ctf(self.h, _ptr(ctfK), _ptr(ctfAttr), float(pixelSize)))
+
+    def pf_get_d(self):
+        D = self.pf_params.mLD
+        d = np.empty((self.nPar, D + 1)); wD = np.empty((self.nPar, D)); sD = np.empty(self.nPar)
+        self._chk(self.lib.thb_pf_get_d(self.h, _ptr(d), _ptr(wD), _ptr(sD)))
+        return dict(d=d[:, :D], topD=d[:, D], wD=wD, sD=sD)
+
     def pf_set_epoch(self, epoch):
         self._chk(self.lib.thb_pf_set_epoch(self.h, int(epoch)))
 
@@ -554,6 +568,11 @@ class Context:
         r = st[..., :4 * R].reshape(nPhases, 2, n, R, 4); t = st[..., 4 * R:].reshape(nPhases, 2, n, T, 2)
         return dict(rPert=np.ascontiguousarray(r[:, 0]), tPert=np.ascontiguousarray(t[:, 0]), rRes=np.ascontiguousarray(r[:, 1]),
                     tRes=np.ascontiguousarray(t[:, 1]))
+
+    def pf_get_draws_d(self, mReco):
+        dD = np.empty((self.nPar, mReco), np.int32)
+        self._chk(self.lib.thb_pf_get_draws_d(self.h, mReco, _ptr(dD)))
+        return dD
 
     def pf_get_draws(self, mReco):
         dR = np.empty((self.nPar, mReco), np.int32); dT = np.empty((self.nPar, mReco), np.int32)

@@ -378,6 +378,7 @@ int launch_insert(thb_ctx* ctx, const InsertArgs& a, const int* hImgIdx)
         if (a.drawT) s.a.drawT = a.drawT + (size_t)l0 * a.mReco;
         if (a.drawCount) s.a.drawCount = a.drawCount + l0;
         if (a.nd.p) { s.a.nd.p = a.nd.p + (size_t)l0 * a.nd.sP; s.a.ctfAttr = a.ctfAttr + 7 * (size_t)l0; }
+        if (a.drawD) s.a.drawD = a.drawD + (size_t)l0 * a.mReco;
         s.seg = (const Seg*)ctx->segM; s.nSeg = ctx->nSegM; s.order = dOrder; s.prep = prep; s.maxD = maxD;
         s.pf = ctx->pfM; s.rMaxPad = ctx->rMaxPadM; s.zMin = -(n / 2); s.th = th;
         span_begin(ctx, KF_INSERT);

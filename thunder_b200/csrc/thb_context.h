@@ -66,6 +66,16 @@ struct PFState {
     double* vari = nullptr;      // [3][nPar] best variR, variT, and no-decrease counter
     int* drawR = nullptr;        // [nPar][mReco]
     int* drawT = nullptr;
+    int* drawD = nullptr;
+    // CTF search (prm.mLD > 0)
+    double* d = nullptr;         // [(mLD + 1)][nPar]: defocus factors, last row = the most likely one
+    double* wD = nullptr;        // [mLD][nPar]
+    double* uDd = nullptr;       // [mLD][nPar] likelihood weights as doubles (resampling)
+    float* uD = nullptr;         // [nPar][mLD] E-kernel output
+    float* ctfK = nullptr;       // [nPar][4]
+    float* ctfAttr = nullptr;    // [nPar][7]
+    float pixelSize = 0.f;
+    bool ctfSet = false;
     int drawCap = 0;
     uint64_t epoch = 0;          // advances the counter-based RNG stream between calls
     float* traceR = nullptr;     // option "pf_trace": the marginal weights of every phase, [traceCap][nPar][mLR] / [..][mLT]

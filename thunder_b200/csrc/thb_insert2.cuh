@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) insert_prep_kernel(const InsertSlabArgs S
             rc = (float)(-tx) / (float)A.N;      // translate(dst, src, -(tran - offset)(0), ...): RFLOAT arguments
             rr = (float)(-ty) / (float)A.N;
             if (A.nd.p) {     // CTF(ctf, pixelSize, voltage, defocusU * d, defocusV * d, ...): RFLOAT arguments (src/Optimiser.cpp:7173-7187)
-                const double dfac = A.nd.at(l, m, 0);
+                const double dfac = A.nd.at(l, A.drawD ? A.drawD[(size_t)l * A.mReco + m] : m, 0);
                 dUs = (float)((double)A.ctfAttr[7 * l + 1] * dfac);
                 dVs = (float)((double)A.ctfAttr[7 * l + 2] * dfac);
             }

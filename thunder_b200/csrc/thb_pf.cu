@@ -13,12 +13,12 @@
 namespace thb {
 
 struct PFDev {
-    double *r, *t, *wR, *wT, *uR, *uT, *scal, *r2, *t2, *w2, *w3, *w4;
-    const float *uRf, *uTf;
+    double *r, *t, *wR, *wT, *uR, *uT, *scal, *r2, *t2, *w2, *w3, *w4, *dd, *wD, *uD;
+    const float *uRf, *uTf, *uDf;
     unsigned char* active;
     int* nPhase;
     int* activeCount;
-    int nPar, mLR, mLT;
+    int nPar, mLR, mLT, mLD;
     uint64_t seed, streamBase;
 };
 
@@ -35,6 +35,7 @@ __device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
     v.r = d.r; v.t = d.t; v.wR = d.wR; v.wT = d.wT; v.uR = d.uR; v.uT = d.uT; v.scal = d.scal;
     v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2; v.w3 = d.w3; v.w4 = d.w4;
     v.n = d.nPar; v.p = p; v.mLR = d.mLR; v.mLT = d.mLT;
+    v.d = d.dd; v.wD = d.wD; v.uD = d.uD; v.mLD = d.mLD;
     return v;
 }
 
@@ -70,6 +71,7 @@ struct StepArgs {
     int doPost, doPre;
     int phase;              // phase whose likelihoods were just computed (doPost)
     double prePf;           // perturbation factor of the next perturb (doPre)
+    double ctfRefineS, prePfD;   // CTF search: sigma of initD (first perturbation), perturbation factor of PAR_D (later ones)
     double* traceRes;       // optional [nPar][4 mLR + 2 mLT]: the support after the resampling (doPost)
     double* tracePert;      // optional, same shape: the support after the perturbation (doPre)
     double transS, transQ;
@@ -100,10 +102,17 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
     bool cont = true;
     if (a.doPost) {
         pf::set_u_keep_peak(v, d.uRf + (size_t)p * d.mLR, d.uTf + (size_t)p * d.mLT);
+        if (d.mLD > 0)
+            for (int i = 0; i < d.mLD; ++i) v.UD(i) = (double)d.uDf[(size_t)p * d.mLD + i];
         pf::rank1st(v);
         pf::cal_vari(v, g);
         pf::resample_R(v, g);
         pf::resample_T(v, g);
+        if (d.mLD > 0) {     // SEARCH_TYPE_CTF: calRank1st / calVari / resample of PAR_D after those of R and T (src/Optimiser.cpp:1483-1488)
+            pf::rank1st_D(v);
+            pf::cal_vari_D(v);
+            pf::resample_D(v, g);
+        }
         pf::norm_w(v);
         if (a.traceRes) pf_trace_store(v, a.traceRes);
         d.nPhase[p] = a.phase + 1;
@@ -122,13 +131,17 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
     if (cont && a.doPre) {
         pf::perturb_R(v, a.prePf, g);
         pf::perturb_T(v, a.prePf, a.transS, a.transQ, g);
+        if (d.mLD > 0) {     // src/Optimiser.cpp:1193-1215
+            if (a.phase < 0) pf::init_D(v, a.ctfRefineS, g);
+            else pf::perturb_D(v, a.prePfD, g);
+        }
         if (a.tracePert) pf_trace_store(v, a.tracePert);
         if ((threadIdx.x & 31) == 0) atomicAdd(d.activeCount, 1);
     }
 }
 
 // Particle::rand(cls, quat, tran, d) x mReco: independent uniform draws of support indices
-__global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, int* drawR, int* drawT, float* w)
+__global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, int* drawR, int* drawT, int* drawD, float* w)
 {
     const int p = pf_particle();
     if (p >= d.nPar) return;
@@ -139,7 +152,8 @@ __global__ void pf_draw_kernel(PFDev d, uint64_t epoch, int mReco, int parGra, i
         (void)g.uniform_int(1);                                   // class
         drawR[(size_t)p * mReco + m] = (int)g.uniform_int((uint32_t)d.mLR);
         drawT[(size_t)p * mReco + m] = (int)g.uniform_int((uint32_t)d.mLT);
-        (void)g.uniform_int(1);                                   // defocus
+        const int iD = (int)g.uniform_int((uint32_t)(d.mLD > 0 ? d.mLD : 1));   // defocus
+        if (drawD) drawD[(size_t)p * mReco + m] = iD;
     }
     const double ww = parGra ? pf::compress_R(v) : 1.0;
     w[p] = (float)ww / (float)mReco;                              // RFLOAT w; w /= mReco
@@ -170,7 +184,8 @@ void pf_free(thb_ctx* ctx)
     PFState& s = ctx->pf_;
     cudaFree(s.r); cudaFree(s.t); cudaFree(s.wR); cudaFree(s.wT); cudaFree(s.scal);
     cudaFree(s.uR); cudaFree(s.uT); cudaFree(s.uC); cudaFree(s.base); cudaFree(s.active); cudaFree(s.nPhase);
-    cudaFree(s.vari); cudaFree(s.drawR); cudaFree(s.drawT);
+    cudaFree(s.vari); cudaFree(s.drawR); cudaFree(s.drawT); cudaFree(s.drawD);
+    cudaFree(s.d); cudaFree(s.wD); cudaFree(s.uDd); cudaFree(s.uD); cudaFree(s.ctfK); cudaFree(s.ctfAttr);
     cudaFree(s.dbl); cudaFree(s.traceR); cudaFree(s.traceT); cudaFree(s.traceSt); cudaFree(s.traceB);
     s = PFState();
 }
@@ -191,7 +206,8 @@ static PFDev dev_view(thb_ctx* ctx)
     d.w2 = q; q += n * mw;
     d.w3 = q; q += n * mw;
     d.w4 = q;
-    d.uRf = s.uR; d.uTf = s.uT;
+    d.uRf = s.uR; d.uTf = s.uT; d.uDf = s.uD;
+    d.dd = s.d; d.wD = s.wD; d.uD = s.uDd; d.mLD = s.prm.mLD;
     d.active = s.active; d.nPhase = s.nPhase; d.activeCount = (int*)s.vari;
     d.nPar = s.nPar; d.mLR = s.prm.mLR; d.mLT = s.prm.mLT;
     d.seed = s.prm.seed; d.streamBase = s.streamBase;
@@ -201,7 +217,7 @@ static PFDev dev_view(thb_ctx* ctx)
 static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
 {
     PFState& s = ctx->pf_;
-    if (s.nPar == nPar && s.prm.mLR == p.mLR && s.prm.mLT == p.mLT && s.r) {
+    if (s.nPar == nPar && s.prm.mLR == p.mLR && s.prm.mLT == p.mLT && s.prm.mLD == p.mLD && s.r) {
         s.prm = p;
         return THB_OK;
     }
@@ -228,6 +244,17 @@ static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
     THB_CUDA(ctx, cudaMalloc(&s.nPhase, sizeof(int) * n));
     THB_CUDA(ctx, cudaMalloc(&s.vari, sizeof(double) * 4));
     THB_CUDA(ctx, cudaMemset(s.scal, 0, sizeof(double) * n * pf::S_COUNT));
+    if (p.mLD > 0) {
+        THB_CUDA(ctx, cudaMalloc(&s.d, sizeof(double) * n * (p.mLD + 1)));
+        THB_CUDA(ctx, cudaMalloc(&s.wD, sizeof(double) * n * p.mLD));
+        THB_CUDA(ctx, cudaMalloc(&s.uDd, sizeof(double) * n * p.mLD));
+        THB_CUDA(ctx, cudaMalloc(&s.uD, sizeof(float) * n * p.mLD));
+        THB_CUDA(ctx, cudaMalloc(&s.ctfK, sizeof(float) * n * 4));
+        THB_CUDA(ctx, cudaMalloc(&s.ctfAttr, sizeof(float) * n * 7));
+        THB_CUDA(ctx, cudaMemset(s.d, 0, sizeof(double) * n * (p.mLD + 1)));
+        THB_CUDA(ctx, cudaMemset(s.wD, 0, sizeof(double) * n * p.mLD));
+        THB_CUDA(ctx, cudaMemset(s.uDd, 0, sizeof(double) * n * p.mLD));
+    }
     s.nPar = nPar;
     s.prm = p;
     return THB_OK;
@@ -263,11 +290,13 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
     if (!ctx) return THB_E_ARG;
     if (nPar <= 0 || !p || !quat || !k123 || !tran || !s01 || p->mLR < 2 || p->mLT < 2)
         return set_error(ctx, THB_E_ARG, "pf_load: bad arguments");
+    if (p->mLD < 0 || p->mLD > (p->mLR > p->mLT ? p->mLR : p->mLT)) return set_error(ctx, THB_E_ARG, "pf_load: mLD must be in [0, max(mLR, mLT)]");
     if (ctx->mode2D) return set_error(ctx, THB_E_STATE, "pf_load: the device particle filter is MODE_3D only; drive MODE_2D through thb_expect_local / thb_expect_scan");
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = pf_alloc(ctx, nPar, *p);
     if (rc) return rc;
     PFState& s = ctx->pf_;
+    s.ctfSet = false;                 // the CTF constants belong to the particles of one load
     const size_t n = nPar;
     double* din = (double*)scratch(ctx, 0, sizeof(double) * n * 11);
     if (!din) return THB_E_CUDA;
@@ -363,6 +392,14 @@ static int expect_args_from_pf(thb_ctx* ctx, ExpectArgs& a)
     a.wR = View3{s.wR, 1, n, 0};
     a.wT = View3{s.wT, 1, n, 0};
     a.uR = s.uR; a.uT = s.uT; a.uC = s.uC; a.base = s.base; a.logL = nullptr;
+    if (s.prm.mLD > 0) {
+        if (!s.ctfSet) return set_error(ctx, THB_E_STATE, "expectation: CTF search needs thb_pf_set_ctf");
+        if (!ctx->freqE || !ctx->stackE.def) return set_error(ctx, THB_E_STATE, "expectation: CTF search needs thb_set_frequency and thb_upload_stack_defocus");
+        a.nD = s.prm.mLD; a.defP = ctx->stackE.def; a.freq = ctx->freqE; a.ctfK = s.ctfK;
+        a.dpar = View3{s.d, 1, n, 0};
+        a.wD = View3{s.wD, 1, n, 0};
+        a.uD = s.uD;
+    }
     return THB_OK;
 }
 
@@ -384,6 +421,7 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
     sa.transS = p.transS; sa.transQ = p.transQ;
     sa.minPhase = p.minPhase; sa.maxPhase = p.maxPhase; sa.fixedPhases = p.fixedPhases;
     sa.noDecreaseLimit = p.noDecreaseLimit; sa.decreaseFactor = p.decreaseFactor;
+    sa.ctfRefineS = p.ctfRefineS; sa.prePfD = p.perturbFactorSCTF;
 
     s.traceN = 0;
     if (s.traceWant > 0 && s.traceCap != s.traceWant) {
@@ -458,10 +496,11 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = s.nPar;
     if (s.drawCap < mReco) {
-        cudaFree(s.drawR); cudaFree(s.drawT);
-        s.drawR = s.drawT = nullptr;
+        cudaFree(s.drawR); cudaFree(s.drawT); cudaFree(s.drawD);
+        s.drawR = s.drawT = s.drawD = nullptr;
         THB_CUDA(ctx, cudaMalloc(&s.drawR, sizeof(int) * n * mReco));
         THB_CUDA(ctx, cudaMalloc(&s.drawT, sizeof(int) * n * mReco));
+        THB_CUDA(ctx, cudaMalloc(&s.drawD, sizeof(int) * n * mReco));
         s.drawCap = mReco;
     }
     float* dw = (float*)scratch(ctx, 0, sizeof(float) * n + sizeof(double) * 2 * n + 64);
@@ -470,7 +509,7 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     if (offS) THB_CUDA(ctx, cudaMemcpyAsync(doff, offS, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     s.epoch += 1;
     span_begin(ctx, KF_PF);
-    pf_draw_kernel<<<nblk(s.nPar), PF_BLOCK, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, mReco, parGra, s.drawR, s.drawT, dw);
+    pf_draw_kernel<<<nblk(s.nPar), PF_BLOCK, 0, ctx->stream>>>(dev_view(ctx), s.epoch << 20, mReco, parGra, s.drawR, s.drawT, s.drawD, dw);
     span_end(ctx);
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
@@ -486,9 +525,53 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     a.nr = View3{s.r, 1, nn, nn * s.prm.mLR};
     a.nt = View3{s.t, 1, nn, nn * s.prm.mLT};
     a.drawR = s.drawR; a.drawT = s.drawT;
+    if (s.prm.mLD > 0) {     // cSearch: the CTF of every draw from its own defocus factor (src/Optimiser.cpp:7171-7215)
+        if (!s.ctfSet) return set_error(ctx, THB_E_STATE, "reconstruct_insert: CTF search needs thb_pf_set_ctf");
+        a.nd = View3{s.d, 1, nn, 0};
+        a.drawD = s.drawD;
+        a.ctfAttr = s.ctfAttr;
+        a.pixelSize = s.pixelSize;
+    }
     int rc = launch_insert(ctx, a, nullptr);
     if (rc) return rc;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_pf_set_ctf(thb_ctx* ctx, const float* ctfK, const float* ctfAttr, float pixelSize)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.r || s.prm.mLD <= 0) return set_error(ctx, THB_E_STATE, "pf_set_ctf: load particles with mLD > 0 first");
+    if (!ctfK || !ctfAttr || !(pixelSize > 0)) return set_error(ctx, THB_E_ARG, "pf_set_ctf: NULL arrays / pixelSize <= 0");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaMemcpyAsync(s.ctfK, ctfK, sizeof(float) * 4 * (size_t)s.nPar, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(s.ctfAttr, ctfAttr, sizeof(float) * 7 * (size_t)s.nPar, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s.pixelSize = pixelSize;
+    s.ctfSet = true;
+    return THB_OK;
+}
+
+int thb_pf_get_d(thb_ctx* ctx, double* d, double* wD, double* sD)
+{
+    if (!ctx) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.d) return set_error(ctx, THB_E_STATE, "pf_get_d: no defocus dimension (mLD == 0)");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = s.nPar;
+    const int D = s.prm.mLD;
+    std::vector<double> tmp(n * (D + 1));
+    if (d) {
+        THB_CUDA(ctx, cudaMemcpy(tmp.data(), s.d, sizeof(double) * n * (D + 1), cudaMemcpyDeviceToHost));
+        to_aos(tmp.data(), d, n, D + 1, 1);
+    }
+    if (wD) {
+        THB_CUDA(ctx, cudaMemcpy(tmp.data(), s.wD, sizeof(double) * n * D, cudaMemcpyDeviceToHost));
+        to_aos(tmp.data(), wD, n, D, 1);
+    }
+    if (sD) THB_CUDA(ctx, cudaMemcpy(sD, s.scal + (size_t)pf::S_SD * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return THB_OK;
 }
 
@@ -537,6 +620,15 @@ int thb_pf_get_draws(thb_ctx* ctx, int mReco, int* drawR, int* drawT)
     if (!s.drawR || mReco > s.drawCap) return set_error(ctx, THB_E_STATE, "pf_get_draws: no draws of that size");
     THB_CUDA(ctx, cudaMemcpy(drawR, s.drawR, sizeof(int) * (size_t)s.nPar * mReco, cudaMemcpyDeviceToHost));
     THB_CUDA(ctx, cudaMemcpy(drawT, s.drawT, sizeof(int) * (size_t)s.nPar * mReco, cudaMemcpyDeviceToHost));
+    return THB_OK;
+}
+
+int thb_pf_get_draws_d(thb_ctx* ctx, int mReco, int* drawD)
+{
+    if (!ctx || !drawD) return THB_E_ARG;
+    PFState& s = ctx->pf_;
+    if (!s.drawD || mReco > s.drawCap) return set_error(ctx, THB_E_STATE, "pf_get_draws_d: no draws of that size");
+    THB_CUDA(ctx, cudaMemcpy(drawD, s.drawD, sizeof(int) * (size_t)s.nPar * mReco, cudaMemcpyDeviceToHost));
     return THB_OK;
 }
 

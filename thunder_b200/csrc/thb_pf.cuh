@@ -36,7 +36,7 @@ namespace thb {
 namespace pf {
 
 enum { S_K1 = 0, S_K2, S_K3, S_S0, S_S1, S_RHO, S_TOPR, S_TOPT = 10, S_SCORE = 12, S_NPHASE = 13, S_VARIR = 14, S_VARIT = 15,
-       S_PEAKR = 16, S_NODEC = 17, S_VARID = 18, S_SPARE = 19, S_COUNT = 20 };
+       S_PEAKR = 16, S_NODEC = 17, S_VARID = 18, S_SD = 19 /* sigma of the defocus factors (_s) */, S_SPARE = 19, S_COUNT = 20 };
 
 // ------------------------------------------------------------------------------------------------
 struct Rng {
@@ -126,6 +126,8 @@ struct View {
     double* r; double* t; double* wR; double* wT; double* uR; double* uT; double* scal;
     double* r2; double* t2; double* w2;      // resampling scratch, same layout as r / t / wR
     double* w3; double* w4;                  // two more rows of max(mLR, mLT) (the shuffle's scatter)
+    double* d; double* wD; double* uD;       // CTF search: mLD defocus factors (+ the top one in row mLD of d), null when mLD == 0
+    int mLD;
     long long n;   // stride between consecutive samples/components = number of particles
     long long p;   // particle index
     int mLR, mLT;
@@ -142,6 +144,9 @@ struct View {
     THB_HD double& UR(int i) const { return uR[(long long)i * n + p]; }
     THB_HD double& UT(int i) const { return uT[(long long)i * n + p]; }
     THB_HD double& S(int k) const { return scal[(long long)k * n + p]; }
+    THB_HD double& D(int i) const { return d[(long long)i * n + p]; }          // i == mLD: the most likely one (_topD)
+    THB_HD double& WD(int i) const { return wD[(long long)i * n + p]; }
+    THB_HD double& UD(int i) const { return uD[(long long)i * n + p]; }
 };
 
 THB_HD void quat_mul(double d[4], const double a[4], const double b[4])
@@ -354,6 +359,11 @@ THB_HD void norm_w(const View& v)
     s = 0.0;
     for (int i = 0; i < v.mLT; ++i) s += v.WT(i);
     for (int i = 0; i < v.mLT; ++i) v.WT(i) /= s;
+    if (v.mLD > 0) {
+        s = 0.0;
+        for (int i = 0; i < v.mLD; ++i) s += v.WD(i);
+        for (int i = 0; i < v.mLD; ++i) v.WD(i) /= s;
+    }
 }
 
 // balanceWeight(PAR_R): wR = 1 / pdfACG(r, A), A = inferACG(r); pdfACG = det^-1/2 (x' A^-1 x)^-2
@@ -640,12 +650,113 @@ THB_HD void load(const View& v, const double q[4], double k1, double k2, double 
     v.S(S_SPARE) = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------ the defocus dimension (CTF search)
+// gsl_stats_mean / gsl_stats_sd_m in GSL's recurrence form (statistics/mean_source.c, variance_source.c)
+THB_HD double mean_D(const View& v)
+{
+    double mean = 0.0;
+    for (int i = 0; i < v.mLD; ++i) mean += (v.D(i) - mean) / (i + 1);
+    return mean;
+}
+THB_HD double sd_m_D(const View& v, double mean)
+{
+    double variance = 0.0;
+    for (int i = 0; i < v.mLD; ++i) {
+        const double delta = v.D(i) - mean;
+        variance += (delta * delta - variance) / (i + 1);
+    }
+    return sqrt(variance * ((double)v.mLD / (double)(v.mLD - 1)));
+}
+
+THB_HD void balance_D(const View& v);
+
+// Particle::initD (src/Particle.cpp:280-310, PARTICLE_DEFOCUS_INIT_GAUSSIAN, PARTICLE_BALANCE_WEIGHT_D)
+THB_HD void init_D(const View& v, double sD, Rng& g)
+{
+    for (int i = 0; i < v.mLD; ++i) v.D(i) = 1.0 + g.gaussian(sD);
+    for (int i = 0; i < v.mLD; ++i) { v.WD(i) = 1.0 / v.mLD; v.UD(i) = 1.0 / v.mLD; }
+    balance_D(v);
+}
+
+// balanceWeight(PAR_D) (src/Particle.cpp:2374-2409): wD = 1 / gaussian_pdf(d - mean, sd), then normW
+THB_HD void balance_D(const View& v)
+{
+    const double m = mean_D(v);
+    const double s = v.mLD == 1 ? 0.0 : sd_m_D(v, m);
+    if (s == 0) {
+        for (int i = 0; i < v.mLD; ++i) v.WD(i) = 1.0;
+    } else {
+        for (int i = 0; i < v.mLD; ++i) {
+            const double u = (v.D(i) - m) / fabs(s);
+            const double pdf = (1.0 / (sqrt(2.0 * 3.14159265358979323846) * fabs(s))) * exp(-u * u / 2.0);   // gsl_ran_gaussian_pdf
+            v.WD(i) = 1.0 / pdf;
+        }
+    }
+    norm_w(v);
+}
+
+// perturb(pf, PAR_D) (src/Particle.cpp:1278-1288)
+THB_HD void perturb_D(const View& v, double pfac, Rng& g)
+{
+    const double s = v.S(S_SD);
+    for (int i = 0; i < v.mLD; ++i) v.D(i) += g.gaussian(s) * pfac;
+    balance_D(v);
+}
+
+// calVari(PAR_D) (src/Particle.cpp:1120-1141): gsl_stats_sd
+THB_HD void cal_vari_D(const View& v) { v.S(S_SD) = v.mLD == 1 ? 0.0 : sd_m_D(v, mean_D(v)); }
+
+// calRank1st(PAR_D) + resample(mLD, PAR_D) (src/Particle.cpp:1430-1475); W2 / W3 / W4 are long enough (max(mLR, mLT) >= mLD is
+// required by the caller)
+THB_HD void resample_D(const View& v, Rng& g)
+{
+    const int n = v.mLD;
+    for (int i = 0; i < n; ++i) v.W2(i) = (double)i;
+    for (int i = n - 1; i > 0; --i) {
+        const int j = (int)g.uniform_int((uint32_t)(i + 1));
+        const double x = v.W2(i); v.W2(i) = v.W2(j); v.W2(j) = x;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int d = (int)v.W2(i);
+        v.R2(d, 0) = v.D(i);          // the rotation scratch doubles as the defocus scratch
+        v.W3(d) = v.WD(i);
+        v.W4(d) = v.UD(i);
+    }
+    for (int i = 0; i < n; ++i) { v.D(i) = v.R2(i, 0); v.WD(i) = v.W3(i); v.UD(i) = v.W4(i); }
+    int top = 0;
+    for (int i = 1; i < n; ++i)
+        if (v.UD(i) > v.UD(top)) top = i;
+    v.D(n) = v.D(top);                // _topD
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) { v.WD(i) *= v.UD(i); s += v.WD(i); }
+    double cum = 0.0;
+    for (int i = 0; i < n; ++i) { v.WD(i) /= s; cum += v.WD(i); v.W2(i) = cum; }
+    const double last = v.W2(n - 1);
+    const double u0 = g.flat(0.0, 1.0 / n);
+    int i = 0;
+    for (int j = 0; j < n; ++j) {
+        const double uj = u0 + j * 1.0 / n;
+        while (i < n - 1 && uj > v.W2(i) / last) ++i;
+        v.R2(j, 0) = v.D(i);
+        v.W3(j) = 1.0 / v.UD(i);
+    }
+    for (int j = 0; j < n; ++j) { v.D(j) = v.R2(j, 0); v.WD(j) = v.W3(j); }
+}
+
+THB_HD void rank1st_D(const View& v)
+{
+    int top = 0;
+    for (int i = 1; i < v.mLD; ++i)
+        if (v.UD(i) > v.UD(top)) top = i;
+    v.D(v.mLD) = v.D(top);
+}
+
 // the stop rule of the phase loop (src/Optimiser.cpp:1510-1615, OPTIMISER_COMPRESS_CRITERIA);
 // returns true when the particle is finished.  variD is the constant defocus sigma (0 here).
 THB_HD bool stop_rule(const View& v, int phase, int minPhase, double decreaseFactor, int noDecreaseLimit)
 {
     if (phase < minPhase) return false;
-    const double r = vari_R(v), t = vari_T(v), d = 0.0;
+    const double r = vari_R(v), t = vari_T(v), d = v.mLD > 0 ? v.S(S_SD) : 0.0;     // variD() = _s
     if (r < v.S(S_VARIR) * decreaseFactor || t < v.S(S_VARIT) * decreaseFactor || d < v.S(S_VARID) * decreaseFactor)
         v.S(S_NODEC) = 0.0;
     else

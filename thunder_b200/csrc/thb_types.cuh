@@ -107,6 +107,7 @@ struct InsertArgs {
     const int* drawCount;     // optional [nImg]: only the first drawCount[l] <= mReco draws of image l are inserted
     // ---- CTF search (cSearch of InsertFT, src/Optimiser.cpp:7171-7215): the CTF of every draw from its own defocus factor
     View3 nd;                 // [nImg][mReco][1] defocus factors, p == null: off
+    const int* drawD;         // optional [nImg][mReco] indices into the sample axis of nd (particle filter draws)
     const float* ctfAttr;     // [nImg][7] voltage, defocusU, defocusV, defocusTheta, Cs, amplitudeContrast, phaseShift
     float pixelSize;
 };
