@@ -211,6 +211,11 @@ int thb_expect_local_ctf(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int 
 int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, const double* tran,
                     const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base,
                     float* logL);
+/* the same for the images [imgBase, imgBase + nImg) of the E stack (a batch of a larger resident stack); output rows are
+ * relative to imgBase.  The whole rotation set goes through ONE launch per chunk of images (passes of 128 rotations inside
+ * the kernel, baseline over the whole table): no merging of partial results on the host. */
+int thb_expect_scan_range(thb_ctx* ctx, int slot, int imgBase, int nImg, int nR, int nT, const double* quat, const double* tran,
+                          const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base, float* logL);
 
 /* ---------------------------------------------------------------- a11-a14: fused M kernel */
 int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad);   /* accumulators F,T: (vdimPad/2+1) x vdimPad^2 */

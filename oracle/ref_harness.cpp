@@ -1249,6 +1249,120 @@ void ref_expect_ctf(void* projH, const float* datP, const float* sigRcpP, const 
     TSFFTW_free(priRotP); TSFFTW_free(priAllP); TSFFTW_free(traP); TSFFTW_free(ctfP);
 }
 
+// ------------------------------------------------------------------------------------------
+// Driver loop 3: the initial phase of the global search / 2D classification (reference src/Optimiser.cpp:756-914): one shared set
+// of nR rotations x nT translations against ALL images, class by class - projection of one template per (class, rotation),
+// product with every translation's phase ramp, logDataVSPrior_m_n over the pixel-major packed arrays, running-baseline weights
+// under per-image locks; OpenMP over rotations, as the reference.
+//   projH[nK]            Projector handles (MODE_2D: ref_projector2d_create, rot[nR][2] = (cos, sin); MODE_3D: rot[nR][4])
+//   datPM, ctfPM, sigPM  pixel-major [nPxl][nImg]
+//   out: wC[nImg][nK], wR[nK][nImg][nR], wT[nK][nImg][nT], baseLine[nImg]
+// ------------------------------------------------------------------------------------------
+void ref_scan(void** projH, int nK, int mode2D, const float* datPM, const float* ctfPM, const float* sigPM, int nImg, int nPxl, int N,
+              const int* iCol, const int* iRow, const double* rot, int nR, const double* tran, int nT, const double* pR,
+              const double* pT, int simd, int nThread, float* wCout, float* wRout, float* wTout, float* baseOut)
+{
+    if (nThread <= 0) nThread = omp_get_max_threads();
+    Complex* traP = (Complex*)TSFFTW_malloc((size_t)nT * nPxl * sizeof(Complex));
+    #pragma omp parallel for schedule(dynamic) num_threads(nThread)
+    for (int m = 0; m < nT; m++) translate(traP + (size_t)m * nPxl, tran[2 * m], tran[2 * m + 1], N, N, iCol, iRow, nPxl, 1);
+    Complex* poolPriRotP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    Complex* poolPriAllP = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    RFLOAT* poolSIMDResult = (RFLOAT*)TSFFTW_malloc((size_t)nImg * nThread * sizeof(RFLOAT));
+    std::vector<omp_lock_t> mtx(nImg);
+    for (int l = 0; l < nImg; l++) omp_init_lock(&mtx[l]);
+    std::vector<RFLOAT> baseLine(nImg, GSL_NAN);
+    memset(wCout, 0, sizeof(float) * (size_t)nImg * nK);
+    memset(wRout, 0, sizeof(float) * (size_t)nK * nImg * nR);
+    memset(wTout, 0, sizeof(float) * (size_t)nK * nImg * nT);
+
+    for (int t = 0; t < nK; t++)
+    {
+        RefProjector* P = (RefProjector*)projH[t];
+        #pragma omp parallel for schedule(dynamic) num_threads(nThread)
+        for (int m = 0; m < nR; m++)
+        {
+            Complex* priRotP = poolPriRotP + (size_t)nPxl * omp_get_thread_num();
+            Complex* priAllP = poolPriAllP + (size_t)nPxl * omp_get_thread_num();
+            RFLOAT* SIMDResult = poolSIMDResult + (size_t)omp_get_thread_num() * nImg;
+            if (mode2D)
+            {
+                dmat22 rot2D;
+                rotate2D(rot2D, dvec2(rot[2 * m], rot[2 * m + 1]));
+                P->proj.project(priRotP, rot2D, iCol, iRow, nPxl, 1);
+            }
+            else
+            {
+                dmat33 rot3D;
+                rotate3D(rot3D, dvec4(rot[4 * m], rot[4 * m + 1], rot[4 * m + 2], rot[4 * m + 3]));
+                P->proj.project(priRotP, rot3D, iCol, iRow, nPxl, 1);
+            }
+            for (int n = 0; n < nT; n++)
+            {
+                for (int i = 0; i < nPxl; i++) priAllP[i] = traP[(size_t)nPxl * n + i] * priRotP[i];
+                memset(SIMDResult, '\0', nImg * sizeof(RFLOAT));
+                RFLOAT* dvp = simd ? logDataVSPrior_m_n_huabin_SIMD256((Complex*)datPM, priAllP, (RFLOAT*)ctfPM, (RFLOAT*)sigPM, nImg, nPxl, SIMDResult)
+                                   : logDataVSPrior_m_n_huabin((Complex*)datPM, priAllP, (RFLOAT*)ctfPM, (RFLOAT*)sigPM, nImg, nPxl, SIMDResult);
+                for (int l = 0; l < nImg; l++)
+                {
+                    omp_set_lock(&mtx[l]);
+                    if (TSGSL_isnan(baseLine[l]))
+                        baseLine[l] = dvp[l];
+                    else if (dvp[l] > baseLine[l])
+                    {
+                        RFLOAT offset = dvp[l] - baseLine[l];
+                        RFLOAT nf = exp(-offset);
+                        for (int td = 0; td < nK; td++)
+                        {
+                            wCout[(size_t)l * nK + td] *= nf;
+                            for (int a = 0; a < nR; a++) wRout[((size_t)td * nImg + l) * nR + a] *= nf;
+                            for (int a = 0; a < nT; a++) wTout[((size_t)td * nImg + l) * nT + a] *= nf;
+                        }
+                        baseLine[l] += offset;
+                    }
+                    RFLOAT w = exp(dvp[l] - baseLine[l]);
+                    wCout[(size_t)l * nK + t] += w * (pR[m] * pT[n]);
+                    wRout[((size_t)t * nImg + l) * nR + m] += w * pT[n];
+                    wTout[((size_t)t * nImg + l) * nT + n] += w * pR[m];
+                    omp_unset_lock(&mtx[l]);
+                }
+            }
+        }
+    }
+    for (int l = 0; l < nImg; l++) { baseOut[l] = baseLine[l]; omp_destroy_lock(&mtx[l]); }
+    TSFFTW_free(traP); TSFFTW_free(poolPriRotP); TSFFTW_free(poolPriAllP); TSFFTW_free(poolSIMDResult);
+}
+
+// the insert loop of reconstructRef in MODE_2D with several classes (src/Optimiser.cpp:7036-7148): mReco draws per image, each into
+// the Reconstructor of its class; OpenMP over images as the reference
+void ref_insert_loop_2d(void** recoH, int nImg, const float* datP, const float* ctfP, const float* wImg, const double* offS,
+                        const int* nc, const double* nr, const double* nt, const int* iCol, const int* iRow, int nPxl, int N,
+                        int mReco, int nThread)
+{
+    if (nThread <= 0) nThread = omp_get_max_threads();
+    Complex* pool = (Complex*)TSFFTW_malloc((size_t)nPxl * nThread * sizeof(Complex));
+    #pragma omp parallel for num_threads(nThread)
+    for (int l = 0; l < nImg; l++)
+    {
+        Complex* transImgP = pool + (size_t)nPxl * omp_get_thread_num();
+        const Complex* orignImgP = (const Complex*)datP + (size_t)nPxl * l;
+        dvec2 offset(offS ? offS[2 * l] : 0, offS ? offS[2 * l + 1] : 0);
+        for (int m = 0; m < mReco; m++)
+        {
+            const size_t o = (size_t)l * mReco + m;
+            dvec2 tran(nt[2 * o], nt[2 * o + 1]);
+            dmat22 rot2D;
+            rotate2D(rot2D, dvec2(nr[2 * o], nr[2 * o + 1]));
+            translate(transImgP, orignImgP, -(tran - offset)(0), -(tran - offset)(1), N, N, iCol, iRow, nPxl, 1);
+            RefReco* R = (RefReco*)recoH[nc[o]];
+            R->reco.insertP(transImgP, ctfP + (size_t)nPxl * l, rot2D, wImg[l], NULL);
+            dvec2 dir = -rot2D * (tran - offset);
+            R->reco.insertDir(dir);
+        }
+    }
+    TSFFTW_free(pool);
+}
+
 void ref_insert_loop_ctf(void* recoH, int nImg, const float* datP, const float* wImg, const double* offS, const double* nr,
                          const double* nt, const double* nd, const float* ctfAttr, float pixelSize, const int* iCol,
                          const int* iRow, int nPxl, int N, int mReco, int nThread)

@@ -131,6 +131,8 @@ def lib():
         L.ref_precal_ctf.argtypes = [_f] * 5 + [_i, _f, _p, _p, _i, _p, _p, _p]
         L.ref_expect_ctf.argtypes = [_p] * 5 + [_f] * 4 + [_p] * 6 + [_d, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 6
         L.ref_insert_loop_ctf.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i]
+        L.ref_scan.argtypes = [_p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]
+        L.ref_insert_loop_2d.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i]
         L.ref_rng_replay.argtypes = [_i]
         L.ref_rng_key.argtypes = [C.c_ulonglong] * 3
         L.ref_rng_replay_loop.argtypes = [C.c_ulonglong] * 3
@@ -508,6 +510,34 @@ def expect_ctf(proj, dat, sigRcp, defP, freq, K1, K2, phaseShift, ac, quat, tran
                          _ptr(wR), _ptr(wT), _ptr(wD), float(wC), _ptr(iCol), _ptr(iRow), P, N, nR, nT, nD, simd, _ptr(oC), _ptr(oR), _ptr(oT),
                          _ptr(oD), _ptr(base), _ptr(logL))
     return dict(uC=oC[0], uR=oR, uT=oT, uD=oD, base=base[0], logL=logL)
+
+
+def scan(projs, mode2D, datP, ctfP, sigRcpP, iCol, iRow, N, rot, tran, pR, pT, simd=1, nThread=1):
+    """the initial phase of the global search / 2D classification (ref_scan in ref_harness.cpp); datP / ctfP / sigRcpP image-major
+    [nImg][nPxl] (transposed to the reference's pixel-major layout here)"""
+    datP = np.ascontiguousarray(datP, np.complex64)
+    nImg, P = datP.shape
+    dPM = np.ascontiguousarray(datP.T); cPM = np.ascontiguousarray(np.asarray(ctfP, np.float32).T); sPM = np.ascontiguousarray(np.asarray(sigRcpP, np.float32).T)
+    rot = np.ascontiguousarray(rot, np.float64); tran = np.ascontiguousarray(tran, np.float64)
+    pR = np.ascontiguousarray(pR, np.float64); pT = np.ascontiguousarray(pT, np.float64)
+    nK, nR, nT = len(projs), len(rot), len(tran)
+    hs = (_p * nK)(*[p.h for p in projs])
+    wC = np.zeros((nImg, nK), np.float32); wR = np.zeros((nK, nImg, nR), np.float32); wT = np.zeros((nK, nImg, nT), np.float32)
+    base = np.zeros(nImg, np.float32)
+    lib().ref_scan(hs, nK, int(mode2D), _ptr(dPM), _ptr(cPM), _ptr(sPM), nImg, P, N, _ptr(iCol), _ptr(iRow), _ptr(rot), nR, _ptr(tran), nT,
+                   _ptr(pR), _ptr(pT), simd, nThread, _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base))
+    return dict(wC=wC, wR=wR, wT=wT, base=base)
+
+
+def insert_loop_2d(recos, dat, ctf_, w, offS, nc, nr, nt, iCol, iRow, N, nThread=1):
+    dat = np.ascontiguousarray(dat, np.complex64)
+    nImg, P = dat.shape
+    ctf_ = np.ascontiguousarray(ctf_, np.float32); w = np.ascontiguousarray(w, np.float32)
+    nc = np.ascontiguousarray(nc, np.int32); nr = np.ascontiguousarray(nr, np.float64); nt = np.ascontiguousarray(nt, np.float64)
+    offS = None if offS is None else np.ascontiguousarray(offS, np.float64)
+    hs = (_p * len(recos))(*[r.h for r in recos])
+    lib().ref_insert_loop_2d(hs, nImg, _ptr(dat), _ptr(ctf_), _ptr(w), _ptr(offS), _ptr(nc), _ptr(nr), _ptr(nt), _ptr(iCol), _ptr(iRow), P, N,
+                             nc.shape[1], nThread)
 
 
 class replay:

@@ -208,6 +208,41 @@ def test_expect_scan_matches_local(ctx, problem):
         assert np.allclose(out["wT"][l], (w * pR[:, None]).sum(0), rtol=1e-4, atol=1e-30)
 
 
+def test_expect_scan_large_rotation_set_against_the_reference_loop(ctx, problem):
+    """the global-search shape at a size that takes several passes inside the kernel (300 rotations > 128 per pass, 20 translations > 15)
+    and an image sub-range, against the reference's own scan loop (oracle/_ref: ref_scan restates src/Optimiser.cpp:756-914 around
+    Projector::project + logDataVSPrior_m_n): weights relative to the baseline, marginals with the priors of the other dimension"""
+    port, ref = _oracle()
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    pb = problem
+    _setup_E(ctx, pb)
+    rng = np.random.default_rng(31)
+    nR, nT = 300, 20
+    quat = synth.random_quats(nR, rng); quat[:pb["nImg"]] = pb["par"]["quat"]
+    tran = rng.normal(scale=1.5, size=(nT, 2))
+    pR = rng.uniform(0.5, 1.5, nR); pR /= pR.sum()
+    pT = rng.uniform(0.5, 1.5, nT); pT /= pT.sum()
+    imgs = np.nonzero(pb["slot"] == 1)[0]
+    P = ref.Projector(pb["pf"])
+    P.set_padded_ft(pb["vols"][1])
+    want = ref.scan([P], False, pb["par"]["dat"][imgs], pb["par"]["ctf"][imgs], pb["par"]["sigRcp"][imgs], pb["pixE"]["iCol"], pb["pixE"]["iRow"], pb["N"],
+                    quat, tran, pR, pT, nThread=4)
+    P.close()
+    for rng_ in (None, (1, pb["nImg"] - 1)):
+        out = ctx.expect_scan(1, quat, tran, pR, pT, img_range=rng_)
+        off = 0 if rng_ is None else rng_[0]
+        for j, l in enumerate(imgs):
+            if l < off:
+                continue
+            assert abs(out["base"][l - off] - want["base"][j]) <= 2e-6 * abs(want["base"][j]) + 1e-4
+            for key, k2 in (("wR", "wR"), ("wT", "wT")):
+                a, b = out[key][l - off].astype(np.float64), want[k2][0][j].astype(np.float64)
+                big = b > 1e-4 * b.max()
+                assert np.allclose(a[big], b[big], rtol=5e-3), (key, l)
+            assert np.isclose(out["wC"][l - off], want["wC"][j, 0], rtol=5e-3)
+
+
 def test_insert_random_two_halves(ctx, problem):
     pb = problem
     port, ref = _oracle()

@@ -99,6 +99,7 @@ def _sig(lib):
     f = lib.thb_project; f.restype = _i; f.argtypes = [_p, _i, _i, _p, _p]
     f = lib.thb_expect_local; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i] + [_p] * 9
     f = lib.thb_expect_scan; f.restype = _i; f.argtypes = [_p, _i, _i, _i] + [_p] * 9
+    f = lib.thb_expect_scan_range; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _i, _i] + [_p] * 9
     f = lib.thb_reco_alloc; f.restype = _i; f.argtypes = [_p, _i, _i]
     f = lib.thb_reco_reset; f.restype = _i; f.argtypes = [_p, _i]
     f = lib.thb_insert; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p]
@@ -403,16 +404,16 @@ class Context:
                                             _ptr(uR), _ptr(uT), _ptr(uC), _ptr(base), _ptr(logL)))
         return dict(uR=uR, uT=uT, uC=uC, base=base, logL=logL)
 
-    def expect_scan(self, slot, quat, tran, pR, pT, want_logL=False):
+    def expect_scan(self, slot, quat, tran, pR, pT, want_logL=False, img_range=None):
         quat = _arr(quat, np.float64); tran = _arr(tran, np.float64)
         nR, nT = quat.shape[0], tran.shape[0]
         pR = _arr(pR, np.float64, (nR,)); pT = _arr(pT, np.float64, (nT,))
-        n = self.nImgE
+        base0, n = (0, self.nImgE) if img_range is None else img_range
         wC = np.empty(n, np.float32); wR = np.empty((n, nR), np.float32); wT = np.empty((n, nT), np.float32)
         base = np.empty(n, np.float32)
         logL = np.empty((n, nR, nT), np.float32) if want_logL else None
-        self._chk(self.lib.thb_expect_scan(self.h, slot, nR, nT, _ptr(quat), _ptr(tran), _ptr(pR), _ptr(pT),
-                                           _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base), _ptr(logL)))
+        self._chk(self.lib.thb_expect_scan_range(self.h, slot, int(base0), int(n), nR, nT, _ptr(quat), _ptr(tran), _ptr(pR), _ptr(pT),
+                                                 _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base), _ptr(logL)))
         return dict(wC=wC, wR=wR, wT=wT, base=base, logL=logL)
 
     # ---- M

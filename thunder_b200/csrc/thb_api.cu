@@ -1262,93 +1262,109 @@ int thb_expect_local_ctf(thb_ctx* ctx, int nAct, const int* imgIdx, int nR, int 
     return THB_OK;
 }
 
-// Global-scan shape (src/Optimiser.cpp:633-914): one shared rotation/translation set against every
-// image.  Round 1: the same fused kernel with particle-stride 0 views; rotations beyond one CTA's
-// shared-memory budget are processed in chunks and merged on the host with the reference's
-// running-baseline rule.
+// Global-scan shape (src/Optimiser.cpp:633-914): one shared rotation / translation set against every image.  The fused kernel
+// takes the whole rotation set in one launch (passes of 128 rotations inside the kernel, log-likelihood table in a global scratch
+// buffer, baseline = the maximum over the whole table, marginals in its epilogue); what is chunked is the IMAGE list, so that the
+// table fits a scratch budget - no merging of partial results, no host round trip per chunk.
 int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, const double* tran, const double* pR,
                     const double* pT, float* wC, float* wR, float* wT, float* base, float* logL)
+{
+    if (!ctx) return THB_E_ARG;
+    return thb_expect_scan_range(ctx, slot, 0, ctx->stackE.nImg, nR, nT, quat, tran, pR, pT, wC, wR, wT, base, logL);
+}
+
+// the same for the images [imgBase, imgBase + nImgRange) of the stack only; output rows are relative to imgBase
+int thb_expect_scan_range(thb_ctx* ctx, int slot, int imgBase, int nImgRange, int nR, int nT, const double* quat, const double* tran,
+                          const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base, float* logL)
 {
     if (!ctx) return THB_E_ARG;
     const int vdim = check_expect_state(ctx, "expect_scan");
     if (vdim < 0) return vdim;
     if (nR <= 0 || nT <= 0 || !quat || !tran || !pR || !pT) return set_error(ctx, THB_E_ARG, "expect_scan: bad arguments");
     if (slot < 0 || slot >= THB_MAX_SLOTS || !ctx->vols[slot].d) return set_error(ctx, THB_E_STATE, "expect_scan: no volume in slot %d", slot);
+    if (imgBase < 0 || nImgRange <= 0 || imgBase + nImgRange > ctx->stackE.nImg) return set_error(ctx, THB_E_ARG, "expect_scan: images [%d,%d) outside the stack", imgBase, imgBase + nImgRange);
     THB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int nImg = ctx->stackE.nImg;
+    const int nImg = nImgRange;
     const std::vector<int>& hslot = ctx->stackE.hslot;
-    std::vector<int> idx;
+    std::vector<int> idx;           // positions within the range
     // MODE_2D (classification, src/Optimiser.cpp:756-914): every image is compared with every class reference
-    for (int i = 0; i < nImg; ++i) if (ctx->mode2D || hslot[i] == slot) idx.push_back(i);
-    const int nAct = (int)idx.size();
+    for (int i = 0; i < nImg; ++i) if (ctx->mode2D || hslot[imgBase + i] == slot) idx.push_back(i);
+    const int nAll = (int)idx.size();
     if (wC) memset(wC, 0, sizeof(float) * nImg);
     if (wR) memset(wR, 0, sizeof(float) * (size_t)nImg * nR);
     if (wT) memset(wT, 0, sizeof(float) * (size_t)nImg * nT);
     if (base) memset(base, 0, sizeof(float) * nImg);
     if (logL) memset(logL, 0, sizeof(float) * (size_t)nImg * nR * nT);
-    if (nAct == 0) return THB_OK;
-
-    const int rChunk = std::max(1, std::min(nR, (int)((160 * 1024) / (sizeof(float) * nT))));
-    std::vector<float> cuR((size_t)nAct * rChunk), cuT((size_t)nAct * nT), cuC(nAct), cbase(nAct), clog;
-    std::vector<float> aR((size_t)nAct * nR, 0.f), aT((size_t)nAct * nT, 0.f), aC(nAct, 0.f), abase(nAct, -INFINITY);
-    if (logL) clog.resize((size_t)nAct * rChunk * nT);
+    if (nAll == 0) return THB_OK;
 
     const int qc = ctx->mode2D ? 2 : 4;
-    double* din = (double*)scratch(ctx, 0, sizeof(double) * ((size_t)rChunk * 4 + nT * 2 + rChunk + nT) + sizeof(int) * (size_t)nAct);
-    if (!din) return THB_E_CUDA;
-    for (int r0 = 0; r0 < nR; r0 += rChunk) {
-        const int nr = std::min(rChunk, nR - r0);
-        double* dq = din; double* dt = dq + (size_t)rChunk * 4; double* dwr = dt + nT * 2; double* dwt = dwr + rChunk;
-        int* didx = (int*)(dwt + nT);
-        const size_t nout = (size_t)nAct * nr + (size_t)nAct * nT + 2 * (size_t)nAct + (logL ? (size_t)nAct * nr * nT : 0);
-        float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
-        if (!dout) return THB_E_CUDA;
-        THB_CUDA(ctx, cudaMemcpyAsync(dq, quat + (size_t)r0 * qc, sizeof(double) * qc * nr, cudaMemcpyHostToDevice, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * 2 * nT, cudaMemcpyHostToDevice, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(dwr, pR + r0, sizeof(double) * nr, cudaMemcpyHostToDevice, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(dwt, pT, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(didx, idx.data(), sizeof(int) * (size_t)nAct, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t nRT = (size_t)nR * nT;
+    // images per launch: the table (and the optional copy of it) within 1 GiB, at least one wave of CTAs where the list allows
+    const size_t budget = (size_t)1 << 30;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nAll, budget / (nRT * sizeof(float) * (logL ? 2 : 1))));
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * ((size_t)nR * 4 + nT * 2 + nR + nT) + sizeof(int) * (size_t)nAll);
+    const size_t nout = (size_t)chunk * nR + (size_t)chunk * nT + 2 * (size_t)chunk + (logL ? (size_t)chunk * nRT : 0);
+    float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
+    if (!din || !dout) return THB_E_CUDA;
+    double* dq = din; double* dt = dq + (size_t)nR * 4; double* dwr = dt + nT * 2; double* dwt = dwr + nR;
+    int* didx = (int*)(dwt + nT);
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * qc * (size_t)nR, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * 2 * nT, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwr, pR, sizeof(double) * nR, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwt, pT, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<int> abs_idx(nAll);
+        for (int i = 0; i < nAll; ++i) abs_idx[i] = imgBase + idx[i];
+        THB_CUDA(ctx, cudaMemcpyAsync(didx, abs_idx.data(), sizeof(int) * (size_t)nAll, cudaMemcpyHostToDevice, ctx->stream));
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<float> hR, hT, hC, hB, hL;
+    const bool scatter = nAll != nImg;        // results go to the rows of the selected images
+    for (int l0 = 0; l0 < nAll; l0 += chunk) {
+        const int nAct = std::min(chunk, nAll - l0);
         ExpectArgs a;
         memset(&a, 0, sizeof(a));
         a.vols = vol_table(ctx); a.vdim = vdim; a.pitch = vol_pitch(vdim);
         a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
         a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
-        a.nAct = nAct; a.imgIdx = didx; a.nR = nr; a.nT = nT;
+        a.nAct = nAct; a.imgIdx = didx + l0; a.nR = nR; a.nT = nT;
         a.slotAll = ctx->mode2D ? slot : -1;
         a.quat = View3{dq, 0, qc, 1};
         a.tran = View3{dt, 0, 2, 1};
         a.wR = View3{dwr, 0, 1, 0};
         a.wT = View3{dwt, 0, 1, 0};
-        a.uR = dout; a.uT = a.uR + (size_t)nAct * nr; a.uC = a.uT + (size_t)nAct * nT; a.base = a.uC + nAct;
+        a.uR = dout; a.uT = a.uR + (size_t)nAct * nR; a.uC = a.uT + (size_t)nAct * nT; a.base = a.uC + nAct;
         a.logL = logL ? a.base + nAct : nullptr;
         int rc = launch_expect_local(ctx, a);
         if (rc) return rc;
-        THB_CUDA(ctx, cudaMemcpyAsync(cuR.data(), a.uR, sizeof(float) * (size_t)nAct * nr, cudaMemcpyDeviceToHost, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(cuT.data(), a.uT, sizeof(float) * (size_t)nAct * nT, cudaMemcpyDeviceToHost, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(cuC.data(), a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
-        THB_CUDA(ctx, cudaMemcpyAsync(cbase.data(), a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
-        if (logL) THB_CUDA(ctx, cudaMemcpyAsync(clog.data(), a.logL, sizeof(float) * (size_t)nAct * nr * nT, cudaMemcpyDeviceToHost, ctx->stream));
-        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        // merge this rotation chunk: rescale to the larger baseline (Optimiser.cpp:846-870)
-        for (int l = 0; l < nAct; ++l) {
-            float nb = std::max(abase[l], cbase[l]);
-            float so = abase[l] == -INFINITY ? 0.f : expf(abase[l] - nb), sn = expf(cbase[l] - nb);
-            for (int r = 0; r < r0; ++r) aR[(size_t)l * nR + r] *= so;
-            for (int r = 0; r < nr; ++r) aR[(size_t)l * nR + r0 + r] = cuR[(size_t)l * nr + r] * sn;
-            for (int t = 0; t < nT; ++t) aT[(size_t)l * nT + t] = aT[(size_t)l * nT + t] * so + cuT[(size_t)l * nT + t] * sn;
-            aC[l] = aC[l] * so + cuC[l] * sn;
-            abase[l] = nb;
-            if (logL)
-                for (int r = 0; r < nr; ++r)
-                    memcpy(logL + ((size_t)idx[l] * nR + r0 + r) * nT, clog.data() + ((size_t)l * nr + r) * nT, sizeof(float) * nT);
+        if (!scatter) {
+            // the selection is the whole stack in order: straight into the caller's arrays
+            if (wR) THB_CUDA(ctx, cudaMemcpyAsync(wR + (size_t)l0 * nR, a.uR, sizeof(float) * (size_t)nAct * nR, cudaMemcpyDeviceToHost, ctx->stream));
+            if (wT) THB_CUDA(ctx, cudaMemcpyAsync(wT + (size_t)l0 * nT, a.uT, sizeof(float) * (size_t)nAct * nT, cudaMemcpyDeviceToHost, ctx->stream));
+            if (wC) THB_CUDA(ctx, cudaMemcpyAsync(wC + l0, a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+            if (base) THB_CUDA(ctx, cudaMemcpyAsync(base + l0, a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+            if (logL) THB_CUDA(ctx, cudaMemcpyAsync(logL + (size_t)l0 * nRT, a.logL, sizeof(float) * (size_t)nAct * nRT, cudaMemcpyDeviceToHost, ctx->stream));
+            THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the scratch table is reused by the next chunk
+            continue;
         }
-    }
-    for (int l = 0; l < nAct; ++l) {
-        const int i = idx[l];
-        if (wC) wC[i] = aC[l];
-        if (base) base[i] = abase[l];
-        if (wR) memcpy(wR + (size_t)i * nR, aR.data() + (size_t)l * nR, sizeof(float) * nR);
-        if (wT) memcpy(wT + (size_t)i * nT, aT.data() + (size_t)l * nT, sizeof(float) * nT);
+        hR.resize((size_t)nAct * nR); hT.resize((size_t)nAct * nT); hC.resize(nAct); hB.resize(nAct);
+        THB_CUDA(ctx, cudaMemcpyAsync(hR.data(), a.uR, sizeof(float) * hR.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(hT.data(), a.uT, sizeof(float) * hT.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(hC.data(), a.uC, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(hB.data(), a.base, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+        if (logL) {
+            hL.resize((size_t)nAct * nRT);
+            THB_CUDA(ctx, cudaMemcpyAsync(hL.data(), a.logL, sizeof(float) * hL.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int l = 0; l < nAct; ++l) {
+            const int i = idx[l0 + l];
+            if (wC) wC[i] = hC[l];
+            if (base) base[i] = hB[l];
+            if (wR) memcpy(wR + (size_t)i * nR, hR.data() + (size_t)l * nR, sizeof(float) * nR);
+            if (wT) memcpy(wT + (size_t)i * nT, hT.data() + (size_t)l * nT, sizeof(float) * nT);
+            if (logL) memcpy(logL + (size_t)i * nRT, hL.data() + (size_t)l * nRT, sizeof(float) * nRT);
+        }
     }
     return THB_OK;
 }
