@@ -719,6 +719,13 @@ def main():
                 "data": "synthetic", "config": config_dict(args, wl, PE, PM, world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "wall_ms_per_step": wall / args.steps,
                 "reconstruct_and_projector_refresh": reco_ms}
+        c_ms, c_n = fam["comm"]
+        if world > 1 and c_n:
+            m = N * pf
+            wire = 2 * (m // 2 + 1) * m * m * 12                       # both half maps, 3 live floats per voxel
+            t = c_ms / c_n / 1e3
+            line["allreduce"] = {"bytes": wire, "ms": c_ms / c_n, "algbw_GBps": wire / t / 1e9, "busbw_GBps": 2 * (world - 1) / world * wire / t / 1e9,
+                                 "note": "rank 0's CUDA-event time around pack + ncclAllReduce + unpack on the compute stream (includes waiting for the slowest rank)"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

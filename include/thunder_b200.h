@@ -330,6 +330,18 @@ typedef struct thb_pf_params {
  * Particle::load semantics (src/Particle.cpp:401-556): ACG cloud about quat, Gaussian cloud about tran. */
 int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* quat, const double* k123,
                 const double* tran, const double* s01);
+/* From the global scan to the support of the local phases - the per-image logic that follows the scan in Optimiser::expectation
+ * (src/Optimiser.cpp:921-1075), on the device: choice of the class (setUC, keepHalfHeightPeak with PEAK_FACTOR_C, resample(nK, PAR_C),
+ * rand), likelihood weights of THAT class on the shared scan grid quat[nR][4] (MODE_2D: [nR][2] = (cos, sin)) / tran[nT][2],
+ * setPeakFactor + keepHalfHeightPeak(PAR_R), resample(mLR, PAR_R), resample(mLT, PAR_T), calVari, floors kFloor on k1 (.. k3) and
+ * sFloor on s0, s1 (OPTIMISER_SCAN_SET_MIN_STD_WITH_PERTURB).  Inputs as thb_expect_scan returns them, class by class:
+ * wC[nPar][nK] (relative to ONE baseline per image: scale the per-class results to the largest baseline), wR[nK][nPar][nR],
+ * wT[nK][nPar][nT].  The chosen class becomes the slot of the image in both resident stacks (clsOut[nPar], may be NULL), the
+ * particles are the loaded ones (as after thb_pf_load; MODE_2D allowed: the phase loop then runs the von Mises operators).
+ * A global-search iteration then continues with thb_expectation with perturbFactorL = perturbFactorSGlobal (its phases start
+ * at 1 in the reference: there is no large first perturbation). */
+int thb_pf_from_scan(thb_ctx* ctx, int nPar, const thb_pf_params* p, int nK, int nR, int nT, const double* quat, const double* tran,
+                     const float* wC, const float* wR, const float* wT, double kFloor, double sFloor, int* clsOut);
 /* CTF search: per particle the constants of the on-the-fly CTF of the E-step, ctfK[nPar][4] = {K1, K2, phaseShift,
  * amplitudeContrast} (allocPreCal, src/Optimiser.cpp:8163-8167), and the attributes the M-step computes the CTF of every draw
  * from, ctfAttr[nPar][7] (the layout of thb_pack_stack), with the pixel size.  Call after thb_pf_load. */

@@ -826,6 +826,65 @@ void ref_particle_set_u(void* h, int which /*0 C,1 R,2 T,3 D*/, const double* u,
     }
 }
 
+// The per-image logic that follows the global scan in Optimiser::expectation (reference src/Optimiser.cpp:921-1075) on a Particle
+// that holds the shared scan grid with the uniform weights of Particle::reset: class choice, marginals of that class, peak
+// factors, resampling down to (mLR, mLT), variances and their floors (OPTIMISER_SCAN_SET_MIN_STD_WITH_PERTURB: the caller passes
+// the floors).  Replay mode: the engine is keyed (seed, stream, epoch) after the grid is in place.
+int ref_particle_from_scan(int mode2D, int nK, int nR, int nT, const double* gridR, const double* gridT, const float* wC,
+                           const float* wR, const float* wT, int mLR, int mLT, double kFloor, double sFloor, double transS,
+                           double transQ, unsigned long long seed, unsigned long long stream, unsigned long long epoch, double* rOut,
+                           double* tOut, double* wROut, double* wTOut, double* scal19)
+{
+    Particle par(mode2D ? MODE_2D : MODE_3D, nK, nR, nT, 1, transS, transQ, NULL);
+    {
+        uvec c(nK);
+        for (int k = 0; k < nK; k++) c(k) = k;
+        par.setC(c);
+        dmat4 r = dmat4::Zero(nR, 4);
+        for (int i = 0; i < nR; i++)
+            for (int j = 0; j < (mode2D ? 2 : 4); j++) r(i, j) = gridR[(size_t)i * (mode2D ? 2 : 4) + j];
+        par.setR(r);
+        dmat2 t(nT, 2);
+        for (int i = 0; i < nT; i++) { t(i, 0) = gridT[2 * i]; t(i, 1) = gridT[2 * i + 1]; }
+        par.setT(t);
+        par.setWC(dvec::Constant(nK, 1.0 / nK)); par.setWR(dvec::Constant(nR, 1.0 / nR)); par.setWT(dvec::Constant(nT, 1.0 / nT));
+        par.setUC(dvec::Constant(nK, 1.0 / nK)); par.setUR(dvec::Constant(nR, 1.0 / nR)); par.setUT(dvec::Constant(nT, 1.0 / nT));
+    }
+    if (g_replay) replay_key(seed, stream, epoch);
+
+    for (int iC = 0; iC < nK; iC++) par.setUC(wC[iC], iC);
+    par.setPeakFactor(PAR_C);
+    par.keepHalfHeightPeak(PAR_C);
+    par.resample(nK, PAR_C);
+    size_t cls;
+    par.rand(cls);
+    par.setNC(1);
+    par.setC(uvec::Constant(1, cls));
+    par.setWC(dvec::Constant(1, 1));
+    par.setUC(dvec::Constant(1, 1));
+    for (int iR = 0; iR < nR; iR++) par.setUR(wR[(size_t)cls * nR + iR], iR);
+    for (int iT = 0; iT < nT; iT++) par.setUT(wT[(size_t)cls * nT + iT], iT);
+    par.setPeakFactor(PAR_R);
+    par.keepHalfHeightPeak(PAR_R);
+    par.resample(mLR, PAR_R);
+    par.resample(mLT, PAR_T);
+    par.calVari(PAR_R);
+    par.calVari(PAR_T);
+    par.setK1(TSGSL_MAX_RFLOAT(kFloor, par.k1()));
+    if (!mode2D)
+    {
+        par.setK2(TSGSL_MAX_RFLOAT(kFloor, par.k2()));
+        par.setK3(TSGSL_MAX_RFLOAT(kFloor, par.k3()));
+    }
+    par.setS0(TSGSL_MAX_RFLOAT(sFloor, par.s0()));
+    par.setS1(TSGSL_MAX_RFLOAT(sFloor, par.s1()));
+
+    for (int i = 0; i < mLR; i++) { for (int j = 0; j < 4; j++) rOut[i * 4 + j] = par._r(i, j); wROut[i] = par._wR(i); }
+    for (int i = 0; i < mLT; i++) { tOut[2 * i] = par._t(i, 0); tOut[2 * i + 1] = par._t(i, 1); wTOut[i] = par._wT(i); }
+    ref_particle_get_scalars(&par, scal19);
+    return (int)cls;
+}
+
 void ref_particle_initD(void* h, int nD, double sD) { ((Particle*)h)->initD(nD, sD); }
 void ref_particle_perturb(void* h, double pf, int pt) { ((Particle*)h)->perturb(pf, (ParticleType)pt); }
 void ref_particle_resample(void* h, int n, int pt) { ((Particle*)h)->resample(n, (ParticleType)pt); }

@@ -133,6 +133,9 @@ def lib():
         L.ref_insert_loop_ctf.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _i]
         L.ref_scan.argtypes = [_p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p]
         L.ref_insert_loop_2d.argtypes = [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i]
+        L.ref_particle_from_scan.restype = _i
+        L.ref_particle_from_scan.argtypes = [_i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _d, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong,
+                                             _p, _p, _p, _p, _p]
         L.ref_rng_replay.argtypes = [_i]
         L.ref_rng_key.argtypes = [C.c_ulonglong] * 3
         L.ref_rng_replay_loop.argtypes = [C.c_ulonglong] * 3
@@ -538,6 +541,17 @@ def insert_loop_2d(recos, dat, ctf_, w, offS, nc, nr, nt, iCol, iRow, N, nThread
     hs = (_p * len(recos))(*[r.h for r in recos])
     lib().ref_insert_loop_2d(hs, nImg, _ptr(dat), _ptr(ctf_), _ptr(w), _ptr(offS), _ptr(nc), _ptr(nr), _ptr(nt), _ptr(iCol), _ptr(iRow), P, N,
                              nc.shape[1], nThread)
+
+
+def particle_from_scan(mode2D, gridR, gridT, wC, wR, wT, mLR, mLT, kFloor, sFloor, key, transS=2.0, transQ=0.01):
+    """post-scan logic of Optimiser::expectation on the reference's Particle (ref_particle_from_scan); wR[nK][nR], wT[nK][nT] of ONE image"""
+    gridR = np.ascontiguousarray(gridR, np.float64); gridT = np.ascontiguousarray(gridT, np.float64)
+    wC = np.ascontiguousarray(wC, np.float32); wR = np.ascontiguousarray(wR, np.float32); wT = np.ascontiguousarray(wT, np.float32)
+    nK, nR, nT = len(wC), len(gridR), len(gridT)
+    r = np.zeros((mLR, 4)); t = np.zeros((mLT, 2)); oR = np.zeros(mLR); oT = np.zeros(mLT); sc = np.zeros(19)
+    cls = lib().ref_particle_from_scan(int(mode2D), nK, nR, nT, _ptr(gridR), _ptr(gridT), _ptr(wC), _ptr(wR), _ptr(wT), mLR, mLT, kFloor, sFloor,
+                                       transS, transQ, key[0], key[1], key[2], _ptr(r), _ptr(t), _ptr(oR), _ptr(oT), _ptr(sc))
+    return dict(cls=cls, r=r, t=t, wR=oR, wT=oT, scal=sc)
 
 
 class replay:

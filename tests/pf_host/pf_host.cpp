@@ -4,6 +4,7 @@
 // Compiled by tests/test_pf_host.py with g++; never part of libthunder_b200.so.
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "thb_pf.cuh"
 #include "thb_pf2d.cuh"
 
@@ -32,7 +33,7 @@ int pfh_run_s(int op, double arg, int mLR, int mLT, double* r, double* t, double
     v.r = r; v.t = t; v.wR = wR; v.wT = wT; v.uR = uR; v.uT = uT; v.scal = scal;
     v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
     v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1;
-    v.mLD = 0; v.d = v.wD = v.uD = nullptr;
+    v.mLD = 0; v.d = v.wD = v.uD = nullptr; v.mode2D = 0;
     pf::Rng g;
     g.init(seed, stream, epoch);
     switch (op) {
@@ -106,6 +107,26 @@ int pfh_run_d(int op, double arg, int mLD, double* d, double* wD, double* uD, co
         default: return -1;
     }
     return 0;
+}
+
+// the hand-over from the global scan (thb_pf2d.cuh: from_scan) for one image; r / t / wR / wT / scal as in pfh_run
+int pfh_from_scan(int mode2D, int nK, int nR, int nT, const double* gridR, const double* gridT, const float* wC, const float* wR,
+                  const float* wT, int mLR, int mLT, double kFloor, double sFloor, double* r, double* t, double* owR, double* owT,
+                  double* scal, unsigned long long seed, unsigned long long stream, unsigned long long epoch)
+{
+    const int mw = mLR > mLT ? mLR : mLT;
+    const int nMax = std::max(std::max(nR, nT), 4 * nK);
+    std::vector<double> r2(4 * mLR), t2(2 * mLT), w2(mw), w3(mw), w4(mw), uR(mLR), uT(mLT), sc(3 * (size_t)nMax);
+    std::vector<int> ix(mLR + mLT);
+    pf::View v;
+    memset(&v, 0, sizeof(v));
+    v.r = r; v.t = t; v.wR = owR; v.wT = owT; v.uR = uR.data(); v.uT = uT.data(); v.scal = scal;
+    v.r2 = r2.data(); v.t2 = t2.data(); v.w2 = w2.data(); v.w3 = w3.data(); v.w4 = w4.data();
+    v.n = 1; v.p = 0; v.mLR = mLR; v.mLT = mLT; v.lane = -1; v.mode2D = mode2D;
+    pf::Rng g;
+    g.init(seed, stream, epoch);
+    return pf::from_scan(v, g, mode2D, nK, nR, nT, gridR, mode2D ? 2 : 4, gridT, wC, wR, (size_t)nR, wT, (size_t)nT, kFloor, sFloor, sc.data(),
+                         sc.data() + nMax, sc.data() + 2 * nMax, ix.data(), ix.data() + mLR);
 }
 
 // the GSL entry points restated in pf::Rng, by kind as ref_rng_draw of oracle/ref_harness.cpp

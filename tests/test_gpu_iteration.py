@@ -590,6 +590,44 @@ def test_iteration_fsc_gate_2000_particles():
         assert np.all(f[1:] >= f0[1:] - 0.002) and np.all(ft[1:] >= ft0[1:] - 0.002)
 
 
+def test_global_search_iteration_scan_handover_phases(ctx, prob):
+    """a global-search E-step in MODE_3D on the device: scan over a shared grid of 3 000 random rotations x 30 translations
+    (thb_expect_scan, one launch per image chunk) -> support of the local phases from the scan's weights (thb_pf_from_scan: class
+    choice trivial with k = 1, setPeakFactor / keepHalfHeightPeak / resample down to 125 x 9, variances with the scan's floors) ->
+    phases (thb_expectation).  The scan's best grid point is ~10 degrees off (grid spacing), the phases bring it down."""
+    pb = prob
+    n, N = pb["nImg"], pb["N"]
+    _setup(ctx, pb)
+    rng = np.random.default_rng(31)
+    nR, nT = 3000, 30
+    grid = synth.random_quats(nR, rng)
+    trans = rng.normal(scale=2.0, size=(nT, 2))
+    pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
+    res = [ctx.expect_scan(s, grid, trans, pR, pT) for s in (0, 1)]
+    # k = 1: every image has ONE reference, its half-set's (the scan of the other slot leaves its rows zero)
+    wC = (res[0]["wC"] + res[1]["wC"])[:, None]
+    wR = (res[0]["wR"] + res[1]["wR"])[None]; wT = (res[0]["wT"] + res[1]["wT"])[None]
+    scanMinStdR = nR ** (-1.0 / 3); pfS = 0.5
+    prm = _params(125, 9, fixed=8, seed=77)
+    prm.perturbFactorL = pfS                       # global search: no large first perturbation (phases start at 1 in the reference)
+    slot_before = pb["slot"].copy()
+    ctx.pf_set_image_base(0, 0)
+    cls = ctx.pf_from_scan(prm, grid, trans, wC, wR, wT, kFloor=(scanMinStdR / pfS) ** 2, sFloor=0.3)
+    assert not cls.any()
+    # pf_from_scan makes the chosen class the image's slot: with k = 1 in a two-half-set context the slots are restored
+    ctx.upload_stack(capi.STACK_EXPECT, pb["par"]["dat"], pb["par"]["ctf"], pb["par"]["sigRcp"], slot_before)
+    ctx.upload_stack(capi.STACK_INSERT, pb["datM"], pb["ctfM"], slotOfImg=slot_before)
+    sc0 = ctx.pf_get_scal()
+    err0 = _ang_deg(sc0[:, 6:10], pb["par"]["quat"])
+    ctx.expectation()
+    sc = ctx.pf_get_scal()
+    err = _ang_deg(sc[:, 6:10], pb["par"]["quat"])
+    print(f"\nglobal search: best grid point of the scan {np.median(err0):.2f} deg off (median), after 8 phases {np.median(err):.2f} deg; "
+          f"translation {np.median(np.linalg.norm(sc[:, 10:12] - pb['par']['tran'], axis=1)):.2f} px")
+    assert np.median(err0) < 15.0
+    assert np.median(err) < 0.6 * np.median(err0)
+
+
 def test_adaptive_stop_rule_runs(ctx, prob):
     """data-dependent phase count (MIN 3, MAX 100, 5% variance-decrease rule) is evaluated on the device"""
     pb = prob

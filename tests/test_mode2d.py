@@ -283,3 +283,82 @@ def test_mode_switch_and_guards(ctx2d):
     ctx2d.set_mode(capi.MODE_3D)                                  # drops the 2D references
     with pytest.raises(capi.ThbError):
         ctx2d.project(0, np.array([[1.0, 0, 0, 0]]))
+
+
+@pytest.mark.gpu
+def test_classification_iteration_on_the_device_scan_handover_phases_insert():
+    """a whole 2D classification iteration without the host in the loop of the particles: scan of every image against every class
+    (thb_expect_scan) -> choice of the class and support of the local phases from the scan's weights (thb_pf_from_scan: the logic
+    of src/Optimiser.cpp:921-1075, pinned to the reference's Particle draw by draw in tests/test_pf_host.py) -> local phases with
+    the von Mises operators on the device (thb_expectation) -> class-wise insert (thb_reconstruct_insert).  Synthetic images of
+    three distinct class averages at per-pixel SNR 0.5: the class is recovered for nearly all images, the in-plane angle to a
+    few degrees, and every draw lands in the accumulator of its image's class."""
+    N, pf, k, n = 64, 2, 3, 96
+    rng = np.random.default_rng(11)
+    refs = _class_averages(N, pf, k, 21)
+    pixE = capi.pixel_list(N, pf, 28.0, 1.0); pixM = capi.pixel_list(N, pf, 30.0, 0.0)
+    PE, PM = len(pixE["iCol"]), len(pixM["iCol"])
+    c = capi.Context(0)
+    try:
+        c.set_mode(capi.MODE_2D)
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        for s_, r_ in enumerate(refs):
+            c.set_volume(s_, r_)
+            c.reco_alloc(s_, N * pf)
+        cls_true = rng.integers(0, k, n); phi = rng.uniform(-np.pi, np.pi, n); tran = rng.normal(scale=1.5, size=(n, 2))
+
+        def simulate(pix):
+            c.set_expect_pixels(N, pf, pix["iCol"], pix["iRow"])
+            clean = np.empty((n, len(pix["iCol"])), np.complex64)
+            for s_ in range(k):
+                sel = np.nonzero(cls_true == s_)[0]
+                clean[sel] = c.project(s_, _unit(phi[sel]))
+            ctf = np.stack([synth.ctf_values(pix["iCol"].astype(float), pix["iRow"].astype(float), N, 1.32, 3e5, 2e4 + 100 * l, 2.02e4 + 100 * l, 0.3,
+                                             2.7e7, 0.1) for l in range(n)]).astype(np.float32)
+            ph = -2 * np.pi * (pix["iCol"][None] * tran[:, :1] / N + pix["iRow"][None] * tran[:, 1:] / N)
+            sig2 = float(np.mean(np.abs(clean * ctf) ** 2)) / 0.5
+            noise = (rng.normal(size=clean.shape) + 1j * rng.normal(size=clean.shape)) * np.sqrt(sig2 / 2)
+            return (ctf * clean * np.exp(1j * ph) + noise).astype(np.complex64), ctf, sig2
+        datM, ctfM, _ = simulate(pixM)
+        datE, ctfE, sig2 = simulate(pixE)
+        c.set_expect_pixels(N, pf, pixE["iCol"], pixE["iRow"])
+        c.upload_stack(capi.STACK_EXPECT, datE, ctfE, np.full((n, PE), -0.5 / sig2, np.float32))
+        c.upload_stack(capi.STACK_INSERT, datM, ctfM)
+        nR, nT = 100, 30
+        ang = np.linspace(-np.pi, np.pi, nR, endpoint=False); cs = _unit(ang)
+        trans = rng.normal(scale=1.5, size=(nT, 2)); pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
+        res = [c.expect_scan(s_, cs, trans, pR, pT) for s_ in range(k)]
+        base = np.max([r_["base"] for r_ in res], axis=0)
+        wC = np.stack([r_["wC"] * np.exp(r_["base"] - base) for r_ in res], 1)            # one baseline per image, as ExpectGlobal2D
+        wR = np.stack([r_["wR"] for r_ in res]); wT = np.stack([r_["wT"] for r_ in res])
+        prm = capi.PFParams(mLR=9, mLT=9, transS=2.0, transQ=0.01, perturbFactorL=0.5, perturbFactorS=0.5, minPhase=3, maxPhase=100,
+                            fixedPhases=5, decreaseFactor=0.95, noDecreaseLimit=1, seed=5)
+        c.pf_set_image_base(0, 0)
+        cls = c.pf_from_scan(prm, cs, trans, wC, wR, wT, kFloor=1.0 / nR / 0.5, sFloor=0.1)
+        assert (cls == cls_true).mean() >= 0.9, (cls == cls_true).mean()
+        st = c.pf_get()
+        assert np.allclose(np.linalg.norm(st["r"][..., :2], axis=2), 1.0, atol=1e-12) and not st["r"][..., 2:].any()
+        # every support point is one of the scan's grid points
+        d = np.abs(st["r"][:, :, None, :2] - cs[None, None]).sum(-1).min(-1)
+        assert d.max() <= 1e-12
+        ok = cls == cls_true
+        sc0 = st["scal"]
+        err0 = np.degrees(np.abs(np.angle(np.exp(1j * (np.arctan2(sc0[:, 7], sc0[:, 6]) - phi)))))
+        print(f"\nafter the hand-over: angle error of the scan's best grid point median {np.median(err0[ok]):.2f} deg, k1 median {np.median(sc0[:, 0]):.4f}, "
+              f"distinct support points median {np.median([len(np.unique(np.round(r_[:, :2], 9), axis=0)) for r_ in st['r']]):.0f}")
+        c.expectation()
+        sc = c.pf_get_scal()
+        st2 = c.pf_get()
+        print(f"after the phases: k1 median {np.median(sc[:, 0]):.5f}, NaN supports {int(np.isnan(st2['r']).any((1, 2)).sum())}")
+        err = np.degrees(np.abs(np.angle(np.exp(1j * (np.arctan2(sc[:, 7], sc[:, 6]) - phi)))))
+        errT = np.linalg.norm(sc[:, 10:12] - tran, axis=1)
+        print(f"\n2D iteration on the device: class recovered for {ok.mean() * 100:.0f} % of {n} images; in-plane angle error median "
+              f"{np.median(err[ok]):.2f} deg (grid step {360 / nR:.1f} deg), translation error median {np.median(errT[ok]):.2f} px")
+        assert np.median(err[ok]) < 3.0 and np.median(errT[ok]) < 0.8
+        mReco = 20
+        c.reconstruct_insert(mReco)
+        cnt = [c.reco_download(s_)["counter"] for s_ in range(k)]
+        assert cnt == [int((cls == s_).sum()) * mReco for s_ in range(k)]
+    finally:
+        c.close()

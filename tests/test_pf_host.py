@@ -32,6 +32,8 @@ def pfh():
     L.pfh_rng.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _p, _p]
     L.pfh_rng_draw.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, _i, _i, _d, _d, _p]
     L.pfh_run_d.restype = _i
+    L.pfh_from_scan.restype = _i
+    L.pfh_from_scan.argtypes = [_i, _i, _i, _i] + [_p] * 5 + [_i, _i, _d, _d] + [_p] * 5 + [C.c_ulonglong] * 3
     L.pfh_run_d.argtypes = [_i, _d, _i, _p, _p, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]
     L.pfh_sample_vms.argtypes = [C.c_ulonglong, _d, _i, _p]
     L.pfh_infer_vms.argtypes = [_i, _p, _p, _p]
@@ -494,3 +496,56 @@ def test_defocus_dimension_replay_exact(pfh, ref):
                 assert abs(d[mLD] - P.scalars()[14]) <= 1e-14                 # _topD
                 both(201, 0.5, lambda: P.perturb(0.5, P.PAR_D))
         P.close()
+
+
+@pytest.mark.parametrize("mode2D", [0, 1])
+def test_scan_hand_over_replay_exact(pfh, ref, mode2D):
+    """from the global scan to the support of the local phases (src/Optimiser.cpp:921-1075): class choice, peak factors, resampling of
+    the scan grid down to (mLR, mLT), variances and floors - against the reference's Particle driven through the same calls with the
+    same random numbers.  Chosen class and support points identical; variances to 1e-9 (3D: where the ACG of the resampled support is
+    well-posed - it holds many duplicates; 2D: von Mises, always)."""
+    rng = np.random.default_rng(77 + mode2D)
+    pt = lambda a: a.ctypes.data_as(_p)
+    skipped = 0
+    for trial in range(12):
+        nK = (1, 3, 20)[trial % 3]
+        nR, nT = (200, 30) if trial % 2 == 0 else (1000, 45)
+        mLR, mLT = (9, 9) if mode2D else (125, 9)
+        if mode2D:
+            ang = rng.uniform(-np.pi, np.pi, nR); gridR = np.stack([np.cos(ang), np.sin(ang)], 1)
+        else:
+            gridR = synth.random_quats(nR, rng)
+        gridT = rng.normal(scale=2.0, size=(nT, 2))
+        # scan weights: a peak around one grid point, per class, different heights
+        best = rng.integers(nR)
+        if mode2D:
+            d2 = 1 - (gridR @ gridR[best]) ** 1
+        else:
+            d2 = 1 - np.abs(gridR @ gridR[best]) ** 2
+        wR = np.stack([np.exp(-d2 / (2 * np.quantile(d2, 0.05 + 0.1 * rng.random()))) * rng.uniform(0.2, 1.0, nR) for _ in range(nK)]).astype(np.float32)
+        wT = np.stack([np.exp(-0.5 * ((gridT - gridT[rng.integers(nT)]) ** 2).sum(1) / rng.uniform(0.5, 4.0)) for _ in range(nK)]).astype(np.float32)
+        wC = (rng.uniform(0.9, 1.0, nK) ** 2).astype(np.float32)
+        wC[rng.integers(nK)] = 1.0
+        kFloor, sFloor = (1e-2 if mode2D else 1e-4), 0.05
+        seed, stream, epoch = 4000 + trial, 7, 3
+        r = np.zeros((4, mLR)); t = np.zeros((2, mLT)); owR = np.zeros(mLR); owT = np.zeros(mLT); scal = np.zeros(20)
+        cls = pfh.pfh_from_scan(mode2D, nK, nR, nT, pt(np.ascontiguousarray(gridR)), pt(np.ascontiguousarray(gridT)), pt(wC), pt(wR), pt(wT), mLR, mLT,
+                                kFloor, sFloor, pt(r), pt(t), pt(owR), pt(owT), pt(scal), seed, stream, epoch)
+        with ref.replay(seed, stream, epoch):
+            want = ref.particle_from_scan(mode2D, gridR, gridT, wC, wR, wT, mLR, mLT, kFloor, sFloor, (seed, stream, epoch))
+        assert cls == want["cls"], trial
+        # grid points, copied (calVari of the 3D filter turns the support by the conjugate of its mean and back: last-bit rounding)
+        assert np.abs(r.T[:, :2 if mode2D else 4] - want["r"][:, :2 if mode2D else 4]).max() <= 1e-12, trial
+        assert np.array_equal(t.T, want["t"])
+        assert np.allclose(owR, want["wR"], rtol=1e-12) and np.allclose(owT, want["wT"], rtol=1e-12)
+        assert np.allclose(scal[3:5], want["scal"][3:5], rtol=1e-12)                                       # s0, s1
+        assert np.array_equal(scal[6:10][:2 if mode2D else 4], want["scal"][8:12][:2 if mode2D else 4])    # topR
+        if mode2D:
+            assert np.isclose(scal[0], want["scal"][0], rtol=1e-12)
+        else:
+            tol = _acg_tol(ref, want["r"])
+            if tol < 1.0:
+                assert np.allclose(scal[0:3], want["scal"][0:3], rtol=max(1e-6, 100 * tol)), (trial, scal[0:3], want["scal"][0:3])
+            else:
+                skipped += 1
+    assert skipped <= 4

@@ -90,6 +90,7 @@ def _sig(lib):
     f = lib.thb_pf_set_image_base; f.restype = _i; f.argtypes = [_p, _i, C.c_uint64]
     f = lib.thb_pf_get_draws; f.restype = _i; f.argtypes = [_p, _i, _p, _p]
     f = lib.thb_pf_get_draws_d; f.restype = _i; f.argtypes = [_p, _i, _p]
+    f = lib.thb_pf_from_scan; f.restype = _i; f.argtypes = [_p, _i, C.POINTER(PFParams), _i, _i, _i, _p, _p, _p, _p, _p, C.c_double, C.c_double, _p]
     f = lib.thb_pf_set_ctf; f.restype = _i; f.argtypes = [_p, _p, _p, C.c_float]
     f = lib.thb_pf_get_d; f.restype = _i; f.argtypes = [_p, _p, _p, _p]
     f = lib.thb_pf_set_epoch; f.restype = _i; f.argtypes = [_p, C.c_uint64]
@@ -536,6 +537,19 @@ class Context:
 
     def pf_set_image_base(self, imgBase, streamBase=0):
         self._chk(self.lib.thb_pf_set_image_base(self.h, int(imgBase), int(streamBase)))
+
+    def pf_from_scan(self, params, quat, tran, wC, wR, wT, kFloor, sFloor):
+        """scan results -> particle supports; wC[nPar][nK], wR[nK][nPar][nR], wT[nK][nPar][nT]; returns the chosen classes"""
+        wC = _arr(wC, np.float32); nPar, nK = wC.shape
+        quat = _arr(quat, np.float64); tran = _arr(tran, np.float64)
+        nR, nT = quat.shape[0], tran.shape[0]
+        wR = _arr(wR, np.float32, (nK, nPar, nR)); wT = _arr(wT, np.float32, (nK, nPar, nT))
+        cls = np.empty(nPar, np.int32)
+        self._chk(self.lib.thb_pf_from_scan(self.h, nPar, C.byref(params), nK, nR, nT, _ptr(quat), _ptr(tran), _ptr(wC), _ptr(wR), _ptr(wT),
+                                            float(kFloor), float(sFloor), _ptr(cls)))
+        self.pf_params = params
+        self.nPar = nPar
+        return cls
 
     def pf_set_ctf(self, ctfK, ctfAttr, pixelSize):
         ctfK = _arr(ctfK, np.float32, (self.nPar, 4)); ctfAttr = _arr(ctfAttr, np.float32, (self.nPar, 7))

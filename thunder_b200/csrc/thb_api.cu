@@ -482,7 +482,7 @@ void thb_destroy(thb_ctx* ctx)
     free_stack(ctx->stackE);
     free_stack(ctx->stackM);
     cudaFree(ctx->pixE); cudaFree(ctx->pixM); cudaFree(ctx->permE); cudaFree(ctx->permM); cudaFree(ctx->segM); cudaFree(ctx->freqE); cudaFree(ctx->tilesE); cudaFree(ctx->dStats);
-    cudaFree(ctx->dO); cudaFree(ctx->dCounter);
+    cudaFree(ctx->dO); cudaFree(ctx->dCounter); cudaFree(ctx->commBuf);
     for (int i = 0; i < THB_N_SCRATCH; ++i) cudaFree(ctx->scratch[i]);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);

@@ -2,8 +2,10 @@
 //
 // Replaces Reconstructor::allReduceF/T/O (reference src/Reconstructor.cpp:2350-2520; NCCL twin
 // gpu/src/cuthunder.cu:5294-5324, 5903-5985, which creates and destroys communicators per call).
-// Here: ONE persistent communicator per context; the accumulators are interleaved {F.re,F.im,T,0}
-// so F and T of a slot travel in one ncclAllReduce; all slots + O + counter go in one group.
+// Here: ONE persistent communicator per context.  The accumulators are interleaved {F.re, F.im, T, 0} for the 16-byte
+// reductions of the insert; on the wire only the three live floats travel: every allocated slot is packed into ONE contiguous
+// buffer of 3 floats per voxel, reduced by a single ncclAllReduce (one large message instead of one per slot, 25 % fewer bytes
+// over NVLink than the padded vectors), and unpacked; O (fp64) and the counters (int32) ride in the same NCCL group.
 //
 // NCCL is resolved at run time with dlopen so that the library loads on machines without it and
 // binds to whichever libnccl.so.2 the host process already carries (torch's bundled copy or the
@@ -57,6 +59,20 @@ NcclApi& api()
 
 namespace thb {
 
+// {F.re, F.im, T, 0} x nVox  <->  3 floats x nVox
+__global__ void pack_acc3_kernel(const float4* __restrict__ acc, size_t nVox, float* __restrict__ buf)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nVox; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = acc[i];
+        buf[3 * i] = v.x; buf[3 * i + 1] = v.y; buf[3 * i + 2] = v.z;
+    }
+}
+__global__ void unpack_acc3_kernel(const float* __restrict__ buf, size_t nVox, float4* __restrict__ acc)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nVox; i += (size_t)gridDim.x * blockDim.x)
+        acc[i] = make_float4(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2], 0.f);
+}
+
 void comm_destroy(thb_ctx* ctx)
 {
     if (ctx->ncclComm && api().ok) api().CommDestroy((ncclComm_t)ctx->ncclComm);
@@ -69,18 +85,42 @@ int comm_allreduce(thb_ctx* ctx)
     NcclApi& n = api();
     if (!n.ok || !ctx->ncclComm) return set_error(ctx, THB_E_NCCL, "allreduce: communicator not initialised");
     ncclComm_t comm = (ncclComm_t)ctx->ncclComm;
+    size_t total = 0;
+    for (int s = 0; s < THB_MAX_SLOTS; ++s)
+        if (ctx->accs[s].d) total += ctx->accs[s].nVox;
+    if (total * 3 * sizeof(float) > ctx->commBufBytes) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->commBuf);
+        ctx->commBuf = nullptr;
+        ctx->commBufBytes = 0;
+        cudaError_t e = cudaMalloc(&ctx->commBuf, total * 3 * sizeof(float));
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(all-reduce wire buffer)");
+        ctx->commBufBytes = total * 3 * sizeof(float);
+    }
+    float* buf = (float*)ctx->commBuf;
     span_begin(ctx, KF_COMM);
+    size_t off = 0;
+    for (int s = 0; s < THB_MAX_SLOTS; ++s)
+        if (ctx->accs[s].d) {
+            pack_acc3_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->accs[s].d, ctx->accs[s].nVox, buf + 3 * off);
+            off += ctx->accs[s].nVox;
+        }
     ncclResult_t r = n.GroupStart();
-    for (int s = 0; s < THB_MAX_SLOTS && r == 0; ++s)
-        if (ctx->accs[s].d)
-            r = n.AllReduce(ctx->accs[s].d, ctx->accs[s].d, ctx->accs[s].nVox * 4, ncclFloat32, ncclSum, comm, ctx->stream);
+    if (r == 0) r = n.AllReduce(buf, buf, total * 3, ncclFloat32, ncclSum, comm, ctx->stream);
     if (r == 0) r = n.AllReduce(ctx->dO, ctx->dO, 3 * THB_MAX_SLOTS, ncclFloat64, ncclSum, comm, ctx->stream);
     if (r == 0) r = n.AllReduce(ctx->dCounter, ctx->dCounter, THB_MAX_SLOTS, ncclInt32, ncclSum, comm, ctx->stream);
     ncclResult_t r2 = n.GroupEnd();
+    off = 0;
+    for (int s = 0; s < THB_MAX_SLOTS; ++s)
+        if (ctx->accs[s].d) {
+            unpack_acc3_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(buf + 3 * off, ctx->accs[s].nVox, ctx->accs[s].d);
+            off += ctx->accs[s].nVox;
+        }
     span_end(ctx);
+    ctx->commBytesLast = total * 3 * sizeof(float);
     if (r == 0) r = r2;
     if (r != 0) return set_error(ctx, THB_E_NCCL, "ncclAllReduce failed: %s", n.GetErrorString ? n.GetErrorString(r) : "?");
-    ctx->launches++;
+    ctx->launches += 3;
     return THB_OK;
 }
 

@@ -76,6 +76,7 @@ struct PFState {
     float* ctfAttr = nullptr;    // [nPar][7]
     float pixelSize = 0.f;
     bool ctfSet = false;
+    int mode2D = 0;              // the support was built in MODE_2D (thb_pf_from_scan): von Mises operators in the phase loop
     int drawCap = 0;
     uint64_t epoch = 0;          // advances the counter-based RNG stream between calls
     float* traceR = nullptr;     // option "pf_trace": the marginal weights of every phase, [traceCap][nPar][mLR] / [..][mLT]
@@ -134,6 +135,8 @@ struct thb_ctx {
     // NCCL
     void* ncclComm = nullptr;
     int nRanks = 1, rank = 0;
+    void* commBuf = nullptr;     // wire buffer of the all-reduce: 3 floats per voxel, all slots back to back
+    size_t commBufBytes = 0, commBytesLast = 0;
 
     // accounting
     cudaEvent_t tA = nullptr, tB = nullptr;

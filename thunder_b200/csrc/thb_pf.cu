@@ -9,6 +9,7 @@
 #include <vector>
 #include "thb_context.h"
 #include "thb_pf.cuh"
+#include "thb_pf2d.cuh"
 
 namespace thb {
 
@@ -18,7 +19,7 @@ struct PFDev {
     unsigned char* active;
     int* nPhase;
     int* activeCount;
-    int nPar, mLR, mLT, mLD;
+    int nPar, mLR, mLT, mLD, mode2D;
     uint64_t seed, streamBase;
 };
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ pf::View make_view(const PFDev& d, int p)
     v.r = d.r; v.t = d.t; v.wR = d.wR; v.wT = d.wT; v.uR = d.uR; v.uT = d.uT; v.scal = d.scal;
     v.r2 = d.r2; v.t2 = d.t2; v.w2 = d.w2; v.w3 = d.w3; v.w4 = d.w4;
     v.n = d.nPar; v.p = p; v.mLR = d.mLR; v.mLT = d.mLT;
-    v.d = d.dd; v.wD = d.wD; v.uD = d.uD; v.mLD = d.mLD;
+    v.d = d.dd; v.wD = d.wD; v.uD = d.uD; v.mLD = d.mLD; v.mode2D = d.mode2D;
     return v;
 }
 
@@ -105,7 +106,8 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
         if (d.mLD > 0)
             for (int i = 0; i < d.mLD; ++i) v.UD(i) = (double)d.uDf[(size_t)p * d.mLD + i];
         pf::rank1st(v);
-        pf::cal_vari(v, g);
+        if (d.mode2D) { pf::cal_vari_R_2d(v); pf::cal_vari_T(v); }
+        else pf::cal_vari(v, g);
         pf::resample_R(v, g);
         pf::resample_T(v, g);
         if (d.mLD > 0) {     // SEARCH_TYPE_CTF: calRank1st / calVari / resample of PAR_D after those of R and T (src/Optimiser.cpp:1483-1488)
@@ -129,7 +131,8 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
         }
     }
     if (cont && a.doPre) {
-        pf::perturb_R(v, a.prePf, g);
+        if (d.mode2D) { pf::perturb_R_2d(v, a.prePf, g); pf::balance_R_2d(v); pf::norm_w(v); }
+        else pf::perturb_R(v, a.prePf, g);
         pf::perturb_T(v, a.prePf, a.transS, a.transQ, g);
         if (d.mLD > 0) {     // src/Optimiser.cpp:1193-1215
             if (a.phase < 0) pf::init_D(v, a.ctfRefineS, g);
@@ -167,16 +170,63 @@ __global__ void pf_op_kernel(PFDev d, int op, double arg, double transS, double 
     pf::Rng g;
     g.init(d.seed, d.streamBase + p, epoch);
     switch (op) {
-        case THB_PF_PERTURB_R: pf::perturb_R(v, arg, g); break;
+        case THB_PF_PERTURB_R:
+            if (d.mode2D) { pf::perturb_R_2d(v, arg, g); pf::balance_R_2d(v); pf::norm_w(v); }
+            else pf::perturb_R(v, arg, g);
+            break;
         case THB_PF_PERTURB_T: pf::perturb_T(v, arg, transS, transQ, g); break;
         case THB_PF_SET_U_KEEP_PEAK: pf::set_u_keep_peak(v, d.uRf + (size_t)p * d.mLR, d.uTf + (size_t)p * d.mLT); break;
         case THB_PF_RANK1ST: pf::rank1st(v); break;
-        case THB_PF_CALVARI: pf::cal_vari(v, g); break;
+        case THB_PF_CALVARI:
+            if (d.mode2D) { pf::cal_vari_R_2d(v); pf::cal_vari_T(v); }
+            else pf::cal_vari(v, g);
+            break;
         case THB_PF_RESAMPLE: pf::resample_R(v, g); pf::resample_T(v, g); pf::norm_w(v); break;
-        case THB_PF_BALANCE_R: pf::balance_R(v); break;
+        case THB_PF_BALANCE_R:
+            if (d.mode2D) { pf::balance_R_2d(v); pf::norm_w(v); }
+            else pf::balance_R(v);
+            break;
         case THB_PF_BALANCE_T: pf::balance_T(v); break;
         default: break;
     }
+}
+
+// one THREAD per particle (serial operators, v.lane = -1): the hand-over from the global scan is once per iteration
+struct ScanArgs {
+    int nK, nR, nT, qc, nMax, p0, pN;
+    const double* gridR; const double* gridT;
+    const float* wC; const float* wR; const float* wT;     // [nPar][nK], [nK][nPar][nR], [nK][nPar][nT]
+    double kFloor, sFloor;
+    double* scratch;        // [chunk][3 nMax]
+    int* idx;               // [chunk][mLR + mLT]
+    int* cls;               // [nPar]
+    uint64_t epoch;
+};
+__global__ void pf_from_scan_kernel(PFDev d, ScanArgs a)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = a.p0 + q;
+    if (q >= a.pN) return;
+    pf::View v = make_view(d, p);
+    v.lane = -1;
+    pf::Rng g;
+    g.init(d.seed, d.streamBase + p, a.epoch);
+    double* sc = a.scratch + (size_t)q * 3 * a.nMax;
+    int* ix = a.idx + (size_t)q * (d.mLR + d.mLT);
+    const int cls = pf::from_scan(v, g, d.mode2D, a.nK, a.nR, a.nT, a.gridR, a.qc, a.gridT, a.wC + (size_t)p * a.nK,
+                                  a.wR + (size_t)p * a.nR, (size_t)d.nPar * a.nR, a.wT + (size_t)p * a.nT, (size_t)d.nPar * a.nT, a.kFloor,
+                                  a.sFloor, sc, sc + a.nMax, sc + 2 * a.nMax, ix, ix + d.mLR);
+    a.cls[p] = cls;
+    d.active[p] = 1;
+    d.nPhase[p] = 0;
+}
+
+__global__ void pf_set_slots_kernel(const int* cls, int n, int imgBase, int* slotE, int* slotM)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (slotE) slotE[imgBase + p] = cls[p];
+    if (slotM) slotM[imgBase + p] = cls[p];
 }
 
 void pf_free(thb_ctx* ctx)
@@ -207,7 +257,7 @@ static PFDev dev_view(thb_ctx* ctx)
     d.w3 = q; q += n * mw;
     d.w4 = q;
     d.uRf = s.uR; d.uTf = s.uT; d.uDf = s.uD;
-    d.dd = s.d; d.wD = s.wD; d.uD = s.uDd; d.mLD = s.prm.mLD;
+    d.dd = s.d; d.wD = s.wD; d.uD = s.uDd; d.mLD = s.prm.mLD; d.mode2D = s.mode2D;
     d.active = s.active; d.nPhase = s.nPhase; d.activeCount = (int*)s.vari;
     d.nPar = s.nPar; d.mLR = s.prm.mLR; d.mLT = s.prm.mLT;
     d.seed = s.prm.seed; d.streamBase = s.streamBase;
@@ -297,6 +347,7 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
     if (rc) return rc;
     PFState& s = ctx->pf_;
     s.ctfSet = false;                 // the CTF constants belong to the particles of one load
+    s.mode2D = 0;
     const size_t n = nPar;
     double* din = (double*)scratch(ctx, 0, sizeof(double) * n * 11);
     if (!din) return THB_E_CUDA;
@@ -311,6 +362,70 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
     ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return THB_OK;
+}
+
+int thb_pf_from_scan(thb_ctx* ctx, int nPar, const thb_pf_params* p, int nK, int nR, int nT, const double* quat, const double* tran,
+                     const float* wC, const float* wR, const float* wT, double kFloor, double sFloor, int* clsOut)
+{
+    if (!ctx) return THB_E_ARG;
+    if (nPar <= 0 || !p || nK <= 0 || nK > THB_MAX_SLOTS || nR < 2 || nT < 2 || !quat || !tran || !wC || !wR || !wT || p->mLR < 2 || p->mLT < 2)
+        return set_error(ctx, THB_E_ARG, "pf_from_scan: bad arguments");
+    if (p->mLD != 0) return set_error(ctx, THB_E_ARG, "pf_from_scan: the CTF search starts from thb_pf_load (mLD must be 0 here)");
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        const int imgBase = ctx->pf_.imgBase;
+        if (imgBase < 0 || imgBase + nPar > ctx->stackE.nImg) return set_error(ctx, THB_E_STATE, "pf_from_scan: particles [%d,%d) exceed the E stack", imgBase, imgBase + nPar);
+    }
+    int rc = pf_alloc(ctx, nPar, *p);
+    if (rc) return rc;
+    PFState& s = ctx->pf_;
+    s.mode2D = ctx->mode2D;
+    s.ctfSet = false;
+    const int qc = ctx->mode2D ? 2 : 4;
+    const int nMax = std::max(std::max(nR, nT), 4 * nK);
+    const size_t n = nPar;
+    const size_t inBytes = sizeof(double) * ((size_t)nR * qc + (size_t)nT * 2) + sizeof(float) * (n * nK + (size_t)nK * n * nR + (size_t)nK * n * nT) + sizeof(int) * n;
+    unsigned char* din = (unsigned char*)scratch(ctx, 0, inBytes + 64);
+    if (!din) return THB_E_CUDA;
+    double* dR = (double*)din; double* dT = dR + (size_t)nR * qc;
+    float* dwC = (float*)(dT + (size_t)nT * 2); float* dwR = dwC + n * nK; float* dwT = dwR + (size_t)nK * n * nR;
+    int* dcls = (int*)(dwT + (size_t)nK * n * nT);
+    THB_CUDA(ctx, cudaMemcpyAsync(dR, quat, sizeof(double) * (size_t)nR * qc, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dT, tran, sizeof(double) * (size_t)nT * 2, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwC, wC, sizeof(float) * n * nK, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwR, wR, sizeof(float) * (size_t)nK * n * nR, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwT, wT, sizeof(float) * (size_t)nK * n * nT, cudaMemcpyHostToDevice, ctx->stream));
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(n, ((size_t)256 << 20) / (sizeof(double) * 3 * nMax + sizeof(int) * (p->mLR + p->mLT))));
+    double* dsc = (double*)scratch(ctx, 1, sizeof(double) * 3 * (size_t)nMax * chunk);
+    int* dix = (int*)scratch(ctx, 2, sizeof(int) * (size_t)(p->mLR + p->mLT) * chunk);
+    if (!dsc || !dix) return THB_E_CUDA;
+    s.epoch += 1;
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nK = nK; a.nR = nR; a.nT = nT; a.qc = qc; a.nMax = nMax;
+    a.gridR = dR; a.gridT = dT; a.wC = dwC; a.wR = dwR; a.wT = dwT; a.kFloor = kFloor; a.sFloor = sFloor;
+    a.scratch = dsc; a.idx = dix; a.cls = dcls; a.epoch = s.epoch << 20;
+    span_begin(ctx, KF_PF);
+    for (int p0 = 0; p0 < nPar; p0 += chunk) {
+        a.p0 = p0; a.pN = std::min(chunk, nPar - p0);
+        pf_from_scan_kernel<<<(a.pN + 63) / 64, 64, 0, ctx->stream>>>(dev_view(ctx), a);
+        ctx->launches++;
+    }
+    // the chosen class is the image's reference from here on (projector slot of the E-step, accumulator of the M-step)
+    pf_set_slots_kernel<<<(nPar + 255) / 256, 256, 0, ctx->stream>>>(dcls, nPar, s.imgBase, ctx->stackE.slot,
+                                                                    (ctx->stackM.slot && s.imgBase + nPar <= ctx->stackM.nImg) ? ctx->stackM.slot : nullptr);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    std::vector<int> hc(nPar);
+    THB_CUDA(ctx, cudaMemcpyAsync(hc.data(), dcls, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < nPar; ++q) {
+        ctx->stackE.hslot[(size_t)s.imgBase + q] = hc[q];
+        if ((size_t)s.imgBase + q < ctx->stackM.hslot.size()) ctx->stackM.hslot[(size_t)s.imgBase + q] = hc[q];
+        if (clsOut) clsOut[q] = hc[q];
+    }
     return THB_OK;
 }
 
@@ -385,6 +500,7 @@ static int expect_args_from_pf(thb_ctx* ctx, ExpectArgs& a)
     a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
     a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
     a.nAct = s.nPar; a.imgIdx = nullptr; a.imgBase = s.imgBase; a.active = s.active;
+    a.slotAll = -1;                  // every image against the reference of ITS slot (MODE_2D: the class thb_pf_from_scan chose)
     a.nR = s.prm.mLR; a.nT = s.prm.mLT;
     const long long n = s.nPar;
     a.quat = View3{s.r, 1, n, n * s.prm.mLR};
@@ -525,6 +641,7 @@ int thb_reconstruct_insert(thb_ctx* ctx, int mReco, int parGra, const double* of
     a.nr = View3{s.r, 1, nn, nn * s.prm.mLR};
     a.nt = View3{s.t, 1, nn, nn * s.prm.mLT};
     a.drawR = s.drawR; a.drawT = s.drawT;
+    a.mode2D = ctx->mode2D;
     if (s.prm.mLD > 0) {     // cSearch: the CTF of every draw from its own defocus factor (src/Optimiser.cpp:7171-7215)
         if (!s.ctfSet) return set_error(ctx, THB_E_STATE, "reconstruct_insert: CTF search needs thb_pf_set_ctf");
         a.nd = View3{s.d, 1, nn, 0};

@@ -128,6 +128,7 @@ struct View {
     double* w3; double* w4;                  // two more rows of max(mLR, mLT) (the shuffle's scatter)
     double* d; double* wD; double* uD;       // CTF search: mLD defocus factors (+ the top one in row mLD of d), null when mLD == 0
     int mLD;
+    int mode2D;                              // MODE_2D: rotations are unit vectors (cos, sin, 0, 0), von Mises-like statistics (thb_pf2d.cuh)
     long long n;   // stride between consecutive samples/components = number of particles
     long long p;   // particle index
     int mLR, mLT;
@@ -602,9 +603,9 @@ THB_HD void resample_T(const View& v, Rng& g)
     }
 }
 
-THB_HD double vari_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), 1.0 / 6); }
+THB_HD double vari_R(const View& v) { return v.mode2D ? v.S(S_K1) : pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), 1.0 / 6); }       // Particle::variR
 THB_HD double vari_T(const View& v) { return sqrt(v.S(S_S0) * v.S(S_S0) * v.S(S_S1) * v.S(S_S1)); }   // rho = 0
-THB_HD double compress_R(const View& v) { return pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), -1.0 / 6); }
+THB_HD double compress_R(const View& v) { return v.mode2D ? 1.0 / v.S(S_K1) : pow(v.S(S_K1) * v.S(S_K2) * v.S(S_K3), -1.0 / 6); }
 
 // Particle::load (src/Particle.cpp:401-556), in the reference's order of random draws: all ACG samples, then one sign per
 // support point, balanceWeight / calVari of the rotations, the translations (one bivariate draw each), their balanceWeight /
