@@ -376,7 +376,11 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
     try:
         ctx.set_option("expect_impl", 3)      # default: direct gather from the quad layout
+        ctx.set_option("expect_spread", 0)    # one CTA per image (what a launch of thousands of images runs)
         a = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_spread", 1)    # the same image spread over (pixel chunk, rotation group) CTAs, double table
+        s1 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_spread", 0)
         ctx.set_option("quad_oct", 0)         # 32-byte quad layout, two occupancy variants
         a3 = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_minb", 3)
@@ -401,10 +405,16 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         ctx.set_option("expect_impl", 3)
         ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_minb", 2)
+        ctx.set_option("expect_spread", -1)
     # each kernel carries its own fp32 summation error (the linear-layout kernel sums ~3000 terms sequentially)
     tol = 2e-6 * np.abs(b["logL"]).max() + 1e-4
     assert np.array_equal(a["logL"], a3["logL"]) and np.array_equal(a["logL"], a4["logL"])   # layouts / occupancy: same bits
     assert np.abs(a["logL"] - b["logL"]).max() <= 2 * tol
+    # spread kernel: same arithmetic per sample, the sum over pixels in another order (partial sums in double)
+    assert np.abs(s1["logL"] - a["logL"]).max() <= tol
+    assert np.abs(s1["base"] - a["base"]).max() <= tol
+    assert np.allclose(s1["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max())
+    assert np.allclose(s1["uR"], a["uR"], rtol=5e-3, atol=1e-6 * a["uR"].max())
     assert np.array_equal(p4["logL"], p4q["logL"])
     assert np.abs(p4["logL"] - a["logL"]).max() <= tol
     assert np.allclose(p4["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p4["base"] - a["base"]).max() <= tol
