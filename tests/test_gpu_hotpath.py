@@ -179,6 +179,55 @@ def test_expect_local_ragged_shapes(ctx, problem):
         assert np.abs(out["logL"][0] - o["logL"]).max() <= 2e-6 * np.abs(o["logL"]).max() + 1e-4, (nR, nT)
 
 
+def test_expect_lockstep_radial_order_equals_free_running(ctx, problem):
+    """lockstep launch of the several-rotations-per-lane kernel (persistent grid, tile barriers, images of one slot adjacent)
+    on the radial pixel order: more images than co-resident CTAs (several waves, the last one partial), both layouts, windows
+    0 and 3 - the same log-likelihoods and weights as the default kernel on the default pixel order and as the oracle"""
+    pb = problem
+    port, ref = _oracle()
+    rng = np.random.default_rng(404)
+    reps = 130                                    # 780 images: 2 full waves of 296 + a partial one
+    nImg, nR, nT = pb["nImg"] * reps, 125, 9
+    dat = np.tile(pb["par"]["dat"], (reps, 1)); ctf = np.tile(pb["par"]["ctf"], (reps, 1)); sig = np.tile(pb["par"]["sigRcp"], (reps, 1))
+    slot = rng.integers(0, 2, nImg).astype(np.int32)
+    q0 = np.tile(pb["par"]["quat"], (reps, 1))
+    quat = np.stack([synth.acg_cloud(q0[l], 2e-4, nR, rng) for l in range(nImg)])
+    tran = np.tile(pb["par"]["tran"], (reps, 1))[:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
+    wR = rng.uniform(0.5, 1.5, (nImg, nR)); wR /= wR.sum(1, keepdims=True)
+    wT = rng.uniform(0.5, 1.5, (nImg, nT)); wT /= wT.sum(1, keepdims=True)
+
+    def run():
+        ctx.set_expect_pixels(pb["N"], pb["pf"], pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+        for s_, v in enumerate(pb["vols"]):
+            ctx.set_volume(s_, v)
+        ctx.upload_stack(capi.STACK_EXPECT, dat, ctf, sig, slot)
+        return ctx.expect_local(quat, tran, wR, wT)
+    try:
+        a = run()
+        outs = []
+        ctx.set_option("expect_order", 1); ctx.set_option("expect_impl", 7); ctx.set_option("expect_lock", 1)
+        for oct_, win, tiles in ((1, 2, 1), (0, 0, 1), (0, 3, 2)):
+            ctx.set_option("quad_oct", oct_); ctx.set_option("expect_lock_window", win); ctx.set_option("expect_lock_tiles", tiles)
+            outs.append(run())
+    finally:
+        for k, v in (("expect_order", 0), ("expect_impl", 3), ("expect_lock", 0), ("quad_oct", 1), ("expect_lock_window", 2), ("expect_lock_tiles", 1)):
+            ctx.set_option(k, v)
+        ctx.set_expect_pixels(pb["N"], pb["pf"], pb["pixE"]["iCol"], pb["pixE"]["iRow"])
+    tol = 2e-6 * np.abs(a["logL"]).max() + 1e-4
+    for b in outs:
+        assert np.abs(b["logL"] - a["logL"]).max() <= tol
+        assert np.abs(b["base"] - a["base"]).max() <= tol
+        assert np.allclose(b["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max())
+        assert np.allclose(b["uR"], a["uR"], rtol=5e-3, atol=1e-6 * a["uR"].max())
+        assert np.allclose(b["uC"], a["uC"], rtol=5e-3)
+    assert np.array_equal(outs[1]["logL"], outs[2]["logL"])      # the barriers change timing, not arithmetic
+    l = 5
+    want = port.expect_local(pb["vols"][slot[l]], pb["pf"], pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"], dat[l], ctf[l], sig[l], quat[l],
+                             tran[l], wR[l], wT[l])
+    assert np.abs(outs[0]["logL"][l] - want["logL"]).max() <= tol
+
+
+
 def test_expect_scan_matches_local(ctx, problem):
     """global-scan shape: one shared rotation/translation set against every image of a slot"""
     pb = problem
@@ -397,6 +446,15 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         ctx.set_option("quad_oct", 0)
         p5q = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("quad_oct", 1)
+        ctx.set_option("expect_impl", 7)      # several rotations per lane (record broadcast amortised), 2 and 4, both layouts
+        ctx.set_option("expect_rpl", 2)
+        m2 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 0)
+        m2q = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("quad_oct", 1)
+        ctx.set_option("expect_rpl", 4)
+        m4 = ctx.expect_local(quat, tran, wR, wT)
+        ctx.set_option("expect_rpl", 2)
         ctx.set_option("expect_impl", 2)      # TMA-staged shared-memory box
         c = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
@@ -406,6 +464,7 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_minb", 2)
         ctx.set_option("expect_spread", -1)
+        ctx.set_option("expect_rpl", 2)
     # each kernel carries its own fp32 summation error (the linear-layout kernel sums ~3000 terms sequentially)
     tol = 2e-6 * np.abs(b["logL"]).max() + 1e-4
     assert np.array_equal(a["logL"], a3["logL"]) and np.array_equal(a["logL"], a4["logL"])   # layouts / occupancy: same bits
@@ -423,6 +482,11 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     assert np.allclose(p5["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p5["base"] - a["base"]).max() <= tol
     assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
     assert np.abs(c["logL"] - a["logL"]).max() <= tol
+    assert np.array_equal(m2["logL"], m2q["logL"])
+    for m in (m2, m4):
+        assert np.abs(m["logL"] - a["logL"]).max() <= tol
+        assert np.allclose(m["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(m["base"] - a["base"]).max() <= tol
+        assert np.allclose(m["uR"], a["uR"], rtol=5e-3, atol=1e-6 * a["uR"].max())
     for l in (0, nImg - 1):
         o = port.expect_local(pb["vols"][pb["slot"][l]], pb["pf"], pb["N"], pb["pixE"]["iCol"], pb["pixE"]["iRow"],
                               pb["par"]["dat"][l], pb["par"]["ctf"][l], pb["par"]["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
@@ -461,8 +525,11 @@ def test_pack_stack_matches_allocPreCal(ctx):
             assert np.array_equal(got["sigRcp"], sigRcpTab[group][:, pix["iSig"]])
         for l in range(nImg):
             want = port.ctf(1.32, *[float(x) for x in attr[l]], N, pix["iCol"], pix["iRow"])
-            # sinf / cosf of a phase of O(100) rad: one ulp of the phase is 3e-5 in the value (device cosf of the angle term)
-            assert np.abs(got["ctf"][l] - want).max() <= 6e-5 and np.median(np.abs(got["ctf"][l] - want)) <= 1e-7
+            # the phase reaches O(100) rad, one ulp of it is 3e-5 in the value: the packing kernel takes cos / sin through the
+            # double-precision library and rounds once, like glibc's cosf / sinf on the reference's side - all but a handful of
+            # pixels agree to the last bit or two of the result
+            err = np.abs(got["ctf"][l] - want)
+            assert err.max() <= 6e-5 and np.median(err) <= 1e-7 and np.mean(err > 5e-7) <= 2e-3, (err.max(), np.mean(err > 5e-7))
     # the packed E stack drives the kernel like an uploaded one
     ctx.set_volume(0, synth.padded_ft(synth.phantom(N, 6, seed=9), pf)); ctx.set_volume(1, synth.padded_ft(synth.phantom(N, 6, seed=8), pf))
     ctx.stack_reserve(capi.STACK_EXPECT, nImg)

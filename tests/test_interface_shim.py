@@ -276,3 +276,92 @@ def test_local_search_through_the_reference_protocol(shim):
     shim.thbi_ExpectLocalBatch(0, _ptr(volc), N * pf, pf, N, _ptr(iCol), _ptr(iRow), P, _ptr(dat), _ptr(ctf), _ptr(sig), nImg, nR, nT,
                                _ptr(q2), _ptr(t2), _ptr(r2), _ptr(s2), _ptr(uC), _ptr(uR), _ptr(uT), _ptr(bl))
     assert np.allclose(uR, wR[:, ph], rtol=2e-4, atol=1e-30) and np.allclose(uT, wT[:, ph], rtol=2e-4, atol=1e-30)
+
+
+SEAM_EXE = ROOT / "oracle" / "_ref" / "seam_insertI"
+
+
+def _run_seam(tmp_path, N, pf, pixM, datM, ctfM, w, offS, nr, nt, nc=None, sym=None):
+    nImg, PM = datM.shape
+    mReco = nr.shape[1]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        np.array([N, N, pf, PM, mReco, nImg, int(nc is not None), 0], np.int32).tofile(f)
+        np.array([1.32], np.float32).tofile(f)
+        for k in ("iColPad", "iRowPad", "iPxl", "iSig"):
+            np.ascontiguousarray(pixM[k], np.int32).tofile(f)
+        np.ascontiguousarray(datM, np.complex64).tofile(f); np.ascontiguousarray(ctfM, np.float32).tofile(f)
+        np.ascontiguousarray(w, np.float32).tofile(f); np.ascontiguousarray(offS, np.float64).tofile(f)
+        np.ascontiguousarray(nr, np.float64).tofile(f); np.ascontiguousarray(nt, np.float64).tofile(f)
+        if nc is not None:
+            np.ascontiguousarray(nc, np.int32).tofile(f)
+    cmd = [os.fspath(SEAM_EXE), os.fspath(fin), os.fspath(fout)] + ([sym] if sym else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-800:], r.stderr[-1500:])
+    raw = np.fromfile(fout, np.uint8)
+    m = int(raw[:4].view(np.int32)[0])
+    nVox = m * m * (m // 2 + 1)
+    o = 4
+    F = raw[o:o + 8 * nVox].view(np.complex64).reshape(m, m, m // 2 + 1); o += 8 * nVox
+    T = raw[o:o + 4 * nVox].view(np.float32).reshape(m, m, m // 2 + 1); o += 4 * nVox
+    O = raw[o:o + 24].view(np.float64); o += 24
+    return dict(F=F, T=T, O=O, counter=int(raw[o:o + 4].view(np.int32)[0]), m=m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sym", [None, "C4"])
+def test_reference_reconstructor_insertI_runs_on_the_shim(tmp_path, sym):
+    """THE REFERENCE'S OWN Reconstructor::insertI (and prepareTFG), compiled from src/Reconstructor.cpp with GPU_INSERT and this
+    repository's Interface.h, linked against libthb_interface.so (oracle/build_ref.sh -> oracle/_ref/seam_insertI), against the
+    reference's CPU path Reconstructor::insertP / insertDir / prepareTF / symmetrize on the same draws"""
+    from oracle import refapi
+    from oracle import portapi as port
+    if not SEAM_EXE.exists() or not refapi.available():
+        pytest.skip("oracle/_ref/seam_insertI not built (oracle/build_ref.sh needs the reference tree)")
+    N, pf = 32, 2
+    rng = np.random.default_rng(21)
+    pixM = port.pixel_list(N, pf, 13.0, 0.0)
+    PM = len(pixM["iCol"])
+    nImg, mReco = 6, 7
+    datM = (rng.normal(size=(nImg, PM)) + 1j * rng.normal(size=(nImg, PM))).astype(np.complex64)
+    ctfM = rng.uniform(-1, 1, (nImg, PM)).astype(np.float32)
+    nr = synth.random_quats(nImg * mReco, rng).reshape(nImg, mReco, 4)
+    nt = rng.normal(scale=2.0, size=(nImg, mReco, 2))
+    w = np.full(nImg, 1.0 / mReco, np.float32)
+    offS = rng.normal(scale=0.5, size=(nImg, 2))
+    got = _run_seam(tmp_path, N, pf, pixM, datM, ctfM, w, offS, nr, nt, sym=sym)
+    R = refapi.Reconstructor(N, N, pf)
+    assert got["m"] == R.pad_size()
+    R.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+    R.insert_loop(datM, ctfM, w, offS, nr, nt, pixM["iCol"], pixM["iRow"], N)
+    if sym:
+        R.prepareTF()               # normalisation by 1 / Re T[0] (no symmetry object attached: the reference skips that part)
+        R.symmetrize(sym)           # symmetrizeT / symmetrizeF with the point group
+    want = R.get()
+    rel = lambda a, b: np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel())
+    if sym is None:
+        assert rel(got["F"], want["F"]) <= 1e-6 and rel(got["T"], want["T"]) <= 1e-6
+        assert np.allclose(got["O"], want["O"], rtol=1e-10, atol=1e-10) and got["counter"] == want["counter"] == nImg * mReco
+    else:
+        m = got["m"]
+        r = R.max_radius() * pf + 1
+        kk, jj, ii = np.meshgrid(np.fft.fftfreq(m, 1 / m), np.fft.fftfreq(m, 1 / m), np.arange(m // 2 + 1), indexing="ij")
+        edge = (ii * ii + jj * jj + kk * kk) == r * r      # voxels on the cut radius: see test_device_symmetrize
+        assert np.abs(got["F"] - want["F"])[~edge].max() <= 4e-6 * np.abs(want["F"]).max()
+        assert np.abs(got["T"] - want["T"])[~edge].max() <= 4e-6 * np.abs(want["T"]).max()
+    R.close()
+
+
+def test_reference_reconstructor_object_links_against_the_shim():
+    """CPU part of the drop-in proof: the seam executable holds the reference's Reconstructor::insertI / prepareTFG object code
+    (compiled from the reference's source with GPU_INSERT), and every seam function it calls is an export of libthb_interface.so"""
+    if not SEAM_EXE.exists():
+        pytest.skip("oracle/_ref/seam_insertI not built (oracle/build_ref.sh needs the reference tree)")
+    defined = subprocess.check_output(["nm", "-C", "--defined-only", os.fspath(SEAM_EXE)]).decode()
+    assert "Reconstructor::insertI(" in defined and "Reconstructor::prepareTFG(" in defined
+    undef = [l.split()[-1] for l in subprocess.check_output(["nm", "-u", os.fspath(SEAM_EXE)]).decode().splitlines()
+             if re.search(r"_Z\d+(InsertFT|PrepareTF)", l)]
+    have = set(l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", os.fspath(LIB)]).decode().splitlines())
+    assert len(undef) >= 2, undef
+    for sym in undef:
+        assert sym in have, sym

@@ -14,6 +14,7 @@
 #include "thb_expect5.cuh"
 #include "thb_insert2.cuh"
 #include "thb_expect6.cuh"
+#include "thb_expect7.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -184,7 +185,7 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     }
     // a handful of images (the reference's one-image-at-a-time seam, the tail of an adaptive E-step): one CTA per image would
     // leave the chip idle - spread every image over (pixel chunk, rotation group) CTAs instead (thb_expect6.cuh)
-    if (ctx->expectImpl == 3 && (ctx->expectSpread == 1 || (ctx->expectSpread < 0 && a.nAct * 4 <= ctx->smCount))) {
+    if ((ctx->expectImpl == 3 || ctx->expectImpl == 7) && (ctx->expectSpread == 1 || (ctx->expectSpread < 0 && a.nAct * 4 <= ctx->smCount))) {
         const int nRT = a.nR * a.nT;
         double* table = (double*)scratch(ctx, 13, sizeof(double) * (size_t)a.nAct * nRT);
         a.work = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * nRT);
@@ -208,7 +209,7 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     }
     // more translations than one pass of the local-search kernel carries (the scans: nT = 30 in demo_2D.json): the variant
     // with 15 per pass halves the number of passes over the gather
-    const bool wideT = ctx->expectImpl == 3 && a.nT > E_TC;
+    const bool wideT = (ctx->expectImpl == 3 || ctx->expectImpl == 7) && a.nT > E_TC;
     const int tc = wideT ? E3_TC_SCAN : E_TC;
     const bool single = a.nR <= E3_ROTS && a.nT <= tc;
     if (!single) {
@@ -218,7 +219,38 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     const size_t smem = (ctx->expectImpl == 5 ? E5_SMEM_BYTES : wideT ? E3_TILE * sizeof(PixelRecT<E3_TC_SCAN>) : E3_SMEM_BYTES) +
                         (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
-    if (ctx->expectImpl == 5) {
+    if (ctx->expectImpl == 7 && single && !wideT && !ctx->mode2D && a.vdim < 65536) {
+        // several rotations per lane (thb_expect7.cuh): the record broadcast is amortised over RPL samples
+        const int rpl = ctx->expectRpl >= 4 ? 4 : 2;
+        const size_t sm7 = rpl == 4 ? e7_smem_bytes<4>(a.nR, a.nT) : e7_smem_bytes<2>(a.nR, a.nT);
+        void (*kern)(const ExpectArgs) = rpl == 4 ? (ctx->quadOct ? expect_multi_kernel<4, true> : expect_multi_kernel<4, false>)
+                                                  : (ctx->quadOct ? expect_multi_kernel<2, true> : expect_multi_kernel<2, false>);
+        THB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm7));
+        int grid = a.nAct;
+        a.order = nullptr; a.lockCtr = nullptr; a.lockTiles = 0; a.lockWindow = 0;
+        if (ctx->expectLock) {
+            // lockstep launch: a persistent grid of co-resident CTAs walks the images wave by wave with a barrier every few pixel
+            // tiles; the images of one slot are adjacent in the launch order so that a wave reads ONE volume
+            int occ = 0;
+            THB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, E3_THREADS, sm7));
+            grid = std::max(1, std::min(a.nAct, occ * ctx->smCount));
+            int* dOrder = (int*)scratch(ctx, 14, sizeof(int) * (size_t)a.nAct + 16);
+            if (!dOrder) return THB_E_CUDA;
+            unsigned int* dCtr = reinterpret_cast<unsigned int*>(dOrder + a.nAct + ((4 - (a.nAct & 3)) & 3));
+            if (!a.imgIdx && a.slotOfImg && (size_t)(a.imgBase + a.nAct) <= ctx->stackE.hslot.size()) {
+                std::vector<int>& ord = ctx->expectOrderHost;
+                ord.resize(a.nAct);
+                for (int i = 0; i < a.nAct; ++i) ord[i] = i;
+                const int* hs = ctx->stackE.hslot.data() + a.imgBase;
+                std::stable_sort(ord.begin(), ord.end(), [&](int l, int r) { return hs[l] < hs[r]; });
+                THB_CUDA(ctx, cudaMemcpyAsync(dOrder, ord.data(), sizeof(int) * (size_t)a.nAct, cudaMemcpyHostToDevice, ctx->stream));
+                a.order = dOrder;
+            }
+            THB_CUDA(ctx, cudaMemsetAsync(dCtr, 0, sizeof(unsigned int), ctx->stream));
+            a.lockCtr = dCtr; a.lockTiles = ctx->expectLockTiles; a.lockWindow = ctx->expectLockWindow;
+        }
+        kern<<<grid, E3_THREADS, sm7, ctx->stream>>>(a);
+    } else if (ctx->expectImpl == 5) {
         if (ctx->mode2D)
             expect_pix_kernel<false, true><<<a.nAct, E5_THREADS, smem, ctx->stream>>>(a);
         else if (ctx->quadOct)
@@ -435,7 +467,12 @@ int thb_create(thb_ctx** out, int device)
     thb_ctx* ctx = new thb_ctx();
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
-    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(5, atoi(e)));
+    if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(7, atoi(e)));
+    if (const char* e = getenv("THB_EXPECT_RPL")) ctx->expectRpl = atoi(e) >= 4 ? 4 : 2;
+    if (const char* e = getenv("THB_EXPECT_ORDER")) ctx->expectOrder = atoi(e) == 1;
+    if (const char* e = getenv("THB_EXPECT_LOCK")) ctx->expectLock = atoi(e) != 0;
+    if (const char* e = getenv("THB_EXPECT_LOCK_TILES")) ctx->expectLockTiles = std::max(1, atoi(e));
+    if (const char* e = getenv("THB_EXPECT_LOCK_WINDOW")) ctx->expectLockWindow = std::max(0, atoi(e));
     if (const char* e = getenv("THB_QUAD_BRICK")) ctx->quadBrick = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("THB_QUAD_OCT")) ctx->quadOct = atoi(e) != 0;
     if (const char* e = getenv("THB_SORT_ROT")) ctx->sortRot = atoi(e) != 0;
@@ -539,8 +576,32 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
 {
     if (!ctx || !key) return THB_E_ARG;
     if (!strcmp(key, "expect_impl")) {
-        if (value < 1 || value > 5) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 .. 5");
+        if (value < 1 || value > 7 || value == 6) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 .. 5 or 7");
         ctx->expectImpl = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_order")) {    // pixel order of the E stack: 0 = 8x8 blocks, 1 = radial; at the next thb_set_expect_pixels
+        if (value < 0 || value > 1) return set_error(ctx, THB_E_ARG, "set_option: expect_order must be 0 or 1");
+        ctx->expectOrder = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_lock")) {     // lockstep launch of expect_impl 7 (persistent grid, tile barriers)
+        ctx->expectLock = value != 0;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_lock_tiles")) {
+        if (value < 1) return set_error(ctx, THB_E_ARG, "set_option: expect_lock_tiles must be >= 1");
+        ctx->expectLockTiles = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_lock_window")) {
+        if (value < 0) return set_error(ctx, THB_E_ARG, "set_option: expect_lock_window must be >= 0");
+        ctx->expectLockWindow = value;
+        return THB_OK;
+    }
+    if (!strcmp(key, "expect_rpl")) {      // rotations per lane of expect_impl 7
+        if (value != 2 && value != 4) return set_error(ctx, THB_E_ARG, "set_option: expect_rpl must be 2 or 4");
+        ctx->expectRpl = value;
         return THB_OK;
     }
     if (!strcmp(key, "tile_w") || !strcmp(key, "tile_h")) {   // takes effect at the next thb_set_expect_pixels
@@ -679,6 +740,30 @@ static void blocked_order(int n, const int* a, const int* b, int unit, std::vect
     }
 }
 
+// Radial order (option "expect_order" = 1): ring by ring (rounded radius), along the ring by angle, alternating direction from
+// ring to ring.  The samples of a pixel at radius rho fall on the sphere of radius pf * rho of the volume whatever the
+// orientation, so CTAs that walk their images in this order IN STEP (thb_expect7.cuh, lockstep launch) read one thin spherical
+// shell of the volume at a time - a working set the L2 holds.
+static void radial_order(int n, const int* a, const int* b, int unit, std::vector<int>& perm, std::vector<long long>* blockOf)
+{
+    std::vector<long long> key(n);
+    for (int i = 0; i < n; ++i) {
+        const double x = a[i] / unit, y = b[i] / unit;
+        const long long ring = llround(sqrt(x * x + y * y) * 2.0);           // half-pixel rings
+        const double ang = atan2(y, x);                                     // [-pi, pi]
+        long long aq = llround((ang + 3.2) * 1e6);
+        if (ring & 1) aq = 7000000 - aq;
+        key[i] = (ring << 32) | aq;
+    }
+    perm.resize(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int l, int r) { return key[l] < key[r]; });
+    if (blockOf) {
+        blockOf->resize(n);
+        for (int i = 0; i < n; ++i) (*blockOf)[i] = i / 64;                  // tiles of the staged kernel: runs of 64 pixels
+    }
+}
+
 // tiles of the blocked order: maximal runs of pixels of one 8x8 block, with the rectangle they span
 static void build_tiles(int n, const int* a, const int* b, int unit, int pf, const std::vector<int>& perm,
                         const std::vector<long long>& blockOf, std::vector<TileDesc>& tiles)
@@ -733,6 +818,8 @@ static int upload_pixels(thb_ctx* ctx, int pf, int nPxl, const int* a, const int
     std::vector<long long> blockOf;
     if (segs)
         rowmajor_order(nPxl, a, b, padded ? pf : 1, perm, *segs);
+    else if (tiles && ctx->expectOrder == 1)
+        radial_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf);
     else
         blocked_order(nPxl, a, b, padded ? pf : 1, perm, &blockOf, BW, BH);
     if (tiles) build_tiles(nPxl, a, b, padded ? pf : 1, pf, perm, blockOf, *tiles);
@@ -768,7 +855,9 @@ int thb_set_expect_pixels(thb_ctx* ctx, int N, int pf, int nPxl, const int* iCol
     ctx->nTilesE = (int)tiles.size();
     THB_CUDA(ctx, cudaMalloc(&ctx->tilesE, sizeof(TileDesc) * tiles.size()));
     THB_CUDA(ctx, cudaMemcpy(ctx->tilesE, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice));
-    if (ctx->nPxlE != nPxl) free_stack(ctx->stackE);   // a resident stack belongs to one pixel list
+    // a resident stack belongs to one pixel list AND one pixel order (its arrays are stored in that order)
+    if (ctx->nPxlE != nPxl || ctx->expectOrderBuilt != ctx->expectOrder) free_stack(ctx->stackE);
+    ctx->expectOrderBuilt = ctx->expectOrder;
     cudaFree(ctx->freqE);                              // ... and so does the frequency table of the CTF search
     ctx->freqE = nullptr;
     ctx->N = N; ctx->pf = pf; ctx->nPxlE = nPxl;

@@ -88,7 +88,7 @@ struct PFState {
 
 }  // namespace thb
 
-#define THB_N_SCRATCH 14
+#define THB_N_SCRATCH 16
 struct thb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -115,6 +115,13 @@ struct thb_ctx {
     int statsOn = 0;
     int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
     int expectImpl = 3;          // 3: direct gather from the quad layout (default), 2: TMA-staged box, 1: direct gather, linear layout
+    int expectRpl = 2;           // option "expect_rpl": rotations per lane of expect_impl 7 (2 or 4)
+    int expectOrder = 0;         // option "expect_order": pixel order of the E stack, 0 = 8x8 blocks, 1 = radial (rings)
+    int expectOrderBuilt = 0;    // the order the current E pixel list (and the resident E stack) was built with
+    int expectLock = 0;          // option "expect_lock": lockstep launch of expect_impl 7
+    int expectLockTiles = 1;     // option "expect_lock_tiles": one barrier every so many tiles of 128 pixels
+    int expectLockWindow = 2;    // option "expect_lock_window": barriers a CTA may run ahead of the slowest one
+    std::vector<int> expectOrderHost;   // launch order of the lockstep launch (images of one slot adjacent)
     int quadBrick = 2;           // log2 brick edge of the quad layout (option "quad_brick"; 4x4x4 bricks measured best)
     int quadOct = 1;             // option "quad_oct": whole trilinear cell in one 64-byte element (8x volume bytes; default,
                                  // falls back to the 32-byte quad when HBM is short)

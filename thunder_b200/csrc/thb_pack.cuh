@@ -13,13 +13,18 @@ struct CtfAttr7 { float voltage, defocusU, defocusV, theta, Cs, ac, phaseShift; 
 // CTF() of src/CTF.cpp:118-151 for one pixel (iCol, iRow), split into what does not depend on the defocus values (the CTF search of
 // the insert evaluates it once per draw with defocusU d, defocusV d) and the rest; same float / double mix and unfused order
 struct CtfPixel { float u2, u4, c2; };     // |k|^2, |k|^4 in physical units, cos(2 (angle - theta))
+// PRECISE: cos / sin through the double-precision library, rounded once - what glibc's cosf / sinf (correctly rounded in all but
+// rare cases) give the reference; CUDA's cosf / sinf are 1 - 2 ulp off, and one ulp of cos(2 angle) moves a phase of hundreds of
+// radians by 1e-5.  The packing kernel (once per image and iteration) uses it; the per-sample CTF of the insert does not.
+template <bool PRECISE = false>
 __device__ __forceinline__ CtfPixel ctf_pixel(int iCol, int iRow, float pixelSize, int N, float theta)
 {
     const float u = (float)hypot((double)((float)iCol / (pixelSize * (float)N)), (double)((float)iRow / (pixelSize * (float)N)));
     const float angle = (float)(atan2((double)iRow, (double)iCol) - (double)theta);
     const double u2d = (double)u * u;
     CtfPixel c;
-    c.u2 = (float)u2d; c.u4 = (float)(u2d * u2d); c.c2 = cosf(__fmul_rn(2.0f, angle));
+    c.u2 = (float)u2d; c.u4 = (float)(u2d * u2d);
+    c.c2 = PRECISE ? (float)cos((double)__fmul_rn(2.0f, angle)) : cosf(__fmul_rn(2.0f, angle));
     return c;
 }
 struct CtfConst { float K1, K2, w1, w2, phaseShift; };
@@ -34,11 +39,13 @@ __device__ __forceinline__ CtfConst ctf_const(float voltage, float Cs, float ac,
     k.phaseShift = phaseShift;
     return k;
 }
+template <bool PRECISE = false>
 __device__ __forceinline__ float ctf_eval(const CtfPixel& c, const CtfConst& k, float dU, float dV)
 {
     const float defocus = __fmul_rn(-__fadd_rn(__fadd_rn(dU, dV), __fmul_rn(__fadd_rn(dU, -dV), c.c2)), 0.5f);
     const float ki = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(k.K1, defocus), c.u2), __fmul_rn(k.K2, c.u4)), -k.phaseShift);
-    return __fadd_rn(__fmul_rn(-k.w1, sinf(ki)), __fmul_rn(k.w2, cosf(ki)));
+    const float sn = PRECISE ? (float)sin((double)ki) : sinf(ki), cs = PRECISE ? (float)cos((double)ki) : cosf(ki);
+    return __fadd_rn(__fmul_rn(-k.w1, sn), __fmul_rn(k.w2, cs));
 }
 
 static __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_t imgStride, const int4* __restrict__ pix,
@@ -58,8 +65,8 @@ static __global__ void pack_stack_kernel(const float2* __restrict__ imgFT, size_
         ddat[d] = imgFT[(size_t)l * imgStride + iPxl[s]];
         if (dsig) dsig[d] = sigRcpTab[(size_t)g * nRing + iSig[s]];
         // the phase reaches hundreds of radians: the reference's unfused operation order is kept (ctf_eval), one ulp of ki is
-        // already 3e-5 in the CTF value
-        dctf[d] = ctf_eval(ctf_pixel(c.z, c.w, pixelSize, N, a.theta), k, a.defocusU, a.defocusV);
+        // already 3e-5 in the CTF value - hence the correctly rounded cos / sin here
+        dctf[d] = ctf_eval<true>(ctf_pixel<true>(c.z, c.w, pixelSize, N, a.theta), k, a.defocusU, a.defocusV);
     }
 }
 

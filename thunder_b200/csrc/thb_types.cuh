@@ -82,6 +82,12 @@ struct ExpectArgs {
     View3 dpar, wD;         // [nAct][nD]  defocus factors and their prior weights
     const float* ctfK;      // [nAct][4]   K1, K2, phaseShift, amplitudeContrast of the image
     float* uD;              // [nAct][nD]
+    // ---- lockstep launch (thb_expect7.cuh): a persistent grid walks the images wave by wave, all CTAs on the same pixel tiles at
+    // the same time, so that the cells the chip reads at any moment are one thin spherical shell of the volume (pixels in radial order)
+    const int* order;       // [nAct] launch position -> particle (images of one slot adjacent), or null
+    unsigned int* lockCtr;  // arrival counter of the tile barriers (zeroed before the launch), null = free-running
+    int lockTiles;          // one barrier every lockTiles tiles
+    int lockWindow;         // a CTA may run this many barriers ahead of the slowest one
 };
 
 struct InsertArgs {

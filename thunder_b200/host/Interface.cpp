@@ -437,6 +437,33 @@ void ExpectLocalBatch(int gpuIdx, Complex* volume, int vdim, int pf, int idim, c
     CHK(ctx, thb_expect_local(ctx, imgNum, nullptr, nR, nT, quat, tran, wRprior, wTprior, wR, wT, wC, baseL, nullptr));
 }
 
+void PrepareTF(int gpuIdx, Complex* F3D, Complex* T3D, int vdim, double* symMat, int nSymmetryElement, int maxRadius, int pf)
+{
+    thb_ctx* ctx = thbContext(gpuIdx);
+    const size_t nVox = (size_t)(vdim / 2 + 1) * vdim * vdim;
+    // normalisation first, as Reconstructor::prepareTF orders it (src/Reconstructor.cpp:1056-1091): sf = 1 / Re T[0]
+    const float sf = 1.0f / T3D[0].dat[0];
+    std::vector<float> F(2 * nVox), T(nVox);
+    for (size_t i = 0; i < nVox; ++i) {
+        F[2 * i] = F3D[i].dat[0] * sf;
+        F[2 * i + 1] = F3D[i].dat[1] * sf;
+        T[i] = T3D[i].dat[0] * sf;
+    }
+    if (nSymmetryElement > 0) {
+        CHK(ctx, thb_set_mode(ctx, THB_MODE_3D));
+        CHK(ctx, thb_reco_alloc(ctx, 0, vdim));
+        CHK(ctx, thb_reco_upload(ctx, 0, F.data(), T.data()));
+        CHK(ctx, thb_symmetrize(ctx, 0, nSymmetryElement, symMat, (double)(maxRadius * pf + 1)));
+        CHK(ctx, thb_reco_download(ctx, 0, F.data(), T.data(), nullptr, nullptr, 0));
+    }
+    for (size_t i = 0; i < nVox; ++i) {
+        F3D[i].dat[0] = F[2 * i];
+        F3D[i].dat[1] = F[2 * i + 1];
+        T3D[i].dat[0] = T[i];
+        T3D[i].dat[1] = 0.0f;
+    }
+}
+
 void InsertFT(Complex* F3D, Complex* T3D, int vdim, double* O3D, int* counter, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP,
               void* ctfaData, double* offS, RFLOAT* w, double* nR, double* nT, double* nD, int* nC, const int* iCol, const int* iRow,
               RFLOAT pixelSize, bool cSearch, int opf, int npxl, int mReco, int idim, int dimSize, int imgNum)

@@ -142,6 +142,12 @@ void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, Complex* da
                int* nC, double* nR, double* nT, double* nD, void* ctfaData, const int* iCol, const int* iRow, RFLOAT pixelSize,
                bool cSearch, int nk, int opf, int npxl, int mReco, int idim, int vdim, int imgNum);
 
+// ---- a15 through the seam: PrepareTF (gpu/interface/Interface.h:320-326, caller Reconstructor::prepareTFG,
+// src/Reconstructor.cpp:1019-1052): normalise F and T by sf = 1 / Re T[0] and add their symmetry copies
+// (symMat[nSymmetryElement][9], column-major dmat33 as Symmetry::get(L, R, i) returns them; rotated positions inside
+// maxRadius * pf + 1), in place on the caller's host volumes.  T3D is the reference's COMPLEX volume (real part used).
+void PrepareTF(int gpuIdx, Complex* F3D, Complex* T3D, int vdim, double* symMat, int nSymmetryElement, int maxRadius, int pf);
+
 #ifdef THB_WITH_THUNDER
 #include "mpi.h"
 #include "Volume.h"
@@ -161,6 +167,10 @@ inline void InsertFT(Volume& F3D, Volume& T3D, double* O3D, int* counter, MPI_Co
 {
     InsertFT(&F3D[0], &T3D[0], (int)F3D.nSlcFT(), O3D, counter, datP, ctfP, sigRcpP, (void*)ctfaData, offS, w, nR, nT, nD,
              nC, iCol, iRow, pixelSize, cSearch, opf, npxl, mReco, idim, dimSize, imgNum);
+}
+inline void PrepareTF(int gpuIdx, Volume& F3D, Volume& T3D, double* symMat, int nSymmetryElement, int maxRadius, int pf)
+{
+    PrepareTF(gpuIdx, &F3D[0], &T3D[0], (int)T3D.nSlcFT(), symMat, nSymmetryElement, maxRadius, pf);
 }
 inline void InsertI2D(Complex* F2D, RFLOAT* T2D, double* O2D, int* counter, MPI_Comm&, MPI_Comm&, Complex* datP, RFLOAT* ctfP,
                       RFLOAT* sigRcpP, RFLOAT* w, double* offS, int* nC, double* nR, double* nT, double* nD, CTFAttr* ctfaData,

@@ -30,15 +30,26 @@ tran = par["tran"][:, None, :] + rng.normal(scale=0.5, size=(nImg, nT, 2))
 wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
 ctx.enable_timing(True)
 ctx.set_option("stats", 1)
-for it in range(4):
-    ctx.kernel_ms(capi.KF_EXPECT, reset=True)
-    out = ctx.expect_local(quat, tran, wR, wT, want_logL=False)
-    ms, n = ctx.kernel_ms(capi.KF_EXPECT, reset=True)
-    bytesE = nImg * (P * 16 + nR * P * 64.0)
-    print(f"E: {ms:.2f} ms  {nImg / ms * 1e3:.0f} particle-phases/s  alg {bytesE / ms / 1e6:.0f} GB/s  "
-          f"{nImg * nR * P / ms / 1e6:.1f} G pixel-rot/s", flush=True)
-    if it == 0:
-        print("   staging:", ctx.expect_stats(), flush=True)
+# KBENCH_IMPLS = comma-separated E kernels to time, "impl[:rpl]" (default: the context's own)
+import os
+variants = [v for v in os.environ.get("KBENCH_IMPLS", "").split(",") if v] or [None]
+for var in variants:
+    if var:
+        impl, _, rpl = var.partition(":")
+        ctx.set_option("expect_impl", int(impl))
+        if rpl:
+            ctx.set_option("expect_rpl", int(rpl))
+    for it in range(4):
+        ctx.kernel_ms(capi.KF_EXPECT, reset=True)
+        out = ctx.expect_local(quat, tran, wR, wT, want_logL=False)
+        ms, n = ctx.kernel_ms(capi.KF_EXPECT, reset=True)
+        bytesE = nImg * (P * 16 + nR * P * 64.0)
+        print(f"E[{var or 'default'}] k={kconc:g}: {ms:.2f} ms  {nImg / ms * 1e3:.0f} particle-phases/s  alg {bytesE / ms / 1e6:.0f} GB/s  "
+              f"{nImg * nR * P / ms / 1e6:.1f} G pixel-rot/s", flush=True)
+        if it == 0 and not var:
+            print("   staging:", ctx.expect_stats(), flush=True)
+if os.environ.get("KBENCH_NO_INSERT"):
+    sys.exit(0)
 for s in (0, 1):
     ctx.reco_alloc(s, N * pf)
 nr = quat[:, rng.integers(0, nR, mReco)]; nt = tran[:, rng.integers(0, nT, mReco)]
