@@ -128,6 +128,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def e_kernel_label():
+    """name of the E kernel the library runs by default (the A/B switches are environment variables, see thb_create)"""
+    impl = int(os.environ.get("THB_EXPECT_IMPL", "7"))
+    if impl == 7:
+        lock = os.environ.get("THB_EXPECT_LOCK", "1") != "0"
+        return ("expect_multi_kernel<2,1> (fused slice extraction + likelihood, two rotations per lane, whole-cell \"oct\" volume layout"
+                + (", persistent lockstep launch on the radial pixel order: all CTAs read one spherical shell of the volume at a time, "
+                   "so the gather is served by the L2 and the algorithmic bytes exceed what DRAM carries - see traffic)" if lock else ")"))
+    return f"expect_impl {impl} (see DESIGN.md section 4)"
+
+
 def ncu_traffic(nPxlE, mLR):
     """per-particle-phase DRAM traffic of the dominant kernel from the committed ncu capture, if any"""
     p = ROOT / "profiles" / "traffic.json"
@@ -691,7 +702,7 @@ def main():
         alg_bytes = B * (PE * 16 + args.mlr * PE * 64.0)           # B_E per particle-phase x particles per launch
         achieved = alg_bytes / (e_ms / max(e_n, 1) / 1e3) / 1e9 if e_n else None
         tr = ncu_traffic(PE, args.mlr)
-        roof = {"bound": "hbm", "kernel": "expect_direct_kernel<2,1> (fused slice extraction + likelihood, whole-cell \"oct\" volume layout)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": e_kernel_label(), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                 "traffic": (tr["dram_bytes_per_particle_phase"] * B if tr else None),
                 "traffic_source": (tr["source"] if tr else None),

@@ -101,9 +101,14 @@ int64_t thb_launch_count(thb_ctx* ctx, int reset);
  * which = 0 expect, 1 insert, 2 particle filter, 3 pack/unpack, 4 allreduce ; launches returned in *n */
 double thb_kernel_ms(thb_ctx* ctx, int which, int64_t* n, int reset);
 int thb_enable_timing(thb_ctx* ctx, int on);
-/* tuning switches (development / A-B measurement): key "expect_impl": 3 = direct gather from the cell layout (default),
+/* tuning switches (development / A-B measurement).  key "expect_impl": 7 = several rotations per lane, lockstep launch on the
+ * radial pixel order (default; 0 selects the default), 3 = direct gather from the cell layout, one rotation per lane,
  * 2 = TMA-staged box, 1 = direct gather from the linear layout, 4 / 5 = paired-lane / pixels-on-lanes variants;
- * "quad_oct", "quad_brick", "sort_rot", "expect_minb", "insert_impl", "stats": see DESIGN.md.  Unknown key -> THB_E_ARG. */
+ * "expect_rpl" (2 | 4 rotations per lane), "expect_order" (0 = 8x8 blocks, 1 = radial; takes effect at the next
+ * thb_set_expect_pixels and drops the resident E stack), "expect_lock" / "expect_lock_tiles" / "expect_lock_window" (tile
+ * barriers of the lockstep launch), "scan_templates" (scans project each shared rotation once per launch), "pf_stage" (particle
+ * filter state staged in shared memory), "quad_oct", "quad_brick", "sort_rot", "expect_minb", "expect_spread", "insert_impl",
+ * "insert_slab_mb", "stats": see DESIGN.md.  Unknown key -> THB_E_ARG. */
 int thb_set_option(thb_ctx* ctx, const char* key, int value);
 /* staging counters of the E kernel since the last reset (enable with option "stats" = 1): tiles, tiles with a
  * shared-memory box, sum of margins, staged elements, (rotation,tile) pairs on the L1/L2 path, all pairs,

@@ -203,14 +203,15 @@ def test_expect_lockstep_radial_order_equals_free_running(ctx, problem):
         ctx.upload_stack(capi.STACK_EXPECT, dat, ctf, sig, slot)
         return ctx.expect_local(quat, tran, wR, wT)
     try:
-        a = run()
+        ctx.set_option("expect_order", 0); ctx.set_option("expect_impl", 3); ctx.set_option("expect_lock", 0)
+        a = run()                                  # one rotation per lane, 8x8-block pixel order, one CTA per image
         outs = []
         ctx.set_option("expect_order", 1); ctx.set_option("expect_impl", 7); ctx.set_option("expect_lock", 1)
         for oct_, win, tiles in ((1, 2, 1), (0, 0, 1), (0, 3, 2)):
             ctx.set_option("quad_oct", oct_); ctx.set_option("expect_lock_window", win); ctx.set_option("expect_lock_tiles", tiles)
             outs.append(run())
     finally:
-        for k, v in (("expect_order", 0), ("expect_impl", 3), ("expect_lock", 0), ("quad_oct", 1), ("expect_lock_window", 2), ("expect_lock_tiles", 1)):
+        for k, v in (("expect_order", 1), ("expect_impl", 0), ("expect_lock", 1), ("quad_oct", 1), ("expect_lock_window", 1), ("expect_lock_tiles", 1)):
             ctx.set_option(k, v)
         ctx.set_expect_pixels(pb["N"], pb["pf"], pb["pixE"]["iCol"], pb["pixE"]["iRow"])
     tol = 2e-6 * np.abs(a["logL"]).max() + 1e-4
@@ -237,7 +238,15 @@ def test_expect_scan_matches_local(ctx, problem):
     nR, nT = 40, 12
     quat = synth.random_quats(nR, rng); tran = rng.normal(scale=2.0, size=(nT, 2))
     pR = np.full(nR, 1.0 / nR); pT = np.full(nT, 1.0 / nT)
-    out = ctx.expect_scan(1, quat, tran, pR, pT, want_logL=True)
+    out = ctx.expect_scan(1, quat, tran, pR, pT, want_logL=True)       # shared templates (thb_expect8.cuh), the default
+    try:
+        ctx.set_option("scan_templates", 0)                             # the fused kernel, every rotation re-gathered per image
+        old = ctx.expect_scan(1, quat, tran, pR, pT, want_logL=True)
+    finally:
+        ctx.set_option("scan_templates", 1)
+    assert np.abs(out["logL"] - old["logL"]).max() <= 2e-6 * np.abs(old["logL"]).max() + 1e-4
+    assert np.abs(out["base"] - old["base"]).max() <= 2e-6 * np.abs(old["base"]).max() + 1e-4
+    assert np.allclose(out["wR"], old["wR"], rtol=5e-3, atol=1e-6 * old["wR"].max()) and np.allclose(out["wC"], old["wC"], rtol=5e-3)
     imgs = np.nonzero(pb["slot"] == 1)[0]
     # pixel-major n-image likelihood of the oracle (logDataVSPrior_m_n) for a few templates
     datPM = np.ascontiguousarray(pb["par"]["dat"][imgs].T); ctfPM = np.ascontiguousarray(pb["par"]["ctf"][imgs].T)
@@ -424,7 +433,7 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     tran = pb["par"]["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
     wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
     try:
-        ctx.set_option("expect_impl", 3)      # default: direct gather from the quad layout
+        ctx.set_option("expect_impl", 3)      # direct gather from the cell layout, one rotation per lane
         ctx.set_option("expect_spread", 0)    # one CTA per image (what a launch of thousands of images runs)
         a = ctx.expect_local(quat, tran, wR, wT)
         ctx.set_option("expect_spread", 1)    # the same image spread over (pixel chunk, rotation group) CTAs, double table
@@ -460,7 +469,7 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
         ctx.set_option("expect_impl", 1)      # direct gather, linear layout, unexpanded likelihood
         b = ctx.expect_local(quat, tran, wR, wT)
     finally:
-        ctx.set_option("expect_impl", 3)
+        ctx.set_option("expect_impl", 0)      # back to the default kernel
         ctx.set_option("quad_oct", 1)
         ctx.set_option("expect_minb", 2)
         ctx.set_option("expect_spread", -1)
@@ -474,17 +483,18 @@ def test_expect_kernels_agree_with_each_other_and_oracle(ctx, problem, k, nR, nT
     assert np.abs(s1["base"] - a["base"]).max() <= tol
     assert np.allclose(s1["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max())
     assert np.allclose(s1["uR"], a["uR"], rtol=5e-3, atol=1e-6 * a["uR"].max())
+    # (kernel against kernel: two independent fp32 summation orders, each within tol of the exact sum)
     assert np.array_equal(p4["logL"], p4q["logL"])
-    assert np.abs(p4["logL"] - a["logL"]).max() <= tol
-    assert np.allclose(p4["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p4["base"] - a["base"]).max() <= tol
+    assert np.abs(p4["logL"] - a["logL"]).max() <= 2 * tol
+    assert np.allclose(p4["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p4["base"] - a["base"]).max() <= 2 * tol
     assert np.array_equal(p5["logL"], p5q["logL"])
-    assert np.abs(p5["logL"] - a["logL"]).max() <= tol
-    assert np.allclose(p5["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p5["base"] - a["base"]).max() <= tol
+    assert np.abs(p5["logL"] - a["logL"]).max() <= 2 * tol
+    assert np.allclose(p5["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(p5["base"] - a["base"]).max() <= 2 * tol
     assert np.abs(c["logL"] - b["logL"]).max() <= 2 * tol
-    assert np.abs(c["logL"] - a["logL"]).max() <= tol
+    assert np.abs(c["logL"] - a["logL"]).max() <= 2 * tol
     assert np.array_equal(m2["logL"], m2q["logL"])
     for m in (m2, m4):
-        assert np.abs(m["logL"] - a["logL"]).max() <= tol
+        assert np.abs(m["logL"] - a["logL"]).max() <= 2 * tol
         assert np.allclose(m["uT"], a["uT"], rtol=2e-3, atol=1e-6 * a["uT"].max()) and np.abs(m["base"] - a["base"]).max() <= tol
         assert np.allclose(m["uR"], a["uR"], rtol=5e-3, atol=1e-6 * a["uR"].max())
     for l in (0, nImg - 1):
@@ -529,7 +539,7 @@ def test_pack_stack_matches_allocPreCal(ctx):
             # double-precision library and rounds once, like glibc's cosf / sinf on the reference's side - all but a handful of
             # pixels agree to the last bit or two of the result
             err = np.abs(got["ctf"][l] - want)
-            assert err.max() <= 6e-5 and np.median(err) <= 1e-7 and np.mean(err > 5e-7) <= 2e-3, (err.max(), np.mean(err > 5e-7))
+            assert err.max() <= 2e-5 and np.median(err) <= 1e-7 and np.mean(err > 5e-7) <= 1e-2, (err.max(), np.mean(err > 5e-7))
     # the packed E stack drives the kernel like an uploaded one
     ctx.set_volume(0, synth.padded_ft(synth.phantom(N, 6, seed=9), pf)); ctx.set_volume(1, synth.padded_ft(synth.phantom(N, 6, seed=8), pf))
     ctx.stack_reserve(capi.STACK_EXPECT, nImg)
@@ -573,6 +583,20 @@ def test_box256_expect_and_insert_against_oracle():
         for i in range(3):
             want = port.project(vol, pf, port.rotate3D(quat[0, i]), pixE["iCol"], pixE["iRow"])
             assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+        if ref is not None:
+            # ... and against THE REFERENCE'S OWN classes at this size (oracle/_ref travels to the GPU box): Projector::project,
+            # translate, logDataVSPrior (the SIMD variant the reference's loops call) for a handful of (rotation, translation) pairs
+            Pr = ref.Projector(pf)
+            Pr.set_padded_ft(vol)
+            for i in range(3):
+                want = Pr.project(ref.rotate3D(quat[0, i]), pixE["iCol"], pixE["iRow"])
+                assert np.abs(got[i] - want).max() <= 2e-6 * np.abs(want).max()
+            for l, r_, t_ in ((0, 0, 0), (0, 57, 4), (1, 124, 8), (1, 3, 2)):
+                pri = Pr.project(ref.rotate3D(quat[l, r_]), pixE["iCol"], pixE["iRow"])
+                tra = ref.translate(tran[l, t_, 0], tran[l, t_, 1], N, pixE["iCol"], pixE["iRow"])
+                want = ref.logDataVSPrior(par["dat"][l], (tra * pri).astype(np.complex64), par["ctf"][l], par["sigRcp"][l])
+                assert abs(out["logL"][l, r_, t_] - want) <= _logL_tol(len(pixE["iCol"]), np.array([want]))
+            Pr.close()
         del vol
         # M at full size
         PM = len(pixM["iCol"])
@@ -592,6 +616,14 @@ def test_box256_expect_and_insert_against_oracle():
         assert a["counter"] == nImg * mReco
         assert _rel_l2(a["F"], want["F"]) <= 1e-6 and _rel_l2(a["T"], want["T"]) <= 1e-6
         assert a["T"].min() >= 0.0
+        if ref is not None:                                    # the reference's Reconstructor::insertP / insertDir loop itself
+            Rr = ref.Reconstructor(N, N, pf)
+            Rr.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
+            Rr.insert_loop(datM, ctfM, w, np.zeros((nImg, 2)), nr, nt, pixM["iCol"], pixM["iRow"], N, nThread=8)
+            wr = Rr.get()
+            Rr.close()
+            assert _rel_l2(a["F"], wr["F"]) <= 1e-6 and _rel_l2(a["T"], wr["T"]) <= 1e-6 and a["counter"] == wr["counter"]
+            del wr
         c.set_option("insert_impl", 2)                         # draw-by-draw insertion gives the same volume
         c.reco_reset(0)
         c.insert(w, nr, nt)

@@ -21,8 +21,8 @@ REF_HDR = Path(os.environ.get("THB_REFERENCE", "/root/reference")) / "gpu" / "in
 MIRRORED = ["getAviDevice", "ExpectPreidx", "ExpectFreeIdx", "ExpectRotran", "ExpectProject", "ExpectGlobal3D", "InsertFT",
             "ExpectGlobal2D", "InsertI2D", "ExpectPrefre", "ExpectLocalIn", "ExpectLocalV2D", "ExpectLocalV3D", "ExpectLocalP",
             "ExpectLocalHostA", "ExpectLocalRTD", "ExpectLocalPreI2D", "ExpectLocalPreI3D", "ExpectLocalM", "ExpectLocalHostF",
-            "ExpectLocalFin"]
-LOCAL_SEAM = MIRRORED[9:]
+            "ExpectLocalFin", "PrepareTF"]
+LOCAL_SEAM = MIRRORED[9:-1]
 _p, _i = C.c_void_p, C.c_int
 
 
@@ -58,6 +58,7 @@ def test_argument_order_matches_reference_header():
     want = [a for a in _params(ref, "InsertFT") if a not in ("hemi", "slav")]
     got = [a for a in _params(ours, "InsertFT") if a != "vdim"]
     assert got == want
+    assert [a for a in _params(ours, "PrepareTF") if a != "vdim"] == _params(ref, "PrepareTF")
 
 
 @pytest.fixture(scope="module")

@@ -103,6 +103,50 @@ def test_device_reconstruct_and_set_projectee(ctx, N):
         reco.close()
 
 
+@pytest.mark.gpu
+def test_device_reconstruct_box128_against_the_reference_class():
+    """thb_reconstruct at box 128 (256^3 transforms, BASELINE config 1's size) against Reconstructor::reconstruct itself: the
+    accumulators come from the device insert of 6 000 noiseless slices (enough to cover Fourier space, see _accumulators), both
+    sides reconstruct the SAME F / T with and without the FSC weighting"""
+    from oracle import refapi
+    from thunder_b200 import capi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    N, pf, nImg = 128, 2, 6000
+    m = N * pf
+    rng = np.random.default_rng(128)
+    vol = synth.phantom(N, 20, seed=3)
+    c = capi.Context(0)
+    try:
+        pixM = capi.pixel_list(N, pf, float(N // 2 - 2), 0.0)
+        PM = len(pixM["iCol"])
+        c.set_projectee(0, vol, N, pf)
+        c.set_expect_pixels(N, pf, pixM["iCol"], pixM["iRow"])
+        c.set_insert_pixels(N, pf, pixM["iColPad"], pixM["iRowPad"])
+        c.reco_alloc(0, m)
+        for b in range(0, nImg, 1000):
+            quats = synth.random_quats(1000, rng)
+            ctf = rng.uniform(0.3, 1.0, (1000, PM)).astype(np.float32)
+            dat = (c.project(0, quats) * ctf).astype(np.complex64)
+            c.upload_stack(capi.STACK_INSERT, dat, ctf)
+            c.insert(np.ones(1000, np.float32), quats[:, None, :], np.zeros((1000, 1, 2)))
+        acc = c.reco_download(0)
+        reco = refapi.Reconstructor(N, N, pf, 16)
+        fsc = np.linspace(0.99, 0.2, N // 2 + 1).astype(np.float32)
+        for f in (None, fsc):
+            c.reco_upload(0, acc["F"], acc["T"])
+            got, nit = c.reconstruct(0, N, pf, gridCorr=True, joinHalf=False, fsc=f)
+            reco.set(acc["F"], acc["T"])
+            reco.prepareTF()
+            want = reco.reconstruct(N, gridCorr=True, joinHalf=False, fsc=f, nThread=16)
+            assert np.linalg.norm(got - want) <= 2e-5 * np.linalg.norm(want), (f is not None, nit)
+            if f is None:
+                assert np.corrcoef(want.ravel(), vol.ravel())[0, 1] > 0.99
+        reco.close()
+    finally:
+        c.close()
+
+
 # ------------------------------------------------------------------------------------------- section 8(f) row 2
 def test_numpy_recentre_remask_matches_reference(ref):
     from oracle import reco_port

@@ -15,6 +15,7 @@
 #include "thb_insert2.cuh"
 #include "thb_expect6.cuh"
 #include "thb_expect7.cuh"
+#include "thb_expect8.cuh"
 #include <cstdlib>
 
 static thread_local std::string g_create_error;
@@ -314,12 +315,57 @@ static int launch_expect_v2(thb_ctx* ctx, ExpectArgs a)
     return THB_OK;
 }
 
+// Global scan with shared templates (thb_expect8.cuh): every rotation of the shared set is projected ONCE per launch into a
+// [pixel][rotation] table (in chunks of rotations within 1 GiB), every image is contracted against it, then the epilogue.
+static int launch_expect_scan_templates(thb_ctx* ctx, ExpectArgs a)
+{
+    const int slot = a.scanSlot1 - 1;
+    const Volume3& v = ctx->vols[slot];
+    const int P = a.P;
+    const size_t nRT = (size_t)a.nR * a.nT;
+    float* table = (float*)scratch(ctx, 7, sizeof(float) * (size_t)a.nAct * nRT);
+    if (!table) return THB_E_CUDA;
+    const size_t budget = (size_t)1 << 30;
+    const int fit = (int)std::max<size_t>(E8_WROT, budget / ((size_t)P * sizeof(float2)) / E8_WROT * E8_WROT);
+    const int chunkR = std::min(a.nR, fit);
+    const int nRpad = (chunkR + E8_WROT - 1) / E8_WROT * E8_WROT;
+    const size_t tbytes = (size_t)P * nRpad * sizeof(float2);
+    const bool fresh = ctx->scratchCap[15] < tbytes || !ctx->scratch[15];
+    float2* tmpl = (float2*)scratch(ctx, 15, tbytes);
+    if (!tmpl) return THB_E_CUDA;
+    if (fresh) THB_CUDA(ctx, cudaMemsetAsync(tmpl, 0, ctx->scratchCap[15], ctx->stream));   // the padding columns are read, never used
+    const bool tc15 = a.nT > E_TC;
+    const size_t smem = tc15 ? e8_smem_bytes<E3_TC_SCAN>() : e8_smem_bytes<E_TC>();
+    if (tc15)
+        THB_CUDA(ctx, cudaFuncSetAttribute(scan_contract_kernel<E3_TC_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        THB_CUDA(ctx, cudaFuncSetAttribute(scan_contract_kernel<E_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_begin(ctx, KF_EXPECT);
+    for (int r0 = 0; r0 < a.nR; r0 += chunkR) {
+        const int nRc = std::min(chunkR, a.nR - r0);
+        scan_project_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->pixE, P, a.quat, r0, nRc, nRpad, ctx->mode2D, tmpl);
+        if (tc15)
+            scan_contract_kernel<E3_TC_SCAN><<<a.nAct, E8_THREADS, smem, ctx->stream>>>(a, tmpl, r0, nRc, nRpad, table);
+        else
+            scan_contract_kernel<E_TC><<<a.nAct, E8_THREADS, smem, ctx->stream>>>(a, tmpl, r0, nRc, nRpad, table);
+        ctx->launches += 2;
+    }
+    scan_epilogue_kernel<<<a.nAct, 256, 0, ctx->stream>>>(a, table);
+    span_end(ctx);
+    ctx->launches++;
+    THB_CUDA(ctx, cudaGetLastError());
+    return THB_OK;
+}
+
 int launch_expect_local(thb_ctx* ctx, const ExpectArgs& a_in)
 {
     ExpectArgs a = a_in;
     if (a.nAct <= 0) return THB_OK;
     a.mode2D = ctx->mode2D;
     if (!ctx->mode2D) a.slotAll = -1;
+    if (a.scanSlot1 > 0 && ctx->scanTemplates && a.nD == 0 && a.quat.sP == 0 && ctx->expectImpl >= 3 &&
+        ctx->vols[a.scanSlot1 - 1].d)
+        return launch_expect_scan_templates(ctx, a);
     if (ctx->expectImpl >= 3) return launch_expect_v3(ctx, a);
     if (ctx->expectImpl == 2 && !ctx->mode2D) return launch_expect_v2(ctx, a);
     const size_t smem = sizeof(PixelE) * E_TILE + (size_t)a.nR * a.nT * sizeof(float);
@@ -469,6 +515,8 @@ int thb_create(thb_ctx** out, int device)
     ctx->smCount = prop.multiProcessorCount;
     if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(7, atoi(e)));
     if (const char* e = getenv("THB_EXPECT_RPL")) ctx->expectRpl = atoi(e) >= 4 ? 4 : 2;
+    if (const char* e = getenv("THB_PF_STAGE")) ctx->pfStage = atoi(e) != 0;
+    if (const char* e = getenv("THB_SCAN_TEMPLATES")) ctx->scanTemplates = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_ORDER")) ctx->expectOrder = atoi(e) == 1;
     if (const char* e = getenv("THB_EXPECT_LOCK")) ctx->expectLock = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_LOCK_TILES")) ctx->expectLockTiles = std::max(1, atoi(e));
@@ -576,8 +624,16 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
 {
     if (!ctx || !key) return THB_E_ARG;
     if (!strcmp(key, "expect_impl")) {
-        if (value < 1 || value > 7 || value == 6) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 1 .. 5 or 7");
-        ctx->expectImpl = value;
+        if (value < 0 || value > 7 || value == 6) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 0 (default), 1 .. 5 or 7");
+        ctx->expectImpl = value ? value : THB_DEFAULT_EXPECT_IMPL;
+        return THB_OK;
+    }
+    if (!strcmp(key, "pf_stage")) {
+        ctx->pfStage = value != 0;
+        return THB_OK;
+    }
+    if (!strcmp(key, "scan_templates")) {  // scans: project each shared rotation once per launch (1, default) or per image (0)
+        ctx->scanTemplates = value != 0;
         return THB_OK;
     }
     if (!strcmp(key, "expect_order")) {    // pixel order of the E stack: 0 = 8x8 blocks, 1 = radial; at the next thb_set_expect_pixels
@@ -1418,6 +1474,7 @@ int thb_expect_scan_range(thb_ctx* ctx, int slot, int imgBase, int nImgRange, in
         a.pix = ctx->pixE; a.P = ctx->nPxlE; a.N = ctx->N;
         a.nAct = nAct; a.imgIdx = didx + l0; a.nR = nR; a.nT = nT;
         a.slotAll = ctx->mode2D ? slot : -1;
+        a.scanSlot1 = slot + 1;
         a.quat = View3{dq, 0, qc, 1};
         a.tran = View3{dt, 0, 2, 1};
         a.wR = View3{dwr, 0, 1, 0};

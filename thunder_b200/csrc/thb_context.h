@@ -89,6 +89,7 @@ struct PFState {
 }  // namespace thb
 
 #define THB_N_SCRATCH 16
+#define THB_DEFAULT_EXPECT_IMPL 7
 struct thb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -114,14 +115,17 @@ struct thb_ctx {
     unsigned long long* dStats = nullptr;   // [8] staging counters of the E kernel (option "stats")
     int statsOn = 0;
     int tileW = 8, tileH = 8;   // pixel tile of the E pixel list (tileW * tileH <= 128)
-    int expectImpl = 3;          // 3: direct gather from the quad layout (default), 2: TMA-staged box, 1: direct gather, linear layout
+    int expectImpl = THB_DEFAULT_EXPECT_IMPL;   // 7: several rotations per lane, lockstep launch (default); 3: direct gather, one rotation per lane;
+                                 // 2: TMA-staged box; 1: direct gather, linear layout; 4 / 5: paired-lane / pixels-on-lanes variants
     int expectRpl = 2;           // option "expect_rpl": rotations per lane of expect_impl 7 (2 or 4)
-    int expectOrder = 0;         // option "expect_order": pixel order of the E stack, 0 = 8x8 blocks, 1 = radial (rings)
-    int expectOrderBuilt = 0;    // the order the current E pixel list (and the resident E stack) was built with
-    int expectLock = 0;          // option "expect_lock": lockstep launch of expect_impl 7
+    int expectOrder = 1;         // option "expect_order": pixel order of the E stack, 0 = 8x8 blocks, 1 = radial (rings)
+    int expectOrderBuilt = 1;    // the order the current E pixel list (and the resident E stack) was built with
+    int expectLock = 1;          // option "expect_lock": lockstep launch of expect_impl 7
     int expectLockTiles = 1;     // option "expect_lock_tiles": one barrier every so many tiles of 128 pixels
-    int expectLockWindow = 2;    // option "expect_lock_window": barriers a CTA may run ahead of the slowest one
+    int expectLockWindow = 1;    // option "expect_lock_window": barriers a CTA may run ahead of the slowest one
     std::vector<int> expectOrderHost;   // launch order of the lockstep launch (images of one slot adjacent)
+    int pfStage = 1;             // option "pf_stage": the particle filter stages the state of a particle in shared memory
+    int scanTemplates = 1;       // option "scan_templates": scans project each shared rotation once per launch (thb_expect8.cuh)
     int quadBrick = 2;           // log2 brick edge of the quad layout (option "quad_brick"; 4x4x4 bricks measured best)
     int quadOct = 1;             // option "quad_oct": whole trilinear cell in one 64-byte element (8x volume bytes; default,
                                  // falls back to the 32-byte quad when HBM is short)

@@ -82,9 +82,9 @@ struct StepArgs {
 };
 
 // support of particle v.p -> dst[p][4 mLR + 2 mLT] as r[mLR][4], t[mLT][2] (test trace; every lane writes the same values)
-__device__ void pf_trace_store(const pf::View& v, double* dst)
+__device__ void pf_trace_store(const pf::View& v, double* dst, long long p)
 {
-    double* o = dst + (size_t)v.p * (4 * v.mLR + 2 * v.mLT);
+    double* o = dst + (size_t)p * (4 * v.mLR + 2 * v.mLT);
     for (int i = 0; i < v.mLR; ++i)
         for (int c = 0; c < 4; ++c) o[4 * i + c] = v.R(i, c);
     o += 4 * v.mLR;
@@ -92,12 +92,100 @@ __device__ void pf_trace_store(const pf::View& v, double* dst)
         for (int c = 0; c < 2; ++c) o[2 * i + c] = v.T(i, c);
 }
 
-__global__ void pf_step_kernel(PFDev d, StepArgs a)
+// The operators walk the particle's state element by element in one serial chain; in global memory (SoA, particle index
+// fastest) every access is a dependent L2 round trip.  pf_step_kernel therefore stages the state of its particle in shared
+// memory (one block of doubles per warp), runs the operators there and writes the persistent arrays back.
+__host__ __device__ inline int pf_stage_doubles(int mLR, int mLT, int mLD)
 {
+    const int mx = mLR > mLT ? mLR : mLT;
+    return 4 * mLR + 2 * mLT + mLR + mLT + mLR + mLT + pf::S_COUNT + 4 * mLR + 2 * mLT + mLR + 2 * mx + (mLD > 0 ? 3 * mLD + 1 : 0);
+}
+
+struct PFStage {
+    pf::View g, s;          // the particle in global memory, and its staged copy (n = 1, p = 0)
+};
+
+__device__ __forceinline__ void pf_copy_rows(double* dst, long long dn, long long dp, const double* src, long long sn, long long sp,
+                                             int rows, int lane)
+{
+    for (int i = lane; i < rows; i += 32) dst[(long long)i * dn + dp] = src[(long long)i * sn + sp];
+}
+
+__device__ __forceinline__ PFStage pf_stage_in(const PFDev& d, int p, double* sm)
+{
+    PFStage st;
+    st.g = make_view(d, p);
+    pf::View v = st.g;
+    const int mLR = d.mLR, mLT = d.mLT, mLD = d.mLD, mx = mLR > mLT ? mLR : mLT;
+    v.n = 1; v.p = 0;
+    v.r = sm; sm += 4 * mLR;
+    v.t = sm; sm += 2 * mLT;
+    v.wR = sm; sm += mLR;
+    v.wT = sm; sm += mLT;
+    v.uR = sm; sm += mLR;
+    v.uT = sm; sm += mLT;
+    v.scal = sm; sm += pf::S_COUNT;
+    v.r2 = sm; sm += 4 * mLR;
+    v.t2 = sm; sm += 2 * mLT;
+    v.w2 = sm; sm += mLR;
+    v.w3 = sm; sm += mx;
+    v.w4 = sm; sm += mx;
+    if (mLD > 0) {
+        v.d = sm; sm += mLD + 1;
+        v.wD = sm; sm += mLD;
+        v.uD = sm; sm += mLD;
+    }
+    st.s = v;
+    const pf::View& g = st.g;
+    const int lane = v.lane;
+    pf_copy_rows(v.r, 1, 0, g.r, g.n, g.p, 4 * mLR, lane);
+    pf_copy_rows(v.t, 1, 0, g.t, g.n, g.p, 2 * mLT, lane);
+    pf_copy_rows(v.wR, 1, 0, g.wR, g.n, g.p, mLR, lane);
+    pf_copy_rows(v.wT, 1, 0, g.wT, g.n, g.p, mLT, lane);
+    pf_copy_rows(v.uR, 1, 0, g.uR, g.n, g.p, mLR, lane);
+    pf_copy_rows(v.uT, 1, 0, g.uT, g.n, g.p, mLT, lane);
+    pf_copy_rows(v.scal, 1, 0, g.scal, g.n, g.p, pf::S_COUNT, lane);
+    if (mLD > 0) {
+        pf_copy_rows(v.d, 1, 0, g.d, g.n, g.p, mLD + 1, lane);
+        pf_copy_rows(v.wD, 1, 0, g.wD, g.n, g.p, mLD, lane);
+        pf_copy_rows(v.uD, 1, 0, g.uD, g.n, g.p, mLD, lane);
+    }
+    __syncwarp();
+    return st;
+}
+
+__device__ __forceinline__ void pf_stage_out(const PFStage& st)
+{
+    const pf::View& g = st.g;
+    const pf::View& v = st.s;
+    const int mLR = v.mLR, mLT = v.mLT, mLD = v.mLD, lane = v.lane;
+    __syncwarp();
+    pf_copy_rows(g.r, g.n, g.p, v.r, 1, 0, 4 * mLR, lane);
+    pf_copy_rows(g.t, g.n, g.p, v.t, 1, 0, 2 * mLT, lane);
+    pf_copy_rows(g.wR, g.n, g.p, v.wR, 1, 0, mLR, lane);
+    pf_copy_rows(g.wT, g.n, g.p, v.wT, 1, 0, mLT, lane);
+    pf_copy_rows(g.uR, g.n, g.p, v.uR, 1, 0, mLR, lane);
+    pf_copy_rows(g.uT, g.n, g.p, v.uT, 1, 0, mLT, lane);
+    pf_copy_rows(g.scal, g.n, g.p, v.scal, 1, 0, pf::S_COUNT, lane);
+    if (mLD > 0) {
+        pf_copy_rows(g.d, g.n, g.p, v.d, 1, 0, mLD + 1, lane);
+        pf_copy_rows(g.wD, g.n, g.p, v.wD, 1, 0, mLD, lane);
+        pf_copy_rows(g.uD, g.n, g.p, v.uD, 1, 0, mLD, lane);
+    }
+}
+
+__global__ void pf_step_kernel(PFDev d, StepArgs a, int staged)
+{
+    extern __shared__ double pf_smem[];
     const int p = pf_particle();
     if (p >= d.nPar) return;
     if (!d.active[p]) return;
-    pf::View v = make_view(d, p);
+    PFStage st;
+    if (staged)
+        st = pf_stage_in(d, p, pf_smem + (size_t)(threadIdx.x >> 5) * pf_stage_doubles(d.mLR, d.mLT, d.mLD));
+    else
+        st.g = st.s = make_view(d, p);
+    pf::View& v = st.s;
     pf::Rng g;
     g.init(d.seed, d.streamBase + p, a.epoch);
     bool cont = true;
@@ -116,7 +204,7 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
             pf::resample_D(v, g);
         }
         pf::norm_w(v);
-        if (a.traceRes) pf_trace_store(v, a.traceRes);
+        if (a.traceRes) pf_trace_store(v, a.traceRes, p);
         d.nPhase[p] = a.phase + 1;
         v.S(pf::S_NPHASE) = (double)(a.phase + 1);
         bool done;
@@ -138,9 +226,10 @@ __global__ void pf_step_kernel(PFDev d, StepArgs a)
             if (a.phase < 0) pf::init_D(v, a.ctfRefineS, g);
             else pf::perturb_D(v, a.prePfD, g);
         }
-        if (a.tracePert) pf_trace_store(v, a.tracePert);
+        if (a.tracePert) pf_trace_store(v, a.tracePert, p);
         if ((threadIdx.x & 31) == 0) atomicAdd(d.activeCount, 1);
     }
+    if (staged) pf_stage_out(st);
 }
 
 // Particle::rand(cls, quat, tran, d) x mReco: independent uniform draws of support indices
@@ -559,7 +648,11 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
     sa.doPost = 0; sa.doPre = 1; sa.phase = -1; sa.prePf = p.perturbFactorL; sa.epoch = (s.epoch << 20);
     THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
     sa.tracePert = tracing ? s.traceSt : nullptr;
-    pf_step_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d, sa);
+    // the particle's state staged in shared memory (one block per warp) unless the support is too large for it
+    const size_t stageBytes = sizeof(double) * (size_t)pf_stage_doubles(p.mLR, p.mLT, p.mLD) * (PF_BLOCK / 32);
+    const int staged = (stageBytes <= 200 * 1024 && ctx->pfStage) ? 1 : 0;
+    if (staged) THB_CUDA(ctx, cudaFuncSetAttribute(pf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stageBytes));
+    pf_step_kernel<<<nb, PF_BLOCK, staged ? stageBytes : 0, ctx->stream>>>(d, sa, staged);
     span_end(ctx);
     ctx->launches += 2;
     const int phaseMax = p.fixedPhases > 0 ? p.fixedPhases : p.maxPhase;
@@ -578,7 +671,7 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
         sa.epoch = (s.epoch << 20) + (uint64_t)(phase + 1);
         THB_CUDA(ctx, cudaMemsetAsync(d.activeCount, 0, sizeof(int), ctx->stream));
         span_begin(ctx, KF_PF);
-        pf_step_kernel<<<nb, PF_BLOCK, 0, ctx->stream>>>(d, sa);
+        pf_step_kernel<<<nb, PF_BLOCK, staged ? stageBytes : 0, ctx->stream>>>(d, sa, staged);
         span_end(ctx);
         ctx->launches++;
         THB_CUDA(ctx, cudaGetLastError());

@@ -88,6 +88,8 @@ struct ExpectArgs {
     unsigned int* lockCtr;  // arrival counter of the tile barriers (zeroed before the launch), null = free-running
     int lockTiles;          // one barrier every lockTiles tiles
     int lockWindow;         // a CTA may run this many barriers ahead of the slowest one
+    int scanSlot1;          // global scan: 1 + the ONE reference (slot) every image of the launch is compared with, rotations
+                            // shared by all images (quat.sP == 0): eligible for the shared-template path (thb_expect8.cuh); 0 = no
 };
 
 struct InsertArgs {
