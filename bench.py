@@ -128,6 +128,25 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def allreduce_selfcheck(ctx, rank, world):
+    """correctness of the one exchange step on THIS launch (the assertions of tests/test_gpu_multi.py, run by every rank of a
+    torchrun job): rank-dependent accumulators in two slots, one thb_allreduce, every rank must hold the sum over ranks"""
+    m = 32
+    shape = (m, m, m // 2 + 1)
+    rng = np.random.default_rng(99)
+    base = [(rng.normal(size=shape) + 1j * rng.normal(size=shape)).astype(np.complex64) for _ in range(2)]
+    for s in range(2):
+        ctx.reco_alloc(s, m)
+        ctx.reco_upload(s, base[s] * (rank + 1), np.full(shape, float(rank + 1 + s), np.float32))
+    ctx.allreduce()
+    k = world * (world + 1) / 2
+    for s in range(2):
+        got = ctx.reco_download(s)
+        if not (np.allclose(got["F"], base[s] * k, rtol=1e-5, atol=1e-5) and np.allclose(got["T"], k + s * world, rtol=1e-6)):
+            raise RuntimeError(f"all-reduce self-check failed on rank {rank} (slot {s})")
+    return {"ranks": world, "slots": 2, "voxels_per_slot": int(np.prod(shape)), "result": "ok"}
+
+
 def e_kernel_label():
     """name of the E kernel the library runs by default (the A/B switches are environment variables, see thb_create)"""
     impl = int(os.environ.get("THB_EXPECT_IMPL", "7"))
@@ -529,8 +548,10 @@ def main():
     from thunder_b200 import dist as tdist
     tdist.init("nccl", local)
     ctx = capi.Context(local)
+    comm_check = None
     if world > 1:
         ctx.comm_init(world, rank, tdist.share_unique_id(capi.comm_unique_id, rank, world))
+        comm_check = allreduce_selfcheck(ctx, rank, world)
 
     N, pf = wl["N"], wl["pf"]
     pixE = capi.pixel_list(N, pf, float(wl["r"]), wl["rL"])
@@ -735,6 +756,7 @@ def main():
             m = N * pf
             wire = 2 * (m // 2 + 1) * m * m * 12                       # both half maps, 3 live floats per voxel
             t = c_ms / c_n / 1e3
+            line["allreduce_selfcheck"] = comm_check
             line["allreduce"] = {"bytes": wire, "ms": c_ms / c_n, "algbw_GBps": wire / t / 1e9, "busbw_GBps": 2 * (world - 1) / world * wire / t / 1e9,
                                  "note": "rank 0's CUDA-event time around pack + ncclAllReduce + unpack on the compute stream (includes waiting for the slowest rank)"}
         print(json.dumps(line))

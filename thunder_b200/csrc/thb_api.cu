@@ -220,7 +220,9 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
     const size_t smem = (ctx->expectImpl == 5 ? E5_SMEM_BYTES : wideT ? E3_TILE * sizeof(PixelRecT<E3_TC_SCAN>) : E3_SMEM_BYTES) +
                         (single ? sizeof(float) * (size_t)a.nR * a.nT : 0);
     span_begin(ctx, KF_EXPECT);
-    if (ctx->expectImpl == 7 && single && !wideT && !ctx->mode2D && a.vdim < 65536) {
+    // (supports of <= 64 rotations - mLR = 25 of demo_3D.json - would leave half of its lanes idle: they take the one-rotation-per-lane
+    // kernel below, whose warps split 1 x 8 / 2 x 4 between rotations and pixels)
+    if (ctx->expectImpl == 7 && single && !wideT && !ctx->mode2D && a.vdim < 65536 && a.nR > 64) {
         // several rotations per lane (thb_expect7.cuh): the record broadcast is amortised over RPL samples
         const int rpl = ctx->expectRpl >= 4 ? 4 : 2;
         const size_t sm7 = rpl == 4 ? e7_smem_bytes<4>(a.nR, a.nT) : e7_smem_bytes<2>(a.nR, a.nT);

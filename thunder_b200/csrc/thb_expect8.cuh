@@ -141,12 +141,19 @@ __global__ void __launch_bounds__(E8_THREADS, 2) scan_contract_kernel(const Expe
                 __syncthreads();
                 if (rw < nRc) {
                     const float2* __restrict__ trow = tmpl + (size_t)tile0 * nRpad + rw + lane;
+                    // the template values of the NEXT pixel are in flight while this one is contracted (the loads are L2 hits:
+                    // without the prefetch the kernel waits for them every iteration)
+                    float2 pv[E8_RPL], pn[E8_RPL];
+                    if (ph < cnt) {
+#pragma unroll
+                        for (int j = 0; j < E8_RPL; ++j) pv[j] = __ldg(trow + (size_t)ph * nRpad + 32 * j);     // padded: always inside the table
+                    }
 #pragma unroll 1
                     for (int k = ph; k < cnt; k += nParts) {
-                        const float2* tp = trow + (size_t)k * nRpad;
-                        float2 pv[E8_RPL];
+                        const int kn = min(k + nParts, cnt - 1);
+                        const float2* tp = trow + (size_t)kn * nRpad;
 #pragma unroll
-                        for (int j = 0; j < E8_RPL; ++j) pv[j] = __ldg(tp + 32 * j);     // padded: always inside the table
+                        for (int j = 0; j < E8_RPL; ++j) pn[j] = __ldg(tp + 32 * j);
                         const ScanRec<TC>& rec = tile[k];
                         const float gk = rec.g;
 #pragma unroll
@@ -157,6 +164,8 @@ __global__ void __launch_bounds__(E8_THREADS, 2) scan_contract_kernel(const Expe
 #pragma unroll
                             for (int j = 0; j < E8_RPL; ++j) acc[j][t] = fmaf(u.x, pv[j].x, fmaf(u.y, pv[j].y, acc[j][t]));
                         }
+#pragma unroll
+                        for (int j = 0; j < E8_RPL; ++j) pv[j] = pn[j];
                     }
                 }
             }

@@ -71,6 +71,29 @@ struct Rng {
         c[0]++;
         have = 4;
     }
+    // block b of the stream without touching the state (the generator is counter-based: draw d is element 3 - d % 4 of block d / 4)
+    THB_HD void block_at(uint32_t b, uint32_t out[4]) const
+    {
+        uint32_t x0 = b, x1 = c[1], x2 = c[2], x3 = c[3], ka = k0, kb = k1;
+        for (int r = 0; r < 10; ++r) {
+            uint32_t h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, x0, h0, l0);
+            mulhilo(0xCD9E8D57u, x2, h1, l1);
+            const uint32_t y0 = h1 ^ x1 ^ ka, y1 = l1, y2 = h0 ^ x3 ^ kb, y3 = l0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+    }
+    THB_HD uint32_t position() const { return 4u * c[0] - (uint32_t)have; }     // draws consumed so far
+    THB_HD void seek(uint32_t pos)                                              // continue with draw `pos`
+    {
+        const uint32_t b = pos >> 2, e = pos & 3u;
+        if (e == 0) { c[0] = b; have = 0; return; }
+        block_at(b, o);
+        c[0] = b + 1;
+        have = 4 - (int)e;
+    }
     THB_HD uint32_t u32()
     {
         if (have == 0) block();
@@ -406,9 +429,67 @@ THB_HD void balance_T(const View& v)
     norm_w(v);
 }
 
+#if defined(__CUDA_ARCH__)
+// The same draws and the same arithmetic as the serial loop below, spread over the warp that executes the particle: the polar
+// method consumes the stream two draws per attempt, whatever the outcome, so attempt a uses draws pos + 2a, pos + 2a + 1 and the
+// k-th ACCEPTED attempt is the k-th Gaussian.  32 attempts are evaluated at a time (one per lane), a ballot ranks the accepted ones.
+// A zero draw (uniform_pos re-draws it: probability 2^-32) shifts the pairing; it is left to the serial loop (returns false with
+// the state untouched).  The 4 mLR Gaussians are the serial chain that dominated the particle-filter kernel.
+__device__ inline bool sample_acg_r2_warp(const View& v, double k1, double k2, double k3, Rng& g)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = v.lane, need = 4 * v.mLR;
+    const uint32_t pos = g.position();
+    int accepted = 0;
+    uint32_t base = 0, lastAttempt = 0;
+    while (accepted < need) {
+        const uint32_t a = base + (uint32_t)lane;
+        const uint32_t d0 = pos + 2u * a;
+        const int e0 = (int)(d0 & 3u);
+        uint32_t o0[4];
+        g.block_at(d0 >> 2, o0);
+        const uint32_t u0 = o0[3 - e0];
+        uint32_t u1;
+        if (e0 == 3) {
+            uint32_t o1[4];
+            g.block_at((d0 >> 2) + 1u, o1);
+            u1 = o1[3];
+        } else
+            u1 = o0[2 - e0];
+        if (__any_sync(full, u0 == 0u || u1 == 0u)) return false;
+        const double x = -1.0 + 2.0 * ((double)u0 * (1.0 / 4294967296.0));
+        const double y = -1.0 + 2.0 * ((double)u1 * (1.0 / 4294967296.0));
+        const double r2 = x * x + y * y;
+        const bool ok = !(r2 > 1.0 || r2 == 0.0);
+        const unsigned mask = __ballot_sync(full, ok);
+        const int gi = accepted + __popc(mask & ((1u << lane) - 1u));
+        if (ok && gi < need) v.R2(gi >> 2, gi & 3) = 1.0 * y * sqrt(-2.0 * log(r2) / r2);
+        const unsigned lastMask = __ballot_sync(full, ok && gi == need - 1);
+        if (lastMask) lastAttempt = base + (uint32_t)(__ffs((int)lastMask) - 1);
+        accepted += __popc(mask);
+        base += 32u;
+    }
+    g.seek(pos + 2u * (lastAttempt + 1u));
+    __syncwarp();
+    const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);
+    for (int i = lane; i < v.mLR; i += 32) {
+        double d[4];
+        d[0] = v.R2(i, 0); d[1] = v.R2(i, 1); d[2] = v.R2(i, 2); d[3] = v.R2(i, 3);
+        d[1] *= l1; d[2] *= l2; d[3] *= l3;
+        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+        for (int c = 0; c < 4; ++c) v.R2(i, c) = d[c] / nrm;
+    }
+    __syncwarp();
+    return true;
+}
+#endif
+
 // sampleACG(dst, k1, k2, k3, n) into the scratch rows R2 (src/Geometry/DirectionalStat.cpp:39-62): L = diag(1, sqrt k) of the LLT
 THB_HD void sample_acg_r2(const View& v, double k1, double k2, double k3, Rng& g)
 {
+#if defined(__CUDA_ARCH__)
+    if (v.lane >= 0 && sample_acg_r2_warp(v, k1, k2, k3, g)) return;
+#endif
     const double l1 = sqrt(k1), l2 = sqrt(k2), l3 = sqrt(k3);
     for (int i = 0; i < v.mLR; ++i) {
         double d[4];
