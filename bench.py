@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--nr", type=int, default=100, help="2d: in-plane rotations of the scan (mS of demo_2D.json)")
     ap.add_argument("--nt", type=int, default=30, help="2d: translations of the scan")
+    ap.add_argument("--phases2d", type=int, default=5, help="2d: local phases after the scan (mLR = mLT = 9, demo_2D.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -282,7 +283,7 @@ def config_2d(args, wl, PE, PM, n_gpus):
                         f"scan of {args.nr} in-plane rotations x {args.nt} translations per class, mReco {args.mreco}, {n_gpus}xB200",
             "particles_resident_per_gpu": args.particles // n_gpus, "batch_per_gpu_per_step": args.batch, "box": wl["N"], "pf": wl["pf"], "r": wl["r"],
             "nPxl_E": PE, "nPxl_M": PM, "classes": args.classes, "nR": args.nr, "nT": args.nt, "mReco": args.mreco,
-            "step": "classification scan of every image against every class + draws from the posterior (host) + class-wise insert + all-reduce",
+            "step": "one classification iteration: scan of every image against every class + class choice and hand-over to the particle filter (device) + local phases (mLR = mLT = 9) + class-wise insert of mReco draws per image + all-reduce",
             "l2": "inputs larger than L2 (each step reads a fresh image batch of %.1f GB)" % (args.batch * (PE * 16 + PM * 12) / 1e9),
             "parallelism": f"particles sharded over {n_gpus} GPU(s); one allreduce of the class accumulators per step"}
 
@@ -416,7 +417,8 @@ def main_2d(args, rank, world, local):
     ang = np.linspace(-np.pi, np.pi, args.nr, endpoint=False); cs = np.stack([np.cos(ang), np.sin(ang)], 1)
     trans = rng.normal(scale=2.0, size=(args.nt, 2)); pR = np.full(args.nr, 1.0 / args.nr); pT = np.full(args.nt, 1.0 / args.nt)
     nBatches = max(nRes // B, 1)
-    w = np.full(B, 1.0 / args.mreco, np.float32)
+    prm2d = capi.PFParams(mLR=9, mLT=9, transS=2.0, transQ=0.01, perturbFactorL=0.5, perturbFactorS=0.5, minPhase=3, maxPhase=100,
+                          fixedPhases=args.phases2d, decreaseFactor=0.95, noDecreaseLimit=1, seed=7)
 
     def upload_async(i):
         base = (i % nBatches) * B
@@ -429,10 +431,17 @@ def main_2d(args, rank, world, local):
             ctx.upload_wait()
             if nBatches > 1:
                 upload_async(i + 1)
-        res = [ctx.expect_scan(k, cs, trans, pR, pT, img_range=(base, B)) for k in range(nK)]
-        nc, nr, nt = _draws_2d(rng, res, nK, args.nr, args.nt, args.mreco, cs, trans)
-        ctx.insert_classes(w, nc, nr, nt, imgIdx=np.arange(base, base + B, dtype=np.int32))
+        # one classification iteration as the reference runs it (src/Optimiser.cpp:633-1660, MODE_2D): scan of every image against
+        # every class -> class choice and support of the local phases from the scan's weights (on the device: thb_pf_from_scan) ->
+        # local phases with mLR = mLT = 9 (thb_expectation) -> mReco draws per image into the accumulator of its class
+        sc = ctx.expect_scan_classes(nK, cs, trans, pR, pT, img_range=(base, B))     # all classes in one launch, one baseline per image
+        ctx.pf_set_image_base(base, rank * nRes + base)
+        ctx.pf_from_scan(prm2d, cs, trans, sc["wC"], sc["wR"], sc["wT"], kFloor=1.0 / args.nr / 0.5, sFloor=0.1)
+        ctx.expectation()
+        ctx.reconstruct_insert(args.mreco)
         ctx.allreduce()
+        if e2e:
+            ctx.pf_get()                       # particle results (class, support, variances) to the host
         if e2e and nBatches == 1:
             upload_async(i + 1)
 
@@ -481,16 +490,19 @@ def main_2d(args, rank, world, local):
         ms2, wall2 = timed(args.steps, 1, e2e=True)
         e2e = {"value": world * B * args.steps / (wall2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(B * (PE * 16 + PM * 12)),
                "d2h_bytes_per_step": int(nK * B * (args.nr + args.nt + 2) * 4 + nK * (N * pf) * (N * pf // 2 + 1) * 12 // args.steps), "steps": args.steps,
-               "note": "host wall clock: pinned-host upload of every batch (second stream) + scan results to the host + draws on the host + insert + class accumulators to the host once"}
+               "note": "host wall clock: pinned-host upload of every batch (second stream) + scan marginals to the host and back into the hand-over + iteration + particle results to the host each step + class accumulators to the host once"}
     if rank == 0:
         peak, peak_src = measured_peak()
         e_ms, e_n = fam["expect"]
         alg = B * nK * (PE * 16 + args.nr * PE * 32.0)
-        roof = {"bound": "hbm", "kernel": "expect_direct_kernel<2,0,1,15> (MODE_2D scan: bilinear cell = one 256-bit load, 15 translations per pass)",
-                "achieved": alg / (e_ms / 1e3) / 1e9 if e_n else None, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                "frac": (alg / (e_ms / 1e3) / 1e9 / peak) if e_n else None, "traffic": None,
-                "note": "algorithmic bytes = images x classes x (P x 16 + nR x P x 32); the class references (0.6 MB each) are L2-resident, so the "
-                        "kernel is bound by instruction issue (2 FMA per sample and translation), not by HBM: frac > 1 is reuse, see profiles/",
+        roof = {"bound": "hbm", "kernel": "scan_contract_kernel<15> (MODE_2D scan with shared templates: every class rotation projected once per "
+                                          "launch, register-tiled contraction of every image against the template table, 15 translations per pass)",
+                "achieved": alg * args.steps / (e_ms / 1e3) / 1e9 if e_n else None, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                "frac": (alg * args.steps / (e_ms / 1e3) / 1e9 / peak) if e_n else None, "traffic": None,
+                "note": "algorithmic bytes = images x classes x (P x 16 + nR x P x 32) as the naive algorithm issues them (SURVEY.md section 8d); the "
+                        "templates are shared by all images and L2-resident, so the kernel is bound by the fp32 FMA pipe / the shared-memory "
+                        "broadcast of the pixel records, not by HBM: frac > 1 is reuse, see pixel_rot_trans_per_s and DESIGN.md section 4.12; the "
+                        "expect family also holds the few local-phase launches that follow the scan",
                 "algorithmic_bytes_per_step": alg, "launches": e_n, "expect_ms_per_step": e_ms / args.steps,
                 "share_of_step": {k: v[0] / ms for k, v in fam.items()},
                 "pixel_rot_trans_per_s": B * nK * args.nr * args.nt * PE * args.steps / (e_ms / 1e3) if e_n else None}

@@ -221,6 +221,13 @@ int thb_expect_scan(thb_ctx* ctx, int slot, int nR, int nT, const double* quat, 
  * the kernel, baseline over the whole table): no merging of partial results on the host. */
 int thb_expect_scan_range(thb_ctx* ctx, int slot, int imgBase, int nImg, int nR, int nT, const double* quat, const double* tran,
                           const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base, float* logL);
+/* MODE_2D classification scan of ALL classes (slots 0 .. nK-1) at once - the shape of ExpectGlobal2D (gpu/interface/Interface.h:176-198,
+ * caller src/Optimiser.cpp:1873-1920; CPU loop :756-914): quat[nR][2] = (cos, sin) of the shared in-plane rotations, tran[nT][2]; every
+ * image of [imgBase, imgBase + nImg) against every class, ONE baseline per image across the classes.  Outputs (host): wC[nImg][nK],
+ * wR[nK][nImg][nR], wT[nK][nImg][nT], base[nImg] - the layouts thb_pf_from_scan takes.  The templates of all (class, rotation) pairs
+ * are projected once per call, the pixel records of an image are built once for all classes. */
+int thb_expect_scan_classes(thb_ctx* ctx, int nK, int imgBase, int nImg, int nR, int nT, const double* quat, const double* tran,
+                            const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base);
 
 /* ---------------------------------------------------------------- a11-a14: fused M kernel */
 int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad);   /* accumulators F,T: (vdimPad/2+1) x vdimPad^2 */

@@ -199,6 +199,38 @@ def test_expect_scan_2d_every_image_against_every_class(ctx2d, nT):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nT", [6, 12])
+def test_expect_scan_all_classes_in_one_launch(ctx2d, nT):
+    """thb_expect_scan_classes (ExpectGlobal2D's shape: all classes in one table, one baseline per image across the classes) equals the
+    class-by-class scans brought to the common baseline, for the whole stack and for an image sub-range"""
+    s = _setup(nImg=7)
+    _load(ctx2d, s, s["cls"])
+    rng = s["rng"]
+    nR, k = 20, s["k"]
+    cs = _unit(np.linspace(-np.pi, np.pi, nR, endpoint=False)); t = rng.normal(size=(nT, 2)) * 2
+    pR = rng.uniform(0.5, 1.5, nR); pR /= pR.sum()
+    pT = rng.uniform(0.5, 1.5, nT); pT /= pT.sum()
+    res = [ctx2d.expect_scan(c, cs, t, pR, pT) for c in range(k)]
+    bmax = np.max([r["base"] for r in res], axis=0)
+    for rng_ in (None, (2, 4)):
+        out = ctx2d.expect_scan_classes(k, cs, t, pR, pT, img_range=rng_)
+        sl = slice(None) if rng_ is None else slice(rng_[0], rng_[0] + rng_[1])
+        assert np.abs(out["base"] - bmax[sl]).max() <= 2e-6 * np.abs(bmax).max() + 1e-4
+        # weights are exp(logL - baseline): a log-likelihood tolerance of 2e-5 |logL| + 1e-4 (the two paths sum the pixels in different
+        # orders) is a RELATIVE tolerance of that size on every weight, compared where the weight is not negligible
+        rtol = 2 * (2e-5 * np.abs(bmax).max() + 1e-4) + 1e-3
+        for c in range(k):
+            f = np.exp((res[c]["base"] - bmax).astype(np.float64))[sl]
+            for key, want in (("wR", res[c]["wR"][sl] * f[:, None]), ("wT", res[c]["wT"][sl] * f[:, None]), ("wC", res[c]["wC"][sl] * f)):
+                got = out[key][c] if key != "wC" else out["wC"][:, c]
+                big = want > 1e-6 * max(want.max(), 1e-300)
+                worst = float(np.max(np.abs(got[big] / want[big] - 1.0))) if big.any() else 0.0
+                print(f"scan_classes vs class-by-class: {key}[{c}] worst relative difference {worst:.2e} (allowed {rtol:.2e}, |baseline| {np.abs(bmax).max():.0f})")
+                assert np.allclose(got[big], want[big], rtol=rtol), (key, c, rtol)
+                assert np.all(got[~big] <= 2e-6 * max(want.max(), 1e-300) + 1e-30), (key, c)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("per_draw_classes", [False, True])
 def test_insert_2d_matches_reference(ctx2d, per_draw_classes):
     ref = _ref()

@@ -101,6 +101,7 @@ def _sig(lib):
     f = lib.thb_expect_local; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _i] + [_p] * 9
     f = lib.thb_expect_scan; f.restype = _i; f.argtypes = [_p, _i, _i, _i] + [_p] * 9
     f = lib.thb_expect_scan_range; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _i, _i] + [_p] * 9
+    f = lib.thb_expect_scan_classes; f.restype = _i; f.argtypes = [_p, _i, _i, _i, _i, _i] + [_p] * 8
     f = lib.thb_reco_alloc; f.restype = _i; f.argtypes = [_p, _i, _i]
     f = lib.thb_reco_reset; f.restype = _i; f.argtypes = [_p, _i]
     f = lib.thb_insert; f.restype = _i; f.argtypes = [_p, _i, _p, _i, _p, _p, _p, _p]
@@ -416,6 +417,18 @@ class Context:
         self._chk(self.lib.thb_expect_scan_range(self.h, slot, int(base0), int(n), nR, nT, _ptr(quat), _ptr(tran), _ptr(pR), _ptr(pT),
                                                  _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base), _ptr(logL)))
         return dict(wC=wC, wR=wR, wT=wT, base=base, logL=logL)
+
+    def expect_scan_classes(self, nK, quat, tran, pR, pT, img_range=None):
+        """MODE_2D: every image against all nK classes in one launch; wC[n][nK], wR[nK][n][nR], wT[nK][n][nT], base[n] (one baseline per image)"""
+        quat = _arr(quat, np.float64); tran = _arr(tran, np.float64)
+        nR, nT = quat.shape[0], tran.shape[0]
+        pR = _arr(pR, np.float64, (nR,)); pT = _arr(pT, np.float64, (nT,))
+        base0, n = (0, self.nImgE) if img_range is None else img_range
+        wC = np.empty((n, nK), np.float32); wR = np.empty((nK, n, nR), np.float32); wT = np.empty((nK, n, nT), np.float32)
+        base = np.empty(n, np.float32)
+        self._chk(self.lib.thb_expect_scan_classes(self.h, int(nK), int(base0), int(n), nR, nT, _ptr(quat), _ptr(tran), _ptr(pR), _ptr(pT),
+                                                   _ptr(wC), _ptr(wR), _ptr(wT), _ptr(base)))
+        return dict(wC=wC, wR=wR, wT=wT, base=base)
 
     # ---- M
     def reco_alloc(self, slot, vdimPad):

@@ -1517,6 +1517,88 @@ int thb_expect_scan_range(thb_ctx* ctx, int slot, int imgBase, int nImgRange, in
     return THB_OK;
 }
 
+// MODE_2D classification scan of all classes at once (ExpectGlobal2D's shape, gpu/interface/Interface.h:176-198): the templates
+// of every (class, rotation) pair in ONE table, every image contracted against all of them in one launch, one baseline per image
+// across the classes.  See scan_classes_epilogue_kernel (thb_expect8.cuh).
+int thb_expect_scan_classes(thb_ctx* ctx, int nK, int imgBase, int nImg, int nR, int nT, const double* quat, const double* tran,
+                            const double* pR, const double* pT, float* wC, float* wR, float* wT, float* base)
+{
+    if (!ctx) return THB_E_ARG;
+    if (!ctx->mode2D) return set_error(ctx, THB_E_STATE, "expect_scan_classes: MODE_2D only (thb_set_mode)");
+    const int vdim = check_expect_state(ctx, "expect_scan_classes");
+    if (vdim < 0) return vdim;
+    if (nK <= 0 || nK > THB_MAX_SLOTS || nR <= 0 || nT <= 0 || !quat || !tran || !pR || !pT || !wC || !wR || !wT || !base)
+        return set_error(ctx, THB_E_ARG, "expect_scan_classes: bad arguments");
+    for (int k = 0; k < nK; ++k)
+        if (!ctx->vols[k].d) return set_error(ctx, THB_E_STATE, "expect_scan_classes: no class reference in slot %d", k);
+    if (imgBase < 0 || nImg <= 0 || imgBase + nImg > ctx->stackE.nImg)
+        return set_error(ctx, THB_E_ARG, "expect_scan_classes: images [%d,%d) outside the stack", imgBase, imgBase + nImg);
+    THB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int P = ctx->nPxlE;
+    const size_t nF = (size_t)nK * nR;
+    const int nFpad = (int)((nF + E8_WROT - 1) / E8_WROT * E8_WROT);
+    const size_t tbytes = (size_t)P * nFpad * sizeof(float2);
+    if (tbytes > ((size_t)2 << 30)) return set_error(ctx, THB_E_ARG, "expect_scan_classes: template table of %zu MB; scan class by class", tbytes >> 20);
+    const bool fresh = ctx->scratchCap[15] < tbytes || !ctx->scratch[15];
+    float2* tmpl = (float2*)scratch(ctx, 15, tbytes);
+    if (!tmpl) return THB_E_CUDA;
+    if (fresh) THB_CUDA(ctx, cudaMemsetAsync(tmpl, 0, ctx->scratchCap[15], ctx->stream));
+    double* din = (double*)scratch(ctx, 0, sizeof(double) * ((size_t)nR * 2 + nT * 2 + nR + nT));
+    if (!din) return THB_E_CUDA;
+    double* dq = din; double* dt = dq + (size_t)nR * 2; double* dwr = dt + nT * 2; double* dwt = dwr + nR;
+    THB_CUDA(ctx, cudaMemcpyAsync(dq, quat, sizeof(double) * 2 * (size_t)nR, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dt, tran, sizeof(double) * 2 * nT, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwr, pR, sizeof(double) * nR, cudaMemcpyHostToDevice, ctx->stream));
+    THB_CUDA(ctx, cudaMemcpyAsync(dwt, pT, sizeof(double) * nT, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t budget = (size_t)1 << 30;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nImg, budget / (nF * nT * sizeof(float))));
+    float* table = (float*)scratch(ctx, 7, sizeof(float) * (size_t)chunk * nF * nT);
+    const size_t nout = (size_t)chunk * nK + (size_t)nK * chunk * nR + (size_t)nK * chunk * nT + chunk;
+    float* dout = (float*)scratch(ctx, 1, sizeof(float) * nout);
+    if (!table || !dout) return THB_E_CUDA;
+    const bool tc15 = nT > E_TC;
+    const size_t smem = tc15 ? e8_smem_bytes<E3_TC_SCAN>() : e8_smem_bytes<E_TC>();
+    if (tc15)
+        THB_CUDA(ctx, cudaFuncSetAttribute(scan_contract_kernel<E3_TC_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        THB_CUDA(ctx, cudaFuncSetAttribute(scan_contract_kernel<E_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_begin(ctx, KF_EXPECT);
+    for (int k = 0; k < nK; ++k) {
+        const Volume3& v = ctx->vols[k];
+        scan_project_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(v.d, v.vdim, v.pitch, ctx->pixE, P, View3{dq, 0, 2, 1}, 0, nR, nFpad, 1, tmpl, k * nR);
+    }
+    span_end(ctx);
+    ctx->launches += nK;
+    for (int l0 = 0; l0 < nImg; l0 += chunk) {
+        const int nAct = std::min(chunk, nImg - l0);
+        ExpectArgs a;
+        memset(&a, 0, sizeof(a));
+        a.vdim = vdim; a.pitch = vol_pitch(vdim);
+        a.dat = ctx->stackE.dat; a.ctf = ctx->stackE.ctf; a.sig = ctx->stackE.sig; a.slotOfImg = ctx->stackE.slot;
+        a.pix = ctx->pixE; a.P = P; a.N = ctx->N; a.mode2D = 1;
+        a.nAct = nAct; a.imgIdx = nullptr; a.imgBase = imgBase + l0; a.nR = (int)nF; a.nT = nT;
+        a.tran = View3{dt, 0, 2, 1};
+        float* dWC = dout; float* dWR = dWC + (size_t)nAct * nK; float* dWT = dWR + (size_t)nK * nAct * nR; float* dB = dWT + (size_t)nK * nAct * nT;
+        span_begin(ctx, KF_EXPECT);
+        if (tc15)
+            scan_contract_kernel<E3_TC_SCAN><<<nAct, E8_THREADS, smem, ctx->stream>>>(a, tmpl, 0, (int)nF, nFpad, table);
+        else
+            scan_contract_kernel<E_TC><<<nAct, E8_THREADS, smem, ctx->stream>>>(a, tmpl, 0, (int)nF, nFpad, table);
+        scan_classes_epilogue_kernel<<<nAct, 256, 0, ctx->stream>>>(table, nAct, nK, nR, nT, dwr, dwt, dWC, dWR, dWT, dB);
+        span_end(ctx);
+        ctx->launches += 2;
+        THB_CUDA(ctx, cudaGetLastError());
+        THB_CUDA(ctx, cudaMemcpyAsync(wC + (size_t)l0 * nK, dWC, sizeof(float) * (size_t)nAct * nK, cudaMemcpyDeviceToHost, ctx->stream));
+        THB_CUDA(ctx, cudaMemcpyAsync(base + l0, dB, sizeof(float) * nAct, cudaMemcpyDeviceToHost, ctx->stream));
+        for (int k = 0; k < nK; ++k) {
+            THB_CUDA(ctx, cudaMemcpyAsync(wR + ((size_t)k * nImg + l0) * nR, dWR + (size_t)k * nAct * nR, sizeof(float) * (size_t)nAct * nR, cudaMemcpyDeviceToHost, ctx->stream));
+            THB_CUDA(ctx, cudaMemcpyAsync(wT + ((size_t)k * nImg + l0) * nT, dWT + (size_t)k * nAct * nT, sizeof(float) * (size_t)nAct * nT, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the scratch table and outputs are reused by the next chunk
+    }
+    return THB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int thb_reco_alloc(thb_ctx* ctx, int slot, int vdimPad)
 {

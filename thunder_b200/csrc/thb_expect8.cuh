@@ -28,15 +28,20 @@ constexpr int E8_RPL = 4;                 // rotations per lane
 constexpr int E8_WROT = 32 * E8_RPL;      // rotations per warp
 constexpr int E8_TILE = 128;
 
+// one record per pixel; its size in 16-byte words is ODD (TC = 15: 9 words, 144 bytes; TC = 9: 5 words, 80 bytes) so that the records of
+// consecutive pixels start in different shared-memory banks: with 128-byte records every store of the record build was a
+// 16-way bank conflict (ncu: 45 % of all shared-memory wavefronts of the kernel)
 template <int TC>
 struct __align__(16) ScanRec {
     float g, pad;       // sig * ctf^2
     float2 u[TC];       // -2 sig ctf dat conj(tra_t)
+    float4 skew[((8 + 8 * TC) / 16) % 2 == 0 ? 1 : 0];
 };
+static_assert(sizeof(ScanRec<15>) == 144 && sizeof(ScanRec<9>) == 80, "record sizes");
 
-// templates of rotations [r0, r0 + nRc) of one reference: tmpl[i * nRpad + (r - r0)], pixel i in the resident (permuted) order
+// templates of rotations [r0, r0 + nRc) of one reference: tmpl[i * nRpad + colBase + (r - r0)], pixel i in the resident (permuted) order
 __global__ void scan_project_kernel(const float2* __restrict__ vol, int n, int pitch, const int4* __restrict__ pix, int P,
-                                    View3 quat, int r0, int nRc, int nRpad, int mode2D, float2* __restrict__ tmpl)
+                                    View3 quat, int r0, int nRc, int nRpad, int mode2D, float2* __restrict__ tmpl, int colBase = 0)
 {
     const size_t total = (size_t)P * nRc;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -47,7 +52,7 @@ __global__ void scan_project_kernel(const float2* __restrict__ vol, int n, int p
         const int4 px = pix[i];
         float x, y, z;
         slice_coord(rot, (double)px.x, (double)px.y, x, y, z);
-        tmpl[(size_t)i * nRpad + rr] = gather_ft(vol, n, pitch, x, y, z);
+        tmpl[(size_t)i * nRpad + colBase + rr] = gather_ft(vol, n, pitch, x, y, z);
     }
 }
 
@@ -226,6 +231,45 @@ __global__ void __launch_bounds__(256) scan_epilogue_kernel(const ExpectArgs A, 
     const int p = blockIdx.x;
     if (A.active && !A.active[p]) return;
     expect_epilogue<256>(A, p, table + (size_t)p * A.nR * A.nT, redf, redd);
+}
+
+// MODE_2D classification scan of ALL classes in one table [image][nK * nR][nT] (template index f = class * nR + rotation: the
+// contraction kernel does not know about classes, 20 classes x 100 rotations fill 2 000 of 2 048 rotation slots instead of 100 of
+// 128 twenty times, and the pixel records are built once for all classes).  Epilogue as ExpectGlobal2D returns it
+// (gpu/interface/Interface.h:176-198, src/Optimiser.cpp:834-894): ONE baseline per image across the classes,
+//   wC[img][k] = sum_rt w pR pT,  wR[k][img][r] = sum_t w pT,  wT[k][img][t] = sum_r w pR,   w = exp(logL - baseline)
+__global__ void __launch_bounds__(256) scan_classes_epilogue_kernel(const float* __restrict__ table, int nAct, int nK, int nR, int nT,
+                                                                  const double* __restrict__ pR, const double* __restrict__ pT,
+                                                                  float* __restrict__ wC, float* __restrict__ wR, float* __restrict__ wT,
+                                                                  float* __restrict__ base)
+{
+    __shared__ float redf[8];
+    __shared__ double redd[8];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const size_t nF = (size_t)nK * nR;
+    const float* L = table + (size_t)p * nF * nT;
+    float m = -INFINITY;
+    for (size_t i = tid; i < nF * nT; i += 256) m = fmaxf(m, L[i]);
+    m = block_reduce_max(m, redf);
+    if (tid == 0) base[p] = m;
+    for (int k = 0; k < nK; ++k) {
+        const float* Lk = L + (size_t)k * nR * nT;
+        double uc = 0.0;
+        for (int r = tid; r < nR; r += 256) {
+            float s = 0.0f;
+            for (int t = 0; t < nT; ++t) s = (float)((double)s + (double)expf(Lk[r * nT + t] - m) * pT[t]);
+            wR[((size_t)k * nAct + p) * nR + r] = s;
+            uc += (double)s * pR[r];
+        }
+        for (int t = tid; t < nT; t += 256) {
+            float s = 0.0f;
+            for (int r = 0; r < nR; ++r) s = (float)((double)s + (double)expf(Lk[r * nT + t] - m) * pR[r]);
+            wT[((size_t)k * nAct + p) * nT + t] = s;
+        }
+        uc = block_reduce_sum(uc, redd);
+        if (tid == 0) wC[(size_t)p * nK + k] = (float)uc;
+        __syncthreads();
+    }
 }
 
 }  // namespace thb

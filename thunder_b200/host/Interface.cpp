@@ -381,11 +381,15 @@ void ExpectGlobal2D(Complex* vol, Complex* datP, RFLOAT* ctfP, RFLOAT* sigRcpP, 
     for (int k = 0; k < nK; ++k) CHK(ctx, thb_set_volume(ctx, k, reinterpret_cast<const float*>(vol + k * sizeModel), vdim));
     CHK(ctx, thb_upload_stack(ctx, THB_STACK_EXPECT, imgNum, reinterpret_cast<const float*>(datP), ctfP, sigRcpP, nullptr));
     g_scan.stackDat = nullptr;
-    std::vector<float> cC(imgNum), cR((size_t)imgNum * nR), cT((size_t)imgNum * nT), cB(imgNum), baseL(imgNum);
-    for (int k = 0; k < nK; ++k) {
-        CHK(ctx, thb_expect_scan(ctx, k, nR, nT, rot, trans, pR, pT, cC.data(), cR.data(), cT.data(), cB.data(), nullptr));
-        mergeClass(cC, cR, cT, cB, wC, wR, wT, baseL.data(), k, nK, nR, nT, imgNum);
-    }
+    // all classes in one launch, one baseline per image across the classes (thb_expect_scan_classes); the reference's layouts are
+    // image-major: weightC[l * k + c], weightR[(l * k + c) * nR + r], weightT[(l * k + c) * nT + t]
+    std::vector<float> cR((size_t)nK * imgNum * nR), cT((size_t)nK * imgNum * nT), cB(imgNum);
+    CHK(ctx, thb_expect_scan_classes(ctx, nK, 0, imgNum, nR, nT, rot, trans, pR, pT, wC, cR.data(), cT.data(), cB.data()));
+    for (int k = 0; k < nK; ++k)
+        for (int l = 0; l < imgNum; ++l) {
+            memcpy(wR + ((size_t)l * nK + k) * nR, cR.data() + ((size_t)k * imgNum + l) * nR, sizeof(float) * nR);
+            memcpy(wT + ((size_t)l * nK + k) * nT, cT.data() + ((size_t)k * imgNum + l) * nT, sizeof(float) * nT);
+        }
 }
 
 // MODE_2D M-step (gpu/interface/Interface.h:239-265; call site src/Optimiser.cpp:6770-6850): F2D [nk][vdim][vdim/2+1] complex,
