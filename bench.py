@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--nr", type=int, default=100, help="2d: in-plane rotations of the scan (mS of demo_2D.json)")
     ap.add_argument("--nt", type=int, default=30, help="2d: translations of the scan")
+    ap.add_argument("--scan-nr", type=int, default=0, help="3d: a GLOBAL-SEARCH iteration - scan of this many shared rotations (demo_3D.json: 10000) x --nt "
+                    "translations, hand-over to the particle filter, then the local phases and the insert (0 = local search only)")
+    ap.add_argument("--rmax", type=int, default=0, help="3d: frequency limit of the E-step in pixels (0 = box/2 - 1); global-search iterations run at low resolution")
     ap.add_argument("--phases2d", type=int, default=5, help="2d: local phases after the scan (mLR = mLT = 9, demo_2D.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -65,7 +68,7 @@ def parse():
 
 def workload(args):
     N, pf = args.box, 2
-    r = N // 2 - 1
+    r = args.rmax if getattr(args, "rmax", 0) > 0 else N // 2 - 1
     rL = float(np.floor(N * 1.32 / 200.0))        # ignoreRes 200 A at 1.32 A/pixel (src/Optimiser.cpp:243)
     return dict(N=N, pf=pf, r=r, rL=rL, k0=7.6e-5, transS=2.0)
 
@@ -80,6 +83,9 @@ def config_dict(args, wl, nPxlE, nPxlM, n_gpus):
         "mLR": args.mlr, "mLT": args.mlt, "phases": args.phases, "mReco": args.mreco, "half_sets": 2,
         "l2": "inputs larger than L2 (each step reads a fresh ~%.1f GB image batch)" % (args.batch * (nPxlE * 16 + nPxlM * 12) / 1e9),
         "parallelism": f"particles sharded over {n_gpus} GPU(s); one allreduce of F|T per step",
+        **({"global_search": f"every step starts with the global scan: {args.scan_nr} shared rotations x {args.nt} translations against every image "
+                             f"(thb_expect_scan, shared templates), hand-over to the particle filter on the device (thb_pf_from_scan), then the "
+                             f"local phases and the insert; E-step frequency limit r = {wl['r']} px"} if getattr(args, "scan_nr", 0) > 0 else {}),
     }
 
 
@@ -199,6 +205,12 @@ def run_reference(args, wl, steps, warmup, rank, world, sample_only=False):
     reco = ref.Reconstructor(N, N, pf, cores)
     reco.set_precal(pixM["iColPad"], pixM["iRowPad"], pixM["iPxl"], pixM["iSig"])
 
+    scan_nr = getattr(args, "scan_nr", 0)
+    if scan_nr > 0:
+        grid_g = synth.random_quats(scan_nr, np.random.default_rng(77))
+        trans_g = np.random.default_rng(78).normal(scale=wl["transS"], size=(args.nt, 2))
+        pR_g = np.full(scan_nr, 1.0 / scan_nr); pT_g = np.full(args.nt, 1.0 / args.nt)
+
     def one_step():
         pars = []
         for l in range(nS):
@@ -206,8 +218,16 @@ def run_reference(args, wl, steps, warmup, rank, world, sample_only=False):
             p.load(args.mlr, args.mlt, quat[l], wl["k0"], wl["k0"], wl["k0"], par["tran"][l], 1.0, 1.0)
             pars.append(p)
         t0 = time.perf_counter()
+        if scan_nr > 0:
+            # the reference's scan loop (ref_scan: Projector::project once per rotation + logDataVSPrior_m_n over all images), then
+            # the post-scan Particle logic per image (ref_particle_from_scan), written into the Particle objects of the phases
+            o = ref.scan([P], False, par["dat"], par["ctf"], par["sigRcp"], pixE["iCol"], pixE["iRow"], N, grid_g, trans_g, pR_g, pT_g, nThread=cores)
+            for l in range(nS):
+                st = ref.particle_from_scan(False, grid_g, trans_g, o["wC"][l], o["wR"][:, l], o["wT"][:, l], args.mlr, args.mlt,
+                                            (scan_nr ** (-1.0 / 3) / 0.5) ** 2, 0.3, (7, l, 1), wl["transS"], 0.01)
+                pars[l].set(r=st["r"], t=st["t"], wR=st["wR"], wT=st["wT"])
         ref.expectation_local(pars, P, par["dat"], par["ctf"], par["sigRcp"], pixE["iCol"], pixE["iRow"], N, args.mlr, args.mlt,
-                              fixedPhases=args.phases, nThread=cores)
+                              pfL=(0.5 if scan_nr > 0 else 2.0), fixedPhases=args.phases, nThread=cores)
         reco.insert_loop(datM, ctfM, None, None, args.mreco, None, pixM["iCol"], pixM["iRow"], N, nThread=cores, pars=pars)
         dt = time.perf_counter() - t0
         for p in pars:
@@ -217,7 +237,8 @@ def run_reference(args, wl, steps, warmup, rank, world, sample_only=False):
     if sample_only:
         dt = one_step()
         return {"value": nS / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"{nS} particles of the same workload (box {N}, {args.mlr}x{args.phases} rotations x {args.mlt} "
+                "sample": f"{nS} particles of the same workload (box {N}, " + (f"global scan {scan_nr} x {args.nt}, " if scan_nr > 0 else "") +
+                          f"{args.mlr}x{args.phases} rotations x {args.mlt} "
                           f"translations, mReco {args.mreco}), one pass, {dt:.1f} s, OpenMP over images on {cores} threads"}
     for _ in range(warmup):
         one_step()
@@ -621,6 +642,11 @@ def main():
     prm = capi.PFParams(mLR=args.mlr, mLT=args.mlt, transS=wl["transS"], transQ=0.01, perturbFactorL=2.0, perturbFactorS=0.5,
                         minPhase=3, maxPhase=100, fixedPhases=args.phases, decreaseFactor=0.95, noDecreaseLimit=1,
                         seed=20260000 + rank)
+    if args.scan_nr > 0:
+        prm.perturbFactorL = 0.5            # global search: no large first perturbation (its phases start at 1 in the reference)
+        grid_g = synth.random_quats(args.scan_nr, np.random.default_rng(77))
+        trans_g = np.random.default_rng(78).normal(scale=wl["transS"], size=(args.nt, 2))
+        pR_g = np.full(args.scan_nr, 1.0 / args.scan_nr); pT_g = np.full(args.nt, 1.0 / args.nt)
     q_start = np.stack([synth.acg_cloud(quat_true[l], wl["k0"], 1, rng)[0] for l in range(B)])
     t_start = tran_true + rng.normal(scale=0.5, size=(B, 2))
     k123 = np.full((B, 3), wl["k0"]); s01 = np.full((B, 2), 1.0)
@@ -639,7 +665,15 @@ def main():
             if nBatches > 1:
                 upload_async(i + 1)             # next batch: overlaps this batch's kernels (double buffering over the stack)
         ctx.pf_set_image_base(base, rank * nRes + base)
-        ctx.pf_load(prm, q_start, k123, t_start, s01)
+        if args.scan_nr > 0:
+            # global-search iteration (src/Optimiser.cpp:633-1136): scan of the shared grid against every image of each half set,
+            # support of the local phases from the scan's weights; k = 1: the slots stay the half sets
+            res = [ctx.expect_scan(s_, grid_g, trans_g, pR_g, pT_g, img_range=(base, B)) for s_ in (0, 1)]
+            wC = (res[0]["wC"] + res[1]["wC"])[:, None]
+            ctx.pf_from_scan(prm, grid_g, trans_g, wC, (res[0]["wR"] + res[1]["wR"])[None], (res[0]["wT"] + res[1]["wT"])[None],
+                             kFloor=(args.scan_nr ** (-1.0 / 3) / 0.5) ** 2, sFloor=0.3)
+        else:
+            ctx.pf_load(prm, q_start, k123, t_start, s01)
         ctx.expectation()
         ctx.reconstruct_insert(args.mreco)
         ctx.allreduce()

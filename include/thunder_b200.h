@@ -348,7 +348,8 @@ int thb_pf_load(thb_ctx* ctx, int nPar, const thb_pf_params* p, const double* qu
  * setPeakFactor + keepHalfHeightPeak(PAR_R), resample(mLR, PAR_R), resample(mLT, PAR_T), calVari, floors kFloor on k1 (.. k3) and
  * sFloor on s0, s1 (OPTIMISER_SCAN_SET_MIN_STD_WITH_PERTURB).  Inputs as thb_expect_scan returns them, class by class:
  * wC[nPar][nK] (relative to ONE baseline per image: scale the per-class results to the largest baseline), wR[nK][nPar][nR],
- * wT[nK][nPar][nT].  The chosen class becomes the slot of the image in both resident stacks (clsOut[nPar], may be NULL), the
+ * wT[nK][nPar][nT].  The chosen class becomes the slot of the image in both resident stacks when nK > 1 (clsOut[nPar], may be NULL; with nK = 1 - a
+ * refinement whose slots are the half sets - the slots are left alone), the
  * particles are the loaded ones (as after thb_pf_load; MODE_2D allowed: the phase loop then runs the von Mises operators).
  * A global-search iteration then continues with thb_expectation with perturbFactorL = perturbFactorSGlobal (its phases start
  * at 1 in the reference: there is no large first perturbation). */

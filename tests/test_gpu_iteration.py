@@ -614,9 +614,7 @@ def test_global_search_iteration_scan_handover_phases(ctx, prob):
     ctx.pf_set_image_base(0, 0)
     cls = ctx.pf_from_scan(prm, grid, trans, wC, wR, wT, kFloor=(scanMinStdR / pfS) ** 2, sFloor=0.3)
     assert not cls.any()
-    # pf_from_scan makes the chosen class the image's slot: with k = 1 in a two-half-set context the slots are restored
-    ctx.upload_stack(capi.STACK_EXPECT, pb["par"]["dat"], pb["par"]["ctf"], pb["par"]["sigRcp"], slot_before)
-    ctx.upload_stack(capi.STACK_INSERT, pb["datM"], pb["ctfM"], slotOfImg=slot_before)
+    # with k = 1 the slots (the two half sets) are left alone: the phases below run every image against its own half-set reference
     sc0 = ctx.pf_get_scal()
     err0 = _ang_deg(sc0[:, 6:10], pb["par"]["quat"])
     ctx.expectation()
@@ -634,10 +632,25 @@ def test_adaptive_stop_rule_runs(ctx, prob):
     _setup(ctx, pb)
     prm = _params(fixed=0)
     prm.maxPhase = 20
+    ctx.pf_set_epoch(1000)                      # a known position of the random streams: the run is repeated below
     _load(ctx, pb, prm)
     nph = ctx.expectation(want_phases=True)
     assert nph.min() >= 4 and nph.max() <= 20
     assert len(np.unique(nph)) > 1
+    # the E launches of the later phases take the compacted list of unfinished particles (a tail of a few particles runs spread over
+    # the chip): same phase counts and same final state as launches over all particles with the finished ones skipped
+    st = ctx.pf_get()
+    try:
+        ctx.set_option("pf_compact", 0)
+        ctx.pf_set_epoch(1000)
+        _load(ctx, pb, prm)
+        nph0 = ctx.expectation(want_phases=True)
+        st0 = ctx.pf_get()
+    finally:
+        ctx.set_option("pf_compact", 1)
+    assert np.array_equal(nph, nph0)
+    for key in ("r", "t", "wR", "wT", "scal"):
+        assert np.allclose(st[key], st0[key], rtol=1e-9, atol=1e-12, equal_nan=True), key
 
 
 def test_closed_loop_iterations_on_device():

@@ -166,6 +166,8 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
         if (ctx->vols[i].d && !ctx->mode2D && ctx->vols[i].quadOct != ctx->quadOct)
             return set_error(ctx, THB_E_STATE, "expect: volume slot %d is not in the layout the launch uses", i);
     a.quads = quad_table(ctx);
+    if (ctx->expectImpl != 3 && ctx->expectImpl != 7 && a.order)
+        return set_error(ctx, THB_E_STATE, "expect: a compacted particle list needs expect_impl 3 or 7");
     a.quadBrick = ctx->mode2D ? 0 : ctx->quadBrick;
     a.sortRot = ctx->mode2D ? 0 : ctx->sortRot;
     a.work = nullptr;
@@ -230,7 +232,7 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
                                                   : (ctx->quadOct ? expect_multi_kernel<2, true> : expect_multi_kernel<2, false>);
         THB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm7));
         int grid = a.nAct;
-        a.order = nullptr; a.lockCtr = nullptr; a.lockTiles = 0; a.lockWindow = 0;
+        a.lockCtr = nullptr; a.lockTiles = 0; a.lockWindow = 0;      // (a.order: null, or the caller's compacted list of active particles)
         if (ctx->expectLock) {
             // lockstep launch: a persistent grid of co-resident CTAs walks the images wave by wave with a barrier every few pixel
             // tiles; the images of one slot are adjacent in the launch order so that a wave reads ONE volume
@@ -240,7 +242,7 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
             int* dOrder = (int*)scratch(ctx, 14, sizeof(int) * (size_t)a.nAct + 16);
             if (!dOrder) return THB_E_CUDA;
             unsigned int* dCtr = reinterpret_cast<unsigned int*>(dOrder + a.nAct + ((4 - (a.nAct & 3)) & 3));
-            if (!a.imgIdx && a.slotOfImg && (size_t)(a.imgBase + a.nAct) <= ctx->stackE.hslot.size()) {
+            if (!a.order && !a.imgIdx && a.slotOfImg && (size_t)(a.imgBase + a.nAct) <= ctx->stackE.hslot.size()) {
                 std::vector<int>& ord = ctx->expectOrderHost;
                 ord.resize(a.nAct);
                 for (int i = 0; i < a.nAct; ++i) ord[i] = i;
@@ -628,6 +630,10 @@ int thb_set_option(thb_ctx* ctx, const char* key, int value)
     if (!strcmp(key, "expect_impl")) {
         if (value < 0 || value > 7 || value == 6) return set_error(ctx, THB_E_ARG, "set_option: expect_impl must be 0 (default), 1 .. 5 or 7");
         ctx->expectImpl = value ? value : THB_DEFAULT_EXPECT_IMPL;
+        return THB_OK;
+    }
+    if (!strcmp(key, "pf_compact")) {     // adaptive E-step: launch the E kernel on the compacted list of unfinished particles
+        ctx->pfCompact = value != 0;
         return THB_OK;
     }
     if (!strcmp(key, "pf_stage")) {

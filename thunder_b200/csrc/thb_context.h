@@ -62,6 +62,7 @@ struct PFState {
     float* uC = nullptr;
     float* base = nullptr;
     unsigned char* active = nullptr;
+    int* order = nullptr;        // [nPar] compacted list of the particles still active (adaptive E-step)
     int* nPhase = nullptr;
     double* vari = nullptr;      // [3][nPar] best variR, variT, and no-decrease counter
     int* drawR = nullptr;        // [nPar][mReco]
@@ -124,6 +125,7 @@ struct thb_ctx {
     int expectLockTiles = 1;     // option "expect_lock_tiles": one barrier every so many tiles of 128 pixels
     int expectLockWindow = 1;    // option "expect_lock_window": barriers a CTA may run ahead of the slowest one
     std::vector<int> expectOrderHost;   // launch order of the lockstep launch (images of one slot adjacent)
+    int pfCompact = 1;           // option "pf_compact": adaptive E-step launches only the unfinished particles (compacted list)
     int pfStage = 1;             // option "pf_stage": the particle filter stages the state of a particle in shared memory
     int scanTemplates = 1;       // option "scan_templates": scans project each shared rotation once per launch (thb_expect8.cuh)
     int quadBrick = 2;           // log2 brick edge of the quad layout (option "quad_brick"; 4x4x4 bricks measured best)

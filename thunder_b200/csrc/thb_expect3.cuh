@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     __shared__ float redf[E3_THREADS / 32];
     __shared__ double redd[E3_THREADS / 32];
 
-    const int p = blockIdx.x;
+    const int pos = blockIdx.x;                             // launch position; A.order (compacted list of active particles) maps it to the particle
+    const int p = A.order ? A.order[pos] : pos;
     if (A.active && !A.active[p]) return;
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
     const int slot = (M2D && A.slotAll >= 0) ? A.slotAll : (A.slotOfImg ? A.slotOfImg[img] : 0);
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(E3_THREADS, MINB) expect_direct_kernel(const E
     const int nD = CTFS ? A.nD : 1;
     const int nRT = A.nR * A.nT * nD;
     const bool single = !CTFS && A.nR <= E3_ROTS && A.nT <= TC;
-    float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_TILE * sizeof(PixelRecT<TC>)) : A.work + (size_t)p * nRT;
+    float* sL = single ? reinterpret_cast<float*>(smem_raw + E3_TILE * sizeof(PixelRecT<TC>)) : A.work + (size_t)pos * nRT;
     const float* __restrict__ defP = CTFS ? A.defP + (size_t)img * P : nullptr;
     float cK1 = 0.f, cK2 = 0.f, cPs = 0.f, cAc = 0.f, cW1 = 0.f;
     if (CTFS) {

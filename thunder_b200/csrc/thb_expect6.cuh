@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(E6_THREADS, 2) expect_spread_kernel(const Expe
     __shared__ float sRC[TC], sRR[TC];
     __shared__ double redd[E6_THREADS / 32];
 
-    const int p = blockIdx.z;
+    const int pos = blockIdx.z;                             // launch position -> particle (A.order: compacted list of active particles)
+    const int p = A.order ? A.order[pos] : pos;
     if (A.active && !A.active[p]) return;
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
     const int slot = (M2D && A.slotAll >= 0) ? A.slotAll : (A.slotOfImg ? A.slotOfImg[img] : 0);
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(E6_THREADS, 2) expect_spread_kernel(const Expe
     const bool rvalid = r < A.nR;
     constexpr int nParts = E6_THREADS / 32;
     const int ph = warp;
-    double* __restrict__ tab = table + (size_t)p * A.nR * A.nT;
+    double* __restrict__ tab = table + (size_t)pos * A.nR * A.nT;
 
     Rot2 rot;
     {
@@ -172,11 +173,12 @@ __global__ void __launch_bounds__(256) expect_table_epilogue_kernel(const Expect
 {
     __shared__ float redf[8];
     __shared__ double redd[8];
-    const int p = blockIdx.x;
+    const int pos = blockIdx.x;
+    const int p = A.order ? A.order[pos] : pos;
     if (A.active && !A.active[p]) return;
     const int nRT = A.nR * A.nT;
-    float* sL = work + (size_t)p * nRT;
-    for (int i = threadIdx.x; i < nRT; i += 256) sL[i] = (float)table[(size_t)p * nRT + i];
+    float* sL = work + (size_t)pos * nRT;
+    for (int i = threadIdx.x; i < nRT; i += 256) sL[i] = (float)table[(size_t)pos * nRT + i];
     __syncthreads();
     expect_epilogue<256>(A, p, sL, redf, redd);
 }

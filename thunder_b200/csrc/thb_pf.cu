@@ -92,6 +92,35 @@ __device__ void pf_trace_store(const pf::View& v, double* dst, long long p)
         for (int c = 0; c < 2; ++c) o[2 * i + c] = v.T(i, c);
 }
 
+// stable compaction of the particles still active into order[0 .. count): one CTA, chunks of its size with a running offset
+__global__ void __launch_bounds__(1024) pf_compact_kernel(const unsigned char* __restrict__ active, int nPar, int* __restrict__ order,
+                                                         int* __restrict__ count)
+{
+    __shared__ int sWarp[32];
+    __shared__ int sBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sBase = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < nPar; p0 += 1024) {
+        const int p = p0 + tid;
+        const int a = (p < nPar && active[p]) ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) sWarp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int v = sWarp[w];
+            if (w < warp) before += v;
+            total += v;
+        }
+        if (a) order[sBase + before + __popc(m & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+        if (tid == 0) sBase += total;
+        __syncthreads();
+    }
+    if (tid == 0) *count = sBase;
+}
+
 // The operators walk the particle's state element by element in one serial chain; in global memory (SoA, particle index
 // fastest) every access is a dependent L2 round trip.  pf_step_kernel therefore stages the state of its particle in shared
 // memory (one block of doubles per warp), runs the operators there and writes the persistent arrays back.
@@ -322,7 +351,7 @@ void pf_free(thb_ctx* ctx)
 {
     PFState& s = ctx->pf_;
     cudaFree(s.r); cudaFree(s.t); cudaFree(s.wR); cudaFree(s.wT); cudaFree(s.scal);
-    cudaFree(s.uR); cudaFree(s.uT); cudaFree(s.uC); cudaFree(s.base); cudaFree(s.active); cudaFree(s.nPhase);
+    cudaFree(s.uR); cudaFree(s.uT); cudaFree(s.uC); cudaFree(s.base); cudaFree(s.active); cudaFree(s.order); cudaFree(s.nPhase);
     cudaFree(s.vari); cudaFree(s.drawR); cudaFree(s.drawT); cudaFree(s.drawD);
     cudaFree(s.d); cudaFree(s.wD); cudaFree(s.uDd); cudaFree(s.uD); cudaFree(s.ctfK); cudaFree(s.ctfAttr);
     cudaFree(s.dbl); cudaFree(s.traceR); cudaFree(s.traceT); cudaFree(s.traceSt); cudaFree(s.traceB);
@@ -380,6 +409,7 @@ static int pf_alloc(thb_ctx* ctx, int nPar, const thb_pf_params& p)
     THB_CUDA(ctx, cudaMalloc(&s.uC, sizeof(float) * n));
     THB_CUDA(ctx, cudaMalloc(&s.base, sizeof(float) * n));
     THB_CUDA(ctx, cudaMalloc(&s.active, n));
+    THB_CUDA(ctx, cudaMalloc(&s.order, sizeof(int) * n));
     THB_CUDA(ctx, cudaMalloc(&s.nPhase, sizeof(int) * n));
     THB_CUDA(ctx, cudaMalloc(&s.vari, sizeof(double) * 4));
     THB_CUDA(ctx, cudaMemset(s.scal, 0, sizeof(double) * n * pf::S_COUNT));
@@ -501,18 +531,23 @@ int thb_pf_from_scan(thb_ctx* ctx, int nPar, const thb_pf_params* p, int nK, int
         pf_from_scan_kernel<<<(a.pN + 63) / 64, 64, 0, ctx->stream>>>(dev_view(ctx), a);
         ctx->launches++;
     }
-    // the chosen class is the image's reference from here on (projector slot of the E-step, accumulator of the M-step)
-    pf_set_slots_kernel<<<(nPar + 255) / 256, 256, 0, ctx->stream>>>(dcls, nPar, s.imgBase, ctx->stackE.slot,
-                                                                    (ctx->stackM.slot && s.imgBase + nPar <= ctx->stackM.nImg) ? ctx->stackM.slot : nullptr);
+    // the chosen class is the image's reference from here on (projector slot of the E-step, accumulator of the M-step).  With ONE
+    // class (k = 1: refinement, the slots are the two half sets) there is nothing to choose and the slots stay what they are.
+    if (nK > 1) {
+        pf_set_slots_kernel<<<(nPar + 255) / 256, 256, 0, ctx->stream>>>(dcls, nPar, s.imgBase, ctx->stackE.slot,
+                                                                        (ctx->stackM.slot && s.imgBase + nPar <= ctx->stackM.nImg) ? ctx->stackM.slot : nullptr);
+        ctx->launches++;
+    }
     span_end(ctx);
-    ctx->launches++;
     THB_CUDA(ctx, cudaGetLastError());
     std::vector<int> hc(nPar);
     THB_CUDA(ctx, cudaMemcpyAsync(hc.data(), dcls, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int q = 0; q < nPar; ++q) {
-        ctx->stackE.hslot[(size_t)s.imgBase + q] = hc[q];
-        if ((size_t)s.imgBase + q < ctx->stackM.hslot.size()) ctx->stackM.hslot[(size_t)s.imgBase + q] = hc[q];
+        if (nK > 1) {
+            ctx->stackE.hslot[(size_t)s.imgBase + q] = hc[q];
+            if ((size_t)s.imgBase + q < ctx->stackM.hslot.size()) ctx->stackM.hslot[(size_t)s.imgBase + q] = hc[q];
+        }
         if (clsOut) clsOut[q] = hc[q];
     }
     return THB_OK;
@@ -676,10 +711,16 @@ int thb_expectation(thb_ctx* ctx, int* nPhaseOut)
         ctx->launches++;
         THB_CUDA(ctx, cudaGetLastError());
         if (p.fixedPhases <= 0) {
+            // adaptive E-step (MIN / MAX_N_PHASE_PER_ITER and the variance rule, src/Optimiser.cpp:1490-1560): the next launch takes the
+            // compacted list of unfinished particles - a tail of a handful of particles then runs spread over the chip
+            // (expect_spread_kernel) instead of one image per SM
             int act = 0;
+            const bool compact = ctx->pfCompact && (ctx->expectImpl == 3 || ctx->expectImpl == 7);
+            if (compact) pf_compact_kernel<<<1, 1024, 0, ctx->stream>>>(s.active, s.nPar, s.order, d.activeCount);
             THB_CUDA(ctx, cudaMemcpyAsync(&act, d.activeCount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (act == 0) break;
+            if (compact && act < s.nPar) { ea.order = s.order; ea.nAct = act; }
         }
     }
     if (nPhaseOut) THB_CUDA(ctx, cudaMemcpyAsync(nPhaseOut, s.nPhase, sizeof(int) * s.nPar, cudaMemcpyDeviceToHost, ctx->stream));

@@ -750,6 +750,8 @@ int thb_remask_pack(thb_ctx* ctx, int base, int nImg, const float* imgOriFT, con
         THB_CUDA(ctx, cudaMemcpyAsync(st.slot + base, slotOfImg, (size_t)nImg * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     else
         THB_CUDA(ctx, cudaMemsetAsync(st.slot + base, 0, (size_t)nImg * sizeof(int), ctx->stream));
+    if (st.hslot.size() >= (size_t)base + nImg)          // host copy of the slots (slot validation, launch order of the lockstep E kernel)
+        for (int i = 0; i < nImg; ++i) st.hslot[(size_t)base + i] = slotOfImg ? slotOfImg[i] : 0;
     THB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return THB_OK;
 }
