@@ -574,10 +574,14 @@ def test_box256_expect_and_insert_against_oracle():
         quat = np.stack([synth.acg_cloud(par["quat"][l], 2e-5, nR, rng) for l in range(nImg)])
         tran = par["tran"][:, None, :] + rng.normal(scale=0.7, size=(nImg, nT, 2))
         wR = np.full((nImg, nR), 1.0 / nR); wT = np.full((nImg, nT), 1.0 / nT)
-        out = c.expect_local(quat, tran, wR, wT)
+        out = c.expect_local(quat, tran, wR, wT)             # two images: the kernel that spreads an image over the chip
+        c.set_option("expect_spread", 0)
+        out7 = c.expect_local(quat, tran, wR, wT)            # ... and the default kernel of large launches (two rotations per lane, lockstep)
+        c.set_option("expect_spread", -1)
         for l in range(nImg):
             o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], par["dat"][l], par["ctf"][l], par["sigRcp"][l], quat[l], tran[l], wR[l], wT[l])
             assert np.abs(out["logL"][l] - o["logL"]).max() <= _logL_tol(len(pixE["iCol"]), o["logL"])
+            assert np.abs(out7["logL"][l] - o["logL"]).max() <= _logL_tol(len(pixE["iCol"]), o["logL"])
         # slices at full size: project == oracle
         got = c.project(0, quat[0, :3])
         for i in range(3):
@@ -732,6 +736,13 @@ def test_box512_config4_offsets_beyond_4GB():
         out = c.expect_local(quat, tran, wR, wT)
         o = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], dat[0], ctf[0], sig[0], quat[0], tran[0], wR[0], wT[0])
         assert np.abs(out["logL"][0] - o["logL"]).max() <= _logL_tol(P, o["logL"])
+        # the default kernel of large launches (two rotations per lane; > 64 rotations, one CTA per image) on the 34 GB cell layout
+        quat7 = synth.random_quats(70, rng)[None]; wR7 = np.full((1, 70), 1.0 / 70)
+        c.set_option("expect_spread", 0)
+        out7 = c.expect_local(quat7, tran, wR7, wT)
+        c.set_option("expect_spread", -1)
+        o7 = port.expect_local(vol, pf, N, pixE["iCol"], pixE["iRow"], dat[0], ctf[0], sig[0], quat7[0], tran[0], wR7[0], wT[0])
+        assert np.abs(out7["logL"][0] - o7["logL"]).max() <= _logL_tol(P, o7["logL"])
         got = c.project(0, quat[0, :2])
         for i in range(2):
             want = port.project(vol, pf, port.rotate3D(quat[0, i]), pixE["iCol"], pixE["iRow"])
