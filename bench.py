@@ -75,8 +75,10 @@ def workload(args):
 
 def config_dict(args, wl, nPxlE, nPxlM, n_gpus):
     return {
-        "workload": f"{args.particles // 1000}k synthetic particles, box {wl['N']}, {args.mlr * args.phases} orientation samples "
-                    f"({args.mlr} rot x {args.phases} phases) x {args.mlt} translations, mReco {args.mreco}, "
+        "workload": f"{args.particles // 1000}k synthetic particles, box {wl['N']}, " +
+                    (f"{args.mlr * args.phases} orientation samples ({args.mlr} rot x {args.phases} phases)" if args.phases > 0 else
+                     f"{args.mlr} rotations per phase, ADAPTIVE phase count per particle (3 .. 100, the reference's 5 % variance rule)") +
+                    f" x {args.mlt} translations, mReco {args.mreco}, "
                     f"{n_gpus}xB200" + (" with NCCL half-map allreduce" if n_gpus > 1 else ""),
         "particles_resident_per_gpu": args.particles // n_gpus, "batch_per_gpu_per_step": args.batch,
         "box": wl["N"], "pf": wl["pf"], "r": wl["r"], "nPxl_E": nPxlE, "nPxl_M": nPxlM,

@@ -46,6 +46,8 @@
  *   thb_insert_counts         InsertFT with nC (3D classification)   gpu/interface/Interface.h:267-291, src/Optimiser.cpp:6862-6950
  *   thb_set_mode,             MODE_2D: ExpectGlobal2D, InsertI2D     gpu/interface/Interface.h:176-198, 239-265
  *   thb_insert_classes        (Projector / Reconstructor 2D twins)   src/Projector.cpp:337-354, src/Reconstructor.cpp:708-780
+ *   thb_expect_scan_classes   ExpectGlobal2D (all classes at once)   gpu/interface/Interface.h:176-198, CPU loop src/Optimiser.cpp:756-914
+ *   thb_pf_from_scan          the post-scan Particle logic           src/Optimiser.cpp:921-1075
  *   thb_symmetrize            Reconstructor::symmetrizeF/T/O         src/Reconstructor.cpp:2676-2716, include/Geometry/Transformation.h:105-194
  *   thb_norm_residual,        Optimiser::normCorrection              src/Optimiser.cpp:6201-6393
  *   thb_scale_images

@@ -520,6 +520,7 @@ int thb_create(thb_ctx** out, int device)
     if (const char* e = getenv("THB_EXPECT_IMPL")) ctx->expectImpl = std::max(1, std::min(7, atoi(e)));
     if (const char* e = getenv("THB_EXPECT_RPL")) ctx->expectRpl = atoi(e) >= 4 ? 4 : 2;
     if (const char* e = getenv("THB_PF_STAGE")) ctx->pfStage = atoi(e) != 0;
+    if (const char* e = getenv("THB_PF_COMPACT")) ctx->pfCompact = atoi(e) != 0;
     if (const char* e = getenv("THB_SCAN_TEMPLATES")) ctx->scanTemplates = atoi(e) != 0;
     if (const char* e = getenv("THB_EXPECT_ORDER")) ctx->expectOrder = atoi(e) == 1;
     if (const char* e = getenv("THB_EXPECT_LOCK")) ctx->expectLock = atoi(e) != 0;

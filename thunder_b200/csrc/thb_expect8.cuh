@@ -1,7 +1,7 @@
 // thb_expect8.cuh - global scan with SHARED TEMPLATES (src/Optimiser.cpp:756-914, logDataVSPrior_m_n_huabin :9931-9973).
 //
 // In the scan every image is compared with the SAME rotation set: the reference projects each rotation once
-// (Projector::project, :788-800) and evaluates all images against that slice.  The fused local-search kernel, used for the scan
+// (Projector::project, :770-786; translations and logDataVSPrior_m_n over all images, :789-830) and evaluates all images against that slice.  The fused local-search kernel, used for the scan
 // until now, re-gathers every shared rotation for every image; ncu showed the scan bound by instruction issue, 60 % of the
 // instructions being the coordinate / weight / gather arithmetic of those repeated projections.  Here:
 //
