@@ -3,6 +3,7 @@
 // (DESIGN.md section 4.1).  cp.async.bulk copies bypass that pipe.  This measures, for an L2-resident footprint, cells/s of
 //   mode 0: two LDG.256 per cell into registers (what the kernel does)
 //   mode 1: one 64-byte cp.async.bulk per cell and lane into shared memory (mbarrier per warp and stage), then 4 x LDS.128
+//   mode 2: four 128-bit texture fetches per cell from a linear texture; mode 3: LDG and texture on alternate cells
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/gpu/bin/tmabench tools/gpu/tmabench.cu ; run: ./tools/gpu/bin/tmabench
 #include <cstdio>
 #include <cstdint>
@@ -101,6 +102,38 @@ __global__ void __launch_bounds__(THREADS, 2) gather_tma(const Quad* __restrict_
     if (acc == 123.456f) out[gid] = acc;
 }
 
+// mode 2: the cell through the TEXTURE data pipe (4 x 128-bit fetches from a linear texture); mode 3: even steps LDG.256 x 2, odd steps
+// texture - do the two data pipes of the L1/TEX unit add up?
+__global__ void __launch_bounds__(THREADS, 2) gather_tex(cudaTextureObject_t tex, uint32_t nCells, int steps, float* out)
+{
+    const uint32_t gid = blockIdx.x * THREADS + threadIdx.x;
+    float acc = 0.f;
+#pragma unroll 2
+    for (int s = 0; s < steps; ++s) {
+        const uint32_t c = hash32(gid * 9781u + s * 6271u) % nCells;
+        const float4 a = tex1Dfetch<float4>(tex, (int)(4 * c)), b = tex1Dfetch<float4>(tex, (int)(4 * c + 1));
+        const float4 d = tex1Dfetch<float4>(tex, (int)(4 * c + 2)), e = tex1Dfetch<float4>(tex, (int)(4 * c + 3));
+        acc += (a.x + a.y + a.z + a.w) * 0.5f + b.x + b.y + b.z + b.w + d.x + d.y + d.z + d.w + e.x + e.y + e.z + e.w;
+    }
+    if (acc == 123.456f) out[gid] = acc;
+}
+
+__global__ void __launch_bounds__(THREADS, 2) gather_mix(const Quad* __restrict__ vol, cudaTextureObject_t tex, uint32_t nCells, int steps, float* out)
+{
+    const uint32_t gid = blockIdx.x * THREADS + threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < steps; s += 2) {
+        const uint32_t c0 = hash32(gid * 9781u + s * 6271u) % nCells, c1 = hash32(gid * 9781u + (s + 1) * 6271u) % nCells;
+        const Quad a = ldg_quad(vol + 2 * (size_t)c0), b = ldg_quad(vol + 2 * (size_t)c0 + 1);
+        const float4 t0 = tex1Dfetch<float4>(tex, (int)(4 * c1)), t1 = tex1Dfetch<float4>(tex, (int)(4 * c1 + 1));
+        const float4 t2 = tex1Dfetch<float4>(tex, (int)(4 * c1 + 2)), t3 = tex1Dfetch<float4>(tex, (int)(4 * c1 + 3));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += a.v[k] * 0.5f + b.v[k];
+        acc += t0.x + t0.y + t0.z + t0.w + t1.x + t1.y + t1.z + t1.w + t2.x + t2.y + t2.z + t2.w + t3.x + t3.y + t3.z + t3.w;
+    }
+    if (acc == 123.456f) out[gid] = acc;
+}
+
 int main()
 {
     int sms = 0;
@@ -115,15 +148,26 @@ int main()
     cudaFuncSetAttribute(gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * THREADS * 64);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = vol;
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+    rd.res.linear.sizeInBytes = maxBytes;
+    cudaTextureDesc td = {};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) { printf("texture object failed\n"); return 1; }
     printf("random 64-byte cells, %d CTAs x %d threads x %d steps\nfootprint_MB  mode  ms  Gcells/s  GB/s\n", grid, THREADS, steps);
     for (int mb : {16, 48, 96, 512}) {
         const uint32_t nCells = (uint32_t)(((size_t)mb << 20) / 64);
-        for (int mode = 0; mode < 2; ++mode) {
+        for (int mode = 0; mode < 4; ++mode) {
             float best = 1e30f;
             for (int rep = 0; rep < 4; ++rep) {
                 cudaEventRecord(e0);
                 if (mode == 0) gather_ldg<<<grid, THREADS>>>(vol, nCells, steps, out);
-                else gather_tma<<<grid, THREADS, STAGES * THREADS * 64>>>(vol, nCells, steps, out);
+                else if (mode == 1) gather_tma<<<grid, THREADS, STAGES * THREADS * 64>>>(vol, nCells, steps, out);
+                else if (mode == 2) gather_tex<<<grid, THREADS>>>(tex, nCells, steps, out);
+                else gather_mix<<<grid, THREADS>>>(vol, tex, nCells, steps, out);
                 cudaEventRecord(e1);
                 cudaEventSynchronize(e1);
                 float ms;
@@ -133,7 +177,7 @@ int main()
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
             const double cellsN = (double)grid * THREADS * steps;
-            printf("%6d  %s  %.3f  %.1f  %.0f\n", mb, mode ? "tma64" : "ldg256x2", best, cellsN / best / 1e6, cellsN * 64 / best / 1e6);
+            printf("%6d  %s  %.3f  %.1f  %.0f\n", mb, (const char*[]){"ldg256x2", "tma64", "tex128x4", "ldg+tex"}[mode], best, cellsN / best / 1e6, cellsN * 64 / best / 1e6);
         }
     }
     return 0;
