@@ -48,3 +48,28 @@ def test_defaults_are_the_baseline_workload():
     assert wl["r"] == 127 and wl["pf"] == 2
     cfg = bench.config_dict(a, wl, 25134, 25135, 1)
     assert cfg["workload"].startswith("100k synthetic particles, box 256, 2000 orientation samples")
+
+
+def test_reference_arm_of_a_global_search_iteration():
+    """--scan-nr: the reference arm runs the reference's own scan loop (ref_scan), its post-scan Particle logic and the phases on the
+    same flags as our arm (tiny shape; the defaults leave the global scan off)"""
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not present")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--box", "64", "--mlr", "16", "--phases", "2", "--mreco", "10",
+                          "--scan-nr", "120", "--nt", "12", "--rmax", "10", "--cpu-sample", "3", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-600:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference" and d["value"] > 0
+    assert "global_search" in d["config"] and "120 shared rotations x 12 translations" in d["config"]["global_search"]
+    assert d["config"]["r"] == 10
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    bench = importlib.import_module("bench")
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        a = bench.parse()
+    finally:
+        sys.argv = argv
+    assert a.scan_nr == 0 and a.rmax == 0 and "global_search" not in bench.config_dict(a, bench.workload(a), 25134, 25135, 1)

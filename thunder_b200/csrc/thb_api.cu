@@ -239,7 +239,10 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
             int occ = 0;
             THB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, E3_THREADS, sm7));
             grid = std::max(1, std::min(a.nAct, occ * ctx->smCount));
-            int* dOrder = (int*)scratch(ctx, 14, sizeof(int) * (size_t)a.nAct + 16);
+            // arrival counters: one per barrier of every wave
+            const int lockTiles = std::max(1, ctx->expectLockTiles);
+            const size_t nBar = (size_t)((a.nAct + grid - 1) / grid) * (((a.P + E3_TILE - 1) / E3_TILE + lockTiles - 1) / lockTiles);
+            int* dOrder = (int*)scratch(ctx, 14, sizeof(int) * ((size_t)a.nAct + 4 + nBar));
             if (!dOrder) return THB_E_CUDA;
             unsigned int* dCtr = reinterpret_cast<unsigned int*>(dOrder + a.nAct + ((4 - (a.nAct & 3)) & 3));
             if (!a.order && !a.imgIdx && a.slotOfImg && (size_t)(a.imgBase + a.nAct) <= ctx->stackE.hslot.size()) {
@@ -251,8 +254,8 @@ static int launch_expect_v3(thb_ctx* ctx, ExpectArgs a)
                 THB_CUDA(ctx, cudaMemcpyAsync(dOrder, ord.data(), sizeof(int) * (size_t)a.nAct, cudaMemcpyHostToDevice, ctx->stream));
                 a.order = dOrder;
             }
-            THB_CUDA(ctx, cudaMemsetAsync(dCtr, 0, sizeof(unsigned int), ctx->stream));
-            a.lockCtr = dCtr; a.lockTiles = ctx->expectLockTiles; a.lockWindow = ctx->expectLockWindow;
+            THB_CUDA(ctx, cudaMemsetAsync(dCtr, 0, sizeof(unsigned int) * nBar, ctx->stream));
+            a.lockCtr = dCtr; a.lockTiles = lockTiles; a.lockWindow = ctx->expectLockWindow;
         }
         kern<<<grid, E3_THREADS, sm7, ctx->stream>>>(a);
     } else if (ctx->expectImpl == 5) {

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(E3_THREADS, RPL >= 4 ? 1 : 2) expect_multi_ker
     float* sL = reinterpret_cast<float*>(smem_raw + (tileBytes > parkBytes ? tileBytes : parkBytes));
     const int LB = A.quadBrick;
     const int g = warp % G, ph = warp / G;
-    // lockstep: barrier j of wave w is complete when the counter reaches (w * gridDim.x * K) + (j + 1) * (CTAs of wave w)
+    // lockstep: barrier j of wave w has its own counter lockCtr[w * K + j]; it is complete when every CTA of wave w has arrived
     const int nTilesImg = (P + E3_TILE - 1) / E3_TILE;
     const int lockTiles = A.lockCtr ? max(1, A.lockTiles) : 0;
     const unsigned K = lockTiles ? (unsigned)((nTilesImg + lockTiles - 1) / lockTiles) : 0u;
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(E3_THREADS, RPL >= 4 ? 1 : 2) expect_multi_ker
     const int p = A.order ? A.order[it] : it;
     __syncthreads();       // the previous image's epilogue is done with the shared arrays
     if (A.active && !A.active[p]) {
-        if (A.lockCtr && tid == 0) atomicAdd(A.lockCtr, K);     // arrive at all barriers of this wave at once
+        if (A.lockCtr)                                           // arrive at all barriers of this wave at once
+            for (unsigned j = tid; j < K; j += E3_THREADS) atomicAdd(A.lockCtr + (unsigned)wave * K + j, 1u);
         continue;
     }
     const int img = A.imgIdx ? A.imgIdx[p] : p + A.imgBase;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(E3_THREADS, RPL >= 4 ? 1 : 2) expect_multi_ker
         __syncthreads();   // previous tile consumed (also orders the sRC / sRR writes)
         const bool lockHere = lockTiles && (tile0 / E3_TILE) % lockTiles == 0;
         const unsigned lockJ = lockHere ? (unsigned)((tile0 / E3_TILE) / lockTiles) : 0u;
-        if (lockHere && tid == 0) atomicAdd(A.lockCtr, 1u);     // this CTA is done with everything before barrier lockJ
+        if (lockHere && tid == 0) atomicAdd(A.lockCtr + (unsigned)wave * K + lockJ, 1u);     // done with everything before barrier lockJ
         {
             // pixel records: 2 threads per pixel, translations split between them
             const int k = tid >> 1, sub = tid & 1;
@@ -146,14 +147,14 @@ __global__ void __launch_bounds__(E3_THREADS, RPL >= 4 ? 1 : 2) expect_multi_ker
         if (lockHere && lockOn && tid == 0) {
             // wait (behind the record build) until every CTA has arrived at barrier lockJ - lockWindow; the spin is bounded:
             // lockstep is a matter of speed, not of correctness
-            // (global barrier index across waves; every wave but the last has gridDim.x participants)
+            // (one counter per barrier, indexed across waves: every wave but the last has gridDim.x participants)
             const int Jg = wave * (int)K + (int)lockJ - A.lockWindow;
             if (Jg >= 0) {
-                const int wv = Jg / (int)K, jj = Jg % (int)K;
+                const int wv = Jg / (int)K;
                 const unsigned nwv = (unsigned)min((int)gridDim.x, A.nAct - wv * (int)gridDim.x);
-                const unsigned target = (unsigned)wv * gridDim.x * K + (unsigned)(jj + 1) * nwv;
+                const volatile unsigned int* c = A.lockCtr + Jg;
                 int spins = 0;
-                while ((int)(*(volatile unsigned int*)A.lockCtr - target) < 0) {
+                while (*c < nwv) {
                     __nanosleep(200);
                     if (++spins > 2000000) { lockOn = false; break; }
                 }

@@ -85,7 +85,7 @@ struct ExpectArgs {
     // ---- lockstep launch (thb_expect7.cuh): a persistent grid walks the images wave by wave, all CTAs on the same pixel tiles at
     // the same time, so that the cells the chip reads at any moment are one thin spherical shell of the volume (pixels in radial order)
     const int* order;       // [nAct] launch position -> particle (images of one slot adjacent), or null
-    unsigned int* lockCtr;  // arrival counter of the tile barriers (zeroed before the launch), null = free-running
+    unsigned int* lockCtr;  // arrival counters of the tile barriers, one per (wave, barrier), zeroed before the launch; null = free-running
     int lockTiles;          // one barrier every lockTiles tiles
     int lockWindow;         // a CTA may run this many barriers ahead of the slowest one
     int scanSlot1;          // global scan: 1 + the ONE reference (slot) every image of the launch is compared with, rotations
