@@ -234,6 +234,26 @@ def test_expect_scan_all_classes_in_one_launch(ctx2d, nT):
                 assert np.allclose(got[c][big], want[c][big], rtol=rtol, atol=0.0), (key, c)
                 assert np.all(got[c][~big] <= 2e-4 * np.broadcast_to(t_, want[c].shape)[~big] + 1e-30), (key, c)
             print(f"scan_classes vs class-by-class, {key}: worst relative difference of the weights that matter {worst:.2e} (allowed {rtol:.2e})")
+    # ... and THE REFERENCE'S OWN scan loop over all classes (oracle/_ref: ref_scan restates src/Optimiser.cpp:756-914 around the MODE_2D
+    # Projector::project + translate + logDataVSPrior_m_n, one baseline per image across the classes): same output layouts
+    from oracle import refapi
+    if refapi.available():
+        projs = [refapi.Projector2D(s["pf"], s["refs"][c]) for c in range(k)]
+        want = refapi.scan(projs, True, s["datE"], s["ctfE"], s["sigE"], s["pixE"]["iCol"], s["pixE"]["iRow"], s["N"], cs, t, pR, pT, nThread=4)
+        for p_ in projs:
+            p_.close()
+        out = ctx2d.expect_scan_classes(k, cs, t, pR, pT)
+        assert np.abs(out["base"] - want["base"]).max() <= 2e-5 * np.abs(want["base"]).max() + 1e-4
+        rtol = 2 * (2e-5 * np.abs(want["base"]).max() + 1e-4) + 1e-3
+        for key in ("wR", "wT", "wC"):
+            w_, g_ = want[key].astype(np.float64), out[key].astype(np.float64)
+            if key == "wC":
+                top = w_.max(1, keepdims=True)                        # [nImg][nK]
+            else:
+                top = w_.max(axis=(0, 2), keepdims=True)              # [nK][nImg][n]: per image over classes and samples
+            big = w_ > 1e-4 * top
+            assert np.allclose(g_[big], w_[big], rtol=rtol, atol=0.0), key
+            assert np.all(g_[~big] <= 2e-4 * np.broadcast_to(top, w_.shape)[~big] + 1e-30), key
 
 
 @pytest.mark.gpu
